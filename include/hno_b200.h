@@ -1,0 +1,158 @@
+/* hno_b200 — C ABI of the B200 (sm_100a) spectral hot path for HNOSeg-XS.
+ *
+ * One shared object, libhno_b200.so, plain pointers and sizes, no torch types.  The reference
+ * (IBM/multimodal-3d-image-segmentation) has no FFI of its own: its boundary for this path is the
+ * Python module API of nets/ (SURVEY.md 8b).  Each entry point below names the reference code it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative value on error; the message is
+ *     available (per thread) from hno_last_error().  Nothing throws, nothing aborts.
+ *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*); no
+ *     implicit synchronisation, no allocation: the caller owns every buffer incl. workspaces.
+ *   - activations are fp32, channel-planar  [B][C][D][P]  where P >= H*W is the plane pitch in
+ *     floats (P == H*W for dense NCDHW tensors; the model pads P to a multiple of 32 so that
+ *     128-bit accesses are legal on odd grids such as 121x121x78).  Columns [H*W, P) are padding.
+ *   - "S" is the per-channel extent D*P.
+ */
+#ifndef HNO_B200_H_
+#define HNO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HNO_B200_VERSION 100
+
+int hno_version(void);
+const char* hno_last_error(void);
+/* 0 if the current CUDA device is compute capability 10.x (B200), error otherwise. */
+int hno_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Truncated 3-D discrete Hartley transform.
+ *   replaces nets/dht.py:16-66 (dhtn/dht3), nets/hnosegxs.py:332-410 (TransformCrop),
+ *            nets/hnosegxs.py:413-494 (PadInverse)
+ * A plan is a position-independent table blob built on the host (no GPU needed) for a grid
+ * (D,H,W) and, per axis, the list of retained frequency indices in OUTPUT order (for
+ * TransformCrop with m modes on an axis of length n: 0..m-1, n-m..n-1).  Upload the same bytes
+ * to the device and pass both copies to the transform calls.
+ * ------------------------------------------------------------------------------------------ */
+size_t hno_dht3_plan_bytes(int D, int H, int W, int Ld, int Lh, int Lw);
+int hno_dht3_plan_fill(void* host_buf, size_t bytes, int D, int H, int W, const int* kd, int Ld, const int* kh,
+                       int Lh, const int* kw, int Lw);
+size_t hno_dht3_workspace_bytes(const void* plan_host, long plane_pitch, int nslab);
+
+/* z[slab][Ld][Lh][Lw] = scale * C * x[slab][D][P]     (TransformCrop forward with scale = 1/(D*H*W);
+ *                                                        PadInverse backward with scale = 1) */
+int hno_dht3_forward(const void* plan_host, const void* plan_dev, const float* x, long plane_pitch,
+                     long slab_stride, float* z, void* workspace, int nslab, float scale, void* stream);
+/* x[slab][D][P] (op)= scale * C^T * z                 (PadInverse forward with scale = 1;
+ *                                                        TransformCrop backward with scale = 1/(D*H*W))
+ * epilogue: 0 store, 1 accumulate into x, 2 store selu(.) (nets/hnosegxs.py:267-268 fused) */
+int hno_dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, float* x, long plane_pitch,
+                     long slab_stride, void* workspace, int nslab, float scale, int epilogue, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pointwise (1x1x1) channel mixing  y = act( W * [in1 ; in2] + bias (+ in1 if residual) )
+ *   replaces nets/nets_utils.py:120-174 (ConvNormAct, kernel_size 1, SELU, no norm),
+ *            nets/hartley_operator.py:287-292 + nets/hnosegxs.py:307-329 (shared-weight mode mix
+ *            + residual + SELU: residual=1, bias=NULL), nets/hnosegxs.py:273-275 (concat conv:
+ *            in1 = activated inverse transform, in2 = block input) and :254-255 (mapping conv).
+ * Tensors are [B][C][S]; W is [CO][CI1+CI2] row-major (Conv3d weight flattened / HartleyOperator
+ * weight); act: 0 none, 1 SELU.  P/HW describe padding columns (s % P >= HW), which contribute
+ * nothing to weight gradients.  Supported channel counts: see hno_pwconv_supported().
+ * ------------------------------------------------------------------------------------------ */
+int hno_pwconv_supported(int ci1, int ci2, int co);
+int hno_pwconv_forward(const float* in1, const float* in2, const float* weight, const float* bias, float* out,
+                       int B, int ci1, int ci2, int co, long S, int act, int residual, void* stream);
+size_t hno_pwconv_backward_workspace_bytes(int ci1, int ci2, int co);
+/* dy, y: gradient and saved OUTPUT of the forward.  din1/din2 may be NULL (not needed).
+ * flags bit0: accumulate into din1, bit1: accumulate into din2,
+ *       bit2: in1 is itself a SELU output, return d/d(pre-activation of in1) in din1,
+ *       bit3: accumulate into dweight/dbias instead of overwriting.
+ * dweight [CO][CI1+CI2], dbias [CO] (NULL when the layer has no bias). */
+int hno_pwconv_backward(const float* dy, const float* y, const float* in1, const float* in2, const float* weight,
+                        float* din1, float* din2, float* dweight, float* dbias, void* workspace, int B, int ci1,
+                        int ci2, int co, long S, long P, long HW, int act, int residual, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-mode ("individual") Hartley mixing with even/odd recombination
+ *   replaces nets/hartley_operator.py:293-299,302-333 (hartley_conv + get_reverse on the cropped block)
+ *   out(k) = 1/2 [ W(k) (X(k)+X(-k)) + W(-k) (X(k)-X(-k)) ],  -k = (n-j) mod n per axis.
+ * x [B][CI][M], w [CO][CI][M], out [B][CO][M], M = n0*n1*n2.
+ * residual_selu != 0 fuses NeuralOperatorBlock (nets/hnosegxs.py:307-329): out = selu(mix(x) + x); the
+ * backward then takes the saved OUTPUT y (NULL for the plain op) and dout = gradient of that output.
+ * ------------------------------------------------------------------------------------------ */
+int hno_hartley_conv_forward(const float* x, const float* w, float* out, int B, int ci, int co, int n0, int n1,
+                             int n2, int residual_selu, void* stream);
+int hno_hartley_conv_backward(const float* dout, const float* y, const float* x, const float* w, float* dx,
+                              float* dw, int B, int ci, int co, int n0, int n1, int n2, int accumulate_dw,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stem: Conv3d(k=2, s=2, p=1) + bias + SELU      replaces nets/hnosegxs.py:102-105,150-151
+ *   x [B][CIN][Dx][Hx][Wx] dense  ->  out [B][F][D][P],  D = Dx/2+1, H = Hx/2+1, W = Wx/2+1
+ *   weight [F][CIN][2][2][2], bias [F].  Padding columns of out are written as 0.
+ * ------------------------------------------------------------------------------------------ */
+int hno_stem_supported(int cin, int f);
+int hno_stem_forward(const float* x, const float* weight, const float* bias, float* out, int B, int cin, int f,
+                     int Dx, int Hx, int Wx, long P, void* stream);
+size_t hno_stem_backward_workspace_bytes(int cin, int f);
+/* dpre: gradient w.r.t. the PRE-activation of the stem output, [B][F][D][P]. */
+int hno_stem_backward(const float* dpre, const float* x, float* dweight, float* dbias, void* workspace, int B,
+                      int cin, int f, int Dx, int Hx, int Wx, long P, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Head: trilinear up-sampling (F.interpolate, align_corners=False) of the low-resolution logits
+ * followed by softmax over channels           replaces nets/hnosegxs.py:174-180
+ * (the 1x1x1 conv_out commutes with the interpolation and is applied first, at low resolution,
+ * with hno_pwconv_forward).  `tables` is built by hno_interp_tables_fill and uploaded by the caller.
+ * ------------------------------------------------------------------------------------------ */
+size_t hno_interp_tables_bytes(int D, int H, int W, int Dx, int Hx, int Wx);
+int hno_interp_tables_fill(void* host_buf, size_t bytes, int D, int H, int W, int Dx, int Hx, int Wx);
+/* logits_low [B][C][D][P] -> probs [B][C][Dx][Hx][Wx] (dense).  C <= 8.  activation: 0 none, 1 softmax. */
+int hno_head_forward(const void* tables_host, const void* tables_dev, const float* logits_low, float* probs, int B,
+                     int C, long P, int activation, void* stream);
+size_t hno_head_backward_workspace_bytes(const void* tables_host, int B, int C);
+/* dprobs, probs [B][C][Dx][Hx][Wx] -> dlogits_low [B][C][D][P] (padding columns = 0). */
+int hno_head_backward(const void* tables_host, const void* tables_dev, const float* dprobs, const float* probs,
+                      float* dlogits_low, void* workspace, int B, int C, long P, int activation, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses on probabilities                     replaces nets/custom_losses.py:17-111
+ *   kind 0: DiceLoss, 1: PCCLoss.  y_pred, y_true [B][C][N] fp32 (y_true one-hot floats).
+ *   forward writes the scalar loss to loss[0] and per-(b,c) backward coefficients
+ *   (alpha, beta, gamma) to coef[B*C*3]:   dL/dy_pred = alpha + beta*y_true + gamma*y_pred.
+ * ------------------------------------------------------------------------------------------ */
+size_t hno_loss_workspace_bytes(int B, int C);
+int hno_loss_forward(const float* y_pred, const float* y_true, float* loss, float* coef, void* workspace, int B,
+                     int C, long N, int kind, void* stream);
+int hno_loss_backward(const float* y_pred, const float* y_true, const float* coef, const float* grad_loss,
+                      float* dy_pred, int B, int C, long N, void* stream);
+
+/* Fused head + loss on integer labels (the library's own training step; probabilities are never
+ * written): logits_low -> (interp, softmax) -> loss sums;  backward recomputes the probabilities.
+ *   replaces experiments/utils.py:74-97 (to_categorical) + nets/hnosegxs.py:174-180 +
+ *            nets/custom_losses.py + their autograd.  labels: uint8 [B][Dx][Hx][Wx]. */
+int hno_head_loss_forward(const void* tables_host, const void* tables_dev, const float* logits_low,
+                          const uint8_t* labels, float* loss, float* coef, void* workspace, int B, int C, long P,
+                          int kind, void* stream);
+int hno_head_loss_backward(const void* tables_host, const void* tables_dev, const float* logits_low,
+                           const uint8_t* labels, const float* coef, const float* grad_loss, float* dlogits_low,
+                           void* workspace, int B, int C, long P, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused Adamax step on a flat parameter vector (torch.optim.Adamax semantics, the optimizer of
+ * experiments/config_files/config_hnoseg_xs.ini:53-55).  step is 1-based.
+ * ------------------------------------------------------------------------------------------ */
+int hno_adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNO_B200_H_ */

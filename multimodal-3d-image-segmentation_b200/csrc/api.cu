@@ -1,0 +1,213 @@
+// extern "C" surface of libhno_b200.so (see include/hno_b200.h).  Thin: argument checks + dispatch.
+#include "common.cuh"
+#include "dht_plan.h"
+#include "hno_b200.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace hno {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+    cached = n;
+    return n;
+  }
+  (void)cudaGetLastError();
+  return 148;  // B200; only used for sizing when no device is visible (CPU-side unit tests)
+}
+
+// implemented in the kernel translation units
+int dht3_forward(const void*, const void*, const float*, long, long, float*, void*, int, float, cudaStream_t);
+int dht3_adjoint(const void*, const void*, const float*, float*, long, long, void*, int, float, int, cudaStream_t);
+size_t dht3_workspace_floats(const void*, long, int);
+int pwconv_supported(int, int, int, int, int);
+int pwconv_forward(const float*, const float*, const float*, const float*, float*, int, int, int, int, long, int, int,
+                   cudaStream_t);
+size_t pwconv_backward_workspace_bytes(int, int, int);
+int pwconv_backward(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
+                    float*, void*, int, int, int, int, long, long, long, int, int, int, cudaStream_t);
+int hartley_conv_forward(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int hartley_conv_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int,
+                          int, int, int, cudaStream_t);
+int stem_supported(int, int);
+int stem_forward(const float*, const float*, const float*, float*, int, int, int, int, int, int, long, cudaStream_t);
+size_t stem_backward_workspace_bytes(int, int);
+int stem_backward(const float*, const float*, float*, float*, void*, int, int, int, int, int, int, long, int,
+                  cudaStream_t);
+size_t interp_tables_bytes(int, int, int, int, int, int);
+int interp_tables_fill(void*, size_t, int, int, int, int, int, int);
+int head_forward(const void*, const void*, const float*, float*, int, int, long, int, cudaStream_t);
+size_t head_backward_workspace_bytes(const void*, int, int);
+int head_backward(const void*, const void*, const float*, const float*, float*, void*, int, int, long, int,
+                  cudaStream_t);
+size_t loss_workspace_bytes(int, int);
+int loss_forward(const float*, const float*, float*, float*, void*, int, int, long, int, cudaStream_t);
+int loss_backward(const float*, const float*, const float*, const float*, float*, int, int, long, cudaStream_t);
+int head_loss_forward(const void*, const void*, const float*, const uint8_t*, float*, float*, void*, int, int, long,
+                      int, cudaStream_t);
+int head_loss_backward(const void*, const void*, const float*, const uint8_t*, const float*, const float*, float*,
+                       void*, int, int, long, cudaStream_t);
+int adamax_step(float*, const float*, float*, float*, long, float, float, float, float, float, int, float,
+                cudaStream_t);
+
+}  // namespace hno
+
+using namespace hno;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int hno_version(void) { return HNO_B200_VERSION; }
+const char* hno_last_error(void) { return g_err; }
+
+int hno_device_check(void) {
+  int dev = 0;
+  HNO_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  HNO_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  HNO_CHECK(major == 10, "hno_b200 kernels are built for sm_100a only; device %d has compute capability %d.x", dev,
+            major);
+  return 0;
+}
+
+size_t hno_dht3_plan_bytes(int D, int H, int W, int Ld, int Lh, int Lw) {
+  const int n[3] = {D, H, W}, L[3] = {Ld, Lh, Lw};
+  return dht_plan_words(n, L) * 4;
+}
+
+int hno_dht3_plan_fill(void* host_buf, size_t bytes, int D, int H, int W, const int* kd, int Ld, const int* kh, int Lh,
+                       const int* kw, int Lw) {
+  HNO_CHECK(kd && kh && kw, "hno_dht3_plan_fill: null frequency list");
+  const int n[3] = {D, H, W}, L[3] = {Ld, Lh, Lw};
+  const int* const kl[3] = {kd, kh, kw};
+  return dht_plan_fill(host_buf, bytes, n, kl, L);
+}
+
+size_t hno_dht3_workspace_bytes(const void* plan_host, long plane_pitch, int nslab) {
+  if (!plan_host) return 0;
+  return dht3_workspace_floats(plan_host, plane_pitch, nslab) * sizeof(float) + 256;
+}
+
+int hno_dht3_forward(const void* plan_host, const void* plan_dev, const float* x, long plane_pitch, long slab_stride,
+                     float* z, void* workspace, int nslab, float scale, void* stream) {
+  return dht3_forward(plan_host, plan_dev, x, plane_pitch, slab_stride, z, workspace, nslab, scale, ST(stream));
+}
+
+int hno_dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, float* x, long plane_pitch,
+                     long slab_stride, void* workspace, int nslab, float scale, int epilogue, void* stream) {
+  return dht3_adjoint(plan_host, plan_dev, z, x, plane_pitch, slab_stride, workspace, nslab, scale, epilogue,
+                      ST(stream));
+}
+
+int hno_pwconv_supported(int ci1, int ci2, int co) { return pwconv_supported(ci1, ci2, co, -1, -1); }
+
+int hno_pwconv_forward(const float* in1, const float* in2, const float* weight, const float* bias, float* out, int B,
+                       int ci1, int ci2, int co, long S, int act, int residual, void* stream) {
+  return pwconv_forward(in1, in2, weight, bias, out, B, ci1, ci2, co, S, act, residual, ST(stream));
+}
+
+size_t hno_pwconv_backward_workspace_bytes(int ci1, int ci2, int co) {
+  return pwconv_backward_workspace_bytes(ci1, ci2, co);
+}
+
+int hno_pwconv_backward(const float* dy, const float* y, const float* in1, const float* in2, const float* weight,
+                        float* din1, float* din2, float* dweight, float* dbias, void* workspace, int B, int ci1,
+                        int ci2, int co, long S, long P, long HW, int act, int residual, int flags, void* stream) {
+  return pwconv_backward(dy, y, in1, in2, weight, din1, din2, dweight, dbias, workspace, B, ci1, ci2, co, S, P, HW,
+                         act, residual, flags, ST(stream));
+}
+
+int hno_hartley_conv_forward(const float* x, const float* w, float* out, int B, int ci, int co, int n0, int n1, int n2,
+                             int residual_selu, void* stream) {
+  return hartley_conv_forward(x, w, out, B, ci, co, n0, n1, n2, residual_selu, ST(stream));
+}
+
+int hno_hartley_conv_backward(const float* dout, const float* y, const float* x, const float* w, float* dx, float* dw,
+                              int B, int ci, int co, int n0, int n1, int n2, int accumulate_dw, void* stream) {
+  return hartley_conv_backward(dout, y, x, w, dx, dw, B, ci, co, n0, n1, n2, accumulate_dw, ST(stream));
+}
+
+int hno_stem_supported(int cin, int f) { return stem_supported(cin, f); }
+
+int hno_stem_forward(const float* x, const float* weight, const float* bias, float* out, int B, int cin, int f, int Dx,
+                     int Hx, int Wx, long P, void* stream) {
+  return stem_forward(x, weight, bias, out, B, cin, f, Dx, Hx, Wx, P, ST(stream));
+}
+
+size_t hno_stem_backward_workspace_bytes(int cin, int f) { return stem_backward_workspace_bytes(cin, f); }
+
+int hno_stem_backward(const float* dpre, const float* x, float* dweight, float* dbias, void* workspace, int B, int cin,
+                      int f, int Dx, int Hx, int Wx, long P, int accumulate, void* stream) {
+  return stem_backward(dpre, x, dweight, dbias, workspace, B, cin, f, Dx, Hx, Wx, P, accumulate, ST(stream));
+}
+
+size_t hno_interp_tables_bytes(int D, int H, int W, int Dx, int Hx, int Wx) {
+  return interp_tables_bytes(D, H, W, Dx, Hx, Wx);
+}
+
+int hno_interp_tables_fill(void* host_buf, size_t bytes, int D, int H, int W, int Dx, int Hx, int Wx) {
+  return interp_tables_fill(host_buf, bytes, D, H, W, Dx, Hx, Wx);
+}
+
+int hno_head_forward(const void* tables_host, const void* tables_dev, const float* logits_low, float* probs, int B,
+                     int C, long P, int activation, void* stream) {
+  return head_forward(tables_host, tables_dev, logits_low, probs, B, C, P, activation, ST(stream));
+}
+
+size_t hno_head_backward_workspace_bytes(const void* tables_host, int B, int C) {
+  return head_backward_workspace_bytes(tables_host, B, C);
+}
+
+int hno_head_backward(const void* tables_host, const void* tables_dev, const float* dprobs, const float* probs,
+                      float* dlogits_low, void* workspace, int B, int C, long P, int activation, void* stream) {
+  return head_backward(tables_host, tables_dev, dprobs, probs, dlogits_low, workspace, B, C, P, activation,
+                       ST(stream));
+}
+
+size_t hno_loss_workspace_bytes(int B, int C) { return loss_workspace_bytes(B, C); }
+
+int hno_loss_forward(const float* y_pred, const float* y_true, float* loss, float* coef, void* workspace, int B, int C,
+                     long N, int kind, void* stream) {
+  return loss_forward(y_pred, y_true, loss, coef, workspace, B, C, N, kind, ST(stream));
+}
+
+int hno_loss_backward(const float* y_pred, const float* y_true, const float* coef, const float* grad_loss,
+                      float* dy_pred, int B, int C, long N, void* stream) {
+  return loss_backward(y_pred, y_true, coef, grad_loss, dy_pred, B, C, N, ST(stream));
+}
+
+int hno_head_loss_forward(const void* tables_host, const void* tables_dev, const float* logits_low,
+                          const uint8_t* labels, float* loss, float* coef, void* workspace, int B, int C, long P,
+                          int kind, void* stream) {
+  return head_loss_forward(tables_host, tables_dev, logits_low, labels, loss, coef, workspace, B, C, P, kind,
+                           ST(stream));
+}
+
+int hno_head_loss_backward(const void* tables_host, const void* tables_dev, const float* logits_low,
+                           const uint8_t* labels, const float* coef, const float* grad_loss, float* dlogits_low,
+                           void* workspace, int B, int C, long P, void* stream) {
+  return head_loss_backward(tables_host, tables_dev, logits_low, labels, coef, grad_loss, dlogits_low, workspace, B, C,
+                            P, ST(stream));
+}
+
+int hno_adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  return adamax_step(param, grad, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                     ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// Shared helpers for the hno_b200 CUDA library (sm_100a only).
+//
+// Everything in csrc/ is compiled into ONE shared object, libhno_b200.so, whose
+// only public surface is the extern "C" API declared in include/hno_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace hno {
+
+// Thread-local error string returned by hno_last_error().
+void set_error(const char* fmt, ...);
+
+#define HNO_CHECK(cond, ...)                 \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::hno::set_error(__VA_ARGS__);         \
+      return -1;                             \
+    }                                        \
+  } while (0)
+
+#define HNO_CUDA(expr)                                                            \
+  do {                                                                            \
+    cudaError_t e_ = (expr);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      ::hno::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),    \
+                       __FILE__, __LINE__);                                       \
+      return -2;                                                                  \
+    }                                                                             \
+  } while (0)
+
+#define HNO_LAUNCH_CHECK() HNO_CUDA(cudaGetLastError())
+
+// SELU constants exactly as PyTorch defines them (aten/src/ATen/native/Activation.cpp);
+// the reference applies F.selu everywhere (nets/nets_utils.py:127-133, nets/hnosegxs.py:267-268,325-327).
+constexpr float kSeluAlpha = 1.6732632423543772848170429916717f;
+constexpr float kSeluScale = 1.0507009873554804934193349852946f;
+constexpr float kSeluNeg = kSeluAlpha * kSeluScale;
+
+__device__ __forceinline__ float selu_f(float x) {
+  return x > 0.f ? kSeluScale * x : kSeluNeg * expm1f(x);
+}
+// d selu / d x expressed from the OUTPUT y = selu(x): scale for y>0, y + scale*alpha otherwise.
+__device__ __forceinline__ float selu_grad_from_out(float y) {
+  return y > 0.f ? kSeluScale : y + kSeluNeg;
+}
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ static Vec ld(const float* p) {
+    Vec r;
+    r.v[0] = __ldg(p);
+    return r;
+  }
+  __device__ __forceinline__ void st(float* p) const { *p = v[0]; }
+};
+template <>
+struct Vec<2> {
+  float v[2];
+  __device__ __forceinline__ static Vec ld(const float* p) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    Vec r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    return r;
+  }
+  __device__ __forceinline__ void st(float* p) const {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  }
+};
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ static Vec ld(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    Vec r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    r.v[2] = t.z;
+    r.v[3] = t.w;
+    return r;
+  }
+  __device__ __forceinline__ void st(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// Largest vector width in {4,2,1} that divides every given stride / count and the pointer alignment.
+inline int pick_vec(const void* const* ptrs, int nptr, const long* counts, int ncount) {
+  int v = 4;
+  for (; v > 1; v >>= 1) {
+    bool ok = true;
+    for (int i = 0; i < nptr && ok; ++i)
+      if (ptrs[i] && (reinterpret_cast<uintptr_t>(ptrs[i]) % (sizeof(float) * v))) ok = false;
+    for (int i = 0; i < ncount && ok; ++i)
+      if (counts[i] % v) ok = false;
+    if (ok) break;
+  }
+  return v;
+}
+
+inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+// Number of SMs of the current device (cached); B200 = 148.
+int sm_count();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace hno

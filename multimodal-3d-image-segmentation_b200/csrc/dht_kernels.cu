@@ -1,0 +1,683 @@
+// Truncated 3-D discrete Hartley transform (forward projection C*x and adjoint C^T*z) for sm_100a.
+//
+// Replaces, for the retained corner modes only (see dht_plan.h for the math):
+//   nets/dht.py:16-36 (dhtn), nets/hnosegxs.py:378-410 (TransformCrop), :454-494 (PadInverse).
+// The reference computes a full complex FFT of every 24-channel volume and throws 98.6 % of it
+// away; here the retained rows are contracted directly:
+//   stage 1  analysis along D (strided axis, HBM-bound: reads the activation exactly once)
+//   stage 2  analysis along H (strided axis, input is 17 % of the activation, L2 resident)
+//   stage 3  analysis along W (contiguous axis)      + 8-term cas recombination
+// and the adjoint runs the exact transposes in the opposite order, so that the big, HBM-bound
+// kernel (synthesis along D) is the one that writes the activation exactly once.
+//
+// All arithmetic is fp32 FFMA with fp64-generated tables: stated precision choice = exact fp32
+// (no TF32 rounding), because 16 chained transforms at TF32 miss the 1e-3 / 99.99 % parity bar
+//  and the folded contraction is HBM-bound on CUDA cores anyway.
+#include "common.cuh"
+#include "dht_plan.h"
+#include "hno_b200.h"
+
+namespace hno {
+
+// ----------------------------------------------------------------------------------------------
+// analysis along a strided axis:  out[b][j][c] = sum_i f_j(i) * in[b][i][c]
+// thread = V adjacent columns c of one batch item b; accumulators for all rows live in registers.
+// even/odd folding: cos rows see e[i] = in[i] + in[n-i], sin rows see o[i] = in[i] - in[n-i].
+// ----------------------------------------------------------------------------------------------
+template <int JCB, int JSB, int V>
+__global__ void __launch_bounds__(256) k_analysis_outer(const float* __restrict__ in, float* __restrict__ out,
+                                                        const float* __restrict__ fcos,
+                                                        const float* __restrict__ fsin, int n, int JC, int JS,
+                                                        int JCp, int JSp, int ncg, long total, long in_rs,
+                                                        long in_bs, long out_rs, long out_bs) {
+  constexpr int CW = (JCB + 3) & ~3;
+  constexpr int SW = (JSB + 3) & ~3;
+  extern __shared__ float4 smem4[];
+  float* scos = reinterpret_cast<float*>(smem4);
+  const int nh = n >> 1;
+  float* ssin = scos + (nh + 1) * CW;
+  for (int idx = threadIdx.x; idx < (nh + 1) * CW; idx += blockDim.x) {
+    int i = idx / CW, j = idx - i * CW;
+    scos[idx] = j < JC ? fcos[i * JCp + j] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < (nh + 1) * SW; idx += blockDim.x) {
+    int i = idx / SW, j = idx - i * SW;
+    ssin[idx] = j < JS ? fsin[i * JSp + j] : 0.f;
+  }
+  __syncthreads();
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long b = t / ncg;
+  const int cg = (int)(t - b * ncg);
+  const float* ip = in + b * in_bs + (long)cg * V;
+
+  float accC[CW][V];
+  float accS[SW][V];
+  {
+    Vec<V> a = Vec<V>::ld(ip);
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+#pragma unroll
+      for (int v = 0; v < V; ++v) accC[j][v] = scos[j] * a.v[v];
+#pragma unroll
+    for (int j = 0; j < SW; ++j)
+#pragma unroll
+      for (int v = 0; v < V; ++v) accS[j][v] = 0.f;
+  }
+  const int npair = (n - 1) >> 1;
+#pragma unroll 2
+  for (int i = 1; i <= npair; ++i) {
+    Vec<V> a = Vec<V>::ld(ip + (long)i * in_rs);
+    Vec<V> c = Vec<V>::ld(ip + (long)(n - i) * in_rs);
+    float e[V], o[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      e[v] = a.v[v] + c.v[v];
+      o[v] = a.v[v] - c.v[v];
+    }
+    const float4* c4 = reinterpret_cast<const float4*>(scos + i * CW);
+#pragma unroll
+    for (int q = 0; q < CW / 4; ++q) {
+      float4 w = c4[q];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        accC[4 * q + 0][v] = fmaf(w.x, e[v], accC[4 * q + 0][v]);
+        accC[4 * q + 1][v] = fmaf(w.y, e[v], accC[4 * q + 1][v]);
+        accC[4 * q + 2][v] = fmaf(w.z, e[v], accC[4 * q + 2][v]);
+        accC[4 * q + 3][v] = fmaf(w.w, e[v], accC[4 * q + 3][v]);
+      }
+    }
+    const float4* s4 = reinterpret_cast<const float4*>(ssin + i * SW);
+#pragma unroll
+    for (int q = 0; q < SW / 4; ++q) {
+      float4 w = s4[q];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        accS[4 * q + 0][v] = fmaf(w.x, o[v], accS[4 * q + 0][v]);
+        accS[4 * q + 1][v] = fmaf(w.y, o[v], accS[4 * q + 1][v]);
+        accS[4 * q + 2][v] = fmaf(w.z, o[v], accS[4 * q + 2][v]);
+        accS[4 * q + 3][v] = fmaf(w.w, o[v], accS[4 * q + 3][v]);
+      }
+    }
+  }
+  if ((n & 1) == 0 && n > 1) {  // Nyquist sample pairs with itself, sine part vanishes
+    Vec<V> a = Vec<V>::ld(ip + (long)nh * in_rs);
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+#pragma unroll
+      for (int v = 0; v < V; ++v) accC[j][v] = fmaf(scos[nh * CW + j], a.v[v], accC[j][v]);
+  }
+  float* op = out + b * out_bs + (long)cg * V;
+#pragma unroll
+  for (int j = 0; j < CW; ++j)
+    if (j < JC) {
+      Vec<V> r;
+#pragma unroll
+      for (int v = 0; v < V; ++v) r.v[v] = accC[j][v];
+      r.st(op + (long)j * out_rs);
+    }
+#pragma unroll
+  for (int j = 0; j < SW; ++j)
+    if (j < JS) {
+      Vec<V> r;
+#pragma unroll
+      for (int v = 0; v < V; ++v) r.v[v] = accS[j][v];
+      r.st(op + (long)(JC + j) * out_rs);
+    }
+}
+
+// generic fallback (any J): one thread per (b, j, c), unfolded rows from the [J][n] table.
+__global__ void __launch_bounds__(256) k_analysis_outer_generic(const float* __restrict__ in,
+                                                                float* __restrict__ out,
+                                                                const float* __restrict__ full, int n, int J,
+                                                                int ncols, long total, long in_rs, long in_bs,
+                                                                long out_rs, long out_bs) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % ncols);
+  const long r = t / ncols;
+  const int j = (int)(r % J);
+  const long b = r / J;
+  const float* ip = in + b * in_bs + c;
+  const float* f = full + (long)j * n;
+  float acc = 0.f;
+  for (int i = 0; i < n; ++i) acc = fmaf(__ldg(f + i), __ldg(ip + (long)i * in_rs), acc);
+  out[b * out_bs + (long)j * out_rs + c] = acc;
+}
+
+// ----------------------------------------------------------------------------------------------
+// synthesis along a strided axis (exact transpose of the analysis):
+//   out[b][i][c] = EPI( scale * sum_j f_j(i) * in[b][j][c] ),  columns >= valid_cols are written as 0
+// EPI: 0 store, 1 out += value, 2 selu(value)
+// ----------------------------------------------------------------------------------------------
+template <int EPI, int V>
+__device__ __forceinline__ void synth_store(float* p, const float (&val)[V], int col0, int valid_cols) {
+  Vec<V> r;
+  if (EPI == 1) {
+    Vec<V> old = Vec<V>::ld(p);
+#pragma unroll
+    for (int v = 0; v < V; ++v) r.v[v] = (col0 + v < valid_cols) ? old.v[v] + val[v] : old.v[v];
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float x = EPI == 2 ? selu_f(val[v]) : val[v];
+      r.v[v] = (col0 + v < valid_cols) ? x : 0.f;
+    }
+  }
+  r.st(p);
+}
+
+template <int JCB, int JSB, int V, int EPI>
+__global__ void __launch_bounds__(256) k_synthesis_outer(const float* __restrict__ in, float* __restrict__ out,
+                                                         const float* __restrict__ fcos,
+                                                         const float* __restrict__ fsin, int n, int JC, int JS,
+                                                         int JCp, int JSp, int ncg, long total, long in_rs,
+                                                         long in_bs, long out_rs, long out_bs, int valid_cols,
+                                                         float scale) {
+  constexpr int CW = (JCB + 3) & ~3;
+  constexpr int SW = (JSB + 3) & ~3;
+  extern __shared__ float4 smem4[];
+  float* scos = reinterpret_cast<float*>(smem4);
+  const int nh = n >> 1;
+  float* ssin = scos + (nh + 1) * CW;
+  for (int idx = threadIdx.x; idx < (nh + 1) * CW; idx += blockDim.x) {
+    int i = idx / CW, j = idx - i * CW;
+    scos[idx] = j < JC ? scale * fcos[i * JCp + j] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < (nh + 1) * SW; idx += blockDim.x) {
+    int i = idx / SW, j = idx - i * SW;
+    ssin[idx] = j < JS ? scale * fsin[i * JSp + j] : 0.f;
+  }
+  __syncthreads();
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long b = t / ncg;
+  const int cg = (int)(t - b * ncg);
+  const int col0 = cg * V;
+  const float* ip = in + b * in_bs + (long)col0;
+
+  float C[CW][V];
+  float S[SW][V];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) {
+    if (j < JC) {
+      Vec<V> a = Vec<V>::ld(ip + (long)j * in_rs);
+#pragma unroll
+      for (int v = 0; v < V; ++v) C[j][v] = a.v[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) C[j][v] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SW; ++j) {
+    if (j < JS) {
+      Vec<V> a = Vec<V>::ld(ip + (long)(JC + j) * in_rs);
+#pragma unroll
+      for (int v = 0; v < V; ++v) S[j][v] = a.v[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) S[j][v] = 0.f;
+    }
+  }
+  float* op = out + b * out_bs + (long)col0;
+  {
+    float e[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) e[v] = 0.f;
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+#pragma unroll
+      for (int v = 0; v < V; ++v) e[v] = fmaf(scos[j], C[j][v], e[v]);
+    synth_store<EPI, V>(op, e, col0, valid_cols);
+  }
+  const int npair = (n - 1) >> 1;
+  for (int i = 1; i <= npair; ++i) {
+    float e[V], o[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) e[v] = o[v] = 0.f;
+    const float4* c4 = reinterpret_cast<const float4*>(scos + i * CW);
+#pragma unroll
+    for (int q = 0; q < CW / 4; ++q) {
+      float4 w = c4[q];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        e[v] = fmaf(w.x, C[4 * q + 0][v], e[v]);
+        e[v] = fmaf(w.y, C[4 * q + 1][v], e[v]);
+        e[v] = fmaf(w.z, C[4 * q + 2][v], e[v]);
+        e[v] = fmaf(w.w, C[4 * q + 3][v], e[v]);
+      }
+    }
+    const float4* s4 = reinterpret_cast<const float4*>(ssin + i * SW);
+#pragma unroll
+    for (int q = 0; q < SW / 4; ++q) {
+      float4 w = s4[q];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        o[v] = fmaf(w.x, S[4 * q + 0][v], o[v]);
+        o[v] = fmaf(w.y, S[4 * q + 1][v], o[v]);
+        o[v] = fmaf(w.z, S[4 * q + 2][v], o[v]);
+        o[v] = fmaf(w.w, S[4 * q + 3][v], o[v]);
+      }
+    }
+    float lo[V], hi[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      lo[v] = e[v] + o[v];
+      hi[v] = e[v] - o[v];
+    }
+    synth_store<EPI, V>(op + (long)i * out_rs, lo, col0, valid_cols);
+    synth_store<EPI, V>(op + (long)(n - i) * out_rs, hi, col0, valid_cols);
+  }
+  if ((n & 1) == 0 && n > 1) {
+    float e[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) e[v] = 0.f;
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+#pragma unroll
+      for (int v = 0; v < V; ++v) e[v] = fmaf(scos[nh * CW + j], C[j][v], e[v]);
+    synth_store<EPI, V>(op + (long)nh * out_rs, e, col0, valid_cols);
+  }
+}
+
+// generic fallback: one thread per (b, i, c)
+template <int EPI>
+__global__ void __launch_bounds__(256) k_synthesis_outer_generic(const float* __restrict__ in,
+                                                                 float* __restrict__ out,
+                                                                 const float* __restrict__ full, int n, int J,
+                                                                 int ncols, long total, long in_rs, long in_bs,
+                                                                 long out_rs, long out_bs, int valid_cols,
+                                                                 float scale) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % ncols);
+  const long r = t / ncols;
+  const int i = (int)(r % n);
+  const long b = r / n;
+  const float* ip = in + b * in_bs + c;
+  float acc = 0.f;
+  if (c < valid_cols)
+    for (int j = 0; j < J; ++j) acc = fmaf(__ldg(full + (long)j * n + i), __ldg(ip + (long)j * in_rs), acc);
+  float val[1] = {scale * acc};
+  synth_store<EPI, 1>(out + b * out_bs + (long)i * out_rs + c, val, c, valid_cols);
+}
+
+// ----------------------------------------------------------------------------------------------
+// contiguous (innermost) axis:  out[r][j] = sum_w f_j(w) in[r][w]     and its transpose
+// ----------------------------------------------------------------------------------------------
+constexpr int kInnerRows = 32;
+
+__global__ void __launch_bounds__(256) k_analysis_inner(const float* __restrict__ in, float* __restrict__ out,
+                                                        const float* __restrict__ full, int n, int J, long R,
+                                                        long in_rs, long out_rs) {
+  extern __shared__ float4 smem4[];
+  float* sb = reinterpret_cast<float*>(smem4);  // [J][n]
+  const int ns = n | 1;                         // odd row pitch -> conflict free column walks
+  float* tile = sb + J * n;                     // [32][ns]
+  const long row0 = (long)blockIdx.x * kInnerRows;
+  for (int idx = threadIdx.x; idx < J * n; idx += blockDim.x) sb[idx] = full[idx];
+  for (int idx = threadIdx.x; idx < kInnerRows * n; idx += blockDim.x) {
+    int r = idx / n, w = idx - r * n;
+    tile[r * ns + w] = (row0 + r < R) ? __ldg(in + (row0 + r) * in_rs + w) : 0.f;
+  }
+  __syncthreads();
+  const int r = threadIdx.x & 31;
+  const int jg = threadIdx.x >> 5;  // 0..7, warp uniform
+  if (row0 + r >= R) return;
+  const float* tr = tile + r * ns;
+  for (int j0 = jg; j0 < J; j0 += 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int jj[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) jj[q] = min(j0 + 8 * q, J - 1);
+    for (int w = 0; w < n; ++w) {
+      float x = tr[w];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(sb[jj[q] * n + w], x, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (j0 + 8 * q < J) out[(row0 + r) * out_rs + j0 + 8 * q] = acc[q];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_synthesis_inner(const float* __restrict__ in, float* __restrict__ out,
+                                                         const float* __restrict__ full, int n, int J, long R,
+                                                         long in_rs, long out_rs) {
+  extern __shared__ float4 smem4[];
+  float* sb = reinterpret_cast<float*>(smem4);  // [J][n]
+  float* tin = sb + J * n;                      // [32][J]
+  const long row0 = (long)blockIdx.x * kInnerRows;
+  for (int idx = threadIdx.x; idx < J * n; idx += blockDim.x) sb[idx] = full[idx];
+  for (int idx = threadIdx.x; idx < kInnerRows * J; idx += blockDim.x) {
+    int r = idx / J, j = idx - r * J;
+    tin[idx] = (row0 + r < R) ? __ldg(in + (row0 + r) * in_rs + j) : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kInnerRows * n; idx += blockDim.x) {
+    int r = idx / n, w = idx - r * n;
+    if (row0 + r >= R) break;
+    const float* tr = tin + r * J;
+    float acc = 0.f;
+    for (int j = 0; j < J; ++j) acc = fmaf(sb[j * n + w], tr[j], acc);
+    out[(row0 + r) * out_rs + w] = acc;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// 8-term cas recombination and its transpose
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_combine(const float* __restrict__ T, float* __restrict__ Z,
+                                                 const int* __restrict__ kd_desc, const int* __restrict__ kh_desc,
+                                                 const int* __restrict__ kw_desc, int Ld, int Lh, int Lw, int Jd,
+                                                 int Jh, int Jw, long total, float scale) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int kw = (int)(t % Lw);
+  long r = t / Lw;
+  const int kh = (int)(r % Lh);
+  r /= Lh;
+  const int kd = (int)(r % Ld);
+  const long slab = r / Ld;
+  const int cd = kd_desc[4 * kd], sd = kd_desc[4 * kd + 1];
+  const float gd = (float)kd_desc[4 * kd + 2];
+  const int ch = kh_desc[4 * kh], sh = kh_desc[4 * kh + 1];
+  const float gh = (float)kh_desc[4 * kh + 2];
+  const int cw = kw_desc[4 * kw], sw = kw_desc[4 * kw + 1];
+  const float gw = (float)kw_desc[4 * kw + 2];
+  const float* Ts = T + slab * (long)Jd * Jh * Jw;
+#define HNO_T(a, b, c) __ldg(Ts + ((long)(a) * Jh + (b)) * Jw + (c))
+  float v = HNO_T(cd, ch, cw);
+  if (sh >= 0 && sw >= 0) v -= gh * gw * HNO_T(cd, sh, sw);
+  if (sd >= 0 && sw >= 0) v -= gd * gw * HNO_T(sd, ch, sw);
+  if (sd >= 0 && sh >= 0) v -= gd * gh * HNO_T(sd, sh, cw);
+  if (sd >= 0) v += gd * HNO_T(sd, ch, cw);
+  if (sh >= 0) v += gh * HNO_T(cd, sh, cw);
+  if (sw >= 0) v += gw * HNO_T(cd, ch, sw);
+  if (sd >= 0 && sh >= 0 && sw >= 0) v -= gd * gh * gw * HNO_T(sd, sh, sw);
+#undef HNO_T
+  Z[t] = scale * v;
+}
+
+__global__ void __launch_bounds__(256) k_combine_t(const float* __restrict__ Z, float* __restrict__ T,
+                                                   const int* __restrict__ jd_desc, const int* __restrict__ jh_desc,
+                                                   const int* __restrict__ jw_desc, int Ld, int Lh, int Lw, int Jd,
+                                                   int Jh, int Jw, long total, float scale) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int jw = (int)(t % Jw);
+  long r = t / Jw;
+  const int jh = (int)(r % Jh);
+  r /= Jh;
+  const int jd = (int)(r % Jd);
+  const long slab = r / Jd;
+  const int isd = jd_desc[4 * jd + 2], ish = jh_desc[4 * jh + 2], isw = jw_desc[4 * jw + 2];
+  const float sign = (isd + ish + isw >= 2) ? -1.f : 1.f;
+  const float* Zs = Z + slab * (long)Ld * Lh * Lw;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int kd = jd_desc[4 * jd + a];
+    if (kd < 0) continue;
+    const float fd = (isd && a == 1) ? -1.f : 1.f;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int kh = jh_desc[4 * jh + b];
+      if (kh < 0) continue;
+      const float fh = (ish && b == 1) ? -fd : fd;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int kw = jw_desc[4 * jw + c];
+        if (kw < 0) continue;
+        const float fw = (isw && c == 1) ? -fh : fh;
+        acc = fmaf(fw, __ldg(Zs + ((long)kd * Lh + kh) * Lw + kw), acc);
+      }
+    }
+  }
+  T[t] = sign * scale * acc;
+}
+
+// ----------------------------------------------------------------------------------------------
+// host launchers
+// ----------------------------------------------------------------------------------------------
+struct OuterArgs {
+  const float* in;
+  float* out;
+  const float* fcos;
+  const float* fsin;
+  const float* full;
+  int n, JC, JS, JCp, JSp, J;
+  int ncols;
+  long nbatch;
+  long in_rs, in_bs, out_rs, out_bs;
+  int valid_cols;
+  float scale;
+  int epi;
+};
+
+template <int JCB, int JSB, int V>
+static int launch_analysis_t(const OuterArgs& a, cudaStream_t st) {
+  constexpr int CW = (JCB + 3) & ~3, SW = (JSB + 3) & ~3;
+  const int ncg = a.ncols / V;
+  const long total = a.nbatch * ncg;
+  const size_t smem = (size_t)(a.n / 2 + 1) * (CW + SW) * sizeof(float);
+  auto kern = k_analysis_outer<JCB, JSB, V>;
+  if (smem > 48 * 1024) HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ceil_div(total, 256), 256, smem, st>>>(a.in, a.out, a.fcos, a.fsin, a.n, a.JC, a.JS, a.JCp, a.JSp, ncg,
+                                                 total, a.in_rs, a.in_bs, a.out_rs, a.out_bs);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int JCB, int JSB, int V>
+static int launch_synthesis_t(const OuterArgs& a, cudaStream_t st) {
+  constexpr int CW = (JCB + 3) & ~3, SW = (JSB + 3) & ~3;
+  const int ncg = a.ncols / V;
+  const long total = a.nbatch * ncg;
+  const size_t smem = (size_t)(a.n / 2 + 1) * (CW + SW) * sizeof(float);
+#define HNO_SYN(EPI)                                                                                              \
+  {                                                                                                               \
+    auto kern = k_synthesis_outer<JCB, JSB, V, EPI>;                                                              \
+    if (smem > 48 * 1024)                                                                                         \
+      HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    kern<<<ceil_div(total, 256), 256, smem, st>>>(a.in, a.out, a.fcos, a.fsin, a.n, a.JC, a.JS, a.JCp, a.JSp,    \
+                                                   ncg, total, a.in_rs, a.in_bs, a.out_rs, a.out_bs,              \
+                                                   a.valid_cols, a.scale);                                        \
+  }
+  if (a.epi == 0) HNO_SYN(0) else if (a.epi == 1) HNO_SYN(1) else HNO_SYN(2)
+#undef HNO_SYN
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+static int pick_outer_vec(const OuterArgs& a) {
+  const void* ptrs[2] = {a.in, a.out};
+  const long cnt[5] = {a.ncols, a.in_rs, a.in_bs, a.out_rs, a.out_bs};
+  return pick_vec(ptrs, 2, cnt, 5);
+}
+
+// Buckets: exact fits for the BASELINE modes (10 -> 11/10 rows, 14 -> 15/14 rows) plus two padded
+// general buckets; anything larger takes the generic (slow, still exact) kernels.
+#define HNO_OUTER_DISPATCH(FN, a, st)                                      \
+  do {                                                                     \
+    const int v_ = pick_outer_vec(a);                                      \
+    const bool smem_ok_ = (size_t)(a.n / 2 + 1) * 32 * 4 <= 200 * 1024;    \
+    if (smem_ok_) {                                                        \
+      if (a.JC <= 4 && a.JS <= 4) {                                        \
+        if (v_ == 4) return FN<4, 4, 4>(a, st);                            \
+        if (v_ == 2) return FN<4, 4, 2>(a, st);                            \
+        return FN<4, 4, 1>(a, st);                                         \
+      }                                                                    \
+      if (a.JC <= 8 && a.JS <= 8) {                                        \
+        if (v_ == 4) return FN<8, 8, 4>(a, st);                            \
+        if (v_ == 2) return FN<8, 8, 2>(a, st);                            \
+        return FN<8, 8, 1>(a, st);                                         \
+      }                                                                    \
+      if (a.JC <= 11 && a.JS <= 10) {                                      \
+        if (v_ == 4) return FN<11, 10, 4>(a, st);                          \
+        if (v_ == 2) return FN<11, 10, 2>(a, st);                          \
+        return FN<11, 10, 1>(a, st);                                       \
+      }                                                                    \
+      if (a.JC <= 15 && a.JS <= 14) {                                      \
+        if (v_ == 4) return FN<15, 14, 2>(a, st); /* 116 accumulators: V=2 keeps it in registers */ \
+        if (v_ == 2) return FN<15, 14, 2>(a, st);                          \
+        return FN<15, 14, 1>(a, st);                                       \
+      }                                                                    \
+    }                                                                      \
+  } while (0)
+
+static int launch_analysis(const OuterArgs& a, cudaStream_t st) {
+  HNO_OUTER_DISPATCH(launch_analysis_t, a, st);
+  const long total = a.nbatch * a.J * a.ncols;
+  k_analysis_outer_generic<<<ceil_div(total, 256), 256, 0, st>>>(a.in, a.out, a.full, a.n, a.J, a.ncols, total,
+                                                                  a.in_rs, a.in_bs, a.out_rs, a.out_bs);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_synthesis(const OuterArgs& a, cudaStream_t st) {
+  HNO_OUTER_DISPATCH(launch_synthesis_t, a, st);
+  const long total = a.nbatch * a.n * a.ncols;
+  if (a.epi == 0)
+    k_synthesis_outer_generic<0><<<ceil_div(total, 256), 256, 0, st>>>(a.in, a.out, a.full, a.n, a.J, a.ncols, total,
+                                                                        a.in_rs, a.in_bs, a.out_rs, a.out_bs,
+                                                                        a.valid_cols, a.scale);
+  else if (a.epi == 1)
+    k_synthesis_outer_generic<1><<<ceil_div(total, 256), 256, 0, st>>>(a.in, a.out, a.full, a.n, a.J, a.ncols, total,
+                                                                        a.in_rs, a.in_bs, a.out_rs, a.out_bs,
+                                                                        a.valid_cols, a.scale);
+  else
+    k_synthesis_outer_generic<2><<<ceil_div(total, 256), 256, 0, st>>>(a.in, a.out, a.full, a.n, a.J, a.ncols, total,
+                                                                        a.in_rs, a.in_bs, a.out_rs, a.out_bs,
+                                                                        a.valid_cols, a.scale);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+static int check_plan(const void* plan_host, const DhtPlanHeader** hdr) {
+  HNO_CHECK(plan_host != nullptr, "dht3: null plan");
+  const auto* h = reinterpret_cast<const DhtPlanHeader*>(plan_host);
+  HNO_CHECK(h->magic == kDhtPlanMagic && h->version == kDhtPlanVersion, "dht3: bad plan blob");
+  *hdr = h;
+  return 0;
+}
+
+struct DhtGeom {
+  int D, H, W, Jd, Jh, Jw, Ld, Lh, Lw;
+  long P;  // plane pitch (floats) of the activation, >= H*W
+  long g1, g2, tt;  // workspace sizes in floats per slab
+};
+
+static DhtGeom geom(const DhtPlanHeader* h, long P) {
+  DhtGeom g;
+  g.D = h->ax[0].n; g.H = h->ax[1].n; g.W = h->ax[2].n;
+  g.Jd = h->ax[0].J; g.Jh = h->ax[1].J; g.Jw = h->ax[2].J;
+  g.Ld = h->ax[0].L; g.Lh = h->ax[1].L; g.Lw = h->ax[2].L;
+  g.P = P;
+  g.g1 = (long)g.Jd * P;
+  g.g2 = (long)g.Jd * g.Jh * g.W;
+  g.tt = (long)g.Jd * g.Jh * g.Jw;
+  return g;
+}
+
+static inline size_t inner_smem(int n, int J, bool analysis) {
+  return (size_t)(J * n + kInnerRows * (analysis ? (n | 1) : J)) * sizeof(float);
+}
+
+int dht3_forward(const void* plan_host, const void* plan_dev, const float* x, long plane_pitch, long slab_stride,
+                 float* z, void* ws, int nslab, float scale, cudaStream_t st) {
+  const DhtPlanHeader* h;
+  if (check_plan(plan_host, &h)) return -1;
+  HNO_CHECK(plan_dev && x && z && ws, "dht3_forward: null pointer");
+  const DhtGeom g = geom(h, plane_pitch);
+  HNO_CHECK(plane_pitch >= (long)g.H * g.W, "dht3_forward: plane pitch %ld < H*W", plane_pitch);
+  const float* pf = reinterpret_cast<const float*>(plan_dev);
+  const int* pi = reinterpret_cast<const int*>(plan_dev);
+  float* G1 = reinterpret_cast<float*>(ws);
+  float* G2 = G1 + nslab * g.g1;
+  float* T = G2 + nslab * g.g2;
+  {  // stage 1: D
+    const DhtAxis& ax = h->ax[0];
+    OuterArgs a{x, G1, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
+                ax.J, (int)plane_pitch, nslab, plane_pitch, slab_stride, plane_pitch, g.g1, (int)plane_pitch, 1.f, 0};
+    if (int rc = launch_analysis(a, st)) return rc;
+  }
+  {  // stage 2: H
+    const DhtAxis& ax = h->ax[1];
+    OuterArgs a{G1, G2, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
+                ax.J, g.W, (long)nslab * g.Jd, g.W, plane_pitch, g.W, (long)g.Jh * g.W, g.W, 1.f, 0};
+    if (int rc = launch_analysis(a, st)) return rc;
+  }
+  {  // stage 3: W
+    const DhtAxis& ax = h->ax[2];
+    const long R = (long)nslab * g.Jd * g.Jh;
+    const size_t smem = inner_smem(ax.n, ax.J, true);
+    HNO_CHECK(smem <= 200 * 1024, "dht3_forward: W axis tables (%zu B) exceed shared memory", smem);
+    if (smem > 48 * 1024)
+      HNO_CUDA(cudaFuncSetAttribute(k_analysis_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_analysis_inner<<<ceil_div(R, kInnerRows), 256, smem, st>>>(G2, T, pf + ax.off_full, ax.n, ax.J, R, g.W, g.Jw);
+    HNO_LAUNCH_CHECK();
+  }
+  {
+    const long total = (long)nslab * g.Ld * g.Lh * g.Lw;
+    k_combine<<<ceil_div(total, 256), 256, 0, st>>>(T, z, pi + h->ax[0].off_kdesc, pi + h->ax[1].off_kdesc,
+                                                     pi + h->ax[2].off_kdesc, g.Ld, g.Lh, g.Lw, g.Jd, g.Jh, g.Jw,
+                                                     total, scale);
+    HNO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, float* x, long plane_pitch,
+                 long slab_stride, void* ws, int nslab, float scale, int epilogue, cudaStream_t st) {
+  const DhtPlanHeader* h;
+  if (check_plan(plan_host, &h)) return -1;
+  HNO_CHECK(plan_dev && x && z && ws, "dht3_adjoint: null pointer");
+  HNO_CHECK(epilogue >= 0 && epilogue <= 2, "dht3_adjoint: epilogue must be 0 (store), 1 (accumulate) or 2 (selu)");
+  const DhtGeom g = geom(h, plane_pitch);
+  HNO_CHECK(plane_pitch >= (long)g.H * g.W, "dht3_adjoint: plane pitch %ld < H*W", plane_pitch);
+  const float* pf = reinterpret_cast<const float*>(plan_dev);
+  const int* pi = reinterpret_cast<const int*>(plan_dev);
+  float* G1 = reinterpret_cast<float*>(ws);
+  float* G2 = G1 + nslab * g.g1;
+  float* T = G2 + nslab * g.g2;
+  {
+    const long total = (long)nslab * g.tt;
+    k_combine_t<<<ceil_div(total, 256), 256, 0, st>>>(z, T, pi + h->ax[0].off_jdesc, pi + h->ax[1].off_jdesc,
+                                                       pi + h->ax[2].off_jdesc, g.Ld, g.Lh, g.Lw, g.Jd, g.Jh, g.Jw,
+                                                       total, scale);
+    HNO_LAUNCH_CHECK();
+  }
+  {  // W
+    const DhtAxis& ax = h->ax[2];
+    const long R = (long)nslab * g.Jd * g.Jh;
+    const size_t smem = inner_smem(ax.n, ax.J, false);
+    HNO_CHECK(smem <= 200 * 1024, "dht3_adjoint: W axis tables (%zu B) exceed shared memory", smem);
+    if (smem > 48 * 1024)
+      HNO_CUDA(cudaFuncSetAttribute(k_synthesis_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_synthesis_inner<<<ceil_div(R, kInnerRows), 256, smem, st>>>(T, G2, pf + ax.off_full, ax.n, ax.J, R, g.Jw, g.W);
+    HNO_LAUNCH_CHECK();
+  }
+  {  // H
+    const DhtAxis& ax = h->ax[1];
+    OuterArgs a{G2, G1, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
+                ax.J, g.W, (long)nslab * g.Jd, g.W, (long)g.Jh * g.W, g.W, plane_pitch, g.W, 1.f, 0};
+    if (int rc = launch_synthesis(a, st)) return rc;
+  }
+  {  // D: the HBM-bound stage, writes the activation once (optionally fused SELU / accumulate)
+    const DhtAxis& ax = h->ax[0];
+    OuterArgs a{G1, x, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
+                ax.J, (int)plane_pitch, nslab, plane_pitch, g.g1, plane_pitch, slab_stride, g.H * g.W, 1.f, epilogue};
+    if (int rc = launch_synthesis(a, st)) return rc;
+  }
+  return 0;
+}
+
+size_t dht3_workspace_floats(const void* plan_host, long plane_pitch, int nslab) {
+  const auto* h = reinterpret_cast<const DhtPlanHeader*>(plan_host);
+  const DhtGeom g = geom(h, plane_pitch);
+  return (size_t)nslab * (g.g1 + g.g2 + g.tt);
+}
+
+}  // namespace hno

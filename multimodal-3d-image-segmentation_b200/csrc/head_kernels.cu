@@ -1,0 +1,606 @@
+// Output head and losses of HNOSeg-XS for sm_100a.
+//
+// Replaces nets/hnosegxs.py:174-180 (trilinear F.interpolate -> 1x1x1 conv_out -> softmax) and
+// nets/custom_losses.py:17-111 (PCCLoss, DiceLoss), plus experiments/utils.py:74-97 (to_categorical)
+// in the fused variant.  conv_out has no bias and trilinear weights sum to one, so the conv commutes
+// with the interpolation exactly: it is applied at LOW resolution (hno_pwconv_forward, 24 -> classes)
+// and only `classes` channels are up-sampled; the 24-channel full-resolution tensor (857 MB/sample at
+// 240x240x155) never exists.
+//
+// Interpolation follows ATen's upsample_trilinear3d with align_corners=False and scales=None
+// (ratio = in/out in fp32, src = max(ratio*(dst+0.5)-0.5, 0), i0 = min(floor(src), in-1),
+// i1 = i0 + (i0 < in-1), lambda1 = clamp(src - i0, 0, 1)); the per-axis tables are built on the host.
+//
+// Backward of the interpolation is a deterministic gather in three separable passes (W, then H, then
+// D): for every low-resolution index the contiguous range of high-resolution indices that touch it is
+// tabulated, so no atomics are needed.
+#include "common.cuh"
+#include "hno_b200.h"
+
+#include <math.h>
+#include <string.h>
+
+namespace hno {
+
+constexpr int kInterpMagic = 0x484E4F49;  // 'HNOI'
+constexpr int kMaxClasses = 8;
+
+struct InterpHeader {
+  int magic;
+  int lo[3];      // D, H, W   (low resolution)
+  int hi[3];      // Dx, Hx, Wx
+  int off_i0[3];  // int [hi]
+  int off_i1[3];  // int [hi]
+  int off_l1[3];  // float [hi]  weight of i1 (weight of i0 is 1 - l1)
+  int off_s[3];   // int [lo]  first hi index touching lo
+  int off_e[3];   // int [lo]  one past the last
+  int total_words;
+  int pad[5];
+};
+
+size_t interp_tables_bytes(int D, int H, int W, int Dx, int Hx, int Wx) {
+  size_t words = sizeof(InterpHeader) / 4 + 3 * ((size_t)Dx + Hx + Wx) + 2 * ((size_t)D + H + W) + 64;
+  return words * 4;
+}
+
+int interp_tables_fill(void* buf, size_t bytes, int D, int H, int W, int Dx, int Hx, int Wx) {
+  HNO_CHECK(buf, "interp_tables_fill: null buffer");
+  HNO_CHECK(bytes >= interp_tables_bytes(D, H, W, Dx, Hx, Wx), "interp_tables_fill: buffer too small");
+  HNO_CHECK(D >= 1 && H >= 1 && W >= 1 && Dx >= 1 && Hx >= 1 && Wx >= 1, "interp_tables_fill: bad sizes");
+  memset(buf, 0, bytes);
+  auto* hdr = reinterpret_cast<InterpHeader*>(buf);
+  int* iw = reinterpret_cast<int*>(buf);
+  float* fw = reinterpret_cast<float*>(buf);
+  hdr->magic = kInterpMagic;
+  const int lo[3] = {D, H, W}, hi[3] = {Dx, Hx, Wx};
+  size_t cur = sizeof(InterpHeader) / 4;
+  for (int a = 0; a < 3; ++a) {
+    hdr->lo[a] = lo[a];
+    hdr->hi[a] = hi[a];
+    hdr->off_i0[a] = (int)cur; cur += hi[a];
+    hdr->off_i1[a] = (int)cur; cur += hi[a];
+    hdr->off_l1[a] = (int)cur; cur += hi[a];
+    hdr->off_s[a] = (int)cur; cur += lo[a];
+    hdr->off_e[a] = (int)cur; cur += lo[a];
+    int* i0 = iw + hdr->off_i0[a];
+    int* i1 = iw + hdr->off_i1[a];
+    float* l1 = fw + hdr->off_l1[a];
+    int* s = iw + hdr->off_s[a];
+    int* e = iw + hdr->off_e[a];
+    for (int t = 0; t < lo[a]; ++t) { s[t] = hi[a]; e[t] = 0; }
+    const float ratio = (float)lo[a] / (float)hi[a];
+    for (int o = 0; o < hi[a]; ++o) {
+      if (hi[a] == lo[a]) {
+        i0[o] = i1[o] = o;
+        l1[o] = 0.f;
+      } else {
+        // one fused multiply-add: bit-identical to ATen's CPU (AVX2/AVX512 builds) and CUDA kernels,
+        // verified against F.interpolate on ramps in tests/test_plan_cpu.py
+        float src = fmaf(ratio, (float)o + 0.5f, -0.5f);
+        if (src < 0.f) src = 0.f;
+        int f = (int)floorf(src);
+        if (f > lo[a] - 1) f = lo[a] - 1;
+        float lam = src - (float)f;
+        lam = lam < 0.f ? 0.f : (lam > 1.f ? 1.f : lam);
+        i0[o] = f;
+        i1[o] = f + (f < lo[a] - 1 ? 1 : 0);
+        l1[o] = lam;
+      }
+      for (int t : {i0[o], i1[o]}) {
+        if (o < s[t]) s[t] = o;
+        if (o + 1 > e[t]) e[t] = o + 1;
+      }
+    }
+    for (int t = 0; t < lo[a]; ++t)
+      if (e[t] < s[t]) s[t] = e[t] = 0;  // untouched low index (down-sampling case): empty range
+  }
+  hdr->total_words = (int)cur;
+  return 0;
+}
+
+struct InterpDev {
+  int lo[3], hi[3];
+  const int* i0[3];
+  const int* i1[3];
+  const float* l1[3];
+  const int* s[3];
+  const int* e[3];
+};
+
+static int make_dev(const void* th, const void* td, InterpDev* d) {
+  HNO_CHECK(th && td, "head: null interpolation tables");
+  const auto* h = reinterpret_cast<const InterpHeader*>(th);
+  HNO_CHECK(h->magic == kInterpMagic, "head: bad interpolation table blob");
+  const int* iw = reinterpret_cast<const int*>(td);
+  const float* fw = reinterpret_cast<const float*>(td);
+  for (int a = 0; a < 3; ++a) {
+    d->lo[a] = h->lo[a];
+    d->hi[a] = h->hi[a];
+    d->i0[a] = iw + h->off_i0[a];
+    d->i1[a] = iw + h->off_i1[a];
+    d->l1[a] = fw + h->off_l1[a];
+    d->s[a] = iw + h->off_s[a];
+    d->e[a] = iw + h->off_e[a];
+  }
+  return 0;
+}
+
+// logits at one high-resolution voxel, same nesting as ATen: W innermost, then H, then D.
+template <int C>
+__device__ __forceinline__ void interp_logits(const float* __restrict__ ll, long S, long P, int W, const InterpDev& t,
+                                              int zd, int zh, int zw, float (&out)[C]) {
+  const int d0 = t.i0[0][zd], d1 = t.i1[0][zd];
+  const int h0 = t.i0[1][zh], h1 = t.i1[1][zh];
+  const int w0 = t.i0[2][zw], w1 = t.i1[2][zw];
+  const float ld1 = t.l1[0][zd], lh1 = t.l1[1][zh], lw1 = t.l1[2][zw];
+  const float ld0 = 1.f - ld1, lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+  const long o00 = (long)d0 * P + (long)h0 * W, o01 = (long)d0 * P + (long)h1 * W;
+  const long o10 = (long)d1 * P + (long)h0 * W, o11 = (long)d1 * P + (long)h1 * W;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float* p = ll + (long)c * S;
+    const float a00 = lw0 * __ldg(p + o00 + w0) + lw1 * __ldg(p + o00 + w1);
+    const float a01 = lw0 * __ldg(p + o01 + w0) + lw1 * __ldg(p + o01 + w1);
+    const float a10 = lw0 * __ldg(p + o10 + w0) + lw1 * __ldg(p + o10 + w1);
+    const float a11 = lw0 * __ldg(p + o11 + w0) + lw1 * __ldg(p + o11 + w1);
+    out[c] = ld0 * (lh0 * a00 + lh1 * a01) + ld1 * (lh0 * a10 + lh1 * a11);
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void softmax_inplace(float (&v)[C]) {
+  float m = v[0];
+#pragma unroll
+  for (int c = 1; c < C; ++c) m = fmaxf(m, v[c]);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    v[c] = expf(v[c] - m);
+    s += v[c];
+  }
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c] *= inv;
+}
+
+// ------------------------------------------------------------------------------------------ head forward
+template <int C, int ACT>
+__global__ void __launch_bounds__(256) k_head_fwd(const float* __restrict__ ll, float* __restrict__ probs,
+                                                  InterpDev t, long P) {
+  const long Nx = (long)t.hi[0] * t.hi[1] * t.hi[2];
+  const long v = blockIdx.x * 256L + threadIdx.x;
+  if (v >= Nx) return;
+  const int b = blockIdx.y;
+  const int zw = (int)(v % t.hi[2]);
+  const long r = v / t.hi[2];
+  const int zh = (int)(r % t.hi[1]);
+  const int zd = (int)(r / t.hi[1]);
+  const long S = (long)t.lo[0] * P;
+  float lg[C];
+  interp_logits<C>(ll + (long)b * C * S, S, P, t.lo[2], t, zd, zh, zw, lg);
+  if (ACT == 1) softmax_inplace<C>(lg);
+  float* po = probs + (long)b * C * Nx + v;
+#pragma unroll
+  for (int c = 0; c < C; ++c) po[(long)c * Nx] = lg[c];
+}
+
+// ------------------------------------------------------------------------------------------ head backward
+// MODE 0: dprobs / probs tensors are given (drop-in autograd path).
+// MODE 1: probabilities are recomputed from the low-resolution logits and dL/dprobs comes from the
+//         loss coefficients and the integer labels (fused training step).
+template <int C, int ACT, int MODE>
+__global__ void __launch_bounds__(256) k_head_bwd_w(const float* __restrict__ dprobs, const float* __restrict__ probs,
+                                                    const float* __restrict__ ll, const uint8_t* __restrict__ labels,
+                                                    const float* __restrict__ coef,
+                                                    const float* __restrict__ grad_loss, float* __restrict__ g1,
+                                                    InterpDev t, long P) {
+  // thread per (zd, zh, w_lo); output g1[b][c][zd][zh][w_lo]
+  const int W = t.lo[2];
+  const long rows = (long)t.hi[0] * t.hi[1];
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= rows * W) return;
+  const int b = blockIdx.y;
+  const int wl = (int)(idx % W);
+  const long row = idx / W;
+  const int zh = (int)(row % t.hi[1]);
+  const int zd = (int)(row / t.hi[1]);
+  const long Nx = rows * t.hi[2];
+  const long S = (long)t.lo[0] * P;
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  float ca[C], cb[C], cg[C];
+  if (MODE == 1) {
+    const float gl = grad_loss ? __ldg(grad_loss) : 1.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      ca[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 0);
+      cb[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 1);
+      cg[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 2);
+    }
+  }
+  const int ws = t.s[2][wl], we = t.e[2][wl];
+  for (int zw = ws; zw < we; ++zw) {
+    const float l1 = t.l1[2][zw];
+    const float wgt = (t.i0[2][zw] == wl ? 1.f - l1 : 0.f) + (t.i1[2][zw] == wl ? l1 : 0.f);
+    if (wgt == 0.f) continue;
+    const long v = row * t.hi[2] + zw;
+    float p[C], g[C];
+    if (MODE == 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        g[c] = __ldg(dprobs + ((long)b * C + c) * Nx + v);
+        if (ACT == 1) p[c] = __ldg(probs + ((long)b * C + c) * Nx + v);
+      }
+    } else {
+      interp_logits<C>(ll + (long)b * C * S, S, P, W, t, zd, zh, zw, p);
+      if (ACT == 1) softmax_inplace<C>(p);
+      const int lab = labels[(long)b * Nx + v];
+#pragma unroll
+      for (int c = 0; c < C; ++c) g[c] = ca[c] + (lab == c ? cb[c] : 0.f) + cg[c] * p[c];
+    }
+    if (ACT == 1) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) dot = fmaf(g[c], p[c], dot);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, p[c] * (g[c] - dot), acc[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, g[c], acc[c]);
+    }
+  }
+  const long plane = rows * W;
+#pragma unroll
+  for (int c = 0; c < C; ++c) g1[((long)b * C + c) * plane + idx] = acc[c];
+}
+
+// g1[bc][zd][zh][w] -> g2[bc][zd][h][w]
+__global__ void __launch_bounds__(256) k_head_bwd_h(const float* __restrict__ g1, float* __restrict__ g2, InterpDev t,
+                                                    long nbc) {
+  const int W = t.lo[2], H = t.lo[1], Hx = t.hi[1], Dx = t.hi[0];
+  const long total = nbc * Dx * H * W;
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= total) return;
+  const int w = (int)(idx % W);
+  long r = idx / W;
+  const int h = (int)(r % H);
+  r /= H;  // r = bc*Dx + zd
+  const float* src = g1 + r * (long)Hx * W + w;
+  float acc = 0.f;
+  for (int zh = t.s[1][h]; zh < t.e[1][h]; ++zh) {
+    const float l1 = t.l1[1][zh];
+    const float wgt = (t.i0[1][zh] == h ? 1.f - l1 : 0.f) + (t.i1[1][zh] == h ? l1 : 0.f);
+    acc = fmaf(wgt, __ldg(src + (long)zh * W), acc);
+  }
+  g2[idx] = acc;
+}
+
+// g2[bc][zd][h][w] -> dll[bc][d][P]  (padding columns zeroed)
+__global__ void __launch_bounds__(256) k_head_bwd_d(const float* __restrict__ g2, float* __restrict__ dll, InterpDev t,
+                                                    long nbc, long P) {
+  const int W = t.lo[2], H = t.lo[1], D = t.lo[0], Dx = t.hi[0];
+  const long total = nbc * D * P;
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx >= total) return;
+  const int p = (int)(idx % P);
+  long r = idx / P;
+  const int d = (int)(r % D);
+  const long bc = r / D;
+  if (p >= H * W) {
+    dll[idx] = 0.f;
+    return;
+  }
+  const float* src = g2 + bc * (long)Dx * H * W + p;
+  float acc = 0.f;
+  for (int zd = t.s[0][d]; zd < t.e[0][d]; ++zd) {
+    const float l1 = t.l1[0][zd];
+    const float wgt = (t.i0[0][zd] == d ? 1.f - l1 : 0.f) + (t.i1[0][zd] == d ? l1 : 0.f);
+    acc = fmaf(wgt, __ldg(src + (long)zd * H * W), acc);
+  }
+  dll[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ losses
+// Five moments per (b, c): sum p, sum t, sum p*t, sum p*p, sum t*t.  Block partials in fp64.
+constexpr int kMoments = 5;
+constexpr int kLossChunks = 296;  // partial rows per (b, c) / per b
+
+__device__ __forceinline__ void block_reduce_store(double (&m)[kMoments], double* dst) {
+  __shared__ double sred[8][kMoments];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kMoments; ++k) m[k] = warp_sum_d(m[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kMoments; ++k) sred[warp][k] = m[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kMoments) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sred[w][threadIdx.x];
+    dst[threadIdx.x] = s;
+  }
+}
+
+// grid (kLossChunks, B*C); y_pred / y_true [B*C][N]
+__global__ void __launch_bounds__(256) k_loss_moments(const float* __restrict__ yp, const float* __restrict__ yt,
+                                                      double* __restrict__ partials, long N) {
+  const long bc = blockIdx.y;
+  const float* p = yp + bc * N;
+  const float* t = yt + bc * N;
+  float m[kMoments] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  double md[kMoments] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  int cnt = 0;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < N; i += (long)gridDim.x * 256L) {
+    const float a = __ldg(p + i), b = __ldg(t + i);
+    m[0] += a;
+    m[1] += b;
+    m[2] = fmaf(a, b, m[2]);
+    m[3] = fmaf(a, a, m[3]);
+    m[4] = fmaf(b, b, m[4]);
+    if (++cnt == 64) {  // bounded fp32 run length, then spill into fp64
+#pragma unroll
+      for (int k = 0; k < kMoments; ++k) {
+        md[k] += (double)m[k];
+        m[k] = 0.f;
+      }
+      cnt = 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMoments; ++k) md[k] += (double)m[k];
+  block_reduce_store(md, partials + (bc * gridDim.x + blockIdx.x) * kMoments);
+}
+
+// fused head + moments on integer labels: grid (kLossChunks, B); partials [B][C][chunks][5]
+template <int C, int ACT>
+__global__ void __launch_bounds__(256) k_head_loss_moments(const float* __restrict__ ll,
+                                                           const uint8_t* __restrict__ labels,
+                                                           double* __restrict__ partials, InterpDev t, long P) {
+  const long Nx = (long)t.hi[0] * t.hi[1] * t.hi[2];
+  const int b = blockIdx.y;
+  const long S = (long)t.lo[0] * P;
+  float m[C][4];
+  double md[C][4];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      m[c][k] = 0.f;
+      md[c][k] = 0.0;
+    }
+  int cnt = 0;
+  for (long v = blockIdx.x * 256L + threadIdx.x; v < Nx; v += (long)gridDim.x * 256L) {
+    const int zw = (int)(v % t.hi[2]);
+    const long r = v / t.hi[2];
+    const int zh = (int)(r % t.hi[1]);
+    const int zd = (int)(r / t.hi[1]);
+    float p[C];
+    interp_logits<C>(ll + (long)b * C * S, S, P, t.lo[2], t, zd, zh, zw, p);
+    if (ACT == 1) softmax_inplace<C>(p);
+    const int lab = labels[(long)b * Nx + v];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float tt = lab == c ? 1.f : 0.f;
+      m[c][0] += p[c];
+      m[c][1] += tt;
+      m[c][2] = fmaf(p[c], tt, m[c][2]);
+      m[c][3] = fmaf(p[c], p[c], m[c][3]);
+    }
+    if (++cnt == 64) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          md[c][k] += (double)m[c][k];
+          m[c][k] = 0.f;
+        }
+      cnt = 0;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    double mm[kMoments];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mm[k] = md[c][k] + (double)m[c][k];
+    mm[4] = mm[1];  // t*t == t for one-hot labels
+    block_reduce_store(mm, partials + (((long)b * C + c) * gridDim.x + blockIdx.x) * kMoments);
+  }
+}
+
+// one block: reduce chunk partials, evaluate the loss and the backward coefficients
+__global__ void __launch_bounds__(256) k_loss_finalize(const double* __restrict__ partials, int nchunks, int BC,
+                                                       double N, int kind, float* __restrict__ loss,
+                                                       float* __restrict__ coef) {
+  __shared__ double sterm[256];
+  double term = 0.0;
+  for (int bc = threadIdx.x; bc < BC; bc += blockDim.x) {
+    double m[kMoments] = {0, 0, 0, 0, 0};
+    for (int ch = 0; ch < nchunks; ++ch)
+#pragma unroll
+      for (int k = 0; k < kMoments; ++k) m[k] += partials[((long)bc * nchunks + ch) * kMoments + k];
+    const double sp = m[0], st = m[1], spt = m[2], spp = m[3], stt = m[4];
+    double a, b, g;
+    if (kind == 0) {  // nets/custom_losses.py:73-111: dice = 2 I / (sum(t + p) + 1e-7); loss = mean(1 - dice)
+      const double U = st + sp + 1e-7;
+      const double dice = 2.0 * spt / U;
+      term += 1.0 - dice;
+      a = 2.0 * spt / (U * U) / BC;
+      b = -2.0 / U / BC;
+      g = 0.0;
+    } else {  // nets/custom_losses.py:17-70: r = tp / sqrt(tt*pp + 1e-7) on centred data; loss = mean(1 - (r+1)/2)
+      const double mt = st / N, mp = sp / N;
+      const double tp = spt - N * mt * mp;
+      const double tt = stt - N * mt * mt;
+      const double pp = spp - N * mp * mp;
+      const double q2 = tt * pp + 1e-7;
+      const double q = sqrt(q2);
+      const double r = tp / q;
+      term += 1.0 - (r + 1.0) * 0.5;
+      const double k = -0.5 / BC;
+      const double w = tp * tt / (q2 * q);
+      a = k * (-mt / q + w * mp);
+      b = k / q;
+      g = -k * w;
+    }
+    coef[bc * 3 + 0] = (float)a;
+    coef[bc * 3 + 1] = (float)b;
+    coef[bc * 3 + 2] = (float)g;
+  }
+  sterm[threadIdx.x] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)blockDim.x; ++i) s += sterm[i];
+    loss[0] = (float)(s / BC);
+  }
+}
+
+// dy_pred = grad_loss * (alpha + beta * y_true + gamma * y_pred)
+__global__ void __launch_bounds__(256) k_loss_bwd(const float* __restrict__ yp, const float* __restrict__ yt,
+                                                  const float* __restrict__ coef, const float* __restrict__ grad_loss,
+                                                  float* __restrict__ dyp, long N) {
+  const long bc = blockIdx.y;
+  const float gl = grad_loss ? __ldg(grad_loss) : 1.f;
+  const float a = gl * coef[bc * 3 + 0], b = gl * coef[bc * 3 + 1], g = gl * coef[bc * 3 + 2];
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < N; i += (long)gridDim.x * 256L)
+    dyp[bc * N + i] = a + b * __ldg(yt + bc * N + i) + g * __ldg(yp + bc * N + i);
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+#define HNO_CLASS_SWITCH(C, ...) \
+  switch (C) {                    \
+    case 1: { constexpr int kC = 1; __VA_ARGS__ } break; \
+    case 2: { constexpr int kC = 2; __VA_ARGS__ } break; \
+    case 3: { constexpr int kC = 3; __VA_ARGS__ } break; \
+    case 4: { constexpr int kC = 4; __VA_ARGS__ } break; \
+    case 5: { constexpr int kC = 5; __VA_ARGS__ } break; \
+    case 6: { constexpr int kC = 6; __VA_ARGS__ } break; \
+    case 7: { constexpr int kC = 7; __VA_ARGS__ } break; \
+    case 8: { constexpr int kC = 8; __VA_ARGS__ } break; \
+    default: set_error("head: number of classes %d not in [1, %d]", C, kMaxClasses); return -1; \
+  }
+
+int head_forward(const void* th, const void* td, const float* ll, float* probs, int B, int C, long P, int activation,
+                 cudaStream_t st) {
+  InterpDev t;
+  if (make_dev(th, td, &t)) return -1;
+  HNO_CHECK(ll && probs, "head_forward: null pointer");
+  HNO_CHECK(P >= (long)t.lo[1] * t.lo[2], "head_forward: plane pitch too small");
+  const long Nx = (long)t.hi[0] * t.hi[1] * t.hi[2];
+  dim3 grid(ceil_div(Nx, 256), B);
+  HNO_CLASS_SWITCH(C, {
+    if (activation == 1) k_head_fwd<kC, 1><<<grid, 256, 0, st>>>(ll, probs, t, P);
+    else k_head_fwd<kC, 0><<<grid, 256, 0, st>>>(ll, probs, t, P);
+  })
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t head_backward_workspace_bytes(const void* th, int B, int C) {
+  if (!th) return 0;
+  const auto* h = reinterpret_cast<const InterpHeader*>(th);
+  const size_t g1 = (size_t)B * C * h->hi[0] * h->hi[1] * h->lo[2];
+  const size_t g2 = (size_t)B * C * h->hi[0] * h->lo[1] * h->lo[2];
+  const size_t mom = (size_t)B * C * kLossChunks * kMoments * sizeof(double);
+  return (g1 + g2) * sizeof(float) + mom + 512;
+}
+
+static int head_backward_passes(const InterpDev& t, float* g1, float* g2, float* dll, int B, int C, long P,
+                                cudaStream_t st) {
+  const long nbc = (long)B * C;
+  {
+    const long total = nbc * t.hi[0] * t.lo[1] * t.lo[2];
+    k_head_bwd_h<<<ceil_div(total, 256), 256, 0, st>>>(g1, g2, t, nbc);
+    HNO_LAUNCH_CHECK();
+  }
+  {
+    const long total = nbc * t.lo[0] * P;
+    k_head_bwd_d<<<ceil_div(total, 256), 256, 0, st>>>(g2, dll, t, nbc, P);
+    HNO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int head_backward(const void* th, const void* td, const float* dprobs, const float* probs, float* dll, void* ws, int B,
+                  int C, long P, int activation, cudaStream_t st) {
+  InterpDev t;
+  if (make_dev(th, td, &t)) return -1;
+  HNO_CHECK(dprobs && dll && ws && (activation == 0 || probs), "head_backward: null pointer");
+  float* g1 = reinterpret_cast<float*>(ws);
+  float* g2 = g1 + (size_t)B * C * t.hi[0] * t.hi[1] * t.lo[2];
+  dim3 grid(ceil_div((long)t.hi[0] * t.hi[1] * t.lo[2], 256), B);
+  HNO_CLASS_SWITCH(C, {
+    if (activation == 1)
+      k_head_bwd_w<kC, 1, 0><<<grid, 256, 0, st>>>(dprobs, probs, nullptr, nullptr, nullptr, nullptr, g1, t, P);
+    else
+      k_head_bwd_w<kC, 0, 0><<<grid, 256, 0, st>>>(dprobs, probs, nullptr, nullptr, nullptr, nullptr, g1, t, P);
+  })
+  HNO_LAUNCH_CHECK();
+  return head_backward_passes(t, g1, g2, dll, B, C, P, st);
+}
+
+size_t loss_workspace_bytes(int B, int C) { return (size_t)B * C * kLossChunks * kMoments * sizeof(double) + 256; }
+
+int loss_forward(const float* yp, const float* yt, float* loss, float* coef, void* ws, int B, int C, long N, int kind,
+                 cudaStream_t st) {
+  HNO_CHECK(yp && yt && loss && coef && ws, "loss_forward: null pointer");
+  HNO_CHECK(kind == 0 || kind == 1, "loss_forward: kind must be 0 (Dice) or 1 (PCC)");
+  HNO_CHECK((long)B * C <= 65535, "loss_forward: too many (batch, label) pairs");
+  double* partials = reinterpret_cast<double*>(ws);
+  int chunks = (int)((N + 255) / 256 < kLossChunks ? (N + 255) / 256 : kLossChunks);
+  dim3 grid(chunks, B * C);
+  k_loss_moments<<<grid, 256, 0, st>>>(yp, yt, partials, N);
+  HNO_LAUNCH_CHECK();
+  k_loss_finalize<<<1, 256, 0, st>>>(partials, chunks, B * C, (double)N, kind, loss, coef);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+int loss_backward(const float* yp, const float* yt, const float* coef, const float* grad_loss, float* dyp, int B, int C,
+                  long N, cudaStream_t st) {
+  HNO_CHECK(yp && yt && coef && dyp, "loss_backward: null pointer");
+  int chunks = (int)((N + 255) / 256 < 1184 ? (N + 255) / 256 : 1184);
+  dim3 grid(chunks, B * C);
+  k_loss_bwd<<<grid, 256, 0, st>>>(yp, yt, coef, grad_loss, dyp, N);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+int head_loss_forward(const void* th, const void* td, const float* ll, const uint8_t* labels, float* loss, float* coef,
+                      void* ws, int B, int C, long P, int kind, cudaStream_t st) {
+  InterpDev t;
+  if (make_dev(th, td, &t)) return -1;
+  HNO_CHECK(ll && labels && loss && coef && ws, "head_loss_forward: null pointer");
+  HNO_CHECK(kind == 0 || kind == 1, "head_loss_forward: kind must be 0 (Dice) or 1 (PCC)");
+  const long Nx = (long)t.hi[0] * t.hi[1] * t.hi[2];
+  // moments live at the END of the head-backward workspace so that forward and backward can share it
+  const size_t g12 = ((size_t)B * C * t.hi[0] * t.hi[1] * t.lo[2] + (size_t)B * C * t.hi[0] * t.lo[1] * t.lo[2]);
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + ((g12 * sizeof(float) + 255) & ~(size_t)255));
+  int chunks = (int)((Nx + 255) / 256 < kLossChunks ? (Nx + 255) / 256 : kLossChunks);
+  dim3 grid(chunks, B);
+  HNO_CLASS_SWITCH(C, { k_head_loss_moments<kC, 1><<<grid, 256, 0, st>>>(ll, labels, partials, t, P); })
+  HNO_LAUNCH_CHECK();
+  k_loss_finalize<<<1, 256, 0, st>>>(partials, chunks, B * C, (double)Nx, kind, loss, coef);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+int head_loss_backward(const void* th, const void* td, const float* ll, const uint8_t* labels, const float* coef,
+                       const float* grad_loss, float* dll, void* ws, int B, int C, long P, cudaStream_t st) {
+  InterpDev t;
+  if (make_dev(th, td, &t)) return -1;
+  HNO_CHECK(ll && labels && coef && dll && ws, "head_loss_backward: null pointer");
+  float* g1 = reinterpret_cast<float*>(ws);
+  float* g2 = g1 + (size_t)B * C * t.hi[0] * t.hi[1] * t.lo[2];
+  dim3 grid(ceil_div((long)t.hi[0] * t.hi[1] * t.lo[2], 256), B);
+  HNO_CLASS_SWITCH(C, {
+    k_head_bwd_w<kC, 1, 1><<<grid, 256, 0, st>>>(nullptr, nullptr, ll, labels, coef, grad_loss, g1, t, P);
+  })
+  HNO_LAUNCH_CHECK();
+  return head_backward_passes(t, g1, g2, dll, B, C, P, st);
+}
+
+}  // namespace hno

@@ -1,0 +1,220 @@
+// Per-mode ("individual" weights) Hartley mixing and the fused Adamax step, sm_100a.
+//
+// Replaces nets/hartley_operator.py:293-299 (the weights_type == 'individual' branch of
+// _call3d_notransform), :302-317 (hartley_conv) and :320-333 (get_reverse = flip + roll by one, i.e.
+// index j -> (n - j) mod n on each of the three mode axes of the CROPPED block):
+//     out(k) = 1/2 [ W(k) (X(k) + X(~k)) + W(~k) (X(k) - X(~k)) ]        summed over input channels
+// The op is bound by the weight read (CO*CI*M floats, 36 MB at 24x24x15,680 modes): every thread owns
+// one mode k, streams W(k) and W(~k) once (both coalesced: ~k runs backwards through memory) and
+// keeps the B x CO outputs in registers.
+#include "common.cuh"
+#include "hno_b200.h"
+
+namespace hno {
+
+__device__ __forceinline__ long rev_index(long k, int n0, int n1, int n2) {
+  const int k2 = (int)(k % n2);
+  const long r = k / n2;
+  const int k1 = (int)(r % n1);
+  const int k0 = (int)(r / n1);
+  const int r0 = k0 == 0 ? 0 : n0 - k0, r1 = k1 == 0 ? 0 : n1 - k1, r2 = k2 == 0 ? 0 : n2 - k2;
+  return ((long)r0 * n1 + r1) * n2 + r2;
+}
+
+constexpr int kHcBatch = 2;  // samples per register tile
+
+template <int CO>
+__global__ void __launch_bounds__(128) k_hartley_conv_fwd(const float* __restrict__ x, const float* __restrict__ w,
+                                                          float* __restrict__ out, int B, int CI, int n0, int n1,
+                                                          int n2, int residual_selu) {
+  const long M = (long)n0 * n1 * n2;
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  if (k >= M) return;
+  const long kr = rev_index(k, n0, n1, n2);
+  for (int b0 = 0; b0 < B; b0 += kHcBatch) {
+    float acc[kHcBatch][CO];
+#pragma unroll
+    for (int bb = 0; bb < kHcBatch; ++bb)
+#pragma unroll
+      for (int o = 0; o < CO; ++o) acc[bb][o] = 0.f;
+    for (int i = 0; i < CI; ++i) {
+      float e[kHcBatch], od[kHcBatch];
+#pragma unroll
+      for (int bb = 0; bb < kHcBatch; ++bb) {
+        const int b = min(b0 + bb, B - 1);
+        const float a = __ldg(x + ((long)b * CI + i) * M + k), c = __ldg(x + ((long)b * CI + i) * M + kr);
+        e[bb] = a + c;
+        od[bb] = a - c;
+      }
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        const float wk = __ldg(w + ((long)o * CI + i) * M + k), wr = __ldg(w + ((long)o * CI + i) * M + kr);
+#pragma unroll
+        for (int bb = 0; bb < kHcBatch; ++bb) acc[bb][o] = fmaf(wk, e[bb], fmaf(wr, od[bb], acc[bb][o]));
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < kHcBatch; ++bb)
+      if (b0 + bb < B) {
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          float v = 0.5f * acc[bb][o];
+          if (residual_selu) v = selu_f(v + __ldg(x + ((long)(b0 + bb) * CI + o) * M + k));  // CI == CO here
+          out[((long)(b0 + bb) * CO + o) * M + k] = v;
+        }
+      }
+  }
+}
+
+// dX(k) = 1/2 sum_o [ W(k) (g(k) - g(~k)) + W(~k) (g(k) + g(~k)) ]
+template <int CI>
+__global__ void __launch_bounds__(128) k_hartley_conv_bwd_x(const float* __restrict__ g, const float* __restrict__ y,
+                                                            const float* __restrict__ w, float* __restrict__ dx, int B,
+                                                            int CO, int n0, int n1, int n2) {
+  const long M = (long)n0 * n1 * n2;
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  if (k >= M) return;
+  const long kr = rev_index(k, n0, n1, n2);
+  for (int b0 = 0; b0 < B; b0 += kHcBatch) {
+    float acc[kHcBatch][CI];
+#pragma unroll
+    for (int bb = 0; bb < kHcBatch; ++bb)
+#pragma unroll
+      for (int i = 0; i < CI; ++i) acc[bb][i] = 0.f;
+    for (int o = 0; o < CO; ++o) {
+      float dm[kHcBatch], dp[kHcBatch];
+#pragma unroll
+      for (int bb = 0; bb < kHcBatch; ++bb) {
+        const int b = min(b0 + bb, B - 1);
+        float a = __ldg(g + ((long)b * CO + o) * M + k), c = __ldg(g + ((long)b * CO + o) * M + kr);
+        if (y != nullptr) {  // fused selu(mix + x): g is the gradient of the activated output
+          a *= selu_grad_from_out(__ldg(y + ((long)b * CO + o) * M + k));
+          c *= selu_grad_from_out(__ldg(y + ((long)b * CO + o) * M + kr));
+        }
+        dm[bb] = a - c;
+        dp[bb] = a + c;
+      }
+#pragma unroll
+      for (int i = 0; i < CI; ++i) {
+        const float wk = __ldg(w + ((long)o * CI + i) * M + k), wr = __ldg(w + ((long)o * CI + i) * M + kr);
+#pragma unroll
+        for (int bb = 0; bb < kHcBatch; ++bb) acc[bb][i] = fmaf(wk, dm[bb], fmaf(wr, dp[bb], acc[bb][i]));
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < kHcBatch; ++bb)
+      if (b0 + bb < B) {
+#pragma unroll
+        for (int i = 0; i < CI; ++i) {
+          float v = 0.5f * acc[bb][i];
+          if (y != nullptr) {  // residual path (CI == CO)
+            const long off = ((long)(b0 + bb) * CO + i) * M + k;
+            v = fmaf(__ldg(g + off), selu_grad_from_out(__ldg(y + off)), v);
+          }
+          dx[((long)(b0 + bb) * CI + i) * M + k] = v;
+        }
+      }
+  }
+}
+
+// dW(k)[o][i] = 1/2 sum_b [ g_o(k) (X_i(k) + X_i(~k)) + g_o(~k) (X_i(~k) - X_i(k)) ]
+__global__ void __launch_bounds__(128) k_hartley_conv_bwd_w(const float* __restrict__ g, const float* __restrict__ y,
+                                                            const float* __restrict__ x, float* __restrict__ dw, int B,
+                                                            int CI, int CO, int n0, int n1, int n2, int accumulate) {
+  const long M = (long)n0 * n1 * n2;
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  if (k >= M) return;
+  const int o = blockIdx.y;
+  const long kr = rev_index(k, n0, n1, n2);
+  for (int i = 0; i < CI; ++i) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float gk = __ldg(g + ((long)b * CO + o) * M + k), gr = __ldg(g + ((long)b * CO + o) * M + kr);
+      if (y != nullptr) {
+        gk *= selu_grad_from_out(__ldg(y + ((long)b * CO + o) * M + k));
+        gr *= selu_grad_from_out(__ldg(y + ((long)b * CO + o) * M + kr));
+      }
+      const float xk = __ldg(x + ((long)b * CI + i) * M + k), xr = __ldg(x + ((long)b * CI + i) * M + kr);
+      acc = fmaf(gk, xk + xr, fmaf(gr, xr - xk, acc));
+    }
+    float* dst = dw + ((long)o * CI + i) * M + k;
+    *dst = accumulate ? *dst + 0.5f * acc : 0.5f * acc;
+  }
+}
+
+#define HNO_HC_CHANNELS(X) X(8) X(16) X(24) X(32)
+
+int hartley_conv_forward(const float* x, const float* w, float* out, int B, int ci, int co, int n0, int n1, int n2,
+                         int residual_selu, cudaStream_t st) {
+  HNO_CHECK(x && w && out, "hartley_conv_forward: null pointer");
+  HNO_CHECK(!residual_selu || ci == co, "hartley_conv_forward: the fused residual needs in_channels == out_channels");
+  const long M = (long)n0 * n1 * n2;
+  const int grid = ceil_div(M, 128);
+#define X(C)                                                                   \
+  if (co == C) {                                                               \
+    k_hartley_conv_fwd<C><<<grid, 128, 0, st>>>(x, w, out, B, ci, n0, n1, n2, residual_selu); \
+    HNO_LAUNCH_CHECK();                                                        \
+    return 0;                                                                  \
+  }
+  HNO_HC_CHANNELS(X)
+#undef X
+  set_error("hartley_conv_forward: out_channels %d not in {8,16,24,32}", co);
+  return -1;
+}
+
+int hartley_conv_backward(const float* dout, const float* y, const float* x, const float* w, float* dx, float* dw,
+                          int B, int ci, int co, int n0, int n1, int n2, int accumulate_dw, cudaStream_t st) {
+  HNO_CHECK(dout && x && w, "hartley_conv_backward: null pointer");
+  HNO_CHECK(y == nullptr || ci == co, "hartley_conv_backward: the fused residual needs in_channels == out_channels");
+  const long M = (long)n0 * n1 * n2;
+  const int grid = ceil_div(M, 128);
+  if (dx) {
+    bool done = false;
+#define X(C)                                                                        \
+  if (ci == C) {                                                                    \
+    k_hartley_conv_bwd_x<C><<<grid, 128, 0, st>>>(dout, y, w, dx, B, co, n0, n1, n2);  \
+    done = true;                                                                    \
+  }
+    HNO_HC_CHANNELS(X)
+#undef X
+    HNO_CHECK(done, "hartley_conv_backward: in_channels %d not in {8,16,24,32}", ci);
+    HNO_LAUNCH_CHECK();
+  }
+  if (dw) {
+    dim3 g2(grid, co);
+    k_hartley_conv_bwd_w<<<g2, 128, 0, st>>>(dout, y, x, dw, B, ci, co, n0, n1, n2, accumulate_dw);
+    HNO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// torch.optim.Adamax (single-tensor semantics) on a flat vector:
+//   g = grad*grad_scale + wd*p;  m = lerp(m, g, 1-b1);  u = max(b2*u, |g| + eps);  p -= lr/(1-b1^t) * m/u
+__global__ void __launch_bounds__(256) k_adamax(float* __restrict__ p, const float* __restrict__ grad,
+                                                float* __restrict__ m, float* __restrict__ u, long n, float clr,
+                                                float b1, float b2, float eps, float wd, float gs) {
+  const long i = blockIdx.x * 256L + threadIdx.x;
+  if (i >= n) return;
+  float g = grad[i] * gs;
+  const float pv = p[i];
+  if (wd != 0.f) g = fmaf(wd, pv, g);
+  const float mv = m[i] + (g - m[i]) * (1.f - b1);
+  const float uv = fmaxf(u[i] * b2, fabsf(g) + eps);
+  m[i] = mv;
+  u[i] = uv;
+  p[i] = pv - clr * (mv / uv);
+}
+
+int adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, long n, float lr, float beta1,
+                float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t st) {
+  HNO_CHECK(param && grad && exp_avg && exp_inf && n >= 0 && step >= 1, "adamax_step: bad arguments");
+  if (n == 0) return 0;
+  const double bc = 1.0 - pow((double)beta1, (double)step);
+  const float clr = (float)((double)lr / bc);
+  k_adamax<<<ceil_div(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_inf, n, clr, beta1, beta2, eps, weight_decay,
+                                              grad_scale);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace hno

@@ -1,0 +1,444 @@
+// Pointwise (1x1x1) channel mixing on channel-planar tensors, forward and backward, sm_100a.
+//
+// Replaces (see include/hno_b200.h for the full list):
+//   nets/nets_utils.py:120-174      ConvNormAct(kernel_size=1) = Conv3d 1x1x1 + bias + SELU
+//   nets/hartley_operator.py:287-292 einsum('oi,bidhw->bodhw') on the cropped modes
+//   nets/hnosegxs.py:307-329        NeuralOperatorBlock: selu(op(x) + x)
+//   nets/hnosegxs.py:254-255,273-275 mapping conv / concat conv on torch.cat([a, b], dim=1)
+// The concat is virtual: the two halves arrive as two pointers, torch.cat never materialises.
+//
+// Forward: one thread owns V adjacent voxels and all CO outputs (register accumulators); the
+// weights are broadcast from shared memory.  Backward: a persistent CTA walks voxel tiles; phase A
+// computes d(pre-activation) and the input gradients per voxel, phase B accumulates the weight
+// gradient as register-tiled outer products out of shared memory.  Per-CTA partial sums are
+// written to a workspace and reduced in fp64 by a second tiny kernel (deterministic, no atomics).
+#include "common.cuh"
+#include "hno_b200.h"
+#include "wgrad.cuh"
+
+namespace hno {
+
+template <int ACT>
+__device__ __forceinline__ float act_f(float x) {
+  return ACT == 1 ? selu_f(x) : x;
+}
+template <int ACT>
+__device__ __forceinline__ float act_grad_from_out(float y) {
+  return ACT == 1 ? selu_grad_from_out(y) : 1.f;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+template <int CI1, int CI2, int CO, int ACT, bool RES, int V>
+__global__ void __launch_bounds__(kPwThreads) k_pwconv_fwd(const float* __restrict__ in1,
+                                                           const float* __restrict__ in2,
+                                                           const float* __restrict__ weight,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           long S) {
+  static_assert(!RES || (CI1 == CO && CI2 == 0), "residual needs CI1 == CO and a single input");
+  constexpr int CI = CI1 + CI2;
+  constexpr int COp = (CO + 3) & ~3;
+  __shared__ __align__(16) float wt[CI * COp];  // transposed: wt[i][o]
+  __shared__ float sbias[COp];
+  for (int idx = threadIdx.x; idx < CI * COp; idx += kPwThreads) {
+    int i = idx / COp, o = idx - i * COp;
+    wt[idx] = o < CO ? weight[o * CI + i] : 0.f;
+  }
+  for (int o = threadIdx.x; o < COp; o += kPwThreads) sbias[o] = (bias != nullptr && o < CO) ? bias[o] : 0.f;
+  __syncthreads();
+  const long s0 = (blockIdx.x * (long)kPwThreads + threadIdx.x) * V;
+  if (s0 >= S) return;
+  const int b = blockIdx.y;
+  float acc[COp][V];
+#pragma unroll
+  for (int o = 0; o < COp; ++o)
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[o][v] = sbias[o];
+
+  const float* p1 = in1 + (long)b * CI1 * S + s0;
+#pragma unroll 4
+  for (int i = 0; i < CI1; ++i) {
+    Vec<V> x = Vec<V>::ld(p1 + (long)i * S);
+    const float4* w4 = reinterpret_cast<const float4*>(wt + i * COp);
+#pragma unroll
+    for (int q = 0; q < COp / 4; ++q) {
+      float4 w = w4[q];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        acc[4 * q + 0][v] = fmaf(w.x, x.v[v], acc[4 * q + 0][v]);
+        acc[4 * q + 1][v] = fmaf(w.y, x.v[v], acc[4 * q + 1][v]);
+        acc[4 * q + 2][v] = fmaf(w.z, x.v[v], acc[4 * q + 2][v]);
+        acc[4 * q + 3][v] = fmaf(w.w, x.v[v], acc[4 * q + 3][v]);
+      }
+    }
+  }
+  if (CI2 > 0) {
+    const float* p2 = in2 + (long)b * CI2 * S + s0;
+#pragma unroll 4
+    for (int i = 0; i < CI2; ++i) {
+      Vec<V> x = Vec<V>::ld(p2 + (long)i * S);
+      const float4* w4 = reinterpret_cast<const float4*>(wt + (CI1 + i) * COp);
+#pragma unroll
+      for (int q = 0; q < COp / 4; ++q) {
+        float4 w = w4[q];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc[4 * q + 0][v] = fmaf(w.x, x.v[v], acc[4 * q + 0][v]);
+          acc[4 * q + 1][v] = fmaf(w.y, x.v[v], acc[4 * q + 1][v]);
+          acc[4 * q + 2][v] = fmaf(w.z, x.v[v], acc[4 * q + 2][v]);
+          acc[4 * q + 3][v] = fmaf(w.w, x.v[v], acc[4 * q + 3][v]);
+        }
+      }
+    }
+  }
+  float* po = out + (long)b * CO * S + s0;
+#pragma unroll
+  for (int o = 0; o < CO; ++o) {
+    Vec<V> r;
+    if (RES) {
+      Vec<V> x = Vec<V>::ld(p1 + (long)o * S);  // second touch of the same line: L1 hit
+#pragma unroll
+      for (int v = 0; v < V; ++v) r.v[v] = act_f<ACT>(acc[o][v] + x.v[v]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) r.v[v] = act_f<ACT>(acc[o][v]);
+    }
+    r.st(po + (long)o * S);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+template <int CI1, int CI2, int CO, int ACT, bool RES, int VV>
+__global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_bwd(
+    const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ in1,
+    const float* __restrict__ in2, const float* __restrict__ weight, float* __restrict__ din1,
+    float* __restrict__ din2, float* __restrict__ partials, long S, long P, long HW, int tiles_per_sample,
+    long total_tiles, int flags) {
+  constexpr int CI = CI1 + CI2;
+  constexpr int CIM = CI1 > CI2 ? CI1 : CI2;
+  constexpr int COp = (CO + 3) & ~3;
+  constexpr int TV = kPwThreads * VV;
+  constexpr int TVS = TV + 4;  // (TVS/4) odd -> float4 rows of different channels land on different bank groups
+  constexpr int PSTRIDE = CO * CI + CO;
+  extern __shared__ float4 smem4[];
+  float* wt = reinterpret_cast<float*>(smem4);  // [CI][COp]
+  float* sdp = wt + CI * COp;                   // [CO][TVS]
+  float* sx = sdp + CO * TVS;                   // [CIM][TVS]
+  for (int idx = threadIdx.x; idx < CI * COp; idx += kPwThreads) {
+    int i = idx / COp, o = idx - i * COp;
+    wt[idx] = o < CO ? weight[o * CI + i] : 0.f;
+  }
+  using T1 = WgTile<CO, CI1>;
+  float accW1[T1::TO][T1::TI];
+  float accB[T1::TO];
+#pragma unroll
+  for (int q = 0; q < T1::TO; ++q) {
+    accB[q] = 0.f;
+#pragma unroll
+    for (int r = 0; r < T1::TI; ++r) accW1[q][r] = 0.f;
+  }
+  constexpr int CI2s = CI2 > 0 ? CI2 : 8;
+  using T2 = WgTile<CO, CI2s>;
+  float accW2[T2::TO][T2::TI];
+  float accB2[T2::TO];
+#pragma unroll
+  for (int q = 0; q < T2::TO; ++q) {
+    accB2[q] = 0.f;
+#pragma unroll
+    for (int r = 0; r < T2::TI; ++r) accW2[q][r] = 0.f;
+  }
+  __syncthreads();
+
+  const int lv = threadIdx.x * VV;
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int b = (int)(tile / tiles_per_sample);
+    const long s0 = (tile - (long)b * tiles_per_sample) * TV + lv;
+    const bool valid = s0 < S;
+    bool live[VV];
+#pragma unroll
+    for (int v = 0; v < VV; ++v) live[v] = valid && ((s0 + v) % P) < HW;
+
+    // ---- phase A1: d(pre-activation), staged to shared memory
+    float dpre[COp][VV];
+#pragma unroll
+    for (int o = 0; o < COp; ++o) {
+      if (o < CO && valid) {
+        Vec<VV> g = Vec<VV>::ld(dy + ((long)b * CO + o) * S + s0);
+        Vec<VV> yy;
+        if (ACT != 0) yy = Vec<VV>::ld(y + ((long)b * CO + o) * S + s0);
+#pragma unroll
+        for (int v = 0; v < VV; ++v)
+          dpre[o][v] = live[v] ? g.v[v] * (ACT != 0 ? act_grad_from_out<ACT>(yy.v[v]) : 1.f) : 0.f;
+      } else {
+#pragma unroll
+        for (int v = 0; v < VV; ++v) dpre[o][v] = 0.f;
+      }
+      if (o < CO) {
+#pragma unroll
+        for (int v = 0; v < VV; ++v) sdp[o * TVS + lv + v] = dpre[o][v];
+      }
+    }
+    // ---- input gradient + staging of input 1
+#pragma unroll 2
+    for (int i = 0; i < CI1; ++i) {
+      float acc[VV];
+#pragma unroll
+      for (int v = 0; v < VV; ++v) acc[v] = RES ? sdp[i * TVS + lv + v] : 0.f;
+      const float4* w4 = reinterpret_cast<const float4*>(wt + i * COp);
+#pragma unroll
+      for (int q = 0; q < COp / 4; ++q) {
+        float4 w = w4[q];
+#pragma unroll
+        for (int v = 0; v < VV; ++v) {
+          acc[v] = fmaf(w.x, dpre[4 * q + 0][v], acc[v]);
+          acc[v] = fmaf(w.y, dpre[4 * q + 1][v], acc[v]);
+          acc[v] = fmaf(w.z, dpre[4 * q + 2][v], acc[v]);
+          acc[v] = fmaf(w.w, dpre[4 * q + 3][v], acc[v]);
+        }
+      }
+      Vec<VV> x;
+#pragma unroll
+      for (int v = 0; v < VV; ++v) x.v[v] = 0.f;
+      if (valid) {
+        const long off = ((long)b * CI1 + i) * S + s0;
+        x = Vec<VV>::ld(in1 + off);
+        if (din1 != nullptr) {
+          Vec<VV> r;
+          if (flags & 4) {
+#pragma unroll
+            for (int v = 0; v < VV; ++v) acc[v] *= selu_grad_from_out(x.v[v]);
+          }
+          if (flags & 1) {
+            Vec<VV> old = Vec<VV>::ld(din1 + off);
+#pragma unroll
+            for (int v = 0; v < VV; ++v) r.v[v] = old.v[v] + acc[v];
+          } else {
+#pragma unroll
+            for (int v = 0; v < VV; ++v) r.v[v] = acc[v];
+          }
+          r.st(din1 + off);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VV; ++v) sx[i * TVS + lv + v] = x.v[v];
+    }
+    __syncthreads();
+    wgrad_tile<CO, CI1, TV, TVS>(sdp, sx, accW1, accB, true);
+    if (CI2 > 0) {
+      __syncthreads();
+#pragma unroll 2
+      for (int i = 0; i < CI2; ++i) {
+        float acc[VV];
+#pragma unroll
+        for (int v = 0; v < VV; ++v) acc[v] = 0.f;
+        const float4* w4 = reinterpret_cast<const float4*>(wt + (CI1 + i) * COp);
+#pragma unroll
+        for (int q = 0; q < COp / 4; ++q) {
+          float4 w = w4[q];
+#pragma unroll
+          for (int v = 0; v < VV; ++v) {
+            acc[v] = fmaf(w.x, dpre[4 * q + 0][v], acc[v]);
+            acc[v] = fmaf(w.y, dpre[4 * q + 1][v], acc[v]);
+            acc[v] = fmaf(w.z, dpre[4 * q + 2][v], acc[v]);
+            acc[v] = fmaf(w.w, dpre[4 * q + 3][v], acc[v]);
+          }
+        }
+        Vec<VV> x;
+#pragma unroll
+        for (int v = 0; v < VV; ++v) x.v[v] = 0.f;
+        if (valid) {
+          const long off = ((long)b * CI2 + i) * S + s0;
+          x = Vec<VV>::ld(in2 + off);
+          if (din2 != nullptr) {
+            Vec<VV> r;
+            if (flags & 2) {
+              Vec<VV> old = Vec<VV>::ld(din2 + off);
+#pragma unroll
+              for (int v = 0; v < VV; ++v) r.v[v] = old.v[v] + acc[v];
+            } else {
+#pragma unroll
+              for (int v = 0; v < VV; ++v) r.v[v] = acc[v];
+            }
+            r.st(din2 + off);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < VV; ++v) sx[i * TVS + lv + v] = x.v[v];
+      }
+      __syncthreads();
+      wgrad_tile<CO, CI2s, TV, TVS>(sdp, sx, accW2, accB2, false);
+    }
+    __syncthreads();  // tiles are overwritten by the next iteration
+  }
+
+  // ---- per-CTA partial sums -> workspace row
+  float* prow = partials + (long)blockIdx.x * PSTRIDE;
+  wgrad_flush<CO, CI1>(sdp, accW1, prow, CI, 0);
+  if (CI2 > 0) wgrad_flush<CO, CI2s>(sdp, accW2, prow, CI, CI1);
+  {  // bias: threads with it == 0 hold partial sums per group
+    const int g = threadIdx.x / T1::G;
+    const int l = threadIdx.x - g * T1::G;
+    const int ot = l / T1::N_IT;
+    const int it = l - ot * T1::N_IT;
+    if (it == 0 && ot * T1::TO < CO) {
+#pragma unroll
+      for (int q = 0; q < T1::TO; ++q) sx[g * CO + ot * T1::TO + q] = accB[q];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < CO; o += kPwThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < T1::NG; ++gg) s += sx[gg * CO + o];
+      prow[CO * CI + o] = s;
+    }
+  }
+}
+
+// partials [nrows][n] -> dst[n] in fp64; flags bit3 accumulates.  dbias may be null.
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int nrows, int n,
+                                                         int nw, float* __restrict__ dweight,
+                                                         float* __restrict__ dbias, int accumulate) {
+  // one warp per output element
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  double s = 0.0;
+  for (int r = lane; r < nrows; r += 32) s += (double)partials[(long)r * n + warp];
+  s = warp_sum_d(s);
+  if (lane == 0) {
+    float* dst = warp < nw ? dweight + warp : (dbias ? dbias + (warp - nw) : nullptr);
+    if (dst) *dst = accumulate ? *dst + (float)s : (float)s;
+  }
+}
+
+int reduce_partials(const float* partials, int nrows, int nw, int nb, float* dweight, float* dbias, int accumulate,
+                    cudaStream_t st) {
+  const int n = nw + nb;
+  k_reduce_partials<<<ceil_div((long)n * 32, 256), 256, 0, st>>>(partials, nrows, n, nw, dweight, dbias, accumulate);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ dispatch
+static int bwd_grid(long total_tiles) {
+  long g = (long)sm_count() * 2;
+  return (int)(total_tiles < g ? total_tiles : g);
+}
+
+template <int CI1, int CI2, int CO, int ACT, bool RES>
+static int fwd_t(const float* in1, const float* in2, const float* w, const float* bias, float* out, int B, long S,
+                 cudaStream_t st) {
+  const void* ptrs[3] = {in1, in2, out};
+  const long cnt[1] = {S};
+  const int v = pick_vec(ptrs, 3, cnt, 1);
+  dim3 grid(ceil_div(S / v, kPwThreads), B);
+  if (v == 4)
+    k_pwconv_fwd<CI1, CI2, CO, ACT, RES, 4><<<grid, kPwThreads, 0, st>>>(in1, in2, w, bias, out, S);
+  else if (v == 2)
+    k_pwconv_fwd<CI1, CI2, CO, ACT, RES, 2><<<grid, kPwThreads, 0, st>>>(in1, in2, w, bias, out, S);
+  else
+    k_pwconv_fwd<CI1, CI2, CO, ACT, RES, 1><<<grid, kPwThreads, 0, st>>>(in1, in2, w, bias, out, S);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int CI1, int CI2, int CO, int VV>
+static size_t bwd_smem() {
+  constexpr int CI = CI1 + CI2;
+  constexpr int CIM = CI1 > CI2 ? CI1 : CI2;
+  constexpr int COp = (CO + 3) & ~3;
+  constexpr int TVS = kPwThreads * VV + 4;
+  return (size_t)(CI * COp + (CO + CIM) * TVS) * sizeof(float);
+}
+
+template <int CI1, int CI2, int CO, int ACT, bool RES>
+static int bwd_t(const float* dy, const float* y, const float* in1, const float* in2, const float* w, float* din1,
+                 float* din2, float* dweight, float* dbias, void* ws, int B, long S, long P, long HW, int flags,
+                 cudaStream_t st) {
+  constexpr int CI = CI1 + CI2;
+  const void* ptrs[6] = {dy, y, in1, in2, din1, din2};
+  const long cnt[1] = {S};
+  const int v = pick_vec(ptrs, 6, cnt, 1);
+  float* partials = reinterpret_cast<float*>(ws);
+  int grid;
+  if (v >= 2) {
+    constexpr int TV = kPwThreads * 2;
+    const int tps = ceil_div(S, TV);
+    const long total = (long)tps * B;
+    grid = bwd_grid(total);
+    auto kern = k_pwconv_bwd<CI1, CI2, CO, ACT, RES, 2>;
+    const size_t smem = bwd_smem<CI1, CI2, CO, 2>();
+    HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kPwThreads, smem, st>>>(dy, y, in1, in2, w, din1, din2, partials, S, P, HW, tps, total, flags);
+  } else {
+    constexpr int TV = kPwThreads;
+    const int tps = ceil_div(S, TV);
+    const long total = (long)tps * B;
+    grid = bwd_grid(total);
+    auto kern = k_pwconv_bwd<CI1, CI2, CO, ACT, RES, 1>;
+    const size_t smem = bwd_smem<CI1, CI2, CO, 1>();
+    HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kPwThreads, smem, st>>>(dy, y, in1, in2, w, din1, din2, partials, S, P, HW, tps, total, flags);
+  }
+  HNO_LAUNCH_CHECK();
+  return reduce_partials(partials, grid, CO * CI, CO, dweight, dbias, (flags & 8) ? 1 : 0, st);
+}
+
+// (CI1, CI2, CO, ACT, RES) combinations the model needs, for filters F in {8, 24} and heads of 2..4 classes.
+#define HNO_PW_CONFIGS(X) \
+  X(8, 0, 8, 1, true)     \
+  X(8, 0, 8, 1, false)    \
+  X(8, 8, 8, 1, false)    \
+  X(8, 0, 2, 0, false)    \
+  X(8, 0, 3, 0, false)    \
+  X(8, 0, 4, 0, false)    \
+  X(24, 0, 24, 1, true)   \
+  X(24, 0, 24, 1, false)  \
+  X(24, 24, 24, 1, false) \
+  X(24, 0, 24, 0, false)  \
+  X(24, 0, 2, 0, false)   \
+  X(24, 0, 3, 0, false)   \
+  X(24, 0, 4, 0, false)
+
+int pwconv_supported(int ci1, int ci2, int co, int act, int residual) {
+#define X(A, B_, C, D, E) \
+  if (ci1 == A && ci2 == B_ && co == C && (act < 0 || act == D) && (residual < 0 || (residual != 0) == E)) return 1;
+  HNO_PW_CONFIGS(X)
+#undef X
+  return 0;
+}
+
+int pwconv_forward(const float* in1, const float* in2, const float* w, const float* bias, float* out, int B, int ci1,
+                   int ci2, int co, long S, int act, int residual, cudaStream_t st) {
+  HNO_CHECK(in1 && w && out && (ci2 == 0 || in2), "pwconv_forward: null pointer");
+  HNO_CHECK(B >= 1 && B <= 65535 && S >= 1, "pwconv_forward: bad sizes B=%d S=%ld", B, S);
+#define X(A, B_, C, D, E)                                                     \
+  if (ci1 == A && ci2 == B_ && co == C && act == D && (residual != 0) == E)   \
+    return fwd_t<A, B_, C, D, E>(in1, in2, w, bias, out, B, S, st);
+  HNO_PW_CONFIGS(X)
+#undef X
+  set_error("pwconv_forward: unsupported configuration ci1=%d ci2=%d co=%d act=%d residual=%d", ci1, ci2, co, act,
+            residual);
+  return -1;
+}
+
+size_t pwconv_backward_workspace_bytes(int ci1, int ci2, int co) {
+  return (size_t)(sm_count() * 2 + 8) * ((size_t)co * (ci1 + ci2) + co) * sizeof(float);
+}
+
+int pwconv_backward(const float* dy, const float* y, const float* in1, const float* in2, const float* w, float* din1,
+                    float* din2, float* dweight, float* dbias, void* ws, int B, int ci1, int ci2, int co, long S,
+                    long P, long HW, int act, int residual, int flags, cudaStream_t st) {
+  HNO_CHECK(dy && in1 && w && dweight && ws && (ci2 == 0 || in2) && (act == 0 || y),
+            "pwconv_backward: null pointer");
+  HNO_CHECK(B >= 1 && S >= 1 && P >= 1 && HW >= 1 && HW <= P, "pwconv_backward: bad sizes");
+#define X(A, B_, C, D, E)                                                                                   \
+  if (ci1 == A && ci2 == B_ && co == C && act == D && (residual != 0) == E)                                 \
+    return bwd_t<A, B_, C, D, E>(dy, y, in1, in2, w, din1, din2, dweight, dbias, ws, B, S, P, HW, flags, st);
+  HNO_PW_CONFIGS(X)
+#undef X
+  set_error("pwconv_backward: unsupported configuration ci1=%d ci2=%d co=%d act=%d residual=%d", ci1, ci2, co, act,
+            residual);
+  return -1;
+}
+
+}  // namespace hno

@@ -1,0 +1,221 @@
+// Stem of HNOSeg-XS: Conv3d(kernel 2, stride 2, padding 1) + bias + SELU, forward and weight gradient.
+//
+// Replaces nets/hnosegxs.py:102-105,150-151 -> nets/nets_utils.py:156-163 (ConvNormAct with
+// kernel_size=2, stride=2: padding = kernel_size // 2 = 1).  With stride == kernel the windows do not
+// overlap, so the op is a gather of a 2x2x2xCIN patch per output voxel followed by a (8*CIN -> F)
+// channel mix: every input voxel is read exactly once.  The model input needs no gradient, so the
+// backward is the weight/bias gradient only.
+#include "common.cuh"
+#include "hno_b200.h"
+#include "wgrad.cuh"
+
+namespace hno {
+
+struct StemGeom {
+  int Dx, Hx, Wx, D, H, W;
+  long P, S, HWx;
+};
+
+__device__ __forceinline__ float stem_tap(const float* __restrict__ xc, const StemGeom& g, int d, int h, int w, int kd,
+                                          int kh, int kw) {
+  const int zd = 2 * d - 1 + kd, zh = 2 * h - 1 + kh, zw = 2 * w - 1 + kw;
+  const bool inb = zd >= 0 && zd < g.Dx && zh >= 0 && zh < g.Hx && zw >= 0 && zw < g.Wx;
+  return inb ? __ldg(xc + (long)zd * g.HWx + (long)zh * g.Wx + zw) : 0.f;
+}
+
+template <int CIN, int F>
+__global__ void __launch_bounds__(256) k_stem_fwd(const float* __restrict__ x, const float* __restrict__ weight,
+                                                  const float* __restrict__ bias, float* __restrict__ out,
+                                                  StemGeom g) {
+  constexpr int Q = 8 * CIN;
+  constexpr int Fp = (F + 3) & ~3;
+  __shared__ __align__(16) float wt[Q * Fp];  // wt[q][o]
+  __shared__ float sb[Fp];
+  for (int idx = threadIdx.x; idx < Q * Fp; idx += 256) {
+    int q = idx / Fp, o = idx - q * Fp;
+    wt[idx] = o < F ? weight[o * Q + q] : 0.f;
+  }
+  for (int o = threadIdx.x; o < Fp; o += 256) sb[o] = (bias && o < F) ? bias[o] : 0.f;
+  __syncthreads();
+  const long s = blockIdx.x * 256L + threadIdx.x;
+  if (s >= g.S) return;
+  const int b = blockIdx.y;
+  float* po = out + (long)b * F * g.S + s;
+  const int d = (int)(s / g.P);
+  const int p = (int)(s - (long)d * g.P);
+  if (p >= g.H * g.W) {
+#pragma unroll
+    for (int o = 0; o < F; ++o) po[(long)o * g.S] = 0.f;
+    return;
+  }
+  const int h = p / g.W, w = p - h * g.W;
+  float acc[Fp];
+#pragma unroll
+  for (int o = 0; o < Fp; ++o) acc[o] = sb[o];
+#pragma unroll
+  for (int i = 0; i < CIN; ++i) {
+    const float* xc = x + ((long)b * CIN + i) * g.Dx * g.HWx;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float xv = stem_tap(xc, g, d, h, w, t >> 2, (t >> 1) & 1, t & 1);
+      const float4* w4 = reinterpret_cast<const float4*>(wt + (i * 8 + t) * Fp);
+#pragma unroll
+      for (int q = 0; q < Fp / 4; ++q) {
+        float4 ww = w4[q];
+        acc[4 * q + 0] = fmaf(ww.x, xv, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(ww.y, xv, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(ww.z, xv, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(ww.w, xv, acc[4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < F; ++o) po[(long)o * g.S] = selu_f(acc[o]);
+}
+
+// dW[o][q] = sum_v dpre[o][v] * patch_q(v),  db[o] = sum_v dpre[o][v]
+template <int CIN, int F>
+__global__ void __launch_bounds__(kPwThreads, 2) k_stem_wgrad(const float* __restrict__ dpre,
+                                                              const float* __restrict__ x,
+                                                              float* __restrict__ partials, StemGeom g,
+                                                              int tiles_per_sample, long total_tiles) {
+  constexpr int Q = 8 * CIN;
+  constexpr int TV = kPwThreads;
+  constexpr int TVS = TV + 4;
+  constexpr int PSTRIDE = F * Q + F;
+  extern __shared__ float4 smem4[];
+  float* sdp = reinterpret_cast<float*>(smem4);  // [F][TVS]
+  float* sx = sdp + F * TVS;                     // [Q][TVS]
+  using T = WgTile<F, Q>;
+  float accW[T::TO][T::TI];
+  float accB[T::TO];
+#pragma unroll
+  for (int q = 0; q < T::TO; ++q) {
+    accB[q] = 0.f;
+#pragma unroll
+    for (int r = 0; r < T::TI; ++r) accW[q][r] = 0.f;
+  }
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int b = (int)(tile / tiles_per_sample);
+    const long s = (tile - (long)b * tiles_per_sample) * TV + threadIdx.x;
+    int d = 0, h = 0, w = 0;
+    bool live = false;
+    if (s < g.S) {
+      d = (int)(s / g.P);
+      const int p = (int)(s - (long)d * g.P);
+      if (p < g.H * g.W) {
+        live = true;
+        h = p / g.W;
+        w = p - h * g.W;
+      }
+    }
+#pragma unroll 4
+    for (int o = 0; o < F; ++o)
+      sdp[o * TVS + threadIdx.x] = live ? __ldg(dpre + ((long)b * F + o) * g.S + s) : 0.f;
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) {
+      const float* xc = x + ((long)b * CIN + i) * g.Dx * g.HWx;
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        sx[(i * 8 + t) * TVS + threadIdx.x] = live ? stem_tap(xc, g, d, h, w, t >> 2, (t >> 1) & 1, t & 1) : 0.f;
+    }
+    __syncthreads();
+    wgrad_tile<F, Q, TV, TVS>(sdp, sx, accW, accB, true);
+    __syncthreads();
+  }
+  float* prow = partials + (long)blockIdx.x * PSTRIDE;
+  wgrad_flush<F, Q>(sdp, accW, prow, Q, 0);
+  {
+    const int gi = threadIdx.x / T::G;
+    const int l = threadIdx.x - gi * T::G;
+    const int ot = l / T::N_IT;
+    const int it = l - ot * T::N_IT;
+    if (it == 0 && ot * T::TO < F) {
+#pragma unroll
+      for (int q = 0; q < T::TO; ++q) sx[gi * F + ot * T::TO + q] = accB[q];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < F; o += kPwThreads) {
+      float sum = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < T::NG; ++gg) sum += sx[gg * F + o];
+      prow[F * Q + o] = sum;
+    }
+  }
+}
+
+#define HNO_STEM_CONFIGS(X) X(1, 8) X(2, 8) X(4, 8) X(1, 24) X(2, 24) X(3, 24) X(4, 24)
+
+int stem_supported(int cin, int f) {
+#define X(A, B_) \
+  if (cin == A && f == B_) return 1;
+  HNO_STEM_CONFIGS(X)
+#undef X
+  return 0;
+}
+
+static int make_geom(StemGeom* g, int Dx, int Hx, int Wx, long P) {
+  g->Dx = Dx; g->Hx = Hx; g->Wx = Wx;
+  g->D = Dx / 2 + 1; g->H = Hx / 2 + 1; g->W = Wx / 2 + 1;
+  g->P = P;
+  g->S = (long)g->D * P;
+  g->HWx = (long)Hx * Wx;
+  HNO_CHECK(Dx >= 1 && Hx >= 1 && Wx >= 1, "stem: bad input size %dx%dx%d", Dx, Hx, Wx);
+  HNO_CHECK(P >= (long)g->H * g->W, "stem: plane pitch %ld < H*W = %ld", P, (long)g->H * g->W);
+  return 0;
+}
+
+int stem_forward(const float* x, const float* weight, const float* bias, float* out, int B, int cin, int f, int Dx,
+                 int Hx, int Wx, long P, cudaStream_t st) {
+  HNO_CHECK(x && weight && out, "stem_forward: null pointer");
+  StemGeom g;
+  if (make_geom(&g, Dx, Hx, Wx, P)) return -1;
+  dim3 grid(ceil_div(g.S, 256), B);
+#define X(A, B_)                                                                  \
+  if (cin == A && f == B_) {                                                      \
+    k_stem_fwd<A, B_><<<grid, 256, 0, st>>>(x, weight, bias, out, g);             \
+    HNO_LAUNCH_CHECK();                                                           \
+    return 0;                                                                     \
+  }
+  HNO_STEM_CONFIGS(X)
+#undef X
+  set_error("stem_forward: unsupported configuration in_channels=%d filters=%d", cin, f);
+  return -1;
+}
+
+size_t stem_backward_workspace_bytes(int cin, int f) {
+  return (size_t)(sm_count() * 2 + 8) * ((size_t)f * 8 * cin + f) * sizeof(float);
+}
+
+template <int CIN, int F>
+static int stem_bwd_t(const float* dpre, const float* x, float* dweight, float* dbias, void* ws, int B,
+                      const StemGeom& g, int accumulate, cudaStream_t st) {
+  constexpr int Q = 8 * CIN;
+  constexpr int TV = kPwThreads;
+  const int tps = ceil_div(g.S, TV);
+  const long total = (long)tps * B;
+  long gmax = (long)sm_count() * 2;
+  const int grid = (int)(total < gmax ? total : gmax);
+  const size_t smem = (size_t)(F + Q) * (TV + 4) * sizeof(float);
+  auto kern = k_stem_wgrad<CIN, F>;
+  HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  float* partials = reinterpret_cast<float*>(ws);
+  kern<<<grid, kPwThreads, smem, st>>>(dpre, x, partials, g, tps, total);
+  HNO_LAUNCH_CHECK();
+  return reduce_partials(partials, grid, F * Q, F, dweight, dbias, accumulate, st);
+}
+
+int stem_backward(const float* dpre, const float* x, float* dweight, float* dbias, void* ws, int B, int cin, int f,
+                  int Dx, int Hx, int Wx, long P, int accumulate, cudaStream_t st) {
+  HNO_CHECK(dpre && x && dweight && ws, "stem_backward: null pointer");
+  StemGeom g;
+  if (make_geom(&g, Dx, Hx, Wx, P)) return -1;
+#define X(A, B_) \
+  if (cin == A && f == B_) return stem_bwd_t<A, B_>(dpre, x, dweight, dbias, ws, B, g, accumulate, st);
+  HNO_STEM_CONFIGS(X)
+#undef X
+  set_error("stem_backward: unsupported configuration in_channels=%d filters=%d", cin, f);
+  return -1;
+}
+
+}  // namespace hno

@@ -1,0 +1,377 @@
+"""Thin PyTorch wrappers (tensor allocation + autograd wiring) over the C ABI.  All compute is in the .so.
+
+Tensor convention: activations are (B, C, D, P) "planar" tensors (P = plane pitch >= H*W) or ordinary dense
+(B, C, D, H, W) tensors, which are the same memory layout with P == H*W.
+"""
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+from .plan import get_crop_plan, get_interp_tables
+
+_ws_cache = {}
+
+
+def _require_cuda(t, name):
+    if t.device.type != 'cuda':
+        raise RuntimeError(f'hno_b200: {name} must be a CUDA tensor (got {t.device}); this package has no CPU path')
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'hno_b200: {name} must be float32 (got {t.dtype})')
+
+
+def workspace(nbytes, device, tag):
+    """Grow-only scratch buffer per (device, tag); kernels on one stream are serialised so reuse is safe."""
+    key = (str(device), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _ws_cache[key] = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+    return buf
+
+
+# ------------------------------------------------------------------------------------------ DHT
+def _geom(x, hw=None):
+    """(nslab, D, pitch, dense_hw) of a planar (B,C,D,P) or dense (B,C,D,H,W) tensor."""
+    if x.ndim == 5:
+        return x.shape[0] * x.shape[1], x.shape[2], x.shape[3] * x.shape[4]
+    assert x.ndim == 4
+    return x.shape[0] * x.shape[1], x.shape[2], x.shape[3]
+
+
+def dht3_forward(x, plan, scale):
+    """z[B,C,Ld,Lh,Lw] = scale * C x."""
+    _require_cuda(x, 'x')
+    x = x.contiguous()
+    nslab, D, pitch = _geom(x)
+    assert D == plan.spatial[0] and pitch >= plan.spatial[1] * plan.spatial[2]
+    z = torch.empty((x.shape[0], x.shape[1]) + plan.modes_shape, dtype=torch.float32, device=x.device)
+    ws = workspace(plan.workspace_bytes(pitch, nslab), x.device, 'dht')
+    call('hno_dht3_forward', plan.host.data_ptr(), plan.dev.data_ptr(), ptr(x), pitch, D * pitch, ptr(z), ptr(ws),
+         nslab, float(scale), stream_ptr())
+    return z
+
+
+def dht3_adjoint(z, plan, scale, epilogue=0, out=None, pitch=None):
+    """x (op)= scale * C^T z.  epilogue 0 store / 1 accumulate into `out` / 2 SELU.  Returns a dense (B,C,D,H,W)
+    tensor when pitch is None, else a planar (B,C,D,pitch) one."""
+    _require_cuda(z, 'z')
+    z = z.contiguous()
+    D, H, W = plan.spatial
+    B, C = z.shape[:2]
+    if out is None:
+        assert epilogue != 1
+        shape = (B, C, D, H, W) if pitch is None else (B, C, D, pitch)
+        out = torch.empty(shape, dtype=torch.float32, device=z.device)
+    nslab, D2, p = _geom(out)
+    assert D2 == D and nslab == B * C and out.is_contiguous()
+    ws = workspace(plan.workspace_bytes(p, nslab), z.device, 'dht')
+    call('hno_dht3_adjoint', plan.host.data_ptr(), plan.dev.data_ptr(), ptr(z), ptr(out), p, D * p, ptr(ws), nslab,
+         float(scale), int(epilogue), stream_ptr())
+    return out
+
+
+class TruncatedDHT(torch.autograd.Function):
+    """TransformCrop: z = (1/N) C x; backward dx = (1/N) C^T dz."""
+
+    @staticmethod
+    def forward(ctx, x, plan):
+        ctx.plan = plan
+        return dht3_forward(x, plan, 1.0 / plan.n_voxels)
+
+    @staticmethod
+    def backward(ctx, dz):
+        return dht3_adjoint(dz, ctx.plan, 1.0 / ctx.plan.n_voxels), None
+
+
+class TruncatedIDHT(torch.autograd.Function):
+    """PadInverse: x = C^T z (unnormalised); backward dz = C dx."""
+
+    @staticmethod
+    def forward(ctx, z, plan):
+        ctx.plan = plan
+        return dht3_adjoint(z, plan, 1.0)
+
+    @staticmethod
+    def backward(ctx, dx):
+        return dht3_forward(dx, ctx.plan, 1.0), None
+
+
+# ------------------------------------------------------------------------------------------ pointwise conv
+def _flat_s(t):
+    s = 1
+    for v in t.shape[2:]:
+        s *= v
+    return s
+
+
+def pwconv_forward(in1, in2, weight, bias, act, residual=False):
+    _require_cuda(in1, 'in1')
+    in1 = in1.contiguous()
+    in2 = in2.contiguous() if in2 is not None else None
+    B, ci1 = in1.shape[:2]
+    ci2 = in2.shape[1] if in2 is not None else 0
+    co = weight.shape[0]
+    out = torch.empty((B, co) + tuple(in1.shape[2:]), dtype=torch.float32, device=in1.device)
+    call('hno_pwconv_forward', ptr(in1), ptr(in2), ptr(weight.contiguous()), ptr(bias), ptr(out), B, ci1, ci2, co,
+         _flat_s(in1), int(act), int(bool(residual)), stream_ptr())
+    return out
+
+
+def pwconv_backward(dy, y, in1, in2, weight, act, residual=False, hw=None, need_in1=True, need_in2=True,
+                    in1_is_selu=False, din1=None, din2=None, dweight=None, dbias=None, has_bias=True,
+                    accumulate_w=False):
+    """Returns (din1, din2, dweight, dbias).  `hw`: (P, HW) when the tensors are planar with padding columns."""
+    B, ci1 = in1.shape[:2]
+    ci2 = in2.shape[1] if in2 is not None else 0
+    co = weight.shape[0]
+    S = _flat_s(in1)
+    P, HW = hw if hw is not None else (S, S)
+    dev = in1.device
+    flags = 0
+    if din1 is not None:
+        flags |= 1
+    elif need_in1:
+        din1 = torch.empty_like(in1)
+    if in2 is not None:
+        if din2 is not None:
+            flags |= 2
+        elif need_in2:
+            din2 = torch.empty_like(in2)
+    if in1_is_selu:
+        flags |= 4
+    if accumulate_w:
+        flags |= 8
+    if dweight is None:
+        dweight = torch.empty((co, ci1 + ci2), dtype=torch.float32, device=dev)
+    if dbias is None and has_bias:
+        dbias = torch.empty((co,), dtype=torch.float32, device=dev)
+    ws = workspace(_lib.load().hno_pwconv_backward_workspace_bytes(ci1, ci2, co), dev, 'pw')
+    call('hno_pwconv_backward', ptr(dy.contiguous()), ptr(y), ptr(in1), ptr(in2), ptr(weight.contiguous()),
+         ptr(din1), ptr(din2), ptr(dweight), ptr(dbias), ptr(ws), B, ci1, ci2, co, S, P, HW, int(act),
+         int(bool(residual)), flags, stream_ptr())
+    return din1, din2, dweight, dbias
+
+
+class PointwiseConv(torch.autograd.Function):
+    """y = act(W [in1; in2] + b (+ in1)); weight (CO, CI) or (CO, CI, 1, 1, 1)."""
+
+    @staticmethod
+    def forward(ctx, in1, in2, weight, bias, act, residual):
+        w2 = weight.reshape(weight.shape[0], -1)
+        in1 = in1.contiguous()
+        in2 = in2.contiguous() if in2 is not None else None
+        y = pwconv_forward(in1, in2, w2, bias, act, residual)
+        ctx.save_for_backward(y, in1, in2, w2, bias)
+        ctx.cfg = (act, residual, weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, in1, in2, w2, bias = ctx.saved_tensors
+        act, residual, wshape = ctx.cfg
+        din1, din2, dw, db = pwconv_backward(dy, y, in1, in2, w2, act, residual, need_in1=ctx.needs_input_grad[0],
+                                             need_in2=in2 is not None and ctx.needs_input_grad[1],
+                                             has_bias=bias is not None)
+        return din1, din2, dw.reshape(wshape), db, None, None
+
+
+# ------------------------------------------------------------------------------------------ individual-weight mixing
+class HartleyConv(torch.autograd.Function):
+    """out(k) = 1/2 [W(k)(X(k)+X(~k)) + W(~k)(X(k)-X(~k))]  (reference nets/hartley_operator.py:293-317)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, residual_selu=False):
+        x = x.contiguous()
+        weight = weight.contiguous()
+        out = hartley_conv_forward(x, weight, residual_selu)
+        ctx.save_for_backward(x, weight, out if residual_selu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, y = ctx.saved_tensors
+        dx, dw = hartley_conv_backward(dout, y, x, weight, need_dx=ctx.needs_input_grad[0],
+                                       need_dw=ctx.needs_input_grad[1])
+        return dx, dw, None
+
+
+def hartley_conv_forward(x, weight, residual_selu=False):
+    _require_cuda(x, 'x')
+    B, ci = x.shape[:2]
+    co = weight.shape[0]
+    n0, n1, n2 = x.shape[2:]
+    assert tuple(weight.shape[2:]) == (n0, n1, n2), 'individual weights must match the cropped mode block'
+    out = torch.empty((B, co, n0, n1, n2), dtype=torch.float32, device=x.device)
+    call('hno_hartley_conv_forward', ptr(x), ptr(weight), ptr(out), B, ci, co, n0, n1, n2, int(bool(residual_selu)),
+         stream_ptr())
+    return out
+
+
+def hartley_conv_backward(dout, y, x, weight, need_dx=True, need_dw=True, dw=None, accumulate=False):
+    B, ci = x.shape[:2]
+    co = weight.shape[0]
+    n0, n1, n2 = x.shape[2:]
+    dx = torch.empty_like(x) if need_dx else None
+    if dw is None and need_dw:
+        dw = torch.empty_like(weight)
+    call('hno_hartley_conv_backward', ptr(dout.contiguous()), ptr(y), ptr(x), ptr(weight), ptr(dx), ptr(dw), B, ci,
+         co, n0, n1, n2, int(accumulate), stream_ptr())
+    return dx, dw
+
+
+# ------------------------------------------------------------------------------------------ stem
+def stem_out_shape(spatial):
+    return tuple(s // 2 + 1 for s in spatial)
+
+
+def stem_forward(x, weight, bias, pitch=None):
+    _require_cuda(x, 'x')
+    x = x.contiguous()
+    B, cin, Dx, Hx, Wx = x.shape
+    f = weight.shape[0]
+    D, H, W = stem_out_shape((Dx, Hx, Wx))
+    shape = (B, f, D, H, W) if pitch is None else (B, f, D, pitch)
+    P = H * W if pitch is None else pitch
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    call('hno_stem_forward', ptr(x), ptr(weight.contiguous()), ptr(bias), ptr(out), B, cin, f, Dx, Hx, Wx, P,
+         stream_ptr())
+    return out
+
+
+def stem_backward(dpre, x, f, pitch=None, dweight=None, dbias=None, accumulate=False):
+    B, cin, Dx, Hx, Wx = x.shape
+    D, H, W = stem_out_shape((Dx, Hx, Wx))
+    P = H * W if pitch is None else pitch
+    if dweight is None:
+        dweight = torch.empty((f, cin, 2, 2, 2), dtype=torch.float32, device=x.device)
+    if dbias is None:
+        dbias = torch.empty((f,), dtype=torch.float32, device=x.device)
+    ws = workspace(_lib.load().hno_stem_backward_workspace_bytes(cin, f), x.device, 'pw')
+    call('hno_stem_backward', ptr(dpre.contiguous()), ptr(x), ptr(dweight), ptr(dbias), ptr(ws), B, cin, f, Dx, Hx,
+         Wx, P, int(accumulate), stream_ptr())
+    return dweight, dbias
+
+
+class StemConv(torch.autograd.Function):
+    """selu(Conv3d(k=2, s=2, p=1)(x)); the gradient w.r.t. x is not provided (x is the network input)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = stem_forward(x, weight, bias)
+        ctx.save_for_backward(x, y)
+        ctx.f = weight.shape[0]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError('hno_b200: the stem does not provide a gradient w.r.t. the network input')
+        x, y = ctx.saved_tensors
+        dpre = selu_backward(dy, y)
+        dw, db = stem_backward(dpre, x, ctx.f)
+        return None, dw, db
+
+
+def selu_backward(dy, y):
+    """dy * selu'(.) from the SELU output (tiny torch expression; only used by the stand-alone stem module)."""
+    scale, alpha = 1.0507009873554805, 1.6732632423543772
+    return dy * torch.where(y > 0, torch.full_like(y, scale), y + scale * alpha)
+
+
+# ------------------------------------------------------------------------------------------ head / losses
+def head_forward(logits_low, tables, pitch, activation=1):
+    B, C = logits_low.shape[:2]
+    probs = torch.empty((B, C) + tuple(tables.hi), dtype=torch.float32, device=logits_low.device)
+    call('hno_head_forward', tables.host.data_ptr(), tables.dev.data_ptr(), ptr(logits_low), ptr(probs), B, C, pitch,
+         int(activation), stream_ptr())
+    return probs
+
+
+def head_backward(dprobs, probs, tables, pitch, activation=1):
+    B, C = dprobs.shape[:2]
+    D, H, W = tables.lo
+    shape = (B, C, D, pitch) if pitch != H * W else (B, C, D, H, W)
+    dll = torch.empty(shape, dtype=torch.float32, device=dprobs.device)
+    ws = workspace(tables.head_backward_workspace_bytes(B, C), dprobs.device, 'head')
+    call('hno_head_backward', tables.host.data_ptr(), tables.dev.data_ptr(), ptr(dprobs.contiguous()), ptr(probs),
+         ptr(dll), ptr(ws), B, C, pitch, int(activation), stream_ptr())
+    return dll
+
+
+class HeadUpsample(torch.autograd.Function):
+    """probs = softmax(trilinear(logits_low)) (activation=1) or just the interpolation (activation=0)."""
+
+    @staticmethod
+    def forward(ctx, logits_low, tables, activation):
+        logits_low = logits_low.contiguous()
+        pitch = _geom(logits_low)[2]
+        probs = head_forward(logits_low, tables, pitch, activation)
+        ctx.save_for_backward(probs)
+        ctx.cfg = (tables, pitch, activation)
+        return probs
+
+    @staticmethod
+    def backward(ctx, dprobs):
+        (probs,) = ctx.saved_tensors
+        tables, pitch, activation = ctx.cfg
+        return head_backward(dprobs, probs, tables, pitch, activation), None, None
+
+
+LOSS_KINDS = {'DiceLoss': 0, 'PCCLoss': 1}
+
+
+class ProbabilityLoss(torch.autograd.Function):
+    """DiceLoss / PCCLoss on probabilities and one-hot float targets (reference nets/custom_losses.py)."""
+
+    @staticmethod
+    def forward(ctx, y_pred, y_true, kind):
+        _require_cuda(y_pred, 'y_pred')
+        y_pred = y_pred.contiguous()
+        y_true = y_true.contiguous().to(torch.float32)
+        B, C = y_pred.shape[:2]
+        N = _flat_s(y_pred)
+        loss = torch.empty((1,), dtype=torch.float32, device=y_pred.device)
+        coef = torch.empty((B * C * 3,), dtype=torch.float32, device=y_pred.device)
+        ws = workspace(_lib.load().hno_loss_workspace_bytes(B, C), y_pred.device, 'loss')
+        call('hno_loss_forward', ptr(y_pred), ptr(y_true), ptr(loss), ptr(coef), ptr(ws), B, C, N, int(kind),
+             stream_ptr())
+        ctx.save_for_backward(y_pred, y_true, coef)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError('hno_b200: losses do not provide a gradient w.r.t. y_true')
+        y_pred, y_true, coef = ctx.saved_tensors
+        B, C = y_pred.shape[:2]
+        N = _flat_s(y_pred)
+        dyp = torch.empty_like(y_pred)
+        g = g.reshape(1).to(torch.float32).contiguous()
+        call('hno_loss_backward', ptr(y_pred), ptr(y_true), ptr(coef), ptr(g), ptr(dyp), B, C, N, stream_ptr())
+        return dyp, None, None
+
+
+def head_loss_forward(logits_low, labels, tables, pitch, kind):
+    """Fused head + loss on uint8 labels: returns (loss[1], coef)."""
+    B, C = logits_low.shape[:2]
+    dev = logits_low.device
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    coef = torch.empty((B * C * 3,), dtype=torch.float32, device=dev)
+    ws = workspace(tables.head_backward_workspace_bytes(B, C), dev, 'head')
+    call('hno_head_loss_forward', tables.host.data_ptr(), tables.dev.data_ptr(), ptr(logits_low), ptr(labels),
+         ptr(loss), ptr(coef), ptr(ws), B, C, pitch, int(kind), stream_ptr())
+    return loss, coef
+
+
+def head_loss_backward(logits_low, labels, coef, grad_loss, tables, pitch):
+    B, C = logits_low.shape[:2]
+    dll = torch.empty_like(logits_low)
+    ws = workspace(tables.head_backward_workspace_bytes(B, C), logits_low.device, 'head')
+    call('hno_head_loss_backward', tables.host.data_ptr(), tables.dev.data_ptr(), ptr(logits_low), ptr(labels),
+         ptr(coef), ptr(grad_loss), ptr(dll), ptr(ws), B, C, pitch, stream_ptr())
+    return dll
+
+
+__all__ = ['dht3_forward', 'dht3_adjoint', 'TruncatedDHT', 'TruncatedIDHT', 'pwconv_forward', 'pwconv_backward',
+           'PointwiseConv', 'HartleyConv', 'stem_forward', 'stem_backward', 'StemConv', 'head_forward',
+           'head_backward', 'HeadUpsample', 'ProbabilityLoss', 'head_loss_forward', 'head_loss_backward',
+           'get_crop_plan', 'get_interp_tables', 'workspace', 'LOSS_KINDS']

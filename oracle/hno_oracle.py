@@ -1,0 +1,290 @@
+"""CPU oracle for the HNOSeg-XS spectral hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a functional restatement, in plain PyTorch CPU ops (fp32 or fp64), of what the reference
+(IBM/multimodal-3d-image-segmentation, read-only at /root/reference in the build container) computes
+on this path.  It exists so that the CUDA kernels can be checked on a GPU box where the reference is
+not available.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+may import it; the product package never does (it has no CPU path at all).
+
+Pinning: the reference ships no tests, golden vectors or fixtures for this path;
+its only known answer is the 28,248 parameter count (README.md:57-63).  The oracle is therefore pinned
+against OUTPUTS OF THE REFERENCE ITSELF: oracle/make_golden.py imports /root/reference/nets in the build
+container, runs both, asserts agreement and writes small fixtures to tests/golden/, which
+tests/test_oracle_golden.py replays everywhere.  The arithmetic underneath (torch.fft, conv) lives in
+PyTorch (unpinned in the reference's pyproject.toml:20; 2.11.0+cu128 here).
+
+Each function cites the reference lines it restates.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SELU_ALPHA = 1.6732632423543772
+SELU_SCALE = 1.0507009873554805
+
+
+# ------------------------------------------------------------------------------------------------
+# Discrete Hartley transform                                      nets/dht.py:16-36
+# ------------------------------------------------------------------------------------------------
+def dhtn(x, dims=(-3, -2, -1), inverse=False):
+    """H = Re(F) - Im(F) of the complex DFT over `dims`; forward carries 1/N, inverse is unscaled."""
+    spec = torch.fft.fftn(x, dim=dims, norm='backward' if inverse else 'forward')
+    return spec.real - spec.imag
+
+
+def cas_matrix(n, ks):
+    """Dense 1-D kernel cos+sin(2*pi*k*i/n) for the listed frequencies, fp64 numpy [len(ks), n]."""
+    k = np.asarray(ks, dtype=np.int64)[:, None]
+    i = np.arange(n, dtype=np.int64)[None, :]
+    ang = 2.0 * np.pi * ((k * i) % n) / n
+    return np.cos(ang) + np.sin(ang)
+
+
+def dht3_dense(x, klists, scale):
+    """Direct O(N * modes) evaluation of the NON-separable 3-D DHT rows (definition in SURVEY.md 7.3):
+    Z[kd,kh,kw] = scale * sum x[d,h,w] cas(2 pi (kd d/D + kh h/H + kw w/W)).  fp64 numpy, small sizes only.
+    cas(a+b+c) is expanded through cos/sin of the per-axis angles."""
+    x = np.asarray(x, dtype=np.float64)
+    D, H, W = x.shape[-3:]
+    cs = []
+    for n, ks in zip((D, H, W), klists):
+        k = np.asarray(ks, dtype=np.int64)[:, None]
+        i = np.arange(n, dtype=np.int64)[None, :]
+        ang = 2.0 * np.pi * ((k * i) % n) / n
+        cs.append((np.cos(ang), np.sin(ang)))
+    (cd, sd), (ch, sh), (cw, sw) = cs
+
+    def proj(fd, fh, fw):
+        return np.einsum('...dhw,ad,bh,cw->...abc', x, fd, fh, fw, optimize=True)
+
+    cos_part = proj(cd, ch, cw) - proj(cd, sh, sw) - proj(sd, ch, sw) - proj(sd, sh, cw)
+    sin_part = proj(sd, ch, cw) + proj(cd, sh, cw) + proj(cd, ch, sw) - proj(sd, sh, sw)
+    return scale * (cos_part + sin_part)
+
+
+def clamp_modes(modes, spatial):
+    """nets/hnosegxs.py:382-387: a mode count that does not fit twice into the axis becomes size // 2."""
+    return tuple(s // 2 if 2 * m > s else m for m, s in zip(modes, spatial))
+
+
+def corner_indices(n, m):
+    """Retained frequencies of one axis in output order: the low block then the high block
+    (nets/hnosegxs.py:393-410 slices [:m] and [-m:] and concatenates low first)."""
+    return list(range(m)) + list(range(n - m, n))
+
+
+def transform_crop(x, modes):
+    """TransformCrop.forward for 5-D input (nets/hnosegxs.py:378-410)."""
+    spatial = x.shape[2:]
+    modes = clamp_modes(modes, spatial)
+    spec = dhtn(x)
+    for axis, (n, m) in enumerate(zip(spatial, modes)):
+        idx = torch.tensor(corner_indices(n, m), dtype=torch.long)
+        spec = spec.index_select(2 + axis, idx)
+    return spec
+
+
+def pad_inverse(z, spatial):
+    """PadInverse.forward (nets/hnosegxs.py:454-494): mode counts are inferred as shape // 2, the corners
+    are scattered into a zero spectrum of the target size, then the unnormalised inverse DHT is taken."""
+    modes = tuple(s // 2 for s in z.shape[2:])
+    assert all(n >= 2 * m for n, m in zip(spatial, modes))
+    full = z
+    for axis, (n, m) in enumerate(zip(spatial, modes)):
+        shape = list(full.shape)
+        shape[2 + axis] = n
+        grown = torch.zeros(shape, dtype=z.dtype)
+        idx = torch.tensor(corner_indices(n, m), dtype=torch.long)
+        grown.index_copy_(2 + axis, idx, full)
+        full = grown
+    return dhtn(full, inverse=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# Hartley operator on already-cropped modes                      nets/hartley_operator.py:287-333
+# ------------------------------------------------------------------------------------------------
+def reverse_modes(t):
+    """get_reverse (hartley_operator.py:320-333): index j -> (n - j) mod n on the last three axes."""
+    for axis in (-3, -2, -1):
+        n = t.shape[axis]
+        idx = torch.tensor([(n - j) % n for j in range(n)], dtype=torch.long)
+        t = t.index_select(axis, idx)
+    return t
+
+
+def hartley_mix(z, weight):
+    """HartleyOperator._call3d_notransform (hartley_operator.py:287-299, 302-317)."""
+    if weight.ndim == 2:  # shared: one (O, I) matrix for every mode
+        return torch.einsum('oi,bidhw->bodhw', weight, z)
+    zr, wr = reverse_modes(z), reverse_modes(weight)
+    even = torch.einsum('oidhw,bidhw->bodhw', weight, z + zr)
+    odd = torch.einsum('oidhw,bidhw->bodhw', wr, z - zr)
+    return 0.5 * (even + odd)
+
+
+def selu(x):
+    return F.selu(x)
+
+
+def pointwise(x, weight, bias=None):
+    """Conv3d with a 1x1x1 kernel (nets/nets_utils.py:162-163); weight (O, I, 1, 1, 1) or (O, I)."""
+    w = weight.reshape(weight.shape[0], weight.shape[1])
+    y = torch.einsum('oi,bidhw->bodhw', w, x)
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1, 1)
+    return y
+
+
+def hartley_operator_with_transform(x, weight, modes, bias=None):
+    """HartleyOperator._call3d, shared weights (hartley_operator.py:168-271): DHT, mix the corners, pad,
+    (+bias), SELU in the frequency domain, inverse DHT."""
+    assert weight.ndim == 2
+    spatial = x.shape[2:]
+    z = hartley_mix(transform_crop(x, modes), weight)
+    modes = tuple(s // 2 for s in z.shape[2:])
+    full = z
+    for axis, (n, m) in enumerate(zip(spatial, modes)):
+        shape = list(full.shape)
+        shape[2 + axis] = n
+        grown = torch.zeros(shape, dtype=z.dtype)
+        grown.index_copy_(2 + axis, torch.tensor(corner_indices(n, m)), full)
+        full = grown
+    if bias is not None:
+        full = full + bias
+    return dhtn(selu(full), inverse=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# HNOSeg-XS                                                       nets/hnosegxs.py
+# ------------------------------------------------------------------------------------------------
+def xs_block(x, sd, prefix, num_convs, modes):
+    """HNOXSBlock.forward (hnosegxs.py:253-279) with NeuralOperatorBlock (:307-329) inlined."""
+    key = prefix + 'mapping_conv.op.weight'
+    if key in sd:
+        x = selu(pointwise(x, sd[key], sd[prefix + 'mapping_conv.op.bias']))
+    skip = x
+    z = transform_crop(x, modes)
+    for j in range(num_convs):
+        z = selu(hartley_mix(z, sd[f'{prefix}conv_blocks.{j}.op.weight']) + z)
+    y = selu(pad_inverse(z, x.shape[2:]))
+    key = prefix + 'conv_concat.op.weight'
+    if key in sd:
+        y = selu(pointwise(torch.cat([y, skip], dim=1), sd[key], sd[prefix + 'conv_concat.op.bias']))
+    else:
+        y = y + skip
+    return y
+
+
+def center_padcrop(x, target):
+    """spatial_padcrop (nets/nets_utils.py:22-99): symmetric pad/crop, the odd voxel goes to the upper side."""
+    for axis, t in enumerate(target):
+        n = x.shape[2 + axis]
+        if t > n:
+            lo = (t - n) // 2
+            pad = [0, 0] * (x.ndim - 2)
+            pos = (x.ndim - 3 - axis) * 2
+            pad[pos], pad[pos + 1] = lo, t - n - lo
+            x = F.pad(x, pad)
+        elif t < n:
+            lo = (n - t) // 2
+            x = x.narrow(2 + axis, lo, t)
+    return x
+
+
+def hnosegxs_forward(sd, x, num_transform_blocks, num_modes, use_resize=True, use_unet_skip=True,
+                     softmax=True, return_logits=False):
+    """HNOSegXS.forward (hnosegxs.py:145-182) driven by a reference-layout state_dict."""
+    image_size = x.shape[2:]
+    if use_resize:  # Conv3d(k=2, s=2, p=1) + SELU                         hnosegxs.py:102-105,150-151
+        x = selu(F.conv3d(x, sd['conv_in.op.weight'], sd['conv_in.op.bias'], stride=2, padding=1))
+    x = selu(pointwise(x, sd['conv1.op.weight'], sd['conv1.op.bias']))
+    nb = len(num_transform_blocks)
+    stash = {}
+    for i, n_convs in enumerate(num_transform_blocks):
+        if use_unet_skip and i > nb // 2:                                   # hnosegxs.py:161-162
+            x = torch.cat([x, stash[nb - 1 - i]], dim=1)
+        x = xs_block(x, sd, f'layers.{i}.', n_convs, num_modes)
+        if use_unet_skip and i < nb // 2:                                   # hnosegxs.py:168-169
+            stash[i] = x
+    if use_resize:
+        x = F.interpolate(x, size=tuple(image_size), mode='trilinear')     # hnosegxs.py:174-176
+    logits = center_padcrop(pointwise(x, sd['conv_out.weight']), image_size)  # :178-179
+    out = torch.softmax(logits, dim=1) if softmax else logits
+    return (out, logits) if return_logits else out
+
+
+# ------------------------------------------------------------------------------------------------
+# Losses                                                          nets/custom_losses.py
+# ------------------------------------------------------------------------------------------------
+def to_categorical(y, num_classes):
+    """experiments/utils.py:74-97: (B,1,D,H,W) integer labels -> (B,C,D,H,W) one-hot float32."""
+    assert y.shape[1] == 1
+    onehot = F.one_hot(y[:, 0].long(), num_classes)
+    return onehot.movedim(-1, 1).to(torch.float32)
+
+
+def dice_loss(y_pred, y_true):
+    """custom_losses.py:73-111."""
+    dims = tuple(range(2, y_true.ndim))
+    inter = (y_true * y_pred).sum(dims)
+    union = (y_true + y_pred).sum(dims)
+    return (1 - 2.0 * inter / (union + 1e-7)).mean()
+
+
+def pcc_loss(y_pred, y_true):
+    """custom_losses.py:17-70."""
+    dims = tuple(range(2, y_true.ndim))
+    t = y_true - y_true.mean(dims, keepdim=True)
+    p = y_pred - y_pred.mean(dims, keepdim=True)
+    r = (t * p).sum(dims) / torch.sqrt((t * t).sum(dims) * (p * p).sum(dims) + 1e-7)
+    return (1 - (r + 1) * 0.5).mean()
+
+
+LOSSES = {'DiceLoss': dice_loss, 'PCCLoss': pcc_loss}
+
+
+# ------------------------------------------------------------------------------------------------
+# Parameters                                                      nets/hnosegxs.py:95-143, nets_utils.py:102-117
+# ------------------------------------------------------------------------------------------------
+def init_state_dict(in_channels, out_channels, filters, num_transform_blocks, num_modes, weights_type='shared',
+                    seed=0, dtype=torch.float32):
+    """Random SNN-style parameters with the reference's key names and shapes (kaiming-normal 'linear'
+    weights, bias ~ U(-1e-3, 1e-3)).  The draws are NOT RNG-compatible with the reference constructors;
+    parity tests always copy one state_dict into both implementations."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, o, i, k=1, bias=True):
+        fan_in = i * k ** 3
+        sd[name + 'weight'] = torch.randn((o, i, k, k, k), generator=g, dtype=dtype) / math.sqrt(fan_in)
+        if bias:
+            sd[name + 'bias'] = (torch.rand((o,), generator=g, dtype=dtype) * 2 - 1) * 1e-3
+
+    conv('conv_in.op.', filters, in_channels, 2)
+    conv('conv1.op.', filters, filters)
+    nb = len(num_transform_blocks)
+    for i, n_convs in enumerate(num_transform_blocks):
+        pre = f'layers.{i}.'
+        if i > nb // 2:
+            conv(pre + 'mapping_conv.op.', filters, 2 * filters)
+        for j in range(n_convs):
+            if weights_type == 'shared':
+                shape, fan_in = (filters, filters), filters
+            else:
+                block = tuple(2 * m for m in num_modes)
+                shape, fan_in = (filters, filters) + block, filters * int(np.prod(block))
+            sd[f'{pre}conv_blocks.{j}.op.weight'] = torch.randn(shape, generator=g, dtype=dtype) / math.sqrt(fan_in)
+        conv(pre + 'conv_concat.op.', filters, 2 * filters)
+    sd['conv_out.weight'] = torch.randn((out_channels, filters, 1, 1, 1), generator=g, dtype=dtype) / math.sqrt(filters)
+    return sd
+
+
+def train_step(sd, x, labels, num_transform_blocks, num_modes, loss='DiceLoss'):
+    """One step of experiments/train_test.py:146-171 without the optimizer: returns (loss, grads by key)."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    probs = hnosegxs_forward(params, x, num_transform_blocks, num_modes)
+    value = LOSSES[loss](probs, to_categorical(labels, probs.shape[1]).to(probs.dtype))
+    grads = torch.autograd.grad(value, list(params.values()))
+    return value.detach(), dict(zip(params.keys(), grads))

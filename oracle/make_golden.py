@@ -1,0 +1,220 @@
+"""Pins oracle/hno_oracle.py against the REAL reference and writes the fixtures under tests/golden/.
+
+Run in the build container only (it imports /root/reference, which does not exist on the GPU box):
+
+    python oracle/make_golden.py [--full]
+
+For every case it (1) runs the reference module, (2) runs the oracle restatement on the same inputs and
+parameters, (3) asserts they agree to fp32 round-off, (4) stores inputs + reference outputs as a small
+.npz.  tests/test_oracle_golden.py replays the fixtures against the oracle; the GPU tests replay them
+against the CUDA path.  --full additionally runs the BASELINE-size model (1x4x240x240x155) and stores the
+reference logits at 8192 sampled voxels.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+
+import nets as ref  # noqa: E402  (the reference package)
+from nets import hnosegxs as ref_xs  # noqa: E402
+from nets.hartley_operator import HartleyOperator  # noqa: E402
+from nets import custom_losses as ref_losses  # noqa: E402
+from nets.dht import dhtn as ref_dhtn  # noqa: E402
+
+from oracle import hno_oracle as orc  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def np_sd(module):
+    return {k: v.detach().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def check(name, a, b, tol=2e-5):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+    print(f'  {name:42s} max-rel-err {err:.2e}')
+    assert err < tol, (name, err)
+
+
+def save(name, **arrays):
+    path = os.path.join(GOLDEN, name + '.npz')
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})
+    print(f'wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)')
+
+
+def case_dht():
+    torch.manual_seed(11)
+    x = torch.randn(2, 3, 9, 8, 7)
+    fwd = ref_dhtn(x, dim=(-3, -2, -1))
+    inv = ref_dhtn(x, dim=(-3, -2, -1), is_inverse=True)
+    check('dhtn forward', orc.dhtn(x), fwd)
+    check('dhtn inverse', orc.dhtn(x, inverse=True), inv)
+    kl = [list(range(9)), list(range(8)), list(range(7))]
+    check('dense cas definition', orc.dht3_dense(x.numpy(), kl, 1.0 / (9 * 8 * 7)), fwd, 1e-6)
+    out = {'x': x.numpy(), 'fwd': fwd.numpy(), 'inv': inv.numpy()}
+    for tag, shape, modes in (('a', (1, 2, 9, 8, 7), (2, 3, 3)), ('b', (2, 2, 12, 10, 9), (10, 14, 14)),
+                              ('c', (1, 3, 16, 11, 10), (4, 3, 5))):
+        xx = torch.randn(*shape)
+        tc = ref_xs.TransformCrop(modes, 5)
+        z = tc(xx)
+        check(f'TransformCrop {shape} {modes}', orc.transform_crop(xx, modes), z)
+        m = orc.clamp_modes(modes, shape[2:])
+        kl = [orc.corner_indices(n, mm) for n, mm in zip(shape[2:], m)]
+        check(f'TransformCrop dense {tag}', orc.dht3_dense(xx.numpy(), kl, 1.0 / np.prod(shape[2:])), z, 1e-6)
+        pi = ref_xs.PadInverse(5)
+        y = pi(z, shape[2:])
+        check(f'PadInverse {shape}', orc.pad_inverse(z, shape[2:]), y)
+        out.update({f'x_{tag}': xx.numpy(), f'z_{tag}': z.numpy(), f'y_{tag}': y.numpy(),
+                    f'modes_{tag}': np.array(modes)})
+    save('dht', **out)
+
+
+def case_operator():
+    torch.manual_seed(12)
+    out = {}
+    z = torch.randn(2, 8, 4, 6, 6)
+    for wt in ('shared', 'individual'):
+        op = HartleyOperator(8, 8, (2, 3, 3), weights_type=wt, use_transform=False)
+        torch.nn.init.normal_(op.weight, std=0.3)
+        y = op(z)
+        check(f'HartleyOperator notransform {wt}', orc.hartley_mix(z, op.weight.detach()), y.detach())
+        g = torch.randn_like(y)
+        zz = z.clone().requires_grad_(True)
+        gy = torch.autograd.grad(op(zz), [zz, op.weight], g)
+        out.update({f'w_{wt}': op.weight.detach().numpy(), f'y_{wt}': y.detach().numpy(), f'g_{wt}': g.numpy(),
+                    f'dz_{wt}': gy[0].numpy(), f'dw_{wt}': gy[1].numpy()})
+    out['z'] = z.numpy()
+    x = torch.randn(1, 8, 9, 8, 7)
+    op = HartleyOperator(8, 8, (2, 3, 3), weights_type='shared', use_transform=True)
+    torch.nn.init.normal_(op.weight, std=0.3)
+    y = op(x)
+    check('HartleyOperator with transform', orc.hartley_operator_with_transform(x, op.weight.detach(), (2, 3, 3)),
+          y.detach())
+    out.update({'x_t': x.numpy(), 'w_t': op.weight.detach().numpy(), 'y_t': y.detach().numpy()})
+    save('operator', **out)
+
+
+def case_block():
+    torch.manual_seed(13)
+    out = {}
+    for tag, cin in (('plain', 8), ('mapped', 16)):
+        blk = ref_xs.HNOXSBlock(2, cin, 8, (2, 3, 3))
+        blk.apply(ref.hnosegxs.init_weights_for_snn)
+        x = torch.randn(2, cin, 9, 8, 7)
+        y = blk(x)
+        sd = {('layers.0.' + k): v for k, v in blk.state_dict().items()}
+        check(f'HNOXSBlock {tag}', orc.xs_block(x, sd, 'layers.0.', 2, (2, 3, 3)), y.detach())
+        out.update({f'x_{tag}': x.numpy(), f'y_{tag}': y.detach().numpy()})
+        out.update({f'sd_{tag}/{k}': v.numpy() for k, v in sd.items()})
+    save('block', **out)
+
+
+def small_model(weights_type='shared'):
+    torch.manual_seed(14)
+    cfg = dict(in_channels=2, out_channels=3, filters=8, num_transform_blocks=[1, 2, 1, 2, 1, 2], num_modes=(2, 3, 3),
+               weights_type=weights_type)
+    model = ref.HNOSegXS(**cfg)
+    return cfg, model
+
+
+def case_model():
+    out = {}
+    for wt in ('shared', 'individual'):
+        cfg, model = small_model(wt)
+        torch.manual_seed(15)
+        x = torch.randn(2, 2, 18, 16, 13)
+        labels = torch.randint(0, 3, (2, 1, 18, 16, 13))
+        logits = {}
+        hook = model.conv_out.register_forward_hook(lambda m, i, o: logits.__setitem__('v', o.detach()))
+        probs = model(x)
+        hook.remove()
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        o_probs, o_logits = orc.hnosegxs_forward(sd, x, cfg['num_transform_blocks'], cfg['num_modes'],
+                                                 return_logits=True)
+        check(f'HNOSegXS {wt} probs', o_probs, probs.detach())
+        check(f'HNOSegXS {wt} logits', o_logits, logits['v'])
+        out.update({f'{wt}/x': x.numpy(), f'{wt}/labels': labels.numpy().astype(np.uint8),
+                    f'{wt}/probs': probs.detach().numpy(), f'{wt}/logits': logits['v'].numpy()})
+        out.update({f'{wt}/sd/{k}': v.numpy() for k, v in sd.items()})
+        onehot = torch.zeros(2, 3, 18, 16, 13).scatter_(1, labels, 1.0)
+        check('to_categorical', orc.to_categorical(labels, 3), onehot, 1e-7)
+        for lname in ('DiceLoss', 'PCCLoss'):
+            model.zero_grad()
+            loss = getattr(ref_losses, lname)()(model(x), onehot)
+            loss.backward()
+            grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+            o_loss, o_grads = orc.train_step(sd, x, labels, cfg['num_transform_blocks'], cfg['num_modes'], lname)
+            check(f'{wt} {lname} value', o_loss, loss.detach(), 1e-6)
+            for k in grads:
+                check(f'{wt} {lname} grad {k}', o_grads[k], grads[k], 2e-4)
+            out[f'{wt}/{lname}/loss'] = loss.detach().numpy()
+            out.update({f'{wt}/{lname}/grad/{k}': v.numpy() for k, v in grads.items()})
+    save('model_small', **out)
+
+
+def case_losses():
+    torch.manual_seed(16)
+    p = torch.softmax(torch.randn(2, 4, 6, 5, 7), dim=1).requires_grad_(True)
+    t = orc.to_categorical(torch.randint(0, 4, (2, 1, 6, 5, 7)), 4)
+    out = {'p': p.detach().numpy(), 't': t.numpy()}
+    for lname in ('DiceLoss', 'PCCLoss'):
+        loss = getattr(ref_losses, lname)()(p, t)
+        (g,) = torch.autograd.grad(loss, p)
+        check(f'{lname}', orc.LOSSES[lname](p.detach(), t), loss.detach(), 1e-6)
+        out[f'{lname}/loss'] = loss.detach().numpy()
+        out[f'{lname}/grad'] = g.numpy()
+    save('losses', **out)
+
+
+def case_full():
+    """BASELINE config 1: HNOSegXS(4,4,24,[3]*8,(10,14,14)) on one 1x4x240x240x155 volume."""
+    torch.manual_seed(0)
+    model = ref.HNOSegXS(4, 4, 24, [3] * 8, (10, 14, 14))
+    n_params = sum(p.numel() for p in model.parameters())
+    assert n_params == 28248, n_params  # README.md:57-63
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, 4, 240, 240, 155, generator=g)
+    logits = {}
+    model.conv_out.register_forward_hook(lambda m, i, o: logits.__setitem__('v', o.detach()))
+    with torch.no_grad():
+        probs = model(x)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        o_probs, o_logits = orc.hnosegxs_forward(sd, x, [3] * 8, (10, 14, 14), return_logits=True)
+    lg = logits['v']
+    rel = ((o_logits - lg).norm() / lg.norm()).item()
+    agree = (o_logits.argmax(1) == lg.argmax(1)).float().mean().item()
+    print(f'  full size: oracle vs reference logits rel-L2 {rel:.2e}, argmax agreement {agree:.7f}')
+    assert rel < 1e-5 and agree > 0.99999
+    gi = torch.Generator().manual_seed(77)
+    idx = torch.randint(0, 240 * 240 * 155, (8192,), generator=gi)
+    flat = lg.reshape(4, -1)
+    out = {'idx': idx.numpy(), 'logits_at_idx': flat[:, idx].numpy(), 'probs_at_idx': probs.reshape(4, -1)[:, idx].numpy(),
+           'logits_std': np.float32(lg.std().item()), 'logits_norm': np.float32(lg.norm().item()),
+           'argmax_hist': np.bincount(lg.argmax(1).flatten().numpy(), minlength=4)}
+    out.update({f'sd/{k}': v.numpy() for k, v in sd.items()})
+    save('model_full_probe', **out)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--full', action='store_true')
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(8)
+    case_dht()
+    case_operator()
+    case_block()
+    case_losses()
+    case_model()
+    if args.full:
+        case_full()
+    print('all oracle-vs-reference checks passed')

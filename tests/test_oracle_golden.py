@@ -1,0 +1,93 @@
+"""The oracle restatement replayed against fixtures produced by the real reference (oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import hno_oracle as orc
+
+
+def _load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + '.npz')))
+
+
+def _close(a, b, tol=2e-5):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+    assert err < tol, err
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def test_dht_fixtures(golden_dir):
+    g = _load(golden_dir, 'dht')
+    x = torch.from_numpy(g['x'])
+    _close(orc.dhtn(x), g['fwd'])
+    _close(orc.dhtn(x, inverse=True), g['inv'])
+    for tag in 'abc':
+        xx = torch.from_numpy(g[f'x_{tag}'])
+        modes = tuple(int(v) for v in g[f'modes_{tag}'])
+        z = orc.transform_crop(xx, modes)
+        _close(z, g[f'z_{tag}'])
+        _close(orc.pad_inverse(torch.from_numpy(g[f'z_{tag}']), xx.shape[2:]), g[f'y_{tag}'])
+        m = orc.clamp_modes(modes, xx.shape[2:])
+        kl = [orc.corner_indices(n, mm) for n, mm in zip(xx.shape[2:], m)]
+        _close(orc.dht3_dense(g[f'x_{tag}'], kl, 1.0 / np.prod(xx.shape[2:])), g[f'z_{tag}'], 1e-6)
+
+
+def test_operator_fixtures(golden_dir):
+    g = _load(golden_dir, 'operator')
+    z = torch.from_numpy(g['z'])
+    for wt in ('shared', 'individual'):
+        w = torch.from_numpy(g[f'w_{wt}']).requires_grad_(True)
+        zz = z.clone().requires_grad_(True)
+        y = orc.hartley_mix(zz, w)
+        _close(y.detach(), g[f'y_{wt}'])
+        dz, dw = torch.autograd.grad(y, [zz, w], torch.from_numpy(g[f'g_{wt}']))
+        _close(dz, g[f'dz_{wt}'])
+        _close(dw, g[f'dw_{wt}'])
+    _close(orc.hartley_operator_with_transform(torch.from_numpy(g['x_t']), torch.from_numpy(g['w_t']), (2, 3, 3)),
+           g['y_t'])
+
+
+def test_block_fixtures(golden_dir):
+    g = _load(golden_dir, 'block')
+    for tag in ('plain', 'mapped'):
+        sd = _sd(g, f'sd_{tag}/')
+        y = orc.xs_block(torch.from_numpy(g[f'x_{tag}']), sd, 'layers.0.', 2, (2, 3, 3))
+        _close(y, g[f'y_{tag}'])
+
+
+def test_loss_fixtures(golden_dir):
+    g = _load(golden_dir, 'losses')
+    for name in ('DiceLoss', 'PCCLoss'):
+        p = torch.from_numpy(g['p']).requires_grad_(True)
+        loss = orc.LOSSES[name](p, torch.from_numpy(g['t']))
+        _close(loss.detach(), g[f'{name}/loss'], 1e-6)
+        _close(torch.autograd.grad(loss, p)[0], g[f'{name}/grad'], 1e-5)
+
+
+def test_small_model_fixtures(golden_dir):
+    g = _load(golden_dir, 'model_small')
+    blocks, modes = [1, 2, 1, 2, 1, 2], (2, 3, 3)
+    for wt in ('shared', 'individual'):
+        sd = _sd(g, f'{wt}/sd/')
+        x = torch.from_numpy(g[f'{wt}/x'])
+        probs, logits = orc.hnosegxs_forward(sd, x, blocks, modes, return_logits=True)
+        _close(probs, g[f'{wt}/probs'])
+        _close(logits, g[f'{wt}/logits'])
+        labels = torch.from_numpy(g[f'{wt}/labels'].astype(np.int64))
+        for lname in ('DiceLoss', 'PCCLoss'):
+            loss, grads = orc.train_step(sd, x, labels, blocks, modes, lname)
+            _close(loss, g[f'{wt}/{lname}/loss'], 1e-6)
+            for k, v in grads.items():
+                _close(v, g[f'{wt}/{lname}/grad/{k}'], 2e-4)
+
+
+def test_param_count_known_answer():
+    # the reference's only published known answer: README.md:57-63
+    sd = orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14))
+    assert sum(v.numel() for v in sd.values()) == 28248
