@@ -1,0 +1,103 @@
+"""Whole-model parity of the CUDA path against fixtures recorded from the real reference and the live oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hno_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('wt', ['shared', 'individual'])
+def test_small_model_against_reference_fixture(cuda, golden_dir, wt):
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'model_small.npz')))
+    model = nets.HNOSegXS(2, 3, 8, [1, 2, 1, 2, 1, 2], (2, 3, 3), weights_type=wt, device=cuda)
+    model.load_state_dict(_sd(g, f'{wt}/sd/'))
+    x = torch.from_numpy(g[f'{wt}/x']).to(cuda)
+    labels = torch.from_numpy(g[f'{wt}/labels'].astype(np.int64)).to(cuda)
+    with torch.no_grad():
+        probs = model(x)
+        logits = model.forward_logits(x)
+        probs_mod = model.forward_modular(x)
+    assert rel(probs, g[f'{wt}/probs']) < 1e-5
+    assert rel(logits, g[f'{wt}/logits']) < 1e-5
+    assert rel(probs_mod, g[f'{wt}/probs']) < 1e-5
+    onehot = orc.to_categorical(labels.cpu(), 3).to(cuda)
+    for lname in ('DiceLoss', 'PCCLoss'):
+        for path in ('dropin', 'fused', 'modular'):
+            model.zero_grad()
+            if path == 'dropin':  # exactly experiments/train_test.py:159-170
+                loss = getattr(nets.custom_losses, lname)()(model(x), onehot)
+            elif path == 'fused':
+                loss = model.loss(x, labels, lname)
+            else:
+                loss = getattr(nets.custom_losses, lname)()(model.forward_modular(x), onehot)
+            loss.backward()
+            assert abs(float(loss) - float(g[f'{wt}/{lname}/loss'])) < 2e-6, (lname, path)
+            for k, p in model.named_parameters():
+                ref = g[f'{wt}/{lname}/grad/{k}']
+                assert rel(p.grad, ref) < 2e-4, (lname, path, k, rel(p.grad, ref))
+
+
+def test_full_size_forward_against_reference_probe(cuda, golden_dir):
+    """BASELINE config 1: logits rel-err <= 1e-3 and >= 99.99 % identical argmax voxels (north_star tolerance)."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'model_full_probe.npz')))
+    sd = _sd(g, 'sd/')
+    model = nets.HNOSegXS(4, 4, 24, [3] * 8, (10, 14, 14), device=cuda)
+    model.load_state_dict(sd)
+    x = torch.randn(1, 4, 240, 240, 155, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        logits = model.forward_logits(x.to(cuda)).cpu()
+        probs = model(x.to(cuda)).cpu()
+    idx = torch.from_numpy(g['idx'])
+    got = logits.reshape(4, -1)[:, idx]
+    ref = torch.from_numpy(g['logits_at_idx'])
+    r = ((got - ref).norm() / ref.norm()).item()
+    assert r < 1e-3, r
+    assert rel(probs.reshape(4, -1)[:, idx], g['probs_at_idx']) < 1e-3
+    assert (got.argmax(0) == ref.argmax(0)).float().mean().item() >= 0.9999
+    hist = np.bincount(logits.argmax(1).flatten().numpy(), minlength=4)
+    assert np.abs(hist - g['argmax_hist']).sum() <= 2e-4 * hist.sum()
+    # live oracle on the host cores: every voxel
+    with torch.no_grad():
+        _, o_logits = orc.hnosegxs_forward(sd, x, [3] * 8, (10, 14, 14), return_logits=True)
+    r_all = ((logits - o_logits).norm() / o_logits.norm()).item()
+    agree = (logits.argmax(1) == o_logits.argmax(1)).float().mean().item()
+    print(f'full-size logits rel-L2 {r_all:.3e}, argmax agreement {agree:.7f}')
+    assert r_all < 1e-3 and agree >= 0.9999
+
+
+def test_training_step_gradients_against_fp64_oracle(cuda, golden_dir):
+    """BASELINE model on a half-size volume, batch 1: gradients of the fused step against the fp64 oracle."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'model_full_probe.npz')))
+    sd = _sd(g, 'sd/')
+    model = nets.HNOSegXS(4, 4, 24, [3] * 8, (10, 14, 14), device=cuda)
+    model.load_state_dict(sd)
+    x = torch.randn(1, 4, 120, 112, 77, generator=torch.Generator().manual_seed(1234))
+    labels = torch.randint(0, 4, (1, 1, 120, 112, 77), generator=torch.Generator().manual_seed(1235))
+    loss = model.loss(x.to(cuda), labels.to(cuda), 'DiceLoss')
+    loss.backward()
+    sd64 = {k: v.double() for k, v in sd.items()}
+    o_loss, o_grads = orc.train_step(sd64, x.double(), labels, [3] * 8, (10, 14, 14), 'DiceLoss')
+    assert abs(float(loss) - float(o_loss)) < 1e-5
+    flat = torch.cat([p.grad.flatten().cpu().double() for _, p in model.named_parameters()])
+    oflat = torch.cat([o_grads[k].flatten() for k, _ in model.named_parameters()])
+    assert ((flat - oflat).norm() / oflat.norm()).item() < 1e-3
+    for k, p in model.named_parameters():
+        assert rel(p.grad, o_grads[k]) < 5e-3, k

@@ -1,0 +1,307 @@
+"""Parity of every CUDA entry point (called through the C ABI) against the CPU oracle / fp64 torch maths."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hno_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def maxrel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def to_planar(x, pitch):
+    """dense (B,C,D,H,W) -> planar (B,C,D,pitch) with zero padding columns"""
+    B, C, D, H, W = x.shape
+    out = torch.zeros(B, C, D, pitch, dtype=x.dtype, device=x.device)
+    out[..., :H * W] = x.reshape(B, C, D, H * W)
+    return out
+
+
+def from_planar(x, H, W):
+    B, C, D, P = x.shape
+    return x[..., :H * W].reshape(B, C, D, H, W)
+
+
+# ---------------------------------------------------------------------------------------------- DHT
+DHT_CASES = [((9, 8, 7), (2, 3, 3)), ((12, 10, 9), (10, 14, 14)), ((16, 11, 10), (4, 3, 5)), ((5, 5, 5), (1, 2, 1)),
+             ((40, 40, 26), (10, 14, 14)), ((31, 33, 20), (10, 14, 14))]
+
+
+@pytest.mark.parametrize('shape,modes', DHT_CASES)
+@pytest.mark.parametrize('padded', [False, True])
+def test_dht_forward_adjoint(cuda, shape, modes, padded):
+    from multimodal_3d_image_segmentation_b200 import ops
+    from multimodal_3d_image_segmentation_b200.plan import get_crop_plan, plane_pitch
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, *shape, generator=g)
+    plan = get_crop_plan(shape, modes, cuda)
+    n = float(np.prod(shape))
+    z_ref = orc.transform_crop(x.double(), modes)
+    H, W = shape[1:]
+    pitch = plane_pitch(H, W) if padded else None
+    xd = to_planar(x.to(cuda), pitch) if padded else x.to(cuda)
+    z = ops.dht3_forward(xd, plan, 1.0 / n)
+    assert rel(z, z_ref) < 2e-6
+    zz = torch.randn(z_ref.shape, generator=g)
+    y_ref = orc.pad_inverse(zz.double(), shape)
+    y = ops.dht3_adjoint(zz.to(cuda), plan, 1.0, pitch=pitch)
+    if padded:
+        assert float(y[..., H * W:].abs().max()) == 0.0 if pitch > H * W else True
+        y = from_planar(y, H, W)
+    assert rel(y, y_ref) < 2e-6
+    # fused SELU epilogue and accumulate epilogue
+    ys = ops.dht3_adjoint(zz.to(cuda), plan, 1.0, epilogue=2, pitch=pitch)
+    ys = from_planar(ys, H, W) if padded else ys
+    assert rel(ys, F.selu(y_ref)) < 2e-6
+    base = torch.randn(2, 3, *shape, generator=g)
+    acc = to_planar(base.to(cuda), pitch) if padded else base.to(cuda).clone()
+    ops.dht3_adjoint(zz.to(cuda), plan, 0.5, epilogue=1, out=acc)
+    acc = from_planar(acc, H, W) if padded else acc
+    assert rel(acc, base.double() + 0.5 * y_ref) < 2e-6
+
+
+def test_dht_golden_fixtures(cuda, golden_dir):
+    """TransformCrop / PadInverse outputs recorded from the real reference (tests/golden/dht.npz)."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'dht.npz')))
+    for tag in 'abc':
+        x = torch.from_numpy(g[f'x_{tag}']).to(cuda)
+        modes = tuple(int(v) for v in g[f'modes_{tag}'])
+        z = nets.TransformCrop(modes, 5)(x)
+        assert maxrel(z, g[f'z_{tag}']) < 1e-5
+        y = nets.PadInverse(5)(torch.from_numpy(g[f'z_{tag}']).to(cuda), x.shape[2:])
+        assert maxrel(y, g[f'y_{tag}']) < 1e-5
+    x = torch.from_numpy(g['x']).to(cuda)
+    assert maxrel(nets.dhtn(x, dim=(-3, -2, -1)), g['fwd']) < 1e-5
+    assert maxrel(nets.dht3(x, is_inverse=True), g['inv']) < 1e-5
+
+
+def test_dht_autograd(cuda):
+    from multimodal_3d_image_segmentation_b200 import nets
+    shape, modes = (9, 8, 7), (2, 3, 3)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 2, *shape, generator=g)
+    w = torch.randn(1, 2, 4, 6, 6, generator=g)
+    xr = x.double().requires_grad_(True)
+    zr = orc.transform_crop(xr, modes)
+    yr = orc.pad_inverse(zr * zr, shape)
+    (yr * yr).sum().backward()
+    xc = x.to(cuda).requires_grad_(True)
+    z = nets.TransformCrop(modes, 5)(xc)
+    y = nets.PadInverse(5)(z * z, shape)
+    (y * y).sum().backward()
+    assert rel(y, yr) < 5e-6 and rel(xc.grad, xr.grad) < 5e-6
+    del w
+
+
+# ---------------------------------------------------------------------------------------------- pointwise conv
+def _pw_ref(in1, in2, w, b, act, res):
+    x = in1 if in2 is None else torch.cat([in1, in2], 1)
+    y = torch.einsum('oi,bis->bos', w, x)
+    if b is not None:
+        y = y + b.view(1, -1, 1)
+    if res:
+        y = y + in1
+    return F.selu(y) if act else y
+
+
+@pytest.mark.parametrize('ci1,ci2,co,act,res,bias', [(24, 0, 24, 1, True, False), (24, 0, 24, 1, False, True),
+                                                     (24, 24, 24, 1, False, True), (24, 0, 4, 0, False, False),
+                                                     (8, 8, 8, 1, False, True), (8, 0, 3, 0, False, False),
+                                                     (8, 0, 8, 1, True, False), (24, 0, 2, 0, False, False)])
+@pytest.mark.parametrize('S,P,HW', [(1000, 1000, 1000), (3 * 64, 64, 58), (777, 777, 777)])
+def test_pwconv(cuda, ci1, ci2, co, act, res, bias, S, P, HW):
+    from multimodal_3d_image_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    B = 2
+    in1 = torch.randn(B, ci1, S, generator=g)
+    in2 = torch.randn(B, ci2, S, generator=g) if ci2 else None
+    if act:  # in1 plays the role of a SELU output in one of the backward variants
+        in1 = F.selu(in1)
+    w = torch.randn(co, ci1 + ci2, generator=g) / np.sqrt(ci1 + ci2)
+    b = torch.randn(co, generator=g) * 0.1 if bias else None
+    dy = torch.randn(B, co, S, generator=g)
+    live = ((torch.arange(S) % P) < HW).double()
+    r1 = in1.double().requires_grad_(True)
+    r2 = in2.double().requires_grad_(True) if ci2 else None
+    rw = w.double().requires_grad_(True)
+    rb = b.double().requires_grad_(True) if bias else None
+    yr = _pw_ref(r1, r2, rw, rb, act, res)
+    (yr * dy.double() * live).sum().backward()
+    dev = lambda t: None if t is None else t.to(cuda)  # noqa: E731
+    y = ops.pwconv_forward(dev(in1), dev(in2), dev(w), dev(b), act, res)
+    assert rel(y, yr) < 2e-6
+    din1, din2, dw, db = ops.pwconv_backward(dev(dy), y, dev(in1), dev(in2), dev(w), act, res, hw=(P, HW),
+                                             has_bias=bias)
+    assert rel(din1, r1.grad) < 3e-6
+    if ci2:
+        assert rel(din2, r2.grad) < 3e-6
+    assert rel(dw, rw.grad) < 3e-6
+    if bias:
+        assert rel(db, rb.grad) < 3e-6
+    else:
+        assert db is None
+    # accumulate flags + "in1 is a SELU output" flag
+    if act:
+        base1 = torch.randn(B, ci1, S, generator=g).to(cuda)
+        wacc = torch.ones(co, ci1 + ci2, device=cuda)
+        d1, _, dw2, _ = ops.pwconv_backward(dev(dy), y, dev(in1), dev(in2), dev(w), act, res, hw=(P, HW),
+                                            in1_is_selu=True, din1=base1.clone(), dweight=wacc, has_bias=bias,
+                                            accumulate_w=True, need_in2=False)
+        sg = torch.where(in1 > 0, torch.full_like(in1, orc.SELU_SCALE), in1 + orc.SELU_SCALE * orc.SELU_ALPHA).double()
+        assert rel(d1, base1.cpu().double() + r1.grad * sg) < 3e-6
+        assert rel(dw2, rw.grad + 1.0) < 3e-6
+
+
+def test_hartley_conv_golden(cuda, golden_dir):
+    from multimodal_3d_image_segmentation_b200 import ops
+    g = dict(np.load(os.path.join(golden_dir, 'operator.npz')))
+    z = torch.from_numpy(g['z']).to(cuda).requires_grad_(True)
+    w = torch.from_numpy(g['w_individual']).to(cuda).requires_grad_(True)
+    y = ops.HartleyConv.apply(z, w)
+    assert maxrel(y, g['y_individual']) < 1e-5
+    dz, dw = torch.autograd.grad(y, [z, w], torch.from_numpy(g['g_individual']).to(cuda))
+    assert maxrel(dz, g['dz_individual']) < 1e-5 and maxrel(dw, g['dw_individual']) < 1e-5
+    # fused residual + SELU variant against the oracle
+    zr = torch.from_numpy(g['z']).double().requires_grad_(True)
+    wr = torch.from_numpy(g['w_individual']).double().requires_grad_(True)
+    yr = F.selu(orc.hartley_mix(zr, wr) + zr)
+    gg = torch.from_numpy(g['g_individual'])
+    dzr, dwr = torch.autograd.grad(yr, [zr, wr], gg.double())
+    y2 = ops.HartleyConv.apply(z, w, True)
+    dz2, dw2 = torch.autograd.grad(y2, [z, w], gg.to(cuda))
+    assert rel(y2, yr) < 2e-6 and rel(dz2, dzr) < 3e-6 and rel(dw2, dwr) < 3e-6
+
+
+# ---------------------------------------------------------------------------------------------- stem
+@pytest.mark.parametrize('cin,f,shape', [(4, 24, (10, 9, 7)), (2, 8, (18, 16, 13)), (1, 8, (6, 6, 6)), (4, 24, (12, 12, 11))])
+def test_stem(cuda, cin, f, shape):
+    from multimodal_3d_image_segmentation_b200 import ops
+    from multimodal_3d_image_segmentation_b200.plan import plane_pitch
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, cin, *shape, generator=g)
+    w = torch.randn(f, cin, 2, 2, 2, generator=g) / np.sqrt(8 * cin)
+    b = torch.randn(f, generator=g) * 0.1
+    rw = w.double().requires_grad_(True)
+    rb = b.double().requires_grad_(True)
+    yr = F.selu(F.conv3d(x.double(), rw, rb, stride=2, padding=1))
+    D, H, W = yr.shape[2:]
+    assert (D, H, W) == ops.stem_out_shape(shape)
+    dy = torch.randn(yr.shape, generator=g)
+    (yr * dy.double()).sum().backward()
+    for pitch in (None, plane_pitch(H, W)):
+        y = ops.stem_forward(x.to(cuda), w.to(cuda), b.to(cuda), pitch=pitch)
+        yd = from_planar(y, H, W) if pitch else y
+        assert rel(yd, yr) < 2e-6
+        if pitch and pitch > H * W:
+            assert float(y[..., H * W:].abs().max()) == 0.0
+        dpre = ops.selu_backward(dy.to(cuda), yd)
+        dpre = to_planar(dpre, pitch) if pitch else dpre
+        dw, db = ops.stem_backward(dpre, x.to(cuda), f, pitch=pitch)
+        assert rel(dw, rw.grad) < 3e-6 and rel(db, rb.grad) < 3e-6
+
+
+# ---------------------------------------------------------------------------------------------- head + losses
+@pytest.mark.parametrize('lo,hi,C', [((10, 9, 7), (18, 16, 13), 3), ((6, 6, 6), (10, 10, 10), 4), ((7, 6, 5), (12, 11, 9), 2)])
+def test_head_forward_backward(cuda, lo, hi, C):
+    from multimodal_3d_image_segmentation_b200 import ops
+    from multimodal_3d_image_segmentation_b200.plan import get_interp_tables, plane_pitch
+    g = torch.Generator().manual_seed(9)
+    ll = torch.randn(2, C, *lo, generator=g) * 3
+    tables = get_interp_tables(lo, hi, cuda)
+    lr = ll.double().requires_grad_(True)
+    pr = torch.softmax(F.interpolate(lr, size=hi, mode='trilinear'), dim=1)
+    dp = torch.randn(pr.shape, generator=g)
+    (pr * dp.double()).sum().backward()
+    H, W = lo[1:]
+    for pitch in (H * W, plane_pitch(H, W)):
+        lld = to_planar(ll.to(cuda), pitch) if pitch != H * W else ll.to(cuda)
+        probs = ops.head_forward(lld, tables, pitch, 1)
+        assert rel(probs, pr) < 3e-6
+        dll = ops.head_backward(dp.to(cuda), probs, tables, pitch, 1)
+        if pitch != H * W:
+            assert float(dll[..., H * W:].abs().max()) == 0.0
+            dll = from_planar(dll, H, W)
+        assert rel(dll, lr.grad) < 5e-6
+    # interpolation only (output_activation disabled)
+    up = ops.head_forward(ll.to(cuda), tables, H * W, 0)
+    assert rel(up, F.interpolate(ll.double(), size=hi, mode='trilinear')) < 2e-6
+
+
+@pytest.mark.parametrize('name', ['DiceLoss', 'PCCLoss'])
+def test_losses_golden_and_oracle(cuda, golden_dir, name):
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'losses.npz')))
+    p = torch.from_numpy(g['p']).to(cuda).requires_grad_(True)
+    t = torch.from_numpy(g['t']).to(cuda)
+    loss = getattr(nets.custom_losses, name)()(p, t)
+    assert abs(float(loss) - float(g[f'{name}/loss'])) < 2e-6
+    (grad,) = torch.autograd.grad(loss, p)
+    assert maxrel(grad, g[f'{name}/grad']) < 2e-5
+    # larger, ragged case vs the fp64 oracle
+    gen = torch.Generator().manual_seed(10)
+    pp = torch.softmax(torch.randn(2, 4, 33, 31, 29, generator=gen), 1)
+    tt = orc.to_categorical(torch.randint(0, 4, (2, 1, 33, 31, 29), generator=gen), 4)
+    pr = pp.double().requires_grad_(True)
+    lr = orc.LOSSES[name](pr, tt.double())
+    (gr,) = torch.autograd.grad(lr, pr)
+    pc = pp.to(cuda).requires_grad_(True)
+    lc = getattr(nets.custom_losses, name)()(pc, tt.to(cuda))
+    (gc,) = torch.autograd.grad(lc * 3.0, pc)
+    assert abs(float(lc) - float(lr)) < 1e-6 and rel(gc, 3.0 * gr) < 1e-5
+
+
+@pytest.mark.parametrize('kind', ['DiceLoss', 'PCCLoss'])
+def test_fused_head_loss(cuda, kind):
+    from multimodal_3d_image_segmentation_b200 import ops
+    from multimodal_3d_image_segmentation_b200.plan import get_interp_tables, plane_pitch
+    lo, hi, C = (10, 9, 7), (18, 16, 13), 3
+    g = torch.Generator().manual_seed(11)
+    ll = torch.randn(2, C, *lo, generator=g) * 2
+    labels = torch.randint(0, C, (2, 1, *hi), generator=g)
+    lr = ll.double().requires_grad_(True)
+    pr = torch.softmax(F.interpolate(lr, size=hi, mode='trilinear'), dim=1)
+    loss_r = orc.LOSSES[kind](pr, orc.to_categorical(labels, C).double())
+    loss_r.backward()
+    tables = get_interp_tables(lo, hi, cuda)
+    pitch = plane_pitch(lo[1], lo[2])
+    lld = to_planar(ll.to(cuda), pitch)
+    lab = labels[:, 0].to(torch.uint8).to(cuda).contiguous()
+    loss, coef = ops.head_loss_forward(lld, lab, tables, pitch, ops.LOSS_KINDS[kind])
+    assert abs(float(loss) - float(loss_r)) < 1e-6
+    dll = ops.head_loss_backward(lld, lab, coef, None, tables, pitch)
+    assert rel(from_planar(dll, lo[1], lo[2]), lr.grad) < 1e-5
+
+
+def test_adamax(cuda):
+    from multimodal_3d_image_segmentation_b200 import _lib
+    g = torch.Generator().manual_seed(12)
+    p0 = torch.randn(1000, generator=g)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adamax([pr], lr=5e-3)
+    pc = p0.to(cuda)
+    m = torch.zeros_like(pc)
+    u = torch.zeros_like(pc)
+    for step in range(1, 4):
+        grad = torch.randn(1000, generator=g)
+        pr.grad = grad.clone()
+        opt.step()
+        _lib.call('hno_adamax_step', pc.data_ptr(), grad.to(cuda).data_ptr(), m.data_ptr(), u.data_ptr(), 1000, 5e-3,
+                  0.9, 0.999, 1e-8, 0.0, step, 1.0, torch.cuda.current_stream().cuda_stream)
+    assert maxrel(pc, pr) < 1e-6
