@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""HNOSeg-XS training throughput on B200 (BASELINE.json: "HNOSeg-XS train volumes/s @4x240x240x155").
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host cores
+
+A step = one pass of the hot path over one batch: forward, Dice loss, backward, gradient all-reduce (N > 1),
+Adamax update, for `--batch` (default 2, BASELINE config 2) synthetic 4x240x240x155 fp32 volumes per GPU with
+random-init weights.  One JSON line is printed by rank 0:
+  value      whole-job volumes/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e        the same through the public API with HOST buffers: pinned H2D copy of every batch inside the
+             timed region (double-buffered on a copy stream) and loss.item() every step
+  roofline   the dominant kernel timed alone with CUDA events against the measured HBM peak
+  cpu_baseline  the oracle port of the reference on this box's host cores (bounded sample: 1 volume, 1 step)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(in_channels=4, out_channels=4, filters=24, num_transform_blocks=[3] * 8, num_modes=(10, 14, 14))
+VOLUME = (240, 240, 155)
+METRIC = 'HNOSeg-XS train volumes/s @4x240x240x155'
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower() == 'active':
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_step_factory(torch, batch):
+    """The reference's training step (experiments/train_test.py:146-171) restated on the oracle: forward,
+    to_categorical, DiceLoss, backward, Adamax -- on the host cores with all the threads torch can use."""
+    from oracle import hno_oracle as orc
+    sd = orc.init_state_dict(CFG['in_channels'], CFG['out_channels'], CFG['filters'], CFG['num_transform_blocks'],
+                             CFG['num_modes'], seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adamax(list(params.values()), lr=5e-3)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, 4, *VOLUME, generator=g)
+    labels = torch.randint(0, 4, (batch, 1, *VOLUME), generator=g)
+
+    def step():
+        y = orc.to_categorical(labels, 4)
+        probs = orc.hnosegxs_forward(params, x, CFG['num_transform_blocks'], CFG['num_modes'])
+        loss = orc.dice_loss(probs, y)
+        value = loss.item()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return value
+    return step
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import torch
+    step = oracle_step_factory(torch, 1)
+    budget = float(os.environ.get('HNO_REFERENCE_BUDGET_S', '150'))
+    t0 = time.perf_counter()
+    step()  # warm-up (also sizes the run)
+    t_first = time.perf_counter() - t0
+    warm = 1
+    while warm < min(args.warmup, 2) and (warm + 1) * t_first < 0.25 * budget:
+        step()
+        warm += 1
+    k = max(1, min(args.steps, int((budget - warm * t_first) / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    dt = time.perf_counter() - t0
+    value = k / dt
+    cores = torch.get_num_threads()
+    sample = (f'{k} timed step(s) (asked {args.steps}) + {warm} warm-up of ONE 4x240x240x155 volume each (batch 1 of the '
+              f'batch-{args.batch} workload), full training step incl. Adamax, oracle port, {cores} threads')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': k,
+        'warmup': warm, 'ms_per_step': 1e3 * dt / k, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'HNOSegXS(4,4,24,[3]*8,(10,14,14)) train step fp32, Dice loss, Adamax, batch {args.batch}/GPU, '
+                               '4x240x240x155 volumes', 'sampled_batch': 1},
+        'cpu_baseline': {'value': value, 'unit': 'volumes/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'volumes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'host_cpus': os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ kernel table
+def kernel_table(torch, dev, batch, peak_gbs):
+    """Times each hot-path entry point alone (CUDA events on the launch stream, buffers >> L2 so every launch is
+    HBM-cold) and relates it to its ALGORITHMIC bytes."""
+    from multimodal_3d_image_segmentation_b200 import ops
+    from multimodal_3d_image_segmentation_b200.plan import get_crop_plan, get_interp_tables, plane_pitch
+    D, H, W = ops.stem_out_shape(VOLUME)
+    P = plane_pitch(H, W)
+    F, C = CFG['filters'], CFG['out_channels']
+    plan = get_crop_plan((D, H, W), CFG['num_modes'], dev)
+    tables = get_interp_tables((D, H, W), VOLUME, dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)  # noqa: E731
+    a = [rnd(batch, F, D, P) for _ in range(4)]
+    z = rnd(batch, F, *plan.modes_shape)
+    x = rnd(batch, 4, *VOLUME)
+    lab = torch.randint(0, C, (batch,) + VOLUME, device=dev, generator=g).to(torch.uint8)
+    w48, w24, b24 = rnd(F, 2 * F) * 0.1, rnd(F, F) * 0.1, rnd(F) * 0.01
+    wout, win = rnd(C, F) * 0.1, rnd(F, 4, 2, 2, 2) * 0.1
+    ll = rnd(batch, C, D, P)
+    A = batch * F * D * H * W * 4.0          # one 24-channel low-res activation (algorithmic, no padding)
+    Z = batch * z[0].numel() * 4.0
+    X = batch * 4 * VOLUME[0] * VOLUME[1] * VOLUME[2] * 4.0
+    L = batch * VOLUME[0] * VOLUME[1] * VOLUME[2] * 1.0
+    LL = batch * C * D * H * W * 4.0
+    loss_coef = ops.head_loss_forward(ll, lab, tables, P, 0)
+    hw = (P, H * W)
+    cases = [
+        # name, launches per step, algorithmic bytes, callable
+        ('dht3_forward', 16, A + Z, lambda: ops.dht3_forward(a[0], plan, 1.0)),
+        ('dht3_adjoint_selu', 8, Z + A, lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=2, out=a[1])),
+        ('dht3_adjoint_accumulate', 8, Z + 2 * A, lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=1, out=a[1])),
+        ('pwconv48_forward', 11, 3 * A, lambda: ops.pwconv_forward(a[0], a[1], w48, b24, 1, False)),
+        ('pwconv24_forward', 1, 2 * A, lambda: ops.pwconv_forward(a[0], None, w24, b24, 1, False)),
+        ('pwconv48_backward', 11, 6 * A,
+         lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, in1_is_selu=True)),
+        ('pwconv24_backward', 1, 4 * A,
+         lambda: ops.pwconv_backward(a[0], a[1], a[2], None, w24, 1, False, hw=hw, in1_is_selu=True)),
+        ('mode_mix_forward', 24, 2 * Z, lambda: ops.pwconv_forward(z, None, w24, None, 1, True)),
+        ('mode_mix_backward', 24, 4 * Z, lambda: ops.pwconv_backward(z, z, z, None, w24, 1, True, has_bias=False)),
+        ('stem_forward', 1, X + A, lambda: ops.stem_forward(x, win, b24, P)),
+        ('stem_backward', 1, X + A, lambda: ops.stem_backward(a[0], x, F, P)),
+        ('head_conv_forward', 1, A + LL, lambda: ops.pwconv_forward(a[0], None, wout, None, 0, False)),
+        ('head_conv_backward', 1, 2 * A + LL,
+         lambda: ops.pwconv_backward(ll, None, a[0], None, wout, 0, False, hw=hw, has_bias=False)),
+        ('head_loss_forward', 1, LL + L, lambda: ops.head_loss_forward(ll, lab, tables, P, 0)),
+        ('head_loss_backward', 1, 2 * LL + L,
+         lambda: ops.head_loss_backward(ll, lab, loss_coef[1], None, tables, P)),
+    ]
+    rows = []
+    for name, per_step, nbytes, fn in cases:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        rows.append({'kernel': name, 'ms': round(ms, 4), 'per_step': per_step, 'alg_bytes': int(nbytes),
+                     'gbs': round(gbs, 1), 'frac': round(gbs / peak_gbs, 4), 'step_ms': round(ms * per_step, 3)})
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=2, help='volumes per GPU per step (BASELINE config 2: 2)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--loss', default='DiceLoss', choices=['DiceLoss', 'PCCLoss'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-table', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from multimodal_3d_image_segmentation_b200 import _lib, nets, parallel
+    from oracle import hno_oracle as orc  # parameter initialiser only (random-init weights of the named config)
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the hno_b200 path has no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    _lib.call('hno_device_check')
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = nets.HNOSegXS(**CFG, device=dev)
+    model.load_state_dict(orc.init_state_dict(CFG['in_channels'], CFG['out_channels'], CFG['filters'],
+                                              CFG['num_transform_blocks'], CFG['num_modes'], seed=0))
+    trainer = parallel.Trainer(model, args.loss, lr=5e-3)
+    B = args.batch
+    gx = torch.Generator().manual_seed(1234 + 2 * rank)
+    gl = torch.Generator().manual_seed(1235 + 2 * rank)
+    n_host = 2  # distinct host batches, cycled
+    xs_host = [torch.randn(B, 4, *VOLUME, generator=gx).pin_memory() for _ in range(n_host)]
+    ls_host = [torch.randint(0, 4, (B, 1, *VOLUME), generator=gl).to(torch.uint8).pin_memory() for _ in range(n_host)]
+    x_dev = xs_host[0].to(dev)
+    l_dev = ls_host[0].to(dev)
+
+    # ---------------- device-resident throughput
+    for _ in range(args.warmup):
+        loss = trainer.step(x_dev, l_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    parallel.launches(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(x_dev, l_dev)
+    e1.record()
+    barrier()
+    launches = parallel.launches()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---------------- end to end: host buffers, copies inside the timed region, loss.item() every step
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(x_dev), torch.empty_like(l_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            bufs[slot][0].copy_(xs_host[i % n_host], non_blocking=True)
+            bufs[slot][1].copy_(ls_host[i % n_host], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(k):
+        cur = torch.cuda.current_stream()
+        for s in range(2):
+            freed[s].record(cur)
+        issue_copy(0)
+        for i in range(k):
+            if i + 1 < k:
+                issue_copy(i + 1)
+            slot = i % 2
+            cur.wait_event(ready[slot])
+            lv = trainer.step(bufs[slot][0], bufs[slot][1])
+            freed[slot].record(cur)
+            lv.item()  # device -> host read of the step's loss, as experiments/train_test.py:162
+
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(ms2.item()) * 1e-3)
+    h2d = xs_host[0].numel() * 4 + ls_host[0].numel()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'volumes/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'HNOSegXS(4,4,24,[3]*8,(10,14,14)) train step fp32 (fwd + {args.loss} + bwd + Adamax), '
+                               f'batch {B}/GPU, 4x240x240x155 volumes, random-init weights',
+                   'global_batch': world * B, 'parallelism': f'dp{world}',
+                   'l2_policy': 'working set (~10 GB of activations per step) >> 126 MB L2; no explicit flush'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'volumes/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
+                'wall_s': round(wall, 4)},
+        'gpu_launches': launches, 'loss': final_loss,
+    }
+    if not args.no_kernel_table:
+        rows = kernel_table(torch, dev, B, peak)
+        top = max(rows, key=lambda r: r['step_ms'])
+        line['roofline'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['gbs'], 'peak': peak,
+                            'unit': 'GB/s', 'frac': top['frac'], 'traffic': None, 'peak_source': peak_src,
+                            'alg_bytes_per_launch': top['alg_bytes'], 'ms_per_launch': top['ms']}
+        line['kernels'] = rows
+        step_alg = sum(r['alg_bytes'] * r['per_step'] for r in rows)
+        line['step_roofline'] = {'alg_bytes_per_step': int(step_alg),
+                                 'frac': round(step_alg / (ms_total / args.steps * 1e-3) / 1e9 / peak, 4)}
+    if world == 1 and not args.no_cpu_baseline:
+        torch.cuda.synchronize()
+        step = oracle_step_factory(torch, 1)
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': 1.0 / dt, 'unit': 'volumes/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'sample': 'ONE full training step (fwd + Dice + bwd + Adamax) of ONE 4x240x240x155 volume '
+                                          '(batch 1), oracle port of the reference, cold (no warm-up)',
+                                'host_cpus': os.cpu_count()}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

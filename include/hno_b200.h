@@ -31,6 +31,8 @@ int hno_version(void);
 const char* hno_last_error(void);
 /* 0 if the current CUDA device is compute capability 10.x (B200), error otherwise. */
 int hno_device_check(void);
+/* Number of CUDA kernels this library has launched in the process (optionally reset to 0). */
+long hno_launch_count(int reset);
 
 /* ------------------------------------------------------------------------------------------
  * Truncated 3-D discrete Hartley transform.

@@ -3,6 +3,7 @@
 #include "dht_plan.h"
 #include "hno_b200.h"
 
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -16,6 +17,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached = 0;
@@ -73,6 +77,10 @@ extern "C" {
 
 int hno_version(void) { return HNO_B200_VERSION; }
 const char* hno_last_error(void) { return g_err; }
+
+long hno_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
 
 int hno_device_check(void) {
   int dev = 0;

@@ -30,7 +30,13 @@ void set_error(const char* fmt, ...);
     }                                                                             \
   } while (0)
 
-#define HNO_LAUNCH_CHECK() HNO_CUDA(cudaGetLastError())
+// Every kernel launch of the library goes through this macro; the counter backs hno_launch_count().
+void count_launch();
+#define HNO_LAUNCH_CHECK()        \
+  do {                            \
+    ::hno::count_launch();        \
+    HNO_CUDA(cudaGetLastError()); \
+  } while (0)
 
 // SELU constants exactly as PyTorch defines them (aten/src/ATen/native/Activation.cpp);
 // the reference applies F.selu everywhere (nets/nets_utils.py:127-133, nets/hnosegxs.py:267-268,325-327).
@@ -45,6 +51,11 @@ __device__ __forceinline__ float selu_f(float x) {
 __device__ __forceinline__ float selu_grad_from_out(float y) {
   return y > 0.f ? kSeluScale : y + kSeluNeg;
 }
+
+// Packed fp32 FMA (Blackwell FFMA2, PTX fma.rn.f32x2): two independent FMAs per issue slot.  The 3-operand scalar
+// FFMA issues at half rate on sm_100 (register-file read ports), so every FMA-heavy inner loop uses this form.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
 
 template <int V>
 struct Vec;

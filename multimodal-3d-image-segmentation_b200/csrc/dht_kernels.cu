@@ -25,7 +25,7 @@ namespace hno {
 // even/odd folding: cos rows see e[i] = in[i] + in[n-i], sin rows see o[i] = in[i] - in[n-i].
 // ----------------------------------------------------------------------------------------------
 template <int JCB, int JSB, int V>
-__global__ void __launch_bounds__(256) k_analysis_outer(const float* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(256, (((JCB + 3) / 4 + (JSB + 3) / 4) * 4 * V <= 48 ? 3 : 2)) k_analysis_outer(const float* __restrict__ in, float* __restrict__ out,
                                                         const float* __restrict__ fcos,
                                                         const float* __restrict__ fsin, int n, int JC, int JS,
                                                         int JCp, int JSp, int ncg, long total, long in_rs,
@@ -51,61 +51,59 @@ __global__ void __launch_bounds__(256) k_analysis_outer(const float* __restrict_
   const int cg = (int)(t - b * ncg);
   const float* ip = in + b * in_bs + (long)cg * V;
 
-  float accC[CW][V];
-  float accS[SW][V];
+  // accumulators paired along the row index j: (row 2q, row 2q+1) -> one FFMA2 per pair and column
+  float2 accC[CW / 2][V];
+  float2 accS[SW / 2][V];
   {
     Vec<V> a = Vec<V>::ld(ip);
 #pragma unroll
-    for (int j = 0; j < CW; ++j)
+    for (int q = 0; q < CW / 2; ++q)
 #pragma unroll
-      for (int v = 0; v < V; ++v) accC[j][v] = scos[j] * a.v[v];
+      for (int v = 0; v < V; ++v) accC[q][v] = make_float2(scos[2 * q] * a.v[v], scos[2 * q + 1] * a.v[v]);
 #pragma unroll
-    for (int j = 0; j < SW; ++j)
+    for (int q = 0; q < SW / 2; ++q)
 #pragma unroll
-      for (int v = 0; v < V; ++v) accS[j][v] = 0.f;
+      for (int v = 0; v < V; ++v) accS[q][v] = make_float2(0.f, 0.f);
   }
   const int npair = (n - 1) >> 1;
 #pragma unroll 2
   for (int i = 1; i <= npair; ++i) {
     Vec<V> a = Vec<V>::ld(ip + (long)i * in_rs);
     Vec<V> c = Vec<V>::ld(ip + (long)(n - i) * in_rs);
-    float e[V], o[V];
+    float2 e[V], o[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      e[v] = a.v[v] + c.v[v];
-      o[v] = a.v[v] - c.v[v];
+      e[v] = dup2(a.v[v] + c.v[v]);
+      o[v] = dup2(a.v[v] - c.v[v]);
     }
     const float4* c4 = reinterpret_cast<const float4*>(scos + i * CW);
 #pragma unroll
     for (int q = 0; q < CW / 4; ++q) {
-      float4 w = c4[q];
+      const float4 w = c4[q];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        accC[4 * q + 0][v] = fmaf(w.x, e[v], accC[4 * q + 0][v]);
-        accC[4 * q + 1][v] = fmaf(w.y, e[v], accC[4 * q + 1][v]);
-        accC[4 * q + 2][v] = fmaf(w.z, e[v], accC[4 * q + 2][v]);
-        accC[4 * q + 3][v] = fmaf(w.w, e[v], accC[4 * q + 3][v]);
+        accC[2 * q + 0][v] = ffma2(make_float2(w.x, w.y), e[v], accC[2 * q + 0][v]);
+        accC[2 * q + 1][v] = ffma2(make_float2(w.z, w.w), e[v], accC[2 * q + 1][v]);
       }
     }
     const float4* s4 = reinterpret_cast<const float4*>(ssin + i * SW);
 #pragma unroll
     for (int q = 0; q < SW / 4; ++q) {
-      float4 w = s4[q];
+      const float4 w = s4[q];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        accS[4 * q + 0][v] = fmaf(w.x, o[v], accS[4 * q + 0][v]);
-        accS[4 * q + 1][v] = fmaf(w.y, o[v], accS[4 * q + 1][v]);
-        accS[4 * q + 2][v] = fmaf(w.z, o[v], accS[4 * q + 2][v]);
-        accS[4 * q + 3][v] = fmaf(w.w, o[v], accS[4 * q + 3][v]);
+        accS[2 * q + 0][v] = ffma2(make_float2(w.x, w.y), o[v], accS[2 * q + 0][v]);
+        accS[2 * q + 1][v] = ffma2(make_float2(w.z, w.w), o[v], accS[2 * q + 1][v]);
       }
     }
   }
   if ((n & 1) == 0 && n > 1) {  // Nyquist sample pairs with itself, sine part vanishes
     Vec<V> a = Vec<V>::ld(ip + (long)nh * in_rs);
 #pragma unroll
-    for (int j = 0; j < CW; ++j)
+    for (int q = 0; q < CW / 2; ++q)
 #pragma unroll
-      for (int v = 0; v < V; ++v) accC[j][v] = fmaf(scos[nh * CW + j], a.v[v], accC[j][v]);
+      for (int v = 0; v < V; ++v)
+        accC[q][v] = ffma2(make_float2(scos[nh * CW + 2 * q], scos[nh * CW + 2 * q + 1]), dup2(a.v[v]), accC[q][v]);
   }
   float* op = out + b * out_bs + (long)cg * V;
 #pragma unroll
@@ -113,7 +111,7 @@ __global__ void __launch_bounds__(256) k_analysis_outer(const float* __restrict_
     if (j < JC) {
       Vec<V> r;
 #pragma unroll
-      for (int v = 0; v < V; ++v) r.v[v] = accC[j][v];
+      for (int v = 0; v < V; ++v) r.v[v] = (j & 1) ? accC[j / 2][v].y : accC[j / 2][v].x;
       r.st(op + (long)j * out_rs);
     }
 #pragma unroll
@@ -121,7 +119,7 @@ __global__ void __launch_bounds__(256) k_analysis_outer(const float* __restrict_
     if (j < JS) {
       Vec<V> r;
 #pragma unroll
-      for (int v = 0; v < V; ++v) r.v[v] = accS[j][v];
+      for (int v = 0; v < V; ++v) r.v[v] = (j & 1) ? accS[j / 2][v].y : accS[j / 2][v].x;
       r.st(op + (long)(JC + j) * out_rs);
     }
 }
@@ -168,7 +166,7 @@ __device__ __forceinline__ void synth_store(float* p, const float (&val)[V], int
 }
 
 template <int JCB, int JSB, int V, int EPI>
-__global__ void __launch_bounds__(256) k_synthesis_outer(const float* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(256, (((JCB + 3) / 4 + (JSB + 3) / 4) * 4 * V <= 48 ? 3 : 2)) k_synthesis_outer(const float* __restrict__ in, float* __restrict__ out,
                                                          const float* __restrict__ fcos,
                                                          const float* __restrict__ fsin, int n, int JC, int JS,
                                                          int JCp, int JSp, int ncg, long total, long in_rs,
@@ -196,75 +194,76 @@ __global__ void __launch_bounds__(256) k_synthesis_outer(const float* __restrict
   const int col0 = cg * V;
   const float* ip = in + b * in_bs + (long)col0;
 
-  float C[CW][V];
-  float S[SW][V];
+  // inputs paired along the row index j so that each FFMA2 consumes one (basis pair, input pair)
+  float2 C[CW / 2][V];
+  float2 S[SW / 2][V];
 #pragma unroll
   for (int j = 0; j < CW; ++j) {
-    if (j < JC) {
-      Vec<V> a = Vec<V>::ld(ip + (long)j * in_rs);
+    Vec<V> a;
 #pragma unroll
-      for (int v = 0; v < V; ++v) C[j][v] = a.v[v];
-    } else {
+    for (int v = 0; v < V; ++v) a.v[v] = 0.f;
+    if (j < JC) a = Vec<V>::ld(ip + (long)j * in_rs);
 #pragma unroll
-      for (int v = 0; v < V; ++v) C[j][v] = 0.f;
+    for (int v = 0; v < V; ++v) {
+      if (j & 1) C[j / 2][v].y = a.v[v];
+      else C[j / 2][v].x = a.v[v];
     }
   }
 #pragma unroll
   for (int j = 0; j < SW; ++j) {
-    if (j < JS) {
-      Vec<V> a = Vec<V>::ld(ip + (long)(JC + j) * in_rs);
+    Vec<V> a;
 #pragma unroll
-      for (int v = 0; v < V; ++v) S[j][v] = a.v[v];
-    } else {
+    for (int v = 0; v < V; ++v) a.v[v] = 0.f;
+    if (j < JS) a = Vec<V>::ld(ip + (long)(JC + j) * in_rs);
 #pragma unroll
-      for (int v = 0; v < V; ++v) S[j][v] = 0.f;
+    for (int v = 0; v < V; ++v) {
+      if (j & 1) S[j / 2][v].y = a.v[v];
+      else S[j / 2][v].x = a.v[v];
     }
   }
   float* op = out + b * out_bs + (long)col0;
   {
     float e[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) e[v] = 0.f;
+    for (int v = 0; v < V; ++v) {
+      float2 e2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < CW; ++j)
-#pragma unroll
-      for (int v = 0; v < V; ++v) e[v] = fmaf(scos[j], C[j][v], e[v]);
+      for (int q = 0; q < CW / 2; ++q) e2 = ffma2(make_float2(scos[2 * q], scos[2 * q + 1]), C[q][v], e2);
+      e[v] = e2.x + e2.y;
+    }
     synth_store<EPI, V>(op, e, col0, valid_cols);
   }
   const int npair = (n - 1) >> 1;
   for (int i = 1; i <= npair; ++i) {
-    float e[V], o[V];
+    float2 e2[V], o2[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) e[v] = o[v] = 0.f;
+    for (int v = 0; v < V; ++v) e2[v] = o2[v] = make_float2(0.f, 0.f);
     const float4* c4 = reinterpret_cast<const float4*>(scos + i * CW);
 #pragma unroll
     for (int q = 0; q < CW / 4; ++q) {
-      float4 w = c4[q];
+      const float4 w = c4[q];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        e[v] = fmaf(w.x, C[4 * q + 0][v], e[v]);
-        e[v] = fmaf(w.y, C[4 * q + 1][v], e[v]);
-        e[v] = fmaf(w.z, C[4 * q + 2][v], e[v]);
-        e[v] = fmaf(w.w, C[4 * q + 3][v], e[v]);
+        e2[v] = ffma2(make_float2(w.x, w.y), C[2 * q + 0][v], e2[v]);
+        e2[v] = ffma2(make_float2(w.z, w.w), C[2 * q + 1][v], e2[v]);
       }
     }
     const float4* s4 = reinterpret_cast<const float4*>(ssin + i * SW);
 #pragma unroll
     for (int q = 0; q < SW / 4; ++q) {
-      float4 w = s4[q];
+      const float4 w = s4[q];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        o[v] = fmaf(w.x, S[4 * q + 0][v], o[v]);
-        o[v] = fmaf(w.y, S[4 * q + 1][v], o[v]);
-        o[v] = fmaf(w.z, S[4 * q + 2][v], o[v]);
-        o[v] = fmaf(w.w, S[4 * q + 3][v], o[v]);
+        o2[v] = ffma2(make_float2(w.x, w.y), S[2 * q + 0][v], o2[v]);
+        o2[v] = ffma2(make_float2(w.z, w.w), S[2 * q + 1][v], o2[v]);
       }
     }
     float lo[V], hi[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      lo[v] = e[v] + o[v];
-      hi[v] = e[v] - o[v];
+      const float e = e2[v].x + e2[v].y, o = o2[v].x + o2[v].y;
+      lo[v] = e + o;
+      hi[v] = e - o;
     }
     synth_store<EPI, V>(op + (long)i * out_rs, lo, col0, valid_cols);
     synth_store<EPI, V>(op + (long)(n - i) * out_rs, hi, col0, valid_cols);
@@ -272,11 +271,13 @@ __global__ void __launch_bounds__(256) k_synthesis_outer(const float* __restrict
   if ((n & 1) == 0 && n > 1) {
     float e[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) e[v] = 0.f;
+    for (int v = 0; v < V; ++v) {
+      float2 e2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < CW; ++j)
-#pragma unroll
-      for (int v = 0; v < V; ++v) e[v] = fmaf(scos[nh * CW + j], C[j][v], e[v]);
+      for (int q = 0; q < CW / 2; ++q)
+        e2 = ffma2(make_float2(scos[nh * CW + 2 * q], scos[nh * CW + 2 * q + 1]), C[q][v], e2);
+      e[v] = e2.x + e2.y;
+    }
     synth_store<EPI, V>(op + (long)nh * out_rs, e, col0, valid_cols);
   }
 }
@@ -515,8 +516,8 @@ static int pick_outer_vec(const OuterArgs& a) {
         return FN<8, 8, 1>(a, st);                                         \
       }                                                                    \
       if (a.JC <= 11 && a.JS <= 10) {                                      \
-        if (v_ == 4) return FN<11, 10, 4>(a, st);                          \
-        if (v_ == 2) return FN<11, 10, 2>(a, st);                          \
+        /* 24 rows x 2 columns = 48 accumulators: 3 CTAs / SM; 4 columns would need ~180 registers */ \
+        if (v_ >= 2) return FN<11, 10, 2>(a, st);                          \
         return FN<11, 10, 1>(a, st);                                       \
       }                                                                    \
       if (a.JC <= 15 && a.JS <= 14) {                                      \

@@ -29,16 +29,16 @@ __device__ __forceinline__ float act_grad_from_out(float y) {
 
 // ------------------------------------------------------------------------------------------ forward
 template <int CI1, int CI2, int CO, int ACT, bool RES, int V>
-__global__ void __launch_bounds__(kPwThreads) k_pwconv_fwd(const float* __restrict__ in1,
-                                                           const float* __restrict__ in2,
-                                                           const float* __restrict__ weight,
-                                                           const float* __restrict__ bias, float* __restrict__ out,
-                                                           long S) {
+__global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_fwd(const float* __restrict__ in1,
+                                                              const float* __restrict__ in2,
+                                                              const float* __restrict__ weight,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              long S) {
   static_assert(!RES || (CI1 == CO && CI2 == 0), "residual needs CI1 == CO and a single input");
   constexpr int CI = CI1 + CI2;
   constexpr int COp = (CO + 3) & ~3;
   __shared__ __align__(16) float wt[CI * COp];  // transposed: wt[i][o]
-  __shared__ float sbias[COp];
+  __shared__ __align__(16) float sbias[COp];
   for (int idx = threadIdx.x; idx < CI * COp; idx += kPwThreads) {
     int i = idx / COp, o = idx - i * COp;
     wt[idx] = o < CO ? weight[o * CI + i] : 0.f;
@@ -48,26 +48,29 @@ __global__ void __launch_bounds__(kPwThreads) k_pwconv_fwd(const float* __restri
   const long s0 = (blockIdx.x * (long)kPwThreads + threadIdx.x) * V;
   if (s0 >= S) return;
   const int b = blockIdx.y;
-  float acc[COp][V];
+  // acc[op][v] = (out[2 op][v], out[2 op + 1][v]): output channels are paired so that the weight pair comes
+  // straight out of one LDS.128 and each FFMA2 retires two FMAs
+  float2 acc[COp / 2][V];
 #pragma unroll
-  for (int o = 0; o < COp; ++o)
+  for (int op = 0; op < COp / 2; ++op)
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[o][v] = sbias[o];
+    for (int v = 0; v < V; ++v) acc[op][v] = make_float2(sbias[2 * op], sbias[2 * op + 1]);
 
   const float* p1 = in1 + (long)b * CI1 * S + s0;
 #pragma unroll 4
   for (int i = 0; i < CI1; ++i) {
     Vec<V> x = Vec<V>::ld(p1 + (long)i * S);
+    float2 xd[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) xd[v] = dup2(x.v[v]);
     const float4* w4 = reinterpret_cast<const float4*>(wt + i * COp);
 #pragma unroll
     for (int q = 0; q < COp / 4; ++q) {
-      float4 w = w4[q];
+      const float4 w = w4[q];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        acc[4 * q + 0][v] = fmaf(w.x, x.v[v], acc[4 * q + 0][v]);
-        acc[4 * q + 1][v] = fmaf(w.y, x.v[v], acc[4 * q + 1][v]);
-        acc[4 * q + 2][v] = fmaf(w.z, x.v[v], acc[4 * q + 2][v]);
-        acc[4 * q + 3][v] = fmaf(w.w, x.v[v], acc[4 * q + 3][v]);
+        acc[2 * q + 0][v] = ffma2(make_float2(w.x, w.y), xd[v], acc[2 * q + 0][v]);
+        acc[2 * q + 1][v] = ffma2(make_float2(w.z, w.w), xd[v], acc[2 * q + 1][v]);
       }
     }
   }
@@ -76,16 +79,17 @@ __global__ void __launch_bounds__(kPwThreads) k_pwconv_fwd(const float* __restri
 #pragma unroll 4
     for (int i = 0; i < CI2; ++i) {
       Vec<V> x = Vec<V>::ld(p2 + (long)i * S);
+      float2 xd[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) xd[v] = dup2(x.v[v]);
       const float4* w4 = reinterpret_cast<const float4*>(wt + (CI1 + i) * COp);
 #pragma unroll
       for (int q = 0; q < COp / 4; ++q) {
-        float4 w = w4[q];
+        const float4 w = w4[q];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          acc[4 * q + 0][v] = fmaf(w.x, x.v[v], acc[4 * q + 0][v]);
-          acc[4 * q + 1][v] = fmaf(w.y, x.v[v], acc[4 * q + 1][v]);
-          acc[4 * q + 2][v] = fmaf(w.z, x.v[v], acc[4 * q + 2][v]);
-          acc[4 * q + 3][v] = fmaf(w.w, x.v[v], acc[4 * q + 3][v]);
+          acc[2 * q + 0][v] = ffma2(make_float2(w.x, w.y), xd[v], acc[2 * q + 0][v]);
+          acc[2 * q + 1][v] = ffma2(make_float2(w.z, w.w), xd[v], acc[2 * q + 1][v]);
         }
       }
     }
@@ -94,19 +98,45 @@ __global__ void __launch_bounds__(kPwThreads) k_pwconv_fwd(const float* __restri
 #pragma unroll
   for (int o = 0; o < CO; ++o) {
     Vec<V> r;
+#pragma unroll
+    for (int v = 0; v < V; ++v) r.v[v] = (o & 1) ? acc[o / 2][v].y : acc[o / 2][v].x;
     if (RES) {
       Vec<V> x = Vec<V>::ld(p1 + (long)o * S);  // second touch of the same line: L1 hit
 #pragma unroll
-      for (int v = 0; v < V; ++v) r.v[v] = act_f<ACT>(acc[o][v] + x.v[v]);
-    } else {
-#pragma unroll
-      for (int v = 0; v < V; ++v) r.v[v] = act_f<ACT>(acc[o][v]);
+      for (int v = 0; v < V; ++v) r.v[v] += x.v[v];
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v) r.v[v] = act_f<ACT>(r.v[v]);
     r.st(po + (long)o * S);
   }
 }
 
 // ------------------------------------------------------------------------------------------ backward
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// global [C][S] columns (lv .. lv+VV) of this thread -> shared [C][TVS], asynchronously (LDGSTS)
+template <int C, int VV, int TVS>
+__device__ __forceinline__ void stage_input(float* __restrict__ sx, const float* __restrict__ src, long S, int lv,
+                                            bool valid) {
+  if (valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(sx + lv);
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      if (VV == 2)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + i * TVS * 4), "l"(src + (long)i * S)
+                     : "memory");
+      else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + i * TVS * 4), "l"(src + (long)i * S)
+                     : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+      for (int v = 0; v < VV; ++v) sx[i * TVS + lv + v] = 0.f;
+  }
+}
+
 template <int CI1, int CI2, int CO, int ACT, bool RES, int VV>
 __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_bwd(
     const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ in1,
@@ -128,23 +158,23 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_bwd(
     wt[idx] = o < CO ? weight[o * CI + i] : 0.f;
   }
   using T1 = WgTile<CO, CI1>;
-  float accW1[T1::TO][T1::TI];
+  float2 accW1[T1::TO][T1::TI];
   float accB[T1::TO];
 #pragma unroll
   for (int q = 0; q < T1::TO; ++q) {
     accB[q] = 0.f;
 #pragma unroll
-    for (int r = 0; r < T1::TI; ++r) accW1[q][r] = 0.f;
+    for (int r = 0; r < T1::TI; ++r) accW1[q][r] = make_float2(0.f, 0.f);
   }
   constexpr int CI2s = CI2 > 0 ? CI2 : 8;
   using T2 = WgTile<CO, CI2s>;
-  float accW2[T2::TO][T2::TI];
+  float2 accW2[T2::TO][T2::TI];
   float accB2[T2::TO];
 #pragma unroll
   for (int q = 0; q < T2::TO; ++q) {
     accB2[q] = 0.f;
 #pragma unroll
-    for (int r = 0; r < T2::TI; ++r) accW2[q][r] = 0.f;
+    for (int r = 0; r < T2::TI; ++r) accW2[q][r] = make_float2(0.f, 0.f);
   }
   __syncthreads();
 
@@ -157,113 +187,104 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_bwd(
 #pragma unroll
     for (int v = 0; v < VV; ++v) live[v] = valid && ((s0 + v) % P) < HW;
 
-    // ---- phase A1: d(pre-activation), staged to shared memory
-    float dpre[COp][VV];
+    // input 1 goes global -> shared with cp.async (no registers, all CI1 requests in flight at once) while the
+    // d(pre-activation) loads below are outstanding too: one exposed memory latency per tile instead of one per channel
+    stage_input<CI1, VV, TVS>(sx, in1 + (long)b * CI1 * S + s0, S, lv, valid);
+
+    // ---- phase A1: d(pre-activation), staged to shared memory; kept in registers as output-channel pairs
+    float2 dp2[COp / 2][VV];
 #pragma unroll
     for (int o = 0; o < COp; ++o) {
+      float d[VV];
       if (o < CO && valid) {
         Vec<VV> g = Vec<VV>::ld(dy + ((long)b * CO + o) * S + s0);
         Vec<VV> yy;
         if (ACT != 0) yy = Vec<VV>::ld(y + ((long)b * CO + o) * S + s0);
 #pragma unroll
         for (int v = 0; v < VV; ++v)
-          dpre[o][v] = live[v] ? g.v[v] * (ACT != 0 ? act_grad_from_out<ACT>(yy.v[v]) : 1.f) : 0.f;
+          d[v] = live[v] ? g.v[v] * (ACT != 0 ? act_grad_from_out<ACT>(yy.v[v]) : 1.f) : 0.f;
       } else {
 #pragma unroll
-        for (int v = 0; v < VV; ++v) dpre[o][v] = 0.f;
+        for (int v = 0; v < VV; ++v) d[v] = 0.f;
+      }
+#pragma unroll
+      for (int v = 0; v < VV; ++v) {
+        if (o & 1) dp2[o / 2][v].y = d[v];
+        else dp2[o / 2][v].x = d[v];
       }
       if (o < CO) {
 #pragma unroll
-        for (int v = 0; v < VV; ++v) sdp[o * TVS + lv + v] = dpre[o][v];
+        for (int v = 0; v < VV; ++v) sdp[o * TVS + lv + v] = d[v];
       }
     }
-    // ---- input gradient + staging of input 1
-#pragma unroll 2
-    for (int i = 0; i < CI1; ++i) {
-      float acc[VV];
+    cp_async_wait_all();
+    // ---- input gradient of input 1 (own columns of sx / sdp only: no barrier needed yet)
+    if (din1 != nullptr && valid) {
+      float* dst = din1 + (long)b * CI1 * S + s0;
+#pragma unroll 4
+      for (int i = 0; i < CI1; ++i) {
+        float2 a2[VV];
 #pragma unroll
-      for (int v = 0; v < VV; ++v) acc[v] = RES ? sdp[i * TVS + lv + v] : 0.f;
-      const float4* w4 = reinterpret_cast<const float4*>(wt + i * COp);
+        for (int v = 0; v < VV; ++v) a2[v] = make_float2(RES ? sdp[i * TVS + lv + v] : 0.f, 0.f);
+        const float4* w4 = reinterpret_cast<const float4*>(wt + i * COp);
 #pragma unroll
-      for (int q = 0; q < COp / 4; ++q) {
-        float4 w = w4[q];
+        for (int q = 0; q < COp / 4; ++q) {
+          const float4 w = w4[q];
 #pragma unroll
-        for (int v = 0; v < VV; ++v) {
-          acc[v] = fmaf(w.x, dpre[4 * q + 0][v], acc[v]);
-          acc[v] = fmaf(w.y, dpre[4 * q + 1][v], acc[v]);
-          acc[v] = fmaf(w.z, dpre[4 * q + 2][v], acc[v]);
-          acc[v] = fmaf(w.w, dpre[4 * q + 3][v], acc[v]);
-        }
-      }
-      Vec<VV> x;
-#pragma unroll
-      for (int v = 0; v < VV; ++v) x.v[v] = 0.f;
-      if (valid) {
-        const long off = ((long)b * CI1 + i) * S + s0;
-        x = Vec<VV>::ld(in1 + off);
-        if (din1 != nullptr) {
-          Vec<VV> r;
-          if (flags & 4) {
-#pragma unroll
-            for (int v = 0; v < VV; ++v) acc[v] *= selu_grad_from_out(x.v[v]);
+          for (int v = 0; v < VV; ++v) {
+            a2[v] = ffma2(make_float2(w.x, w.y), dp2[2 * q + 0][v], a2[v]);
+            a2[v] = ffma2(make_float2(w.z, w.w), dp2[2 * q + 1][v], a2[v]);
           }
-          if (flags & 1) {
-            Vec<VV> old = Vec<VV>::ld(din1 + off);
-#pragma unroll
-            for (int v = 0; v < VV; ++v) r.v[v] = old.v[v] + acc[v];
-          } else {
-#pragma unroll
-            for (int v = 0; v < VV; ++v) r.v[v] = acc[v];
-          }
-          r.st(din1 + off);
         }
-      }
+        Vec<VV> r;
 #pragma unroll
-      for (int v = 0; v < VV; ++v) sx[i * TVS + lv + v] = x.v[v];
+        for (int v = 0; v < VV; ++v) r.v[v] = a2[v].x + a2[v].y;
+        if (flags & 4) {
+#pragma unroll
+          for (int v = 0; v < VV; ++v) r.v[v] *= selu_grad_from_out(sx[i * TVS + lv + v]);
+        }
+        if (flags & 1) {
+          Vec<VV> old = Vec<VV>::ld(dst + (long)i * S);
+#pragma unroll
+          for (int v = 0; v < VV; ++v) r.v[v] += old.v[v];
+        }
+        r.st(dst + (long)i * S);
+      }
     }
     __syncthreads();
     wgrad_tile<CO, CI1, TV, TVS>(sdp, sx, accW1, accB, true);
     if (CI2 > 0) {
-      __syncthreads();
-#pragma unroll 2
-      for (int i = 0; i < CI2; ++i) {
-        float acc[VV];
+      __syncthreads();  // everyone is done reading input 1 from sx
+      stage_input<CI2s, VV, TVS>(sx, in2 + (long)b * CI2 * S + s0, S, lv, valid);
+      if (din2 != nullptr && valid) {
+        float* dst = din2 + (long)b * CI2 * S + s0;
+#pragma unroll 4
+        for (int i = 0; i < CI2; ++i) {
+          float2 a2[VV];
 #pragma unroll
-        for (int v = 0; v < VV; ++v) acc[v] = 0.f;
-        const float4* w4 = reinterpret_cast<const float4*>(wt + (CI1 + i) * COp);
+          for (int v = 0; v < VV; ++v) a2[v] = make_float2(0.f, 0.f);
+          const float4* w4 = reinterpret_cast<const float4*>(wt + (CI1 + i) * COp);
 #pragma unroll
-        for (int q = 0; q < COp / 4; ++q) {
-          float4 w = w4[q];
+          for (int q = 0; q < COp / 4; ++q) {
+            const float4 w = w4[q];
 #pragma unroll
-          for (int v = 0; v < VV; ++v) {
-            acc[v] = fmaf(w.x, dpre[4 * q + 0][v], acc[v]);
-            acc[v] = fmaf(w.y, dpre[4 * q + 1][v], acc[v]);
-            acc[v] = fmaf(w.z, dpre[4 * q + 2][v], acc[v]);
-            acc[v] = fmaf(w.w, dpre[4 * q + 3][v], acc[v]);
-          }
-        }
-        Vec<VV> x;
-#pragma unroll
-        for (int v = 0; v < VV; ++v) x.v[v] = 0.f;
-        if (valid) {
-          const long off = ((long)b * CI2 + i) * S + s0;
-          x = Vec<VV>::ld(in2 + off);
-          if (din2 != nullptr) {
-            Vec<VV> r;
-            if (flags & 2) {
-              Vec<VV> old = Vec<VV>::ld(din2 + off);
-#pragma unroll
-              for (int v = 0; v < VV; ++v) r.v[v] = old.v[v] + acc[v];
-            } else {
-#pragma unroll
-              for (int v = 0; v < VV; ++v) r.v[v] = acc[v];
+            for (int v = 0; v < VV; ++v) {
+              a2[v] = ffma2(make_float2(w.x, w.y), dp2[2 * q + 0][v], a2[v]);
+              a2[v] = ffma2(make_float2(w.z, w.w), dp2[2 * q + 1][v], a2[v]);
             }
-            r.st(din2 + off);
           }
-        }
+          Vec<VV> r;
 #pragma unroll
-        for (int v = 0; v < VV; ++v) sx[i * TVS + lv + v] = x.v[v];
+          for (int v = 0; v < VV; ++v) r.v[v] = a2[v].x + a2[v].y;
+          if (flags & 2) {
+            Vec<VV> old = Vec<VV>::ld(dst + (long)i * S);
+#pragma unroll
+            for (int v = 0; v < VV; ++v) r.v[v] += old.v[v];
+          }
+          r.st(dst + (long)i * S);
+        }
       }
+      cp_async_wait_all();  // the input-2 copy overlapped the input-gradient math above
       __syncthreads();
       wgrad_tile<CO, CI2s, TV, TVS>(sdp, sx, accW2, accB2, false);
     }
@@ -329,7 +350,10 @@ static int fwd_t(const float* in1, const float* in2, const float* w, const float
                  cudaStream_t st) {
   const void* ptrs[3] = {in1, in2, out};
   const long cnt[1] = {S};
-  const int v = pick_vec(ptrs, 3, cnt, 1);
+  int v = pick_vec(ptrs, 3, cnt, 1);
+  // 2 voxels per thread keeps the CO/2 x V packed accumulators + operands under 85 registers (3 CTAs / SM);
+  // 4 voxels would need ~160 registers and halve the number of loads in flight per SM.
+  if (CO > 8 && v == 4) v = 2;
   dim3 grid(ceil_div(S / v, kPwThreads), B);
   if (v == 4)
     k_pwconv_fwd<CI1, CI2, CO, ACT, RES, 4><<<grid, kPwThreads, 0, st>>>(in1, in2, w, bias, out, S);

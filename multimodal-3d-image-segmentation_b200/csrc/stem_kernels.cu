@@ -87,13 +87,13 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_stem_wgrad(const float* __res
   float* sdp = reinterpret_cast<float*>(smem4);  // [F][TVS]
   float* sx = sdp + F * TVS;                     // [Q][TVS]
   using T = WgTile<F, Q>;
-  float accW[T::TO][T::TI];
+  float2 accW[T::TO][T::TI];
   float accB[T::TO];
 #pragma unroll
   for (int q = 0; q < T::TO; ++q) {
     accB[q] = 0.f;
 #pragma unroll
-    for (int r = 0; r < T::TI; ++r) accW[q][r] = 0.f;
+    for (int r = 0; r < T::TI; ++r) accW[q][r] = make_float2(0.f, 0.f);
   }
   for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int b = (int)(tile / tiles_per_sample);

@@ -22,7 +22,7 @@ struct WgTile {
 // Accumulate dW[o][i] += sum_v dpre[o][v] * x[i][v] over this group's share of a TV-voxel tile.
 template <int CO, int CI, int TV, int TVS>
 __device__ __forceinline__ void wgrad_tile(const float* __restrict__ sdp, const float* __restrict__ sx,
-                                           float (&accW)[WgTile<CO, CI>::TO][WgTile<CO, CI>::TI],
+                                           float2 (&accW)[WgTile<CO, CI>::TO][WgTile<CO, CI>::TI],
                                            float (&accB)[WgTile<CO, CI>::TO], bool with_bias) {
   using T = WgTile<CO, CI>;
   const int g = threadIdx.x / T::G;
@@ -44,11 +44,10 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ sdp, const 
     for (int q = 0; q < T::TO; ++q)
 #pragma unroll
       for (int r = 0; r < T::TI; ++r) {
-        float a = accW[q][r];
-        a = fmaf(d[q].x, x[r].x, a);
-        a = fmaf(d[q].y, x[r].y, a);
-        a = fmaf(d[q].z, x[r].z, a);
-        a = fmaf(d[q].w, x[r].w, a);
+        // two packed FMAs per 4 voxels; the two lanes are summed once, in wgrad_flush
+        float2 a = accW[q][r];
+        a = ffma2(make_float2(d[q].x, d[q].y), make_float2(x[r].x, x[r].y), a);
+        a = ffma2(make_float2(d[q].z, d[q].w), make_float2(x[r].z, x[r].w), a);
         accW[q][r] = a;
       }
     if (with_bias && it == 0) {
@@ -61,7 +60,7 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ sdp, const 
 // Cross-group reduction of the register tiles through shared memory, then one partial row per CTA.
 template <int CO, int CI>
 __device__ __forceinline__ void wgrad_flush(float* __restrict__ scratch /* >= NG*CO*CI floats */,
-                                            const float (&accW)[WgTile<CO, CI>::TO][WgTile<CO, CI>::TI],
+                                            const float2 (&accW)[WgTile<CO, CI>::TO][WgTile<CO, CI>::TI],
                                             float* __restrict__ dst /* [CO][ldw] */, int ldw, int col0) {
   using T = WgTile<CO, CI>;
   const int g = threadIdx.x / T::G;
@@ -74,7 +73,7 @@ __device__ __forceinline__ void wgrad_flush(float* __restrict__ scratch /* >= NG
     for (int q = 0; q < T::TO; ++q)
 #pragma unroll
       for (int r = 0; r < T::TI; ++r)
-        scratch[g * (CO * CI) + (ot * T::TO + q) * CI + it * T::TI + r] = accW[q][r];
+        scratch[g * (CO * CI) + (ot * T::TO + q) * CI + it * T::TI + r] = accW[q][r].x + accW[q][r].y;
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < CO * CI; idx += kPwThreads) {

@@ -111,10 +111,24 @@ class XSEngine:
         return probs, S
 
     # ------------------------------------------------------------------------------------------ backward
-    def run_backward(self, S, dprobs=None, fused=None):
+    def run_backward(self, S, dprobs=None, fused=None, dst=None):
         """Returns the gradients in named_slots() order.  Either `dprobs` (drop-in autograd) or
-        fused=(labels_u8, coef, grad_loss) (fused head + loss) drives the head."""
+        fused=(labels_u8, coef, grad_loss) (fused head + loss) drives the head.  `dst`: optional list of
+        destination tensors in named_slots() order (views of a flat gradient buffer); they are overwritten."""
         m = self.model
+        slot = {id(p): i for i, p in enumerate(self.named_slots())}
+
+        def out_w(conv_or_param):
+            """(dweight 2-D view, dbias) destinations for a conv / parameter, or (None, None)."""
+            if dst is None:
+                return None, None
+            if isinstance(conv_or_param, torch.nn.Parameter):
+                w = dst[slot[id(conv_or_param)]]
+                return (w.view(w.shape[0], -1) if w.ndim == 2 or w.ndim == 5 and w.shape[2:] == (1, 1, 1) else w), None
+            w = dst[slot[id(conv_or_param.weight)]]
+            b = dst[slot[id(conv_or_param.bias)]] if conv_or_param.bias is not None else None
+            return w.view(w.shape[0], -1), b
+
         D, H, W, pitch = S.geom
         hw = (pitch, H * W)
         plan = S.plan
@@ -127,8 +141,9 @@ class XSEngine:
             dll = ops.head_loss_backward(S.ll, labels, coef, grad_loss, S.tables, pitch)
         else:
             dll = ops.head_backward(dprobs, S.probs, S.tables, pitch, S.act)
+        dw_, _ = out_w(m.conv_out)
         dcur, _, g_out, _ = ops.pwconv_backward(dll, None, S.last, None, _w2(m.conv_out), 0, False, hw=hw,
-                                                has_bias=False)
+                                                has_bias=False, dweight=dw_)
         block_grads = [None] * nb
         dstash = {}
         for i in reversed(range(nb)):
@@ -139,8 +154,9 @@ class XSEngine:
             target = dstash.pop(i - 1) if (not has_map and (i - 1) in dstash) else None
             if layer.conv_concat is not None:
                 op = layer.conv_concat.op
+                dw_, db_ = out_w(op)
                 dt, dxin, g_wc, g_bc = ops.pwconv_backward(dcur, rec.y, rec.u, rec.xin, _w2(op), 1, False, hw=hw,
-                                                           in1_is_selu=True, din2=target)
+                                                           in1_is_selu=True, din2=target, dweight=dw_, dbias=db_)
             else:
                 dt = ops.selu_backward(dcur, rec.u)
                 if target is not None:
@@ -152,10 +168,12 @@ class XSEngine:
             g_mix = []
             for j in reversed(range(len(layer.conv_blocks))):
                 w = layer.conv_blocks[j].op.weight
+                dw_, _ = out_w(w)
                 if shared:
-                    dz, _, gw, _ = ops.pwconv_backward(dz, rec.zs[j + 1], rec.zs[j], None, w, 1, True, has_bias=False)
+                    dz, _, gw, _ = ops.pwconv_backward(dz, rec.zs[j + 1], rec.zs[j], None, w, 1, True, has_bias=False,
+                                                       dweight=dw_)
                 else:
-                    dz, gw = ops.hartley_conv_backward(dz, rec.zs[j + 1], rec.zs[j], w)
+                    dz, gw = ops.hartley_conv_backward(dz, rec.zs[j + 1], rec.zs[j], w, dw=dw_)
                 g_mix.append(gw)
             g_mix.reverse()
             ops.dht3_adjoint(dz, plan, inv_n, epilogue=1, out=dxin)  # dxin += (1/N) C^T dz
@@ -163,8 +181,9 @@ class XSEngine:
                 prev, enc = rec.map_in
                 op = layer.mapping_conv.op
                 tgt = dstash.pop(i - 1) if (i - 1) in dstash else None
+                dw_, db_ = out_w(op)
                 dprev, denc, g_wm, g_bm = ops.pwconv_backward(dxin, rec.xin, prev, enc, _w2(op), 1, False, hw=hw,
-                                                              din1=tgt)
+                                                              din1=tgt, dweight=dw_, dbias=db_)
                 k = nb - 1 - i
                 if k in dstash:
                     dstash[k] += denc
@@ -178,9 +197,13 @@ class XSEngine:
             if layer.conv_concat is not None:
                 g += [g_wc.reshape(layer.conv_concat.op.weight.shape), g_bc]
             block_grads[i] = g
+        dw_, db_ = out_w(m.conv1.op)
         dpre0, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, _w2(m.conv1.op), 1, False, hw=hw,
-                                                   in1_is_selu=True)
-        g_win, g_bin = ops.stem_backward(dpre0, S.x, F, pitch)
+                                                   in1_is_selu=True, dweight=dw_, dbias=db_)
+        dw_, db_ = out_w(m.conv_in.op)
+        g_win, g_bin = ops.stem_backward(dpre0, S.x, F, pitch, dweight=dw_, dbias=db_)
+        if dst is not None:
+            return dst
         grads = [g_win, g_bin, g_w1.reshape(m.conv1.op.weight.shape), g_b1]
         for g in block_grads:
             grads += g

@@ -1,0 +1,130 @@
+"""Data-parallel training plumbing: flat parameter / gradient buffers, ONE all-reduce per step, fused Adamax.
+
+The reference is single-GPU (experiments/run.py:39).  HNOSeg-XS has 28,248 parameters (113 KB), every loss term
+is a mean over (sample, label) pairs (nets/custom_losses.py:70,111), so batch-sharded data parallelism needs
+exactly one SUM all-reduce of the flat gradient per step followed by a division by the world size; the
+optimizer then runs replicated.  One process per GPU, torch.distributed (NCCL over NVLink on the GPU box, gloo
+in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+
+class FlatParameters:
+    """Re-homes all parameters of a module into one contiguous buffer (and a matching gradient buffer)."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters()]
+        if not self.params:
+            raise ValueError('module has no parameters')
+        dev, dt = self.params[0].device, self.params[0].dtype
+        n = sum(p.numel() for p in self.params)
+        self.data = torch.empty(n, dtype=dt, device=dev)
+        self.grad = torch.zeros(n, dtype=dt, device=dev)
+        self.views, self.grad_views = [], []
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.data[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.data[off:off + k].view(p.shape)
+                gv = self.grad[off:off + k].view(p.shape)
+                p.grad = gv
+                self.views.append(p.data)
+                self.grad_views.append(gv)
+                off += k
+        self.numel = n
+
+    def grad_view_of(self, param):
+        for p, g in zip(self.params, self.grad_views):
+            if p is param:
+                return g
+        raise KeyError('parameter is not part of this flat buffer')
+
+
+def allreduce_mean_(flat_grad, group=None):
+    """SUM all-reduce + 1/world scaling of the flat gradient: the only collective of a training step."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.mul_(1.0 / dist.get_world_size(group))
+    return flat_grad
+
+
+def attach_gradient_allreduce(optimizer, flat, group=None):
+    """Drop-in hook for ANY torch.optim optimizer used by experiments/train_test.py:164-171: averages the flat
+    gradient across ranks right before optimizer.step(), leaving the reference's training loop untouched."""
+    def hook(opt, args, kwargs):
+        allreduce_mean_(flat.grad, group)
+    return optimizer.register_step_pre_hook(hook)
+
+
+class FusedAdamax:
+    """torch.optim.Adamax semantics (the reference's optimizer, config_hnoseg_xs.ini:53-55) as ONE kernel over
+    the flat parameter vector; supports a per-step learning rate (cosine warm restarts are computed on the host)."""
+
+    def __init__(self, flat, lr=5e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.flat = flat
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat.data)
+        self.exp_inf = torch.zeros_like(flat.data)
+        self.step_count = 0
+
+    def step(self, lr=None):
+        self.step_count += 1
+        call('hno_adamax_step', ptr(self.flat.data), ptr(self.flat.grad), ptr(self.exp_avg), ptr(self.exp_inf),
+             self.flat.numel, float(self.lr if lr is None else lr), float(self.betas[0]), float(self.betas[1]),
+             float(self.eps), float(self.weight_decay), self.step_count, 1.0, stream_ptr())
+
+    def state_dict(self):
+        return {'exp_avg': self.exp_avg, 'exp_inf': self.exp_inf, 'step': self.step_count, 'lr': self.lr}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd['exp_avg'])
+        self.exp_inf.copy_(sd['exp_inf'])
+        self.step_count = int(sd['step'])
+        self.lr = sd.get('lr', self.lr)
+
+
+class Trainer:
+    """The library's own training step for HNOSegXS: forward, fused head+loss on integer labels, backward straight
+    into the flat gradient buffer (no autograd graph), one gradient all-reduce, fused Adamax.
+
+    Equivalent to the step body of experiments/train_test.py:146-171 with `to_categorical`, `loss_fn(model(x), y)`,
+    `loss.backward()` and `optimizer.step()`; returns the loss as a 1-element device tensor (call .item() to
+    reproduce the reference's per-step host sync).
+    """
+
+    def __init__(self, model, loss_name='DiceLoss', lr=5e-3, group=None):
+        from . import ops
+        self.model = model
+        self.engine = model.engine()
+        self.kind = ops.LOSS_KINDS[loss_name]
+        self.flat = FlatParameters(model)
+        self.slots = self.engine.named_slots()
+        self.dst = [self.flat.grad_view_of(p) for p in self.slots]
+        self.optimizer = FusedAdamax(self.flat, lr=lr)
+        self.group = group
+
+    def loss_and_grad(self, x, labels):
+        from . import ops
+        from .engine import _labels_u8
+        with torch.no_grad():
+            _, S = self.engine.run_forward(x, save=True, head=False)
+            lab = _labels_u8(labels, x)
+            loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], self.kind)
+            self.engine.run_backward(S, fused=(lab, coef, None), dst=self.dst)
+        return loss
+
+    def step(self, x, labels, lr=None):
+        loss = self.loss_and_grad(x, labels)
+        allreduce_mean_(self.flat.grad, self.group)
+        self.optimizer.step(lr)
+        return loss
+
+
+def launches(reset=False):
+    """Kernels launched by libhno_b200.so in this process so far."""
+    return int(_lib.load().hno_launch_count(1 if reset else 0))
