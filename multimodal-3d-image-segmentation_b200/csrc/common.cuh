@@ -44,8 +44,30 @@ constexpr float kSeluAlpha = 1.6732632423543772848170429916717f;
 constexpr float kSeluScale = 1.0507009873554804934193349852946f;
 constexpr float kSeluNeg = kSeluAlpha * kSeluScale;
 
+// SELU with a purpose-built expm1 for the negative branch (16 instructions, one SFU op, instead of ~29 with
+// several SFU/conversion ops for libm's expm1f -- the activation epilogues were 44 % of the dynamic instructions
+// of the 48->24 channel mix):
+//   x in (-0.5, 0]: degree-8 Taylor polynomial of e^x - 1 (relative error < 2e-8, no cancellation)
+//   x <= -0.5     : ex2.approx(x * log2 e) - 1   (relative error of the result <= 1.6 * 2^-22)
+// A plain exp(x) - 1 is NOT acceptable: its cancellation near 0 (relative error ~6e-8/|x|) triples the gradient
+// error of the whole network.  Measured on the oracle (fp32, flat gradient rel-L2 vs the fp64 oracle, 120x112x77):
+// libm expm1 3.8e-4, this scheme 3.7e-4, exp(x) - 1 1.05e-3.
 __device__ __forceinline__ float selu_f(float x) {
-  return x > 0.f ? kSeluScale * x : kSeluNeg * expm1f(x);
+  constexpr float sa = kSeluNeg;
+  float p = sa / 40320.f;
+  p = fmaf(p, x, sa / 5040.f);
+  p = fmaf(p, x, sa / 720.f);
+  p = fmaf(p, x, sa / 120.f);
+  p = fmaf(p, x, sa / 24.f);
+  p = fmaf(p, x, sa / 6.f);
+  p = fmaf(p, x, sa / 2.f);
+  p = fmaf(p, x, sa);
+  p *= x;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  e = fmaf(sa, e, -sa);
+  const float neg = x > -0.5f ? p : e;
+  return x > 0.f ? kSeluScale * x : neg;
 }
 // d selu / d x expressed from the OUTPUT y = selu(x): scale for y>0, y + scale*alpha otherwise.
 __device__ __forceinline__ float selu_grad_from_out(float y) {
@@ -99,6 +121,26 @@ struct Vec<4> {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
 };
+
+// ---- Ampere-style asynchronous global -> shared copies (LDGSTS).  Used as PER-THREAD rings: a thread only reads
+// back bytes it copied itself, so cp.async.wait_group is the only synchronisation the pipelines need.
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+template <int V>
+__device__ __forceinline__ void cp_async_vec(float* smem_dst, const float* gsrc) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (V == 4)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gsrc) : "memory");
+  else if (V == 2)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(gsrc) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // Largest vector width in {4,2,1} that divides every given stride / count and the pointer alignment.
 inline int pick_vec(const void* const* ptrs, int nptr, const long* counts, int ncount) {

@@ -28,61 +28,92 @@ __device__ __forceinline__ float act_grad_from_out(float y) {
 }
 
 // ------------------------------------------------------------------------------------------ forward
+constexpr int kFwdRows = 8;    // input-channel rows per pipeline stage
+constexpr int kFwdStages = 4;  // stages of the per-thread cp.async ring
+
+// Persistent CTAs; every thread owns V adjacent voxels of a tile and streams the CI input rows of that tile
+// through a PRIVATE 4-stage cp.async ring in shared memory (it only ever reads back the bytes it copied itself,
+// so the pipeline needs no barriers at all).  The ring keeps 3 x 8 rows x V x 4 B per thread in flight
+// (96 KB per SM at 2 CTAs), and it runs across tile boundaries, so HBM latency is paid once per kernel.
 template <int CI1, int CI2, int CO, int ACT, bool RES, int V>
 __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_fwd(const float* __restrict__ in1,
                                                               const float* __restrict__ in2,
                                                               const float* __restrict__ weight,
                                                               const float* __restrict__ bias, float* __restrict__ out,
-                                                              long S) {
+                                                              long S, int tiles_per_sample, long total_tiles) {
   static_assert(!RES || (CI1 == CO && CI2 == 0), "residual needs CI1 == CO and a single input");
   constexpr int CI = CI1 + CI2;
+  static_assert(CI % kFwdRows == 0, "input channels must be a multiple of 8");
+  constexpr int NCH = CI / kFwdRows;
   constexpr int COp = (CO + 3) & ~3;
-  __shared__ __align__(16) float wt[CI * COp];  // transposed: wt[i][o]
-  __shared__ __align__(16) float sbias[COp];
+  constexpr int TV = kPwThreads * V;
+  extern __shared__ float4 smem4[];
+  float* wt = reinterpret_cast<float*>(smem4);      // [CI][COp] transposed weights
+  float* sbias = wt + CI * COp;                      // [COp]
+  float* ring = sbias + COp;                         // [kFwdStages][kFwdRows][TV]
   for (int idx = threadIdx.x; idx < CI * COp; idx += kPwThreads) {
     int i = idx / COp, o = idx - i * COp;
     wt[idx] = o < CO ? weight[o * CI + i] : 0.f;
   }
   for (int o = threadIdx.x; o < COp; o += kPwThreads) sbias[o] = (bias != nullptr && o < CO) ? bias[o] : 0.f;
   __syncthreads();
-  const long s0 = (blockIdx.x * (long)kPwThreads + threadIdx.x) * V;
-  if (s0 >= S) return;
-  const int b = blockIdx.y;
+
+  const int lv = threadIdx.x * V;
+  const long n_my = total_tiles > blockIdx.x ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long G = n_my * NCH;
+
+  auto issue = [&](long g) {
+    if (g < G) {
+      const long k = g / NCH;
+      const int ch = (int)(g - k * NCH);
+      const long tile = blockIdx.x + k * gridDim.x;
+      const int b = (int)(tile / tiles_per_sample);
+      const long s0 = (tile - (long)b * tiles_per_sample) * TV + lv;
+      if (s0 < S) {
+        float* dst = ring + ((int)(g % kFwdStages) * kFwdRows) * TV + lv;
+#pragma unroll
+        for (int r = 0; r < kFwdRows; ++r) {
+          const int c = ch * kFwdRows + r;
+          const float* src = (CI2 == 0 || c < CI1) ? in1 + ((long)b * CI1 + c) * S + s0
+                                                   : in2 + ((long)b * CI2 + (c - CI1)) * S + s0;
+          cp_async_vec<V>(dst + r * TV, src);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int g = 0; g < kFwdStages - 1; ++g) issue(g);
+
   // acc[op][v] = (out[2 op][v], out[2 op + 1][v]): output channels are paired so that the weight pair comes
   // straight out of one LDS.128 and each FFMA2 retires two FMAs
   float2 acc[COp / 2][V];
+  for (long g = 0; g < G; ++g) {
+    issue(g + kFwdStages - 1);
+    cp_async_wait_group<kFwdStages - 1>();
+    const long k = g / NCH;
+    const int ch = (int)(g - k * NCH);
+    if (ch == 0) {
 #pragma unroll
-  for (int op = 0; op < COp / 2; ++op)
+      for (int op = 0; op < COp / 2; ++op)
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[op][v] = make_float2(sbias[2 * op], sbias[2 * op + 1]);
-
-  const float* p1 = in1 + (long)b * CI1 * S + s0;
-#pragma unroll 4
-  for (int i = 0; i < CI1; ++i) {
-    Vec<V> x = Vec<V>::ld(p1 + (long)i * S);
-    float2 xd[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) xd[v] = dup2(x.v[v]);
-    const float4* w4 = reinterpret_cast<const float4*>(wt + i * COp);
-#pragma unroll
-    for (int q = 0; q < COp / 4; ++q) {
-      const float4 w = w4[q];
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        acc[2 * q + 0][v] = ffma2(make_float2(w.x, w.y), xd[v], acc[2 * q + 0][v]);
-        acc[2 * q + 1][v] = ffma2(make_float2(w.z, w.w), xd[v], acc[2 * q + 1][v]);
-      }
+        for (int v = 0; v < V; ++v) acc[op][v] = make_float2(sbias[2 * op], sbias[2 * op + 1]);
     }
-  }
-  if (CI2 > 0) {
-    const float* p2 = in2 + (long)b * CI2 * S + s0;
-#pragma unroll 4
-    for (int i = 0; i < CI2; ++i) {
-      Vec<V> x = Vec<V>::ld(p2 + (long)i * S);
-      float2 xd[V];
+    const float* src = ring + ((int)(g % kFwdStages) * kFwdRows) * TV + lv;
 #pragma unroll
-      for (int v = 0; v < V; ++v) xd[v] = dup2(x.v[v]);
-      const float4* w4 = reinterpret_cast<const float4*>(wt + (CI1 + i) * COp);
+    for (int r = 0; r < kFwdRows; ++r) {
+      float2 xd[V];
+      if (V == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(src + r * TV);
+        xd[0] = dup2(t.x); xd[1 % V] = dup2(t.y); xd[2 % V] = dup2(t.z); xd[3 % V] = dup2(t.w);
+      } else if (V == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(src + r * TV);
+        xd[0] = dup2(t.x); xd[1 % V] = dup2(t.y);
+      } else {
+        xd[0] = dup2(src[r * TV]);
+      }
+      const float4* w4 = reinterpret_cast<const float4*>(wt + (ch * kFwdRows + r) * COp);
 #pragma unroll
       for (int q = 0; q < COp / 4; ++q) {
         const float4 w = w4[q];
@@ -93,26 +124,32 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_fwd(const float* __res
         }
       }
     }
-  }
-  float* po = out + (long)b * CO * S + s0;
+    if (ch == NCH - 1) {
+      const long tile = blockIdx.x + k * gridDim.x;
+      const int b = (int)(tile / tiles_per_sample);
+      const long s0 = (tile - (long)b * tiles_per_sample) * TV + lv;
+      if (s0 < S) {
+        float* po = out + (long)b * CO * S + s0;
 #pragma unroll
-  for (int o = 0; o < CO; ++o) {
-    Vec<V> r;
+        for (int o = 0; o < CO; ++o) {
+          Vec<V> r;
 #pragma unroll
-    for (int v = 0; v < V; ++v) r.v[v] = (o & 1) ? acc[o / 2][v].y : acc[o / 2][v].x;
-    if (RES) {
-      Vec<V> x = Vec<V>::ld(p1 + (long)o * S);  // second touch of the same line: L1 hit
+          for (int v = 0; v < V; ++v) r.v[v] = (o & 1) ? acc[o / 2][v].y : acc[o / 2][v].x;
+          if (RES) {
+            Vec<V> x = Vec<V>::ld(in1 + ((long)b * CI1 + o) * S + s0);  // just streamed: L2 hit
 #pragma unroll
-      for (int v = 0; v < V; ++v) r.v[v] += x.v[v];
+            for (int v = 0; v < V; ++v) r.v[v] += x.v[v];
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) r.v[v] = act_f<ACT>(r.v[v]);
+          r.st(po + (long)o * S);
+        }
+      }
     }
-#pragma unroll
-    for (int v = 0; v < V; ++v) r.v[v] = act_f<ACT>(r.v[v]);
-    r.st(po + (long)o * S);
   }
 }
 
 // ------------------------------------------------------------------------------------------ backward
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // global [C][S] columns (lv .. lv+VV) of this thread -> shared [C][TVS], asynchronously (LDGSTS)
 template <int C, int VV, int TVS>
@@ -345,24 +382,38 @@ static int bwd_grid(long total_tiles) {
   return (int)(total_tiles < g ? total_tiles : g);
 }
 
+template <int CI1, int CI2, int CO, int V>
+static size_t fwd_smem() {
+  constexpr int COp = (CO + 3) & ~3;
+  return (size_t)((CI1 + CI2) * COp + COp + kFwdStages * kFwdRows * kPwThreads * V) * sizeof(float);
+}
+
+template <int CI1, int CI2, int CO, int ACT, bool RES, int V>
+static int fwd_launch(const float* in1, const float* in2, const float* w, const float* bias, float* out, int B, long S,
+                      cudaStream_t st) {
+  constexpr int TV = kPwThreads * V;
+  const int tps = ceil_div(S, TV);
+  const long total = (long)tps * B;
+  const long gmax = (long)sm_count() * 2;
+  const int grid = (int)(total < gmax ? total : gmax);
+  auto kern = k_pwconv_fwd<CI1, CI2, CO, ACT, RES, V>;
+  const size_t smem = fwd_smem<CI1, CI2, CO, V>();
+  HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kPwThreads, smem, st>>>(in1, in2, w, bias, out, S, tps, total);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int CI1, int CI2, int CO, int ACT, bool RES>
 static int fwd_t(const float* in1, const float* in2, const float* w, const float* bias, float* out, int B, long S,
                  cudaStream_t st) {
   const void* ptrs[3] = {in1, in2, out};
   const long cnt[1] = {S};
   int v = pick_vec(ptrs, 3, cnt, 1);
-  // 2 voxels per thread keeps the CO/2 x V packed accumulators + operands under 85 registers (3 CTAs / SM);
-  // 4 voxels would need ~160 registers and halve the number of loads in flight per SM.
-  if (CO > 8 && v == 4) v = 2;
-  dim3 grid(ceil_div(S / v, kPwThreads), B);
-  if (v == 4)
-    k_pwconv_fwd<CI1, CI2, CO, ACT, RES, 4><<<grid, kPwThreads, 0, st>>>(in1, in2, w, bias, out, S);
-  else if (v == 2)
-    k_pwconv_fwd<CI1, CI2, CO, ACT, RES, 2><<<grid, kPwThreads, 0, st>>>(in1, in2, w, bias, out, S);
-  else
-    k_pwconv_fwd<CI1, CI2, CO, ACT, RES, 1><<<grid, kPwThreads, 0, st>>>(in1, in2, w, bias, out, S);
-  HNO_LAUNCH_CHECK();
-  return 0;
+  // 2 voxels per thread keep the CO/2 x V packed accumulators + operands at ~110 registers (2 CTAs / SM)
+  if (v == 4) v = 2;
+  if (v == 2) return fwd_launch<CI1, CI2, CO, ACT, RES, 2>(in1, in2, w, bias, out, B, S, st);
+  return fwd_launch<CI1, CI2, CO, ACT, RES, 1>(in1, in2, w, bias, out, B, S, st);
 }
 
 template <int CI1, int CI2, int CO, int VV>
