@@ -33,6 +33,10 @@ const char* hno_last_error(void);
 int hno_device_check(void);
 /* Number of CUDA kernels this library has launched in the process (optionally reset to 0). */
 long hno_launch_count(int reset);
+/* The HBM-bound contractions (pointwise convolutions, D-axis stages of the truncated DHT) run on the tcgen05 tensor
+ * cores with 3xTF32 operand splitting whenever strides allow TMA (16-byte multiples).  This switch forces the fp32
+ * CUDA-core kernels instead (A/B measurements, tests); returns the previous setting.  Default: enabled. */
+int hno_set_tensor_cores(int enable);
 
 /* ------------------------------------------------------------------------------------------
  * Truncated 3-D discrete Hartley transform.

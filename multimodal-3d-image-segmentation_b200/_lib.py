@@ -27,6 +27,7 @@ SIGNATURES = {
     'hno_last_error': (c_char_p, []),
     'hno_device_check': (_I, []),
     'hno_launch_count': (_L, [_I]),
+    'hno_set_tensor_cores': (_I, [_I]),
     'hno_dht3_plan_bytes': (_Z, [_I] * 6),
     'hno_dht3_plan_fill': (_I, [_P, _Z, _I, _I, _I, _P, _I, _P, _I, _P, _I]),
     'hno_dht3_workspace_bytes': (_Z, [_P, _L, _I]),

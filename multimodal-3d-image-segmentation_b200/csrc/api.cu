@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "dht_plan.h"
 #include "hno_b200.h"
+#include "tc_stream.h"
 
 #include <atomic>
 #include <stdarg.h>
@@ -76,6 +77,7 @@ using namespace hno;
 extern "C" {
 
 int hno_version(void) { return HNO_B200_VERSION; }
+int hno_set_tensor_cores(int enable) { return tc_set_enabled(enable); }
 const char* hno_last_error(void) { return g_err; }
 
 long hno_launch_count(int reset) {

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "dht_plan.h"
 #include "hno_b200.h"
+#include "tc_stream.h"
 
 namespace hno {
 
@@ -455,6 +456,7 @@ struct OuterArgs {
   int valid_cols;
   float scale;
   int epi;
+  bool tc_ok = false;  // the D stages (whole planes, one slab per batch item) may use the tensor-core path
 };
 
 template <int JCB, int JSB, int V>
@@ -528,7 +530,56 @@ static int pick_outer_vec(const OuterArgs& a) {
     }                                                                      \
   } while (0)
 
+// Tensor-core route for the two HBM-bound stages (analysis / synthesis along D over whole planes).
+static bool tc_outer(const OuterArgs& a, bool synthesis, TcStreamArgs* t) {
+  TcStreamArgs r{};
+  r.nsrc = 1;
+  r.a[0] = a.in;
+  r.lda[0] = a.in_rs;
+  r.gsa[0] = a.in_bs;
+  r.mext = a.ncols;
+  r.G = (int)a.nbatch;
+  r.b = a.full;
+  r.scale = a.scale;
+  r.bias = nullptr;
+  r.out = a.out;
+  r.ldo = a.out_rs;
+  r.gso = a.out_bs;
+  if (!synthesis) {
+    r.rows[0] = a.n;
+    r.kc = 32;
+    r.chunks_per_src = (a.n + 31) / 32;
+    r.ldbn = a.n;
+    r.ldbk = 1;
+    r.kvalid = a.n;
+    r.nout = a.J;
+    r.valid_m = a.ncols;
+    r.act = 0;
+    r.epi = 0;
+  } else {
+    r.rows[0] = a.J;
+    r.kc = a.J <= 8 ? 8 : (a.J <= 24 ? 24 : 32);
+    r.chunks_per_src = (a.J + r.kc - 1) / r.kc;
+    r.ldbn = 1;
+    r.ldbk = a.n;
+    r.kvalid = a.J;
+    r.nout = a.n;
+    r.valid_m = a.valid_cols;
+    r.act = a.epi == 2 ? 1 : 0;
+    r.epi = a.epi == 1 ? 1 : 0;
+  }
+  if (a.nbatch >= (1L << 31) || a.ncols < 1024 || a.out_rs % 4 || a.out_bs % 4 ||
+      reinterpret_cast<uintptr_t>(a.out) % 16 || !tc_stream_eligible(r))
+    return false;
+  *t = r;
+  return true;
+}
+
 static int launch_analysis(const OuterArgs& a, cudaStream_t st) {
+  {
+    TcStreamArgs t;
+    if (a.tc_ok && tc_outer(a, false, &t)) return tc_stream_launch(t, st);
+  }
   HNO_OUTER_DISPATCH(launch_analysis_t, a, st);
   const long total = a.nbatch * a.J * a.ncols;
   k_analysis_outer_generic<<<ceil_div(total, 256), 256, 0, st>>>(a.in, a.out, a.full, a.n, a.J, a.ncols, total,
@@ -538,6 +589,10 @@ static int launch_analysis(const OuterArgs& a, cudaStream_t st) {
 }
 
 static int launch_synthesis(const OuterArgs& a, cudaStream_t st) {
+  {
+    TcStreamArgs t;
+    if (a.tc_ok && tc_outer(a, true, &t)) return tc_stream_launch(t, st);
+  }
   HNO_OUTER_DISPATCH(launch_synthesis_t, a, st);
   const long total = a.nbatch * a.n * a.ncols;
   if (a.epi == 0)
@@ -602,6 +657,7 @@ int dht3_forward(const void* plan_host, const void* plan_dev, const float* x, lo
     const DhtAxis& ax = h->ax[0];
     OuterArgs a{x, G1, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
                 ax.J, (int)plane_pitch, nslab, plane_pitch, slab_stride, plane_pitch, g.g1, (int)plane_pitch, 1.f, 0};
+    a.tc_ok = true;
     if (int rc = launch_analysis(a, st)) return rc;
   }
   {  // stage 2: H
@@ -670,6 +726,7 @@ int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, fl
     const DhtAxis& ax = h->ax[0];
     OuterArgs a{G1, x, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
                 ax.J, (int)plane_pitch, nslab, plane_pitch, g.g1, plane_pitch, slab_stride, g.H * g.W, 1.f, epilogue};
+    a.tc_ok = true;
     if (int rc = launch_synthesis(a, st)) return rc;
   }
   return 0;

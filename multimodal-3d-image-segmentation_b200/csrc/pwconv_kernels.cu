@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "hno_b200.h"
 #include "wgrad.cuh"
+#include "tc_stream.h"
 
 namespace hno {
 
@@ -487,6 +488,37 @@ int pwconv_forward(const float* in1, const float* in2, const float* w, const flo
                    int ci2, int co, long S, int act, int residual, cudaStream_t st) {
   HNO_CHECK(in1 && w && out && (ci2 == 0 || in2), "pwconv_forward: null pointer");
   HNO_CHECK(B >= 1 && B <= 65535 && S >= 1, "pwconv_forward: bad sizes B=%d S=%ld", B, S);
+  if (!residual && (ci2 == 0 || ci2 == ci1) && S >= 4096) {
+    // tensor-core path (tcgen05, 3xTF32): the activation streams through TMA exactly once
+    TcStreamArgs a{};
+    a.a[0] = in1;
+    a.a[1] = in2;
+    a.lda[0] = a.lda[1] = S;
+    a.gsa[0] = (long)ci1 * S;
+    a.gsa[1] = (long)ci2 * S;
+    a.rows[0] = ci1;
+    a.rows[1] = ci2;
+    a.nsrc = ci2 > 0 ? 2 : 1;
+    a.mext = S;
+    a.G = B;
+    a.kc = ci1 % 32 == 0 ? 32 : (ci1 % 24 == 0 ? 24 : (ci1 % 8 == 0 ? 8 : 0));
+    a.chunks_per_src = a.kc ? ci1 / a.kc : 0;
+    a.b = w;
+    a.ldbn = ci1 + ci2;
+    a.ldbk = 1;
+    a.kvalid = ci1 + ci2;
+    a.scale = 1.f;
+    a.bias = bias;
+    a.out = out;
+    a.ldo = S;
+    a.gso = (long)co * S;
+    a.nout = co;
+    a.valid_m = S;
+    a.act = act;
+    a.epi = 0;
+    if (a.kc && (act == 0 || act == 1) && reinterpret_cast<uintptr_t>(out) % 16 == 0 && tc_stream_eligible(a))
+      return tc_stream_launch(a, st);
+  }
 #define X(A, B_, C, D, E)                                                     \
   if (ci1 == A && ci2 == B_ && co == C && act == D && (residual != 0) == E)   \
     return fwd_t<A, B_, C, D, E>(in1, in2, w, bias, out, B, S, st);

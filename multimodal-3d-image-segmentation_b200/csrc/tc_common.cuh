@@ -1,0 +1,149 @@
+// tcgen05 / TMEM / TMA / mbarrier primitives (inline PTX, sm_100a) shared by the tensor-core kernels.
+//
+// Every encoding below was verified on a B200 with tools/tc_probe.cu (profiles/r1_tc_probe.log):
+//   * tf32 operand with the GEMM M (or N) index contiguous in memory ("MN-major"): TMA tensor map swizzle
+//     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B  <->  UMMA layout type 1 (SWIZZLE_128B_BASE32B); atoms are 32 floats (MN) x 4
+//     rows (K) = 512 B, SBO = 512 B between K atoms, LBO = byte distance between 32-float MN blocks.
+//   * tf32 operand with K contiguous ("K-major"): TMA CU_TENSOR_MAP_SWIZZLE_128B <-> UMMA layout type 2, 8-row groups
+//     of 128 B rows, SBO = 1024 B, one MMA (K = 8) advances the start address by 32 B.
+//   * K-major operand without swizzle written by ordinary stores: 8 x 16 B core matrices, LBO between the two K halves,
+//     SBO between 8-row groups.
+//   * M = 128 accumulators: row i = TMEM lane i; M = 64: row i = lane (i / 16) * 32 + i % 16.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hno {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared memory matrix descriptor (64 bit)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+constexpr uint32_t kLayoutNone = 0, kLayoutSw128Base32 = 1, kLayoutSw128 = 2;
+
+// ---- instruction descriptor for kind::tf32, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---- TMA (tile mode, 3-D tensor map, completion on an mbarrier)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// ---- proxy / tcgen05 fences
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp executes these)
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- MMA issue (one thread) and completion -> mbarrier
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// tf32 operand split: the tensor core reads an fp32 word and ignores the 13 low mantissa bits, so the "hi" part of
+// x is x itself (as stored) and only the remainder has to be materialised.  3xTF32: a*b ~= ah*bh + al*bh + ah*bl.
+// round-to-nearest (ties away) conversion to TF32, returned in an fp32 container
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_lo(float x) { return x - tf32_hi(x); }
+
+// Element (n, k) of a K-major, non-swizzled operand image: 8 x 16 B core matrices, the two K halves of one MMA 128 B
+// apart, 8-row groups 256 B apart, one MMA (K = 8) per `kstep` = (NROWS / 8) * 256 bytes.  Returns a float index.
+template <int NROWS>
+__device__ __host__ __forceinline__ int kmajor_plain_index(int n, int k) {
+  return ((k >> 3) * (NROWS / 8) * 256 + ((k & 7) >> 2) * 128 + (n >> 3) * 256 + (n & 7) * 16 + (k & 3) * 4) >> 2;
+}
+constexpr uint32_t kPlainLbo = 128, kPlainSbo = 256;
+
+}  // namespace tc
+
+// Host side: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+// dims/strides innermost first; strides (bytes) for dims 1..rank-1.  Returns 0 on success (error set otherwise).
+int encode_tensor_map(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box, int swizzle /* 0 none, 1 128B, 2 128B_ATOM_32B */);
+
+}  // namespace hno

@@ -1,0 +1,40 @@
+// Host interface of the streamed tensor-core contraction (tc_stream.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace hno {
+
+// out[g][n][m] (op)= act( scale * sum_k A[g][k][m] * B[n][k] + bias[n] )
+//   A: nsrc (1 or 2) tensors [G][rows][mext] (row stride lda, slab stride gsa, floats); the K axis is the virtual
+//      concatenation of chunks_per_src * kc rows of each source (rows beyond rows[i] read as zero).
+//   B: b[n * ldbn + k * ldbk], n < nout, k < kvalid (zero beyond).
+//   out: out[g * gso + n * ldo + m];  columns m >= valid_m are written as 0 (epi 0) or left untouched (epi 1).
+struct TcStreamArgs {
+  const float* a[2];
+  long lda[2], gsa[2];
+  int rows[2];
+  int nsrc;
+  long mext;
+  int G;
+  int kc;              // rows per chunk: 8, 24 or 32
+  int chunks_per_src;
+  const float* b;
+  long ldbn, ldbk;
+  int kvalid;
+  float scale;
+  const float* bias;   // [nout] or null
+  float* out;
+  long ldo, gso;
+  int nout;
+  long valid_m;
+  int act;             // 0 none, 1 SELU
+  int epi;             // 0 store, 1 accumulate
+};
+
+bool tc_stream_eligible(const TcStreamArgs& a);
+int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st);
+// Global switch (tests / A-B measurements): returns the previous value.
+int tc_set_enabled(int on);
+bool tc_enabled();
+
+}  // namespace hno
