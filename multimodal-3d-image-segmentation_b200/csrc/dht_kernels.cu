@@ -547,8 +547,8 @@ static bool tc_outer(const OuterArgs& a, bool synthesis, TcStreamArgs* t) {
   r.gso = a.out_bs;
   if (!synthesis) {
     r.rows[0] = a.n;
-    r.kc = 32;
-    r.chunks_per_src = (a.n + 31) / 32;
+    r.kc = 16;
+    r.chunks_per_src = (a.n + 15) / 16;
     r.ldbn = a.n;
     r.ldbk = 1;
     r.kvalid = a.n;

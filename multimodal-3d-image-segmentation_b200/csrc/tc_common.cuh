@@ -69,6 +69,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 prefetch of a box (no shared-memory destination, no completion tracking): decouples the number of bytes in flight
+// towards HBM from the shared-memory stage count.
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1),
+               "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

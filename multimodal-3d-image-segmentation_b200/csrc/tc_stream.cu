@@ -25,13 +25,16 @@
 #include "tc_stream.h"
 
 #include <atomic>
+#include <stdio.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace hno {
 
 using namespace tc;
 
-constexpr int kTcThreads = 128;
+constexpr int kTcWorkers = 128;            // 4 worker warps: operand split + epilogue (one TMEM lane each)
+constexpr int kTcThreads = kTcWorkers + 64;  // + warp 4: TMA producer, warp 5: MMA issuer
 
 struct TcDev {
   const float* b;
@@ -42,39 +45,54 @@ struct TcDev {
   float* out;
   long ldo, gso;
   int nout;
-  long mext, valid_m;
+  int mext, valid_m;
   int nchunk, chunks_per_src;
   int tiles_per_slab;
-  long total_tiles;
+  int total_tiles;
   int act, epi;
 };
 
-template <int KC, int NPAD, int NST>
+template <int KC, int NPAD, int NST, int kNLo>
 struct TcSmem {
   static constexpr int kChunkBytes = KC * 512;  // 4 blocks of 32 m x KC rows x 4 B
   static size_t bytes(int nchunk) {
-    return 1024 /* alignment slack */ + (size_t)(NST + 2) * kChunkBytes + (size_t)2 * NPAD * nchunk * KC * 4 + NPAD * 4;
+    return 1024 /* alignment slack */ + (size_t)(NST + kNLo) * kChunkBytes + (size_t)2 * NPAD * nchunk * KC * 4 +
+           NPAD * 4;
   }
 };
 
-template <int KC, int NPAD, int NST>
-__global__ void __launch_bounds__(kTcThreads) k_tc_stream(const __grid_constant__ CUtensorMap tm0,
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// round-to-nearest TF32 "hi" part with two integer ops (half-ulp add, mask) -- the F2F conversion unit is an
+// eighth-rate pipe and would dominate the operand split
+__device__ __forceinline__ float rn_tf32_bits(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+template <int KC, int NPAD, int NST, int kNLo>
+__global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2 : 1))) k_tc_stream(const __grid_constant__ CUtensorMap tm0,
                                                            const __grid_constant__ CUtensorMap tm1, const TcDev p) {
   constexpr int kChunkBytes = KC * 512;
   constexpr int NKG = KC / 8;
   constexpr uint32_t kIdesc = make_idesc_tf32(128, NPAD, 1, 0);
-  constexpr uint32_t kTmemCols = NPAD < 32 ? 32 : NPAD;
+  constexpr uint32_t kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;  // two accumulator buffers
   static_assert(KC % 8 == 0 && NPAD % 16 == 0 && NPAD <= 256, "bad tile configuration");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* raw = smem;                                     // [NST][kChunkBytes]
-  uint8_t* lob = raw + (size_t)NST * kChunkBytes;          // [2][kChunkBytes]
-  float* bhi = reinterpret_cast<float*>(lob + 2 * kChunkBytes);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // align on the shared-window address so that the compiler keeps the shared address space (LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* raw = smem;                              // [NST][kChunkBytes]
+  uint8_t* lob = raw + NST * kChunkBytes;           // [kNLo][kChunkBytes]
+  float* bhi = reinterpret_cast<float*>(lob + kNLo * kChunkBytes);
   const int ktot = p.nchunk * KC;
-  float* blo = bhi + (size_t)NPAD * ktot;
-  float* sbias = blo + (size_t)NPAD * ktot;
-  __shared__ __align__(8) uint64_t bar_full[NST];
-  __shared__ __align__(8) uint64_t bar_done[NST];
+  float* blo = bhi + NPAD * ktot;
+  float* sbias = blo + NPAD * ktot;
+  __shared__ __align__(8) uint64_t bar_full[NST];   // TMA bytes landed                     (1 arrival + tx)
+  __shared__ __align__(8) uint64_t bar_split[NST];  // hi / lo operands ready                (128 arrivals)
+  __shared__ __align__(8) uint64_t bar_done[NST];   // MMAs of the item retired              (tcgen05.commit)
+  __shared__ __align__(8) uint64_t bar_accfree[2];  // accumulator buffer drained by epilogue (128 arrivals)
+  __shared__ __align__(8) uint64_t bar_accfull[2];  // all MMAs of a tile retired            (tcgen05.commit)
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -84,153 +102,225 @@ __global__ void __launch_bounds__(kTcThreads) k_tc_stream(const __grid_constant_
     const int n = idx / ktot, k = idx - n * ktot;
     float v = 0.f;
     if (n < p.nvalid && k < p.kvalid) v = p.scale * __ldg(p.b + (long)n * p.ldbn + (long)k * p.ldbk);
-    float hi, lo;
-    hi = rna_tf32(v);
-    lo = rna_tf32(v - hi);
+    const float hi = rn_tf32_bits(v);
     const int o = kmajor_plain_index<NPAD>(n, k);
     bhi[o] = hi;
-    blo[o] = lo;
+    blo[o] = v - hi;
   }
   for (int n = tid; n < NPAD; n += kTcThreads) sbias[n] = (p.bias != nullptr && n < p.nout) ? __ldg(p.bias + n) : 0.f;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NST; ++s) {
       mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_split[s], kTcWorkers);
       mbar_init(&bar_done[s], 1);
     }
+    mbar_init(&bar_accfree[0], kTcWorkers);
+    mbar_init(&bar_accfree[1], kTcWorkers);
+    mbar_init(&bar_accfull[0], 1);
+    mbar_init(&bar_accfull[1], 1);
     mbar_fence_init();
-    tma_prefetch_desc(&tm0);
-    tma_prefetch_desc(&tm1);
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+  if (warp == 4) tmem_alloc(&tmem_slot, kTmemCols);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  const long my_tiles = p.total_tiles > blockIdx.x ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long nitems = my_tiles * p.nchunk;
+  const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nchunk = p.nchunk;
 
-  auto issue_load = [&](long it) {  // thread 0 only
-    const long ti = it / p.nchunk;
-    const int c = (int)(it - ti * p.nchunk);
-    const long tile = blockIdx.x + ti * gridDim.x;
-    const int g = (int)(tile / p.tiles_per_slab);
-    const int m0 = (int)(tile - (long)g * p.tiles_per_slab) * 128;
-    const int src = c / p.chunks_per_src;
-    const int row0 = (c - src * p.chunks_per_src) * KC;
-    const int s = (int)(it % NST);
-    uint8_t* dst = raw + (size_t)s * kChunkBytes;
-    mbar_expect_tx(&bar_full[s], kChunkBytes);
-    const CUtensorMap* tm = src == 0 ? &tm0 : &tm1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * (KC * 128), tm, m0 + 32 * j, row0, g, &bar_full[s]);
-  };
-
-  if (tid == 0) {
-    for (long it = 0; it < NST - 1 && it < nitems; ++it) issue_load(it);
-  }
-
-  for (long it = 0; it < nitems; ++it) {
-    const int s = (int)(it % NST);
-    const uint32_t ph = (uint32_t)((it / NST) & 1);
-    const long ti = it / p.nchunk;
-    const int c = (int)(it - ti * p.nchunk);
-    mbar_wait(&bar_full[s], ph);
-    if (it >= 2) {  // the lo buffer of item it-2 must have been consumed
-      const long j = it - 2;
-      mbar_wait(&bar_done[j % NST], (uint32_t)((j / NST) & 1));
-    }
-    // ---- operand split: hi in place, lo to the side buffer
-    {
-      float4* r4 = reinterpret_cast<float4*>(raw + (size_t)s * kChunkBytes);
-      float4* l4 = reinterpret_cast<float4*>(lob + (size_t)(it & 1) * kChunkBytes);
-#pragma unroll
-      for (int i = 0; i < kChunkBytes / 16 / kTcThreads; ++i) {
-        const int idx = tid + i * kTcThreads;
-        const float4 x = r4[idx];
-        float4 h, l;
-        h.x = rna_tf32(x.x);
-        h.y = rna_tf32(x.y);
-        h.z = rna_tf32(x.z);
-        h.w = rna_tf32(x.w);
-        l.x = rna_tf32(x.x - h.x);
-        l.y = rna_tf32(x.y - h.y);
-        l.z = rna_tf32(x.z - h.z);
-        l.w = rna_tf32(x.w - h.w);
-        r4[idx] = h;
-        l4[idx] = l;
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after_sync();
-      const uint32_t a_hi = smem_u32(raw + (size_t)s * kChunkBytes);
-      const uint32_t a_lo = smem_u32(lob + (size_t)(it & 1) * kChunkBytes);
-      const uint32_t b_hi = smem_u32(bhi), b_lo = smem_u32(blo);
-#pragma unroll
-      for (int g = 0; g < NKG; ++g) {
-        const uint32_t boff = (uint32_t)(c * NKG + g) * (NPAD / 8) * 256;
-        const uint64_t dah = make_smem_desc(a_hi + g * 1024, KC * 128, 512, kLayoutSw128Base32);
-        const uint64_t dal = make_smem_desc(a_lo + g * 1024, KC * 128, 512, kLayoutSw128Base32);
-        const uint64_t dbh = make_smem_desc(b_hi + boff, kPlainLbo, kPlainSbo, kLayoutNone);
-        const uint64_t dbl = make_smem_desc(b_lo + boff, kPlainLbo, kPlainSbo, kLayoutNone);
-        mma_tf32(tmem, dal, dbh, kIdesc, !(c == 0 && g == 0));
-        mma_tf32(tmem, dah, dbl, kIdesc, true);
-        mma_tf32(tmem, dah, dbh, kIdesc, true);
-      }
-      mma_commit(&bar_done[s]);
-      // refill the stage used by the previous item with the load that is NST-1 items ahead
-      const long nxt = it + NST - 1;
-      if (nxt < nitems) {
-        if (it >= 1) {
-          const long j = it - 1;
-          mbar_wait(&bar_done[j % NST], (uint32_t)((j / NST) & 1));
+  if (warp == 4) {
+    // =============================================================== TMA producer (one thread)
+    if (lane == 0) {
+      tma_prefetch_desc(&tm0);
+      tma_prefetch_desc(&tm1);
+      // (tile, chunk) cursor; `pf` runs kPrefetch items ahead of `ld` and only warms L2
+      struct Cursor {
+        int ti, c, src, cs, row0, g, m0;
+      };
+      auto locate = [&](Cursor& k) {
+        const uint32_t tile = blockIdx.x + (uint32_t)k.ti * gridDim.x;
+        k.g = tile / (uint32_t)p.tiles_per_slab;
+        k.m0 = (tile - (uint32_t)k.g * p.tiles_per_slab) * 128;
+      };
+      auto advance = [&](Cursor& k) {
+        k.row0 += KC;
+        if (++k.cs == p.chunks_per_src) {
+          k.cs = 0;
+          k.row0 = 0;
+          ++k.src;
         }
-        issue_load(nxt);
+        if (++k.c == nchunk) {
+          k.c = 0;
+          k.src = 0;
+          k.cs = 0;
+          k.row0 = 0;
+          ++k.ti;
+          if (k.ti < my_tiles) locate(k);
+        }
+      };
+      constexpr int kPrefetch = (96 * 1024) / kChunkBytes;
+      Cursor ld{0, 0, 0, 0, 0, 0, 0}, pf{0, 0, 0, 0, 0, 0, 0};
+      if (my_tiles > 0) {
+        locate(ld);
+        locate(pf);
+      }
+      for (int i = 0; i < kPrefetch && pf.ti < my_tiles; ++i) {
+        const CUtensorMap* tm = pf.src == 0 ? &tm0 : &tm1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_prefetch_l2_3d(tm, pf.m0 + 32 * j, pf.row0, pf.g);
+        advance(pf);
+      }
+      int it = 0, s = 0;
+      uint32_t ph = 0;  // parity of the current use of stage s
+      while (ld.ti < my_tiles) {
+        if (pf.ti < my_tiles) {
+          const CUtensorMap* tm = pf.src == 0 ? &tm0 : &tm1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_prefetch_l2_3d(tm, pf.m0 + 32 * j, pf.row0, pf.g);
+          advance(pf);
+        }
+        if (it >= NST) mbar_wait(&bar_done[s], ph ^ 1);  // previous use of this stage fully consumed
+        uint8_t* dst = raw + s * kChunkBytes;
+        mbar_expect_tx(&bar_full[s], kChunkBytes);
+        const CUtensorMap* tm = ld.src == 0 ? &tm0 : &tm1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * (KC * 128), tm, ld.m0 + 32 * j, ld.row0, ld.g, &bar_full[s]);
+        advance(ld);
+        ++it;
+        if (++s == NST) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
-    if (c == p.nchunk - 1) {
-      // ---- epilogue of this tile
-      mbar_wait(&bar_done[s], ph);
+    __syncwarp();
+  } else if (warp == 5) {
+    // =============================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      int it = 0, s = 0;
+      uint32_t ph = 0;
+      const uint32_t b_hi = smem_u32(bhi), b_lo = smem_u32(blo);
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int buf = ti & 1;
+        if (ti >= 2) mbar_wait(&bar_accfree[buf], (uint32_t)(((ti >> 1) - 1) & 1));
+        const uint32_t acc = tmem + buf * NPAD;
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(&bar_split[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_hi = smem_u32(raw + s * kChunkBytes);
+          const uint32_t a_lo = smem_u32(lob + (it % kNLo) * kChunkBytes);
+#pragma unroll
+          for (int g = 0; g < NKG; ++g) {
+            const uint32_t boff = (uint32_t)(c * NKG + g) * (NPAD / 8) * 256;
+            const uint64_t dah = make_smem_desc(a_hi + g * 1024, KC * 128, 512, kLayoutSw128Base32);
+            const uint64_t dal = make_smem_desc(a_lo + g * 1024, KC * 128, 512, kLayoutSw128Base32);
+            const uint64_t dbh = make_smem_desc(b_hi + boff, kPlainLbo, kPlainSbo, kLayoutNone);
+            const uint64_t dbl = make_smem_desc(b_lo + boff, kPlainLbo, kPlainSbo, kLayoutNone);
+            mma_tf32(acc, dal, dbh, kIdesc, !(c == 0 && g == 0));
+            mma_tf32(acc, dah, dbl, kIdesc, true);
+            mma_tf32(acc, dah, dbh, kIdesc, true);
+          }
+          mma_commit(&bar_done[s]);
+          if (c == nchunk - 1) mma_commit(&bar_accfull[buf]);
+          ++it;
+          if (++s == NST) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================================== workers: operand split + epilogue
+    // The epilogue of tile t runs AFTER the operands of tile t+1 have been split, so the tensor-core round trip of
+    // tile t (issue, execute, commit, wake-up: ~1.5 us) is hidden behind useful work instead of being waited for.
+    auto epilogue = [&](int ti) {
+      mbar_wait(&bar_accfull[ti & 1], (uint32_t)((ti >> 1) & 1));
       tc_fence_after_sync();
-      const long tile = blockIdx.x + ti * gridDim.x;
-      const int g = (int)(tile / p.tiles_per_slab);
-      const long m = (long)(tile - (long)g * p.tiles_per_slab) * 128 + warp * 32 + lane;
+      const uint32_t tile = blockIdx.x + (uint32_t)ti * gridDim.x;
+      const int g = tile / (uint32_t)p.tiles_per_slab;
+      const int m = (tile - (uint32_t)g * p.tiles_per_slab) * 128 + warp * 32 + lane;
       const bool in_range = m < p.mext;
       const bool live = m < p.valid_m;
       float* po = p.out + (long)g * p.gso + m;
+      const uint32_t acc = tmem + (ti & 1) * NPAD + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
       for (int n0 = 0; n0 < NPAD; n0 += 32) {
         if (n0 >= p.nout) break;
         float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, v);
+        tmem_ld32(acc + n0, v);
+        if (n0 + 32 >= p.nout || n0 + 32 >= NPAD) {  // last read of this buffer: hand it back to the MMA warp
+          tc_fence_before_sync();
+          mbar_arrive(&bar_accfree[ti & 1]);
+        }
         if (in_range) {
+          float* q = po + (long)n0 * p.ldo;
+          if (p.epi == 1) {
+            if (live) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            if (n < p.nout) {
-              float val = v[j] + sbias[n];
-              if (p.act == 1) val = selu_f(val);
-              float* q = po + (long)n * p.ldo;
-              if (p.epi == 1) {
-                if (live) *q += val;
-              } else {
-                *q = live ? val : 0.f;
+              for (int j0 = 0; j0 < 32; j0 += 8) {
+                float old[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (n0 + j0 + j < p.nout) old[j] = q[(long)(j0 + j) * p.ldo];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (n0 + j0 + j < p.nout) q[(long)(j0 + j) * p.ldo] = old[j] + v[j0 + j];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + j < p.nout) {
+                float val = v[j] + sbias[n0 + j];
+                if (p.act == 1) val = selu_f(val);
+                q[(long)j * p.ldo] = live ? val : 0.f;
               }
             }
           }
         }
       }
-      tc_fence_before_sync();  // ordered before the next tile's first MMA by the __syncthreads of the next item
+    };
+    int it = 0, s = 0;
+    uint32_t ph = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      for (int c = 0; c < nchunk; ++c) {
+        if (it >= kNLo) {  // the lo buffer is free once the MMAs of item it - kNLo have retired
+          const int j = it - kNLo;
+          mbar_wait(&bar_done[j % NST], (uint32_t)((j / NST) & 1));
+        }
+        mbar_wait(&bar_full[s], ph);
+        {
+          // hi operand = the fp32 word as it is (the tensor core ignores the 13 low mantissa bits);
+          // lo operand = the exact remainder x - trunc_tf32(x)
+          const float4* r4 = reinterpret_cast<const float4*>(raw + s * kChunkBytes);
+          float4* l4 = reinterpret_cast<float4*>(lob + (it % kNLo) * kChunkBytes);
+#pragma unroll
+          for (int i = 0; i < kChunkBytes / 16 / kTcWorkers; ++i) {
+            const int idx = tid + i * kTcWorkers;
+            const float4 x = r4[idx];
+            l4[idx] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bar_split[s]);
+        if (c == nchunk - 1 && ti > 0) epilogue(ti - 1);
+        ++it;
+        if (++s == NST) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
     }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -284,9 +374,9 @@ bool tc_stream_eligible(const TcStreamArgs& a) {
     if (reinterpret_cast<uintptr_t>(a.a[i]) % 16) return false;
     if (a.lda[i] % 4 || a.gsa[i] % 4) return false;
   }
-  if (a.mext < 1 || a.mext >= (1L << 31) || a.G < 1) return false;
+  if (a.mext < 1 || a.mext >= (1L << 30) || a.G < 1 || (a.mext + 127) / 128 * a.G >= (1L << 30)) return false;
   const int kc = a.kc;
-  if (kc != 24 && kc != 32 && kc != 8) return false;
+  if (kc != 24 && kc != 32 && kc != 16 && kc != 8) return false;
   if (a.nout > 256) return false;
   const int npad = a.nout <= 32 ? 32 : (a.nout <= 128 ? 128 : 256);
   const int nchunk = a.chunks_per_src * a.nsrc;
@@ -294,7 +384,7 @@ bool tc_stream_eligible(const TcStreamArgs& a) {
   return true;
 }
 
-template <int KC, int NPAD, int NST>
+template <int KC, int NPAD, int NST, int kNLo>
 static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   CUtensorMap tm[2];
   for (int i = 0; i < 2; ++i) {
@@ -316,20 +406,25 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   p.ldo = a.ldo;
   p.gso = a.gso;
   p.nout = a.nout;
-  p.mext = a.mext;
-  p.valid_m = a.valid_m;
+  p.mext = (int)a.mext;
+  p.valid_m = (int)(a.valid_m < a.mext ? a.valid_m : a.mext);
   p.chunks_per_src = a.chunks_per_src;
   p.nchunk = a.chunks_per_src * a.nsrc;
   p.tiles_per_slab = ceil_div(a.mext, 128);
-  p.total_tiles = (long)p.tiles_per_slab * a.G;
+  p.total_tiles = p.tiles_per_slab * a.G;
   p.act = a.act;
   p.epi = a.epi;
-  const size_t smem = TcSmem<KC, NPAD, NST>::bytes(p.nchunk);
-  auto kern = k_tc_stream<KC, NPAD, NST>;
+  const size_t smem = TcSmem<KC, NPAD, NST, kNLo>::bytes(p.nchunk);
+  auto kern = k_tc_stream<KC, NPAD, NST, kNLo>;
   HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // CTAs per SM: cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for every kernel that allocates TMEM
+  // (measured: also with 0 B of dynamic shared memory), while the hardware does co-schedule them; count resources here:
+  // 228 KB of shared memory per SM (1 KB reserved per CTA + 1 KB static), <= 112 registers x 192 threads, 512 TMEM columns.
+  int per_sm = (int)(233472 / (smem + 2 * 1024));
+  if (per_sm > 3) per_sm = 3;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 512 / (NPAD < 32 ? 32 : NPAD)) per_sm = 512 / (NPAD < 32 ? 32 : NPAD);
+  if (per_sm > 512 / (2 * NPAD)) per_sm = 512 / (2 * NPAD);
   if (per_sm > 4) per_sm = 4;
   long grid = (long)sm_count() * per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
@@ -341,17 +436,28 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
 int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st) {
   HNO_CHECK(tc_stream_eligible(a), "tc_stream: configuration is not eligible for the tensor-core path");
   const int npad = a.nout <= 32 ? 32 : (a.nout <= 128 ? 128 : 256);
-#define HNO_TC_CASE(KC_, NP_)                                     \
-  if (a.kc == KC_ && npad == NP_) return launch_t<KC_, NP_, 3>(a, st);
-  HNO_TC_CASE(24, 32)
-  HNO_TC_CASE(32, 32)
-  HNO_TC_CASE(8, 32)
-  HNO_TC_CASE(24, 128)
-  HNO_TC_CASE(32, 128)
-  HNO_TC_CASE(8, 128)
-  HNO_TC_CASE(24, 256)
-  HNO_TC_CASE(32, 256)
-  HNO_TC_CASE(8, 256)
+  static const int variant = getenv("HNO_TC_VARIANT") ? atoi(getenv("HNO_TC_VARIANT")) : 0;
+#define HNO_TC_CASE(KC_, NP_, NST_, NLO_, VAR_)                                  \
+  if (a.kc == KC_ && npad == NP_ && variant == VAR_) return launch_t<KC_, NP_, NST_, NLO_>(a, st);
+  HNO_TC_CASE(24, 32, 4, 3, 1)
+  HNO_TC_CASE(24, 32, 4, 4, 2)
+  HNO_TC_CASE(24, 32, 3, 3, 3)
+  HNO_TC_CASE(16, 32, 5, 4, 1)
+  HNO_TC_CASE(16, 32, 6, 4, 2)
+  HNO_TC_CASE(16, 32, 4, 3, 3)
+#undef HNO_TC_CASE
+#define HNO_TC_CASE(KC_, NP_, NST_, NLO_)                                  \
+  if (a.kc == KC_ && npad == NP_) return launch_t<KC_, NP_, NST_, NLO_>(a, st);
+  HNO_TC_CASE(24, 32, 3, 2)   // pointwise conv 24(+24) -> <= 32: 3 CTAs / SM
+  HNO_TC_CASE(32, 32, 3, 2)
+  HNO_TC_CASE(16, 32, 5, 2)   // D-axis analysis: 8 KB chunks
+  HNO_TC_CASE(8, 32, 4, 2)
+  HNO_TC_CASE(24, 128, 3, 2)  // D-axis synthesis
+  HNO_TC_CASE(32, 128, 3, 2)
+  HNO_TC_CASE(8, 128, 3, 2)
+  HNO_TC_CASE(24, 256, 3, 2)
+  HNO_TC_CASE(32, 256, 3, 2)
+  HNO_TC_CASE(8, 256, 3, 2)
 #undef HNO_TC_CASE
   set_error("tc_stream: no kernel instance for kc=%d npad=%d", a.kc, npad);
   return -1;
