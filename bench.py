@@ -50,7 +50,8 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []   # (arrival time, csv line)
+        self.windows = []  # [t0, t1] intervals (perf_counter) during which the GPU was under OUR load
 
     def start(self):
         try:
@@ -64,7 +65,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc is None:
@@ -76,7 +80,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        slack = 0.12  # nvidia-smi reports the state ~one sampling period late
+        for ts, ln in self.lines:
+            if self.windows and not any(a <= ts - slack <= b + slack for a, b in self.windows):
+                continue
             f = [t.strip() for t in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -244,7 +251,6 @@ def main():
     import torch
     import torch.distributed as dist
     from multimodal_3d_image_segmentation_b200 import _lib, nets, parallel
-    from oracle import hno_oracle as orc  # parameter initialiser only (random-init weights of the named config)
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (the hno_b200 path has no CPU fallback)')
@@ -260,9 +266,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    model = nets.HNOSegXS(**CFG, device=dev)
-    model.load_state_dict(orc.init_state_dict(CFG['in_channels'], CFG['out_channels'], CFG['filters'],
-                                              CFG['num_transform_blocks'], CFG['num_modes'], seed=0))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~1 s to come up: start early, keep only the samples taken under load
+    torch.manual_seed(0)
+    model = nets.HNOSegXS(**CFG, device=dev)  # random init = the reference's SNN initialiser (nets_utils.py:102-117)
     trainer = parallel.Trainer(model, args.loss, lr=5e-3)
     B = args.batch
     gx = torch.Generator().manual_seed(1234 + 2 * rank)
@@ -277,19 +285,17 @@ def main():
     for _ in range(args.warmup):
         loss = trainer.step(x_dev, l_dev)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     parallel.launches(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_load0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         loss = trainer.step(x_dev, l_dev)
     e1.record()
     barrier()
+    sampler.mark(t_load0, time.perf_counter())
     launches = parallel.launches()
-    clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -333,6 +339,15 @@ def main():
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
+    sampler.mark(t0, t0 + wall)
+    if rank == 0 and wall + (sampler.windows[0][1] - sampler.windows[0][0]) < 1.5:
+        # short runs: keep the same workload going until nvidia-smi (200 ms period) has seen it under load
+        t1 = time.perf_counter()
+        while time.perf_counter() - t1 < 1.5:
+            trainer.loss_and_grad(x_dev, l_dev)
+            torch.cuda.synchronize()
+        sampler.mark(t1, time.perf_counter())
+    clocks = sampler.stop() if rank == 0 else None
     ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)

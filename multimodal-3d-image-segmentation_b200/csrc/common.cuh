@@ -44,40 +44,67 @@ constexpr float kSeluAlpha = 1.6732632423543772848170429916717f;
 constexpr float kSeluScale = 1.0507009873554804934193349852946f;
 constexpr float kSeluNeg = kSeluAlpha * kSeluScale;
 
-// SELU with a purpose-built expm1 for the negative branch (16 instructions, one SFU op, instead of ~29 with
-// several SFU/conversion ops for libm's expm1f -- the activation epilogues were 44 % of the dynamic instructions
-// of the 48->24 channel mix):
-//   x in (-0.5, 0]: degree-8 Taylor polynomial of e^x - 1 (relative error < 2e-8, no cancellation)
+// Packed fp32 math (Blackwell FFMA2 / FMUL2, PTX fma.rn.f32x2): two independent operations per issue slot.  The
+// 3-operand scalar FFMA issues at half rate on sm_100 (register-file read ports), so every FMA-heavy loop uses it.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
+
+// SELU with a purpose-built expm1 for the negative branch (one SFU op and ~11 ALU ops instead of ~29 with several
+// SFU / conversion ops for libm's expm1f -- the activation epilogues were 44 % of the dynamic instructions of the
+// 48->24 channel mix):
+//   x in (-0.5, 0]: x * q(x), q = degree-5 minimax fit of (e^x - 1) / x on [-0.5, 0] (fit error 1e-9; evaluated in
+//                   fp32 Horner form the relative error is <= 1.04e-7, i.e. rounding limited, no cancellation)
 //   x <= -0.5     : ex2.approx(x * log2 e) - 1   (relative error of the result <= 1.6 * 2^-22)
 // A plain exp(x) - 1 is NOT acceptable: its cancellation near 0 (relative error ~6e-8/|x|) triples the gradient
 // error of the whole network.  Measured on the oracle (fp32, flat gradient rel-L2 vs the fp64 oracle, 120x112x77):
 // libm expm1 3.8e-4, this scheme 3.7e-4, exp(x) - 1 1.05e-3.
-__device__ __forceinline__ float selu_f(float x) {
-  constexpr float sa = kSeluNeg;
-  float p = sa / 40320.f;
-  p = fmaf(p, x, sa / 5040.f);
-  p = fmaf(p, x, sa / 720.f);
-  p = fmaf(p, x, sa / 120.f);
-  p = fmaf(p, x, sa / 24.f);
-  p = fmaf(p, x, sa / 6.f);
-  p = fmaf(p, x, sa / 2.f);
-  p = fmaf(p, x, sa);
-  p *= x;
+constexpr float kSeluQ0 = kSeluNeg * 0.9999999987618426f;
+constexpr float kSeluQ1 = kSeluNeg * 0.49999982068866156f;
+constexpr float kSeluQ2 = kSeluNeg * 0.1666624492152664f;
+constexpr float kSeluQ3 = kSeluNeg * 0.041630243386182875f;
+constexpr float kSeluQ4 = kSeluNeg * 0.008190002775750417f;
+constexpr float kSeluQ5 = kSeluNeg * 0.001123715104247875f;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-  e = fmaf(sa, e, -sa);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+__device__ __forceinline__ float selu_f(float x) {
+  float p = kSeluQ5;
+  p = fmaf(p, x, kSeluQ4);
+  p = fmaf(p, x, kSeluQ3);
+  p = fmaf(p, x, kSeluQ2);
+  p = fmaf(p, x, kSeluQ1);
+  p = fmaf(p, x, kSeluQ0);
+  p *= x;
+  const float e = fmaf(kSeluNeg, ex2_approx(x * kLog2e), -kSeluNeg);
   const float neg = x > -0.5f ? p : e;
   return x > 0.f ? kSeluScale * x : neg;
+}
+// two values at once on the packed pipe (same arithmetic, bit-identical to selu_f per element)
+__device__ __forceinline__ float2 selu2(float2 x) {
+  float2 p = dup2(kSeluQ5);
+  p = ffma2(p, x, dup2(kSeluQ4));
+  p = ffma2(p, x, dup2(kSeluQ3));
+  p = ffma2(p, x, dup2(kSeluQ2));
+  p = ffma2(p, x, dup2(kSeluQ1));
+  p = ffma2(p, x, dup2(kSeluQ0));
+  p = fmul2(p, x);
+  const float2 t = fmul2(x, dup2(kLog2e));
+  const float2 e = ffma2(dup2(kSeluNeg), make_float2(ex2_approx(t.x), ex2_approx(t.y)), dup2(-kSeluNeg));
+  const float2 pos = fmul2(x, dup2(kSeluScale));
+  float2 r;
+  r.x = x.x > 0.f ? pos.x : (x.x > -0.5f ? p.x : e.x);
+  r.y = x.y > 0.f ? pos.y : (x.y > -0.5f ? p.y : e.y);
+  return r;
 }
 // d selu / d x expressed from the OUTPUT y = selu(x): scale for y>0, y + scale*alpha otherwise.
 __device__ __forceinline__ float selu_grad_from_out(float y) {
   return y > 0.f ? kSeluScale : y + kSeluNeg;
 }
-
-// Packed fp32 FMA (Blackwell FFMA2, PTX fma.rn.f32x2): two independent FMAs per issue slot.  The 3-operand scalar
-// FFMA issues at half rate on sm_100 (register-file read ports), so every FMA-heavy inner loop uses this form.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
 
 template <int V>
 struct Vec;

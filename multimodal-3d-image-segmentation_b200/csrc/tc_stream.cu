@@ -50,6 +50,13 @@ struct TcDev {
   int tiles_per_slab;
   int total_tiles;
   int act, epi;
+  int prefetch_items;  // L2 prefetch distance of the producer, in chunks (0 = off)
+  long long* prof;     // debug (HNO_TC_PROF=1): per-CTA cycle counters [grid][8], else null
+  // streamed operand as raw pointers (LDGSTS loader); the TMA loader uses the tensor maps instead
+  const float* a[2];
+  long lda[2], gsa[2];
+  int rows[2];
+  int loader;          // 0 = cp.async (LDGSTS) warp, 1 = TMA (one thread)
 };
 
 template <int KC, int NPAD, int NST, int kNLo>
@@ -76,8 +83,14 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
                                                            const __grid_constant__ CUtensorMap tm1, const TcDev p) {
   constexpr int kChunkBytes = KC * 512;
   constexpr int NKG = KC / 8;
+  // kFuseN: A_hi * [B_hi | B_lo] as ONE MMA of N = 2 * NPAD (the two halves are added in the epilogue) plus A_lo * B_hi
+  // into the first half: the streamed operand is read from shared memory twice per k-step instead of three times
+  // (shared-memory bandwidth, not the tensor pipe, is what bounds this kernel once HBM is fed properly).
+  constexpr bool kFuseN = false;  // measured slower on B200 (pw48f 0.169 -> 0.200 ms): kept for reference
+  constexpr int NB = kFuseN ? 2 * NPAD : NPAD;  // rows of the resident B image / accumulator columns per buffer
   constexpr uint32_t kIdesc = make_idesc_tf32(128, NPAD, 1, 0);
-  constexpr uint32_t kTmemCols = 2 * NPAD < 32 ? 32 : 2 * NPAD;  // two accumulator buffers
+  constexpr uint32_t kIdesc2 = make_idesc_tf32(128, NB, 1, 0);
+  constexpr uint32_t kTmemCols = 2 * NB < 32 ? 32 : 2 * NB;  // two accumulator buffers
   static_assert(KC % 8 == 0 && NPAD % 16 == 0 && NPAD <= 256, "bad tile configuration");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align on the shared-window address so that the compiler keeps the shared address space (LDS / STS)
@@ -103,15 +116,20 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
     float v = 0.f;
     if (n < p.nvalid && k < p.kvalid) v = p.scale * __ldg(p.b + (long)n * p.ldbn + (long)k * p.ldbk);
     const float hi = rn_tf32_bits(v);
-    const int o = kmajor_plain_index<NPAD>(n, k);
-    bhi[o] = hi;
-    blo[o] = v - hi;
+    if (kFuseN) {  // one image: rows [0, NPAD) = hi, rows [NPAD, 2 NPAD) = lo
+      bhi[kmajor_plain_index<NB>(n, k)] = hi;
+      bhi[kmajor_plain_index<NB>(NPAD + n, k)] = v - hi;
+    } else {
+      const int o = kmajor_plain_index<NPAD>(n, k);
+      bhi[o] = hi;
+      blo[o] = v - hi;
+    }
   }
   for (int n = tid; n < NPAD; n += kTcThreads) sbias[n] = (p.bias != nullptr && n < p.nout) ? __ldg(p.bias + n) : 0.f;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NST; ++s) {
-      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_full[s], p.loader == 1 ? 1 : 32);
       mbar_init(&bar_split[s], kTcWorkers);
       mbar_init(&bar_done[s], 1);
     }
@@ -131,7 +149,45 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
   const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int nchunk = p.nchunk;
 
-  if (warp == 4) {
+  if (warp == 4 && p.loader == 0) {
+    // =============================================================== LDGSTS producer (one warp)
+    // TMA tile loads of 128-byte-wide boxes (the widest a swizzled MN-major tf32 operand allows) are limited by the TMA
+    // unit to one box row per ~8.6 cycles per SM = 4.2 TB/s chip-wide (tools/ubench_tma.cu, profiles/r1b_ubench_tma.log);
+    // 16-byte cp.async copies issued by one warp (512 contiguous bytes of one row per instruction) reach the HBM limit.
+    // The warp writes the 128B_BASE32B swizzle pattern itself: the 32-byte chunk c of row r lands at chunk c ^ (r & 3).
+    const int q = lane & 7, j = lane >> 3;  // 16-byte piece within a 128-byte row, 32-float column block
+    int it = 0, s = 0;
+    uint32_t ph = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const uint32_t tile = blockIdx.x + (uint32_t)ti * gridDim.x;
+      const int g = tile / (uint32_t)p.tiles_per_slab;
+      const int col = (tile - (uint32_t)g * p.tiles_per_slab) * 128 + j * 32 + q * 4;
+      const bool col_ok = col < p.mext;
+      for (int c = 0; c < nchunk; ++c) {
+        const int src = c / p.chunks_per_src;
+        const int row0 = (c - src * p.chunks_per_src) * KC;
+        if (it >= NST) mbar_wait(&bar_done[s], ph ^ 1);  // previous use of this stage fully consumed
+        const float* gp = p.a[src] + (long)g * p.gsa[src] + (long)row0 * p.lda[src] + (col_ok ? col : 0);
+        const long ld = p.lda[src];
+        const int nrow = p.rows[src] - row0;  // rows of this chunk that exist (the rest reads as zero)
+        const uint32_t dst0 = smem_u32(raw + s * kChunkBytes) + j * (KC * 128) + ((q & 1) << 4);
+#pragma unroll 8
+        for (int r = 0; r < KC; ++r) {
+          const uint32_t dst = dst0 + r * 128 + ((((q >> 1) ^ r) & 3) << 5);
+          const bool ok = col_ok && r < nrow;
+          const float* sp = ok ? gp + (long)r * ld : p.a[src];
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(sp), "r"(ok ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
+        ++it;
+        if (++s == NST) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == 4) {
     // =============================================================== TMA producer (one thread)
     if (lane == 0) {
       tma_prefetch_desc(&tm0);
@@ -161,8 +217,10 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
           if (k.ti < my_tiles) locate(k);
         }
       };
-      constexpr int kPrefetch = (96 * 1024) / kChunkBytes;
+      const int kPrefetch = p.prefetch_items;
       Cursor ld{0, 0, 0, 0, 0, 0, 0}, pf{0, 0, 0, 0, 0, 0, 0};
+      long long prof_acc[1] = {0};
+      const long long t_begin = p.prof ? clock64() : 0;
       if (my_tiles > 0) {
         locate(ld);
         locate(pf);
@@ -182,7 +240,11 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
           for (int j = 0; j < 4; ++j) tma_prefetch_l2_3d(tm, pf.m0 + 32 * j, pf.row0, pf.g);
           advance(pf);
         }
-        if (it >= NST) mbar_wait(&bar_done[s], ph ^ 1);  // previous use of this stage fully consumed
+        if (it >= NST) {  // previous use of this stage fully consumed
+          const long long t0 = p.prof ? clock64() : 0;
+          mbar_wait(&bar_done[s], ph ^ 1);
+          if (p.prof) prof_acc[0] += clock64() - t0;
+        }
         uint8_t* dst = raw + s * kChunkBytes;
         mbar_expect_tx(&bar_full[s], kChunkBytes);
         const CUtensorMap* tm = ld.src == 0 ? &tm0 : &tm1;
@@ -195,6 +257,10 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
           ph ^= 1;
         }
       }
+      if (p.prof) {
+        p.prof[blockIdx.x * 8 + 0] = prof_acc[0];
+        p.prof[blockIdx.x * 8 + 1] = clock64() - t_begin;
+      }
     }
     __syncwarp();
   } else if (warp == 5) {
@@ -203,25 +269,35 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
       int it = 0, s = 0;
       uint32_t ph = 0;
       const uint32_t b_hi = smem_u32(bhi), b_lo = smem_u32(blo);
+      long long w_free = 0, w_split = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
         const int buf = ti & 1;
+        long long t0 = p.prof ? clock64() : 0;
         if (ti >= 2) mbar_wait(&bar_accfree[buf], (uint32_t)(((ti >> 1) - 1) & 1));
-        const uint32_t acc = tmem + buf * NPAD;
+        if (p.prof) w_free += clock64() - t0;
+        const uint32_t acc = tmem + buf * NB;
         for (int c = 0; c < nchunk; ++c) {
+          t0 = p.prof ? clock64() : 0;
           mbar_wait(&bar_split[s], ph);
+          if (p.prof) w_split += clock64() - t0;
           tc_fence_after_sync();
           const uint32_t a_hi = smem_u32(raw + s * kChunkBytes);
           const uint32_t a_lo = smem_u32(lob + (it % kNLo) * kChunkBytes);
 #pragma unroll
           for (int g = 0; g < NKG; ++g) {
-            const uint32_t boff = (uint32_t)(c * NKG + g) * (NPAD / 8) * 256;
+            const uint32_t boff = (uint32_t)(c * NKG + g) * (NB / 8) * 256;
             const uint64_t dah = make_smem_desc(a_hi + g * 1024, KC * 128, 512, kLayoutSw128Base32);
             const uint64_t dal = make_smem_desc(a_lo + g * 1024, KC * 128, 512, kLayoutSw128Base32);
             const uint64_t dbh = make_smem_desc(b_hi + boff, kPlainLbo, kPlainSbo, kLayoutNone);
-            const uint64_t dbl = make_smem_desc(b_lo + boff, kPlainLbo, kPlainSbo, kLayoutNone);
-            mma_tf32(acc, dal, dbh, kIdesc, !(c == 0 && g == 0));
-            mma_tf32(acc, dah, dbl, kIdesc, true);
-            mma_tf32(acc, dah, dbh, kIdesc, true);
+            if (kFuseN) {
+              mma_tf32(acc, dah, dbh, kIdesc2, !(c == 0 && g == 0));  // [hi*hi | hi*lo]
+              mma_tf32(acc, dal, dbh, kIdesc, true);                   // lo*hi into the first half
+            } else {
+              const uint64_t dbl = make_smem_desc(b_lo + boff, kPlainLbo, kPlainSbo, kLayoutNone);
+              mma_tf32(acc, dal, dbh, kIdesc, !(c == 0 && g == 0));
+              mma_tf32(acc, dah, dbl, kIdesc, true);
+              mma_tf32(acc, dah, dbh, kIdesc, true);
+            }
           }
           mma_commit(&bar_done[s]);
           if (c == nchunk - 1) mma_commit(&bar_accfull[buf]);
@@ -232,14 +308,22 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
           }
         }
       }
+      if (p.prof) {
+        p.prof[blockIdx.x * 8 + 2] = w_free;
+        p.prof[blockIdx.x * 8 + 3] = w_split;
+      }
     }
     __syncwarp();
   } else {
     // =============================================================== workers: operand split + epilogue
     // The epilogue of tile t runs AFTER the operands of tile t+1 have been split, so the tensor-core round trip of
     // tile t (issue, execute, commit, wake-up: ~1.5 us) is hidden behind useful work instead of being waited for.
+    long long w_lo = 0, w_full = 0, w_acc = 0, t_epi = 0, t_split = 0;
+    const long long t_begin_w = p.prof ? clock64() : 0;
     auto epilogue = [&](int ti) {
+      const long long te0 = p.prof ? clock64() : 0;
       mbar_wait(&bar_accfull[ti & 1], (uint32_t)((ti >> 1) & 1));
+      if (p.prof) w_acc += clock64() - te0;
       tc_fence_after_sync();
       const uint32_t tile = blockIdx.x + (uint32_t)ti * gridDim.x;
       const int g = tile / (uint32_t)p.tiles_per_slab;
@@ -247,12 +331,18 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
       const bool in_range = m < p.mext;
       const bool live = m < p.valid_m;
       float* po = p.out + (long)g * p.gso + m;
-      const uint32_t acc = tmem + (ti & 1) * NPAD + ((uint32_t)(warp * 32) << 16);
+      const uint32_t acc = tmem + (ti & 1) * NB + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
       for (int n0 = 0; n0 < NPAD; n0 += 32) {
         if (n0 >= p.nout) break;
         float v[32];
         tmem_ld32(acc + n0, v);
+        if (kFuseN) {
+          float v2[32];
+          tmem_ld32(acc + NPAD + n0, v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
         if (n0 + 32 >= p.nout || n0 + 32 >= NPAD) {  // last read of this buffer: hand it back to the MMA warp
           tc_fence_before_sync();
           mbar_arrive(&bar_accfree[ti & 1]);
@@ -263,37 +353,69 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
             if (live) {
 #pragma unroll
               for (int j0 = 0; j0 < 32; j0 += 8) {
+                if (n0 + j0 >= p.nout) break;  // warp uniform
+                const bool full = n0 + j0 + 8 <= p.nout;
                 float old[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  if (n0 + j0 + j < p.nout) old[j] = q[(long)(j0 + j) * p.ldo];
+                  if (full || n0 + j0 + j < p.nout) old[j] = q[(long)(j0 + j) * p.ldo];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  if (n0 + j0 + j < p.nout) q[(long)(j0 + j) * p.ldo] = old[j] + v[j0 + j];
+                  if (full || n0 + j0 + j < p.nout) q[(long)(j0 + j) * p.ldo] = old[j] + v[j0 + j];
               }
             }
           } else {
+            // groups of 8 output rows: full groups run without per-row predicates (nout is 24 / 21 / 121 / 4 ...)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n0 + j < p.nout) {
-                float val = v[j] + sbias[n0 + j];
-                if (p.act == 1) val = selu_f(val);
-                q[(long)j * p.ldo] = live ? val : 0.f;
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+              if (n0 + j0 >= p.nout) break;  // warp uniform
+              float2 r[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 b2 = *reinterpret_cast<const float2*>(sbias + n0 + j0 + 2 * j);
+                r[j] = make_float2(v[j0 + 2 * j] + b2.x, v[j0 + 2 * j + 1] + b2.y);
+                if (p.act == 1) r[j] = selu2(r[j]);
+                if (!live) r[j] = make_float2(0.f, 0.f);
+              }
+              if (n0 + j0 + 8 <= p.nout) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  q[(long)(j0 + 2 * j) * p.ldo] = r[j].x;
+                  q[(long)(j0 + 2 * j + 1) * p.ldo] = r[j].y;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (n0 + j0 + 2 * j < p.nout) q[(long)(j0 + 2 * j) * p.ldo] = r[j].x;
+                  if (n0 + j0 + 2 * j + 1 < p.nout) q[(long)(j0 + 2 * j + 1) * p.ldo] = r[j].y;
+                }
               }
             }
           }
         }
       }
+      if (p.prof) t_epi += clock64() - te0;
     };
     int it = 0, s = 0;
     uint32_t ph = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
       for (int c = 0; c < nchunk; ++c) {
+        long long t0 = p.prof ? clock64() : 0;
         if (it >= kNLo) {  // the lo buffer is free once the MMAs of item it - kNLo have retired
           const int j = it - kNLo;
           mbar_wait(&bar_done[j % NST], (uint32_t)((j / NST) & 1));
         }
+        if (p.prof) {
+          const long long t1 = clock64();
+          w_lo += t1 - t0;
+          t0 = t1;
+        }
         mbar_wait(&bar_full[s], ph);
+        if (p.prof) {
+          const long long t1 = clock64();
+          w_full += t1 - t0;
+          t0 = t1;
+        }
         {
           // hi operand = the fp32 word as it is (the tensor core ignores the 13 low mantissa bits);
           // lo operand = the exact remainder x - trunc_tf32(x)
@@ -308,6 +430,7 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
         }
         fence_proxy_async_smem();
         mbar_arrive(&bar_split[s]);
+        if (p.prof) t_split += clock64() - t0;
         if (c == nchunk - 1 && ti > 0) epilogue(ti - 1);
         ++it;
         if (++s == NST) {
@@ -317,6 +440,16 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
       }
     }
     if (my_tiles > 0) epilogue(my_tiles - 1);
+    if (p.prof && tid == 0) {
+      p.prof[blockIdx.x * 8 + 4] = w_lo;
+      p.prof[blockIdx.x * 8 + 5] = w_full;
+      p.prof[blockIdx.x * 8 + 6] = w_acc;
+      p.prof[blockIdx.x * 8 + 7] = t_epi;
+      if (p.loader == 0) {
+        p.prof[blockIdx.x * 8 + 0] = t_split;
+        p.prof[blockIdx.x * 8 + 1] = clock64() - t_begin_w;
+      }
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -356,9 +489,13 @@ int encode_tensor_map(CUtensorMap* out, const float* base, int rank, const uint6
   const CUtensorMapSwizzle sw = swizzle == 2   ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                                 : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  static const int promo_env = getenv("HNO_TC_L2PROMO") ? atoi(getenv("HNO_TC_L2PROMO")) : 3;
+  const CUtensorMapL2promotion promo = promo_env == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                        : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   const CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, b, e,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HNO_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)rc);
   return 0;
 }
@@ -374,6 +511,7 @@ bool tc_stream_eligible(const TcStreamArgs& a) {
     if (reinterpret_cast<uintptr_t>(a.a[i]) % 16) return false;
     if (a.lda[i] % 4 || a.gsa[i] % 4) return false;
   }
+  if (a.mext % 4) return false;
   if (a.mext < 1 || a.mext >= (1L << 30) || a.G < 1 || (a.mext + 127) / 128 * a.G >= (1L << 30)) return false;
   const int kc = a.kc;
   if (kc != 24 && kc != 32 && kc != 16 && kc != 8) return false;
@@ -414,6 +552,21 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   p.total_tiles = p.tiles_per_slab * a.G;
   p.act = a.act;
   p.epi = a.epi;
+  for (int i = 0; i < 2; ++i) {
+    const int j = i < a.nsrc ? i : 0;
+    p.a[i] = a.a[j];
+    p.lda[i] = a.lda[j];
+    p.gsa[i] = a.gsa[j];
+    p.rows[i] = a.rows[j];
+  }
+  {
+    static const int loader = getenv("HNO_TC_LOADER") ? atoi(getenv("HNO_TC_LOADER")) : 0;
+    p.loader = loader;
+  }
+  {
+    static const int pf_kb = getenv("HNO_TC_PREFETCH_KB") ? atoi(getenv("HNO_TC_PREFETCH_KB")) : 96;
+    p.prefetch_items = pf_kb * 1024 / (KC * 512);
+  }
   const size_t smem = TcSmem<KC, NPAD, NST, kNLo>::bytes(p.nchunk);
   auto kern = k_tc_stream<KC, NPAD, NST, kNLo>;
   HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -428,8 +581,31 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   if (per_sm > 4) per_sm = 4;
   long grid = (long)sm_count() * per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
+  static const bool prof_on = getenv("HNO_TC_PROF") != nullptr;
+  static long long* prof_buf = nullptr;
+  p.prof = nullptr;
+  if (prof_on) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 4096 * 8 * sizeof(long long));
+    cudaMemsetAsync(prof_buf, 0, 4096 * 8 * sizeof(long long), st);
+    p.prof = prof_buf;
+  }
   kern<<<(int)grid, kTcThreads, smem, st>>>(tm[0], tm[1], p);
   HNO_LAUNCH_CHECK();
+  if (prof_on) {  // debug only: synchronous read-back of the per-CTA wait-cycle counters
+    static long long host[4096 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, prof_buf, grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s[8] = {0};
+    for (long i = 0; i < grid; ++i)
+      for (int j = 0; j < 8; ++j) s[j] += (double)host[i * 8 + j];
+    const double tiles = (double)p.total_tiles / grid;
+    fprintf(stderr,
+            "[tc_prof KC=%d NPAD=%d NST=%d grid=%ld tiles/cta=%.1f nchunk=%d] cycles per tile per CTA: total %.0f | producer wait "
+            "done (loader 0: worker split) %.0f | mma wait accfree %.0f, wait split %.0f | worker wait lo %.0f, wait full %.0f, wait acc %.0f, epilogue "
+            "%.0f\n",
+            KC, NPAD, NST, grid, tiles, p.nchunk, s[1] / grid / tiles, s[0] / grid / tiles, s[2] / grid / tiles,
+            s[3] / grid / tiles, s[4] / grid / tiles, s[5] / grid / tiles, s[6] / grid / tiles, s[7] / grid / tiles);
+  }
   return 0;
 }
 
