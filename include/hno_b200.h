@@ -100,6 +100,23 @@ int hno_hartley_conv_backward(const float* dout, const float* y, const float* x,
                               void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The n_XS shared-weight mixes of one HNO-XS block as one launch
+ *   replaces nets/hnosegxs.py:261-262 (loop over NeuralOperatorBlock.forward :307-329) with
+ *            nets/hartley_operator.py:287-292 (weights_type 'shared'):  z_l = selu(W_l z_{l-1} + z_{l-1}), l = 1..L
+ * z0 [B][C][M]; weights: HOST array of L device pointers to [C][C] matrices; zs [L][B][C][M] receives z_1..z_L
+ * (all of them are needed by the backward).  C in {8, 24}, L <= 8.
+ * backward: dzL = gradient of z_L; writes dz0 [B][C][M] and dweights[l] [C][C] (HOST array of L device pointers;
+ * accumulate != 0 adds to them).
+ * ------------------------------------------------------------------------------------------ */
+int hno_modechain_supported(int C);
+int hno_modechain_forward(const float* z0, const float* const* weights, float* zs, int B, int C, long M, int L,
+                          void* stream);
+size_t hno_modechain_backward_workspace_bytes(int B, int C, long M, int L);
+int hno_modechain_backward(const float* dzL, const float* z0, const float* zs, const float* const* weights, float* dz0,
+                           float* const* dweights, void* workspace, int B, int C, long M, int L, int accumulate,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stem: Conv3d(k=2, s=2, p=1) + bias + SELU      replaces nets/hnosegxs.py:102-105,150-151
  *   x [B][CIN][Dx][Hx][Wx] dense  ->  out [B][F][D][P],  D = Dx/2+1, H = Hx/2+1, W = Wx/2+1
  *   weight [F][CIN][2][2][2], bias [F].  Padding columns of out are written as 0.

@@ -37,6 +37,10 @@ SIGNATURES = {
     'hno_pwconv_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _I, _I, _P]),
     'hno_pwconv_backward_workspace_bytes': (_Z, [_I, _I, _I]),
     'hno_pwconv_backward': (_I, [_P] * 10 + [_I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _P]),
+    'hno_modechain_supported': (_I, [_I]),
+    'hno_modechain_forward': (_I, [_P, _P, _P, _I, _I, _L, _I, _P]),
+    'hno_modechain_backward_workspace_bytes': (_Z, [_I, _I, _L, _I]),
+    'hno_modechain_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _I, _P]),
     'hno_hartley_conv_forward': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'hno_hartley_conv_backward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'hno_stem_supported': (_I, [_I, _I]),

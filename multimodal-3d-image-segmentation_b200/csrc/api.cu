@@ -45,6 +45,13 @@ int pwconv_forward(const float*, const float*, const float*, const float*, float
 size_t pwconv_backward_workspace_bytes(int, int, int);
 int pwconv_backward(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
                     float*, void*, int, int, int, int, long, long, long, int, int, int, cudaStream_t);
+int modechain_supported(int C);
+int modechain_forward(const float* z0, const float* const* weights, float* zs, int B, int C, long M, int L,
+                      cudaStream_t st);
+size_t modechain_backward_workspace_bytes(int B, int C, long M, int L);
+int modechain_backward(const float* dzL, const float* z0, const float* zs, const float* const* weights, float* dz0,
+                       float* const* dweights, void* workspace, int B, int C, long M, int L, int accumulate,
+                       cudaStream_t st);
 int hartley_conv_forward(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int hartley_conv_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int,
                           int, int, int, cudaStream_t);
@@ -139,6 +146,23 @@ int hno_pwconv_backward(const float* dy, const float* y, const float* in1, const
                         int ci2, int co, long S, long P, long HW, int act, int residual, int flags, void* stream) {
   return pwconv_backward(dy, y, in1, in2, weight, din1, din2, dweight, dbias, workspace, B, ci1, ci2, co, S, P, HW,
                          act, residual, flags, ST(stream));
+}
+
+int hno_modechain_supported(int C) { return modechain_supported(C); }
+
+int hno_modechain_forward(const float* z0, const float* const* weights, float* zs, int B, int C, long M, int L,
+                          void* stream) {
+  return modechain_forward(z0, weights, zs, B, C, M, L, ST(stream));
+}
+
+size_t hno_modechain_backward_workspace_bytes(int B, int C, long M, int L) {
+  return modechain_backward_workspace_bytes(B, C, M, L);
+}
+
+int hno_modechain_backward(const float* dzL, const float* z0, const float* zs, const float* const* weights, float* dz0,
+                           float* const* dweights, void* workspace, int B, int C, long M, int L, int accumulate,
+                           void* stream) {
+  return modechain_backward(dzL, z0, zs, weights, dz0, dweights, workspace, B, C, M, L, accumulate, ST(stream));
 }
 
 int hno_hartley_conv_forward(const float* x, const float* w, float* out, int B, int ci, int co, int n0, int n1, int n2,

@@ -18,7 +18,20 @@
 #include "hno_b200.h"
 #include "tc_stream.h"
 
+#include <stdlib.h>
+
 namespace hno {
+
+// fused middle stages (dht_mid.cu)
+bool dht_mid_eligible(const void* plan_host, long P, int nslab);
+int dht_mid_forward(const void* plan_host, const void* plan_dev, const float* G1, long P, float* z, int nslab,
+                    float scale, cudaStream_t st);
+int dht_mid_adjoint(const void* plan_host, const void* plan_dev, const float* z, float* G1, long P, int nslab,
+                    float scale, cudaStream_t st);
+static bool mid_enabled() {
+  static const bool on = !(getenv("HNO_DHT_MID") && atoi(getenv("HNO_DHT_MID")) == 0);
+  return on;
+}
 
 // ----------------------------------------------------------------------------------------------
 // analysis along a strided axis:  out[b][j][c] = sum_i f_j(i) * in[b][i][c]
@@ -556,6 +569,7 @@ static bool tc_outer(const OuterArgs& a, bool synthesis, TcStreamArgs* t) {
     r.valid_m = a.ncols;
     r.act = 0;
     r.epi = 0;
+    r.loader = 1;
   } else {
     r.rows[0] = a.J;
     r.kc = a.J <= 8 ? 8 : (a.J <= 24 ? 24 : 32);
@@ -567,6 +581,7 @@ static bool tc_outer(const OuterArgs& a, bool synthesis, TcStreamArgs* t) {
     r.valid_m = a.valid_cols;
     r.act = a.epi == 2 ? 1 : 0;
     r.epi = a.epi == 1 ? 1 : 0;
+    r.loader = 0;
   }
   if (a.nbatch >= (1L << 31) || a.ncols < 1024 || a.out_rs % 4 || a.out_bs % 4 ||
       reinterpret_cast<uintptr_t>(a.out) % 16 || !tc_stream_eligible(r))
@@ -660,6 +675,8 @@ int dht3_forward(const void* plan_host, const void* plan_dev, const float* x, lo
     a.tc_ok = true;
     if (int rc = launch_analysis(a, st)) return rc;
   }
+  if (mid_enabled() && dht_mid_eligible(plan_host, plane_pitch, nslab))  // stages 2, 3 and the recombination, fused
+    return dht_mid_forward(plan_host, plan_dev, G1, plane_pitch, z, nslab, scale, st);
   {  // stage 2: H
     const DhtAxis& ax = h->ax[1];
     OuterArgs a{G1, G2, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
@@ -699,14 +716,17 @@ int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, fl
   float* G1 = reinterpret_cast<float*>(ws);
   float* G2 = G1 + nslab * g.g1;
   float* T = G2 + nslab * g.g2;
-  {
+  const bool fused_mid = mid_enabled() && dht_mid_eligible(plan_host, plane_pitch, nslab);
+  if (fused_mid) {
+    if (int rc = dht_mid_adjoint(plan_host, plan_dev, z, G1, plane_pitch, nslab, scale, st)) return rc;
+  } else {
     const long total = (long)nslab * g.tt;
     k_combine_t<<<ceil_div(total, 256), 256, 0, st>>>(z, T, pi + h->ax[0].off_jdesc, pi + h->ax[1].off_jdesc,
                                                        pi + h->ax[2].off_jdesc, g.Ld, g.Lh, g.Lw, g.Jd, g.Jh, g.Jw,
                                                        total, scale);
     HNO_LAUNCH_CHECK();
   }
-  {  // W
+  if (!fused_mid) {  // W
     const DhtAxis& ax = h->ax[2];
     const long R = (long)nslab * g.Jd * g.Jh;
     const size_t smem = inner_smem(ax.n, ax.J, false);
@@ -716,7 +736,7 @@ int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, fl
     k_synthesis_inner<<<ceil_div(R, kInnerRows), 256, smem, st>>>(T, G2, pf + ax.off_full, ax.n, ax.J, R, g.Jw, g.W);
     HNO_LAUNCH_CHECK();
   }
-  {  // H
+  if (!fused_mid) {  // H
     const DhtAxis& ax = h->ax[1];
     OuterArgs a{G2, G1, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
                 ax.J, g.W, (long)nslab * g.Jd, g.W, (long)g.Jh * g.W, g.W, plane_pitch, g.W, 1.f, 0};

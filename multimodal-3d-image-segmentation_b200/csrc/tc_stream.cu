@@ -27,6 +27,7 @@
 #include <atomic>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 
 namespace hno {
@@ -560,8 +561,8 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
     p.rows[i] = a.rows[j];
   }
   {
-    static const int loader = getenv("HNO_TC_LOADER") ? atoi(getenv("HNO_TC_LOADER")) : 0;
-    p.loader = loader;
+    static const int loader = getenv("HNO_TC_LOADER") ? atoi(getenv("HNO_TC_LOADER")) : -1;
+    p.loader = loader >= 0 ? loader : a.loader;
   }
   {
     static const int pf_kb = getenv("HNO_TC_PREFETCH_KB") ? atoi(getenv("HNO_TC_PREFETCH_KB")) : 96;
@@ -611,6 +612,11 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
 
 int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st) {
   HNO_CHECK(tc_stream_eligible(a), "tc_stream: configuration is not eligible for the tensor-core path");
+  {  // HNO_TC_KERNEL=regs selects the experimental ring -> registers -> tensor-memory data path (tc_regs.cu); measured
+     // on B200 it ties with the shared-memory-operand ring below (pw48f 0.171-0.182 ms vs 0.169 ms), see DESIGN.md
+    static const bool regs = getenv("HNO_TC_KERNEL") && !strcmp(getenv("HNO_TC_KERNEL"), "regs");
+    if (regs && tc_regs_eligible(a)) return tc_regs_launch(a, st);
+  }
   const int npad = a.nout <= 32 ? 32 : (a.nout <= 128 ? 128 : 256);
   static const int variant = getenv("HNO_TC_VARIANT") ? atoi(getenv("HNO_TC_VARIANT")) : 0;
 #define HNO_TC_CASE(KC_, NP_, NST_, NLO_, VAR_)                                  \

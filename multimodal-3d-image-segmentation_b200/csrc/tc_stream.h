@@ -29,10 +29,15 @@ struct TcStreamArgs {
   long valid_m;
   int act;             // 0 none, 1 SELU
   int epi;             // 0 store, 1 accumulate
+  int loader;          // producer of the shared-memory ring: 0 = cp.async warp (fastest for 24/48-row operands),
+                       // 1 = TMA (fastest for the 121-row D-axis analysis); HNO_TC_LOADER overrides
 };
 
 bool tc_stream_eligible(const TcStreamArgs& a);
 int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st);
+// register-fed variant (tc_regs.cu): A operand loaded global -> registers -> tensor memory; the default
+bool tc_regs_eligible(const TcStreamArgs& a);
+int tc_regs_launch(const TcStreamArgs& a, cudaStream_t st);
 // Global switch (tests / A-B measurements): returns the previous value.
 int tc_set_enabled(int on);
 bool tc_enabled();

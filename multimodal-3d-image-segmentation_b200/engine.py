@@ -84,11 +84,18 @@ class XSEngine:
             else:
                 xin = cur
             zs = [ops.dht3_forward(xin, plan, inv_n)]
-            for blk in layer.conv_blocks:
-                if shared:
-                    zs.append(ops.pwconv_forward(zs[-1], None, blk.op.weight, None, 1, True))
-                else:
-                    zs.append(ops.hartley_conv_forward(zs[-1], blk.op.weight, True))
+            rec.chain = None
+            nmix = len(layer.conv_blocks)
+            if shared and nmix and ops.modechain_supported(zs[0].shape[1], nmix):
+                # all n_XS mixes of the block in one launch (reference nets/hnosegxs.py:261-262)
+                rec.chain = ops.modechain_forward(zs[0], [blk.op.weight for blk in layer.conv_blocks])
+                zs += [rec.chain[j] for j in range(nmix)]
+            else:
+                for blk in layer.conv_blocks:
+                    if shared:
+                        zs.append(ops.pwconv_forward(zs[-1], None, blk.op.weight, None, 1, True))
+                    else:
+                        zs.append(ops.hartley_conv_forward(zs[-1], blk.op.weight, True))
             u = ops.dht3_adjoint(zs[-1], plan, 1.0, epilogue=2, pitch=pitch)  # selu(PadInverse(z))
             if layer.conv_concat is not None:
                 y = ops.pwconv_forward(u, xin, _w2(layer.conv_concat.op), layer.conv_concat.op.bias, 1, False)
@@ -166,16 +173,22 @@ class XSEngine:
                     dxin = dcur.clone()
             dz = ops.dht3_forward(dt, plan, 1.0)
             g_mix = []
-            for j in reversed(range(len(layer.conv_blocks))):
-                w = layer.conv_blocks[j].op.weight
-                dw_, _ = out_w(w)
-                if shared:
-                    dz, _, gw, _ = ops.pwconv_backward(dz, rec.zs[j + 1], rec.zs[j], None, w, 1, True, has_bias=False,
-                                                       dweight=dw_)
-                else:
-                    dz, gw = ops.hartley_conv_backward(dz, rec.zs[j + 1], rec.zs[j], w, dw=dw_)
-                g_mix.append(gw)
-            g_mix.reverse()
+            if rec.chain is not None:
+                ws = [blk.op.weight for blk in layer.conv_blocks]
+                dws = [out_w(w)[0] for w in ws] if dst is not None else None
+                dz, g_mix = ops.modechain_backward(dz, rec.zs[0], rec.chain, ws, dweights=dws)
+                g_mix = list(g_mix)
+            else:
+                for j in reversed(range(len(layer.conv_blocks))):
+                    w = layer.conv_blocks[j].op.weight
+                    dw_, _ = out_w(w)
+                    if shared:
+                        dz, _, gw, _ = ops.pwconv_backward(dz, rec.zs[j + 1], rec.zs[j], None, w, 1, True,
+                                                           has_bias=False, dweight=dw_)
+                    else:
+                        dz, gw = ops.hartley_conv_backward(dz, rec.zs[j + 1], rec.zs[j], w, dw=dw_)
+                    g_mix.append(gw)
+                g_mix.reverse()
             ops.dht3_adjoint(dz, plan, inv_n, epilogue=1, out=dxin)  # dxin += (1/N) C^T dz
             if has_map:
                 prev, enc = rec.map_in

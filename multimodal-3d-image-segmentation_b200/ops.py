@@ -174,6 +174,60 @@ class PointwiseConv(torch.autograd.Function):
         return din1, din2, dw.reshape(wshape), db, None, None
 
 
+# ------------------------------------------------------------------------------------------ shared-weight mode chain
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def modechain_forward(z0, weights):
+    """z_l = selu(W_l z_{l-1} + z_{l-1}) for every layer in ONE launch.  Returns a (L, B, C, ...) tensor of z_1..z_L."""
+    _require_cuda(z0, 'z0')
+    z0 = z0.contiguous()
+    ws = [w.contiguous() for w in weights]
+    B, C = z0.shape[:2]
+    M = _flat_s(z0)
+    zs = torch.empty((len(ws),) + tuple(z0.shape), dtype=torch.float32, device=z0.device)
+    call('hno_modechain_forward', ptr(z0), _ptr_array(ws), ptr(zs), B, C, M, len(ws), stream_ptr())
+    return zs
+
+
+def modechain_backward(dzL, z0, zs, weights, dweights=None, accumulate=False):
+    """Returns (dz0, [dW_1..dW_L]); `dweights`: optional destination tensors (views of a flat gradient buffer)."""
+    ws = [w.contiguous() for w in weights]
+    L = len(ws)
+    B, C = z0.shape[:2]
+    M = _flat_s(z0)
+    if dweights is None:
+        dweights = [torch.empty_like(w) for w in ws]
+    dz0 = torch.empty_like(z0)
+    wsp = workspace(_lib.load().hno_modechain_backward_workspace_bytes(B, C, M, L), z0.device, 'mc')
+    call('hno_modechain_backward', ptr(dzL.contiguous()), ptr(z0), ptr(zs), _ptr_array(ws), ptr(dz0),
+         _ptr_array(dweights), ptr(wsp), B, C, M, L, int(bool(accumulate)), stream_ptr())
+    return dz0, dweights
+
+
+class ModeChain(torch.autograd.Function):
+    """The n_XS shared-weight NeuralOperatorBlocks of one HNO-XS block (reference nets/hnosegxs.py:261-262)."""
+
+    @staticmethod
+    def forward(ctx, z0, *weights):
+        z0 = z0.contiguous()
+        zs = modechain_forward(z0, weights)
+        ctx.save_for_backward(z0, zs, *weights)
+        return zs[-1]
+
+    @staticmethod
+    def backward(ctx, dz):
+        z0, zs, *weights = ctx.saved_tensors
+        dz0, dws = modechain_backward(dz, z0, zs, weights)
+        return (dz0,) + tuple(dws)
+
+
+def modechain_supported(C, L):
+    return bool(_lib.load().hno_modechain_supported(int(C))) and 1 <= L <= 8
+
+
 # ------------------------------------------------------------------------------------------ individual-weight mixing
 class HartleyConv(torch.autograd.Function):
     """out(k) = 1/2 [W(k)(X(k)+X(~k)) + W(~k)(X(k)-X(~k))]  (reference nets/hartley_operator.py:293-317)."""

@@ -305,3 +305,29 @@ def test_adamax(cuda):
         _lib.call('hno_adamax_step', pc.data_ptr(), grad.to(cuda).data_ptr(), m.data_ptr(), u.data_ptr(), 1000, 5e-3,
                   0.9, 0.999, 1e-8, 0.0, step, 1.0, torch.cuda.current_stream().cuda_stream)
     assert maxrel(pc, pr) < 1e-6
+
+
+@pytest.mark.parametrize('C,L,M,B', [(24, 3, 20 * 28 * 28, 2), (24, 1, 777, 1), (8, 4, 1000, 3)])
+def test_modechain_matches_layerwise(cuda, C, L, M, B):
+    """The fused n_XS-mix kernel against the oracle's per-layer selu(W z + z) chain and its autograd (fp64)."""
+    import torch
+    from multimodal_3d_image_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    z0 = torch.randn(B, C, M, generator=g)
+    ws = [torch.randn(C, C, generator=g) / C ** 0.5 for _ in range(L)]
+    dz = torch.randn(B, C, M, generator=g)
+    zr = z0.double().requires_grad_(True)
+    wr = [w.double().requires_grad_(True) for w in ws]
+    cur = zr
+    outs = []
+    for w in wr:
+        cur = torch.nn.functional.selu(torch.einsum('oi,bim->bom', w, cur) + cur)
+        outs.append(cur)
+    grads = torch.autograd.grad(cur, [zr] + wr, dz.double())
+    zs = ops.modechain_forward(z0.to(cuda), [w.to(cuda) for w in ws])
+    for l in range(L):
+        assert torch.allclose(zs[l].cpu().double(), outs[l].detach(), rtol=2e-5, atol=2e-5)
+    dz0, dws = ops.modechain_backward(dz.to(cuda), z0.to(cuda), zs, [w.to(cuda) for w in ws])
+    assert ((dz0.cpu().double() - grads[0]).norm() / grads[0].norm()).item() < 1e-5
+    for l in range(L):
+        assert ((dws[l].cpu().double() - grads[1 + l]).norm() / grads[1 + l].norm()).item() < 1e-5
