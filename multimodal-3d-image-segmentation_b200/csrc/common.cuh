@@ -49,6 +49,25 @@ constexpr float kSeluNeg = kSeluAlpha * kSeluScale;
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
+// The same on operands that LIVE as 64-bit registers: values built lane by lane (x in one statement, y in another) are
+// kept in unrelated scalar registers by the compiler, which then re-packs them with two MOVs in front of EVERY packed
+// FMA (measured: 2 of 3 instructions of the input-gradient loops).  A b64 register is an aligned pair by construction.
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pack2(float lo, float hi) {
+  pk2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(pk2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ pk2 ffma2p(pk2 a, pk2 b, pk2 c) {
+  pk2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 
 // SELU with a purpose-built expm1 for the negative branch (one SFU op and ~11 ALU ops instead of ~29 with several
 // SFU / conversion ops for libm's expm1f -- the activation epilogues were 44 % of the dynamic instructions of the

@@ -230,30 +230,31 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_bwd(
     stage_input<CI1, VV, TVS>(sx, in1 + (long)b * CI1 * S + s0, S, lv, valid);
 
     // ---- phase A1: d(pre-activation), staged to shared memory; kept in registers as output-channel pairs
-    float2 dp2[COp / 2][VV];
+    pk2 dp2[COp / 2][VV];  // output-channel pairs (2q, 2q+1), packed (see pack2 in common.cuh)
 #pragma unroll
-    for (int o = 0; o < COp; ++o) {
-      float d[VV];
-      if (o < CO && valid) {
-        Vec<VV> g = Vec<VV>::ld(dy + ((long)b * CO + o) * S + s0);
-        Vec<VV> yy;
-        if (ACT != 0) yy = Vec<VV>::ld(y + ((long)b * CO + o) * S + s0);
+    for (int op = 0; op < COp / 2; ++op) {
+      float d[2][VV];
 #pragma unroll
-        for (int v = 0; v < VV; ++v)
-          d[v] = live[v] ? g.v[v] * (ACT != 0 ? act_grad_from_out<ACT>(yy.v[v]) : 1.f) : 0.f;
-      } else {
+      for (int h = 0; h < 2; ++h) {
+        const int o = 2 * op + h;
+        if (o < CO && valid) {
+          Vec<VV> g = Vec<VV>::ld(dy + ((long)b * CO + o) * S + s0);
+          Vec<VV> yy;
+          if (ACT != 0) yy = Vec<VV>::ld(y + ((long)b * CO + o) * S + s0);
 #pragma unroll
-        for (int v = 0; v < VV; ++v) d[v] = 0.f;
+          for (int v = 0; v < VV; ++v)
+            d[h][v] = live[v] ? g.v[v] * (ACT != 0 ? act_grad_from_out<ACT>(yy.v[v]) : 1.f) : 0.f;
+        } else {
+#pragma unroll
+          for (int v = 0; v < VV; ++v) d[h][v] = 0.f;
+        }
+        if (o < CO) {
+#pragma unroll
+          for (int v = 0; v < VV; ++v) sdp[o * TVS + lv + v] = d[h][v];
+        }
       }
 #pragma unroll
-      for (int v = 0; v < VV; ++v) {
-        if (o & 1) dp2[o / 2][v].y = d[v];
-        else dp2[o / 2][v].x = d[v];
-      }
-      if (o < CO) {
-#pragma unroll
-        for (int v = 0; v < VV; ++v) sdp[o * TVS + lv + v] = d[v];
-      }
+      for (int v = 0; v < VV; ++v) dp2[op][v] = pack2(d[0][v], d[1][v]);
     }
     cp_async_wait_all();
     // ---- input gradient of input 1 (own columns of sx / sdp only: no barrier needed yet)
@@ -261,22 +262,25 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_bwd(
       float* dst = din1 + (long)b * CI1 * S + s0;
 #pragma unroll 4
       for (int i = 0; i < CI1; ++i) {
-        float2 a2[VV];
+        pk2 a2[VV];
 #pragma unroll
-        for (int v = 0; v < VV; ++v) a2[v] = make_float2(RES ? sdp[i * TVS + lv + v] : 0.f, 0.f);
-        const float4* w4 = reinterpret_cast<const float4*>(wt + i * COp);
+        for (int v = 0; v < VV; ++v) a2[v] = pack2(RES ? sdp[i * TVS + lv + v] : 0.f, 0.f);
+        const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wt + i * COp);
 #pragma unroll
         for (int q = 0; q < COp / 4; ++q) {
-          const float4 w = w4[q];
+          const ulonglong2 w = w4[q];
 #pragma unroll
           for (int v = 0; v < VV; ++v) {
-            a2[v] = ffma2(make_float2(w.x, w.y), dp2[2 * q + 0][v], a2[v]);
-            a2[v] = ffma2(make_float2(w.z, w.w), dp2[2 * q + 1][v], a2[v]);
+            a2[v] = ffma2p(w.x, dp2[2 * q + 0][v], a2[v]);
+            a2[v] = ffma2p(w.y, dp2[2 * q + 1][v], a2[v]);
           }
         }
         Vec<VV> r;
 #pragma unroll
-        for (int v = 0; v < VV; ++v) r.v[v] = a2[v].x + a2[v].y;
+        for (int v = 0; v < VV; ++v) {
+          const float2 t = unpack2(a2[v]);
+          r.v[v] = t.x + t.y;
+        }
         if (flags & 4) {
 #pragma unroll
           for (int v = 0; v < VV; ++v) r.v[v] *= selu_grad_from_out(sx[i * TVS + lv + v]);
@@ -298,22 +302,25 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_bwd(
         float* dst = din2 + (long)b * CI2 * S + s0;
 #pragma unroll 4
         for (int i = 0; i < CI2; ++i) {
-          float2 a2[VV];
+          pk2 a2[VV];
 #pragma unroll
-          for (int v = 0; v < VV; ++v) a2[v] = make_float2(0.f, 0.f);
-          const float4* w4 = reinterpret_cast<const float4*>(wt + (CI1 + i) * COp);
+          for (int v = 0; v < VV; ++v) a2[v] = 0ull;
+          const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wt + (CI1 + i) * COp);
 #pragma unroll
           for (int q = 0; q < COp / 4; ++q) {
-            const float4 w = w4[q];
+            const ulonglong2 w = w4[q];
 #pragma unroll
             for (int v = 0; v < VV; ++v) {
-              a2[v] = ffma2(make_float2(w.x, w.y), dp2[2 * q + 0][v], a2[v]);
-              a2[v] = ffma2(make_float2(w.z, w.w), dp2[2 * q + 1][v], a2[v]);
+              a2[v] = ffma2p(w.x, dp2[2 * q + 0][v], a2[v]);
+              a2[v] = ffma2p(w.y, dp2[2 * q + 1][v], a2[v]);
             }
           }
           Vec<VV> r;
 #pragma unroll
-          for (int v = 0; v < VV; ++v) r.v[v] = a2[v].x + a2[v].y;
+          for (int v = 0; v < VV; ++v) {
+            const float2 t = unpack2(a2[v]);
+            r.v[v] = t.x + t.y;
+          }
           if (flags & 2) {
             Vec<VV> old = Vec<VV>::ld(dst + (long)i * S);
 #pragma unroll

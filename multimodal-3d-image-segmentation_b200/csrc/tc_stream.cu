@@ -34,8 +34,17 @@ namespace hno {
 
 using namespace tc;
 
-constexpr int kTcWorkers = 128;            // 4 worker warps: operand split + epilogue (one TMEM lane each)
-constexpr int kTcThreads = kTcWorkers + 64;  // + warp 4: TMA producer, warp 5: MMA issuer
+// Worker warps (operand split + epilogue): 4 for narrow outputs; 8 for NPAD >= 128, where the epilogue (up to 121 rows
+// of SELU + stores per voxel) is the critical path: warps w and w + 4 share a TMEM lane quarter and take alternating
+// 32-column blocks of the accumulator.  Two more warps follow: producer (cp.async or TMA) and MMA issuer.
+template <int NPAD>
+struct TcShape {
+  // measured on B200: 8 warps do not speed up the store/SELU epilogue (instruction bound, dhts 0.138 ms either way) and
+  // cost the accumulate epilogue its second prefetch block (dhta 0.196 -> 0.292 ms), so every shape runs with 4
+  static constexpr int kWorkerWarps = 4;
+  static constexpr int kWorkers = 32 * kWorkerWarps;
+  static constexpr int kThreads = kWorkers + 64;
+};
 
 struct TcDev {
   const float* b;
@@ -80,10 +89,13 @@ __device__ __forceinline__ float rn_tf32_bits(float x) {
 }
 
 template <int KC, int NPAD, int NST, int kNLo>
-__global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2 : 1))) k_tc_stream(const __grid_constant__ CUtensorMap tm0,
+__global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2 : 1))) k_tc_stream(const __grid_constant__ CUtensorMap tm0,
                                                            const __grid_constant__ CUtensorMap tm1, const TcDev p) {
   constexpr int kChunkBytes = KC * 512;
   constexpr int NKG = KC / 8;
+  constexpr int kTcWorkers = TcShape<NPAD>::kWorkers, kTcThreads = TcShape<NPAD>::kThreads;
+  constexpr int kWW = TcShape<NPAD>::kWorkerWarps;  // producer = warp kWW, MMA issuer = warp kWW + 1
+  constexpr int kHalves = kWW / 4;                   // worker warps per TMEM lane quarter
   // kFuseN: A_hi * [B_hi | B_lo] as ONE MMA of N = 2 * NPAD (the two halves are added in the epilogue) plus A_lo * B_hi
   // into the first half: the streamed operand is read from shared memory twice per k-step instead of three times
   // (shared-memory bandwidth, not the tensor pipe, is what bounds this kernel once HBM is fed properly).
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
     mbar_init(&bar_accfull[1], 1);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_slot, kTmemCols);
+  if (warp == kWW) tmem_alloc(&tmem_slot, kTmemCols);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
   const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int nchunk = p.nchunk;
 
-  if (warp == 4 && p.loader == 0) {
+  if (warp == kWW && p.loader == 0) {
     // =============================================================== LDGSTS producer (one warp)
     // TMA tile loads of 128-byte-wide boxes (the widest a swizzled MN-major tf32 operand allows) are limited by the TMA
     // unit to one box row per ~8.6 cycles per SM = 4.2 TB/s chip-wide (tools/ubench_tma.cu, profiles/r1b_ubench_tma.log);
@@ -188,7 +200,7 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp == 4) {
+  } else if (warp == kWW) {
     // =============================================================== TMA producer (one thread)
     if (lane == 0) {
       tma_prefetch_desc(&tm0);
@@ -264,7 +276,7 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == kWW + 1) {
     // =============================================================== MMA issuer (one thread)
     if (lane == 0) {
       int it = 0, s = 0;
@@ -323,18 +335,67 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
     const long long t_begin_w = p.prof ? clock64() : 0;
     auto epilogue = [&](int ti) {
       const long long te0 = p.prof ? clock64() : 0;
-      mbar_wait(&bar_accfull[ti & 1], (uint32_t)((ti >> 1) & 1));
-      if (p.prof) w_acc += clock64() - te0;
-      tc_fence_after_sync();
       const uint32_t tile = blockIdx.x + (uint32_t)ti * gridDim.x;
       const int g = tile / (uint32_t)p.tiles_per_slab;
-      const int m = (tile - (uint32_t)g * p.tiles_per_slab) * 128 + warp * 32 + lane;
+      const int quarter = warp & 3, half = warp >> 2;  // TMEM lane quarter / which 32-column blocks this warp takes
+      const int m = (tile - (uint32_t)g * p.tiles_per_slab) * 128 + quarter * 32 + lane;
       const bool in_range = m < p.mext;
       const bool live = m < p.valid_m;
       float* po = p.out + (long)g * p.gso + m;
-      const uint32_t acc = tmem + (ti & 1) * NB + ((uint32_t)(warp * 32) << 16);
+      const uint32_t acc = tmem + (ti & 1) * NB + ((uint32_t)(quarter * 32) << 16);
+      if (p.epi == 1) {
+        // accumulate: out += acc.  The old values of a 32-row block are requested BEFORE the accumulator is waited for
+        // and one block ahead of the stores (64 loads in flight per thread instead of 8: the epilogue was a chain of
+        // exposed HBM round trips, 185 us against 77 us for the store-only form)
+        float old[kHalves == 1 ? 2 : 1][32];
+        auto fetch = [&](int n0, float (&o)[32]) {
+          if (live && n0 < p.nout) {
+            const float* q = po + (long)n0 * p.ldo;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.nout) o[j] = __ldcs(q + (long)j * p.ldo);
+          }
+        };
+        constexpr int kDepth = kHalves == 1 ? 2 : 1;  // 8 worker warps: registers allow one block in flight per warp
+        fetch(32 * half, old[0]);
+        mbar_wait(&bar_accfull[ti & 1], (uint32_t)((ti >> 1) & 1));
+        if (p.prof) w_acc += clock64() - te0;
+        tc_fence_after_sync();
+        bool released = false;
+#pragma unroll
+        for (int b = 0; b < NPAD / 32 / kHalves; ++b) {
+          const int n0 = 32 * (b * kHalves + half);
+          if (n0 < p.nout) {
+            if (kDepth == 2 && b + 1 < NPAD / 32 / kHalves) fetch(n0 + 32 * kHalves, old[(b + 1) % kDepth]);
+            float v[32];
+            tmem_ld32(acc + n0, v);
+            if (n0 + 32 * kHalves >= p.nout || b + 1 == NPAD / 32 / kHalves) {  // this warp's last read of the buffer
+              tc_fence_before_sync();
+              mbar_arrive(&bar_accfree[ti & 1]);
+              released = true;
+            }
+            if (live) {
+              float* q = po + (long)n0 * p.ldo;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.nout) __stcs(q + (long)j * p.ldo, old[b % kDepth][j] + v[j]);
+            }
+            if (kDepth == 1 && b + 1 < NPAD / 32 / kHalves) fetch(n0 + 32 * kHalves, old[0]);
+          }
+        }
+        if (!released) {  // this warp owns no block below nout
+          tc_fence_before_sync();
+          mbar_arrive(&bar_accfree[ti & 1]);
+        }
+        if (p.prof) t_epi += clock64() - te0;
+        return;
+      }
+      mbar_wait(&bar_accfull[ti & 1], (uint32_t)((ti >> 1) & 1));
+      if (p.prof) w_acc += clock64() - te0;
+      tc_fence_after_sync();
+      bool released = false;
 #pragma unroll 1
-      for (int n0 = 0; n0 < NPAD; n0 += 32) {
+      for (int n0 = 32 * half; n0 < NPAD; n0 += 32 * kHalves) {
         if (n0 >= p.nout) break;
         float v[32];
         tmem_ld32(acc + n0, v);
@@ -344,9 +405,10 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += v2[j];
         }
-        if (n0 + 32 >= p.nout || n0 + 32 >= NPAD) {  // last read of this buffer: hand it back to the MMA warp
+        if (n0 + 32 * kHalves >= p.nout || n0 + 32 * kHalves >= NPAD) {  // this warp's last read of the buffer
           tc_fence_before_sync();
           mbar_arrive(&bar_accfree[ti & 1]);
+          released = true;
         }
         if (in_range) {
           float* q = po + (long)n0 * p.ldo;
@@ -394,6 +456,10 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
             }
           }
         }
+      }
+      if (!released) {  // this warp owns no 32-column block below nout
+        tc_fence_before_sync();
+        mbar_arrive(&bar_accfree[ti & 1]);
       }
       if (p.prof) t_epi += clock64() - te0;
     };
@@ -454,7 +520,7 @@ __global__ void __launch_bounds__(kTcThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kWW) tmem_dealloc(tmem, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -590,7 +656,7 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
     cudaMemsetAsync(prof_buf, 0, 4096 * 8 * sizeof(long long), st);
     p.prof = prof_buf;
   }
-  kern<<<(int)grid, kTcThreads, smem, st>>>(tm[0], tm[1], p);
+  kern<<<(int)grid, TcShape<NPAD>::kThreads, smem, st>>>(tm[0], tm[1], p);
   HNO_LAUNCH_CHECK();
   if (prof_on) {  // debug only: synchronous read-back of the per-CTA wait-cycle counters
     static long long host[4096 * 8];

@@ -33,6 +33,7 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ sdp, const 
   static_assert(TVG % 4 == 0, "tile share must be a multiple of 4 voxels");
   if (ot * T::TO >= CO) return;
   const int v0 = g * TVG;
+  const bool do_bias = with_bias && it == 0;
 #pragma unroll 2
   for (int v = v0; v < v0 + TVG; v += 4) {
     float4 d[T::TO], x[T::TI];
@@ -50,7 +51,7 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ sdp, const 
         a = ffma2(make_float2(d[q].z, d[q].w), make_float2(x[r].z, x[r].w), a);
         accW[q][r] = a;
       }
-    if (with_bias && it == 0) {
+    if (do_bias) {
 #pragma unroll
       for (int q = 0; q < T::TO; ++q) accB[q] += (d[q].x + d[q].y) + (d[q].z + d[q].w);
     }
