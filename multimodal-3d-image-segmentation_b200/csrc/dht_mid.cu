@@ -42,7 +42,7 @@ static MidSmem mid_smem_fwd(const MidGeom& g) {
   int cur = g.H * g.Wp;               // plane rows padded to Wp
   s.fh = cur; cur += (g.nhh + 1) * (g.JChp + g.JShp);  // folded cos table [i][JChp], then folded sin table [i][JShp]
   s.fw = cur; cur += g.W * g.Jwp;     // [w][Jwp]
-  s.t2 = cur; cur += r4(g.Jh * g.W);  // [jh][W]
+  s.t2 = cur; cur += g.Wp * (g.JChp + g.JShp);  // transposed: [w][JChp + JShp]
   s.T = cur; cur += r4(2 * g.Jh * g.Jw);
   s.total = cur;
   return s;
@@ -68,7 +68,7 @@ __device__ __forceinline__ int find_sin_row(const int* jdesc, int Jd, int JCd, i
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(kMidThreads, 2) k_dht_mid_fwd(const float* __restrict__ G1, float* __restrict__ Z,
+__global__ void __launch_bounds__(kMidThreads, 3) k_dht_mid_fwd(const float* __restrict__ G1, float* __restrict__ Z,
                                                                const float* __restrict__ pf,
                                                                const int* __restrict__ pi, const MidGeom g,
                                                                const MidSmem sm, float scale) {
@@ -91,10 +91,8 @@ __global__ void __launch_bounds__(kMidThreads, 2) k_dht_mid_fwd(const float* __r
   float* fsn = fh + (g.nhh + 1) * g.JChp;
   for (int idx = tid; idx < (g.nhh + 1) * g.JChp; idx += kMidThreads) fcs[idx] = __ldg(pf + g.off_fcos_h + idx);
   for (int idx = tid; idx < (g.nhh + 1) * g.JShp; idx += kMidThreads) fsn[idx] = __ldg(pf + g.off_fsin_h + idx);
-  for (int idx = tid; idx < g.W * g.Jwp; idx += kMidThreads) {
-    const int w = idx / g.Jwp, j = idx - w * g.Jwp;
-    fw[idx] = j < g.Jw ? __ldg(pf + g.off_full_w + (long)j * g.W + w) : 0.f;
-  }
+  for (int j = tid >> 5; j < g.Jwp; j += kMidThreads / 32)  // fw[w][j] <- full[j][w]: a warp per table row
+    for (int w = tid & 31; w < g.W; w += 32) fw[w * g.Jwp + j] = j < g.Jw ? __ldg(pf + g.off_full_w + j * g.W + w) : 0.f;
 
   for (int pass = 0; pass < 2; ++pass) {
     const int row = pass == 0 ? jc : js;
@@ -103,25 +101,25 @@ __global__ void __launch_bounds__(kMidThreads, 2) k_dht_mid_fwd(const float* __r
     __syncthreads();  // previous pass is done with `plane` and `t2`
     {
       const float* src = G1 + (slab * g.Jd + row) * g.P;
-      if ((g.W & 1) == 0) {  // 8-byte pieces: rows of W floats -> rows of Wp floats
+      const int wrp = tid >> 5, ln = tid & 31;
+      if ((g.W & 1) == 0) {  // 8-byte pieces: rows of W floats -> rows of Wp floats (a warp per row, no divisions)
         const int hw2 = g.W >> 1;
-        const int n2 = g.H * hw2;
-        for (int i = tid; i < n2; i += kMidThreads) {
-          const int h = i / hw2, c = i - h * hw2;
-          const unsigned dst = (unsigned)__cvta_generic_to_shared(plane + h * g.Wp + 2 * c);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + h * g.W + 2 * c) : "memory");
+        for (int h = wrp; h < g.H; h += kMidThreads / 32) {
+          const float* sr = src + h * g.W;
+          const unsigned dr = (unsigned)__cvta_generic_to_shared(plane + h * g.Wp);
+          for (int c = ln; c < hw2; c += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dr + 8 * c), "l"(sr + 2 * c) : "memory");
         }
       } else {
-        for (int i = tid; i < HW; i += kMidThreads) {
-          const int h = i / g.W, c = i - h * g.W;
-          const unsigned dst = (unsigned)__cvta_generic_to_shared(plane + h * g.Wp + c);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src + i) : "memory");
+        for (int h = wrp; h < g.H; h += kMidThreads / 32) {
+          const float* sr = src + h * g.W;
+          const unsigned dr = (unsigned)__cvta_generic_to_shared(plane + h * g.Wp);
+          for (int c = ln; c < g.W; c += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dr + 4 * c), "l"(sr + c) : "memory");
         }
       }
-      for (int i = tid; i < g.H * (g.Wp - g.W); i += kMidThreads) {  // zero the row padding (read by the 4-wide tiles)
-        const int h = i / (g.Wp - g.W), c = i - h * (g.Wp - g.W);
-        plane[h * g.Wp + g.W + c] = 0.f;
-      }
+      if (g.Wp != g.W && ln < g.Wp - g.W)  // zero the row padding (read by the 4-wide tiles)
+        for (int h = wrp; h < g.H; h += kMidThreads / 32) plane[h * g.Wp + g.W + ln] = 0.f;
       cp_async_wait_all();
     }
     __syncthreads();
@@ -133,7 +131,8 @@ __global__ void __launch_bounds__(kMidThreads, 2) k_dht_mid_fwd(const float* __r
       const int ntile = (gc + gs) * wq;
       const int n = g.H, npair = (n - 1) >> 1;
       for (int tile = tid; tile < ntile; tile += kMidThreads) {
-        const int jg = tile / wq, wg = tile - jg * wq;
+        // row groups run fastest: the eight threads of a store phase then write 128 contiguous bytes of one t2 column
+        const int wg = tile / (gc + gs), jg = tile - wg * (gc + gs);
         const bool is_sin = jg >= gc;
         const int jq = is_sin ? jg - gc : jg;
         const int pitch = is_sin ? g.JShp : g.JChp;
@@ -166,44 +165,60 @@ __global__ void __launch_bounds__(kMidThreads, 2) k_dht_mid_fwd(const float* __r
         if (!is_sin && (n & 1) == 0 && n > 1)  // Nyquist sample pairs with itself, its sine vanishes
           step(*reinterpret_cast<const float4*>(pp + (n >> 1) * g.Wp),
                *reinterpret_cast<const float4*>(tab + (n >> 1) * pitch));
-        const int j0 = (is_sin ? g.JCh : 0) + 4 * jq;
-        const int jend = is_sin ? g.JCh + g.JSh : g.JCh;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (j0 + r < jend) {
-            float* o = t2 + (j0 + r) * g.W + 4 * wg;
-            const float v[4] = {acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y};
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (4 * wg + c < g.W) o[c] = v[c];
-          }
-        }
+        // t2 is kept transposed, [w][JT] with the cos rows at [0, JChp) and the sin rows at [JChp, JChp + JShp):
+        // one STS.128 per column here, one LDS.128 per (w, 4 rows) in the W analysis
+        const int JT = g.JChp + g.JShp;
+        float* o = t2 + (4 * wg) * JT + (is_sin ? g.JChp : 0) + 4 * jq;
+        if (4 * wg + 0 < g.W) *reinterpret_cast<float4*>(o) = make_float4(acc[0][0].x, acc[1][0].x, acc[2][0].x, acc[3][0].x);
+        if (4 * wg + 1 < g.W) *reinterpret_cast<float4*>(o + JT) = make_float4(acc[0][0].y, acc[1][0].y, acc[2][0].y, acc[3][0].y);
+        if (4 * wg + 2 < g.W) *reinterpret_cast<float4*>(o + 2 * JT) = make_float4(acc[0][1].x, acc[1][1].x, acc[2][1].x, acc[3][1].x);
+        if (4 * wg + 3 < g.W) *reinterpret_cast<float4*>(o + 3 * JT) = make_float4(acc[0][1].y, acc[1][1].y, acc[2][1].y, acc[3][1].y);
       }
     }
     __syncthreads();
-    // ---- W analysis: T[jh][jw] = sum_w t2[jh][w] fw[jw][w]; tile = 1 row jh x 4 columns jw
+    // ---- W analysis: T[jh][jw] = sum_w t2[w][jh] fw[w][jw]; tile = 4 rows jh x 4 columns jw (2 LDS.128 + 8 FFMA2 a step)
     {
-      const int q = g.Jwp >> 2;
-      const int ntile = g.Jh * q;
+      const int JT = g.JChp + g.JShp;
+      const int gh = JT >> 2, gw = g.Jwp >> 2;
+      const int ntile = gh * gw;
       for (int tile = tid; tile < ntile; tile += kMidThreads) {
-        const int jh = tile / q, jg = tile - jh * q;
-        const float* tp = t2 + jh * g.W;
-        const float4* f4 = reinterpret_cast<const float4*>(fw + 4 * jg);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+        const int hq = tile / gw, wq4 = tile - hq * gw;
+        const float* tp = t2 + 4 * hq;
+        const float* fp = fw + 4 * wq4;
+        float2 acc[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+#pragma unroll 2
         for (int w = 0; w < g.W; ++w) {
-          const float x = tp[w];
-          const float4 f = f4[w * q];
-          acc.x = fmaf(f.x, x, acc.x);
-          acc.y = fmaf(f.y, x, acc.y);
-          acc.z = fmaf(f.z, x, acc.z);
-          acc.w = fmaf(f.w, x, acc.w);
+          const float4 x = *reinterpret_cast<const float4*>(tp + w * JT);     // 4 rows jh
+          const float4 f = *reinterpret_cast<const float4*>(fp + w * g.Jwp);  // 4 columns jw
+          const float2 f01 = make_float2(f.x, f.y), f23 = make_float2(f.z, f.w);
+          acc[0][0] = ffma2(dup2(x.x), f01, acc[0][0]);
+          acc[0][1] = ffma2(dup2(x.x), f23, acc[0][1]);
+          acc[1][0] = ffma2(dup2(x.y), f01, acc[1][0]);
+          acc[1][1] = ffma2(dup2(x.y), f23, acc[1][1]);
+          acc[2][0] = ffma2(dup2(x.z), f01, acc[2][0]);
+          acc[2][1] = ffma2(dup2(x.z), f23, acc[2][1]);
+          acc[3][0] = ffma2(dup2(x.w), f01, acc[3][0]);
+          acc[3][1] = ffma2(dup2(x.w), f23, acc[3][1]);
         }
-        const int j0 = 4 * jg;
-        if (j0 + 0 < g.Jw) Tp[jh * g.Jw + j0 + 0] = acc.x;
-        if (j0 + 1 < g.Jw) Tp[jh * g.Jw + j0 + 1] = acc.y;
-        if (j0 + 2 < g.Jw) Tp[jh * g.Jw + j0 + 2] = acc.z;
-        if (j0 + 3 < g.Jw) Tp[jh * g.Jw + j0 + 3] = acc.w;
+        // rows of the padded numbering -> rows of T (cos rows [0, JCh), sin rows [JCh, Jh))
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int jp = 4 * hq + r;
+          int jh = -1;
+          if (jp < g.JChp) {
+            if (jp < g.JCh) jh = jp;
+          } else if (jp - g.JChp < g.JSh) {
+            jh = g.JCh + jp - g.JChp;
+          }
+          if (jh >= 0) {
+            const float v[4] = {acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (4 * wq4 + c < g.Jw) Tp[jh * g.Jw + 4 * wq4 + c] = v[c];
+          }
+        }
       }
     }
   }
@@ -420,7 +435,7 @@ static MidGeom make_geom(const DhtPlanHeader* h, long P) {
   return g;
 }
 
-constexpr size_t kMidSmemLimit = 110 * 1024;  // two CTAs per SM
+constexpr size_t kMidSmemLimit = 110 * 1024;  // at least two CTAs per SM
 
 bool dht_mid_eligible(const void* plan_host, long P, int nslab) {
   const auto* h = reinterpret_cast<const DhtPlanHeader*>(plan_host);
