@@ -1,0 +1,398 @@
+// Backward of the 24(+24) -> 24 pointwise (1x1x1) convolution + SELU, pipelined (sm_100a).
+//
+// Replaces the autograd of nets/nets_utils.py:120-174 (ConvNormAct k=1, SELU) for the concat / mapping convolutions of
+// nets/hnosegxs.py:254-255, 273-275 -- the kernel with the largest share of an HNOSeg-XS training step.
+//   d(pre)[o]  = dy[o] * selu'(y[o])
+//   din[i]     = sum_o W[o][i] d(pre)[o]        (x selu'(in1[i]) for the first input when it is itself a SELU output)
+//   dW[o][i]  += sum_voxels d(pre)[o] in[i],   db[o] += sum_voxels d(pre)[o]
+// The phase-by-phase FFMA kernel (pwconv_kernels.cu) was latency bound at 2.1 TB/s: five CTA-wide barriers per tile and
+// no overlap of its loads with its math (ncu: FMA pipe 37 %, DRAM 26 %).  Here
+//   * a loader warp streams dy, y, in1, in2 of a 128-voxel tile as four 24-row stages of a deep cp.async ring
+//     (completion on mbarriers, rows padded to 132 floats so that the weight-gradient reads are conflict free);
+//   * every worker thread owns one voxel (= one TMEM lane): it forms d(pre) in registers, writes the two TF32 terms to
+//     tensor memory and the fp32 value to a shared tile;
+//   * the input gradient runs on the tensor cores: A = d(pre) from TMEM (M = 128 voxels, K = 24), B = [W^T_hi | W^T_lo]
+//     resident in shared memory, 3xTF32 as two instructions per k-step (tc_regs.cu explains the fusion);
+//   * while those MMAs execute, the workers accumulate the weight gradient with packed FFMA2 out of shared memory
+//     (exact fp32 products, fp32 partial sums per CTA, fp64 final reduction: k_reduce_partials);
+//   * the epilogue reads the accumulator (one lane per voxel), applies selu'(in1) / the += of U-Net skips and writes
+//     coalesced 128-byte rows.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_stream.h"
+#include "wgrad.cuh"
+
+#include <stdlib.h>
+
+namespace hno {
+
+using namespace tc;
+
+constexpr int kBtC = 24;                      // channels per source / output channels
+constexpr int kBtWorkers = 128;
+constexpr int kBtThreads = kBtWorkers + 64;   // + warp 4: MMA issuer, warp 5: loader
+constexpr int kBtPitch = 132;                 // floats per ring / tile row (128 voxels + 4: bank spread for the LDS.128 reads)
+constexpr int kBtStageFloats = kBtC * kBtPitch;
+constexpr int kBtMaxStages = 8;
+
+struct BtDev {
+  const float* dy;
+  const float* y;
+  const float* in1;
+  const float* in2;
+  const float* w;      // [24][CI]
+  float* din1;
+  float* din2;
+  float* partials;     // [grid][24 * CI + 24]
+  long S, P, HW;
+  int tiles_per_sample, total_tiles;
+  int flags;
+  int nst;
+};
+
+__device__ __forceinline__ void bt_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bt_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void bt_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void bt_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void bt_mma(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void bt_worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// CI2 = 0: single input (24 -> 24);  CI2 = 24: virtual concat of two inputs (48 -> 24)
+template <int CI2>
+__global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) {
+  constexpr int C = kBtC;
+  constexpr int CI = C + CI2;
+  constexpr int NP = CI == 48 ? 48 : 32;       // MMA N of one half (multiple of 16)
+  constexpr int NB = 2 * NP;                    // rows of the fused B image [hi | lo]
+  constexpr int NSRC = CI2 > 0 ? 4 : 3;         // ring stages per tile: dy, y, in1 (, in2)
+  constexpr uint32_t kIdesc1 = make_idesc_tf32(128, NB, 0, 0);
+  constexpr uint32_t kIdesc2 = make_idesc_tf32(128, NP, 0, 0);
+  constexpr uint32_t kACol = 0, kDCol = 2 * C;  // TMEM: A = d(pre) hi [0,24) lo [24,48); accumulator [48, 48 + NB)
+  constexpr uint32_t kTmemCols = 256;
+  constexpr int PSTRIDE = C * CI + C;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int NST = p.nst;
+  float* ring = reinterpret_cast<float*>(smem);            // [NST][24][132]
+  float* sdp = ring + NST * kBtStageFloats;                 // [24][132]   d(pre) of the current tile
+  float* bimg = sdp + kBtStageFloats;                       // [NB rows][24 k] K-major core-matrix image of W^T (hi | lo)
+  float* scratch = bimg + NB * C;                           // end-of-kernel reduction of the weight-gradient tiles
+  __shared__ __align__(8) uint64_t bar_full[kBtMaxStages];  // stage landed              (32 cp.async arrivals)
+  __shared__ __align__(8) uint64_t bar_empty[kBtMaxStages]; // stage no longer needed    (128 arrivals)
+  __shared__ __align__(8) uint64_t bar_ready;               // d(pre) is in tensor memory (128 arrivals)
+  __shared__ __align__(8) uint64_t bar_accfull;             // the MMAs of the tile have retired (tcgen05.commit)
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- resident operand: B[n][k] = W[k][n] (n = input channel, k = output channel), hi rows then lo rows
+  for (int idx = tid; idx < NP * C; idx += kBtThreads) {
+    const int n = idx / C, k = idx - n * C;
+    const float v = n < CI ? __ldg(p.w + k * CI + n) : 0.f;
+    const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    bimg[kmajor_plain_index<NB>(n, k)] = hi;
+    bimg[kmajor_plain_index<NB>(NP + n, k)] = v - hi;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kBtMaxStages; ++s) {
+      mbar_init(&bar_full[s], 32);
+      mbar_init(&bar_empty[s], kBtWorkers);
+    }
+    mbar_init(&bar_ready, kBtWorkers);
+    mbar_init(&bar_accfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(&tmem_slot, kTmemCols);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 4) {
+    // =============================================================== MMA issuer (one thread): input gradient
+    if (lane == 0) {
+      const uint32_t b0 = smem_u32(bimg);
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        mbar_wait(&bar_ready, (uint32_t)(ti & 1));
+        tc_fence_after_sync();
+#pragma unroll
+        for (int g = 0; g < C / 8; ++g) {
+          const uint64_t db = make_smem_desc(b0 + g * (NB / 8) * 256, kPlainLbo, kPlainSbo, kLayoutNone);
+          bt_mma(tmem + kDCol, tmem + kACol + 8 * g, db, kIdesc1, g != 0);       // [hi*hi | hi*lo]
+          bt_mma(tmem + kDCol, tmem + kACol + C + 8 * g, db, kIdesc2, true);      // lo*hi into the first half
+        }
+        mma_commit(&bar_accfull);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // =============================================================== loader (one warp): 512-byte rows -> padded stages
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const long tile = blockIdx.x + (long)ti * gridDim.x;
+      const int b = (int)(tile / p.tiles_per_sample);
+      const long s0 = (tile - (long)b * p.tiles_per_sample) * 128 + lane * 4;
+      const bool ok = s0 < p.S;  // S % 4 == 0: a 16-byte piece is entirely inside or outside
+#pragma unroll 1
+      for (int q = 0; q < NSRC; ++q) {
+        const float* base = q == 0 ? p.dy : (q == 1 ? p.y : (q == 2 ? p.in1 : p.in2));
+        const float* gp = base + (long)b * C * p.S + (ok ? s0 : 0);
+        if (it >= NST) mbar_wait(&bar_empty[s], ph ^ 1);
+        const uint32_t dst0 = smem_u32(ring + s * kBtStageFloats) + lane * 16;
+#pragma unroll 8
+        for (int r = 0; r < C; ++r)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + r * (kBtPitch * 4)),
+                       "l"(gp + (long)r * p.S), "r"(ok ? 16 : 0)
+                       : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
+        ++it;
+        if (++s == NST) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    // =============================================================== workers
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // weight-gradient ownership (wgrad.cuh tiling for 128 threads): 2 voxel groups x 64 threads, 3 x 3 outputs each
+    const int wg = tid >> 6, wl = tid & 63;
+    const int ot = wl >> 3, it8 = wl & 7;
+    float2 accW[2][3][3];
+    float accB[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) accW[h][q][r] = make_float2(0.f, 0.f);
+
+    auto wgrad = [&](const float* sx, float2 (&acc)[3][3], bool with_bias) {
+      const float* dp0 = sdp + (ot * 3) * kBtPitch + wg * 64;
+      const float* x0 = sx + (it8 * 3) * kBtPitch + wg * 64;
+#pragma unroll 2
+      for (int v = 0; v < 64; v += 4) {
+        float4 d[3], x[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) d[q] = *reinterpret_cast<const float4*>(dp0 + q * kBtPitch + v);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) x[r] = *reinterpret_cast<const float4*>(x0 + r * kBtPitch + v);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            float2 a = acc[q][r];
+            a = ffma2(make_float2(d[q].x, d[q].y), make_float2(x[r].x, x[r].y), a);
+            a = ffma2(make_float2(d[q].z, d[q].w), make_float2(x[r].z, x[r].w), a);
+            acc[q][r] = a;
+          }
+        if (with_bias) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) accB[q] += (d[q].x + d[q].y) + (d[q].z + d[q].w);
+        }
+      }
+    };
+
+    int s = 0;
+    uint32_t ph = 0;
+    auto next_stage = [&]() {
+      if (++s == NST) {
+        s = 0;
+        ph ^= 1;
+      }
+    };
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const long tile = blockIdx.x + (long)ti * gridDim.x;
+      const int b = (int)(tile / p.tiles_per_sample);
+      const long sv = (tile - (long)b * p.tiles_per_sample) * 128 + tid;  // this thread's voxel
+      const bool valid = sv < p.S;
+      const bool live = valid && (sv % p.P) < p.HW;
+      // ---- d(pre) = dy * selu'(y)
+      const int s_dy = s;
+      mbar_wait(&bar_full[s], ph);
+      next_stage();
+      const int s_y = s;
+      mbar_wait(&bar_full[s], ph);
+      next_stage();
+      uint32_t hi[C], lo[C];
+      {
+        const float* pdy = ring + s_dy * kBtStageFloats + tid;
+        const float* py = ring + s_y * kBtStageFloats + tid;
+#pragma unroll
+        for (int o = 0; o < C; ++o) {
+          const float d = live ? pdy[o * kBtPitch] * selu_grad_from_out(py[o * kBtPitch]) : 0.f;
+          hi[o] = __float_as_uint(d);
+          lo[o] = __float_as_uint(tf32_lo(d));
+          sdp[o * kBtPitch + tid] = d;
+        }
+      }
+      // previous tile: its MMAs retired before its epilogue ran (the epilogue waited for them), so the A columns are free
+      bt_st16(lane_base + kACol, hi);
+      bt_st8(lane_base + kACol + 16, hi + 16);
+      bt_st16(lane_base + kACol + C, lo);
+      bt_st8(lane_base + kACol + C + 16, lo + 16);
+      bt_arrive(&bar_empty[s_dy]);
+      bt_arrive(&bar_empty[s_y]);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before_sync();
+      bt_arrive(&bar_ready);
+      bt_worker_sync();  // d(pre) tile complete in shared memory
+      // ---- weight gradient (FFMA2) while the tensor core computes the input gradient
+      const int s_in1 = s;
+      mbar_wait(&bar_full[s], ph);
+      next_stage();
+      wgrad(ring + s_in1 * kBtStageFloats, accW[0], it8 == 0);
+      int s_in2 = 0;
+      if (CI2 > 0) {
+        s_in2 = s;
+        mbar_wait(&bar_full[s], ph);
+        next_stage();
+        wgrad(ring + s_in2 * kBtStageFloats, accW[1], false);
+      }
+      // ---- epilogue: input gradients from the accumulator, one lane = one voxel
+      mbar_wait(&bar_accfull, (uint32_t)(ti & 1));
+      tc_fence_after_sync();
+      {
+        const uint32_t acc = lane_base + kDCol;
+        const long off = (long)b * C * p.S + sv;
+        const float* pin1 = ring + s_in1 * kBtStageFloats + tid;
+#pragma unroll
+        for (int i0 = 0; i0 < CI; i0 += 8) {
+          float a[8], c[8];
+          bt_ld8(acc + i0, a);
+          bt_ld8(acc + NP + i0, c);
+          float* dst = (i0 < C ? p.din1 : p.din2);
+          const bool accumulate = i0 < C ? (p.flags & 1) : (p.flags & 2);
+          if (dst != nullptr && valid) {
+            float* q = dst + off + (long)(i0 < C ? i0 : i0 - C) * p.S;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = a[j] + c[j];
+              if (i0 < C && (p.flags & 4)) v *= selu_grad_from_out(pin1[(i0 + j) * kBtPitch]);
+              if (accumulate) v += q[(long)j * p.S];
+              q[(long)j * p.S] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      bt_arrive(&bar_empty[s_in1]);
+      if (CI2 > 0) bt_arrive(&bar_empty[s_in2]);
+      bt_worker_sync();  // everyone is done with sdp before the next tile overwrites it
+    }
+    // ---- per-CTA partial sums: reduce the two voxel groups through shared memory, one row per CTA
+    {
+      float* prow = p.partials + (long)blockIdx.x * PSTRIDE;
+#pragma unroll
+      for (int h = 0; h < (CI2 > 0 ? 2 : 1); ++h)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+            scratch[wg * (C * CI) + (ot * 3 + q) * CI + h * C + it8 * 3 + r] = accW[h][q][r].x + accW[h][q][r].y;
+      if (it8 == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) scratch[2 * C * CI + wg * C + ot * 3 + q] = accB[q];
+      }
+      bt_worker_sync();
+      for (int idx = tid; idx < C * CI; idx += kBtWorkers) prow[idx] = scratch[idx] + scratch[C * CI + idx];
+      for (int o = tid; o < C; o += kBtWorkers) prow[C * CI + o] = scratch[2 * C * CI + o] + scratch[2 * C * CI + C + o];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+bool pwconv_bwd_tc_eligible(const float* dy, const float* y, const float* in1, const float* in2, const float* din1,
+                            const float* din2, int ci1, int ci2, int co, long S, int act, int residual) {
+  if (!tc_enabled()) return false;
+  static const bool off = getenv("HNO_PWBWD_TC") && atoi(getenv("HNO_PWBWD_TC")) == 0;
+  if (off) return false;
+  if (ci1 != kBtC || co != kBtC || (ci2 != 0 && ci2 != kBtC) || act != 1 || residual) return false;
+  if (S < 4096 || S % 4) return false;
+  const void* ptrs[6] = {dy, y, in1, in2, din1, din2};
+  for (const void* q : ptrs)
+    if (q && reinterpret_cast<uintptr_t>(q) % 16) return false;
+  return true;
+}
+
+template <int CI2>
+static int launch_bt(BtDev p, cudaStream_t st, int* grid_out) {
+  constexpr int CI = kBtC + CI2;
+  constexpr int NB = 2 * (CI == 48 ? 48 : 32);
+  const size_t fixed = 1024 + (size_t)(kBtStageFloats + NB * kBtC + 2 * kBtC * CI + 2 * kBtC + 64) * sizeof(float);
+  int nst = (int)((233472 / 2 - 2 * 1024 - fixed) / (kBtStageFloats * sizeof(float)));
+  static const int nst_env = getenv("HNO_PWBWD_NST") ? atoi(getenv("HNO_PWBWD_NST")) : 0;
+  if (nst_env > 0) nst = nst_env;
+  if (nst > kBtMaxStages) nst = kBtMaxStages;
+  HNO_CHECK(nst >= 5, "pwconv_bwd_tc: not enough shared memory for the ring");
+  p.nst = nst;
+  const size_t smem = fixed + (size_t)nst * kBtStageFloats * sizeof(float);
+  auto kern = k_pwconv_bwd_tc<CI2>;
+  HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long grid = (long)sm_count() * 2;  // two CTAs per SM (256 TMEM columns and ~100 KB of shared memory each)
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  *grid_out = (int)grid;
+  kern<<<(int)grid, kBtThreads, smem, st>>>(p);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+int pwconv_bwd_tc(const float* dy, const float* y, const float* in1, const float* in2, const float* w, float* din1,
+                  float* din2, float* dweight, float* dbias, void* ws, int B, int ci2, long S, long P, long HW, int flags,
+                  cudaStream_t st) {
+  BtDev p;
+  p.dy = dy;
+  p.y = y;
+  p.in1 = in1;
+  p.in2 = in2;
+  p.w = w;
+  p.din1 = din1;
+  p.din2 = din2;
+  p.partials = reinterpret_cast<float*>(ws);
+  p.S = S;
+  p.P = P;
+  p.HW = HW;
+  p.tiles_per_sample = ceil_div(S, 128);
+  p.total_tiles = p.tiles_per_sample * B;
+  p.flags = flags;
+  int grid = 0;
+  if (int rc = ci2 > 0 ? launch_bt<kBtC>(p, st, &grid) : launch_bt<0>(p, st, &grid)) return rc;
+  const int ci = kBtC + ci2;
+  return reduce_partials(p.partials, grid, kBtC * ci, kBtC, dweight, dbias, (flags & 8) ? 1 : 0, st);
+}
+
+}  // namespace hno

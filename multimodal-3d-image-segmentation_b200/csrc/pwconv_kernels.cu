@@ -19,6 +19,13 @@
 
 namespace hno {
 
+// pipelined tensor-core variant for the 24(+24) -> 24 SELU layers (pwconv_bwd_tc.cu)
+bool pwconv_bwd_tc_eligible(const float* dy, const float* y, const float* in1, const float* in2, const float* din1,
+                            const float* din2, int ci1, int ci2, int co, long S, int act, int residual);
+int pwconv_bwd_tc(const float* dy, const float* y, const float* in1, const float* in2, const float* w, float* din1,
+                  float* din2, float* dweight, float* dbias, void* ws, int B, int ci2, long S, long P, long HW, int flags,
+                  cudaStream_t st);
+
 template <int ACT>
 __device__ __forceinline__ float act_f(float x) {
   return ACT == 1 ? selu_f(x) : x;
@@ -546,6 +553,8 @@ int pwconv_backward(const float* dy, const float* y, const float* in1, const flo
   HNO_CHECK(dy && in1 && w && dweight && ws && (ci2 == 0 || in2) && (act == 0 || y),
             "pwconv_backward: null pointer");
   HNO_CHECK(B >= 1 && S >= 1 && P >= 1 && HW >= 1 && HW <= P, "pwconv_backward: bad sizes");
+  if (pwconv_bwd_tc_eligible(dy, y, in1, in2, din1, din2, ci1, ci2, co, S, act, residual))
+    return pwconv_bwd_tc(dy, y, in1, in2, w, din1, din2, dweight, dbias, ws, B, ci2, S, P, HW, flags, st);
 #define X(A, B_, C, D, E)                                                                                   \
   if (ci1 == A && ci2 == B_ && co == C && act == D && (residual != 0) == E)                                 \
     return bwd_t<A, B_, C, D, E>(dy, y, in1, in2, w, din1, din2, dweight, dbias, ws, B, S, P, HW, flags, st);

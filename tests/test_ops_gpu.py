@@ -125,7 +125,8 @@ def _pw_ref(in1, in2, w, b, act, res):
                                                      (24, 24, 24, 1, False, True), (24, 0, 4, 0, False, False),
                                                      (8, 8, 8, 1, False, True), (8, 0, 3, 0, False, False),
                                                      (8, 0, 8, 1, True, False), (24, 0, 2, 0, False, False)])
-@pytest.mark.parametrize('S,P,HW', [(1000, 1000, 1000), (3 * 64, 64, 58), (777, 777, 777)])
+@pytest.mark.parametrize('S,P,HW', [(1000, 1000, 1000), (3 * 64, 64, 58), (777, 777, 777),
+                                    (5 * 1024, 1024, 1000), (4100, 4100, 4100)])  # the last two: tensor-core paths
 def test_pwconv(cuda, ci1, ci2, co, act, res, bias, S, P, HW):
     from multimodal_3d_image_segmentation_b200 import ops
     g = torch.Generator().manual_seed(7)
