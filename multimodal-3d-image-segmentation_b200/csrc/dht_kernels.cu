@@ -28,6 +28,11 @@ int dht_mid_forward(const void* plan_host, const void* plan_dev, const float* G1
                     float scale, cudaStream_t st);
 int dht_mid_adjoint(const void* plan_host, const void* plan_dev, const float* z, float* G1, long P, int nslab,
                     float scale, cudaStream_t st);
+bool dht_tail_eligible(const void* plan_host, int nslab);
+int dht_tail_forward(const void* plan_host, const void* plan_dev, const float* T2, float* z, int nslab, float scale,
+                     cudaStream_t st);
+int dht_tail_adjoint(const void* plan_host, const void* plan_dev, const float* z, float* T2, int nslab, float scale,
+                     cudaStream_t st);
 static bool mid_enabled() {
   static const bool on = !(getenv("HNO_DHT_MID") && atoi(getenv("HNO_DHT_MID")) == 0);
   return on;
@@ -656,6 +661,66 @@ static inline size_t inner_smem(int n, int J, bool analysis) {
   return (size_t)(J * n + kInnerRows * (analysis ? (n | 1) : J)) * sizeof(float);
 }
 
+// ---- tensor-core H stage ("hsplit"): D stage -> G1h[slab][h][jd][Wp] -> streamed H stage with (jd, w) contiguous ->
+//      T2[slab][jh][jd][Wp] -> tail kernel (W stage + recombination).  All but 2 % of the transform's arithmetic then
+//      runs on tcgen05 (3xTF32); HNO_DHT_HSPLIT=0 selects the fused CUDA-core middle stage instead (dht_mid.cu).
+struct HsplitGeom {
+  int D, H, W, Wp, Jd, Jh;
+  long P, rowlen;  // rowlen = Jd * Wp
+};
+static bool hsplit_enabled() {
+  static const bool on = !(getenv("HNO_DHT_HSPLIT") && atoi(getenv("HNO_DHT_HSPLIT")) == 0);
+  return on;
+}
+static bool hsplit_geom(const DhtPlanHeader* h, long P, long slab_stride, const float* x, int nslab, HsplitGeom* out) {
+  HsplitGeom g;
+  g.D = h->ax[0].n; g.H = h->ax[1].n; g.W = h->ax[2].n;
+  g.Wp = (g.W + 3) & ~3;
+  g.Jd = h->ax[0].J; g.Jh = h->ax[1].J;
+  g.P = P;
+  g.rowlen = (long)g.Jd * g.Wp;
+  *out = g;
+  if (!hsplit_enabled() || !tc_enabled() || !mid_enabled()) return false;
+  if (g.W % 2 || g.rowlen < 256 || P < 1024 || P % 4 || slab_stride % 4 || reinterpret_cast<uintptr_t>(x) % 16) return false;
+  if (g.Jd > 32 || g.Jh > 32) return false;  // one 32-column accumulator block per analysis stage
+  return dht_tail_eligible(h, nslab);
+}
+static TcStreamArgs hsplit_stage(const float* a, long lda, long gsa, int rows, long mext, int G, const float* b,
+                                 bool synthesis, int n_axis, int J, float* out, long ldo, long gso, long valid_m) {
+  TcStreamArgs r{};
+  r.nsrc = 1;
+  r.a[0] = a;
+  r.lda[0] = lda;
+  r.gsa[0] = gsa;
+  r.rows[0] = rows;
+  r.mext = mext;
+  r.G = G;
+  r.b = b;
+  r.scale = 1.f;
+  r.out = out;
+  r.ldo = ldo;
+  r.gso = gso;
+  r.valid_m = valid_m;
+  if (!synthesis) {  // K = axis samples, N = retained rows
+    r.kc = 16;
+    r.chunks_per_src = (n_axis + 15) / 16;
+    r.ldbn = n_axis;
+    r.ldbk = 1;
+    r.kvalid = n_axis;
+    r.nout = J;
+    r.loader = 1;
+  } else {           // K = retained rows, N = axis samples
+    r.kc = J <= 8 ? 8 : (J <= 24 ? 24 : 16);
+    r.chunks_per_src = (J + r.kc - 1) / r.kc;
+    r.ldbn = 1;
+    r.ldbk = n_axis;
+    r.kvalid = J;
+    r.nout = n_axis;
+    r.loader = 0;
+  }
+  return r;
+}
+
 int dht3_forward(const void* plan_host, const void* plan_dev, const float* x, long plane_pitch, long slab_stride,
                  float* z, void* ws, int nslab, float scale, cudaStream_t st) {
   const DhtPlanHeader* h;
@@ -668,6 +733,26 @@ int dht3_forward(const void* plan_host, const void* plan_dev, const float* x, lo
   float* G1 = reinterpret_cast<float*>(ws);
   float* G2 = G1 + nslab * g.g1;
   float* T = G2 + nslab * g.g2;
+  {
+    HsplitGeom hg;
+    if (hsplit_geom(h, plane_pitch, slab_stride, x, nslab, &hg)) {
+      const long g1h = (long)hg.H * hg.rowlen;  // floats per slab of G1h
+      // D analysis: x[slab][d][m] -> G1h[slab][h][jd][Wp]   (epilogue re-maps m = h * W + w)
+      TcStreamArgs s1 = hsplit_stage(x, plane_pitch, slab_stride, hg.D, plane_pitch, nslab, pf + h->ax[0].off_full,
+                                     false, hg.D, hg.Jd, G1, hg.Wp, g1h, (long)hg.H * hg.W);
+      s1.out_rw = hg.W;
+      s1.out_rp = hg.rowlen;
+      // H analysis: G1h[slab][h][(jd, w)] -> T2[slab][jh][(jd, w)]
+      float* T2 = G1 + (long)nslab * g1h;
+      TcStreamArgs s2 = hsplit_stage(G1, hg.rowlen, g1h, hg.H, hg.rowlen, nslab, pf + h->ax[1].off_full, false, hg.H,
+                                     hg.Jh, T2, hg.rowlen, (long)hg.Jh * hg.rowlen, hg.rowlen);
+      if (tc_stream_eligible(s1) && tc_stream_eligible(s2)) {
+        if (int rc = tc_stream_launch(s1, st)) return rc;
+        if (int rc = tc_stream_launch(s2, st)) return rc;
+        return dht_tail_forward(plan_host, plan_dev, T2, z, nslab, scale, st);
+      }
+    }
+  }
   {  // stage 1: D
     const DhtAxis& ax = h->ax[0];
     OuterArgs a{x, G1, pf + ax.off_fcos, pf + ax.off_fsin, pf + ax.off_full, ax.n, ax.JC, ax.JS, ax.JCp, ax.JSp,
@@ -716,6 +801,28 @@ int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, fl
   float* G1 = reinterpret_cast<float*>(ws);
   float* G2 = G1 + nslab * g.g1;
   float* T = G2 + nslab * g.g2;
+  {
+    HsplitGeom hg;
+    if (hsplit_geom(h, plane_pitch, slab_stride, x, nslab, &hg)) {
+      const long g1h = (long)hg.H * hg.rowlen;
+      // H synthesis: T2[slab][jh][(jd, w)] -> G1h[slab][h][(jd, w)]
+      float* T2 = G1 + (long)nslab * g1h;
+      TcStreamArgs s2 = hsplit_stage(T2, hg.rowlen, (long)hg.Jh * hg.rowlen, hg.Jh, hg.rowlen, nslab,
+                                     pf + h->ax[1].off_full, true, hg.H, hg.Jh, G1, hg.rowlen, g1h, hg.rowlen);
+      // D synthesis: G1h (loader re-maps m = h * W + w) -> x[slab][d][m], fused SELU / accumulate
+      TcStreamArgs s1 = hsplit_stage(G1, hg.Wp, g1h, hg.Jd, plane_pitch, nslab, pf + h->ax[0].off_full, true, hg.D,
+                                     hg.Jd, x, plane_pitch, slab_stride, (long)hg.H * hg.W);
+      s1.in_rw = hg.W;
+      s1.in_rp = hg.rowlen;
+      s1.act = epilogue == 2 ? 1 : 0;
+      s1.epi = epilogue == 1 ? 1 : 0;
+      if (tc_stream_eligible(s1) && tc_stream_eligible(s2)) {
+        if (int rc = dht_tail_adjoint(plan_host, plan_dev, z, T2, nslab, scale, st)) return rc;
+        if (int rc = tc_stream_launch(s2, st)) return rc;
+        return tc_stream_launch(s1, st);
+      }
+    }
+  }
   const bool fused_mid = mid_enabled() && dht_mid_eligible(plan_host, plane_pitch, nslab);
   if (fused_mid) {
     if (int rc = dht_mid_adjoint(plan_host, plan_dev, z, G1, plane_pitch, nslab, scale, st)) return rc;
@@ -755,7 +862,11 @@ int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, fl
 size_t dht3_workspace_floats(const void* plan_host, long plane_pitch, int nslab) {
   const auto* h = reinterpret_cast<const DhtPlanHeader*>(plan_host);
   const DhtGeom g = geom(h, plane_pitch);
-  return (size_t)nslab * (g.g1 + g.g2 + g.tt);
+  // the tensor-core H stage variant keeps G1h[H][Jd][Wp] and T2[Jh][Jd][Wp] per slab (rows padded to 16 bytes)
+  const long Wp = (g.W + 3) & ~3;
+  const size_t plain = (size_t)nslab * (g.g1 + g.g2 + g.tt);
+  const size_t hsplit = (size_t)nslab * ((size_t)g.H * g.Jd * Wp + (size_t)g.Jh * g.Jd * Wp);
+  return plain > hsplit ? plain : hsplit;
 }
 
 }  // namespace hno

@@ -401,6 +401,263 @@ __global__ void __launch_bounds__(kMidThreads, 2) k_dht_mid_adj(const float* __r
   }
 }
 
+// ================================================================================================ tails
+// Tensor-core H stage variant (dht_kernels.cu: dht_hsplit_*): the D stage keeps its result as G1h[slab][h][jd][Wp] and
+// the SAME streamed tcgen05 kernel contracts H with (jd, w) as the contiguous axis, T2[slab][jh][jd][Wp].  What is left
+// for CUDA cores is 2 % of the arithmetic: the W contraction of 29 short rows per plane and the cas recombination.
+// One CTA owns one (slab, |u_d|) pair as above.
+
+struct TailGeom {
+  int W, Wp, Jd, JCd, Jh, Jhp, Jw, Jwp, Ld, Lh, Lw;
+  long rowlen;       // Jd * Wp: distance between jh rows of T2
+  long slablen;      // Jh * rowlen
+  int off_full_w;
+  int off_kdesc[3], off_jdesc[3];
+};
+
+constexpr int kTailThreads = 256;
+
+// forward: T2 -> W analysis -> recombination -> Z
+__global__ void __launch_bounds__(kTailThreads) k_dht_tail_fwd(const float* __restrict__ T2, float* __restrict__ Z,
+                                                              const float* __restrict__ pf,
+                                                              const int* __restrict__ pi, const TailGeom g,
+                                                              float scale) {
+  extern __shared__ float4 smem4[];
+  float* s = reinterpret_cast<float*>(smem4);
+  float* t2s = s;                              // [2][Jhp][Wp]
+  float* fw = t2s + 2 * g.Jhp * g.Wp;          // [Wp][Jwp]   (rows >= W are zero)
+  float* T = fw + g.Wp * g.Jwp;                // [2][Jh * Jw]
+  const int tid = threadIdx.x;
+  const int jc = blockIdx.x;
+  const long slab = blockIdx.y;
+  const int* jd_desc = pi + g.off_jdesc[0];
+  const int js = find_sin_row(jd_desc, g.Jd, g.JCd, jc);
+  const int npass = js >= 0 ? 2 : 1;
+  // ---- the 2 x Jh rows of this CTA (16-byte asynchronous copies; pad columns and pad rows are zeroed afterwards)
+  {
+    const int q = g.Wp >> 2;
+    const int n = npass * g.Jh * q;
+    for (int idx = tid; idx < n; idx += kTailThreads) {
+      const int pass = idx / (g.Jh * q), r = idx - pass * g.Jh * q;
+      const int jh = r / q, c = r - jh * q;
+      const int row = pass == 0 ? jc : js;
+      const float* src = T2 + slab * g.slablen + (long)jh * g.rowlen + (long)row * g.Wp + 4 * c;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(t2s + (pass * g.Jhp + jh) * g.Wp + 4 * c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+    }
+  }
+  for (int idx = tid; idx < g.Wp * g.Jwp; idx += kTailThreads) {  // fw[w][j] <- full[j][w]
+    const int w = idx / g.Jwp, j = idx - w * g.Jwp;
+    fw[idx] = (w < g.W && j < g.Jw) ? __ldg(pf + g.off_full_w + j * g.W + w) : 0.f;
+  }
+  for (int idx = tid; idx < 2 * (g.Jhp - g.Jh) * g.Wp; idx += kTailThreads) {  // pad rows jh >= Jh
+    const int pass = idx / ((g.Jhp - g.Jh) * g.Wp), r = idx - pass * (g.Jhp - g.Jh) * g.Wp;
+    t2s[(pass * g.Jhp + g.Jh) * g.Wp + r] = 0.f;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (g.Wp != g.W) {  // pad columns hold whatever the workspace held: zero them (0 * NaN would poison the sums)
+    const int np = g.Wp - g.W;
+    for (int idx = tid; idx < npass * g.Jh * np; idx += kTailThreads) {
+      const int r = idx / np, c = idx - r * np;
+      const int pass = r / g.Jh, jh = r - pass * g.Jh;
+      t2s[(pass * g.Jhp + jh) * g.Wp + g.W + c] = 0.f;
+    }
+    __syncthreads();
+  }
+  // ---- W analysis: T[pass][jh][jw] = sum_w t2s[pass][jh][w] fw[w][jw]
+  //      item = (pass, 4 rows jh, 4 columns jw, half of the w range); the two halves sit in adjacent lanes
+  {
+    const int gh = g.Jhp >> 2, gw = g.Jwp >> 2;
+    const int nitem = npass * gh * gw * 2;
+    const int wq = g.Wp >> 2;
+    const int wq_half = (wq + 1) >> 1;
+    for (int item0 = 0; item0 < nitem; item0 += kTailThreads) {
+      const int item = item0 + tid;
+      const bool act = item < nitem;
+      const int half = item & 1;
+      const int tile = act ? item >> 1 : 0;
+      const int pass = tile / (gh * gw), r = tile - pass * gh * gw;
+      const int hq = r / gw, wq4 = r - hq * gw;
+      float2 acc[4][2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = make_float2(0.f, 0.f);
+      if (act) {
+        const float* tp = t2s + (pass * g.Jhp + 4 * hq) * g.Wp;
+        const float* fp = fw + 4 * wq4;
+        const int q0 = half * wq_half, q1 = half ? wq : wq_half;
+        for (int qd = q0; qd < q1; ++qd) {
+          float4 x[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) x[a] = *reinterpret_cast<const float4*>(tp + a * g.Wp + 4 * qd);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 f = *reinterpret_cast<const float4*>(fp + (4 * qd + k) * g.Jwp);
+            const float2 f01 = make_float2(f.x, f.y), f23 = make_float2(f.z, f.w);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const float xv = k == 0 ? x[a].x : (k == 1 ? x[a].y : (k == 2 ? x[a].z : x[a].w));
+              acc[a][0] = ffma2(dup2(xv), f01, acc[a][0]);
+              acc[a][1] = ffma2(dup2(xv), f23, acc[a][1]);
+            }
+          }
+        }
+      }
+      // both halves end up with the full sums; the even lane stores rows 0-1, the odd lane rows 2-3
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          acc[a][c].x += __shfl_xor_sync(0xffffffffu, acc[a][c].x, 1);
+          acc[a][c].y += __shfl_xor_sync(0xffffffffu, acc[a][c].y, 1);
+        }
+      if (act) {
+        float* Tp = T + pass * g.Jh * g.Jw;
+#pragma unroll
+        for (int a2 = 0; a2 < 2; ++a2) {
+          const int a = 2 * half + a2;
+          const int jh = 4 * hq + a;
+          if (jh < g.Jh) {
+            const float2 v01 = half ? acc[2 + a2][0] : acc[a2][0];
+            const float2 v23 = half ? acc[2 + a2][1] : acc[a2][1];
+            const float v[4] = {v01.x, v01.y, v23.x, v23.y};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (4 * wq4 + c < g.Jw) Tp[jh * g.Jw + 4 * wq4 + c] = v[c];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 8-term recombination for kd = +u and -u (same expression as k_combine, T from shared memory)
+  const int* kd_desc = pi + g.off_kdesc[0];
+  const int* kh_desc = pi + g.off_kdesc[1];
+  const int* kw_desc = pi + g.off_kdesc[2];
+  const float* Tc = T;
+  const float* Ts = T + g.Jh * g.Jw;
+  for (int a = 0; a < 2; ++a) {
+    const int kd = jd_desc[4 * jc + a];
+    if (kd < 0) continue;
+    const int sd = kd_desc[4 * kd + 1];
+    const float gd = (float)kd_desc[4 * kd + 2];
+    float* zo = Z + ((slab * g.Ld + kd) * g.Lh) * (long)g.Lw;
+    const int n = g.Lh * g.Lw;
+    for (int o = tid; o < n; o += kTailThreads) {
+      const int kh = o / g.Lw, kw = o - kh * g.Lw;
+      const int ch = kh_desc[4 * kh], sh = kh_desc[4 * kh + 1];
+      const float gh = (float)kh_desc[4 * kh + 2];
+      const int cw = kw_desc[4 * kw], sw = kw_desc[4 * kw + 1];
+      const float gw = (float)kw_desc[4 * kw + 2];
+      float v = Tc[ch * g.Jw + cw];
+      if (sh >= 0 && sw >= 0) v -= gh * gw * Tc[sh * g.Jw + sw];
+      if (sd >= 0 && sw >= 0) v -= gd * gw * Ts[ch * g.Jw + sw];
+      if (sd >= 0 && sh >= 0) v -= gd * gh * Ts[sh * g.Jw + cw];
+      if (sd >= 0) v += gd * Ts[ch * g.Jw + cw];
+      if (sh >= 0) v += gh * Tc[sh * g.Jw + cw];
+      if (sw >= 0) v += gw * Tc[ch * g.Jw + sw];
+      if (sd >= 0 && sh >= 0 && sw >= 0) v -= gd * gh * gw * Ts[sh * g.Jw + sw];
+      zo[o] = scale * v;
+    }
+  }
+}
+
+// adjoint: Z -> recombination^T -> W synthesis -> T2
+__global__ void __launch_bounds__(kTailThreads) k_dht_tail_adj(const float* __restrict__ Z, float* __restrict__ T2,
+                                                              const float* __restrict__ pf,
+                                                              const int* __restrict__ pi, const TailGeom g,
+                                                              float scale) {
+  extern __shared__ float4 smem4[];
+  float* s = reinterpret_cast<float*>(smem4);
+  float* fw = s;                         // [Jw][Wp]  (columns >= W are zero)
+  float* Tt = fw + g.Jw * g.Wp;          // [2][Jw][Jhp]  transposed: one LDS.128 yields four rows jh
+  const int tid = threadIdx.x;
+  const int jc = blockIdx.x;
+  const long slab = blockIdx.y;
+  const int* jd_desc = pi + g.off_jdesc[0];
+  const int* jh_desc = pi + g.off_jdesc[1];
+  const int* jw_desc = pi + g.off_jdesc[2];
+  const int js = find_sin_row(jd_desc, g.Jd, g.JCd, jc);
+  const int npass = js >= 0 ? 2 : 1;
+  for (int idx = tid; idx < g.Jw * g.Wp; idx += kTailThreads) {
+    const int j = idx / g.Wp, w = idx - j * g.Wp;
+    fw[idx] = w < g.W ? __ldg(pf + g.off_full_w + (long)j * g.W + w) : 0.f;
+  }
+  // ---- recombination^T (same expression as k_combine_t) for the rows jc and js
+  const float* Zs = Z + slab * (long)g.Ld * g.Lh * g.Lw;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int jd = pass == 0 ? jc : js;
+    const int isd = jd_desc[4 * jd + 2];
+    const int n = g.Jhp * g.Jw;
+    for (int o = tid; o < n; o += kTailThreads) {
+      const int jw = o / g.Jhp, jh = o - jw * g.Jhp;
+      float acc = 0.f;
+      float sign = 1.f;
+      if (jh < g.Jh) {
+        const int ish = jh_desc[4 * jh + 2], isw = jw_desc[4 * jw + 2];
+        sign = (isd + ish + isw >= 2) ? -1.f : 1.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int kd = jd_desc[4 * jd + a];
+          if (kd < 0) continue;
+          const float fd = (isd && a == 1) ? -1.f : 1.f;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int kh = jh_desc[4 * jh + b];
+            if (kh < 0) continue;
+            const float fhs = (ish && b == 1) ? -fd : fd;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int kw = jw_desc[4 * jw + c];
+              if (kw < 0) continue;
+              const float fws = (isw && c == 1) ? -fhs : fhs;
+              acc = fmaf(fws, __ldg(Zs + ((long)kd * g.Lh + kh) * g.Lw + kw), acc);
+            }
+          }
+        }
+      }
+      Tt[pass * g.Jw * g.Jhp + o] = sign * scale * acc;
+    }
+  }
+  __syncthreads();
+  // ---- W synthesis: T2[jh][row][w] = sum_jw fw[jw][w] T[jh][jw]; tile = 4 rows jh x 4 columns w
+  {
+    const int gh = g.Jhp >> 2, q = g.Wp >> 2;
+    const int nitem = npass * gh * q;
+    for (int item = tid; item < nitem; item += kTailThreads) {
+      const int pass = item / (gh * q), r = item - pass * gh * q;
+      const int hq = r / q, wg = r - hq * q;
+      const float* tp = Tt + pass * g.Jw * g.Jhp + 4 * hq;
+      const float* fp = fw + 4 * wg;
+      float2 acc[4][2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = make_float2(0.f, 0.f);
+#pragma unroll 2
+      for (int jw = 0; jw < g.Jw; ++jw) {
+        const float4 x = *reinterpret_cast<const float4*>(tp + jw * g.Jhp);
+        const float4 f = *reinterpret_cast<const float4*>(fp + jw * g.Wp);
+        const float2 f01 = make_float2(f.x, f.y), f23 = make_float2(f.z, f.w);
+        acc[0][0] = ffma2(dup2(x.x), f01, acc[0][0]);
+        acc[0][1] = ffma2(dup2(x.x), f23, acc[0][1]);
+        acc[1][0] = ffma2(dup2(x.y), f01, acc[1][0]);
+        acc[1][1] = ffma2(dup2(x.y), f23, acc[1][1]);
+        acc[2][0] = ffma2(dup2(x.z), f01, acc[2][0]);
+        acc[2][1] = ffma2(dup2(x.z), f23, acc[2][1]);
+        acc[3][0] = ffma2(dup2(x.w), f01, acc[3][0]);
+        acc[3][1] = ffma2(dup2(x.w), f23, acc[3][1]);
+      }
+      const int row = pass == 0 ? jc : js;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int jh = 4 * hq + a;
+        if (jh < g.Jh)
+          *reinterpret_cast<float4*>(T2 + slab * g.slablen + (long)jh * g.rowlen + (long)row * g.Wp + 4 * wg) =
+              make_float4(acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static MidGeom make_geom(const DhtPlanHeader* h, long P) {
   MidGeom g;
@@ -471,6 +728,69 @@ int dht_mid_adjoint(const void* plan_host, const void* plan_dev, const float* z,
     HNO_CUDA(cudaFuncSetAttribute(k_dht_mid_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   k_dht_mid_adj<<<dim3(g.JCd, nslab), kMidThreads, bytes, st>>>(z, G1, reinterpret_cast<const float*>(plan_dev),
                                                                  reinterpret_cast<const int*>(plan_dev), g, sm, scale);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- tails of the tensor-core H stage variant
+static TailGeom make_tail_geom(const DhtPlanHeader* h) {
+  TailGeom g;
+  g.W = h->ax[2].n;
+  g.Wp = r4(g.W);
+  g.Jd = h->ax[0].J;
+  g.JCd = h->ax[0].JC;
+  g.Jh = h->ax[1].J;
+  g.Jhp = r4(g.Jh);
+  g.Jw = h->ax[2].J;
+  g.Jwp = r4(g.Jw);
+  g.Ld = h->ax[0].L;
+  g.Lh = h->ax[1].L;
+  g.Lw = h->ax[2].L;
+  g.rowlen = (long)g.Jd * g.Wp;
+  g.slablen = (long)g.Jh * g.rowlen;
+  g.off_full_w = h->ax[2].off_full;
+  for (int a = 0; a < 3; ++a) {
+    g.off_kdesc[a] = h->ax[a].off_kdesc;
+    g.off_jdesc[a] = h->ax[a].off_jdesc;
+  }
+  return g;
+}
+static size_t tail_smem_fwd(const TailGeom& g) {
+  return (size_t)(2 * g.Jhp * g.Wp + g.Wp * g.Jwp + r4(2 * g.Jh * g.Jw)) * 4;
+}
+static size_t tail_smem_adj(const TailGeom& g) { return (size_t)(g.Jw * g.Wp + 2 * g.Jw * g.Jhp) * 4; }
+
+bool dht_tail_eligible(const void* plan_host, int nslab) {
+  const auto* h = reinterpret_cast<const DhtPlanHeader*>(plan_host);
+  const TailGeom g = make_tail_geom(h);
+  if (nslab < 1 || nslab > 65535) return false;
+  return tail_smem_fwd(g) <= kMidSmemLimit && tail_smem_adj(g) <= kMidSmemLimit;
+}
+
+// T2 [nslab][Jh][Jd][Wp] -> z [nslab][Ld][Lh][Lw]
+int dht_tail_forward(const void* plan_host, const void* plan_dev, const float* T2, float* z, int nslab, float scale,
+                     cudaStream_t st) {
+  const auto* h = reinterpret_cast<const DhtPlanHeader*>(plan_host);
+  const TailGeom g = make_tail_geom(h);
+  const size_t bytes = tail_smem_fwd(g);
+  if (bytes > 48 * 1024)
+    HNO_CUDA(cudaFuncSetAttribute(k_dht_tail_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  k_dht_tail_fwd<<<dim3(g.JCd, nslab), kTailThreads, bytes, st>>>(T2, z, reinterpret_cast<const float*>(plan_dev),
+                                                                   reinterpret_cast<const int*>(plan_dev), g, scale);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+// z [nslab][Ld][Lh][Lw] -> T2 [nslab][Jh][Jd][Wp]
+int dht_tail_adjoint(const void* plan_host, const void* plan_dev, const float* z, float* T2, int nslab, float scale,
+                     cudaStream_t st) {
+  const auto* h = reinterpret_cast<const DhtPlanHeader*>(plan_host);
+  const TailGeom g = make_tail_geom(h);
+  const size_t bytes = tail_smem_adj(g);
+  if (bytes > 48 * 1024)
+    HNO_CUDA(cudaFuncSetAttribute(k_dht_tail_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  k_dht_tail_adj<<<dim3(g.JCd, nslab), kTailThreads, bytes, st>>>(z, T2, reinterpret_cast<const float*>(plan_dev),
+                                                                   reinterpret_cast<const int*>(plan_dev), g, scale);
   HNO_LAUNCH_CHECK();
   return 0;
 }

@@ -43,7 +43,13 @@ struct TcShape {
   // cost the accumulate epilogue its second prefetch block (dhta 0.196 -> 0.292 ms), so every shape runs with 4
   static constexpr int kWorkerWarps = 4;
   static constexpr int kWorkers = 32 * kWorkerWarps;
-  static constexpr int kThreads = kWorkers + 64;
+  // Wide outputs (the synthesis stages: up to 121 rows per voxel) leave through shared memory and bulk tensor stores
+  // issued by a seventh warp: one STS per element instead of one STG with 64-bit address arithmetic, and the
+  // accumulate form becomes a bulk reduce-add (the old values are never loaded by the SM).
+  static constexpr bool kTmaOut = NPAD >= 128;
+  static constexpr int kStageBufs = kTmaOut ? 2 : 0;        // staging buffers of 32 rows x 128 voxels
+  static constexpr int kStageBytes = 32 * 128 * 4;
+  static constexpr int kThreads = kWorkers + 64 + (kTmaOut ? 32 : 0);
 };
 
 struct TcDev {
@@ -62,11 +68,17 @@ struct TcDev {
   int act, epi;
   int prefetch_items;  // L2 prefetch distance of the producer, in chunks (0 = off)
   long long* prof;     // debug (HNO_TC_PROF=1): per-CTA cycle counters [grid][8], else null
+  int dbg;             // HNO_TC_DBG bits (timing experiments only, results are wrong): 1 no STS, 2 no tmem ld, 4 no fence,
+                       // 8 no wait for the staging buffer, 16 no activation
+  int prof_mode;       // HNO_TC_PROF=2: slots 4..7 = staged epilogue breakdown (tmem ld, wait free, compute + STS, fence)
   // streamed operand as raw pointers (LDGSTS loader); the TMA loader uses the tensor maps instead
   const float* a[2];
   long lda[2], gsa[2];
   int rows[2];
   int loader;          // 0 = cp.async (LDGSTS) warp, 1 = TMA (one thread)
+  int tma_out;         // epilogue through shared memory + bulk tensor store / reduce-add (NPAD >= 128 instances)
+  int out_rw, in_rw;   // row re-mapping of the contiguous axis (tc_stream.h), 0 = off
+  long out_rp, in_rp;
 };
 
 template <int KC, int NPAD, int NST, int kNLo>
@@ -74,7 +86,7 @@ struct TcSmem {
   static constexpr int kChunkBytes = KC * 512;  // 4 blocks of 32 m x KC rows x 4 B
   static size_t bytes(int nchunk) {
     return 1024 /* alignment slack */ + (size_t)(NST + kNLo) * kChunkBytes + (size_t)2 * NPAD * nchunk * KC * 4 +
-           NPAD * 4;
+           NPAD * 4 + (size_t)TcShape<NPAD>::kStageBufs * TcShape<NPAD>::kStageBytes;
   }
 };
 
@@ -90,7 +102,8 @@ __device__ __forceinline__ float rn_tf32_bits(float x) {
 
 template <int KC, int NPAD, int NST, int kNLo>
 __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2 : 1))) k_tc_stream(const __grid_constant__ CUtensorMap tm0,
-                                                           const __grid_constant__ CUtensorMap tm1, const TcDev p) {
+                                                           const __grid_constant__ CUtensorMap tm1,
+                                                           const __grid_constant__ CUtensorMap tmo, const TcDev p) {
   constexpr int kChunkBytes = KC * 512;
   constexpr int NKG = KC / 8;
   constexpr int kTcWorkers = TcShape<NPAD>::kWorkers, kTcThreads = TcShape<NPAD>::kThreads;
@@ -114,6 +127,12 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
   const int ktot = p.nchunk * KC;
   float* blo = bhi + NPAD * ktot;
   float* sbias = blo + NPAD * ktot;
+  constexpr bool kTmaOut = TcShape<NPAD>::kTmaOut;
+  // staging buffers of the bulk-store epilogue: the B image and the bias occupy a multiple of 128 bytes, so these stay
+  // 128-byte aligned
+  float* stage = sbias + NPAD;
+  __shared__ __align__(8) uint64_t bar_stfull[2];   // staging buffer written by the workers   (128 arrivals)
+  __shared__ __align__(8) uint64_t bar_stfree[2];   // bulk store has read the staging buffer (1 arrival)
   __shared__ __align__(8) uint64_t bar_full[NST];   // TMA bytes landed                     (1 arrival + tx)
   __shared__ __align__(8) uint64_t bar_split[NST];  // hi / lo operands ready                (128 arrivals)
   __shared__ __align__(8) uint64_t bar_done[NST];   // MMAs of the item retired              (tcgen05.commit)
@@ -150,6 +169,10 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
     mbar_init(&bar_accfree[1], kTcWorkers);
     mbar_init(&bar_accfull[0], 1);
     mbar_init(&bar_accfull[1], 1);
+    mbar_init(&bar_stfull[0], kTcWorkers);
+    mbar_init(&bar_stfull[1], kTcWorkers);
+    mbar_init(&bar_stfree[0], 1);
+    mbar_init(&bar_stfree[1], 1);
     mbar_fence_init();
   }
   if (warp == kWW) tmem_alloc(&tmem_slot, kTmemCols);
@@ -176,10 +199,50 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
       const int g = tile / (uint32_t)p.tiles_per_slab;
       const int col = (tile - (uint32_t)g * p.tiles_per_slab) * 128 + j * 32 + q * 4;
       const bool col_ok = col < p.mext;
+      // re-mapped source (in_rw > 0): 8-byte pieces, this lane copies pieces `lane` and `lane + 32` of every row
+      long roff[2] = {0, 0};
+      bool rok[2] = {false, false};
+      uint32_t rdst[2] = {0, 0};
+      if (p.in_rw > 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pc = lane + 32 * h;  // piece 0..63 of the 512-byte tile row
+          const int m = (tile - (uint32_t)g * p.tiles_per_slab) * 128 + 2 * pc;
+          rok[h] = m < p.mext && m < p.valid_m;
+          const int hh = m / p.in_rw;
+          roff[h] = rok[h] ? (long)hh * p.in_rp + (m - hh * p.in_rw) : 0;
+          // 32-float block pc >> 4, 32-byte chunk (pc >> 2) & 3 (XOR-ed with the row below), 8-byte piece pc & 3
+          rdst[h] = (uint32_t)(pc >> 4) * (KC * 128) + ((pc & 3) << 3);
+        }
+      }
       for (int c = 0; c < nchunk; ++c) {
         const int src = c / p.chunks_per_src;
         const int row0 = (c - src * p.chunks_per_src) * KC;
         if (it >= NST) mbar_wait(&bar_done[s], ph ^ 1);  // previous use of this stage fully consumed
+        if (p.in_rw > 0) {
+          const long ld = p.lda[src];
+          const int nrow = p.rows[src] - row0;
+          const float* gp = p.a[src] + (long)g * p.gsa[src] + (long)row0 * ld;
+          const uint32_t base = smem_u32(raw + s * kChunkBytes);
+#pragma unroll 4
+          for (int r = 0; r < KC; ++r) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int pc = lane + 32 * h;
+              const uint32_t dst = base + rdst[h] + r * 128 + (((((pc >> 2) & 3) ^ r) & 3) << 5);
+              const bool ok = rok[h] && r < nrow;
+              const float* sp = ok ? gp + (long)r * ld + roff[h] : p.a[src];
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(sp), "r"(ok ? 8 : 0) : "memory");
+            }
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
+          ++it;
+          if (++s == NST) {
+            s = 0;
+            ph ^= 1;
+          }
+          continue;
+        }
         const float* gp = p.a[src] + (long)g * p.gsa[src] + (long)row0 * p.lda[src] + (col_ok ? col : 0);
         const long ld = p.lda[src];
         const int nrow = p.rows[src] - row0;  // rows of this chunk that exist (the rest reads as zero)
@@ -276,6 +339,35 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
       }
     }
     __syncwarp();
+  } else if (kTmaOut && warp == kWW + 2) {
+    // =============================================================== bulk-store issuer (one thread)
+    if (lane == 0 && p.tma_out) {
+      tma_prefetch_desc(&tmo);
+      int sblk = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const uint32_t tile = blockIdx.x + (uint32_t)ti * gridDim.x;
+        const int g = tile / (uint32_t)p.tiles_per_slab;
+        const int m0 = (tile - (uint32_t)g * p.tiles_per_slab) * 128;
+        for (int n0 = 0; n0 < p.nout; n0 += 32, ++sblk) {
+          const int sb = sblk & 1;
+          mbar_wait(&bar_stfull[sb], (uint32_t)((sblk >> 1) & 1));
+          const uint32_t src = smem_u32(stage + sb * (32 * 128));
+          if (p.epi == 1)
+            asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmo),
+                         "r"(src), "r"(m0), "r"(n0), "r"(g)
+                         : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmo),
+                         "r"(src), "r"(m0), "r"(n0), "r"(g)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer may be rewritten
+          mbar_arrive(&bar_stfree[sb]);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
   } else if (warp == kWW + 1) {
     // =============================================================== MMA issuer (one thread)
     if (lane == 0) {
@@ -332,6 +424,7 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
     // The epilogue of tile t runs AFTER the operands of tile t+1 have been split, so the tensor-core round trip of
     // tile t (issue, execute, commit, wake-up: ~1.5 us) is hidden behind useful work instead of being waited for.
     long long w_lo = 0, w_full = 0, w_acc = 0, t_epi = 0, t_split = 0;
+    int st_blk = 0;  // running index of the 32-row output blocks this CTA has staged (bulk-store epilogue)
     const long long t_begin_w = p.prof ? clock64() : 0;
     auto epilogue = [&](int ti) {
       const long long te0 = p.prof ? clock64() : 0;
@@ -339,10 +432,70 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
       const int g = tile / (uint32_t)p.tiles_per_slab;
       const int quarter = warp & 3, half = warp >> 2;  // TMEM lane quarter / which 32-column blocks this warp takes
       const int m = (tile - (uint32_t)g * p.tiles_per_slab) * 128 + quarter * 32 + lane;
-      const bool in_range = m < p.mext;
       const bool live = m < p.valid_m;
-      float* po = p.out + (long)g * p.gso + m;
+      const bool in_range = p.out_rw > 0 ? (m < p.mext && live) : m < p.mext;  // re-mapped: dead columns have no address
+      long moff = m;
+      if (p.out_rw > 0) {
+        const int hh = m / p.out_rw;
+        moff = in_range ? (long)hh * p.out_rp + (m - hh * p.out_rw) : 0;
+      }
+      float* po = p.out + (long)g * p.gso + moff;
       const uint32_t acc = tmem + (ti & 1) * NB + ((uint32_t)(quarter * 32) << 16);
+      if (kTmaOut && p.tma_out) {
+        // rows leave in blocks of 32 through the staging buffers; the store warp turns each block into one bulk tensor
+        // store (or reduce-add) that clips rows >= nout and columns >= mext itself
+        mbar_wait(&bar_accfull[ti & 1], (uint32_t)((ti >> 1) & 1));
+        if (p.prof && p.prof_mode != 2) w_acc += clock64() - te0;
+        tc_fence_after_sync();
+        const bool tile_live = (int)((tile - (uint32_t)g * p.tiles_per_slab) * 128 + 128) <= p.valid_m;  // uniform
+        const bool has_bias = p.bias != nullptr;
+        for (int n0 = 0; n0 < p.nout; n0 += 32, ++st_blk) {
+          float v[32];
+          long long q0 = p.prof_mode == 2 ? clock64() : 0, q1;
+          if (!(p.dbg & 2)) tmem_ld32(acc + n0, v);
+          if (n0 + 32 >= p.nout) {  // last read of the accumulator buffer
+            tc_fence_before_sync();
+            mbar_arrive(&bar_accfree[ti & 1]);
+          }
+          if (p.prof_mode == 2) { q1 = clock64(); w_lo += q1 - q0; q0 = q1; }
+          const int sb = st_blk & 1;
+          if (st_blk >= 2 && !(p.dbg & 8)) mbar_wait(&bar_stfree[sb], (uint32_t)(((st_blk >> 1) - 1) & 1));
+          if (p.prof_mode == 2) { q1 = clock64(); w_full += q1 - q0; q0 = q1; }
+          float* so = stage + sb * (32 * 128) + (quarter * 32 + lane);
+          if (tile_live && !has_bias) {  // the common block: no predicates at all (rows >= nout are zeros of the
+                                         // padded B image and are clipped by the bulk store)
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float2 r = make_float2(v[j], v[j + 1]);
+              if (p.act == 1 && !(p.dbg & 16)) r = selu2(r);
+              if (!(p.dbg & 1)) {
+                so[j * 128] = r.x;
+                so[(j + 1) * 128] = r.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              if (n0 + j >= p.nout) break;  // warp uniform (rows beyond nout are clipped by the store anyway)
+              float2 r = make_float2(v[j], v[j + 1]);
+              if (has_bias) {
+                r.x += sbias[n0 + j];
+                r.y += sbias[n0 + j + 1];
+              }
+              if (p.act == 1) r = selu2(r);
+              if (!live) r = make_float2(0.f, 0.f);
+              so[j * 128] = r.x;
+              so[(j + 1) * 128] = r.y;
+            }
+          }
+          if (p.prof_mode == 2) { q1 = clock64(); w_acc += q1 - q0; q0 = q1; }
+          if (!(p.dbg & 4)) fence_proxy_async_smem();
+          mbar_arrive(&bar_stfull[sb]);
+          if (p.prof_mode == 2) { q1 = clock64(); t_epi += q1 - q0; }
+        }
+        if (p.prof && p.prof_mode != 2) t_epi += clock64() - te0;
+        return;
+      }
       if (p.epi == 1) {
         // accumulate: out += acc.  The old values of a 32-row block are requested BEFORE the accumulator is waited for
         // and one block ahead of the stores (64 loads in flight per thread instead of 8: the epilogue was a chain of
@@ -465,20 +618,22 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
     };
     int it = 0, s = 0;
     uint32_t ph = 0;
-    for (int ti = 0; ti < my_tiles; ++ti) {
+    // one extra pass of the tile loop runs the epilogue of the last tile: ONE inlined copy of the (large) epilogue
+    for (int ti = 0; ti <= my_tiles; ++ti) {
       for (int c = 0; c < nchunk; ++c) {
+        if (ti < my_tiles) {
         long long t0 = p.prof ? clock64() : 0;
         if (it >= kNLo) {  // the lo buffer is free once the MMAs of item it - kNLo have retired
           const int j = it - kNLo;
           mbar_wait(&bar_done[j % NST], (uint32_t)((j / NST) & 1));
         }
-        if (p.prof) {
+        if (p.prof && p.prof_mode != 2) {
           const long long t1 = clock64();
           w_lo += t1 - t0;
           t0 = t1;
         }
         mbar_wait(&bar_full[s], ph);
-        if (p.prof) {
+        if (p.prof && p.prof_mode != 2) {
           const long long t1 = clock64();
           w_full += t1 - t0;
           t0 = t1;
@@ -498,15 +653,15 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
         fence_proxy_async_smem();
         mbar_arrive(&bar_split[s]);
         if (p.prof) t_split += clock64() - t0;
-        if (c == nchunk - 1 && ti > 0) epilogue(ti - 1);
         ++it;
         if (++s == NST) {
           s = 0;
           ph ^= 1;
         }
+        }
+        if (c == nchunk - 1 && ti > 0) epilogue(ti - 1);
       }
     }
-    if (my_tiles > 0) epilogue(my_tiles - 1);
     if (p.prof && tid == 0) {
       p.prof[blockIdx.x * 8 + 4] = w_lo;
       p.prof[blockIdx.x * 8 + 5] = w_full;
@@ -579,6 +734,8 @@ bool tc_stream_eligible(const TcStreamArgs& a) {
     if (a.lda[i] % 4 || a.gsa[i] % 4) return false;
   }
   if (a.mext % 4) return false;
+  if (a.in_rw < 0 || a.out_rw < 0 || a.in_rw % 2 || a.in_rp % 2) return false;
+  if (a.in_rw > 0 && a.nsrc != 1) return false;
   if (a.mext < 1 || a.mext >= (1L << 30) || a.G < 1 || (a.mext + 127) / 128 * a.G >= (1L << 30)) return false;
   const int kc = a.kc;
   if (kc != 24 && kc != 32 && kc != 16 && kc != 8) return false;
@@ -600,6 +757,19 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
     if (int rc = encode_tensor_map(&tm[i], a.a[j], 3, dims, strides, box, 2)) return rc;
   }
   TcDev p;
+  p.tma_out = 0;
+  CUtensorMap tmo = tm[0];
+  if (TcShape<NPAD>::kTmaOut) {
+    static const bool tma_out_on = !(getenv("HNO_TC_TMA_OUT") && atoi(getenv("HNO_TC_TMA_OUT")) == 0);
+    if (tma_out_on && a.out_rw == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0 && a.ldo % 4 == 0 && a.gso % 4 == 0 &&
+        a.nout >= 1) {
+      const uint64_t dims[3] = {(uint64_t)a.mext, (uint64_t)a.nout, (uint64_t)a.G};
+      const uint64_t strides[2] = {(uint64_t)a.ldo * 4, (uint64_t)a.gso * 4};
+      const uint32_t box[3] = {128, 32, 1};
+      if (int rc = encode_tensor_map(&tmo, a.out, 3, dims, strides, box, 0)) return rc;
+      p.tma_out = 1;
+    }
+  }
   p.b = a.b;
   p.ldbn = a.ldbn;
   p.ldbk = a.ldbk;
@@ -630,6 +800,11 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
     static const int loader = getenv("HNO_TC_LOADER") ? atoi(getenv("HNO_TC_LOADER")) : -1;
     p.loader = loader >= 0 ? loader : a.loader;
   }
+  p.out_rw = a.out_rw;
+  p.out_rp = a.out_rp;
+  p.in_rw = a.in_rw;
+  p.in_rp = a.in_rp;
+  if (p.in_rw > 0) p.loader = 0;  // only the cp.async loader can gather
   {
     static const int pf_kb = getenv("HNO_TC_PREFETCH_KB") ? atoi(getenv("HNO_TC_PREFETCH_KB")) : 96;
     p.prefetch_items = pf_kb * 1024 / (KC * 512);
@@ -651,12 +826,17 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   static const bool prof_on = getenv("HNO_TC_PROF") != nullptr;
   static long long* prof_buf = nullptr;
   p.prof = nullptr;
+  p.prof_mode = prof_on ? atoi(getenv("HNO_TC_PROF")) : 0;
+  {
+    static const int dbg = getenv("HNO_TC_DBG") ? atoi(getenv("HNO_TC_DBG")) : 0;
+    p.dbg = dbg;
+  }
   if (prof_on) {
     if (!prof_buf) cudaMalloc(&prof_buf, 4096 * 8 * sizeof(long long));
     cudaMemsetAsync(prof_buf, 0, 4096 * 8 * sizeof(long long), st);
     p.prof = prof_buf;
   }
-  kern<<<(int)grid, TcShape<NPAD>::kThreads, smem, st>>>(tm[0], tm[1], p);
+  kern<<<(int)grid, TcShape<NPAD>::kThreads, smem, st>>>(tm[0], tm[1], tmo, p);
   HNO_LAUNCH_CHECK();
   if (prof_on) {  // debug only: synchronous read-back of the per-CTA wait-cycle counters
     static long long host[4096 * 8];
@@ -693,15 +873,17 @@ int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st) {
   HNO_TC_CASE(16, 32, 5, 4, 1)
   HNO_TC_CASE(16, 32, 6, 4, 2)
   HNO_TC_CASE(16, 32, 4, 3, 3)
+  HNO_TC_CASE(16, 32, 5, 2, 4)
 #undef HNO_TC_CASE
 #define HNO_TC_CASE(KC_, NP_, NST_, NLO_)                                  \
   if (a.kc == KC_ && npad == NP_) return launch_t<KC_, NP_, NST_, NLO_>(a, st);
   HNO_TC_CASE(24, 32, 3, 2)   // pointwise conv 24(+24) -> <= 32: 3 CTAs / SM
   HNO_TC_CASE(32, 32, 3, 2)
-  HNO_TC_CASE(16, 32, 5, 2)   // D-axis analysis: 8 KB chunks
+  HNO_TC_CASE(16, 32, 3, 2)   // D / H-axis analysis: 8 KB chunks, 3 CTAs / SM (TMA loader + L2 prefetch cursor)
   HNO_TC_CASE(8, 32, 4, 2)
-  HNO_TC_CASE(24, 128, 3, 2)  // D-axis synthesis
-  HNO_TC_CASE(32, 128, 3, 2)
+  HNO_TC_CASE(24, 128, 2, 2)  // D-axis synthesis (one chunk per tile)
+  HNO_TC_CASE(16, 128, 3, 2)  // H-axis synthesis (29 rows = two chunks)
+  HNO_TC_CASE(32, 128, 2, 1)
   HNO_TC_CASE(8, 128, 3, 2)
   HNO_TC_CASE(24, 256, 3, 2)
   HNO_TC_CASE(32, 256, 3, 2)

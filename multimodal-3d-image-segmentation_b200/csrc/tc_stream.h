@@ -31,6 +31,14 @@ struct TcStreamArgs {
   int epi;             // 0 store, 1 accumulate
   int loader;          // producer of the shared-memory ring: 0 = cp.async warp (fastest for 24/48-row operands),
                        // 1 = TMA (fastest for the 121-row D-axis analysis); HNO_TC_LOADER overrides
+  // Optional row re-mapping of the contiguous axis (0 = off): column m lives at (m / rw) * rp + m % rw instead of m.
+  // Used by the truncated DHT to keep its D-stage intermediate as [h][jd][w] (the H stage then streams it with
+  // (jd, w) as the contiguous axis).  out_*: applied by the epilogue (columns >= valid_m are then not written);
+  // in_*: applied by the cp.async loader, 8-byte pieces (rw, rp, lda even; columns >= valid_m read as zero).
+  int out_rw;
+  long out_rp;
+  int in_rw;
+  long in_rp;
 };
 
 bool tc_stream_eligible(const TcStreamArgs& a);
