@@ -68,8 +68,6 @@ struct TcDev {
   int act, epi;
   int prefetch_items;  // L2 prefetch distance of the producer, in chunks (0 = off)
   long long* prof;     // debug (HNO_TC_PROF=1): per-CTA cycle counters [grid][8], else null
-  int dbg;             // HNO_TC_DBG bits (timing experiments only, results are wrong): 1 no STS, 2 no tmem ld, 4 no fence,
-                       // 8 no wait for the staging buffer, 16 no activation
   int prof_mode;       // HNO_TC_PROF=2: slots 4..7 = staged epilogue breakdown (tmem ld, wait free, compute + STS, fence)
   // streamed operand as raw pointers (LDGSTS loader); the TMA loader uses the tensor maps instead
   const float* a[2];
@@ -452,14 +450,14 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
         for (int n0 = 0; n0 < p.nout; n0 += 32, ++st_blk) {
           float v[32];
           long long q0 = p.prof_mode == 2 ? clock64() : 0, q1;
-          if (!(p.dbg & 2)) tmem_ld32(acc + n0, v);
+          tmem_ld32(acc + n0, v);
           if (n0 + 32 >= p.nout) {  // last read of the accumulator buffer
             tc_fence_before_sync();
             mbar_arrive(&bar_accfree[ti & 1]);
           }
           if (p.prof_mode == 2) { q1 = clock64(); w_lo += q1 - q0; q0 = q1; }
           const int sb = st_blk & 1;
-          if (st_blk >= 2 && !(p.dbg & 8)) mbar_wait(&bar_stfree[sb], (uint32_t)(((st_blk >> 1) - 1) & 1));
+          if (st_blk >= 2) mbar_wait(&bar_stfree[sb], (uint32_t)(((st_blk >> 1) - 1) & 1));
           if (p.prof_mode == 2) { q1 = clock64(); w_full += q1 - q0; q0 = q1; }
           float* so = stage + sb * (32 * 128) + (quarter * 32 + lane);
           if (tile_live && !has_bias) {  // the common block: no predicates at all (rows >= nout are zeros of the
@@ -467,11 +465,9 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               float2 r = make_float2(v[j], v[j + 1]);
-              if (p.act == 1 && !(p.dbg & 16)) r = selu2(r);
-              if (!(p.dbg & 1)) {
-                so[j * 128] = r.x;
-                so[(j + 1) * 128] = r.y;
-              }
+              if (p.act == 1) r = selu2(r);
+              so[j * 128] = r.x;
+              so[(j + 1) * 128] = r.y;
             }
           } else {
 #pragma unroll
@@ -489,7 +485,7 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
             }
           }
           if (p.prof_mode == 2) { q1 = clock64(); w_acc += q1 - q0; q0 = q1; }
-          if (!(p.dbg & 4)) fence_proxy_async_smem();
+          fence_proxy_async_smem();
           mbar_arrive(&bar_stfull[sb]);
           if (p.prof_mode == 2) { q1 = clock64(); t_epi += q1 - q0; }
         }
@@ -827,10 +823,6 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   static long long* prof_buf = nullptr;
   p.prof = nullptr;
   p.prof_mode = prof_on ? atoi(getenv("HNO_TC_PROF")) : 0;
-  {
-    static const int dbg = getenv("HNO_TC_DBG") ? atoi(getenv("HNO_TC_DBG")) : 0;
-    p.dbg = dbg;
-  }
   if (prof_on) {
     if (!prof_buf) cudaMalloc(&prof_buf, 4096 * 8 * sizeof(long long));
     cudaMemsetAsync(prof_buf, 0, 4096 * 8 * sizeof(long long), st);

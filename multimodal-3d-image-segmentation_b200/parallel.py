@@ -6,6 +6,8 @@ exactly one SUM all-reduce of the flat gradient per step followed by a division 
 optimizer then runs replicated.  One process per GPU, torch.distributed (NCCL over NVLink on the GPU box, gloo
 in the CPU tests).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -97,8 +99,14 @@ class Trainer:
     reproduce the reference's per-step host sync).
     """
 
-    def __init__(self, model, loss_name='DiceLoss', lr=5e-3, group=None):
+    def __init__(self, model, loss_name='DiceLoss', lr=5e-3, group=None, use_graph=None):
         from . import ops
+        # CUDA graph of forward + loss + backward (168 dependent launches per step): one graph per distinct pair of input
+        # buffers, all sharing one memory pool; the all-reduce and the Adamax kernel (whose step count is a host
+        # scalar) stay outside.  HNO_GRAPH=0 / use_graph=False launches kernel by kernel.
+        self.use_graph = (os.environ.get('HNO_GRAPH', '1') != '0') if use_graph is None else bool(use_graph)
+        self._graphs = {}
+        self._pool = None
         self.model = model
         self.engine = model.engine()
         self.kind = ops.LOSS_KINDS[loss_name]
@@ -118,13 +126,48 @@ class Trainer:
             self.engine.run_backward(S, fused=(lab, coef, None), dst=self.dst)
         return loss
 
+    def loss_and_grad_graphed(self, x, labels):
+        """loss_and_grad replayed from a CUDA graph captured for exactly these two buffers (contents may change)."""
+        global _graph_launches
+        key = (x.data_ptr(), labels.data_ptr(), tuple(x.shape), tuple(labels.shape), labels.dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 8:  # callers that allocate a fresh batch every step gain nothing from graphs
+                self.use_graph = False
+                return self.loss_and_grad(x, labels)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # eager pass first: plans, tables and workspaces are created here
+                self.loss_and_grad(x, labels)
+            cur.wait_stream(side)
+            n0 = launches()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=self._pool):
+                loss = self.loss_and_grad(x, labels)
+            if self._pool is None:
+                self._pool = graph.pool()
+            n = launches() - n0
+            _graph_launches -= n  # the capture itself launched nothing on the GPU
+            ent = self._graphs[key] = (graph, loss, n, x, labels)  # x / labels kept alive: their addresses are baked in
+        ent[0].replay()
+        _graph_launches += ent[2]
+        return ent[1]
+
     def step(self, x, labels, lr=None):
-        loss = self.loss_and_grad(x, labels)
+        loss = self.loss_and_grad_graphed(x, labels) if self.use_graph else self.loss_and_grad(x, labels)
         allreduce_mean_(self.flat.grad, self.group)
         self.optimizer.step(lr)
         return loss
 
 
+_graph_launches = 0  # kernels of libhno_b200.so launched through CUDA-graph replays (the library only counts direct ones)
+
+
 def launches(reset=False):
-    """Kernels launched by libhno_b200.so in this process so far."""
-    return int(_lib.load().hno_launch_count(1 if reset else 0))
+    """Kernels of libhno_b200.so launched in this process so far (direct launches + graph replays)."""
+    global _graph_launches
+    n = int(_lib.load().hno_launch_count(1 if reset else 0)) + _graph_launches
+    if reset:
+        _graph_launches = 0
+    return n

@@ -14,7 +14,7 @@ dev = torch.device('cuda:0')
 cfg = dict(in_channels=4, out_channels=4, filters=24, num_transform_blocks=[3] * 8, num_modes=(10, 14, 14))
 model = nets.HNOSegXS(**cfg, device=dev)
 model.load_state_dict(orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14), seed=0))
-trainer = parallel.Trainer(model, 'DiceLoss')
+trainer = parallel.Trainer(model, "DiceLoss", use_graph=False)
 g = torch.Generator().manual_seed(1234)
 x = torch.randn(batch, 4, 240, 240, 155, generator=g).to(dev)
 lab = torch.randint(0, 4, (batch, 1, 240, 240, 155), generator=g).to(torch.uint8).to(dev)
