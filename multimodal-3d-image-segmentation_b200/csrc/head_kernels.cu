@@ -18,6 +18,7 @@
 #include "hno_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace hno {
@@ -163,6 +164,27 @@ __device__ __forceinline__ void softmax_inplace(float (&v)[C]) {
   for (int c = 0; c < C; ++c) v[c] *= inv;
 }
 
+// Softmax of the fused training kernels: ex2.approx on a log2(e)-scaled argument and rcp.approx (each ~1 ulp; the
+// probabilities differ from expf / IEEE division by <= ~1e-6 relative, far inside the parity tolerance, and the row
+// kernels drop from ~70 to ~25 instructions per voxel for it).  The drop-in head keeps softmax_inplace.
+template <int C>
+__device__ __forceinline__ void softmax_fast(float (&v)[C]) {
+  float m = v[0];
+#pragma unroll
+  for (int c = 1; c < C; ++c) m = fmaxf(m, v[c]);
+  const float ml = m * kLog2e;
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    v[c] = ex2_approx(fmaf(v[c], kLog2e, -ml));
+    s += v[c];
+  }
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(s));
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c] *= inv;
+}
+
 // ------------------------------------------------------------------------------------------ head forward
 template <int C, int ACT>
 __global__ void __launch_bounds__(256) k_head_fwd(const float* __restrict__ ll, float* __restrict__ probs,
@@ -255,50 +277,46 @@ __global__ void __launch_bounds__(256) k_head_bwd_w(const float* __restrict__ dp
   for (int c = 0; c < C; ++c) g1[((long)b * C + c) * plane + idx] = acc[c];
 }
 
-// g1[bc][zd][zh][w] -> g2[bc][zd][h][w]
+// g1[bc][zd][zh][w] -> g2[bc][zd][h][w]; grid (ceil(H*W / 256), nbc * Dx): 32-bit index arithmetic only
 __global__ void __launch_bounds__(256) k_head_bwd_h(const float* __restrict__ g1, float* __restrict__ g2, InterpDev t,
                                                     long nbc) {
-  const int W = t.lo[2], H = t.lo[1], Hx = t.hi[1], Dx = t.hi[0];
-  const long total = nbc * Dx * H * W;
-  const long idx = blockIdx.x * 256L + threadIdx.x;
-  if (idx >= total) return;
-  const int w = (int)(idx % W);
-  long r = idx / W;
-  const int h = (int)(r % H);
-  r /= H;  // r = bc*Dx + zd
+  const int W = t.lo[2], H = t.lo[1], Hx = t.hi[1];
+  const int hw = blockIdx.x * 256 + threadIdx.x;
+  if (hw >= H * W) return;
+  const long r = blockIdx.y;  // bc * Dx + zd
+  const int h = hw / W, w = hw - h * W;
   const float* src = g1 + r * (long)Hx * W + w;
   float acc = 0.f;
   for (int zh = t.s[1][h]; zh < t.e[1][h]; ++zh) {
     const float l1 = t.l1[1][zh];
     const float wgt = (t.i0[1][zh] == h ? 1.f - l1 : 0.f) + (t.i1[1][zh] == h ? l1 : 0.f);
-    acc = fmaf(wgt, __ldg(src + (long)zh * W), acc);
+    acc = fmaf(wgt, __ldg(src + zh * W), acc);
   }
-  g2[idx] = acc;
+  g2[r * (long)H * W + hw] = acc;
 }
 
-// g2[bc][zd][h][w] -> dll[bc][d][P]  (padding columns zeroed)
+// g2[bc][zd][h][w] -> dll[bc][d][P]  (padding columns zeroed); grid (ceil(P / 256), D, nbc)
 __global__ void __launch_bounds__(256) k_head_bwd_d(const float* __restrict__ g2, float* __restrict__ dll, InterpDev t,
                                                     long nbc, long P) {
   const int W = t.lo[2], H = t.lo[1], D = t.lo[0], Dx = t.hi[0];
-  const long total = nbc * D * P;
-  const long idx = blockIdx.x * 256L + threadIdx.x;
-  if (idx >= total) return;
-  const int p = (int)(idx % P);
-  long r = idx / P;
-  const int d = (int)(r % D);
-  const long bc = r / D;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= P) return;
+  const int d = blockIdx.y;
+  const long bc = blockIdx.z;
+  float* dst = dll + (bc * D + d) * P + p;
   if (p >= H * W) {
-    dll[idx] = 0.f;
+    *dst = 0.f;
     return;
   }
-  const float* src = g2 + bc * (long)Dx * H * W + p;
+  const int HW = H * W;
+  const float* src = g2 + bc * (long)Dx * HW + p;
   float acc = 0.f;
   for (int zd = t.s[0][d]; zd < t.e[0][d]; ++zd) {
     const float l1 = t.l1[0][zd];
     const float wgt = (t.i0[0][zd] == d ? 1.f - l1 : 0.f) + (t.i1[0][zd] == d ? l1 : 0.f);
-    acc = fmaf(wgt, __ldg(src + (long)zd * H * W), acc);
+    acc = fmaf(wgt, __ldg(src + (long)zd * HW), acc);
   }
-  dll[idx] = acc;
+  *dst = acc;
 }
 
 // ------------------------------------------------------------------------------------------ losses
@@ -410,17 +428,273 @@ __global__ void __launch_bounds__(256) k_head_loss_moments(const float* __restri
   }
 }
 
+// ---- row kernels of the fused head + loss (the training hot path) --------------------------------------------------
+// One CTA walks whole high-resolution rows (b, zd, zh); a warp owns 32 consecutive voxels of the row (forward) or a
+// group of low-resolution taps and every voxel that touches them (backward).  The warp first blends the four
+// low-resolution rows (d0|d1 x h0|h1) of every class into ONE row segment in shared memory with coalesced loads, then
+// each lane interpolates along W from that segment: 2 shared loads per class and voxel instead of 8 scattered global
+// ones, and every voxel's softmax is evaluated exactly once (the gather of the W pass goes through shared memory).
+// (Trilinear interpolation is linear, so blending D and H before W is the same map as ATen's W-first nesting up to
+// fp32 rounding of the intermediate sums, ~1e-7 relative.)
+constexpr int kRowWarps = 6;
+
+// per-row constants of the D / H blend (identical for every lane: computed once per row)
+struct RowBlend {
+  int o00, o01, o10, o11;  // offsets of the four low-resolution rows inside one class volume (fit 32 bits)
+  float c00, c01, c10, c11;
+};
+__device__ __forceinline__ RowBlend make_row_blend(const InterpDev& t, long P, int W, int zd, int zh) {
+  const int d0 = t.i0[0][zd], d1 = t.i1[0][zd];
+  const int h0 = t.i0[1][zh], h1 = t.i1[1][zh];
+  const float ld1 = t.l1[0][zd], lh1 = t.l1[1][zh];
+  const float ld0 = 1.f - ld1, lh0 = 1.f - lh1;
+  RowBlend r;
+  r.o00 = d0 * (int)P + h0 * W;
+  r.o01 = d0 * (int)P + h1 * W;
+  r.o10 = d1 * (int)P + h0 * W;
+  r.o11 = d1 * (int)P + h1 * W;
+  r.c00 = lh0;
+  r.c01 = lh1;
+  r.c10 = ld0;
+  r.c11 = ld1;
+  return r;
+}
+template <int C>
+__device__ __forceinline__ void blend_rows(const float* __restrict__ llb, int S, const RowBlend& rb, int w,
+                                           float (&r)[C]) {
+  float a[C][4];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {  // all loads first: 4 C independent requests in flight per lane
+    const float* p = llb + c * S + w;
+    a[c][0] = __ldg(p + rb.o00);
+    a[c][1] = __ldg(p + rb.o01);
+    a[c][2] = __ldg(p + rb.o10);
+    a[c][3] = __ldg(p + rb.o11);
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    r[c] = rb.c10 * (rb.c00 * a[c][0] + rb.c01 * a[c][1]) + rb.c11 * (rb.c00 * a[c][2] + rb.c01 * a[c][3]);
+}
+
+// forward: moments per (b, c); grid (chunks, B); partials [B][C][chunks][5]
+template <int C, int ACT>
+__global__ void __launch_bounds__(32 * kRowWarps, 4) k_head_loss_rows(const float* __restrict__ ll,
+                                                                      const uint8_t* __restrict__ labels,
+                                                                      double* __restrict__ partials, InterpDev t,
+                                                                      long P) {
+  __shared__ float sR[kRowWarps][C][32];
+  __shared__ double sacc[kRowWarps][C][4];  // per-warp fp64 running sums (the lanes' fp32 sums are folded in every 64 rows)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int Wx = t.hi[2], Hx = t.hi[1], W = t.lo[2];
+  const int rows = t.hi[0] * Hx;
+  const int S = t.lo[0] * (int)P;
+  const float* llb = ll + (long)b * C * S;
+  const uint8_t* lb = labels + (long)b * rows * Wx;
+  float m[C][4];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[c][k] = 0.f;
+  if (lane < C * 4) sacc[warp][lane >> 2][lane & 3] = 0.0;
+  __syncwarp();
+  auto fold = [&]() {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = warp_sum(m[c][k]);
+        if (lane == 0) sacc[warp][c][k] += (double)v;
+        m[c][k] = 0.f;
+      }
+  };
+  int cnt = 0;
+  const int nseg = (Wx + 31) >> 5;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int zd = row / Hx, zh = row - zd * Hx;
+    const RowBlend rb = make_row_blend(t, P, W, zd, zh);
+    const uint8_t* lrow = lb + (long)row * Wx;
+    for (int seg = warp; seg < nseg; seg += kRowWarps) {
+      const int zw0 = seg << 5;
+      const int zw = zw0 + lane;
+      const int lab = zw < Wx ? (int)lrow[zw] : 0;  // requested before the blend: its latency hides behind it
+      const int wb = t.i0[2][zw0];
+      const int ntap = t.i1[2][min(zw0 + 31, Wx - 1)] - wb + 1;
+      if (lane < ntap) {
+        float r[C];
+        blend_rows<C>(llb, S, rb, wb + lane, r);
+#pragma unroll
+        for (int c = 0; c < C; ++c) sR[warp][c][lane] = r[c];
+      }
+      __syncwarp();
+      if (zw < Wx) {
+        const int w0 = t.i0[2][zw] - wb, w1 = t.i1[2][zw] - wb;
+        const float lw1 = t.l1[2][zw], lw0 = 1.f - lw1;
+        float p[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) p[c] = lw0 * sR[warp][c][w0] + lw1 * sR[warp][c][w1];
+        if (ACT == 1) softmax_fast<C>(p);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float tt = lab == c ? 1.f : 0.f;
+          m[c][0] += p[c];
+          m[c][1] += tt;
+          m[c][2] = fmaf(p[c], tt, m[c][2]);
+          m[c][3] = fmaf(p[c], p[c], m[c][3]);
+        }
+      }
+      __syncwarp();
+    }
+    if (++cnt == 64) {  // bounded fp32 run length, then into fp64
+      fold();
+      cnt = 0;
+    }
+  }
+  fold();
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * kMoments; i += blockDim.x) {
+    const int c = i / kMoments, k = i - c * kMoments;
+    const int kk = k == 4 ? 1 : k;  // t*t == t for one-hot labels
+    double sum = 0.0;
+    for (int w = 0; w < kRowWarps; ++w) sum += sacc[w][c][kk];
+    partials[(((long)b * C + c) * gridDim.x + blockIdx.x) * kMoments + k] = sum;
+  }
+}
+
+// backward, W pass: g1[b][c][zd][zh][w_lo] = sum over the voxels of the row that touch tap w_lo of weight * dlogit.
+// A warp owns TG consecutive taps and the <= 32 voxels [s(first tap), e(last tap)) that touch them.
+template <int C, int ACT>
+__global__ void __launch_bounds__(32 * kRowWarps, 4) k_head_bwd_w_rows(const float* __restrict__ ll,
+                                                                    const uint8_t* __restrict__ labels,
+                                                                    const float* __restrict__ coef,
+                                                                    const float* __restrict__ grad_loss,
+                                                                    float* __restrict__ g1, InterpDev t, long P,
+                                                                    int TG) {
+  __shared__ float sR[kRowWarps][C][32];
+  __shared__ float sD[kRowWarps][C][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int Wx = t.hi[2], Hx = t.hi[1], W = t.lo[2];
+  const int rows = t.hi[0] * Hx;
+  const int S = t.lo[0] * (int)P;
+  const float* llb = ll + (long)b * C * S;
+  const uint8_t* lb = labels + (long)b * rows * Wx;
+  float ca[C], cb[C], cg[C];
+  {
+    const float gl = grad_loss ? __ldg(grad_loss) : 1.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      ca[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 0);
+      cb[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 1);
+      cg[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 2);
+    }
+  }
+  const int ngroup = (W + TG - 1) / TG;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int zd = row / Hx, zh = row - zd * Hx;
+    const RowBlend rb = make_row_blend(t, P, W, zd, zh);
+    const uint8_t* lrow = lb + (long)row * Wx;
+    for (int q = warp; q < ngroup; q += kRowWarps) {
+      const int t0 = q * TG, t1 = min(t0 + TG, W);  // taps [t0, t1)
+      const int zs = t.s[2][t0], ze = t.e[2][t1 - 1];
+      const int zw = zs + lane;
+      const int lab = zw < ze ? (int)lrow[zw] : 0;  // requested before the blend: its latency hides behind it
+      const int wb = t.i0[2][zs];
+      const int ntap = t.i1[2][ze - 1] - wb + 1;
+      if (lane < ntap) {
+        float r[C];
+        blend_rows<C>(llb, S, rb, wb + lane, r);
+#pragma unroll
+        for (int c = 0; c < C; ++c) sR[warp][c][lane] = r[c];
+      }
+      __syncwarp();
+      if (zw < ze) {
+        const int w0 = t.i0[2][zw] - wb, w1 = t.i1[2][zw] - wb;
+        const float lw1 = t.l1[2][zw], lw0 = 1.f - lw1;
+        float p[C], g[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) p[c] = lw0 * sR[warp][c][w0] + lw1 * sR[warp][c][w1];
+        if (ACT == 1) softmax_fast<C>(p);
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c] = ca[c] + (lab == c ? cb[c] : 0.f) + cg[c] * p[c];
+        if (ACT == 1) {
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) dot = fmaf(g[c], p[c], dot);
+#pragma unroll
+          for (int c = 0; c < C; ++c) sD[warp][c][lane] = p[c] * (g[c] - dot);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) sD[warp][c][lane] = g[c];
+        }
+      }
+      __syncwarp();
+      const int wl = t0 + lane;
+      if (wl < t1) {
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.f;
+        for (int z2 = t.s[2][wl]; z2 < t.e[2][wl]; ++z2) {
+          const float l1 = t.l1[2][z2];
+          const float wgt = (t.i0[2][z2] == wl ? 1.f - l1 : 0.f) + (t.i1[2][z2] == wl ? l1 : 0.f);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, sD[warp][c][z2 - zs], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) g1[(((long)b * C + c) * (long)rows + row) * W + wl] = acc[c];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Largest tap-group size (<= 16) for which every group's voxels and taps fit one warp; 0 = use the per-voxel kernels.
+static int row_kernels_tap_group(const void* th) {
+  const auto* h = reinterpret_cast<const InterpHeader*>(th);
+  const int* iw = reinterpret_cast<const int*>(th);
+  const int W = h->lo[2], Wx = h->hi[2];
+  if (Wx < W || W < 1) return 0;
+  const int* i0 = iw + h->off_i0[2];
+  const int* i1 = iw + h->off_i1[2];
+  const int* s = iw + h->off_s[2];
+  const int* e = iw + h->off_e[2];
+  for (int w = 0; w < W; ++w)
+    if (e[w] <= s[w]) return 0;  // untouched tap
+  for (int seg = 0; seg * 32 < Wx; ++seg) {  // forward segments
+    const int zl = seg * 32 + 31 < Wx - 1 ? seg * 32 + 31 : Wx - 1;
+    if (i1[zl] - i0[seg * 32] + 1 > 32) return 0;
+  }
+  for (int tg = 16; tg >= 1; --tg) {
+    bool ok = true;
+    for (int t0 = 0; t0 < W && ok; t0 += tg) {
+      const int t1 = t0 + tg < W ? t0 + tg : W;
+      const int zs = s[t0], ze = e[t1 - 1];
+      if (ze - zs > 32 || i1[ze - 1] - i0[zs] + 1 > 32) ok = false;
+    }
+    if (ok) return tg;
+  }
+  return 0;
+}
+static bool row_kernels_enabled() {
+  static const bool on = !(getenv("HNO_HEAD_ROWS") && atoi(getenv("HNO_HEAD_ROWS")) == 0);
+  return on;
+}
+
 // one block: reduce chunk partials, evaluate the loss and the backward coefficients
 __global__ void __launch_bounds__(256) k_loss_finalize(const double* __restrict__ partials, int nchunks, int BC,
                                                        double N, int kind, float* __restrict__ loss,
                                                        float* __restrict__ coef) {
   __shared__ double sterm[256];
   double term = 0.0;
-  for (int bc = threadIdx.x; bc < BC; bc += blockDim.x) {
+  const int fwarp = threadIdx.x >> 5, flane = threadIdx.x & 31, fnw = blockDim.x >> 5;
+  for (int bc = fwarp; bc < BC; bc += fnw) {  // one warp per (b, c): lanes stride over the chunk partials
     double m[kMoments] = {0, 0, 0, 0, 0};
-    for (int ch = 0; ch < nchunks; ++ch)
+    for (int ch = flane; ch < nchunks; ch += 32)
 #pragma unroll
       for (int k = 0; k < kMoments; ++k) m[k] += partials[((long)bc * nchunks + ch) * kMoments + k];
+#pragma unroll
+    for (int k = 0; k < kMoments; ++k) m[k] = warp_sum_d(m[k]);
+    if (flane != 0) continue;
     const double sp = m[0], st = m[1], spt = m[2], spp = m[3], stt = m[4];
     double a, b, g;
     if (kind == 0) {  // nets/custom_losses.py:73-111: dice = 2 I / (sum(t + p) + 1e-7); loss = mean(1 - dice)
@@ -511,14 +785,15 @@ size_t head_backward_workspace_bytes(const void* th, int B, int C) {
 static int head_backward_passes(const InterpDev& t, float* g1, float* g2, float* dll, int B, int C, long P,
                                 cudaStream_t st) {
   const long nbc = (long)B * C;
+  HNO_CHECK(nbc * t.hi[0] <= 65535 && t.lo[0] <= 65535 && nbc <= 65535, "head backward: grid too large");
   {
-    const long total = nbc * t.hi[0] * t.lo[1] * t.lo[2];
-    k_head_bwd_h<<<ceil_div(total, 256), 256, 0, st>>>(g1, g2, t, nbc);
+    dim3 grid(ceil_div((long)t.lo[1] * t.lo[2], 256), (unsigned)(nbc * t.hi[0]));
+    k_head_bwd_h<<<grid, 256, 0, st>>>(g1, g2, t, nbc);
     HNO_LAUNCH_CHECK();
   }
   {
-    const long total = nbc * t.lo[0] * P;
-    k_head_bwd_d<<<ceil_div(total, 256), 256, 0, st>>>(g2, dll, t, nbc, P);
+    dim3 grid(ceil_div(P, 256), t.lo[0], (unsigned)nbc);
+    k_head_bwd_d<<<grid, 256, 0, st>>>(g2, dll, t, nbc, P);
     HNO_LAUNCH_CHECK();
   }
   return 0;
@@ -581,7 +856,14 @@ int head_loss_forward(const void* th, const void* td, const float* ll, const uin
   double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + ((g12 * sizeof(float) + 255) & ~(size_t)255));
   int chunks = (int)((Nx + 255) / 256 < kLossChunks ? (Nx + 255) / 256 : kLossChunks);
   dim3 grid(chunks, B);
-  HNO_CLASS_SWITCH(C, { k_head_loss_moments<kC, 1><<<grid, 256, 0, st>>>(ll, labels, partials, t, P); })
+  if (row_kernels_enabled() && row_kernels_tap_group(th) > 0) {
+    const long rows = (long)t.hi[0] * t.hi[1];
+    chunks = (int)(rows < kLossChunks ? rows : kLossChunks);
+    grid = dim3(chunks, B);
+    HNO_CLASS_SWITCH(C, { k_head_loss_rows<kC, 1><<<grid, 32 * kRowWarps, 0, st>>>(ll, labels, partials, t, P); })
+  } else {
+    HNO_CLASS_SWITCH(C, { k_head_loss_moments<kC, 1><<<grid, 256, 0, st>>>(ll, labels, partials, t, P); })
+  }
   HNO_LAUNCH_CHECK();
   k_loss_finalize<<<1, 256, 0, st>>>(partials, chunks, B * C, (double)Nx, kind, loss, coef);
   HNO_LAUNCH_CHECK();
@@ -595,10 +877,19 @@ int head_loss_backward(const void* th, const void* td, const float* ll, const ui
   HNO_CHECK(ll && labels && coef && dll && ws, "head_loss_backward: null pointer");
   float* g1 = reinterpret_cast<float*>(ws);
   float* g2 = g1 + (size_t)B * C * t.hi[0] * t.hi[1] * t.lo[2];
-  dim3 grid(ceil_div((long)t.hi[0] * t.hi[1] * t.lo[2], 256), B);
-  HNO_CLASS_SWITCH(C, {
-    k_head_bwd_w<kC, 1, 1><<<grid, 256, 0, st>>>(nullptr, nullptr, ll, labels, coef, grad_loss, g1, t, P);
-  })
+  const int tg = row_kernels_enabled() ? row_kernels_tap_group(th) : 0;
+  if (tg > 0) {
+    const long rows = (long)t.hi[0] * t.hi[1];
+    dim3 grid((int)(rows < 4 * 296 ? rows : 4 * 296), B);
+    HNO_CLASS_SWITCH(C, {
+      k_head_bwd_w_rows<kC, 1><<<grid, 32 * kRowWarps, 0, st>>>(ll, labels, coef, grad_loss, g1, t, P, tg);
+    })
+  } else {
+    dim3 grid(ceil_div((long)t.hi[0] * t.hi[1] * t.lo[2], 256), B);
+    HNO_CLASS_SWITCH(C, {
+      k_head_bwd_w<kC, 1, 1><<<grid, 256, 0, st>>>(nullptr, nullptr, ll, labels, coef, grad_loss, g1, t, P);
+    })
+  }
   HNO_LAUNCH_CHECK();
   return head_backward_passes(t, g1, g2, dll, B, C, P, st);
 }

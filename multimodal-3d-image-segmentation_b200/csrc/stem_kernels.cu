@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_stem_fwd(const float* __restrict__ x, c
 
 // dW[o][q] = sum_v dpre[o][v] * patch_q(v),  db[o] = sum_v dpre[o][v]
 template <int CIN, int F>
-__global__ void __launch_bounds__(kPwThreads, 2) k_stem_wgrad(const float* __restrict__ dpre,
+__global__ void __launch_bounds__(kPwThreads, 3) k_stem_wgrad(const float* __restrict__ dpre,
                                                               const float* __restrict__ x,
                                                               float* __restrict__ partials, StemGeom g,
                                                               int tiles_per_sample, long total_tiles) {
@@ -184,7 +184,7 @@ int stem_forward(const float* x, const float* weight, const float* bias, float* 
 }
 
 size_t stem_backward_workspace_bytes(int cin, int f) {
-  return (size_t)(sm_count() * 2 + 8) * ((size_t)f * 8 * cin + f) * sizeof(float);
+  return (size_t)(sm_count() * 3 + 8) * ((size_t)f * 8 * cin + f) * sizeof(float);
 }
 
 template <int CIN, int F>
@@ -194,7 +194,7 @@ static int stem_bwd_t(const float* dpre, const float* x, float* dweight, float* 
   constexpr int TV = kPwThreads;
   const int tps = ceil_div(g.S, TV);
   const long total = (long)tps * B;
-  long gmax = (long)sm_count() * 2;
+  long gmax = (long)sm_count() * 3;  // 58 KB of shared memory per CTA: three fit, and the phases of one hide behind the others
   const int grid = (int)(total < gmax ? total : gmax);
   const size_t smem = (size_t)(F + Q) * (TV + 4) * sizeof(float);
   auto kern = k_stem_wgrad<CIN, F>;
