@@ -58,7 +58,8 @@ int hno_dht3_forward(const void* plan_host, const void* plan_dev, const float* x
                      long slab_stride, float* z, void* workspace, int nslab, float scale, void* stream);
 /* x[slab][D][P] (op)= scale * C^T * z                 (PadInverse forward with scale = 1;
  *                                                        TransformCrop backward with scale = 1/(D*H*W))
- * epilogue: 0 store, 1 accumulate into x, 2 store selu(.) (nets/hnosegxs.py:267-268 fused) */
+ * epilogue: 0 store, 1 accumulate into x, 2 store selu(.) (nets/hnosegxs.py:267-268 fused),
+ *           3 x = selu(x + .) (nets/architectures.py:521-536: spectral branch + conv branch, then the activation) */
 int hno_dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, float* x, long plane_pitch,
                      long slab_stride, void* workspace, int nslab, float scale, int epilogue, void* stream);
 

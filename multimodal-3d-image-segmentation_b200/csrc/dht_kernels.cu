@@ -165,15 +165,18 @@ __global__ void __launch_bounds__(256) k_analysis_outer_generic(const float* __r
 // ----------------------------------------------------------------------------------------------
 // synthesis along a strided axis (exact transpose of the analysis):
 //   out[b][i][c] = EPI( scale * sum_j f_j(i) * in[b][j][c] ),  columns >= valid_cols are written as 0
-// EPI: 0 store, 1 out += value, 2 selu(value)
+// EPI: 0 store, 1 out += value, 2 selu(value), 3 out = selu(out + value)
 // ----------------------------------------------------------------------------------------------
 template <int EPI, int V>
 __device__ __forceinline__ void synth_store(float* p, const float (&val)[V], int col0, int valid_cols) {
   Vec<V> r;
-  if (EPI == 1) {
+  if (EPI == 1 || EPI == 3) {
     Vec<V> old = Vec<V>::ld(p);
 #pragma unroll
-    for (int v = 0; v < V; ++v) r.v[v] = (col0 + v < valid_cols) ? old.v[v] + val[v] : old.v[v];
+    for (int v = 0; v < V; ++v) {
+      const float x = EPI == 3 ? selu_f(old.v[v] + val[v]) : old.v[v] + val[v];
+      r.v[v] = (col0 + v < valid_cols) ? x : old.v[v];
+    }
   } else {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -506,7 +509,7 @@ static int launch_synthesis_t(const OuterArgs& a, cudaStream_t st) {
                                                    ncg, total, a.in_rs, a.in_bs, a.out_rs, a.out_bs,              \
                                                    a.valid_cols, a.scale);                                        \
   }
-  if (a.epi == 0) HNO_SYN(0) else if (a.epi == 1) HNO_SYN(1) else HNO_SYN(2)
+  if (a.epi == 0) HNO_SYN(0) else if (a.epi == 1) HNO_SYN(1) else if (a.epi == 2) HNO_SYN(2) else HNO_SYN(3)
 #undef HNO_SYN
   HNO_LAUNCH_CHECK();
   return 0;
@@ -584,8 +587,8 @@ static bool tc_outer(const OuterArgs& a, bool synthesis, TcStreamArgs* t) {
     r.kvalid = a.J;
     r.nout = a.n;
     r.valid_m = a.valid_cols;
-    r.act = a.epi == 2 ? 1 : 0;
-    r.epi = a.epi == 1 ? 1 : 0;
+    r.act = a.epi >= 2 ? 1 : 0;
+    r.epi = (a.epi == 1 || a.epi == 3) ? 1 : 0;
     r.loader = 0;
   }
   if (a.nbatch >= (1L << 31) || a.ncols < 1024 || a.out_rs % 4 || a.out_bs % 4 ||
@@ -623,8 +626,12 @@ static int launch_synthesis(const OuterArgs& a, cudaStream_t st) {
     k_synthesis_outer_generic<1><<<ceil_div(total, 256), 256, 0, st>>>(a.in, a.out, a.full, a.n, a.J, a.ncols, total,
                                                                         a.in_rs, a.in_bs, a.out_rs, a.out_bs,
                                                                         a.valid_cols, a.scale);
-  else
+  else if (a.epi == 2)
     k_synthesis_outer_generic<2><<<ceil_div(total, 256), 256, 0, st>>>(a.in, a.out, a.full, a.n, a.J, a.ncols, total,
+                                                                        a.in_rs, a.in_bs, a.out_rs, a.out_bs,
+                                                                        a.valid_cols, a.scale);
+  else
+    k_synthesis_outer_generic<3><<<ceil_div(total, 256), 256, 0, st>>>(a.in, a.out, a.full, a.n, a.J, a.ncols, total,
                                                                         a.in_rs, a.in_bs, a.out_rs, a.out_bs,
                                                                         a.valid_cols, a.scale);
   HNO_LAUNCH_CHECK();
@@ -793,7 +800,8 @@ int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, fl
   const DhtPlanHeader* h;
   if (check_plan(plan_host, &h)) return -1;
   HNO_CHECK(plan_dev && x && z && ws, "dht3_adjoint: null pointer");
-  HNO_CHECK(epilogue >= 0 && epilogue <= 2, "dht3_adjoint: epilogue must be 0 (store), 1 (accumulate) or 2 (selu)");
+  HNO_CHECK(epilogue >= 0 && epilogue <= 3,
+            "dht3_adjoint: epilogue must be 0 (store), 1 (accumulate), 2 (selu) or 3 (selu of the accumulated sum)");
   const DhtGeom g = geom(h, plane_pitch);
   HNO_CHECK(plane_pitch >= (long)g.H * g.W, "dht3_adjoint: plane pitch %ld < H*W", plane_pitch);
   const float* pf = reinterpret_cast<const float*>(plan_dev);
@@ -814,8 +822,8 @@ int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, fl
                                      hg.Jd, x, plane_pitch, slab_stride, (long)hg.H * hg.W);
       s1.in_rw = hg.W;
       s1.in_rp = hg.rowlen;
-      s1.act = epilogue == 2 ? 1 : 0;
-      s1.epi = epilogue == 1 ? 1 : 0;
+      s1.act = epilogue >= 2 ? 1 : 0;
+      s1.epi = (epilogue == 1 || epilogue == 3) ? 1 : 0;
       if (tc_stream_eligible(s1) && tc_stream_eligible(s2)) {
         if (int rc = dht_tail_adjoint(plan_host, plan_dev, z, T2, nslab, scale, st)) return rc;
         if (int rc = tc_stream_launch(s2, st)) return rc;

@@ -110,7 +110,12 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
   // kFuseN: A_hi * [B_hi | B_lo] as ONE MMA of N = 2 * NPAD (the two halves are added in the epilogue) plus A_lo * B_hi
   // into the first half: the streamed operand is read from shared memory twice per k-step instead of three times
   // (shared-memory bandwidth, not the tensor pipe, is what bounds this kernel once HBM is fed properly).
-  constexpr bool kFuseN = false;  // measured slower on B200 (pw48f 0.169 -> 0.200 ms): kept for reference
+#ifndef HNO_TC_FUSEN_KC16
+#define HNO_TC_FUSEN_KC16 1
+#endif
+  // measured slower on the 48-row pointwise convolution (pw48f 0.169 -> 0.200 ms) but the 121-row analysis stages are
+  // bound by shared-memory bandwidth (27 KB cross it per 4 KB streamed), where one read less of A per k-step pays
+  constexpr bool kFuseN = HNO_TC_FUSEN_KC16 && KC == 16 && NPAD == 32;
   constexpr int NB = kFuseN ? 2 * NPAD : NPAD;  // rows of the resident B image / accumulator columns per buffer
   constexpr uint32_t kIdesc = make_idesc_tf32(128, NPAD, 1, 0);
   constexpr uint32_t kIdesc2 = make_idesc_tf32(128, NB, 1, 0);
@@ -527,7 +532,10 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
               float* q = po + (long)n0 * p.ldo;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.nout) __stcs(q + (long)j * p.ldo, old[b % kDepth][j] + v[j]);
+                if (n0 + j < p.nout) {
+                  const float sum = old[b % kDepth][j] + v[j];
+                  __stcs(q + (long)j * p.ldo, p.act == 1 ? selu_f(sum) : sum);
+                }
             }
             if (kDepth == 1 && b + 1 < NPAD / 32 / kHalves) fetch(n0 + 32 * kHalves, old[0]);
           }
@@ -757,7 +765,7 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   CUtensorMap tmo = tm[0];
   if (TcShape<NPAD>::kTmaOut) {
     static const bool tma_out_on = !(getenv("HNO_TC_TMA_OUT") && atoi(getenv("HNO_TC_TMA_OUT")) == 0);
-    if (tma_out_on && a.out_rw == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0 && a.ldo % 4 == 0 && a.gso % 4 == 0 &&
+    if (tma_out_on && !(a.epi == 1 && a.act == 1) /* a bulk reduce-add cannot apply the SELU */ && a.out_rw == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0 && a.ldo % 4 == 0 && a.gso % 4 == 0 &&
         a.nout >= 1) {
       const uint64_t dims[3] = {(uint64_t)a.mext, (uint64_t)a.nout, (uint64_t)a.G};
       const uint64_t strides[2] = {(uint64_t)a.ldo * 4, (uint64_t)a.gso * 4};

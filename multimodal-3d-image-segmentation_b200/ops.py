@@ -51,14 +51,14 @@ def dht3_forward(x, plan, scale):
 
 
 def dht3_adjoint(z, plan, scale, epilogue=0, out=None, pitch=None):
-    """x (op)= scale * C^T z.  epilogue 0 store / 1 accumulate into `out` / 2 SELU.  Returns a dense (B,C,D,H,W)
+    """x (op)= scale * C^T z.  epilogue 0 store / 1 accumulate into `out` / 2 SELU / 3 out = selu(out + .).  Returns a dense (B,C,D,H,W)
     tensor when pitch is None, else a planar (B,C,D,pitch) one."""
     _require_cuda(z, 'z')
     z = z.contiguous()
     D, H, W = plan.spatial
     B, C = z.shape[:2]
     if out is None:
-        assert epilogue != 1
+        assert epilogue not in (1, 3)
         shape = (B, C, D, H, W) if pitch is None else (B, C, D, pitch)
         out = torch.empty(shape, dtype=torch.float32, device=z.device)
     nslab, D2, p = _geom(out)
@@ -93,6 +93,25 @@ class TruncatedIDHT(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dx):
         return dht3_forward(dx, ctx.plan, 1.0), None
+
+
+class AddIDHTSelu(torch.autograd.Function):
+    """y = selu(t + C^T z): the spectral branch of an FNO / HNO block added to its 1x1x1 conv branch and activated
+    (reference nets/architectures.py:521-536), evaluated by the epilogue of the adjoint-DHT's last stage."""
+
+    @staticmethod
+    def forward(ctx, t, z, plan):
+        y = t.detach().clone()
+        dht3_adjoint(z.detach(), plan, 1.0, epilogue=3, out=y)
+        ctx.plan = plan
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dt = selu_backward(dy.contiguous(), y)
+        return dt, dht3_forward(dt, ctx.plan, 1.0), None
 
 
 # ------------------------------------------------------------------------------------------ pointwise conv
@@ -425,7 +444,7 @@ def head_loss_backward(logits_low, labels, coef, grad_loss, tables, pitch):
     return dll
 
 
-__all__ = ['dht3_forward', 'dht3_adjoint', 'TruncatedDHT', 'TruncatedIDHT', 'pwconv_forward', 'pwconv_backward',
+__all__ = ['dht3_forward', 'dht3_adjoint', 'TruncatedDHT', 'TruncatedIDHT', 'AddIDHTSelu', 'pwconv_forward', 'pwconv_backward',
            'PointwiseConv', 'HartleyConv', 'stem_forward', 'stem_backward', 'StemConv', 'head_forward',
            'head_backward', 'HeadUpsample', 'ProbabilityLoss', 'head_loss_forward', 'head_loss_backward',
            'get_crop_plan', 'get_interp_tables', 'workspace', 'LOSS_KINDS']

@@ -216,6 +216,43 @@ def hnosegxs_forward(sd, x, num_transform_blocks, num_modes, use_resize=True, us
 
 
 # ------------------------------------------------------------------------------------------------
+# HNOSeg (NeuralOperatorSeg, transform_type='Hartley')            nets/architectures.py
+# ------------------------------------------------------------------------------------------------
+def hno_block(x, sd, prefix, modes):
+    """NeuralOperatorBlock via _TransBlock.forward (architectures.py:521-548, 551-608), shared weights, SELU:
+    spectral layer with its own transform pair + 1x1x1 conv branch -> SELU -> concat skip conv (or additive skip)."""
+    x1 = hartley_operator_with_transform(x, sd[prefix + 'op.weight'], modes)
+    x2 = pointwise(x, sd[prefix + 'conv_branch.weight'], sd.get(prefix + 'conv_branch.bias'))
+    y = selu(x1 + x2)
+    key = prefix + 'conv_concat.op.weight'
+    if key in sd:
+        return selu(pointwise(torch.cat([y, x], dim=1), sd[key], sd[prefix + 'conv_concat.op.bias']))
+    return y + x
+
+
+def hnoseg_forward(sd, x, num_transform_blocks, num_modes, softmax=True, return_logits=False):
+    """_TransSeg.forward (architectures.py:321-353) for NeuralOperatorSeg(..., 'Hartley'), use_resize=True, no deep
+    supervision."""
+    image_size = x.shape[2:]
+    x = selu(F.conv3d(x, sd['conv_in.op.weight'], sd['conv_in.op.bias'], stride=2, padding=1))
+    x = selu(pointwise(x, sd['conv1.op.weight'], sd['conv1.op.bias']))
+    for i in range(num_transform_blocks):
+        x = hno_block(x, sd, f'layers.{i}.', num_modes)
+    x = F.interpolate(x, size=tuple(image_size), mode='trilinear')
+    logits = center_padcrop(pointwise(x, sd['conv_out.weight']), image_size)
+    out = torch.softmax(logits, dim=1) if softmax else logits
+    return (out, logits) if return_logits else out
+
+
+def hnoseg_train_step(sd, x, labels, num_transform_blocks, num_modes, loss='DiceLoss'):
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    probs = hnoseg_forward(params, x, num_transform_blocks, num_modes)
+    value = LOSSES[loss](probs, to_categorical(labels, probs.shape[1]).to(probs.dtype))
+    grads = torch.autograd.grad(value, list(params.values()))
+    return value.detach(), dict(zip(params.keys(), grads))
+
+
+# ------------------------------------------------------------------------------------------------
 # Losses                                                          nets/custom_losses.py
 # ------------------------------------------------------------------------------------------------
 def to_categorical(y, num_classes):

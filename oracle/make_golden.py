@@ -160,6 +160,40 @@ def case_model():
     save('model_small', **out)
 
 
+def case_hnoseg():
+    """NeuralOperatorSeg(transform_type='Hartley') = HNOSeg: small model, forward + Dice gradients."""
+    torch.manual_seed(21)
+    cfg = dict(in_channels=2, out_channels=3, filters=8, num_transform_blocks=3, num_modes=(2, 3, 3),
+               transform_type='Hartley')
+    model = ref.NeuralOperatorSeg(**cfg)
+    torch.manual_seed(22)
+    x = torch.randn(2, 2, 18, 16, 13)
+    labels = torch.randint(0, 3, (2, 1, 18, 16, 13))
+    logits = {}
+    hook = model.conv_out.register_forward_hook(lambda m, i, o: logits.__setitem__('v', o.detach()))
+    probs = model(x)
+    hook.remove()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    o_probs, o_logits = orc.hnoseg_forward(sd, x, cfg['num_transform_blocks'], cfg['num_modes'], return_logits=True)
+    check('HNOSeg probs', o_probs, probs.detach())
+    check('HNOSeg logits', o_logits, logits['v'])
+    out = {'x': x.numpy(), 'labels': labels.numpy().astype(np.uint8), 'probs': probs.detach().numpy(),
+           'logits': logits['v'].numpy()}
+    out.update({f'sd/{k}': v.numpy() for k, v in sd.items()})
+    onehot = torch.zeros(2, 3, 18, 16, 13).scatter_(1, labels, 1.0)
+    model.zero_grad()
+    loss = ref_losses.DiceLoss()(model(x), onehot)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    o_loss, o_grads = orc.hnoseg_train_step(sd, x, labels, cfg['num_transform_blocks'], cfg['num_modes'], 'DiceLoss')
+    check('HNOSeg DiceLoss value', o_loss, loss.detach(), 1e-6)
+    for k in grads:
+        check(f'HNOSeg DiceLoss grad {k}', o_grads[k], grads[k], 2e-4)
+    out['DiceLoss/loss'] = loss.detach().numpy()
+    out.update({f'DiceLoss/grad/{k}': v.numpy() for k, v in grads.items()})
+    save('hnoseg_small', **out)
+
+
 def case_losses():
     torch.manual_seed(16)
     p = torch.softmax(torch.randn(2, 4, 6, 5, 7), dim=1).requires_grad_(True)
@@ -215,6 +249,7 @@ if __name__ == '__main__':
     case_block()
     case_losses()
     case_model()
+    case_hnoseg()
     if args.full:
         case_full()
     print('all oracle-vs-reference checks passed')

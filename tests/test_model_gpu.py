@@ -133,3 +133,51 @@ def test_trainer_cuda_graph_matches_eager(cuda):
     assert l0 == l1, (l0, l1)
     assert torch.equal(p0, p1)
     assert n0 > 100 and n1 >= n0  # the graph path adds one eager pass before its capture
+
+
+def test_hnoseg_against_reference_fixture(cuda, golden_dir):
+    """NeuralOperatorSeg(transform_type='Hartley') (HNOSeg) on the CUDA kernels against outputs and
+    Dice gradients recorded from the real reference; state_dict keys are the reference's."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'hnoseg_small.npz')))
+    model = nets.NeuralOperatorSeg(2, 3, 8, 3, (2, 3, 3), 'Hartley', device=cuda)
+    sd = _sd(g, 'sd/')
+    assert set(sd) == set(model.state_dict())
+    model.load_state_dict(sd)
+    x = torch.from_numpy(g['x']).to(cuda)
+    labels = torch.from_numpy(g['labels'].astype(np.int64))
+    probs = model(x)
+    assert rel(probs, g['probs']) < 1e-5
+    assert (probs.argmax(1).cpu() == torch.from_numpy(g['probs']).argmax(1)).float().mean().item() >= 0.9999
+    onehot = orc.to_categorical(labels, 3).to(cuda)
+    loss = nets.custom_losses.DiceLoss()(probs, onehot)
+    loss.backward()
+    assert abs(float(loss) - float(g['DiceLoss/loss'])) < 2e-6
+    for k, p in model.named_parameters():
+        ref = g[f'DiceLoss/grad/{k}']
+        assert rel(p.grad, ref) < 2e-4, (k, rel(p.grad, ref))
+    with pytest.raises(NotImplementedError):
+        nets.NeuralOperatorSeg(2, 3, 8, 1, (2, 3, 3), 'Fourier', device=cuda)
+
+
+def test_hnoseg_block_baseline_grid_against_oracle(cuda):
+    """One HNO block (transform pair inside the block) on a tensor-core-sized grid, forward and backward, against the
+    fp64 oracle: exercises the selu(accumulate) epilogue of the adjoint DHT (hno_dht3_adjoint epilogue 3)."""
+    from multimodal_3d_image_segmentation_b200.nets.architectures import NeuralOperatorBlock
+    torch.manual_seed(5)
+    blk = NeuralOperatorBlock(8, 8, (4, 5, 6), 'Hartley', device=cuda)
+    torch.nn.init.normal_(blk.op.weight, std=0.3)
+    x = torch.randn(1, 8, 20, 33, 40, generator=torch.Generator().manual_seed(6))
+    xc = x.to(cuda).requires_grad_(True)
+    y = blk(xc)
+    w = torch.randn(y.shape, generator=torch.Generator().manual_seed(7))
+    (y * w.to(cuda)).sum().backward()
+    sd = {'l.' + k: v.detach().cpu().double() for k, v in blk.state_dict().items()}
+    xr = x.double().requires_grad_(True)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    yr = orc.hno_block(xr, params, 'l.', (4, 5, 6))
+    (yr * w.double()).sum().backward()
+    assert rel(y, yr) < 1e-5
+    assert rel(xc.grad, xr.grad) < 2e-5
+    for k, p in blk.named_parameters():
+        assert rel(p.grad, params['l.' + k].grad) < 1e-4, k

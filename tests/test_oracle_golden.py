@@ -91,3 +91,18 @@ def test_param_count_known_answer():
     # the reference's only published known answer: README.md:57-63
     sd = orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14))
     assert sum(v.numel() for v in sd.values()) == 28248
+
+
+def test_hnoseg_fixture(golden_dir):
+    """NeuralOperatorSeg(transform_type='Hartley') = HNOSeg, recorded from the real reference."""
+    g = _load(golden_dir, 'hnoseg_small')
+    sd = _sd(g, 'sd/')
+    x = torch.from_numpy(g['x'])
+    probs, logits = orc.hnoseg_forward(sd, x, 3, (2, 3, 3), return_logits=True)
+    _close(probs, g['probs'])
+    _close(logits, g['logits'])
+    labels = torch.from_numpy(g['labels'].astype(np.int64))
+    loss, grads = orc.hnoseg_train_step(sd, x, labels, 3, (2, 3, 3), 'DiceLoss')
+    _close(loss, g['DiceLoss/loss'], 1e-6)
+    for k, v in grads.items():
+        _close(v, g[f'DiceLoss/grad/{k}'], 2e-4)
