@@ -19,6 +19,7 @@ plan = get_crop_plan((D, H, W), MODES, dev)
 g = torch.Generator(device=dev).manual_seed(3)
 rnd = lambda *s: torch.randn(*s, device=dev, generator=g)  # noqa: E731
 a = [rnd(batch, F, D, P) for _ in range(4)]
+acc = [rnd(batch, F, D, P) for _ in range(2)]
 z = rnd(batch, F, *plan.modes_shape)
 w48, w24, b24 = rnd(F, 2 * F) * 0.1, rnd(F, F) * 0.1, rnd(F) * 0.01
 hw = (P, H * W)
@@ -29,6 +30,7 @@ table = {
     'dhts': lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=2, out=a[1]),
     'dhta': lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=1, out=a[1]),
     'pw48b': lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, in1_is_selu=True),
+    'pw48ba': lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, din1=acc[0], din2=acc[1]),
     'pw24b': lambda: ops.pwconv_backward(a[0], a[1], a[2], None, w24, 1, False, hw=hw, in1_is_selu=True),
 }
 for n in names:
