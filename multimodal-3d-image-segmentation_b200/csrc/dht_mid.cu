@@ -401,6 +401,19 @@ __global__ void __launch_bounds__(kMidThreads, 2) k_dht_mid_adj(const float* __r
   }
 }
 
+// block-wide variant of find_sin_row: one round trip instead of a chain of up to JS dependent global loads at the very
+// start of every CTA (every thread must call it)
+__device__ __forceinline__ int find_sin_row_block(const int* jdesc, int Jd, int JCd, int jc) {
+  __shared__ int s_js;
+  if (threadIdx.x == 0) s_js = -1;
+  __syncthreads();
+  const int u = jdesc[4 * jc + 3];
+  const int j = JCd + (int)threadIdx.x;
+  if (j < Jd && jdesc[4 * j + 3] == u) s_js = j;
+  __syncthreads();
+  return s_js;
+}
+
 // ================================================================================================ tails
 // Tensor-core H stage variant (dht_kernels.cu: dht_hsplit_*): the D stage keeps its result as G1h[slab][h][jd][Wp] and
 // the SAME streamed tcgen05 kernel contracts H with (jd, w) as the contiguous axis, T2[slab][jh][jd][Wp].  What is left
@@ -411,7 +424,7 @@ struct TailGeom {
   int W, Wp, Jd, JCd, Jh, Jhp, Jw, Jwp, Ld, Lh, Lw;
   long rowlen;       // Jd * Wp: distance between jh rows of T2
   long slablen;      // Jh * rowlen
-  int off_full_w;
+  int off_full_w, off_fullT_w, off_fullP_w;
   int off_kdesc[3], off_jdesc[3];
 };
 
@@ -431,24 +444,25 @@ __global__ void __launch_bounds__(kTailThreads) k_dht_tail_fwd(const float* __re
   const int jc = blockIdx.x;
   const long slab = blockIdx.y;
   const int* jd_desc = pi + g.off_jdesc[0];
-  const int js = find_sin_row(jd_desc, g.Jd, g.JCd, jc);
+  const int js = find_sin_row_block(jd_desc, g.Jd, g.JCd, jc);
   const int npass = js >= 0 ? 2 : 1;
   // ---- the 2 x Jh rows of this CTA (16-byte asynchronous copies; pad columns and pad rows are zeroed afterwards)
   {
     const int q = g.Wp >> 2;
-    const int n = npass * g.Jh * q;
-    for (int idx = tid; idx < n; idx += kTailThreads) {
-      const int pass = idx / (g.Jh * q), r = idx - pass * g.Jh * q;
-      const int jh = r / q, c = r - jh * q;
+    const int wrp = tid >> 5, ln = tid & 31;
+    for (int r = wrp; r < npass * g.Jh; r += kTailThreads / 32) {  // a warp per row: no index divisions
+      const int pass = r >= g.Jh ? 1 : 0, jh = r - pass * g.Jh;
       const int row = pass == 0 ? jc : js;
-      const float* src = T2 + slab * g.slablen + (long)jh * g.rowlen + (long)row * g.Wp + 4 * c;
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(t2s + (pass * g.Jhp + jh) * g.Wp + 4 * c);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+      const float* src = T2 + slab * g.slablen + (long)jh * g.rowlen + (long)row * g.Wp;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(t2s + (pass * g.Jhp + jh) * g.Wp);
+      for (int c = ln; c < q; c += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16 * c), "l"(src + 4 * c) : "memory");
     }
-  }
-  for (int idx = tid; idx < g.Wp * g.Jwp; idx += kTailThreads) {  // fw[w][j] <- full[j][w]
-    const int w = idx / g.Jwp, j = idx - w * g.Jwp;
-    fw[idx] = (w < g.W && j < g.Jw) ? __ldg(pf + g.off_full_w + j * g.W + w) : 0.f;
+    // fw[w][j]: the plan's transposed, zero-padded copy of the W rows ([Wp][Jwp] floats, 16-byte pieces)
+    const float* fsrc = pf + g.off_fullT_w;
+    const unsigned fdst = (unsigned)__cvta_generic_to_shared(fw);
+    for (int c = tid; c < (g.Wp * g.Jwp) >> 2; c += kTailThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(fdst + 16 * c), "l"(fsrc + 4 * c) : "memory");
   }
   for (int idx = tid; idx < 2 * (g.Jhp - g.Jh) * g.Wp; idx += kTailThreads) {  // pad rows jh >= Jh
     const int pass = idx / ((g.Jhp - g.Jh) * g.Wp), r = idx - pass * (g.Jhp - g.Jh) * g.Wp;
@@ -542,9 +556,9 @@ __global__ void __launch_bounds__(kTailThreads) k_dht_tail_fwd(const float* __re
     const int sd = kd_desc[4 * kd + 1];
     const float gd = (float)kd_desc[4 * kd + 2];
     float* zo = Z + ((slab * g.Ld + kd) * g.Lh) * (long)g.Lw;
-    const int n = g.Lh * g.Lw;
-    for (int o = tid; o < n; o += kTailThreads) {
-      const int kh = o / g.Lw, kw = o - kh * g.Lw;
+    for (int kh = tid >> 5; kh < g.Lh; kh += kTailThreads / 32)
+     for (int kw = tid & 31; kw < g.Lw; kw += 32) {  // a warp per output row: no index divisions
+      const int o = kh * g.Lw + kw;
       const int ch = kh_desc[4 * kh], sh = kh_desc[4 * kh + 1];
       const float gh = (float)kh_desc[4 * kh + 2];
       const int cw = kw_desc[4 * kw], sw = kw_desc[4 * kw + 1];
@@ -577,20 +591,22 @@ __global__ void __launch_bounds__(kTailThreads) k_dht_tail_adj(const float* __re
   const int* jd_desc = pi + g.off_jdesc[0];
   const int* jh_desc = pi + g.off_jdesc[1];
   const int* jw_desc = pi + g.off_jdesc[2];
-  const int js = find_sin_row(jd_desc, g.Jd, g.JCd, jc);
+  const int js = find_sin_row_block(jd_desc, g.Jd, g.JCd, jc);
   const int npass = js >= 0 ? 2 : 1;
-  for (int idx = tid; idx < g.Jw * g.Wp; idx += kTailThreads) {
-    const int j = idx / g.Wp, w = idx - j * g.Wp;
-    fw[idx] = w < g.W ? __ldg(pf + g.off_full_w + (long)j * g.W + w) : 0.f;
+  {  // fw[jw][w]: the plan's zero-padded copy of the W rows ([Jw][Wp] floats, 16-byte pieces)
+    const float* fsrc = pf + g.off_fullP_w;
+    const unsigned fdst = (unsigned)__cvta_generic_to_shared(fw);
+    for (int c = tid; c < (g.Jw * g.Wp) >> 2; c += kTailThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(fdst + 16 * c), "l"(fsrc + 4 * c) : "memory");
   }
   // ---- recombination^T (same expression as k_combine_t) for the rows jc and js
   const float* Zs = Z + slab * (long)g.Ld * g.Lh * g.Lw;
   for (int pass = 0; pass < npass; ++pass) {
     const int jd = pass == 0 ? jc : js;
     const int isd = jd_desc[4 * jd + 2];
-    const int n = g.Jhp * g.Jw;
-    for (int o = tid; o < n; o += kTailThreads) {
-      const int jw = o / g.Jhp, jh = o - jw * g.Jhp;
+    for (int jw = tid >> 5; jw < g.Jw; jw += kTailThreads / 32)
+     for (int jh = tid & 31; jh < g.Jhp; jh += 32) {  // a warp per column of T: no index divisions
+      const int o = jw * g.Jhp + jh;
       float acc = 0.f;
       float sign = 1.f;
       if (jh < g.Jh) {
@@ -619,6 +635,7 @@ __global__ void __launch_bounds__(kTailThreads) k_dht_tail_adj(const float* __re
       Tt[pass * g.Jw * g.Jhp + o] = sign * scale * acc;
     }
   }
+  cp_async_wait_all();
   __syncthreads();
   // ---- W synthesis: T2[jh][row][w] = sum_jw fw[jw][w] T[jh][jw]; tile = 4 rows jh x 4 columns w
   {
@@ -749,6 +766,8 @@ static TailGeom make_tail_geom(const DhtPlanHeader* h) {
   g.rowlen = (long)g.Jd * g.Wp;
   g.slablen = (long)g.Jh * g.rowlen;
   g.off_full_w = h->ax[2].off_full;
+  g.off_fullT_w = h->ax[2].off_fullT;
+  g.off_fullP_w = h->ax[2].off_fullP;
   for (int a = 0; a < 3; ++a) {
     g.off_kdesc[a] = h->ax[a].off_kdesc;
     g.off_jdesc[a] = h->ax[a].off_jdesc;

@@ -19,6 +19,7 @@ size_t dht_plan_words(const int n[3], const int L[3]) {
     int jp = round4(std::max(jmax, 1));
     words += (size_t)(nh + 1) * jp * 2;   // fold cos + fold sin
     words += (size_t)2 * jmax * n[a];     // full rows
+    words += (size_t)2 * round4(n[a]) * round4(2 * jmax);  // transposed + padded copies of the full rows
     words += (size_t)4 * L[a];            // kdesc
     words += (size_t)4 * 2 * jmax;        // jdesc
     words += 16;                          // alignment slack
@@ -113,6 +114,19 @@ int dht_plan_fill(void* blob, size_t bytes, const int n[3], const int* const kli
         fw[cur + (size_t)j * na + i] = (float)(j < ax.JC ? c : s);
       }
     cur += (size_t)ax.J * na;
+    align4();
+    {
+      const int n4 = round4(na), J4 = round4(ax.J);
+      const size_t full = (size_t)ax.off_full;
+      ax.off_fullT = (int)cur;
+      for (int i = 0; i < na; ++i)
+        for (int j = 0; j < ax.J; ++j) fw[cur + (size_t)i * J4 + j] = fw[full + (size_t)j * na + i];
+      cur += (size_t)n4 * J4;
+      ax.off_fullP = (int)cur;
+      for (int j = 0; j < ax.J; ++j)
+        for (int i = 0; i < na; ++i) fw[cur + (size_t)j * n4 + i] = fw[full + (size_t)j * na + i];
+      cur += (size_t)ax.J * n4;
+    }
     align4();
     ax.off_kdesc = (int)cur;
     for (int t = 0; t < La; ++t) {

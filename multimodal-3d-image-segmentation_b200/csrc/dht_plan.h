@@ -37,7 +37,9 @@ struct DhtAxis {
   int off_full;  // float [J][n]        : unfolded rows (cos rows first, then sin rows)
   int off_kdesc; // int   [L][4]        : {cos row, sin row or -1, sigma, k}
   int off_jdesc; // int   [J][4]        : {index in k list of +u or -1, index of -u or -1, is_sin, u}
-  int pad[3];
+  int off_fullT; // float [n4][J4]      : transposed unfolded rows, zero padded (n4, J4 = n, J rounded up to 4)
+  int off_fullP; // float [J][n4]       : unfolded rows, zero padded to n4 columns
+  int pad[1];
 };
 
 struct DhtPlanHeader {
@@ -49,7 +51,7 @@ struct DhtPlanHeader {
 };
 
 constexpr int kDhtPlanMagic = 0x484E4F50;
-constexpr int kDhtPlanVersion = 1;
+constexpr int kDhtPlanVersion = 2;
 
 size_t dht_plan_words(const int n[3], const int L[3]);
 // Returns 0 on success; fills `blob` (must hold dht_plan_words()*4 bytes).

@@ -478,6 +478,7 @@ static int bwd_t(const float* dy, const float* y, const float* in1, const float*
   X(8, 0, 8, 1, true)     \
   X(8, 0, 8, 1, false)    \
   X(8, 8, 8, 1, false)    \
+  X(8, 8, 8, 0, false)    \
   X(8, 0, 8, 0, false)    \
   X(8, 0, 2, 0, false)    \
   X(8, 0, 3, 0, false)    \
@@ -485,6 +486,7 @@ static int bwd_t(const float* dy, const float* y, const float* in1, const float*
   X(24, 0, 24, 1, true)   \
   X(24, 0, 24, 1, false)  \
   X(24, 24, 24, 1, false) \
+  X(24, 24, 24, 0, false) \
   X(24, 0, 24, 0, false)  \
   X(24, 0, 2, 0, false)   \
   X(24, 0, 3, 0, false)   \

@@ -146,19 +146,27 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- resident operand: B image (hi / lo), bias
-  for (int idx = tid; idx < NPAD * ktot; idx += kTcThreads) {
-    const int n = idx / ktot, k = idx - n * ktot;
-    float v = 0.f;
-    if (n < p.nvalid && k < p.kvalid) v = p.scale * __ldg(p.b + (long)n * p.ldbn + (long)k * p.ldbk);
-    const float hi = rn_tf32_bits(v);
-    if (kFuseN) {  // one image: rows [0, NPAD) = hi, rows [NPAD, 2 NPAD) = lo
-      bhi[kmajor_plain_index<NB>(n, k)] = hi;
-      bhi[kmajor_plain_index<NB>(NPAD + n, k)] = v - hi;
-    } else {
-      const int o = kmajor_plain_index<NPAD>(n, k);
-      bhi[o] = hi;
-      blo[o] = v - hi;
-    }
+  {
+    // no divisions, coalesced along whichever index of B is contiguous in memory (every CTA of every launch pays this
+    // prologue: 1.5 tiles per CTA in the H stages of the transform)
+    constexpr int kNW = kTcThreads / 32;
+    const bool k_contig = p.ldbk == 1;
+    const int n_outer = k_contig ? NPAD : ktot, n_inner = k_contig ? ktot : NPAD;
+    for (int o = tid >> 5; o < n_outer; o += kNW)
+      for (int i = tid & 31; i < n_inner; i += 32) {
+        const int n = k_contig ? o : i, k = k_contig ? i : o;
+        float v = 0.f;
+        if (n < p.nvalid && k < p.kvalid) v = p.scale * __ldg(p.b + (long)n * p.ldbn + (long)k * p.ldbk);
+        const float hi = rn_tf32_bits(v);
+        if (kFuseN) {  // one image: rows [0, NPAD) = hi, rows [NPAD, 2 NPAD) = lo
+          bhi[kmajor_plain_index<NB>(n, k)] = hi;
+          bhi[kmajor_plain_index<NB>(NPAD + n, k)] = v - hi;
+        } else {
+          const int idx = kmajor_plain_index<NPAD>(n, k);
+          bhi[idx] = hi;
+          blo[idx] = v - hi;
+        }
+      }
   }
   for (int n = tid; n < NPAD; n += kTcThreads) sbias[n] = (p.bias != nullptr && n < p.nout) ? __ldg(p.bias + n) : 0.f;
   if (tid == 0) {

@@ -7,6 +7,7 @@ Same class names, constructor signatures, attribute names and ``state_dict`` key
 from . import custom_losses  # noqa: F401
 from .architectures import NeuralOperatorSeg  # noqa: F401
 from .dht import dht2, dht3, dhtn  # noqa: F401
+from .fourier_operator import FourierOperator  # noqa: F401
 from .hartley_operator import HartleyOperator, get_reverse, hartley_conv  # noqa: F401
 from .hnosegxs import HNOSegXS, HNOXSBlock, NeuralOperatorBlock, PadInverse, TransformCrop  # noqa: F401
 from .nets_utils import ConvNormAct, init_weights_for_snn, spatial_padcrop  # noqa: F401

@@ -9,8 +9,9 @@ and the concat-skip convolution.  Here a block is four launches of the same kern
 
 (``selu(0) == 0``, so the SELU the reference applies to the zero-padded spectrum only acts on the retained modes.)
 The module tree and ``state_dict`` keys are the reference's (``layers.{i}.op.weight``, ``layers.{i}.conv_branch.weight``,
-``layers.{i}.conv_concat.op.*``).  ``transform_type='Fourier'`` (FNO / FNOSeg, nets/fourier_operator.py) is the next
-widening step and raises NotImplementedError: there is no PyTorch fallback in this package.
+``layers.{i}.conv_concat.op.*``).  ``transform_type='Fourier'`` (FNOSeg, "FNOSeg3D" of BASELINE.json) swaps the mix for
+``FourierOperator.spectral`` (nets/fourier_operator.py: the same truncated transform onto the symmetric mode set, complex
+24x24 mixing, no frequency-domain activation); keys ``layers.{i}.op.weight_real / weight_imag``.
 """
 from functools import partial
 from typing import Union
@@ -21,6 +22,7 @@ from torch import nn
 
 from .. import ops
 from ..plan import get_crop_plan, get_interp_tables, plane_pitch  # noqa: F401
+from .fourier_operator import FourierOperator
 from .hartley_operator import HartleyOperator
 from .nets_utils import ConvNormAct, _is_selu, init_weights_for_snn, spatial_padcrop
 
@@ -33,9 +35,6 @@ class NeuralOperatorBlock(nn.Module):
                  use_block_concat=True):
         super().__init__()
         assert transform_type in ('Fourier', 'Hartley')
-        if transform_type == 'Fourier':
-            raise NotImplementedError('hno_b200: the Fourier spectral layer (FNO / FNOSeg) is not built yet; '
-                                      "use transform_type='Hartley' (HNOSeg)")
         if ndim != 5:
             raise NotImplementedError('hno_b200 NeuralOperatorBlock supports 3-D (ndim=5) only')
         if not _is_selu(activation):
@@ -46,8 +45,10 @@ class NeuralOperatorBlock(nn.Module):
             raise NotImplementedError("hno_b200: NeuralOperatorBlock supports weights_type='shared' only (the "
                                       "per-mode 'individual' weights are available through HartleyOperator itself)")
         self.use_block_skip = use_block_skip
-        self.op = HartleyOperator(in_channels, out_channels, num_modes, use_bias=False, weights_type=weights_type,
-                                  ndim=ndim, device=device)
+        op = FourierOperator if transform_type == 'Fourier' else HartleyOperator
+        self.op = op(in_channels, out_channels, num_modes, use_bias=False, weights_type=weights_type, ndim=ndim,
+                     device=device)
+        self.transform_type = transform_type
         self.conv_branch = nn.Conv3d(in_channels, out_channels, kernel_size=1, bias=use_bias_conv_branch, device=device)
         self.normalization = None
         self.activation = nn.functional.selu
@@ -66,9 +67,12 @@ class NeuralOperatorBlock(nn.Module):
         spatial = tuple(x.shape[2:])
         wb = self.conv_branch.weight
         t = ops.PointwiseConv.apply(x, None, wb.view(wb.shape[0], -1), self.conv_branch.bias, 0, False)
-        plan = get_crop_plan(spatial, self.op.num_modes, x.device)
-        z = ops.TruncatedDHT.apply(x, plan)
-        z = ops.PointwiseConv.apply(z, None, self.op.weight, None, 1, False)  # mix + SELU on the retained modes
+        if self.transform_type == 'Fourier':  # no activation in the frequency domain (fourier_operator.py:148-211)
+            z, plan = self.op.spectral(x)
+        else:
+            plan = get_crop_plan(spatial, self.op.num_modes, x.device)
+            z = ops.TruncatedDHT.apply(x, plan)
+            z = ops.PointwiseConv.apply(z, None, self.op.weight, None, 1, False)  # mix + SELU on the retained modes
         y = ops.AddIDHTSelu.apply(t, z, plan)
         if self.use_block_skip:
             if self.conv_concat is not None:
@@ -79,7 +83,7 @@ class NeuralOperatorBlock(nn.Module):
 
 
 class NeuralOperatorSeg(nn.Module):
-    """FNO / FNOSeg / HNOSeg family (reference :356-429 over _TransSeg :255-353); Hartley transform only for now."""
+    """FNO / FNOSeg / HNOSeg family (reference :356-429 over _TransSeg :255-353), shared weights."""
 
     def __init__(self, in_channels, out_channels, filters, num_transform_blocks, num_modes, transform_type,
                  weights_type='shared', use_resize=True, use_deep_supervision=False, use_bias_conv_branch=False,

@@ -38,11 +38,15 @@ def spatial_padcrop(x, target_shape):
 
 def init_weights_for_snn(module):
     """SNN initialisation (reference :102-117): kaiming-normal 'linear' weights, bias ~ U(-1e-3, 1e-3)."""
+    from .fourier_operator import FourierOperator
     from .hartley_operator import HartleyOperator
     if isinstance(module, (nn.Conv2d, nn.Conv3d, nn.ConvTranspose2d, nn.ConvTranspose3d, HartleyOperator)):
         nn.init.kaiming_normal_(module.weight, nonlinearity='linear')
         if module.bias is not None:
             nn.init.uniform_(module.bias, -0.001, 0.001)
+    elif isinstance(module, FourierOperator):
+        nn.init.kaiming_normal_(module.weight_real, nonlinearity='linear')
+        nn.init.kaiming_normal_(module.weight_imag, nonlinearity='linear')
 
 
 def _is_selu(activation):

@@ -218,10 +218,27 @@ def hnosegxs_forward(sd, x, num_transform_blocks, num_modes, use_resize=True, us
 # ------------------------------------------------------------------------------------------------
 # HNOSeg (NeuralOperatorSeg, transform_type='Hartley')            nets/architectures.py
 # ------------------------------------------------------------------------------------------------
+def fourier_operator_with_transform(x, weight_real, weight_imag, modes):
+    """FourierOperator._call3d, shared weights, no bias (fourier_operator.py:148-211): rfftn(norm='forward'), mix the
+    four retained corners of the half-spectrum with the complex (O, I) weight, zero-pad, irfftn(norm='forward')."""
+    s0, s1, s2 = x.shape[2:]
+    m0, m1, m2 = (s // 2 if 2 * m > s else m for m, s in zip(modes, (s0, s1, s2)))
+    f = torch.fft.rfftn(x, dim=(-3, -2, -1), norm='forward')
+    w = torch.complex(weight_real, weight_imag)
+    full = torch.zeros((x.shape[0], w.shape[0], s0, s1, m2), dtype=f.dtype)
+    for sd_ in (slice(0, m0), slice(s0 - m0, s0)):
+        for sh_ in (slice(0, m1), slice(s1 - m1, s1)):
+            full[:, :, sd_, sh_, :] = torch.einsum('oi,bidhw->bodhw', w, f[:, :, sd_, sh_, :m2])
+    return torch.fft.irfftn(full, s=(s0, s1, s2), dim=(-3, -2, -1), norm='forward')
+
+
 def hno_block(x, sd, prefix, modes):
     """NeuralOperatorBlock via _TransBlock.forward (architectures.py:521-548, 551-608), shared weights, SELU:
     spectral layer with its own transform pair + 1x1x1 conv branch -> SELU -> concat skip conv (or additive skip)."""
-    x1 = hartley_operator_with_transform(x, sd[prefix + 'op.weight'], modes)
+    if prefix + 'op.weight_real' in sd:  # transform_type='Fourier' (FNOSeg): no activation in the frequency domain
+        x1 = fourier_operator_with_transform(x, sd[prefix + 'op.weight_real'], sd[prefix + 'op.weight_imag'], modes)
+    else:
+        x1 = hartley_operator_with_transform(x, sd[prefix + 'op.weight'], modes)
     x2 = pointwise(x, sd[prefix + 'conv_branch.weight'], sd.get(prefix + 'conv_branch.bias'))
     y = selu(x1 + x2)
     key = prefix + 'conv_concat.op.weight'

@@ -160,11 +160,33 @@ def case_model():
     save('model_small', **out)
 
 
-def case_hnoseg():
-    """NeuralOperatorSeg(transform_type='Hartley') = HNOSeg: small model, forward + Dice gradients."""
+def case_fourier_operator():
+    """FourierOperator with transform, shared weights (BASELINE config 3's layer): forward + gradients, incl. the
+    clamp path (modes larger than half the grid) and an even grid."""
+    from nets.fourier_operator import FourierOperator
+    out = {}
+    for tag, shape, modes in (('a', (9, 8, 7), (2, 3, 3)), ('b', (6, 7, 8), (5, 2, 9))):
+        torch.manual_seed(31)
+        op = FourierOperator(8, 8, modes)  # channel counts the CUDA pointwise kernels are instantiated for
+        x = torch.randn(2, 8, *shape, requires_grad=True)
+        y = op(x)
+        w = torch.randn(y.shape)
+        (y * w).sum().backward()
+        yo = orc.fourier_operator_with_transform(x.detach(), op.weight_real.detach(), op.weight_imag.detach(), modes)
+        check(f'FourierOperator {tag}', yo, y.detach())
+        out.update({f'{tag}/x': x.detach().numpy(), f'{tag}/w': w.numpy(), f'{tag}/y': y.detach().numpy(),
+                    f'{tag}/wr': op.weight_real.detach().numpy(), f'{tag}/wi': op.weight_imag.detach().numpy(),
+                    f'{tag}/dx': x.grad.numpy(), f'{tag}/dwr': op.weight_real.grad.numpy(),
+                    f'{tag}/dwi': op.weight_imag.grad.numpy(), f'{tag}/modes': np.array(modes)})
+    save('fourier_operator', **out)
+
+
+def case_hnoseg(transform_type='Hartley', name='hnoseg_small'):
+    """NeuralOperatorSeg(transform_type='Hartley') = HNOSeg / ('Fourier') = FNOSeg: small model,
+    forward + Dice gradients."""
     torch.manual_seed(21)
     cfg = dict(in_channels=2, out_channels=3, filters=8, num_transform_blocks=3, num_modes=(2, 3, 3),
-               transform_type='Hartley')
+               transform_type=transform_type)
     model = ref.NeuralOperatorSeg(**cfg)
     torch.manual_seed(22)
     x = torch.randn(2, 2, 18, 16, 13)
@@ -191,7 +213,7 @@ def case_hnoseg():
         check(f'HNOSeg DiceLoss grad {k}', o_grads[k], grads[k], 2e-4)
     out['DiceLoss/loss'] = loss.detach().numpy()
     out.update({f'DiceLoss/grad/{k}': v.numpy() for k, v in grads.items()})
-    save('hnoseg_small', **out)
+    save(name, **out)
 
 
 def case_losses():
@@ -250,6 +272,8 @@ if __name__ == '__main__':
     case_losses()
     case_model()
     case_hnoseg()
+    case_fourier_operator()
+    case_hnoseg('Fourier', 'fnoseg_small')
     if args.full:
         case_full()
     print('all oracle-vs-reference checks passed')

@@ -156,8 +156,6 @@ def test_hnoseg_against_reference_fixture(cuda, golden_dir):
     for k, p in model.named_parameters():
         ref = g[f'DiceLoss/grad/{k}']
         assert rel(p.grad, ref) < 2e-4, (k, rel(p.grad, ref))
-    with pytest.raises(NotImplementedError):
-        nets.NeuralOperatorSeg(2, 3, 8, 1, (2, 3, 3), 'Fourier', device=cuda)
 
 
 def test_hnoseg_block_baseline_grid_against_oracle(cuda):
@@ -181,3 +179,68 @@ def test_hnoseg_block_baseline_grid_against_oracle(cuda):
     assert rel(xc.grad, xr.grad) < 2e-5
     for k, p in blk.named_parameters():
         assert rel(p.grad, params['l.' + k].grad) < 1e-4, k
+
+
+def test_fourier_operator_against_reference_fixture(cuda, golden_dir):
+    """FourierOperator (rfftn -> corner mix with a complex weight -> irfftn in the reference) evaluated as truncated
+    Hartley contractions on the symmetric mode set: outputs and gradients recorded from the real reference, including
+    the clamp path (modes > half the grid) on an even grid."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'fourier_operator.npz')))
+    for tag in ('a', 'b'):
+        modes = tuple(int(v) for v in g[f'{tag}/modes'])
+        op = nets.FourierOperator(8, 8, modes, device=cuda)
+        with torch.no_grad():
+            op.weight_real.copy_(torch.from_numpy(g[f'{tag}/wr']))
+            op.weight_imag.copy_(torch.from_numpy(g[f'{tag}/wi']))
+        x = torch.from_numpy(g[f'{tag}/x']).to(cuda).requires_grad_(True)
+        y = op(x)
+        assert rel(y, g[f'{tag}/y']) < 1e-5, (tag, rel(y, g[f'{tag}/y']))
+        (y * torch.from_numpy(g[f'{tag}/w']).to(cuda)).sum().backward()
+        assert rel(x.grad, g[f'{tag}/dx']) < 1e-5
+        assert rel(op.weight_real.grad, g[f'{tag}/dwr']) < 1e-5
+        assert rel(op.weight_imag.grad, g[f'{tag}/dwi']) < 1e-5
+
+
+def test_fnoseg_against_reference_fixture(cuda, golden_dir):
+    """NeuralOperatorSeg(transform_type='Fourier') = FNOSeg ("FNOSeg3D" of BASELINE.json config 3) against outputs and
+    Dice gradients recorded from the real reference."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'fnoseg_small.npz')))
+    model = nets.NeuralOperatorSeg(2, 3, 8, 3, (2, 3, 3), 'Fourier', device=cuda)
+    sd = _sd(g, 'sd/')
+    assert set(sd) == set(model.state_dict())
+    model.load_state_dict(sd)
+    x = torch.from_numpy(g['x']).to(cuda)
+    labels = torch.from_numpy(g['labels'].astype(np.int64))
+    probs = model(x)
+    assert rel(probs, g['probs']) < 1e-5
+    loss = nets.custom_losses.DiceLoss()(probs, orc.to_categorical(labels, 3).to(cuda))
+    loss.backward()
+    assert abs(float(loss) - float(g['DiceLoss/loss'])) < 2e-6
+    for k, p in model.named_parameters():
+        ref = g[f'DiceLoss/grad/{k}']
+        assert rel(p.grad, ref) < 2e-4, (k, rel(p.grad, ref))
+
+
+def test_fourier_layer_baseline_grid_against_oracle(cuda):
+    """BASELINE config 3: the Fourier spectral layer forward / backward on a BraTS-shaped low-resolution grid
+    (24 channels, 121 x 121 x 78, modes (10, 14, 14)) against the torch.fft oracle."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    torch.manual_seed(3)
+    op = nets.FourierOperator(24, 24, (10, 14, 14), device=cuda)
+    torch.nn.init.normal_(op.weight_real, std=0.2)
+    torch.nn.init.normal_(op.weight_imag, std=0.2)
+    x = torch.randn(1, 24, 121, 121, 78, generator=torch.Generator().manual_seed(4))
+    xc = x.to(cuda).requires_grad_(True)
+    y = op(xc)
+    w = torch.randn(y.shape, generator=torch.Generator().manual_seed(5))
+    (y * w.to(cuda)).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    wr = op.weight_real.detach().cpu().clone().requires_grad_(True)
+    wi = op.weight_imag.detach().cpu().clone().requires_grad_(True)
+    yr = orc.fourier_operator_with_transform(xr, wr, wi, (10, 14, 14))
+    (yr * w).sum().backward()
+    assert rel(y, yr) < 1e-5
+    assert rel(xc.grad, xr.grad) < 1e-5
+    assert rel(op.weight_real.grad, wr.grad) < 1e-4 and rel(op.weight_imag.grad, wi.grad) < 1e-4

@@ -106,3 +106,17 @@ def test_hnoseg_fixture(golden_dir):
     _close(loss, g['DiceLoss/loss'], 1e-6)
     for k, v in grads.items():
         _close(v, g[f'DiceLoss/grad/{k}'], 2e-4)
+
+
+def test_fourier_fixtures(golden_dir):
+    """FourierOperator and NeuralOperatorSeg(transform_type='Fourier') = FNOSeg, recorded from the real reference."""
+    g = _load(golden_dir, 'fourier_operator')
+    for tag in ('a', 'b'):
+        y = orc.fourier_operator_with_transform(torch.from_numpy(g[f'{tag}/x']), torch.from_numpy(g[f'{tag}/wr']),
+                                                torch.from_numpy(g[f'{tag}/wi']), tuple(int(v) for v in g[f'{tag}/modes']))
+        _close(y, g[f'{tag}/y'])
+    g = _load(golden_dir, 'fnoseg_small')
+    sd = _sd(g, 'sd/')
+    probs, logits = orc.hnoseg_forward(sd, torch.from_numpy(g['x']), 3, (2, 3, 3), return_logits=True)
+    _close(probs, g['probs'])
+    _close(logits, g['logits'])
