@@ -893,7 +893,8 @@ int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st) {
   HNO_TC_CASE(16, 128, 3, 2)  // H-axis synthesis (29 rows = two chunks)
   HNO_TC_CASE(32, 128, 2, 1)
   HNO_TC_CASE(8, 128, 3, 2)
-  HNO_TC_CASE(24, 256, 3, 2)
+  HNO_TC_CASE(24, 256, 3, 2)  // synthesis onto axes of 129..256 samples (2x super-resolution grids)
+  HNO_TC_CASE(16, 256, 3, 2)
   HNO_TC_CASE(32, 256, 3, 2)
   HNO_TC_CASE(8, 256, 3, 2)
 #undef HNO_TC_CASE

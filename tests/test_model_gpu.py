@@ -244,3 +244,27 @@ def test_fourier_layer_baseline_grid_against_oracle(cuda):
     assert rel(y, yr) < 1e-5
     assert rel(xc.grad, xr.grad) < 1e-5
     assert rel(op.weight_real.grad, wr.grad) < 1e-4 and rel(op.weight_imag.grad, wi.grad) < 1e-4
+
+
+def test_superres_grid_transform_and_inference(cuda):
+    """BASELINE config 4: zero-shot super-resolution = the same weights on a 2x grid (4 x 480 x 480 x 310 -> internal grid
+    241 x 241 x 156, modes unchanged).  The truncated transform pair is checked against the FFT oracle at that grid and
+    the whole HNOSeg-XS forward is run at full size (finite, normalised probabilities, same model as at 1x)."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    from multimodal_3d_image_segmentation_b200.nets.hnosegxs import PadInverse, TransformCrop
+    shape, modes = (241, 241, 156), (10, 14, 14)
+    x = torch.randn(1, 2, *shape, generator=torch.Generator().manual_seed(8))
+    z = TransformCrop(modes, 5)(x.to(cuda))
+    z_ref = orc.transform_crop(x, modes)
+    assert rel(z, z_ref) < 1e-5
+    y = PadInverse(5)(z, shape)
+    assert rel(y, orc.pad_inverse(z_ref, shape)) < 1e-5
+    del y, z
+    model = nets.HNOSegXS(4, 4, 24, [3] * 8, modes, device=cuda)
+    model.load_state_dict(orc.init_state_dict(4, 4, 24, [3] * 8, modes, seed=0))
+    xin = torch.randn(1, 4, 480, 480, 310, generator=torch.Generator().manual_seed(9)).to(cuda)
+    with torch.no_grad():
+        probs = model(xin)
+    assert probs.shape == (1, 4, 480, 480, 310)
+    assert bool(torch.isfinite(probs).all())
+    assert float((probs.sum(1) - 1).abs().max()) < 1e-5
