@@ -190,7 +190,11 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) 
     const int wg = tid >> 6, wl = tid & 63;
     const int ot = wl >> 3, it8 = wl & 7;
     float2 accW[2][3][3];
-    float accB[3] = {0.f, 0.f, 0.f};
+    // bias gradient: every thread sums d(pre) of ITS voxel over the tiles (12 packed adds per tile); folding it into
+    // the weight-gradient loop cost 9 divergent FADDs per 18 FFMA2 on every warp (7 % of the kernel's instructions)
+    float2 accB2[C / 2];
+#pragma unroll
+    for (int o = 0; o < C / 2; ++o) accB2[o] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) 
 #pragma unroll
         for (int r = 0; r < 3; ++r) accW[h][q][r] = make_float2(0.f, 0.f);
 
-    auto wgrad = [&](const float* sx, float2 (&acc)[3][3], bool with_bias) {
+    auto wgrad = [&](const float* sx, float2 (&acc)[3][3]) {
       const float* dp0 = sdp + (ot * 3) * kBtPitch + wg * 64;
       const float* x0 = sx + (it8 * 3) * kBtPitch + wg * 64;
 #pragma unroll 2
@@ -217,10 +221,6 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) 
             a = ffma2(make_float2(d[q].z, d[q].w), make_float2(x[r].z, x[r].w), a);
             acc[q][r] = a;
           }
-        if (with_bias) {
-#pragma unroll
-          for (int q = 0; q < 3; ++q) accB[q] += (d[q].x + d[q].y) + (d[q].z + d[q].w);
-        }
       }
     };
 
@@ -250,11 +250,16 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) 
         const float* pdy = ring + s_dy * kBtStageFloats + tid;
         const float* py = ring + s_y * kBtStageFloats + tid;
 #pragma unroll
-        for (int o = 0; o < C; ++o) {
-          const float d = live ? pdy[o * kBtPitch] * selu_grad_from_out(py[o * kBtPitch]) : 0.f;
-          hi[o] = __float_as_uint(d);
-          lo[o] = __float_as_uint(tf32_lo(d));
-          sdp[o * kBtPitch + tid] = d;
+        for (int o = 0; o < C; o += 2) {
+          const float d0 = live ? pdy[o * kBtPitch] * selu_grad_from_out(py[o * kBtPitch]) : 0.f;
+          const float d1 = live ? pdy[(o + 1) * kBtPitch] * selu_grad_from_out(py[(o + 1) * kBtPitch]) : 0.f;
+          hi[o] = __float_as_uint(d0);
+          lo[o] = __float_as_uint(tf32_lo(d0));
+          hi[o + 1] = __float_as_uint(d1);
+          lo[o + 1] = __float_as_uint(tf32_lo(d1));
+          sdp[o * kBtPitch + tid] = d0;
+          sdp[(o + 1) * kBtPitch + tid] = d1;
+          accB2[o / 2] = __fadd2_rn(accB2[o / 2], make_float2(d0, d1));
         }
       }
       // previous tile: its MMAs retired before its epilogue ran (the epilogue waited for them), so the A columns are free
@@ -272,13 +277,13 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) 
       const int s_in1 = s;
       mbar_wait(&bar_full[s], ph);
       next_stage();
-      wgrad(ring + s_in1 * kBtStageFloats, accW[0], it8 == 0);
+      wgrad(ring + s_in1 * kBtStageFloats, accW[0]);
       int s_in2 = 0;
       if (CI2 > 0) {
         s_in2 = s;
         mbar_wait(&bar_full[s], ph);
         next_stage();
-        wgrad(ring + s_in2 * kBtStageFloats, accW[1], false);
+        wgrad(ring + s_in2 * kBtStageFloats, accW[1]);
       }
       // ---- epilogue: input gradients from the accumulator, one lane = one voxel.
       // Accumulating destinations (U-Net skip gradients): the old values of a block of 8 rows are requested two blocks
@@ -339,13 +344,22 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) 
 #pragma unroll
           for (int r = 0; r < 3; ++r)
             scratch[wg * (C * CI) + (ot * 3 + q) * CI + h * C + it8 * 3 + r] = accW[h][q][r].x + accW[h][q][r].y;
-      if (it8 == 0) {
+      {  // bias partials: warp sums, one row of C per worker warp
+        const int lane = tid & 31;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) scratch[2 * C * CI + wg * C + ot * 3 + q] = accB[q];
+        for (int o = 0; o < C / 2; ++o) {
+          const float bx = warp_sum(accB2[o].x), by = warp_sum(accB2[o].y);
+          if (lane == 0) {
+            scratch[2 * C * CI + warp * C + 2 * o] = bx;
+            scratch[2 * C * CI + warp * C + 2 * o + 1] = by;
+          }
+        }
       }
       bt_worker_sync();
       for (int idx = tid; idx < C * CI; idx += kBtWorkers) prow[idx] = scratch[idx] + scratch[C * CI + idx];
-      for (int o = tid; o < C; o += kBtWorkers) prow[C * CI + o] = scratch[2 * C * CI + o] + scratch[2 * C * CI + C + o];
+      for (int o = tid; o < C; o += kBtWorkers)
+        prow[C * CI + o] = (scratch[2 * C * CI + o] + scratch[2 * C * CI + C + o]) +
+                           (scratch[2 * C * CI + 2 * C + o] + scratch[2 * C * CI + 3 * C + o]);
     }
   }
   tc_fence_before_sync();

@@ -40,7 +40,10 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ sdp, const 
 #pragma unroll
     for (int q = 0; q < T::TO; ++q) d[q] = *reinterpret_cast<const float4*>(sdp + (ot * T::TO + q) * TVS + v);
 #pragma unroll
-    for (int r = 0; r < T::TI; ++r) x[r] = *reinterpret_cast<const float4*>(sx + (it * T::TI + r) * TVS + v);
+    // input rows are dealt to the N_IT column threads round-robin (row r * N_IT + it): the 8 distinct rows a warp reads
+    // per LDS.128 are then TVS floats apart (TVS % 32 == 4 -> 8 x 4 distinct banks) instead of TI * TVS apart
+    // (4-way conflicts: 55 M excess wavefronts in the stem weight gradient)
+    for (int r = 0; r < T::TI; ++r) x[r] = *reinterpret_cast<const float4*>(sx + (r * T::N_IT + it) * TVS + v);
 #pragma unroll
     for (int q = 0; q < T::TO; ++q)
 #pragma unroll
@@ -74,7 +77,7 @@ __device__ __forceinline__ void wgrad_flush(float* __restrict__ scratch /* >= NG
     for (int q = 0; q < T::TO; ++q)
 #pragma unroll
       for (int r = 0; r < T::TI; ++r)
-        scratch[g * (CO * CI) + (ot * T::TO + q) * CI + it * T::TI + r] = accW[q][r].x + accW[q][r].y;
+        scratch[g * (CO * CI) + (ot * T::TO + q) * CI + r * T::N_IT + it] = accW[q][r].x + accW[q][r].y;
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < CO * CI; idx += kPwThreads) {

@@ -23,7 +23,11 @@ acc = [rnd(batch, F, D, P) for _ in range(2)]
 z = rnd(batch, F, *plan.modes_shape)
 w48, w24, b24 = rnd(F, 2 * F) * 0.1, rnd(F, F) * 0.1, rnd(F) * 0.01
 hw = (P, H * W)
+xin = rnd(batch, 4, *VOLUME)
+win = rnd(F, 4, 2, 2, 2) * 0.1
 table = {
+    'stemf': lambda: ops.stem_forward(xin, win, b24, P),
+    'stemb': lambda: ops.stem_backward(a[0], xin, F, P),
     'pw48f': lambda: ops.pwconv_forward(a[0], a[1], w48, b24, 1, False),
     'pw24f': lambda: ops.pwconv_forward(a[0], None, w24, b24, 1, False),
     'dhtf': lambda: ops.dht3_forward(a[0], plan, 1.0),
