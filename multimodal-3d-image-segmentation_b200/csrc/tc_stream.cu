@@ -49,7 +49,17 @@ struct TcShape {
   static constexpr bool kTmaOut = NPAD >= 128;
   static constexpr int kStageBufs = kTmaOut ? 2 : 0;        // staging buffers of 32 rows x 128 voxels
   static constexpr int kStageBytes = 32 * 128 * 4;
-  static constexpr int kThreads = kWorkers + 64 + (kTmaOut ? 32 : 0);
+  // Narrow outputs (pointwise convolutions, analysis stages): the operand split of tile t+1 and the epilogue of tile t
+  // run on DIFFERENT warps (4 split warps + 4 epilogue warps) instead of one after the other on the same four -- the
+  // worker warps were the critical path (cycle counters: split 2240 + epilogue 2837 of 6375 cycles per tile of the
+  // 48 -> 24 convolution).  HNO_TC_SPLIT_EPI=0 at compile time restores the single worker group.
+#ifndef HNO_TC_SPLIT_EPI
+#define HNO_TC_SPLIT_EPI 1
+#endif
+  static constexpr bool kSplitEpi = HNO_TC_SPLIT_EPI && NPAD <= 32;
+  static constexpr int kEpiWarps = kSplitEpi ? 4 : 0;
+  static constexpr int kHelper0 = kWorkerWarps + kEpiWarps;  // first helper warp: producer, then MMA issuer, then store
+  static constexpr int kThreads = kWorkers + 32 * kEpiWarps + 64 + (kTmaOut ? 32 : 0);
 };
 
 struct TcDev {
@@ -99,14 +109,16 @@ __device__ __forceinline__ float rn_tf32_bits(float x) {
 }
 
 template <int KC, int NPAD, int NST, int kNLo>
-__global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NPAD <= 128 ? 2 : 1))) k_tc_stream(const __grid_constant__ CUtensorMap tm0,
+__global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
+                                  (NPAD <= 32 ? (TcShape<NPAD>::kSplitEpi ? 2 : 3) : (NPAD <= 128 ? 2 : 1))) k_tc_stream(const __grid_constant__ CUtensorMap tm0,
                                                            const __grid_constant__ CUtensorMap tm1,
                                                            const __grid_constant__ CUtensorMap tmo, const TcDev p) {
   constexpr int kChunkBytes = KC * 512;
   constexpr int NKG = KC / 8;
   constexpr int kTcWorkers = TcShape<NPAD>::kWorkers, kTcThreads = TcShape<NPAD>::kThreads;
-  constexpr int kWW = TcShape<NPAD>::kWorkerWarps;  // producer = warp kWW, MMA issuer = warp kWW + 1
-  constexpr int kHalves = kWW / 4;                   // worker warps per TMEM lane quarter
+  constexpr int kWW = TcShape<NPAD>::kHelper0;      // producer = warp kWW, MMA issuer = warp kWW + 1
+  constexpr int kHalves = TcShape<NPAD>::kWorkerWarps / 4;  // worker warps per TMEM lane quarter
+  constexpr bool kSplitEpi = TcShape<NPAD>::kSplitEpi;
   // kFuseN: A_hi * [B_hi | B_lo] as ONE MMA of N = 2 * NPAD (the two halves are added in the epilogue) plus A_lo * B_hi
   // into the first half: the streamed operand is read from shared memory twice per k-step instead of three times
   // (shared-memory bandwidth, not the tensor pipe, is what bounds this kernel once HBM is fed properly).
@@ -126,7 +138,12 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* raw = smem;                              // [NST][kChunkBytes]
   uint8_t* lob = raw + NST * kChunkBytes;           // [kNLo][kChunkBytes]
-  float* bhi = reinterpret_cast<float*>(lob + kNLo * kChunkBytes);
+  // loader 2 ("plain TMA"): the ring holds unswizzled [k][128 m] boxes (512-byte rows: the TMA unit moves those at
+  // HBM speed, 128-byte-row swizzled boxes cap at 4.2 TB/s and a cp.async warp at ~3 TB/s with 2 CTAs per SM) and the
+  // split step writes BOTH operand images (hi, lo) in the swizzled layout the MMA reads.  hib: [kNLo][kChunkBytes],
+  // like every operand buffer a multiple of 512 bytes from the 1024-byte aligned base (the swizzle uses address bits).
+  uint8_t* hib = lob + kNLo * kChunkBytes;
+  float* bhi = reinterpret_cast<float*>(hib + (p.loader == 2 ? kNLo * kChunkBytes : 0));
   const int ktot = p.nchunk * KC;
   float* blo = bhi + NPAD * ktot;
   float* sbias = blo + NPAD * ktot;
@@ -134,6 +151,7 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
   // staging buffers of the bulk-store epilogue: the B image and the bias occupy a multiple of 128 bytes, so these stay
   // 128-byte aligned
   float* stage = sbias + NPAD;
+  __shared__ __align__(8) uint64_t bar_read[NST];   // loader 2: ring stage read by the split warps (128 arrivals)
   __shared__ __align__(8) uint64_t bar_stfull[2];   // staging buffer written by the workers   (128 arrivals)
   __shared__ __align__(8) uint64_t bar_stfree[2];   // bulk store has read the staging buffer (1 arrival)
   __shared__ __align__(8) uint64_t bar_full[NST];   // TMA bytes landed                     (1 arrival + tx)
@@ -172,9 +190,10 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NST; ++s) {
-      mbar_init(&bar_full[s], p.loader == 1 ? 1 : 32);
+      mbar_init(&bar_full[s], p.loader != 0 ? 1 : 32);
       mbar_init(&bar_split[s], kTcWorkers);
       mbar_init(&bar_done[s], 1);
+      mbar_init(&bar_read[s], kTcWorkers);
     }
     mbar_init(&bar_accfree[0], kTcWorkers);
     mbar_init(&bar_accfree[1], kTcWorkers);
@@ -312,10 +331,15 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
         locate(ld);
         locate(pf);
       }
+      const bool plain = p.loader == 2;
       for (int i = 0; i < kPrefetch && pf.ti < my_tiles; ++i) {
         const CUtensorMap* tm = pf.src == 0 ? &tm0 : &tm1;
+        if (plain) {
+          tma_prefetch_l2_3d(tm, pf.m0, pf.row0, pf.g);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_prefetch_l2_3d(tm, pf.m0 + 32 * j, pf.row0, pf.g);
+          for (int j = 0; j < 4; ++j) tma_prefetch_l2_3d(tm, pf.m0 + 32 * j, pf.row0, pf.g);
+        }
         advance(pf);
       }
       int it = 0, s = 0;
@@ -323,20 +347,28 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
       while (ld.ti < my_tiles) {
         if (pf.ti < my_tiles) {
           const CUtensorMap* tm = pf.src == 0 ? &tm0 : &tm1;
+          if (plain) {
+            tma_prefetch_l2_3d(tm, pf.m0, pf.row0, pf.g);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_prefetch_l2_3d(tm, pf.m0 + 32 * j, pf.row0, pf.g);
+            for (int j = 0; j < 4; ++j) tma_prefetch_l2_3d(tm, pf.m0 + 32 * j, pf.row0, pf.g);
+          }
           advance(pf);
         }
-        if (it >= NST) {  // previous use of this stage fully consumed
+        if (it >= NST) {  // previous use of this stage fully consumed (loader 2: read by the split warps)
           const long long t0 = p.prof ? clock64() : 0;
-          mbar_wait(&bar_done[s], ph ^ 1);
+          mbar_wait(plain ? &bar_read[s] : &bar_done[s], ph ^ 1);
           if (p.prof) prof_acc[0] += clock64() - t0;
         }
         uint8_t* dst = raw + s * kChunkBytes;
         mbar_expect_tx(&bar_full[s], kChunkBytes);
         const CUtensorMap* tm = ld.src == 0 ? &tm0 : &tm1;
+        if (plain) {
+          tma_load_3d(dst, tm, ld.m0, ld.row0, ld.g, &bar_full[s]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * (KC * 128), tm, ld.m0 + 32 * j, ld.row0, ld.g, &bar_full[s]);
+          for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * (KC * 128), tm, ld.m0 + 32 * j, ld.row0, ld.g, &bar_full[s]);
+        }
         advance(ld);
         ++it;
         if (++s == NST) {
@@ -397,7 +429,7 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
           mbar_wait(&bar_split[s], ph);
           if (p.prof) w_split += clock64() - t0;
           tc_fence_after_sync();
-          const uint32_t a_hi = smem_u32(raw + s * kChunkBytes);
+          const uint32_t a_hi = p.loader == 2 ? smem_u32(hib + (it % kNLo) * kChunkBytes) : smem_u32(raw + s * kChunkBytes);
           const uint32_t a_lo = smem_u32(lob + (it % kNLo) * kChunkBytes);
 #pragma unroll
           for (int g = 0; g < NKG; ++g) {
@@ -441,7 +473,7 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
       const long long te0 = p.prof ? clock64() : 0;
       const uint32_t tile = blockIdx.x + (uint32_t)ti * gridDim.x;
       const int g = tile / (uint32_t)p.tiles_per_slab;
-      const int quarter = warp & 3, half = warp >> 2;  // TMEM lane quarter / which 32-column blocks this warp takes
+      const int quarter = warp & 3, half = kHalves > 1 ? (warp >> 2) : 0;  // TMEM lane quarter / which 32-column blocks this warp takes
       const int m = (tile - (uint32_t)g * p.tiles_per_slab) * 128 + quarter * 32 + lane;
       const bool live = m < p.valid_m;
       const bool in_range = p.out_rw > 0 ? (m < p.mext && live) : m < p.mext;  // re-mapped: dead columns have no address
@@ -630,9 +662,16 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
     };
     int it = 0, s = 0;
     uint32_t ph = 0;
+    const bool epi_warp = kSplitEpi && warp >= TcShape<NPAD>::kWorkerWarps;  // epilogue-only warpgroup
     // one extra pass of the tile loop runs the epilogue of the last tile: ONE inlined copy of the (large) epilogue
     for (int ti = 0; ti <= my_tiles; ++ti) {
       for (int c = 0; c < nchunk; ++c) {
+        if (kSplitEpi) {
+          if (epi_warp) {
+            if (c == 0 && ti < my_tiles) epilogue(ti);
+            continue;
+          }
+        }
         if (ti < my_tiles) {
         long long t0 = p.prof ? clock64() : 0;
         if (it >= kNLo) {  // the lo buffer is free once the MMAs of item it - kNLo have retired
@@ -650,7 +689,24 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
           w_full += t1 - t0;
           t0 = t1;
         }
-        {
+        if (p.loader == 2) {
+          // plain ring [k][128 m] -> hi and lo operand images in the 128B_BASE32B swizzle: 32-float block j of row r
+          // lives at j * KC * 128 + r * 128, its 32-byte chunk c at chunk c ^ (r & 3).  This thread's float4 sits at
+          // column c4 = tid & 31 of rows (tid >> 5) + 4 i, so (r & 3) and with it the whole intra-row offset are fixed.
+          const float4* r4 = reinterpret_cast<const float4*>(raw + s * kChunkBytes);
+          const int c4 = tid & 31, r0 = tid >> 5;
+          const int q = c4 & 7;
+          const uint32_t off0 = (uint32_t)(c4 >> 3) * (KC * 128) + r0 * 128 + ((((q >> 1) ^ r0) & 3) << 5) + ((q & 1) << 4);
+          uint8_t* hb = hib + (it % kNLo) * kChunkBytes + off0;
+          uint8_t* lb = lob + (it % kNLo) * kChunkBytes + off0;
+#pragma unroll
+          for (int i = 0; i < kChunkBytes / 16 / kTcWorkers; ++i) {
+            const float4 x = r4[tid + i * kTcWorkers];
+            *reinterpret_cast<float4*>(hb + i * 512) = x;
+            *reinterpret_cast<float4*>(lb + i * 512) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+          }
+          mbar_arrive(&bar_read[s]);  // the ring stage may be refilled
+        } else {
           // hi operand = the fp32 word as it is (the tensor core ignores the 13 low mantissa bits);
           // lo operand = the exact remainder x - trunc_tf32(x)
           const float4* r4 = reinterpret_cast<const float4*>(raw + s * kChunkBytes);
@@ -671,7 +727,7 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads, (NPAD <= 32 ? 3 : (NP
           ph ^= 1;
         }
         }
-        if (c == nchunk - 1 && ti > 0) epilogue(ti - 1);
+        if (!kSplitEpi && c == nchunk - 1 && ti > 0) epilogue(ti - 1);
       }
     }
     if (p.prof && tid == 0) {
@@ -760,13 +816,14 @@ bool tc_stream_eligible(const TcStreamArgs& a) {
 
 template <int KC, int NPAD, int NST, int kNLo>
 static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
+  const int loader_sel = a.loader;  // resolved by tc_stream_launch
   CUtensorMap tm[2];
   for (int i = 0; i < 2; ++i) {
     const int j = i < a.nsrc ? i : 0;
     const uint64_t dims[3] = {(uint64_t)a.mext, (uint64_t)a.rows[j], (uint64_t)a.G};
     const uint64_t strides[2] = {(uint64_t)a.lda[j] * 4, (uint64_t)a.gsa[j] * 4};
-    const uint32_t box[3] = {32, (uint32_t)KC, 1};
-    if (int rc = encode_tensor_map(&tm[i], a.a[j], 3, dims, strides, box, 2)) return rc;
+    const uint32_t box[3] = {loader_sel == 2 ? 128u : 32u, (uint32_t)KC, 1};
+    if (int rc = encode_tensor_map(&tm[i], a.a[j], 3, dims, strides, box, loader_sel == 2 ? 0 : 2)) return rc;
   }
   TcDev p;
   p.tma_out = 0;
@@ -808,20 +865,16 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
     p.gsa[i] = a.gsa[j];
     p.rows[i] = a.rows[j];
   }
-  {
-    static const int loader = getenv("HNO_TC_LOADER") ? atoi(getenv("HNO_TC_LOADER")) : -1;
-    p.loader = loader >= 0 ? loader : a.loader;
-  }
+  p.loader = loader_sel;
   p.out_rw = a.out_rw;
   p.out_rp = a.out_rp;
   p.in_rw = a.in_rw;
   p.in_rp = a.in_rp;
-  if (p.in_rw > 0) p.loader = 0;  // only the cp.async loader can gather
   {
     static const int pf_kb = getenv("HNO_TC_PREFETCH_KB") ? atoi(getenv("HNO_TC_PREFETCH_KB")) : 96;
     p.prefetch_items = pf_kb * 1024 / (KC * 512);
   }
-  const size_t smem = TcSmem<KC, NPAD, NST, kNLo>::bytes(p.nchunk);
+  const size_t smem = TcSmem<KC, NPAD, NST, kNLo>::bytes(p.nchunk) + (p.loader == 2 ? (size_t)kNLo * KC * 512 : 0);
   auto kern = k_tc_stream<KC, NPAD, NST, kNLo>;
   HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -830,6 +883,7 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   // 228 KB of shared memory per SM (1 KB reserved per CTA + 1 KB static), <= 112 registers x 192 threads, 512 TMEM columns.
   int per_sm = (int)(233472 / (smem + 2 * 1024));
   if (per_sm > 3) per_sm = 3;
+  if (TcShape<NPAD>::kSplitEpi && per_sm > 2) per_sm = 2;  // 320 threads per CTA, ~100 registers each
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 512 / (2 * NPAD)) per_sm = 512 / (2 * NPAD);
   if (per_sm > 4) per_sm = 4;
@@ -864,8 +918,14 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
   return 0;
 }
 
-int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st) {
-  HNO_CHECK(tc_stream_eligible(a), "tc_stream: configuration is not eligible for the tensor-core path");
+int tc_stream_launch(const TcStreamArgs& a_in, cudaStream_t st) {
+  HNO_CHECK(tc_stream_eligible(a_in), "tc_stream: configuration is not eligible for the tensor-core path");
+  TcStreamArgs a = a_in;
+  {
+    static const int loader = getenv("HNO_TC_LOADER") ? atoi(getenv("HNO_TC_LOADER")) : -1;
+    if (loader >= 0) a.loader = loader;
+    if (a.in_rw > 0) a.loader = 0;  // only the cp.async loader can gather
+  }
   {  // HNO_TC_KERNEL=regs selects the experimental ring -> registers -> tensor-memory data path (tc_regs.cu); measured
      // on B200 it ties with the shared-memory-operand ring below (pw48f 0.171-0.182 ms vs 0.169 ms), see DESIGN.md
     static const bool regs = getenv("HNO_TC_KERNEL") && !strcmp(getenv("HNO_TC_KERNEL"), "regs");
@@ -877,17 +937,20 @@ int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st) {
   if (a.kc == KC_ && npad == NP_ && variant == VAR_) return launch_t<KC_, NP_, NST_, NLO_>(a, st);
   HNO_TC_CASE(24, 32, 4, 3, 1)
   HNO_TC_CASE(24, 32, 4, 4, 2)
-  HNO_TC_CASE(24, 32, 3, 3, 3)
+  HNO_TC_CASE(24, 32, 3, 2, 3)
   HNO_TC_CASE(16, 32, 5, 4, 1)
   HNO_TC_CASE(16, 32, 6, 4, 2)
-  HNO_TC_CASE(16, 32, 4, 3, 3)
+  HNO_TC_CASE(16, 32, 3, 2, 3)
   HNO_TC_CASE(16, 32, 5, 2, 4)
 #undef HNO_TC_CASE
+  // loader 2 keeps a third set of chunk buffers (the hi image): its own stage counts so that 2 CTAs still fit an SM
+  if (a.loader == 2 && a.kc == 24 && npad == 32 && variant == 0) return launch_t<24, 32, 4, 2>(a, st);
+  if (a.loader == 2 && a.kc == 16 && npad == 32 && variant == 0) return launch_t<16, 32, 3, 2>(a, st);
 #define HNO_TC_CASE(KC_, NP_, NST_, NLO_)                                  \
   if (a.kc == KC_ && npad == NP_) return launch_t<KC_, NP_, NST_, NLO_>(a, st);
-  HNO_TC_CASE(24, 32, 3, 2)   // pointwise conv 24(+24) -> <= 32: 3 CTAs / SM
+  HNO_TC_CASE(24, 32, 5, 3)   // pointwise conv 24(+24) -> <= 32: 2 CTAs / SM of 4 split + 4 epilogue warps
   HNO_TC_CASE(32, 32, 3, 2)
-  HNO_TC_CASE(16, 32, 3, 2)   // D / H-axis analysis: 8 KB chunks, 3 CTAs / SM (TMA loader + L2 prefetch cursor)
+  HNO_TC_CASE(16, 32, 6, 3)   // D / H-axis analysis: 8 KB chunks (TMA loader + L2 prefetch cursor)
   HNO_TC_CASE(8, 32, 4, 2)
   HNO_TC_CASE(24, 128, 2, 2)  // D-axis synthesis (one chunk per tile)
   HNO_TC_CASE(16, 128, 3, 2)  // H-axis synthesis (29 rows = two chunks)
