@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(kTailThreads) k_dht_tail_adj(const float* __re
                                                               const float* __restrict__ pf,
                                                               const int* __restrict__ pi, const TailGeom g,
                                                               float scale) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the H-synthesis kernel may start its prologue
   extern __shared__ float4 smem4[];
   float* s = reinterpret_cast<float*>(smem4);
   float* fw = s;                         // [Jw][Wp]  (columns >= W are zero)

@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
                                                          int nw, float* __restrict__ dweight,
                                                          float* __restrict__ dbias, int accumulate) {
   // one warp per output element
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a streamed tensor-core kernel usually follows
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;

@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
   constexpr uint32_t kIdesc2 = make_idesc_tf32(128, NB, 1, 0);
   constexpr uint32_t kTmemCols = 2 * NB < 32 ? 32 : 2 * NB;  // two accumulator buffers
   static_assert(KC % 8 == 0 && NPAD % 16 == 0 && NPAD <= 256, "bad tile configuration");
+  // Programmatic dependent launch: let the NEXT kernel on the stream begin (its prologue overlaps this kernel's tail) ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align on the shared-window address so that the compiler keeps the shared address space (LDS / STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -211,6 +213,9 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  // ... and wait here, after the prologue (B image from constants, barriers, TMEM), for the PREVIOUS kernel's results:
+  // nothing above reads or writes data another kernel of the step produces.  A no-op without the launch attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int nchunk = p.nchunk;
@@ -898,7 +903,22 @@ static int launch_t(const TcStreamArgs& a, cudaStream_t st) {
     cudaMemsetAsync(prof_buf, 0, 4096 * 8 * sizeof(long long), st);
     p.prof = prof_buf;
   }
-  kern<<<(int)grid, TcShape<NPAD>::kThreads, smem, st>>>(tm[0], tm[1], tmo, p);
+  static const bool pdl = !(getenv("HNO_TC_PDL") && atoi(getenv("HNO_TC_PDL")) == 0);
+  if (pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TcShape<NPAD>::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HNO_CUDA(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tmo, p));
+  } else {
+    kern<<<(int)grid, TcShape<NPAD>::kThreads, smem, st>>>(tm[0], tm[1], tmo, p);
+  }
   HNO_LAUNCH_CHECK();
   if (prof_on) {  // debug only: synchronous read-back of the per-CTA wait-cycle counters
     static long long host[4096 * 8];
