@@ -48,6 +48,13 @@ struct BtDev {
   int tiles_per_sample, total_tiles;
   int flags;
   int nst;
+  int tma;             // 1: the ring is filled by one bulk tensor copy per stage (box 132 x 24), 0: by the cp.async warp
+};
+
+// the four streamed tensors (dy, y, in1, in2) as [B][24][S] tensor maps with a 132-float-wide box: the 4 extra columns
+// reproduce the padded row pitch of the ring (bank spread of the weight-gradient reads) and are never used as data
+struct BtMaps {
+  CUtensorMap m[4];
 };
 
 __device__ __forceinline__ void bt_arrive(uint64_t* bar) {
@@ -86,7 +93,7 @@ __device__ __forceinline__ void bt_worker_sync() { asm volatile("bar.sync 1, 128
 
 // CI2 = 0: single input (24 -> 24);  CI2 = 24: virtual concat of two inputs (48 -> 24)
 template <int CI2, bool ACC>
-__global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) {
+__global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p, const __grid_constant__ BtMaps maps) {
   constexpr int C = kBtC;
   constexpr int CI = C + CI2;
   constexpr int NP = CI == 48 ? 48 : 32;       // MMA N of one half (multiple of 16)
@@ -122,7 +129,7 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) 
   }
   if (tid == 0) {
     for (int s = 0; s < kBtMaxStages; ++s) {
-      mbar_init(&bar_full[s], 32);
+      mbar_init(&bar_full[s], p.tma ? 1 : 32);
       mbar_init(&bar_empty[s], kBtWorkers);
     }
     mbar_init(&bar_ready, kBtWorkers);
@@ -158,6 +165,30 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p) 
     // =============================================================== loader (one warp): 512-byte rows -> padded stages
     int s = 0, it = 0;
     uint32_t ph = 0;
+    if (p.tma) {
+      // one elected thread, one bulk tensor copy per stage: 512-byte rows move at HBM speed through the TMA unit where
+      // the cp.async warp is limited to ~3 TB/s with two CTAs per SM (measured on the forward convolution)
+      if (lane == 0) {
+        for (int q = 0; q < NSRC; ++q) tma_prefetch_desc(&maps.m[q]);
+        for (int ti = 0; ti < my_tiles; ++ti) {
+          const long tile = blockIdx.x + (long)ti * gridDim.x;
+          const int b = (int)(tile / p.tiles_per_sample);
+          const int s0 = (int)((tile - (long)b * p.tiles_per_sample) * 128);
+#pragma unroll 1
+          for (int q = 0; q < NSRC; ++q) {
+            if (it >= NST) mbar_wait(&bar_empty[s], ph ^ 1);
+            mbar_expect_tx(&bar_full[s], kBtStageFloats * 4);
+            tma_load_3d(ring + s * kBtStageFloats, &maps.m[q], s0, 0, b, &bar_full[s]);
+            ++it;
+            if (++s == NST) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else
     for (int ti = 0; ti < my_tiles; ++ti) {
       const long tile = blockIdx.x + (long)ti * gridDim.x;
       const int b = (int)(tile / p.tiles_per_sample);
@@ -398,7 +429,21 @@ static int launch_bt(BtDev p, cudaStream_t st, int* grid_out) {
   long grid = (long)sm_count() * 2;  // two CTAs per SM (256 TMEM columns and ~100 KB of shared memory each)
   if (grid > p.total_tiles) grid = p.total_tiles;
   *grid_out = (int)grid;
-  kern<<<(int)grid, kBtThreads, smem, st>>>(p);
+  BtMaps maps;
+  {
+    static const bool tma_on = !(getenv("HNO_PWBWD_TMA") && atoi(getenv("HNO_PWBWD_TMA")) == 0);
+    p.tma = tma_on && p.S < (1L << 31) ? 1 : 0;
+    const float* src[4] = {p.dy, p.y, p.in1, CI2 > 0 ? p.in2 : p.in1};
+    const int B = p.total_tiles / p.tiles_per_sample;
+    for (int q = 0; q < 4; ++q) {
+      const uint64_t dims[3] = {(uint64_t)p.S, (uint64_t)kBtC, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)p.S * 4, (uint64_t)kBtC * p.S * 4};
+      const uint32_t box[3] = {(uint32_t)kBtPitch, (uint32_t)kBtC, 1};
+      if (p.tma)
+        if (int rc = encode_tensor_map(&maps.m[q], src[q], 3, dims, strides, box, 0)) return rc;
+    }
+  }
+  kern<<<(int)grid, kBtThreads, smem, st>>>(p, maps);
   HNO_LAUNCH_CHECK();
   return 0;
 }
