@@ -148,13 +148,14 @@ int hno_head_backward(const void* tables_host, const void* tables_dev, const flo
 
 /* ------------------------------------------------------------------------------------------
  * Losses on probabilities                     replaces nets/custom_losses.py:17-111
- *   kind 0: DiceLoss, 1: PCCLoss.  y_pred, y_true [B][C][N] fp32 (y_true one-hot floats).
+ *   kind 0: DiceLoss, 1: PCCLoss, 2: ExpDiceLoss (param = its exponent, :114-133; ignored otherwise).
+ *   y_pred, y_true [B][C][N] fp32 (y_true one-hot floats).
  *   forward writes the scalar loss to loss[0] and per-(b,c) backward coefficients
  *   (alpha, beta, gamma) to coef[B*C*3]:   dL/dy_pred = alpha + beta*y_true + gamma*y_pred.
  * ------------------------------------------------------------------------------------------ */
 size_t hno_loss_workspace_bytes(int B, int C);
 int hno_loss_forward(const float* y_pred, const float* y_true, float* loss, float* coef, void* workspace, int B,
-                     int C, long N, int kind, void* stream);
+                     int C, long N, int kind, float param, void* stream);
 int hno_loss_backward(const float* y_pred, const float* y_true, const float* coef, const float* grad_loss,
                       float* dy_pred, int B, int C, long N, void* stream);
 
@@ -164,10 +165,26 @@ int hno_loss_backward(const float* y_pred, const float* y_true, const float* coe
  *            nets/custom_losses.py + their autograd.  labels: uint8 [B][Dx][Hx][Wx]. */
 int hno_head_loss_forward(const void* tables_host, const void* tables_dev, const float* logits_low,
                           const uint8_t* labels, float* loss, float* coef, void* workspace, int B, int C, long P,
-                          int kind, void* stream);
+                          int kind, float param, void* stream);
 int hno_head_loss_backward(const void* tables_host, const void* tables_dev, const float* logits_low,
                            const uint8_t* labels, const float* coef, const float* grad_loss, float* dlogits_low,
                            void* workspace, int B, int C, long P, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross entropy ON PROBABILITIES             replaces torch.nn.CrossEntropyLoss() as the reference
+ *   configures and calls it: experiments/run.py:105-110 (loss_name looked up in torch.nn),
+ *   experiments/train_test.py:159-160 (loss_fn(model(x), one_hot)): the model's softmax OUTPUT is
+ *   the "input" of log-softmax, targets are class probabilities, reduction 'mean' over B*N:
+ *     loss = 1/(B N) sum_{b,v} [ (sum_c t_c) logsumexp_c(p) - sum_c t_c p_c ].
+ *   y_pred [B][C][N] fp32.  Targets: exactly one of y_true ([B][C][N] fp32) and labels ([B][N]
+ *   uint8 class indices, i.e. the input of experiments/utils.py:74-97 instead of its output).
+ *   backward: dy_pred = grad_loss * (softmax(p)_c * sum_c' t_c' - t_c) / (B N)  (grad_loss NULL = 1).
+ * ------------------------------------------------------------------------------------------ */
+size_t hno_ce_loss_workspace_bytes(int B);
+int hno_ce_loss_forward(const float* y_pred, const float* y_true, const uint8_t* labels, float* loss,
+                        void* workspace, int B, int C, long N, void* stream);
+int hno_ce_loss_backward(const float* y_pred, const float* y_true, const uint8_t* labels,
+                         const float* grad_loss, float* dy_pred, int B, int C, long N, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adamax step on a flat parameter vector (torch.optim.Adamax semantics, the optimizer of

@@ -53,10 +53,13 @@ SIGNATURES = {
     'hno_head_backward_workspace_bytes': (_Z, [_P, _I, _I]),
     'hno_head_backward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
     'hno_loss_workspace_bytes': (_Z, [_I, _I]),
-    'hno_loss_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
+    'hno_loss_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P]),
     'hno_loss_backward': (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P]),
-    'hno_head_loss_forward': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
+    'hno_head_loss_forward': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P]),
     'hno_head_loss_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    'hno_ce_loss_workspace_bytes': (_Z, [_I]),
+    'hno_ce_loss_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    'hno_ce_loss_backward': (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P]),
     'hno_adamax_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 

@@ -67,10 +67,13 @@ size_t head_backward_workspace_bytes(const void*, int, int);
 int head_backward(const void*, const void*, const float*, const float*, float*, void*, int, int, long, int,
                   cudaStream_t);
 size_t loss_workspace_bytes(int, int);
-int loss_forward(const float*, const float*, float*, float*, void*, int, int, long, int, cudaStream_t);
+int loss_forward(const float*, const float*, float*, float*, void*, int, int, long, int, float, cudaStream_t);
 int loss_backward(const float*, const float*, const float*, const float*, float*, int, int, long, cudaStream_t);
 int head_loss_forward(const void*, const void*, const float*, const uint8_t*, float*, float*, void*, int, int, long,
-                      int, cudaStream_t);
+                      int, float, cudaStream_t);
+size_t ce_loss_workspace_bytes(int);
+int ce_loss_forward(const float*, const float*, const uint8_t*, float*, void*, int, int, long, cudaStream_t);
+int ce_loss_backward(const float*, const float*, const uint8_t*, const float*, float*, int, int, long, cudaStream_t);
 int head_loss_backward(const void*, const void*, const float*, const uint8_t*, const float*, const float*, float*,
                        void*, int, int, long, cudaStream_t);
 int adamax_step(float*, const float*, float*, float*, long, float, float, float, float, float, int, float,
@@ -215,8 +218,8 @@ int hno_head_backward(const void* tables_host, const void* tables_dev, const flo
 size_t hno_loss_workspace_bytes(int B, int C) { return loss_workspace_bytes(B, C); }
 
 int hno_loss_forward(const float* y_pred, const float* y_true, float* loss, float* coef, void* workspace, int B, int C,
-                     long N, int kind, void* stream) {
-  return loss_forward(y_pred, y_true, loss, coef, workspace, B, C, N, kind, ST(stream));
+                     long N, int kind, float param, void* stream) {
+  return loss_forward(y_pred, y_true, loss, coef, workspace, B, C, N, kind, param, ST(stream));
 }
 
 int hno_loss_backward(const float* y_pred, const float* y_true, const float* coef, const float* grad_loss,
@@ -226,8 +229,8 @@ int hno_loss_backward(const float* y_pred, const float* y_true, const float* coe
 
 int hno_head_loss_forward(const void* tables_host, const void* tables_dev, const float* logits_low,
                           const uint8_t* labels, float* loss, float* coef, void* workspace, int B, int C, long P,
-                          int kind, void* stream) {
-  return head_loss_forward(tables_host, tables_dev, logits_low, labels, loss, coef, workspace, B, C, P, kind,
+                          int kind, float param, void* stream) {
+  return head_loss_forward(tables_host, tables_dev, logits_low, labels, loss, coef, workspace, B, C, P, kind, param,
                            ST(stream));
 }
 
@@ -236,6 +239,18 @@ int hno_head_loss_backward(const void* tables_host, const void* tables_dev, cons
                            void* workspace, int B, int C, long P, void* stream) {
   return head_loss_backward(tables_host, tables_dev, logits_low, labels, coef, grad_loss, dlogits_low, workspace, B, C,
                             P, ST(stream));
+}
+
+size_t hno_ce_loss_workspace_bytes(int B) { return ce_loss_workspace_bytes(B); }
+
+int hno_ce_loss_forward(const float* y_pred, const float* y_true, const uint8_t* labels, float* loss, void* workspace,
+                        int B, int C, long N, void* stream) {
+  return ce_loss_forward(y_pred, y_true, labels, loss, workspace, B, C, N, ST(stream));
+}
+
+int hno_ce_loss_backward(const float* y_pred, const float* y_true, const uint8_t* labels, const float* grad_loss,
+                         float* dy_pred, int B, int C, long N, void* stream) {
+  return ce_loss_backward(y_pred, y_true, labels, grad_loss, dy_pred, B, C, N, ST(stream));
 }
 
 int hno_adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, long n, float lr, float beta1,

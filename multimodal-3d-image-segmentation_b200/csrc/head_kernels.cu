@@ -342,7 +342,9 @@ __device__ __forceinline__ void block_reduce_store(double (&m)[kMoments], double
   }
 }
 
-// grid (kLossChunks, B*C); y_pred / y_true [B*C][N]
+// grid (kLossChunks, B*C); y_pred / y_true [B*C][N].  V = 4: 16-byte loads, two pairs in flight per thread (N % 4 == 0 and
+// 16-byte aligned bases; the launcher checks), V = 1: any N.
+template <int V>
 __global__ void __launch_bounds__(256) k_loss_moments(const float* __restrict__ yp, const float* __restrict__ yt,
                                                       double* __restrict__ partials, long N) {
   const long bc = blockIdx.y;
@@ -351,20 +353,40 @@ __global__ void __launch_bounds__(256) k_loss_moments(const float* __restrict__ 
   float m[kMoments] = {0.f, 0.f, 0.f, 0.f, 0.f};
   double md[kMoments] = {0.0, 0.0, 0.0, 0.0, 0.0};
   int cnt = 0;
-  for (long i = blockIdx.x * 256L + threadIdx.x; i < N; i += (long)gridDim.x * 256L) {
-    const float a = __ldg(p + i), b = __ldg(t + i);
+  auto add = [&](float a, float b) {
     m[0] += a;
     m[1] += b;
     m[2] = fmaf(a, b, m[2]);
     m[3] = fmaf(a, a, m[3]);
     m[4] = fmaf(b, b, m[4]);
-    if (++cnt == 64) {  // bounded fp32 run length, then spill into fp64
+  };
+  auto spill = [&]() {  // bounded fp32 run length (64 elements), then into fp64
 #pragma unroll
-      for (int k = 0; k < kMoments; ++k) {
-        md[k] += (double)m[k];
-        m[k] = 0.f;
-      }
-      cnt = 0;
+    for (int k = 0; k < kMoments; ++k) {
+      md[k] += (double)m[k];
+      m[k] = 0.f;
+    }
+    cnt = 0;
+  };
+  if (V == 4) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    const float4* t4 = reinterpret_cast<const float4*>(t);
+    const long n4 = N >> 2, step = (long)gridDim.x * 256L;
+    long i = blockIdx.x * 256L + threadIdx.x;
+    for (; i + step < n4; i += 2 * step) {
+      const float4 a0 = __ldg(p4 + i), b0 = __ldg(t4 + i), a1 = __ldg(p4 + i + step), b1 = __ldg(t4 + i + step);
+      add(a0.x, b0.x); add(a0.y, b0.y); add(a0.z, b0.z); add(a0.w, b0.w);
+      add(a1.x, b1.x); add(a1.y, b1.y); add(a1.z, b1.z); add(a1.w, b1.w);
+      if (++cnt == 8) spill();
+    }
+    if (i < n4) {
+      const float4 a0 = __ldg(p4 + i), b0 = __ldg(t4 + i);
+      add(a0.x, b0.x); add(a0.y, b0.y); add(a0.z, b0.z); add(a0.w, b0.w);
+    }
+  } else {
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < N; i += (long)gridDim.x * 256L) {
+      add(__ldg(p + i), __ldg(t + i));
+      if (++cnt == 64) spill();
     }
   }
 #pragma unroll
@@ -682,8 +704,8 @@ static bool row_kernels_enabled() {
 
 // one block: reduce chunk partials, evaluate the loss and the backward coefficients
 __global__ void __launch_bounds__(256) k_loss_finalize(const double* __restrict__ partials, int nchunks, int BC,
-                                                       double N, int kind, float* __restrict__ loss,
-                                                       float* __restrict__ coef) {
+                                                       double N, int kind, double param,
+                                                       float* __restrict__ loss, float* __restrict__ coef) {
   __shared__ double sterm[256];
   double term = 0.0;
   const int fwarp = threadIdx.x >> 5, flane = threadIdx.x & 31, fnw = blockDim.x >> 5;
@@ -703,6 +725,18 @@ __global__ void __launch_bounds__(256) k_loss_finalize(const double* __restrict_
       term += 1.0 - dice;
       a = 2.0 * spt / (U * U) / BC;
       b = -2.0 / U / BC;
+      g = 0.0;
+    } else if (kind == 2) {  // nets/custom_losses.py:114-133: mean((-log(clamp(dice, 1e-7, 1 - 1e-7)))^exp)
+      const double U = st + sp + 1e-7;
+      const double dice = 2.0 * spt / U;
+      const double lo = 1e-7, hi = 1.0 - 1e-7;
+      const double dc = fmin(fmax(dice, lo), hi);
+      const double nl = -log(dc);
+      term += pow(nl, param);
+      // d term / d dice (zero where the clamp is active), then d dice / d p = 2 t / U - 2 I / U^2
+      const double sl = (dice >= lo && dice <= hi) ? -param * pow(nl, param - 1.0) / dc : 0.0;
+      a = sl * (-2.0 * spt / (U * U)) / BC;
+      b = sl * (2.0 / U) / BC;
       g = 0.0;
     } else {  // nets/custom_losses.py:17-70: r = tp / sqrt(tt*pp + 1e-7) on centred data; loss = mean(1 - (r+1)/2)
       const double mt = st / N, mp = sp / N;
@@ -741,6 +775,150 @@ __global__ void __launch_bounds__(256) k_loss_bwd(const float* __restrict__ yp, 
   const float a = gl * coef[bc * 3 + 0], b = gl * coef[bc * 3 + 1], g = gl * coef[bc * 3 + 2];
   for (long i = blockIdx.x * 256L + threadIdx.x; i < N; i += (long)gridDim.x * 256L)
     dyp[bc * N + i] = a + b * __ldg(yt + bc * N + i) + g * __ldg(yp + bc * N + i);
+}
+
+// ------------------------------------------------------------------------------------------ cross entropy
+// torch.nn.CrossEntropyLoss() as the reference configures it (experiments/run.py:105-110, called as
+// loss_fn(y_pred, y_true) in train_test.py:159-160): the "logits" are the network's softmax OUTPUT p, the target is
+// class probabilities t (one-hot floats), reduction 'mean' over batch x voxels:
+//   loss = 1/(B N) sum_{b,v} [ (sum_c t_c) lse(p) - sum_c t_c p_c ],   d loss / d p_c = (softmax(p)_c sum t - t_c) / (B N)
+// One pass over p and t (or uint8 labels, LAB = 1: t = one-hot(label)); y [B][C][N]; grid (chunks, B).
+// V voxels per thread and iteration: V = 4 uses 16-byte loads (uchar4 for labels); needs N % 4 == 0 and aligned bases.
+constexpr int kCeChunks = 592;  // blocks per sample: 4 per SM
+
+template <int V>
+__device__ __forceinline__ void ce_ldf(const float* __restrict__ base, long i, float (&out)[V]) {
+  if constexpr (V == 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(base) + i);
+    out[0] = q.x, out[1] = q.y, out[2] = q.z, out[3] = q.w;
+  } else {
+    out[0] = __ldg(base + i);
+  }
+}
+
+template <int C, int LAB, int V>
+__device__ __forceinline__ void ce_load(const float* __restrict__ p, const float* __restrict__ t,
+                                        const uint8_t* __restrict__ lab, long N, long i, float (&pv)[C][V],
+                                        float (&tv)[C][V]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) ce_ldf<V>(p + c * N, i, pv[c]);
+  if constexpr (LAB) {
+    int l[V];
+    if constexpr (V == 4) {
+      const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(lab) + i);
+      l[0] = q.x, l[1] = q.y, l[2] = q.z, l[3] = q.w;
+    } else {
+      l[0] = (int)__ldg(lab + i);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int v = 0; v < V; ++v) tv[c][v] = l[v] == c ? 1.f : 0.f;
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) ce_ldf<V>(t + c * N, i, tv[c]);
+  }
+}
+
+template <int C, int LAB, int V>
+__global__ void __launch_bounds__(256) k_ce_fwd(const float* __restrict__ yp, const float* __restrict__ yt,
+                                                const uint8_t* __restrict__ labels, double* __restrict__ partials,
+                                                long N) {
+  __shared__ double sred[8];
+  const long b = blockIdx.y;
+  const float* p = yp + b * C * N;
+  const float* t = LAB ? nullptr : yt + b * C * N;
+  const uint8_t* lab = LAB ? labels + b * N : nullptr;
+  float acc = 0.f;
+  double accd = 0.0;
+  int cnt = 0;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < N / V; i += (long)gridDim.x * 256L) {
+    float pv[C][V], tv[C][V];
+    ce_load<C, LAB, V>(p, t, lab, N, i, pv, tv);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float mx = pv[0][v];
+#pragma unroll
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, pv[c][v]);
+      float se = 0.f, dot = 0.f, ts = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        se += expf(pv[c][v] - mx);
+        dot = fmaf(tv[c][v], pv[c][v], dot);
+        ts += tv[c][v];
+      }
+      acc += fmaf(ts, mx + logf(se), -dot);
+    }
+    if (++cnt == 64 / V) {  // bounded fp32 run length, then spill into fp64
+      accd += (double)acc;
+      acc = 0.f;
+      cnt = 0;
+    }
+  }
+  accd = warp_sum_d(accd + (double)acc);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = accd;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sred[w];
+    partials[b * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ce_finalize(const double* __restrict__ partials, int n, double inv_count,
+                                                     float* __restrict__ loss) {
+  __shared__ double sred[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += sred[w];
+    loss[0] = (float)(tot * inv_count);
+  }
+}
+
+template <int C, int LAB, int V>
+__global__ void __launch_bounds__(256) k_ce_bwd(const float* __restrict__ yp, const float* __restrict__ yt,
+                                                const uint8_t* __restrict__ labels,
+                                                const float* __restrict__ grad_loss, float* __restrict__ dyp, long N,
+                                                float inv_count) {
+  const long b = blockIdx.y;
+  const float* p = yp + b * C * N;
+  const float* t = LAB ? nullptr : yt + b * C * N;
+  const uint8_t* lab = LAB ? labels + b * N : nullptr;
+  float* d = dyp + b * C * N;
+  const float k = (grad_loss ? __ldg(grad_loss) : 1.f) * inv_count;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < N / V; i += (long)gridDim.x * 256L) {
+    float pv[C][V], tv[C][V];
+    ce_load<C, LAB, V>(p, t, lab, N, i, pv, tv);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float mx = pv[0][v];
+#pragma unroll
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, pv[c][v]);
+      float se = 0.f, ts = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        pv[c][v] = expf(pv[c][v] - mx);
+        se += pv[c][v];
+        ts += tv[c][v];
+      }
+      const float r = ts / se;
+#pragma unroll
+      for (int c = 0; c < C; ++c) pv[c][v] = k * fmaf(pv[c][v], r, -tv[c][v]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if constexpr (V == 4) {
+        reinterpret_cast<float4*>(d + c * N)[i] = make_float4(pv[c][0], pv[c][1], pv[c][2], pv[c][3]);
+      } else {
+        d[c * N + i] = pv[c][0];
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -820,16 +998,20 @@ int head_backward(const void* th, const void* td, const float* dprobs, const flo
 size_t loss_workspace_bytes(int B, int C) { return (size_t)B * C * kLossChunks * kMoments * sizeof(double) + 256; }
 
 int loss_forward(const float* yp, const float* yt, float* loss, float* coef, void* ws, int B, int C, long N, int kind,
-                 cudaStream_t st) {
+                 float param, cudaStream_t st) {
   HNO_CHECK(yp && yt && loss && coef && ws, "loss_forward: null pointer");
-  HNO_CHECK(kind == 0 || kind == 1, "loss_forward: kind must be 0 (Dice) or 1 (PCC)");
+  HNO_CHECK(kind >= 0 && kind <= 2, "loss_forward: kind must be 0 (Dice), 1 (PCC) or 2 (ExpDice)");
+  HNO_CHECK(kind != 2 || param > 0.f, "loss_forward: ExpDice needs a positive exponent");
   HNO_CHECK((long)B * C <= 65535, "loss_forward: too many (batch, label) pairs");
   double* partials = reinterpret_cast<double*>(ws);
   int chunks = (int)((N + 255) / 256 < kLossChunks ? (N + 255) / 256 : kLossChunks);
   dim3 grid(chunks, B * C);
-  k_loss_moments<<<grid, 256, 0, st>>>(yp, yt, partials, N);
+  if (N % 4 == 0 && ((reinterpret_cast<uintptr_t>(yp) | reinterpret_cast<uintptr_t>(yt)) & 15) == 0)
+    k_loss_moments<4><<<grid, 256, 0, st>>>(yp, yt, partials, N);
+  else
+    k_loss_moments<1><<<grid, 256, 0, st>>>(yp, yt, partials, N);
   HNO_LAUNCH_CHECK();
-  k_loss_finalize<<<1, 256, 0, st>>>(partials, chunks, B * C, (double)N, kind, loss, coef);
+  k_loss_finalize<<<1, 256, 0, st>>>(partials, chunks, B * C, (double)N, kind, (double)param, loss, coef);
   HNO_LAUNCH_CHECK();
   return 0;
 }
@@ -844,12 +1026,68 @@ int loss_backward(const float* yp, const float* yt, const float* coef, const flo
   return 0;
 }
 
+size_t ce_loss_workspace_bytes(int B) { return (size_t)B * kCeChunks * sizeof(double) + 256; }
+
+// 16-byte path: four voxels per thread; needs every channel row (pitch N floats) and label row (N bytes) aligned
+static bool ce_vec4(const void* a, const void* b, const void* c, const void* d, long N, int C) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                         reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(d);
+  return N % 4 == 0 && (bits & 15) == 0 && C <= 4;
+}
+
+int ce_loss_forward(const float* yp, const float* yt, const uint8_t* labels, float* loss, void* ws, int B, int C,
+                    long N, cudaStream_t st) {
+  HNO_CHECK(yp && loss && ws, "ce_loss_forward: null pointer");
+  HNO_CHECK((yt != nullptr) != (labels != nullptr), "ce_loss_forward: pass exactly one of y_true and labels");
+  HNO_CHECK(B >= 1 && B <= 65535 && N >= 1, "ce_loss_forward: bad sizes");
+  double* partials = reinterpret_cast<double*>(ws);
+  const bool v4 = ce_vec4(yp, yt, labels, nullptr, N, C);
+  const long items = v4 ? N / 4 : N;
+  const int chunks = (int)((items + 255) / 256 < kCeChunks ? (items + 255) / 256 : kCeChunks);
+  dim3 grid(chunks, B);
+  HNO_CLASS_SWITCH(C, {
+    if constexpr (kC <= 4) {
+      if (v4 && labels) k_ce_fwd<kC, 1, 4><<<grid, 256, 0, st>>>(yp, nullptr, labels, partials, N);
+      else if (v4) k_ce_fwd<kC, 0, 4><<<grid, 256, 0, st>>>(yp, yt, nullptr, partials, N);
+    }
+    if (!v4 && labels) k_ce_fwd<kC, 1, 1><<<grid, 256, 0, st>>>(yp, nullptr, labels, partials, N);
+    else if (!v4) k_ce_fwd<kC, 0, 1><<<grid, 256, 0, st>>>(yp, yt, nullptr, partials, N);
+  })
+  HNO_LAUNCH_CHECK();
+  k_ce_finalize<<<1, 256, 0, st>>>(partials, chunks * B, 1.0 / ((double)B * (double)N), loss);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+int ce_loss_backward(const float* yp, const float* yt, const uint8_t* labels, const float* grad_loss, float* dyp, int B,
+                     int C, long N, cudaStream_t st) {
+  HNO_CHECK(yp && dyp, "ce_loss_backward: null pointer");
+  HNO_CHECK((yt != nullptr) != (labels != nullptr), "ce_loss_backward: pass exactly one of y_true and labels");
+  HNO_CHECK(B >= 1 && B <= 65535 && N >= 1, "ce_loss_backward: bad sizes");
+  const bool v4 = ce_vec4(yp, yt, labels, dyp, N, C);
+  const long items = v4 ? N / 4 : N;
+  const int chunks = (int)((items + 255) / 256 < 1184 ? (items + 255) / 256 : 1184);
+  dim3 grid(chunks, B);
+  const float inv = (float)(1.0 / ((double)B * (double)N));
+  HNO_CLASS_SWITCH(C, {
+    if constexpr (kC <= 4) {
+      if (v4 && labels) k_ce_bwd<kC, 1, 4><<<grid, 256, 0, st>>>(yp, nullptr, labels, grad_loss, dyp, N, inv);
+      else if (v4) k_ce_bwd<kC, 0, 4><<<grid, 256, 0, st>>>(yp, yt, nullptr, grad_loss, dyp, N, inv);
+    }
+    if (!v4 && labels) k_ce_bwd<kC, 1, 1><<<grid, 256, 0, st>>>(yp, nullptr, labels, grad_loss, dyp, N, inv);
+    else if (!v4) k_ce_bwd<kC, 0, 1><<<grid, 256, 0, st>>>(yp, yt, nullptr, grad_loss, dyp, N, inv);
+  })
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
 int head_loss_forward(const void* th, const void* td, const float* ll, const uint8_t* labels, float* loss, float* coef,
-                      void* ws, int B, int C, long P, int kind, cudaStream_t st) {
+                      void* ws, int B, int C, long P, int kind, float param, cudaStream_t st) {
   InterpDev t;
   if (make_dev(th, td, &t)) return -1;
   HNO_CHECK(ll && labels && loss && coef && ws, "head_loss_forward: null pointer");
-  HNO_CHECK(kind == 0 || kind == 1, "head_loss_forward: kind must be 0 (Dice) or 1 (PCC)");
+  HNO_CHECK(kind >= 0 && kind <= 2, "head_loss_forward: kind must be 0 (Dice), 1 (PCC) or 2 (ExpDice)");
+  HNO_CHECK(kind != 2 || param > 0.f, "head_loss_forward: ExpDice needs a positive exponent");
   const long Nx = (long)t.hi[0] * t.hi[1] * t.hi[2];
   // moments live at the END of the head-backward workspace so that forward and backward can share it
   const size_t g12 = ((size_t)B * C * t.hi[0] * t.hi[1] * t.lo[2] + (size_t)B * C * t.hi[0] * t.lo[1] * t.lo[2]);
@@ -865,7 +1103,7 @@ int head_loss_forward(const void* th, const void* td, const float* ll, const uin
     HNO_CLASS_SWITCH(C, { k_head_loss_moments<kC, 1><<<grid, 256, 0, st>>>(ll, labels, partials, t, P); })
   }
   HNO_LAUNCH_CHECK();
-  k_loss_finalize<<<1, 256, 0, st>>>(partials, chunks, B * C, (double)Nx, kind, loss, coef);
+  k_loss_finalize<<<1, 256, 0, st>>>(partials, chunks, B * C, (double)Nx, kind, (double)param, loss, coef);
   HNO_LAUNCH_CHECK();
   return 0;
 }

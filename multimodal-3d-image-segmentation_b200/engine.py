@@ -45,10 +45,17 @@ class XSEngine:
             return _XSFunction.apply(self, x, *params)
         return self.run_forward(x, save=False)[0]
 
-    def loss(self, x, labels, loss_name='DiceLoss'):
+    def loss(self, x, labels, loss_name='DiceLoss', param=None):
         """Fused training objective on integer labels: the probabilities are never materialised.
-        Numerically the same as loss_fn(model(x), to_categorical(labels)) of experiments/train_test.py:152-160."""
-        return _XSLossFunction.apply(self, x, labels, ops.LOSS_KINDS[loss_name], *self.named_slots())
+        Numerically the same as loss_fn(model(x), to_categorical(labels)) of experiments/train_test.py:152-160.
+        `param` is the loss's constructor argument where it has one (ExpDiceLoss: exp, default 0.3).
+        CrossEntropyLoss (torch.nn fall-through of run.py:105-110) is not of the five-moment form: it runs the head kernel,
+        then the one-pass cross-entropy kernels on the uint8 labels, then the head backward."""
+        if loss_name == 'CrossEntropyLoss':
+            return _XSCrossEntropyFunction.apply(self, x, labels, *self.named_slots())
+        if param is None:
+            param = ops.LOSS_DEFAULT_PARAM[loss_name]
+        return _XSLossFunction.apply(self, x, labels, ops.LOSS_KINDS[loss_name], float(param), *self.named_slots())
 
     # ------------------------------------------------------------------------------------------ forward
     def run_forward(self, x, save=True, head=True):
@@ -252,12 +259,12 @@ class _XSFunction(torch.autograd.Function):
 
 class _XSLossFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, x, labels, kind, *params):
+    def forward(ctx, engine, x, labels, kind, param, *params):
         _, S = engine.run_forward(x, save=True, head=False)
         if S.act != 1:
             raise NotImplementedError('the fused loss needs output_activation="softmax"')
         lab = _labels_u8(labels, x)
-        loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], kind)
+        loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], kind, param)
         ctx.engine, ctx.S, ctx.lab, ctx.coef = engine, S, lab, coef
         return loss[0]
 
@@ -266,4 +273,22 @@ class _XSLossFunction(torch.autograd.Function):
         g = g.reshape(1).to(torch.float32).contiguous()
         grads = ctx.engine.run_backward(ctx.S, fused=(ctx.lab, ctx.coef, g))
         ctx.S = None
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class _XSCrossEntropyFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, labels, *params):
+        probs, S = engine.run_forward(x, save=True)
+        lab = _labels_u8(labels, x)
+        loss = ops.ce_loss_forward(probs, labels=lab)
+        ctx.engine, ctx.S, ctx.lab, ctx.probs = engine, S, lab, probs
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.reshape(1).to(torch.float32).contiguous()
+        dprobs = ops.ce_loss_backward(ctx.probs, labels=ctx.lab, grad_loss=g)
+        grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs)
+        ctx.S = ctx.probs = None
+        return (None, None, None) + tuple(grads)

@@ -226,9 +226,10 @@ class HNOSegXS(nn.Module):
             _, S = self.engine().run_forward(x, save=False, head=False)
             return ops.head_forward(S.ll, S.tables, S.geom[3], 0)
 
-    def loss(self, x, labels, loss_name='DiceLoss'):
-        """Fused head + loss on integer labels; equals loss_fn(self(x), to_categorical(labels))."""
-        return self.engine().loss(x, labels, loss_name)
+    def loss(self, x, labels, loss_name='DiceLoss', param=None):
+        """Fused head + loss on integer labels; equals loss_fn(self(x), to_categorical(labels)) for loss_name in
+        DiceLoss / PCCLoss / ExpDiceLoss(exp=param) / CrossEntropyLoss."""
+        return self.engine().loss(x, labels, loss_name, param)
 
     def forward_modular(self, x):
         """Same network composed from the stand-alone sub-modules (dense tensors, one autograd node per op).

@@ -389,14 +389,16 @@ class HeadUpsample(torch.autograd.Function):
         return head_backward(dprobs, probs, tables, pitch, activation), None, None
 
 
-LOSS_KINDS = {'DiceLoss': 0, 'PCCLoss': 1}
+# moment-based losses (one pass, five sums per (sample, label)); ExpDiceLoss carries its exponent as `param`
+LOSS_KINDS = {'DiceLoss': 0, 'PCCLoss': 1, 'ExpDiceLoss': 2}
+LOSS_DEFAULT_PARAM = {'DiceLoss': 0.0, 'PCCLoss': 0.0, 'ExpDiceLoss': 0.3}
 
 
 class ProbabilityLoss(torch.autograd.Function):
-    """DiceLoss / PCCLoss on probabilities and one-hot float targets (reference nets/custom_losses.py)."""
+    """DiceLoss / PCCLoss / ExpDiceLoss on probabilities and one-hot float targets (reference nets/custom_losses.py)."""
 
     @staticmethod
-    def forward(ctx, y_pred, y_true, kind):
+    def forward(ctx, y_pred, y_true, kind, param=0.0):
         _require_cuda(y_pred, 'y_pred')
         y_pred = y_pred.contiguous()
         y_true = y_true.contiguous().to(torch.float32)
@@ -406,7 +408,7 @@ class ProbabilityLoss(torch.autograd.Function):
         coef = torch.empty((B * C * 3,), dtype=torch.float32, device=y_pred.device)
         ws = workspace(_lib.load().hno_loss_workspace_bytes(B, C), y_pred.device, 'loss')
         call('hno_loss_forward', ptr(y_pred), ptr(y_true), ptr(loss), ptr(coef), ptr(ws), B, C, N, int(kind),
-             stream_ptr())
+             float(param), stream_ptr())
         ctx.save_for_backward(y_pred, y_true, coef)
         return loss[0]
 
@@ -420,10 +422,72 @@ class ProbabilityLoss(torch.autograd.Function):
         dyp = torch.empty_like(y_pred)
         g = g.reshape(1).to(torch.float32).contiguous()
         call('hno_loss_backward', ptr(y_pred), ptr(y_true), ptr(coef), ptr(g), ptr(dyp), B, C, N, stream_ptr())
-        return dyp, None, None
+        return dyp, None, None, None
 
 
-def head_loss_forward(logits_low, labels, tables, pitch, kind):
+def _ce_check(y_pred, y_true, labels):
+    _require_cuda(y_pred, 'y_pred')
+    if (y_true is None) == (labels is None):
+        raise ValueError('cross entropy: pass exactly one of y_true (one-hot floats) and labels (uint8)')
+    if not y_pred.is_contiguous():
+        raise ValueError('cross entropy: y_pred must be a dense NCDHW tensor')
+    if y_true is not None:
+        _require_cuda(y_true, 'y_true')
+        if y_true.shape != y_pred.shape or not y_true.is_contiguous():
+            raise ValueError('cross entropy: y_true must be a dense tensor of the shape of y_pred')
+    else:
+        if labels.dtype != torch.uint8 or not labels.is_contiguous() or labels.device != y_pred.device or \
+                tuple(labels.shape) != (y_pred.shape[0],) + tuple(y_pred.shape[2:]):
+            raise ValueError('cross entropy: labels must be dense uint8 class indices of shape (B, *spatial) on the '
+                             'device of y_pred')
+
+
+def ce_loss_forward(y_pred, y_true=None, labels=None):
+    """Cross entropy on probabilities (torch.nn.CrossEntropyLoss() as experiments/run.py:105-110 + train_test.py:159-160
+    use it) against one-hot float targets OR uint8 labels [B][N]: returns loss[1]."""
+    _ce_check(y_pred, y_true, labels)
+    B, C = y_pred.shape[:2]
+    N = _flat_s(y_pred)
+    loss = torch.empty((1,), dtype=torch.float32, device=y_pred.device)
+    ws = workspace(_lib.load().hno_ce_loss_workspace_bytes(B), y_pred.device, 'ce')
+    call('hno_ce_loss_forward', ptr(y_pred), ptr(y_true), ptr(labels), ptr(loss), ptr(ws), B, C, N, stream_ptr())
+    return loss
+
+
+def ce_loss_backward(y_pred, y_true=None, labels=None, grad_loss=None):
+    _ce_check(y_pred, y_true, labels)
+    B, C = y_pred.shape[:2]
+    dyp = torch.empty_like(y_pred)
+    call('hno_ce_loss_backward', ptr(y_pred), ptr(y_true), ptr(labels), ptr(grad_loss), ptr(dyp), B, C, _flat_s(y_pred),
+         stream_ptr())
+    return dyp
+
+
+class CrossEntropyOnProbabilities(torch.autograd.Function):
+    """loss_fn(y_pred, y_true) for loss_name = CrossEntropyLoss; y_true is one-hot floats (or any class probabilities)."""
+
+    @staticmethod
+    def forward(ctx, y_pred, y_true):
+        _require_cuda(y_pred, 'y_pred')
+        y_pred = y_pred.contiguous()
+        y_true = y_true.contiguous().to(torch.float32)
+        if y_true.shape != y_pred.shape:
+            raise ValueError(f'CrossEntropyLoss: y_true {tuple(y_true.shape)} must match y_pred {tuple(y_pred.shape)} '
+                             '(class-probability targets, as experiments/train_test.py:152 builds them)')
+        loss = ce_loss_forward(y_pred, y_true=y_true)
+        ctx.save_for_backward(y_pred, y_true)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError('hno_b200: losses do not provide a gradient w.r.t. y_true')
+        y_pred, y_true = ctx.saved_tensors
+        g = g.reshape(1).to(torch.float32).contiguous()
+        return ce_loss_backward(y_pred, y_true=y_true, grad_loss=g), None
+
+
+def head_loss_forward(logits_low, labels, tables, pitch, kind, param=0.0):
     """Fused head + loss on uint8 labels: returns (loss[1], coef)."""
     B, C = logits_low.shape[:2]
     dev = logits_low.device
@@ -431,7 +495,7 @@ def head_loss_forward(logits_low, labels, tables, pitch, kind):
     coef = torch.empty((B * C * 3,), dtype=torch.float32, device=dev)
     ws = workspace(tables.head_backward_workspace_bytes(B, C), dev, 'head')
     call('hno_head_loss_forward', tables.host.data_ptr(), tables.dev.data_ptr(), ptr(logits_low), ptr(labels),
-         ptr(loss), ptr(coef), ptr(ws), B, C, pitch, int(kind), stream_ptr())
+         ptr(loss), ptr(coef), ptr(ws), B, C, pitch, int(kind), float(param), stream_ptr())
     return loss, coef
 
 
@@ -446,5 +510,6 @@ def head_loss_backward(logits_low, labels, coef, grad_loss, tables, pitch):
 
 __all__ = ['dht3_forward', 'dht3_adjoint', 'TruncatedDHT', 'TruncatedIDHT', 'AddIDHTSelu', 'pwconv_forward', 'pwconv_backward',
            'PointwiseConv', 'HartleyConv', 'stem_forward', 'stem_backward', 'StemConv', 'head_forward',
-           'head_backward', 'HeadUpsample', 'ProbabilityLoss', 'head_loss_forward', 'head_loss_backward',
+           'head_backward', 'HeadUpsample', 'ProbabilityLoss', 'CrossEntropyOnProbabilities', 'ce_loss_forward',
+           'ce_loss_backward', 'LOSS_DEFAULT_PARAM', 'head_loss_forward', 'head_loss_backward',
            'get_crop_plan', 'get_interp_tables', 'workspace', 'LOSS_KINDS']

@@ -99,7 +99,7 @@ class Trainer:
     reproduce the reference's per-step host sync).
     """
 
-    def __init__(self, model, loss_name='DiceLoss', lr=5e-3, group=None, use_graph=None):
+    def __init__(self, model, loss_name='DiceLoss', lr=5e-3, group=None, use_graph=None, loss_param=None):
         from . import ops
         # CUDA graph of forward + loss + backward (168 dependent launches per step): one graph per distinct pair of input
         # buffers, all sharing one memory pool; the all-reduce and the Adamax kernel (whose step count is a host
@@ -109,7 +109,9 @@ class Trainer:
         self._pool = None
         self.model = model
         self.engine = model.engine()
-        self.kind = ops.LOSS_KINDS[loss_name]
+        # CrossEntropyLoss (kind None) is not of the five-moment form: head kernel + one-pass CE kernels + head backward
+        self.kind = None if loss_name == 'CrossEntropyLoss' else ops.LOSS_KINDS[loss_name]
+        self.loss_param = float(ops.LOSS_DEFAULT_PARAM.get(loss_name, 0.0) if loss_param is None else loss_param)
         self.flat = FlatParameters(model)
         self.slots = self.engine.named_slots()
         self.dst = [self.flat.grad_view_of(p) for p in self.slots]
@@ -120,9 +122,14 @@ class Trainer:
         from . import ops
         from .engine import _labels_u8
         with torch.no_grad():
-            _, S = self.engine.run_forward(x, save=True, head=False)
             lab = _labels_u8(labels, x)
-            loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], self.kind)
+            if self.kind is None:
+                probs, S = self.engine.run_forward(x, save=True)
+                loss = ops.ce_loss_forward(probs, labels=lab)
+                self.engine.run_backward(S, dprobs=ops.ce_loss_backward(probs, labels=lab), dst=self.dst)
+                return loss
+            _, S = self.engine.run_forward(x, save=True, head=False)
+            loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], self.kind, self.loss_param)
             self.engine.run_backward(S, fused=(lab, coef, None), dst=self.dst)
         return loss
 

@@ -296,7 +296,25 @@ def pcc_loss(y_pred, y_true):
     return (1 - (r + 1) * 0.5).mean()
 
 
-LOSSES = {'DiceLoss': dice_loss, 'PCCLoss': pcc_loss}
+def exp_dice_loss(y_pred, y_true, exp=0.3):
+    """custom_losses.py:114-133: mean((-log(clamp(dice, 1e-7, 1 - 1e-7))) ** exp)."""
+    dims = tuple(range(2, y_true.ndim))
+    dice = 2.0 * (y_true * y_pred).sum(dims) / ((y_true + y_pred).sum(dims) + 1e-7)
+    return torch.pow(-torch.log(torch.clamp(dice, 1e-7, 1.0 - 1e-7)), exp).mean()
+
+
+def cross_entropy_loss(y_pred, y_true):
+    """torch.nn.CrossEntropyLoss() the way the reference reaches it: experiments/run.py:105-110 looks `loss_name` up
+    in torch.nn when custom_losses has no such class, and train_test.py:159-160 calls loss_fn(model(x), one_hot).  So the
+    log-softmax runs over the network's softmax OUTPUT and the target is class probabilities; 'mean' divides by the
+    batch x voxel count.  Written out instead of calling F.cross_entropy."""
+    lse = torch.logsumexp(y_pred, dim=1, keepdim=True)
+    per_voxel = -(y_true * (y_pred - lse)).sum(1)
+    return per_voxel.mean()
+
+
+LOSSES = {'DiceLoss': dice_loss, 'PCCLoss': pcc_loss, 'ExpDiceLoss': exp_dice_loss,
+          'CrossEntropyLoss': cross_entropy_loss}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -221,8 +221,10 @@ def case_losses():
     p = torch.softmax(torch.randn(2, 4, 6, 5, 7), dim=1).requires_grad_(True)
     t = orc.to_categorical(torch.randint(0, 4, (2, 1, 6, 5, 7)), 4)
     out = {'p': p.detach().numpy(), 't': t.numpy()}
-    for lname in ('DiceLoss', 'PCCLoss'):
-        loss = getattr(ref_losses, lname)()(p, t)
+    for lname in ('DiceLoss', 'PCCLoss', 'ExpDiceLoss', 'CrossEntropyLoss'):
+        # experiments/run.py:105-110: custom_losses first, torch.nn otherwise
+        loss_fn = getattr(ref_losses, lname)() if hasattr(ref_losses, lname) else getattr(torch.nn, lname)()
+        loss = loss_fn(p, t)
         (g,) = torch.autograd.grad(loss, p)
         check(f'{lname}', orc.LOSSES[lname](p.detach(), t), loss.detach(), 1e-6)
         out[f'{lname}/loss'] = loss.detach().numpy()

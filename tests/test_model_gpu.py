@@ -53,6 +53,38 @@ def test_small_model_against_reference_fixture(cuda, golden_dir, wt):
                 assert rel(p.grad, ref) < 2e-4, (lname, path, k, rel(p.grad, ref))
 
 
+@pytest.mark.parametrize('lname', ['ExpDiceLoss', 'CrossEntropyLoss'])
+def test_small_model_other_losses_against_fp64_oracle(cuda, golden_dir, lname):
+    """ExpDiceLoss (custom_losses.py:114-133) and the torch.nn.CrossEntropyLoss fall-through (run.py:105-110) through the
+    drop-in modules, the fused model.loss and the Trainer's flat gradient, against the fp64 oracle."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    from multimodal_3d_image_segmentation_b200.parallel import Trainer
+    g = dict(np.load(os.path.join(golden_dir, 'model_small.npz')))
+    sd = _sd(g, 'shared/sd/')
+    model = nets.HNOSegXS(2, 3, 8, [1, 2, 1, 2, 1, 2], (2, 3, 3), device=cuda)
+    model.load_state_dict(sd)
+    x = torch.from_numpy(g['shared/x'])
+    labels = torch.from_numpy(g['shared/labels'].astype(np.int64))
+    o_loss, o_grads = orc.train_step({k: v.double() for k, v in sd.items()}, x.double(), labels, [1, 2, 1, 2, 1, 2],
+                                     (2, 3, 3), lname)
+    onehot = orc.to_categorical(labels, 3).to(cuda)
+    for path in ('dropin', 'fused'):
+        model.zero_grad()
+        if path == 'dropin':
+            loss = getattr(nets.custom_losses, lname)()(model(x.to(cuda)), onehot)
+        else:
+            loss = model.loss(x.to(cuda), labels.to(cuda), lname)
+        loss.backward()
+        assert abs(float(loss) - float(o_loss)) < 1e-5, (lname, path)
+        for k, p in model.named_parameters():
+            assert rel(p.grad, o_grads[k]) < 2e-4, (lname, path, k, rel(p.grad, o_grads[k]))
+    tr = Trainer(model, loss_name=lname, use_graph=False)
+    loss = tr.loss_and_grad(x.to(cuda), labels.to(cuda))
+    assert abs(float(loss) - float(o_loss)) < 1e-5
+    for k, p in model.named_parameters():
+        assert rel(tr.flat.grad_view_of(p), o_grads[k]) < 2e-4, (lname, 'trainer', k)
+
+
 def test_full_size_forward_against_reference_probe(cuda, golden_dir):
     """BASELINE config 1: logits rel-err <= 1e-3 and >= 99.99 % identical argmax voxels (north_star tolerance)."""
     from multimodal_3d_image_segmentation_b200 import nets

@@ -245,7 +245,7 @@ def test_head_forward_backward(cuda, lo, hi, C):
     assert rel(up, F.interpolate(ll.double(), size=hi, mode='trilinear')) < 2e-6
 
 
-@pytest.mark.parametrize('name', ['DiceLoss', 'PCCLoss'])
+@pytest.mark.parametrize('name', ['DiceLoss', 'PCCLoss', 'ExpDiceLoss', 'CrossEntropyLoss'])
 def test_losses_golden_and_oracle(cuda, golden_dir, name):
     from multimodal_3d_image_segmentation_b200 import nets
     g = dict(np.load(os.path.join(golden_dir, 'losses.npz')))
@@ -268,7 +268,66 @@ def test_losses_golden_and_oracle(cuda, golden_dir, name):
     assert abs(float(lc) - float(lr)) < 1e-6 and rel(gc, 3.0 * gr) < 1e-5
 
 
-@pytest.mark.parametrize('kind', ['DiceLoss', 'PCCLoss'])
+def test_exp_dice_exponent_and_ce_arguments(cuda):
+    from multimodal_3d_image_segmentation_b200 import nets
+    gen = torch.Generator().manual_seed(13)
+    pp = torch.softmax(torch.randn(1, 3, 9, 8, 7, generator=gen), 1)
+    tt = orc.to_categorical(torch.randint(0, 3, (1, 1, 9, 8, 7), generator=gen), 3)
+    for e in (0.3, 1.0, 2.5):
+        pr = pp.double().requires_grad_(True)
+        lr = orc.exp_dice_loss(pr, tt.double(), e)
+        (gr,) = torch.autograd.grad(lr, pr)
+        pc = pp.to(cuda).requires_grad_(True)
+        lc = nets.custom_losses.ExpDiceLoss(exp=e)(pc, tt.to(cuda))
+        (gc,) = torch.autograd.grad(lc, pc)
+        assert abs(float(lc) - float(lr)) < 2e-6 * max(1.0, float(lr)) and rel(gc, gr) < 1e-5, e
+    with pytest.raises(ValueError):
+        nets.custom_losses.ExpDiceLoss(exp=0.0)
+    with pytest.raises(NotImplementedError):
+        nets.custom_losses.CrossEntropyLoss(label_smoothing=0.1)
+    with pytest.raises(ValueError):  # class-index targets are not what the reference passes (train_test.py:152)
+        nets.custom_losses.CrossEntropyLoss()(pp.to(cuda), torch.zeros(1, 9, 8, 7, device=cuda))
+
+
+@pytest.mark.parametrize('shape', [(2, 4, 33, 31, 29), (1, 3, 5, 4, 3), (3, 1, 17, 16, 15), (1, 8, 40, 9, 11)])
+def test_cross_entropy_labels_soft_targets_and_torch(cuda, shape):
+    """The CE kernels on uint8 labels equal the one-hot route bit for bit; soft (non one-hot) class-probability targets
+    and unnormalised inputs follow torch.nn.CrossEntropyLoss (the class the reference instantiates, run.py:110)."""
+    from multimodal_3d_image_segmentation_b200 import nets, ops
+    B, C = shape[:2]
+    gen = torch.Generator().manual_seed(14)
+    pp = torch.softmax(torch.randn(*shape, generator=gen), 1)
+    labels = torch.randint(0, C, (B, 1) + shape[2:], generator=gen)
+    onehot = orc.to_categorical(labels, C).contiguous()  # (the raw entry points take dense NCDHW tensors)
+    pc = pp.to(cuda)
+    lab = labels[:, 0].to(torch.uint8).to(cuda).contiguous()
+    if C > 1:  # to_categorical returns a channels-last view, as the reference's moveaxis does (utils.py:96)
+        with pytest.raises(ValueError):
+            ops.ce_loss_forward(pc, y_true=orc.to_categorical(labels, C).to(cuda))
+    l_lab = ops.ce_loss_forward(pc, labels=lab)
+    l_hot = ops.ce_loss_forward(pc, y_true=onehot.to(cuda))
+    assert float(l_lab) == float(l_hot)
+    gscale = torch.tensor([0.37], device=cuda)
+    g_lab = ops.ce_loss_backward(pc, labels=lab, grad_loss=gscale)
+    g_hot = ops.ce_loss_backward(pc, y_true=onehot.to(cuda), grad_loss=gscale)
+    assert torch.equal(g_lab, g_hot)
+    pr = pp.double().requires_grad_(True)
+    lr = orc.cross_entropy_loss(pr, onehot.double())
+    (gr,) = torch.autograd.grad(lr, pr)
+    assert abs(float(l_lab) - float(lr)) < 1e-6 and rel(g_lab, 0.37 * gr) < 1e-5
+    # soft targets, raw scores instead of probabilities
+    xs = torch.randn(*shape, generator=gen) * 3
+    ts = torch.softmax(torch.randn(*shape, generator=gen), 1)
+    xr = xs.double().requires_grad_(True)
+    lt = torch.nn.CrossEntropyLoss()(xr, ts.double())
+    (gt,) = torch.autograd.grad(lt, xr)
+    xc = xs.to(cuda).requires_grad_(True)
+    lc = nets.custom_losses.CrossEntropyLoss()(xc, ts.to(cuda))
+    (gc,) = torch.autograd.grad(lc, xc)
+    assert abs(float(lc) - float(lt)) < 2e-6 * max(1.0, float(lt)) and rel(gc, gt) < 1e-5
+
+
+@pytest.mark.parametrize('kind', ['DiceLoss', 'PCCLoss', 'ExpDiceLoss'])
 def test_fused_head_loss(cuda, kind):
     from multimodal_3d_image_segmentation_b200 import ops
     from multimodal_3d_image_segmentation_b200.plan import get_interp_tables, plane_pitch
@@ -284,7 +343,7 @@ def test_fused_head_loss(cuda, kind):
     pitch = plane_pitch(lo[1], lo[2])
     lld = to_planar(ll.to(cuda), pitch)
     lab = labels[:, 0].to(torch.uint8).to(cuda).contiguous()
-    loss, coef = ops.head_loss_forward(lld, lab, tables, pitch, ops.LOSS_KINDS[kind])
+    loss, coef = ops.head_loss_forward(lld, lab, tables, pitch, ops.LOSS_KINDS[kind], ops.LOSS_DEFAULT_PARAM[kind])
     assert abs(float(loss) - float(loss_r)) < 1e-6
     dll = ops.head_loss_backward(lld, lab, coef, None, tables, pitch)
     assert rel(from_planar(dll, lo[1], lo[2]), lr.grad) < 1e-5

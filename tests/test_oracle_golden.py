@@ -63,7 +63,7 @@ def test_block_fixtures(golden_dir):
 
 def test_loss_fixtures(golden_dir):
     g = _load(golden_dir, 'losses')
-    for name in ('DiceLoss', 'PCCLoss'):
+    for name in ('DiceLoss', 'PCCLoss', 'ExpDiceLoss', 'CrossEntropyLoss'):
         p = torch.from_numpy(g['p']).requires_grad_(True)
         loss = orc.LOSSES[name](p, torch.from_numpy(g['t']))
         _close(loss.detach(), g[f'{name}/loss'], 1e-6)
