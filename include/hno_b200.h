@@ -101,6 +101,22 @@ int hno_hartley_conv_backward(const float* dout, const float* y, const float* x,
                               void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Complex per-mode ("individual" weights) mixing of the retained Fourier half-spectrum
+ *   replaces nets/fourier_operator.py:165-187 (weights_type == 'individual': four corner einsums
+ *   'oidhw,bidhw->bodhw' with weight = complex(weight_real, weight_imag), :155) on real / imaginary
+ *   mode tensors re, im [B][ci][M] -> a, b [B][co][M];  w_real, w_imag [co][ci][M] with
+ *   M = 2 m0 * 2 m1 * m2 in the weights' own order (:67-72):   a + i b = (w_real + i w_imag)(re + i im).
+ *   backward: dre/dim and dw_real/dw_imag are optional PAIRS (both NULL or both set);
+ *   accumulate_dw != 0 adds into dw_*.
+ * ------------------------------------------------------------------------------------------ */
+int hno_complex_modemix_forward(const float* re, const float* im, const float* w_real, const float* w_imag,
+                                float* a, float* b, int B, int ci, int co, long M, void* stream);
+int hno_complex_modemix_backward(const float* da, const float* db, const float* re, const float* im,
+                                 const float* w_real, const float* w_imag, float* dre, float* dim,
+                                 float* dw_real, float* dw_imag, int B, int ci, int co, long M,
+                                 int accumulate_dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The n_XS shared-weight mixes of one HNO-XS block as one launch
  *   replaces nets/hnosegxs.py:261-262 (loop over NeuralOperatorBlock.forward :307-329) with
  *            nets/hartley_operator.py:287-292 (weights_type 'shared'):  z_l = selu(W_l z_{l-1} + z_{l-1}), l = 1..L

@@ -43,6 +43,8 @@ SIGNATURES = {
     'hno_modechain_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _I, _P]),
     'hno_hartley_conv_forward': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'hno_hartley_conv_backward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'hno_complex_modemix_forward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _P]),
+    'hno_complex_modemix_backward': (_I, [_P] * 10 + [_I, _I, _I, _L, _I, _P]),
     'hno_stem_supported': (_I, [_I, _I]),
     'hno_stem_forward': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _P]),
     'hno_stem_backward_workspace_bytes': (_Z, [_I, _I]),

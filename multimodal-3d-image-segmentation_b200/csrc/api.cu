@@ -76,6 +76,10 @@ int ce_loss_forward(const float*, const float*, const uint8_t*, float*, void*, i
 int ce_loss_backward(const float*, const float*, const uint8_t*, const float*, float*, int, int, long, cudaStream_t);
 int head_loss_backward(const void*, const void*, const float*, const uint8_t*, const float*, const float*, float*,
                        void*, int, int, long, cudaStream_t);
+int complex_modemix_forward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, long,
+                            cudaStream_t);
+int complex_modemix_backward(const float*, const float*, const float*, const float*, const float*, const float*, float*,
+                             float*, float*, float*, int, int, int, long, int, cudaStream_t);
 int adamax_step(float*, const float*, float*, float*, long, float, float, float, float, float, int, float,
                 cudaStream_t);
 
@@ -239,6 +243,18 @@ int hno_head_loss_backward(const void* tables_host, const void* tables_dev, cons
                            void* workspace, int B, int C, long P, void* stream) {
   return head_loss_backward(tables_host, tables_dev, logits_low, labels, coef, grad_loss, dlogits_low, workspace, B, C,
                             P, ST(stream));
+}
+
+int hno_complex_modemix_forward(const float* re, const float* im, const float* w_real, const float* w_imag, float* a,
+                                float* b, int B, int ci, int co, long M, void* stream) {
+  return complex_modemix_forward(re, im, w_real, w_imag, a, b, B, ci, co, M, ST(stream));
+}
+
+int hno_complex_modemix_backward(const float* da, const float* db, const float* re, const float* im,
+                                 const float* w_real, const float* w_imag, float* dre, float* dim, float* dw_real,
+                                 float* dw_imag, int B, int ci, int co, long M, int accumulate_dw, void* stream) {
+  return complex_modemix_backward(da, db, re, im, w_real, w_imag, dre, dim, dw_real, dw_imag, B, ci, co, M,
+                                  accumulate_dw, ST(stream));
 }
 
 size_t hno_ce_loss_workspace_bytes(int B) { return ce_loss_workspace_bytes(B); }

@@ -188,6 +188,133 @@ int hartley_conv_backward(const float* dout, const float* y, const float* x, con
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ complex per-mode mixing
+// Replaces the weights_type == 'individual' branch of FourierOperator._call3d (nets/fourier_operator.py:165-187, four
+// corner einsums 'oidhw,bidhw->bodhw' with weight = complex(weight_real, weight_imag)) on the retained half-spectrum
+// held as separate real / imaginary mode tensors [B][C][M] (M = 2 m0 * 2 m1 * m2, the weights' own index order):
+//     a + i b = (wr + i wi)(re + i im)   per mode, summed over input channels.
+// Bound by the weight read (2 CO CI M floats): a thread owns one (o, k) pair, k fastest, so wr / wi stream through once,
+// coalesced; the activations (a few hundred KB) are re-read from L1 / L2.  Samples in register tiles of kCmBatch.
+constexpr int kCmBatch = 4;
+
+__global__ void __launch_bounds__(128) k_cmix_fwd(const float* __restrict__ re, const float* __restrict__ im,
+                                                  const float* __restrict__ wr, const float* __restrict__ wi,
+                                                  float* __restrict__ a, float* __restrict__ b, int B, int CI, int CO,
+                                                  long M) {
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  const int o = blockIdx.y;
+  if (k >= M) return;
+  for (int b0 = 0; b0 < B; b0 += kCmBatch) {
+    float aa[kCmBatch], ab[kCmBatch];
+#pragma unroll
+    for (int bb = 0; bb < kCmBatch; ++bb) aa[bb] = ab[bb] = 0.f;
+    for (int i = 0; i < CI; ++i) {
+      const float r = __ldg(wr + ((long)o * CI + i) * M + k), q = __ldg(wi + ((long)o * CI + i) * M + k);
+#pragma unroll
+      for (int bb = 0; bb < kCmBatch; ++bb) {
+        if (b0 + bb < B) {
+          const float xr = __ldg(re + ((long)(b0 + bb) * CI + i) * M + k);
+          const float xi = __ldg(im + ((long)(b0 + bb) * CI + i) * M + k);
+          aa[bb] = fmaf(r, xr, fmaf(-q, xi, aa[bb]));
+          ab[bb] = fmaf(q, xr, fmaf(r, xi, ab[bb]));
+        }
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < kCmBatch; ++bb) {
+      if (b0 + bb < B) {
+        a[((long)(b0 + bb) * CO + o) * M + k] = aa[bb];
+        b[((long)(b0 + bb) * CO + o) * M + k] = ab[bb];
+      }
+    }
+  }
+}
+
+// d re = sum_o (wr da + wi db),  d im = sum_o (-wi da + wr db): a thread owns one (i, k) pair
+__global__ void __launch_bounds__(128) k_cmix_bwd_x(const float* __restrict__ da, const float* __restrict__ db,
+                                                    const float* __restrict__ wr, const float* __restrict__ wi,
+                                                    float* __restrict__ dre, float* __restrict__ dim_, int B, int CI,
+                                                    int CO, long M) {
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  const int i = blockIdx.y;
+  if (k >= M) return;
+  for (int b0 = 0; b0 < B; b0 += kCmBatch) {
+    float gr[kCmBatch], gi[kCmBatch];
+#pragma unroll
+    for (int bb = 0; bb < kCmBatch; ++bb) gr[bb] = gi[bb] = 0.f;
+    for (int o = 0; o < CO; ++o) {
+      const float r = __ldg(wr + ((long)o * CI + i) * M + k), q = __ldg(wi + ((long)o * CI + i) * M + k);
+#pragma unroll
+      for (int bb = 0; bb < kCmBatch; ++bb) {
+        if (b0 + bb < B) {
+          const float ga = __ldg(da + ((long)(b0 + bb) * CO + o) * M + k);
+          const float gb = __ldg(db + ((long)(b0 + bb) * CO + o) * M + k);
+          gr[bb] = fmaf(r, ga, fmaf(q, gb, gr[bb]));
+          gi[bb] = fmaf(-q, ga, fmaf(r, gb, gi[bb]));
+        }
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < kCmBatch; ++bb) {
+      if (b0 + bb < B) {
+        dre[((long)(b0 + bb) * CI + i) * M + k] = gr[bb];
+        dim_[((long)(b0 + bb) * CI + i) * M + k] = gi[bb];
+      }
+    }
+  }
+}
+
+// d wr = sum_b (da re + db im),  d wi = sum_b (-da im + db re): a thread owns one (o, i, k) triple; grid (M/128, CI, CO)
+__global__ void __launch_bounds__(128) k_cmix_bwd_w(const float* __restrict__ da, const float* __restrict__ db,
+                                                    const float* __restrict__ re, const float* __restrict__ im,
+                                                    float* __restrict__ dwr, float* __restrict__ dwi, int B, int CI,
+                                                    int CO, long M, int accumulate) {
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  const int i = blockIdx.y, o = blockIdx.z;
+  if (k >= M) return;
+  float gr = 0.f, gi = 0.f;
+  for (int bb = 0; bb < B; ++bb) {
+    const float ga = __ldg(da + ((long)bb * CO + o) * M + k), gb = __ldg(db + ((long)bb * CO + o) * M + k);
+    const float xr = __ldg(re + ((long)bb * CI + i) * M + k), xi = __ldg(im + ((long)bb * CI + i) * M + k);
+    gr = fmaf(ga, xr, fmaf(gb, xi, gr));
+    gi = fmaf(-ga, xi, fmaf(gb, xr, gi));
+  }
+  const long idx = ((long)o * CI + i) * M + k;
+  dwr[idx] = accumulate ? dwr[idx] + gr : gr;
+  dwi[idx] = accumulate ? dwi[idx] + gi : gi;
+}
+
+int complex_modemix_forward(const float* re, const float* im, const float* wr, const float* wi, float* a, float* b,
+                            int B, int ci, int co, long M, cudaStream_t st) {
+  HNO_CHECK(re && im && wr && wi && a && b, "complex_modemix_forward: null pointer");
+  HNO_CHECK(B >= 1 && ci >= 1 && co >= 1 && co <= 65535 && M >= 1, "complex_modemix_forward: bad sizes");
+  dim3 grid(ceil_div(M, 128), co);
+  k_cmix_fwd<<<grid, 128, 0, st>>>(re, im, wr, wi, a, b, B, ci, co, M);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+int complex_modemix_backward(const float* da, const float* db, const float* re, const float* im, const float* wr,
+                             const float* wi, float* dre, float* dim_, float* dwr, float* dwi, int B, int ci, int co,
+                             long M, int accumulate_dw, cudaStream_t st) {
+  HNO_CHECK(da && db && re && im && wr && wi, "complex_modemix_backward: null pointer");
+  HNO_CHECK((dre == nullptr) == (dim_ == nullptr) && (dwr == nullptr) == (dwi == nullptr),
+            "complex_modemix_backward: gradients come in (real, imaginary) pairs");
+  HNO_CHECK(B >= 1 && ci >= 1 && co >= 1 && ci <= 65535 && co <= 65535 && M >= 1,
+            "complex_modemix_backward: bad sizes");
+  if (dre) {
+    dim3 grid(ceil_div(M, 128), ci);
+    k_cmix_bwd_x<<<grid, 128, 0, st>>>(da, db, wr, wi, dre, dim_, B, ci, co, M);
+    HNO_LAUNCH_CHECK();
+  }
+  if (dwr) {
+    dim3 grid(ceil_div(M, 128), ci, co);
+    k_cmix_bwd_w<<<grid, 128, 0, st>>>(da, db, re, im, dwr, dwi, B, ci, co, M, accumulate_dw);
+    HNO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 // torch.optim.Adamax (single-tensor semantics) on a flat vector:
 //   g = grad*grad_scale + wd*p;  m = lerp(m, g, 1-b1);  u = max(b2*u, |g| + eps);  p -= lr/(1-b1^t) * m/u
 __global__ void __launch_bounds__(256) k_adamax(float* __restrict__ p, const float* __restrict__ grad,

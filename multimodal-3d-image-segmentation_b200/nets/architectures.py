@@ -41,9 +41,9 @@ class NeuralOperatorBlock(nn.Module):
             raise NotImplementedError('hno_b200 implements the SELU (self-normalising) variant only')
         if not use_conv_branch:
             raise NotImplementedError('hno_b200: NeuralOperatorBlock without the conv branch is not supported')
-        if weights_type != 'shared':
-            raise NotImplementedError("hno_b200: NeuralOperatorBlock supports weights_type='shared' only (the "
-                                      "per-mode 'individual' weights are available through HartleyOperator itself)")
+        if weights_type != 'shared' and transform_type != 'Fourier':
+            raise NotImplementedError("hno_b200: the HNOSeg block supports weights_type='shared' only (per-mode "
+                                      "'individual' weights: FourierOperator blocks, or HartleyOperator itself)")
         self.use_block_skip = use_block_skip
         op = FourierOperator if transform_type == 'Fourier' else HartleyOperator
         self.op = op(in_channels, out_channels, num_modes, use_bias=False, weights_type=weights_type, ndim=ndim,

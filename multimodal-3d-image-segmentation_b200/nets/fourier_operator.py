@@ -35,7 +35,8 @@ def _axis_sets(n, m, half):
 
 
 class FourierOperator(Module):
-    """Complex channel mixing of the retained Fourier modes; 3-D, with transform, shared weights."""
+    """Complex channel mixing of the retained Fourier modes; 3-D, with transform; 'shared' (O, I) weights or
+    'individual' per-mode weights (O, I, 2 m0, 2 m1, m2) as in experiments/config_files/config_fno.ini."""
 
     def __init__(self, in_channels, out_channels, num_modes=None, use_bias=False, weights_type='shared',
                  use_transform=True, ndim=5, device=None, dtype=None):
@@ -45,8 +46,6 @@ class FourierOperator(Module):
             raise ValueError(f'weights_type must be one of {valid}')
         if ndim != 5:
             raise NotImplementedError('hno_b200 FourierOperator supports 3-D (ndim=5) only')
-        if weights_type != 'shared':
-            raise NotImplementedError("hno_b200 FourierOperator supports weights_type='shared' only")
         if not use_transform:
             raise NotImplementedError('hno_b200 FourierOperator(use_transform=False) (complex inputs) is not supported')
         if use_bias:
@@ -64,8 +63,12 @@ class FourierOperator(Module):
             else:
                 assert len(self.num_modes) == ndim - 2
                 self.num_modes = tuple(self.num_modes)
-        self.weight_real = Parameter(torch.empty((out_channels, in_channels), device=device, dtype=dtype))
-        self.weight_imag = Parameter(torch.empty((out_channels, in_channels), device=device, dtype=dtype))
+        shape = (out_channels, in_channels)
+        if weights_type == 'individual':  # rfft keeps the non-negative frequencies of the last axis only (:67-72)
+            assert self.num_modes is not None
+            shape = shape + tuple(2 * int(m) for m in self.num_modes[:-1]) + (int(self.num_modes[-1]),)
+        self.weight_real = Parameter(torch.empty(shape, device=device, dtype=dtype))
+        self.weight_imag = Parameter(torch.empty(shape, device=device, dtype=dtype))
         self.register_parameter('bias', None)
         self._geom_cache = {}
         self.reset_parameters()
@@ -78,7 +81,12 @@ class FourierOperator(Module):
         key = (tuple(spatial), str(device))
         g = self._geom_cache.get(key)
         if g is None:
-            modes = [s // 2 if 2 * int(m) > s else int(m) for m, s in zip(self.num_modes, spatial)]
+            if self.weights_type == 'individual':  # reference :159: no clamping
+                modes = [int(m) for m in self.num_modes]
+                assert all(s >= 2 * m for m, s in zip(modes, spatial)), \
+                    f'individual weights need a grid of at least twice the modes {modes}, got {tuple(spatial)}'
+            else:
+                modes = [s // 2 if 2 * int(m) > s else int(m) for m, s in zip(self.num_modes, spatial)]
             axes = [_axis_sets(n, m, half=(a == 2)) for a, (n, m) in enumerate(zip(spatial, modes))]
             plan = get_dht_plan(tuple(spatial), [ax[1] for ax in axes], device)
             ls = [len(ax[1]) for ax in axes]
@@ -106,8 +114,11 @@ class FourierOperator(Module):
         re = ((hk + hn) * 0.5).contiguous()
         im = ((hn - hk) * 0.5).contiguous()
         wr, wi = self.weight_real, self.weight_imag
-        a = ops.PointwiseConv.apply(re, im, torch.cat([wr, -wi], 1), None, 0, False)  # Re of (wr + i wi)(re + i im)
-        b = ops.PointwiseConv.apply(re, im, torch.cat([wi, wr], 1), None, 0, False)   # Im
+        if self.weights_type == 'individual':
+            a, b = ops.ComplexModeMix.apply(re, im, wr, wi)
+        else:
+            a = ops.PointwiseConv.apply(re, im, torch.cat([wr, -wi], 1), None, 0, False)  # Re of (wr + i wi)(re + i im)
+            b = ops.PointwiseConv.apply(re, im, torch.cat([wi, wr], 1), None, 0, False)   # Im
         hp = x.new_zeros((B, self.out_channels, ls[0] * ls[1] * ls[2]))
         hp = hp.index_add(2, lin_k, (ck * (a - b) * 0.5).reshape(B, self.out_channels, -1))
         hp = hp.index_add(2, lin_n, (ck * (a + b) * 0.5).reshape(B, self.out_channels, -1))

@@ -291,6 +291,43 @@ def hartley_conv_backward(dout, y, x, weight, need_dx=True, need_dw=True, dw=Non
     return dx, dw
 
 
+class ComplexModeMix(torch.autograd.Function):
+    """(a + i b)(k) = sum_i (wr + i wi)(o, i, k) (re + i im)(i, k): per-mode complex weights of FourierOperator
+    (reference nets/fourier_operator.py:165-187, weights_type='individual') on real / imaginary mode tensors."""
+
+    @staticmethod
+    def forward(ctx, re, im, wr, wi):
+        _require_cuda(re, 're')
+        re, im, wr, wi = re.contiguous(), im.contiguous(), wr.contiguous(), wi.contiguous()
+        B, ci = re.shape[:2]
+        co = wr.shape[0]
+        M = _flat_s(re)
+        if tuple(wr.shape) != (co, ci) + tuple(re.shape[2:]) or wi.shape != wr.shape or im.shape != re.shape:
+            raise ValueError(f'individual Fourier weights {tuple(wr.shape)} do not match the retained modes '
+                             f'{tuple(re.shape)}')
+        a = torch.empty((B, co) + tuple(re.shape[2:]), dtype=torch.float32, device=re.device)
+        b = torch.empty_like(a)
+        call('hno_complex_modemix_forward', ptr(re), ptr(im), ptr(wr), ptr(wi), ptr(a), ptr(b), B, ci, co, M,
+             stream_ptr())
+        ctx.save_for_backward(re, im, wr, wi)
+        return a, b
+
+    @staticmethod
+    def backward(ctx, da, db):
+        re, im, wr, wi = ctx.saved_tensors
+        B, ci = re.shape[:2]
+        co = wr.shape[0]
+        need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        dre = torch.empty_like(re) if need_x else None
+        dim = torch.empty_like(im) if need_x else None
+        dwr = torch.empty_like(wr) if need_w else None
+        dwi = torch.empty_like(wi) if need_w else None
+        call('hno_complex_modemix_backward', ptr(da.contiguous()), ptr(db.contiguous()), ptr(re), ptr(im), ptr(wr),
+             ptr(wi), ptr(dre), ptr(dim), ptr(dwr), ptr(dwi), B, ci, co, _flat_s(re), 0, stream_ptr())
+        return dre, dim, dwr, dwi
+
+
 # ------------------------------------------------------------------------------------------ stem
 def stem_out_shape(spatial):
     return tuple(s // 2 + 1 for s in spatial)
@@ -509,7 +546,7 @@ def head_loss_backward(logits_low, labels, coef, grad_loss, tables, pitch):
 
 
 __all__ = ['dht3_forward', 'dht3_adjoint', 'TruncatedDHT', 'TruncatedIDHT', 'AddIDHTSelu', 'pwconv_forward', 'pwconv_backward',
-           'PointwiseConv', 'HartleyConv', 'stem_forward', 'stem_backward', 'StemConv', 'head_forward',
+           'PointwiseConv', 'HartleyConv', 'ComplexModeMix', 'stem_forward', 'stem_backward', 'StemConv', 'head_forward',
            'head_backward', 'HeadUpsample', 'ProbabilityLoss', 'CrossEntropyOnProbabilities', 'ce_loss_forward',
            'ce_loss_backward', 'LOSS_DEFAULT_PARAM', 'head_loss_forward', 'head_loss_backward',
            'get_crop_plan', 'get_interp_tables', 'workspace', 'LOSS_KINDS']

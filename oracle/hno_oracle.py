@@ -219,20 +219,30 @@ def hnosegxs_forward(sd, x, num_transform_blocks, num_modes, use_resize=True, us
 # HNOSeg (NeuralOperatorSeg, transform_type='Hartley')            nets/architectures.py
 # ------------------------------------------------------------------------------------------------
 def fourier_operator_with_transform(x, weight_real, weight_imag, modes):
-    """FourierOperator._call3d, shared weights, no bias (fourier_operator.py:148-211): rfftn(norm='forward'), mix the
-    four retained corners of the half-spectrum with the complex (O, I) weight, zero-pad, irfftn(norm='forward')."""
+    """FourierOperator._call3d, no bias (fourier_operator.py:148-211): rfftn(norm='forward'), mix the four retained
+    corners of the half-spectrum with the complex weight -- (O, I) shared, or (O, I, 2 m0, 2 m1, m2) 'individual' whose
+    first / last m entries per axis belong to the low / high corner (:165-187) --, zero-pad, irfftn(norm='forward')."""
     s0, s1, s2 = x.shape[2:]
-    m0, m1, m2 = (s // 2 if 2 * m > s else m for m, s in zip(modes, (s0, s1, s2)))
+    individual = weight_real.ndim == 5
+    if individual:  # :159 no clamping, the grid must hold the modes
+        m0, m1, m2 = modes
+        assert s0 >= 2 * m0 and s1 >= 2 * m1 and s2 >= 2 * m2
+    else:
+        m0, m1, m2 = (s // 2 if 2 * m > s else m for m, s in zip(modes, (s0, s1, s2)))
     f = torch.fft.rfftn(x, dim=(-3, -2, -1), norm='forward')
     w = torch.complex(weight_real, weight_imag)
     full = torch.zeros((x.shape[0], w.shape[0], s0, s1, m2), dtype=f.dtype)
-    for sd_ in (slice(0, m0), slice(s0 - m0, s0)):
-        for sh_ in (slice(0, m1), slice(s1 - m1, s1)):
-            full[:, :, sd_, sh_, :] = torch.einsum('oi,bidhw->bodhw', w, f[:, :, sd_, sh_, :m2])
+    for sd_, wd_ in ((slice(0, m0), slice(0, m0)), (slice(s0 - m0, s0), slice(m0, 2 * m0))):
+        for sh_, wh_ in ((slice(0, m1), slice(0, m1)), (slice(s1 - m1, s1), slice(m1, 2 * m1))):
+            if individual:
+                full[:, :, sd_, sh_, :] = torch.einsum('oidhw,bidhw->bodhw', w[:, :, wd_, wh_, :m2],
+                                                       f[:, :, sd_, sh_, :m2])
+            else:
+                full[:, :, sd_, sh_, :] = torch.einsum('oi,bidhw->bodhw', w, f[:, :, sd_, sh_, :m2])
     return torch.fft.irfftn(full, s=(s0, s1, s2), dim=(-3, -2, -1), norm='forward')
 
 
-def hno_block(x, sd, prefix, modes):
+def hno_block(x, sd, prefix, modes, use_block_skip=True):
     """NeuralOperatorBlock via _TransBlock.forward (architectures.py:521-548, 551-608), shared weights, SELU:
     spectral layer with its own transform pair + 1x1x1 conv branch -> SELU -> concat skip conv (or additive skip)."""
     if prefix + 'op.weight_real' in sd:  # transform_type='Fourier' (FNOSeg): no activation in the frequency domain
@@ -241,29 +251,31 @@ def hno_block(x, sd, prefix, modes):
         x1 = hartley_operator_with_transform(x, sd[prefix + 'op.weight'], modes)
     x2 = pointwise(x, sd[prefix + 'conv_branch.weight'], sd.get(prefix + 'conv_branch.bias'))
     y = selu(x1 + x2)
+    if not use_block_skip:  # config_fno.ini: the original FNO block
+        return y
     key = prefix + 'conv_concat.op.weight'
     if key in sd:
         return selu(pointwise(torch.cat([y, x], dim=1), sd[key], sd[prefix + 'conv_concat.op.bias']))
     return y + x
 
 
-def hnoseg_forward(sd, x, num_transform_blocks, num_modes, softmax=True, return_logits=False):
+def hnoseg_forward(sd, x, num_transform_blocks, num_modes, softmax=True, return_logits=False, use_block_skip=True):
     """_TransSeg.forward (architectures.py:321-353) for NeuralOperatorSeg(..., 'Hartley'), use_resize=True, no deep
     supervision."""
     image_size = x.shape[2:]
     x = selu(F.conv3d(x, sd['conv_in.op.weight'], sd['conv_in.op.bias'], stride=2, padding=1))
     x = selu(pointwise(x, sd['conv1.op.weight'], sd['conv1.op.bias']))
     for i in range(num_transform_blocks):
-        x = hno_block(x, sd, f'layers.{i}.', num_modes)
+        x = hno_block(x, sd, f'layers.{i}.', num_modes, use_block_skip)
     x = F.interpolate(x, size=tuple(image_size), mode='trilinear')
     logits = center_padcrop(pointwise(x, sd['conv_out.weight']), image_size)
     out = torch.softmax(logits, dim=1) if softmax else logits
     return (out, logits) if return_logits else out
 
 
-def hnoseg_train_step(sd, x, labels, num_transform_blocks, num_modes, loss='DiceLoss'):
+def hnoseg_train_step(sd, x, labels, num_transform_blocks, num_modes, loss='DiceLoss', use_block_skip=True):
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    probs = hnoseg_forward(params, x, num_transform_blocks, num_modes)
+    probs = hnoseg_forward(params, x, num_transform_blocks, num_modes, use_block_skip=use_block_skip)
     value = LOSSES[loss](probs, to_categorical(labels, probs.shape[1]).to(probs.dtype))
     grads = torch.autograd.grad(value, list(params.values()))
     return value.detach(), dict(zip(params.keys(), grads))

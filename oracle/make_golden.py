@@ -165,9 +165,12 @@ def case_fourier_operator():
     clamp path (modes larger than half the grid) and an even grid."""
     from nets.fourier_operator import FourierOperator
     out = {}
-    for tag, shape, modes in (('a', (9, 8, 7), (2, 3, 3)), ('b', (6, 7, 8), (5, 2, 9))):
+    for tag, shape, modes, wt in (('a', (9, 8, 7), (2, 3, 3), 'shared'), ('b', (6, 7, 8), (5, 2, 9), 'shared'),
+                                  ('c', (9, 8, 7), (2, 4, 3), 'individual'), ('d', (8, 13, 6), (4, 2, 3), 'individual')):
         torch.manual_seed(31)
-        op = FourierOperator(8, 8, modes)  # channel counts the CUDA pointwise kernels are instantiated for
+        # 8 channels: what the CUDA pointwise kernels are instantiated for.  'c' / 'd': per-mode complex weights
+        # (config_fno.ini), incl. axes that the two corners fill exactly (n == 2m)
+        op = FourierOperator(8, 8, modes, weights_type=wt)
         x = torch.randn(2, 8, *shape, requires_grad=True)
         y = op(x)
         w = torch.randn(y.shape)
@@ -181,12 +184,13 @@ def case_fourier_operator():
     save('fourier_operator', **out)
 
 
-def case_hnoseg(transform_type='Hartley', name='hnoseg_small'):
+def case_hnoseg(transform_type='Hartley', name='hnoseg_small', **extra):
     """NeuralOperatorSeg(transform_type='Hartley') = HNOSeg / ('Fourier') = FNOSeg: small model,
     forward + Dice gradients."""
     torch.manual_seed(21)
     cfg = dict(in_channels=2, out_channels=3, filters=8, num_transform_blocks=3, num_modes=(2, 3, 3),
-               transform_type=transform_type)
+               transform_type=transform_type, **extra)
+    skip = extra.get('use_block_skip', True)
     model = ref.NeuralOperatorSeg(**cfg)
     torch.manual_seed(22)
     x = torch.randn(2, 2, 18, 16, 13)
@@ -196,7 +200,8 @@ def case_hnoseg(transform_type='Hartley', name='hnoseg_small'):
     probs = model(x)
     hook.remove()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
-    o_probs, o_logits = orc.hnoseg_forward(sd, x, cfg['num_transform_blocks'], cfg['num_modes'], return_logits=True)
+    o_probs, o_logits = orc.hnoseg_forward(sd, x, cfg['num_transform_blocks'], cfg['num_modes'], return_logits=True,
+                                           use_block_skip=skip)
     check('HNOSeg probs', o_probs, probs.detach())
     check('HNOSeg logits', o_logits, logits['v'])
     out = {'x': x.numpy(), 'labels': labels.numpy().astype(np.uint8), 'probs': probs.detach().numpy(),
@@ -207,7 +212,8 @@ def case_hnoseg(transform_type='Hartley', name='hnoseg_small'):
     loss = ref_losses.DiceLoss()(model(x), onehot)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
-    o_loss, o_grads = orc.hnoseg_train_step(sd, x, labels, cfg['num_transform_blocks'], cfg['num_modes'], 'DiceLoss')
+    o_loss, o_grads = orc.hnoseg_train_step(sd, x, labels, cfg['num_transform_blocks'], cfg['num_modes'], 'DiceLoss',
+                                            use_block_skip=skip)
     check('HNOSeg DiceLoss value', o_loss, loss.detach(), 1e-6)
     for k in grads:
         check(f'HNOSeg DiceLoss grad {k}', o_grads[k], grads[k], 2e-4)
@@ -276,6 +282,8 @@ if __name__ == '__main__':
     case_hnoseg()
     case_fourier_operator()
     case_hnoseg('Fourier', 'fnoseg_small')
+    # config_fno.ini: the original FNO (per-mode complex weights, biased conv branch, no block skip)
+    case_hnoseg('Fourier', 'fno_small', weights_type='individual', use_bias_conv_branch=True, use_block_skip=False)
     if args.full:
         case_full()
     print('all oracle-vs-reference checks passed')

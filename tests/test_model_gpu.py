@@ -219,9 +219,11 @@ def test_fourier_operator_against_reference_fixture(cuda, golden_dir):
     the clamp path (modes > half the grid) on an even grid."""
     from multimodal_3d_image_segmentation_b200 import nets
     g = dict(np.load(os.path.join(golden_dir, 'fourier_operator.npz')))
-    for tag in ('a', 'b'):
+    for tag in ('a', 'b', 'c', 'd'):  # c, d: per-mode ('individual') complex weights, incl. axes with n == 2m
         modes = tuple(int(v) for v in g[f'{tag}/modes'])
-        op = nets.FourierOperator(8, 8, modes, device=cuda)
+        wt = 'individual' if g[f'{tag}/wr'].ndim == 5 else 'shared'
+        op = nets.FourierOperator(8, 8, modes, weights_type=wt, device=cuda)
+        assert tuple(op.weight_real.shape) == g[f'{tag}/wr'].shape
         with torch.no_grad():
             op.weight_real.copy_(torch.from_numpy(g[f'{tag}/wr']))
             op.weight_imag.copy_(torch.from_numpy(g[f'{tag}/wi']))
@@ -253,6 +255,50 @@ def test_fnoseg_against_reference_fixture(cuda, golden_dir):
     for k, p in model.named_parameters():
         ref = g[f'DiceLoss/grad/{k}']
         assert rel(p.grad, ref) < 2e-4, (k, rel(p.grad, ref))
+
+
+def test_fno_individual_weights_against_reference_fixture(cuda, golden_dir):
+    """experiments/config_files/config_fno.ini in small: NeuralOperatorSeg('Fourier', weights_type='individual',
+    use_bias_conv_branch=True, use_block_skip=False) against outputs and Dice gradients of the real reference."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'fno_small.npz')))
+    model = nets.NeuralOperatorSeg(2, 3, 8, 3, (2, 3, 3), 'Fourier', weights_type='individual',
+                                   use_bias_conv_branch=True, use_block_skip=False, device=cuda)
+    sd = _sd(g, 'sd/')
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(sd)
+    x = torch.from_numpy(g['x']).to(cuda)
+    labels = torch.from_numpy(g['labels'].astype(np.int64))
+    probs = model(x)
+    assert rel(probs, g['probs']) < 1e-5
+    loss = nets.custom_losses.DiceLoss()(probs, orc.to_categorical(labels, 3).to(cuda))
+    loss.backward()
+    assert abs(float(loss) - float(g['DiceLoss/loss'])) < 2e-6
+    for k, p in model.named_parameters():
+        ref = g[f'DiceLoss/grad/{k}']
+        assert rel(p.grad, ref) < 2e-4, (k, rel(p.grad, ref))
+    with pytest.raises(AssertionError):  # reference fourier_operator.py:159: the grid must hold the modes
+        nets.FourierOperator(8, 8, (6, 3, 3), weights_type='individual', device=cuda)(
+            torch.zeros(1, 8, 10, 9, 7, device=cuda))
+
+
+def test_complex_modemix_sizes(cuda):
+    """hno_complex_modemix_* for channel counts / batch sizes off the register-tile multiples, against einsum in fp64."""
+    from multimodal_3d_image_segmentation_b200 import ops
+    gen = torch.Generator().manual_seed(17)
+    for B, ci, co, shape in ((1, 3, 5, (4, 6, 3)), (5, 24, 24, (8, 12, 6)), (9, 7, 2, (2, 2, 67))):
+        re, im = (torch.randn(B, ci, *shape, generator=gen) for _ in range(2))
+        wr, wi = (torch.randn(co, ci, *shape, generator=gen) for _ in range(2))
+        ga, gb = (torch.randn(B, co, *shape, generator=gen) for _ in range(2))
+        t64 = [t.double().requires_grad_(True) for t in (re, im, wr, wi)]
+        yc = torch.einsum('oidhw,bidhw->bodhw', torch.complex(t64[2], t64[3]), torch.complex(t64[0], t64[1]))
+        (yc.real * ga.double() + yc.imag * gb.double()).sum().backward()
+        tc = [t.to(cuda).requires_grad_(True) for t in (re, im, wr, wi)]
+        a, b = ops.ComplexModeMix.apply(*tc)
+        (a * ga.to(cuda) + b * gb.to(cuda)).sum().backward()
+        assert rel(a, yc.real) < 1e-6 and rel(b, yc.imag) < 1e-6
+        for u, v in zip(tc, t64):
+            assert rel(u.grad, v.grad) < 1e-6
 
 
 def test_fourier_layer_baseline_grid_against_oracle(cuda):

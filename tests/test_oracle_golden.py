@@ -111,7 +111,7 @@ def test_hnoseg_fixture(golden_dir):
 def test_fourier_fixtures(golden_dir):
     """FourierOperator and NeuralOperatorSeg(transform_type='Fourier') = FNOSeg, recorded from the real reference."""
     g = _load(golden_dir, 'fourier_operator')
-    for tag in ('a', 'b'):
+    for tag in ('a', 'b', 'c', 'd'):  # c, d: per-mode ('individual') complex weights
         y = orc.fourier_operator_with_transform(torch.from_numpy(g[f'{tag}/x']), torch.from_numpy(g[f'{tag}/wr']),
                                                 torch.from_numpy(g[f'{tag}/wi']), tuple(int(v) for v in g[f'{tag}/modes']))
         _close(y, g[f'{tag}/y'])
@@ -120,3 +120,16 @@ def test_fourier_fixtures(golden_dir):
     probs, logits = orc.hnoseg_forward(sd, torch.from_numpy(g['x']), 3, (2, 3, 3), return_logits=True)
     _close(probs, g['probs'])
     _close(logits, g['logits'])
+    # experiments/config_files/config_fno.ini in small: individual weights, biased conv branch, no block skip
+    g = _load(golden_dir, 'fno_small')
+    sd = _sd(g, 'sd/')
+    assert tuple(sd['layers.0.op.weight_real'].shape) == (8, 8, 4, 6, 3) and 'layers.0.conv_concat.op.weight' not in sd
+    probs, logits = orc.hnoseg_forward(sd, torch.from_numpy(g['x']), 3, (2, 3, 3), return_logits=True,
+                                       use_block_skip=False)
+    _close(probs, g['probs'])
+    _close(logits, g['logits'])
+    loss, grads = orc.hnoseg_train_step(sd, torch.from_numpy(g['x']), torch.from_numpy(g['labels'].astype(np.int64)), 3,
+                                        (2, 3, 3), 'DiceLoss', use_block_skip=False)
+    _close(loss, g['DiceLoss/loss'], 1e-6)
+    for k, v in grads.items():
+        _close(v, g[f'DiceLoss/grad/{k}'], 2e-4)
