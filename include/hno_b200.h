@@ -203,6 +203,23 @@ int hno_ce_loss_backward(const float* y_pred, const float* y_true, const uint8_t
                          const float* grad_loss, float* dy_pred, int B, int C, long N, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input side of the step on the device
+ *   hno_to_categorical        replaces experiments/utils.py:74-97 (called at train_test.py:152, :197):
+ *     labels [B][N] (label_bytes 1 = uint8, 8 = int64) -> onehot fp32 [B][C][N] (dense channel-first;
+ *     the reference returns the same values as a channels-last view).  bad_count (device int, may be
+ *     NULL) receives the number of labels outside [0, C) -- the reference raises IndexError on those.
+ *   hno_normalize_modalities  replaces experiments/utils.py:25-71 (x_processing, run.py:52-55):
+ *     data [rows][n] fp32, one modality per row: optional np.clip(clip_lo, clip_hi), mean and
+ *     population std over the voxels whose CLIPPED value differs from mask_val (all voxels without
+ *     a mask), out = (x - mean) / std, masked voxels = 0.  out must not alias data.
+ * ------------------------------------------------------------------------------------------ */
+int hno_to_categorical(const void* labels, int label_bytes, float* onehot, int* bad_count, int B, int C, long N,
+                       void* stream);
+size_t hno_normalize_workspace_bytes(int rows);
+int hno_normalize_modalities(const float* data, float* out, void* workspace, int rows, long n, int has_mask,
+                             float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused Adamax step on a flat parameter vector (torch.optim.Adamax semantics, the optimizer of
  * experiments/config_files/config_hnoseg_xs.ini:53-55).  step is 1-based.
  * ------------------------------------------------------------------------------------------ */

@@ -18,7 +18,7 @@ __version__ = '0.1.0'
 
 def __getattr__(name):
     # lazy: importing the package must not require torch.cuda
-    if name in ('nets', 'ops', 'plan', 'engine', 'parallel'):
+    if name in ('nets', 'ops', 'plan', 'engine', 'parallel', 'experiments'):
         import importlib
         return importlib.import_module(f'{__name__}.{name}')
     raise AttributeError(name)

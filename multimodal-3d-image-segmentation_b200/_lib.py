@@ -62,6 +62,9 @@ SIGNATURES = {
     'hno_ce_loss_workspace_bytes': (_Z, [_I]),
     'hno_ce_loss_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P]),
     'hno_ce_loss_backward': (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    'hno_to_categorical': (_I, [_P, _I, _P, _P, _I, _I, _L, _P]),
+    'hno_normalize_workspace_bytes': (_Z, [_I]),
+    'hno_normalize_modalities': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
     'hno_adamax_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 

@@ -80,6 +80,9 @@ int complex_modemix_forward(const float*, const float*, const float*, const floa
                             cudaStream_t);
 int complex_modemix_backward(const float*, const float*, const float*, const float*, const float*, const float*, float*,
                              float*, float*, float*, int, int, int, long, int, cudaStream_t);
+int to_categorical(const void*, int, float*, int*, int, int, long, cudaStream_t);
+size_t normalize_workspace_bytes(int);
+int normalize_modalities(const float*, float*, void*, int, long, int, float, int, float, float, cudaStream_t);
 int adamax_step(float*, const float*, float*, float*, long, float, float, float, float, float, int, float,
                 cudaStream_t);
 
@@ -267,6 +270,19 @@ int hno_ce_loss_forward(const float* y_pred, const float* y_true, const uint8_t*
 int hno_ce_loss_backward(const float* y_pred, const float* y_true, const uint8_t* labels, const float* grad_loss,
                          float* dy_pred, int B, int C, long N, void* stream) {
   return ce_loss_backward(y_pred, y_true, labels, grad_loss, dy_pred, B, C, N, ST(stream));
+}
+
+int hno_to_categorical(const void* labels, int label_bytes, float* onehot, int* bad_count, int B, int C, long N,
+                       void* stream) {
+  return to_categorical(labels, label_bytes, onehot, bad_count, B, C, N, ST(stream));
+}
+
+size_t hno_normalize_workspace_bytes(int rows) { return normalize_workspace_bytes(rows); }
+
+int hno_normalize_modalities(const float* data, float* out, void* workspace, int rows, long n, int has_mask,
+                             float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream) {
+  return normalize_modalities(data, out, workspace, rows, n, has_mask, mask_val, has_clip, clip_lo, clip_hi,
+                              ST(stream));
 }
 
 int hno_adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, long n, float lr, float beta1,

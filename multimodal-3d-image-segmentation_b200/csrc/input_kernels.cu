@@ -1,0 +1,200 @@
+// Input side of the training step on the device, sm_100a: the two array transforms that sit between the
+// loader and the network in the reference.
+//
+//   to_categorical          experiments/utils.py:74-97   integer labels (B,1,D,H,W) -> one-hot fp32 (B,C,D,H,W)
+//                           (called every step at train_test.py:152 / :197 on the device tensor)
+//   normalize_modalities    experiments/utils.py:25-71   per modality: optional clip, mean / std over the voxels that
+//                           differ from mask_val (after clipping), (x - mean) / std, masked voxels -> 0
+//                           (x_processing of the loader, experiments/run.py:52-55: mask_val = 0 by default)
+//
+// Both are HBM-bound streaming passes: labels are read once as uchar4 / int64 and the C one-hot planes written with
+// 16-byte stores; the normalisation is one moments pass (count, sum, sum of squares in fp64 block partials) and one apply
+// pass, i.e. 2 reads + 1 write of the volume (the numpy original makes ~8 passes and a masked-array copy).
+#include "common.cuh"
+#include "hno_b200.h"
+
+#include <stdint.h>
+
+namespace hno {
+
+// ------------------------------------------------------------------------------------------ to_categorical
+template <int V>
+__global__ void __launch_bounds__(256) k_to_categorical_u8(const uint8_t* __restrict__ lab, float* __restrict__ out,
+                                                           int* __restrict__ bad, int C, long N) {
+  const long b = blockIdx.y;
+  const uint8_t* l = lab + b * N;
+  float* o = out + b * C * N;
+  int nbad = 0;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < N / V; i += (long)gridDim.x * 256L) {
+    if (V == 4) {
+      const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(l) + i);
+      nbad += (q.x >= C) + (q.y >= C) + (q.z >= C) + (q.w >= C);
+      for (int c = 0; c < C; ++c)
+        reinterpret_cast<float4*>(o + c * N)[i] =
+            make_float4(q.x == c ? 1.f : 0.f, q.y == c ? 1.f : 0.f, q.z == c ? 1.f : 0.f, q.w == c ? 1.f : 0.f);
+    } else {
+      const int q = (int)__ldg(l + i);
+      nbad += q >= C;
+      for (int c = 0; c < C; ++c) o[c * N + i] = q == c ? 1.f : 0.f;
+    }
+  }
+  if (bad && nbad) atomicAdd(bad, nbad);
+}
+
+__global__ void __launch_bounds__(256) k_to_categorical_i64(const long long* __restrict__ lab, float* __restrict__ out,
+                                                            int* __restrict__ bad, int C, long N) {
+  const long b = blockIdx.y;
+  const long long* l = lab + b * N;
+  float* o = out + b * C * N;
+  int nbad = 0;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < N; i += (long)gridDim.x * 256L) {
+    const long long q = __ldg(l + i);
+    nbad += q < 0 || q >= C;
+    for (int c = 0; c < C; ++c) o[c * N + i] = q == c ? 1.f : 0.f;
+  }
+  if (bad && nbad) atomicAdd(bad, nbad);
+}
+
+int to_categorical(const void* labels, int label_bytes, float* onehot, int* bad_count, int B, int C, long N,
+                   cudaStream_t st) {
+  HNO_CHECK(labels && onehot, "to_categorical: null pointer");
+  HNO_CHECK(label_bytes == 1 || label_bytes == 8, "to_categorical: labels must be uint8 or int64");
+  HNO_CHECK(B >= 1 && B <= 65535 && C >= 1 && N >= 1, "to_categorical: bad sizes");
+  HNO_CHECK(label_bytes == 8 || C <= 256, "to_categorical: uint8 labels cannot address %d classes", C);
+  if (bad_count) HNO_CUDA(cudaMemsetAsync(bad_count, 0, sizeof(int), st));
+  const bool v4 = label_bytes == 1 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(labels) & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(onehot) & 15) == 0;
+  const long items = v4 ? N / 4 : N;
+  dim3 grid((unsigned)((items + 255) / 256 < 1184 ? (items + 255) / 256 : 1184), B);
+  if (label_bytes == 8)
+    k_to_categorical_i64<<<grid, 256, 0, st>>>(static_cast<const long long*>(labels), onehot, bad_count, C, N);
+  else if (v4)
+    k_to_categorical_u8<4><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(labels), onehot, bad_count, C, N);
+  else
+    k_to_categorical_u8<1><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(labels), onehot, bad_count, C, N);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ normalize_modalities
+constexpr int kNormChunks = 296;
+
+struct NormArgs {
+  int has_mask, has_clip;
+  float mask_val, clip_lo, clip_hi;
+};
+
+__device__ __forceinline__ float norm_clip(float v, const NormArgs& a) {
+  return a.has_clip ? fminf(fmaxf(v, a.clip_lo), a.clip_hi) : v;  // np.clip
+}
+
+// grid (chunks, rows): partials [rows][chunks][3] = (count, sum, sum of squares) of the unmasked, clipped voxels
+template <int V>
+__global__ void __launch_bounds__(256) k_norm_moments(const float* __restrict__ x, double* __restrict__ partials, long n,
+                                                      NormArgs a) {
+  __shared__ double sred[8][3];
+  const float* p = x + (long)blockIdx.y * n;
+  float s = 0.f, ss = 0.f;
+  double cnt = 0.0, sd = 0.0, ssd = 0.0;
+  int c32 = 0, run = 0;
+  auto add = [&](float v) {
+    v = norm_clip(v, a);
+    if (!(a.has_mask && v == a.mask_val)) {
+      s += v;
+      ss = fmaf(v, v, ss);
+      ++c32;
+    }
+  };
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n / V; i += (long)gridDim.x * 256L) {
+    if (V == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+      add(q.x), add(q.y), add(q.z), add(q.w);
+    } else {
+      add(__ldg(p + i));
+    }
+    if (++run == 32 / V) {  // bounded fp32 run length (raw intensities reach 1e3 - 1e4), then into fp64
+      sd += (double)s, ssd += (double)ss, cnt += (double)c32;
+      s = ss = 0.f, c32 = 0, run = 0;
+    }
+  }
+  double m[3] = {cnt + (double)c32, sd + (double)s, ssd + (double)ss};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m[k] = warp_sum_d(m[k]);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sred[threadIdx.x >> 5][k] = m[k];
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sred[w][threadIdx.x];
+    partials[((long)blockIdx.y * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
+  }
+}
+
+// one warp per row: mean and (population, ddof = 0) standard deviation as fp32, like numpy's float32 result
+__global__ void __launch_bounds__(32) k_norm_finalize(const double* __restrict__ partials, int chunks,
+                                                      float* __restrict__ stats) {
+  const int row = blockIdx.x;
+  double m[3] = {0.0, 0.0, 0.0};
+  for (int ch = threadIdx.x; ch < chunks; ch += 32)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) m[k] += partials[((long)row * chunks + ch) * 3 + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m[k] = warp_sum_d(m[k]);
+  if (threadIdx.x == 0) {
+    const double mean = m[0] > 0.0 ? m[1] / m[0] : 0.0;
+    const double var = m[0] > 0.0 ? fmax(m[2] / m[0] - mean * mean, 0.0) : 0.0;
+    stats[row * 2 + 0] = (float)mean;
+    stats[row * 2 + 1] = (float)sqrt(var);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) k_norm_apply(const float* __restrict__ x, float* __restrict__ out,
+                                                    const float* __restrict__ stats, long n, NormArgs a) {
+  const float* p = x + (long)blockIdx.y * n;
+  float* o = out + (long)blockIdx.y * n;
+  const float mean = stats[blockIdx.y * 2 + 0], sd = stats[blockIdx.y * 2 + 1];
+  auto f = [&](float v) {
+    v = norm_clip(v, a);
+    return (a.has_mask && v == a.mask_val) ? 0.f : (v - mean) / sd;  // true division, as numpy
+  };
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n / V; i += (long)gridDim.x * 256L) {
+    if (V == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+      reinterpret_cast<float4*>(o)[i] = make_float4(f(q.x), f(q.y), f(q.z), f(q.w));
+    } else {
+      o[i] = f(__ldg(p + i));
+    }
+  }
+}
+
+size_t normalize_workspace_bytes(int rows) {
+  return (size_t)rows * kNormChunks * 3 * sizeof(double) + (size_t)rows * 2 * sizeof(float) + 256;
+}
+
+int normalize_modalities(const float* data, float* out, void* ws, int rows, long n, int has_mask, float mask_val,
+                         int has_clip, float clip_lo, float clip_hi, cudaStream_t st) {
+  HNO_CHECK(data && out && ws, "normalize_modalities: null pointer");
+  HNO_CHECK(rows >= 1 && rows <= 65535 && n >= 1, "normalize_modalities: bad sizes");
+  HNO_CHECK(!has_clip || clip_lo <= clip_hi, "normalize_modalities: clip_val must be (min, max)");
+  double* partials = reinterpret_cast<double*>(ws);
+  float* stats = reinterpret_cast<float*>(partials + (size_t)rows * kNormChunks * 3);
+  const NormArgs a{has_mask, has_clip, mask_val, clip_lo, clip_hi};
+  const bool v4 = n % 4 == 0 && ((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const long items = v4 ? n / 4 : n;
+  const int chunks = (int)((items + 255) / 256 < kNormChunks ? (items + 255) / 256 : kNormChunks);
+  dim3 g1(chunks, rows);
+  if (v4) k_norm_moments<4><<<g1, 256, 0, st>>>(data, partials, n, a);
+  else k_norm_moments<1><<<g1, 256, 0, st>>>(data, partials, n, a);
+  HNO_LAUNCH_CHECK();
+  k_norm_finalize<<<rows, 32, 0, st>>>(partials, chunks, stats);
+  HNO_LAUNCH_CHECK();
+  dim3 g2((unsigned)((items + 255) / 256 < 1184 ? (items + 255) / 256 : 1184), rows);
+  if (v4) k_norm_apply<4><<<g2, 256, 0, st>>>(data, out, stats, n, a);
+  else k_norm_apply<1><<<g2, 256, 0, st>>>(data, out, stats, n, a);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace hno

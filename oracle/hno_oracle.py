@@ -291,6 +291,25 @@ def to_categorical(y, num_classes):
     return onehot.movedim(-1, 1).to(torch.float32)
 
 
+def normalize_modalities(data, mask_val=None, clip_val=None):
+    """experiments/utils.py:25-71 in numpy: per modality (first axis) clip, masked mean / population std, (x - mean) / std,
+    masked voxels (clipped value == mask_val) -> 0.  Statistics in float64 here (numpy's own float32 pairwise sums differ
+    from this by ~1e-7 relative; make_golden.py checks the two against each other)."""
+    out = []
+    for da in np.asarray(data, dtype=np.float32):
+        if clip_val is not None:
+            da = np.clip(da, *clip_val)
+        keep = np.ones(da.shape, bool) if mask_val is None else da != np.float32(mask_val)
+        vals = da[keep].astype(np.float64)
+        if vals.size == 0:
+            out.append(np.zeros_like(da))
+            continue
+        mean, std = np.float32(vals.mean()), np.float32(vals.std())
+        with np.errstate(divide='ignore', invalid='ignore'):
+            out.append(np.where(keep, (da - mean) / std, np.float32(0)).astype(np.float32))
+    return np.stack(out)
+
+
 def dice_loss(y_pred, y_true):
     """custom_losses.py:73-111."""
     dims = tuple(range(2, y_true.ndim))

@@ -238,6 +238,45 @@ def case_losses():
     save('losses', **out)
 
 
+def _reference_experiments_utils():
+    """experiments/utils.py needs SimpleITK and torchinfo at import time (absent here); only its two array
+    helpers matter, so the module is loaded by path with those two imports stubbed."""
+    import importlib.util
+    import types
+    for name in ('SimpleITK', 'torchinfo'):
+        if name not in sys.modules:
+            stub = types.ModuleType(name)
+            stub.summary = None
+            sys.modules[name] = stub
+    spec = importlib.util.spec_from_file_location('_ref_experiments_utils', os.path.join('/root/reference', 'experiments', 'utils.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def case_input_side():
+    """to_categorical / normalize_modalities recorded from the reference's experiments/utils.py."""
+    ru = _reference_experiments_utils()
+    rng = np.random.default_rng(41)
+    out = {}
+    labels = torch.from_numpy(rng.integers(0, 4, (2, 1, 6, 5, 7)))
+    onehot = ru.to_categorical(labels, 4)
+    assert torch.equal(orc.to_categorical(labels, 4), onehot)
+    out['labels'] = labels.numpy().astype(np.uint8)
+    out['onehot'] = np.ascontiguousarray(onehot.numpy())
+    # BraTS-like intensities: background exactly 0, tissue in the hundreds / thousands, four modalities of different scale
+    vol = rng.gamma(4.0, 150.0, (4, 9, 10, 11)).astype(np.float32) * np.array([1, 0.5, 3, 0.1], np.float32).reshape(4, 1, 1, 1)
+    vol[:, :2] = 0
+    vol[:, :, :, -3:] = 0
+    out['vol'] = vol
+    for tag, kw in (('plain', {}), ('mask', dict(mask_val=0)), ('clip', dict(clip_val=(50.0, 900.0))),
+                    ('maskclip', dict(mask_val=0, clip_val=(0.0, 700.0))), ('maskhit', dict(mask_val=700, clip_val=(0.0, 700.0)))):
+        y = ru.normalize_modalities(vol, **kw)
+        check(f'normalize_modalities {tag}', torch.from_numpy(orc.normalize_modalities(vol, **kw)), torch.from_numpy(y), 1e-5)
+        out[f'norm/{tag}'] = y
+    save('input_side', **out)
+
+
 def case_full():
     """BASELINE config 1: HNOSegXS(4,4,24,[3]*8,(10,14,14)) on one 1x4x240x240x155 volume."""
     torch.manual_seed(0)
@@ -278,6 +317,7 @@ if __name__ == '__main__':
     case_operator()
     case_block()
     case_losses()
+    case_input_side()
     case_model()
     case_hnoseg()
     case_fourier_operator()

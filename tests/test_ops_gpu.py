@@ -391,3 +391,56 @@ def test_modechain_matches_layerwise(cuda, C, L, M, B):
     assert ((dz0.cpu().double() - grads[0]).norm() / grads[0].norm()).item() < 1e-5
     for l in range(L):
         assert ((dws[l].cpu().double() - grads[1 + l]).norm() / grads[1 + l].norm()).item() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- input side (8f-4)
+def test_to_categorical(cuda, golden_dir):
+    from multimodal_3d_image_segmentation_b200.experiments import to_categorical
+    g = dict(np.load(os.path.join(golden_dir, 'input_side.npz')))
+    for dt in (torch.uint8, torch.int64, torch.int32, torch.float32):  # train_test.py feeds whatever the loader yields
+        y = to_categorical(torch.from_numpy(g['labels']).to(cuda).to(dt), 4)
+        assert y.dtype == torch.float32 and y.is_contiguous() and np.array_equal(y.cpu().numpy(), g['onehot'])
+    gen = torch.Generator().manual_seed(18)
+    for shape, C in (((2, 1, 24, 20, 31), 4), ((1, 1, 5, 3, 7), 2), ((3, 1, 16, 16, 16), 7)):  # N % 4 != 0 and == 0
+        lab = torch.randint(0, C, shape, generator=gen)
+        ref = orc.to_categorical(lab, C)
+        for dt in (torch.uint8, torch.int64):
+            assert torch.equal(to_categorical(lab.to(dt).to(cuda), C).cpu(), ref)
+        assert torch.equal(to_categorical(lab.to(torch.uint8).to(cuda)).cpu(), orc.to_categorical(lab, int(lab.max()) + 1))
+    with pytest.raises(IndexError):  # the reference's scatter raises on labels >= num_classes
+        to_categorical(torch.full((1, 1, 4, 4, 4), 5, dtype=torch.uint8, device=cuda), 4)
+    with pytest.raises(IndexError):
+        to_categorical(torch.full((1, 1, 4, 4, 3), -1, dtype=torch.int64, device=cuda), 4)
+    with pytest.raises(RuntimeError):
+        to_categorical(torch.zeros(1, 1, 4, 4, 4, dtype=torch.uint8), 4)
+    # feeds the drop-in losses exactly like train_test.py:152-160
+    from multimodal_3d_image_segmentation_b200 import nets
+    p = torch.softmax(torch.randn(2, 4, 24, 20, 31, generator=gen), 1)
+    lab = torch.randint(0, 4, (2, 1, 24, 20, 31), generator=gen)
+    loss = nets.custom_losses.PCCLoss()(p.to(cuda), to_categorical(lab.to(cuda), 4))
+    assert abs(float(loss) - float(orc.pcc_loss(p.double(), orc.to_categorical(lab, 4).double()))) < 1e-6
+
+
+def test_normalize_modalities(cuda, golden_dir):
+    from multimodal_3d_image_segmentation_b200.experiments import normalize_modalities
+    g = dict(np.load(os.path.join(golden_dir, 'input_side.npz')))
+    cases = {'plain': {}, 'mask': dict(mask_val=0), 'clip': dict(clip_val=(50.0, 900.0)),
+             'maskclip': dict(mask_val=0, clip_val=(0.0, 700.0)), 'maskhit': dict(mask_val=700, clip_val=(0.0, 700.0))}
+    vol = torch.from_numpy(g['vol']).to(cuda)
+    for tag, kw in cases.items():
+        y = normalize_modalities(vol, **kw)
+        assert y.dtype == torch.float32 and float((y.cpu() - torch.from_numpy(g[f'norm/{tag}'])).abs().max()) < 1e-5, tag
+    # BraTS-shaped volume (4 x 155 x 240 x 240, background 0) against the numpy oracle; int16 input as SimpleITK yields
+    rng = np.random.default_rng(19)
+    big = rng.gamma(4.0, 150.0, (4, 155, 240, 240)).astype(np.float32)
+    big *= (rng.random((1, 155, 240, 240)) < 0.4)
+    big = np.round(big).astype(np.int16)
+    ref = orc.normalize_modalities(big, mask_val=0)
+    y = normalize_modalities(torch.from_numpy(big).to(cuda), mask_val=0).cpu().numpy()
+    assert np.abs(y - ref).max() < 2e-5
+    assert np.all(y[big == 0] == 0) and abs(float(y[0][big[0] != 0].mean())) < 1e-4
+    # ragged length (n % 4 != 0), an all-background modality
+    odd = rng.normal(100.0, 20.0, (3, 5, 7, 9)).astype(np.float32)
+    odd[1] = 0
+    y = normalize_modalities(torch.from_numpy(odd).to(cuda), mask_val=0).cpu().numpy()
+    assert np.abs(y - orc.normalize_modalities(odd, mask_val=0)).max() < 1e-5 and np.all(y[1] == 0)

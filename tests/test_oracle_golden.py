@@ -133,3 +133,15 @@ def test_fourier_fixtures(golden_dir):
     _close(loss, g['DiceLoss/loss'], 1e-6)
     for k, v in grads.items():
         _close(v, g[f'DiceLoss/grad/{k}'], 2e-4)
+
+
+def test_input_side_fixtures(golden_dir):
+    """to_categorical / normalize_modalities restatements against outputs of the reference's experiments/utils.py."""
+    g = _load(golden_dir, 'input_side')
+    onehot = orc.to_categorical(torch.from_numpy(g['labels'].astype(np.int64)), 4)
+    assert np.array_equal(onehot.numpy(), g['onehot'])
+    cases = {'plain': {}, 'mask': dict(mask_val=0), 'clip': dict(clip_val=(50.0, 900.0)),
+             'maskclip': dict(mask_val=0, clip_val=(0.0, 700.0)), 'maskhit': dict(mask_val=700, clip_val=(0.0, 700.0))}
+    for tag, kw in cases.items():
+        y = orc.normalize_modalities(g['vol'], **kw)
+        assert y.dtype == np.float32 and np.abs(y - g[f'norm/{tag}']).max() < 1e-5, tag

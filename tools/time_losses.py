@@ -1,4 +1,4 @@
-"""Times the stand-alone loss kernels at the BASELINE volume size (2 x 4 x 240 x 240 x 155) with CUDA events.
+"""Times the stand-alone loss and input-side kernels at the BASELINE volume size (2 x 4 x 240 x 240 x 155) with CUDA events.
 Algorithmic bytes: moments pass P + P (one-hot floats), CE forward P + T, CE backward P + T + P, T = one-hot floats (P)
 or uint8 labels (P / 16).  Usage: python tools/time_losses.py [out.json]"""
 import json
@@ -45,6 +45,14 @@ def main():
     for name in ('DiceLoss', 'PCCLoss', 'ExpDiceLoss'):
         fn = getattr(nets.custom_losses, name)()
         add(name + '_fwd_onehot', timed(lambda: fn(p, onehot)), 2 * P)
+    # input side: one-hot from uint8 labels (reads L, writes P), modality normalisation of one
+    # 4 x 155 x 240 x 240 sample with the background masked (2 reads + 1 write of the 142.8 MB volume)
+    from multimodal_3d_image_segmentation_b200.experiments import normalize_modalities, to_categorical
+    lab5 = lab[:, None]
+    add('to_categorical_u8', timed(lambda: to_categorical(lab5, C, validate=False)), P + L)
+    vol = torch.rand(4, 155, 240, 240, device=dev) * 1000
+    vol *= (torch.rand(1, 155, 240, 240, device=dev) < 0.4)
+    add('normalize_modalities_mask0', timed(lambda: normalize_modalities(vol, mask_val=0)), 3 * vol.numel() * 4)
     print(json.dumps(rows, indent=1))
     if len(sys.argv) > 1:
         json.dump(rows, open(sys.argv[1], 'w'), indent=1)
