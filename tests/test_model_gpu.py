@@ -135,7 +135,8 @@ def test_training_step_gradients_against_fp64_oracle(cuda, golden_dir):
         assert rel(p.grad, o_grads[k]) < 5e-3, k
 
 
-def test_trainer_cuda_graph_matches_eager(cuda):
+@pytest.mark.parametrize('lname', ['DiceLoss', 'ExpDiceLoss', 'CrossEntropyLoss'])
+def test_trainer_cuda_graph_matches_eager(cuda, lname):
     """Trainer.step replayed from a CUDA graph (forward + fused loss + backward captured once per input buffer)
     gives bit-identical parameters and losses to kernel-by-kernel launches, also when the buffer contents change
     between replays, and reports its launches."""
@@ -149,7 +150,7 @@ def test_trainer_cuda_graph_matches_eager(cuda):
     for use_graph in (False, True):
         model = nets.HNOSegXS(**cfg, device=cuda)
         model.load_state_dict(sd)
-        tr = parallel.Trainer(model, 'DiceLoss', lr=5e-3, use_graph=use_graph)
+        tr = parallel.Trainer(model, lname, lr=5e-3, use_graph=use_graph)
         xb, lb = xs[0].to(cuda), ls[0].to(cuda)
         losses = []
         parallel.launches(reset=True)
