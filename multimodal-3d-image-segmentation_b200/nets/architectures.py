@@ -41,9 +41,6 @@ class NeuralOperatorBlock(nn.Module):
             raise NotImplementedError('hno_b200 implements the SELU (self-normalising) variant only')
         if not use_conv_branch:
             raise NotImplementedError('hno_b200: NeuralOperatorBlock without the conv branch is not supported')
-        if weights_type != 'shared' and transform_type != 'Fourier':
-            raise NotImplementedError("hno_b200: the HNOSeg block supports weights_type='shared' only (per-mode "
-                                      "'individual' weights: FourierOperator blocks, or HartleyOperator itself)")
         self.use_block_skip = use_block_skip
         op = FourierOperator if transform_type == 'Fourier' else HartleyOperator
         self.op = op(in_channels, out_channels, num_modes, use_bias=False, weights_type=weights_type, ndim=ndim,
@@ -67,12 +64,8 @@ class NeuralOperatorBlock(nn.Module):
         spatial = tuple(x.shape[2:])
         wb = self.conv_branch.weight
         t = ops.PointwiseConv.apply(x, None, wb.view(wb.shape[0], -1), self.conv_branch.bias, 0, False)
-        if self.transform_type == 'Fourier':  # no activation in the frequency domain (fourier_operator.py:148-211)
-            z, plan = self.op.spectral(x)
-        else:
-            plan = get_crop_plan(spatial, self.op.num_modes, x.device)
-            z = ops.TruncatedDHT.apply(x, plan)
-            z = ops.PointwiseConv.apply(z, None, self.op.weight, None, 1, False)  # mix + SELU on the retained modes
+        # Fourier: no activation in the frequency domain (fourier_operator.py:148-211); Hartley: mix + SELU on the modes
+        z, plan = self.op.spectral(x)
         y = ops.AddIDHTSelu.apply(t, z, plan)
         if self.use_block_skip:
             if self.conv_concat is not None:

@@ -71,12 +71,17 @@ class HartleyOperator(Module):
         if self.use_bias:
             raise NotImplementedError('hno_b200: HartleyOperator(use_transform=True, use_bias=True) is not supported '
                                       '(no reference architecture enables it)')
+        z, plan = self.spectral(inputs)
+        return ops.TruncatedIDHT.apply(z, plan)
+
+    def spectral(self, inputs):
+        """inputs -> (z, plan): the mixed, SELU-activated retained modes and the plan whose adjoint transform gives the
+        layer output (the HNOSeg block fuses that adjoint with its conv branch, nets/architectures.py)."""
         spatial = tuple(inputs.shape[2:])
         if self.weights_type == 'shared':
             plan = get_crop_plan(spatial, self.num_modes, inputs.device)
             z = ops.TruncatedDHT.apply(inputs, plan)
-            z = ops.PointwiseConv.apply(z, None, self.weight, None, 1, False)  # mix + SELU in the frequency domain
-            return ops.TruncatedIDHT.apply(z, plan)
+            return ops.PointwiseConv.apply(z, None, self.weight, None, 1, False), plan  # mix + SELU on the modes
         # individual weights on the FULL spectrum's reversal (reference :196-241): the partner of the retained
         # index n-m is +m, which lies outside the retained set, so the forward transform also produces it.
         m = [int(v) for v in self.num_modes]
@@ -86,7 +91,7 @@ class HartleyOperator(Module):
         z_ext = ops.TruncatedDHT.apply(inputs, get_dht_plan(spatial, ext, inputs.device))
         z = hartley_conv_full_reverse(z_ext, self.weight, spatial, m)
         z = torch.nn.functional.selu(z)
-        return ops.TruncatedIDHT.apply(z.contiguous(), get_dht_plan(spatial, kl, inputs.device))
+        return z.contiguous(), get_dht_plan(spatial, kl, inputs.device)
 
 
 def hartley_conv_full_reverse(z_ext, weight, spatial, m):

@@ -156,6 +156,28 @@ def hartley_operator_with_transform(x, weight, modes, bias=None):
     return dhtn(selu(full), inverse=True)
 
 
+def hartley_operator_with_transform_individual(x, weight, modes):
+    """HartleyOperator._call3d with weights_type='individual', no bias (hartley_operator.py:179, 196-241, 243-271): the
+    even/odd recombination pairs every retained mode with its reversal in the FULL spectrum (get_reverse of the
+    transformed input, index j -> (n - j) mod n), but W with its reversal inside its own (2 m0, 2 m1, 2 m2) block; the
+    weight's first / last m entries per axis serve the low / high corner.  Then pad, SELU, inverse DHT."""
+    assert weight.ndim == 5
+    spatial = tuple(x.shape[2:])
+    assert all(n >= 2 * m for n, m in zip(spatial, modes))
+    X = dhtn(x)
+    Xr, Wr = reverse_modes(X), reverse_modes(weight)
+    full = torch.zeros((x.shape[0], weight.shape[0]) + spatial, dtype=x.dtype)
+    corners = [((slice(0, m), slice(0, m)), (slice(n - m, n), slice(m, 2 * m))) for n, m in zip(spatial, modes)]
+    for sd_, wd_ in corners[0]:
+        for sh_, wh_ in corners[1]:
+            for sw_, ww_ in corners[2]:
+                xs, xr = X[:, :, sd_, sh_, sw_], Xr[:, :, sd_, sh_, sw_]
+                even = torch.einsum('oidhw,bidhw->bodhw', weight[:, :, wd_, wh_, ww_], xs + xr)
+                odd = torch.einsum('oidhw,bidhw->bodhw', Wr[:, :, wd_, wh_, ww_], xs - xr)
+                full[:, :, sd_, sh_, sw_] = 0.5 * (even + odd)
+    return dhtn(selu(full), inverse=True)
+
+
 # ------------------------------------------------------------------------------------------------
 # HNOSeg-XS                                                       nets/hnosegxs.py
 # ------------------------------------------------------------------------------------------------
@@ -247,6 +269,8 @@ def hno_block(x, sd, prefix, modes, use_block_skip=True):
     spectral layer with its own transform pair + 1x1x1 conv branch -> SELU -> concat skip conv (or additive skip)."""
     if prefix + 'op.weight_real' in sd:  # transform_type='Fourier' (FNOSeg): no activation in the frequency domain
         x1 = fourier_operator_with_transform(x, sd[prefix + 'op.weight_real'], sd[prefix + 'op.weight_imag'], modes)
+    elif sd[prefix + 'op.weight'].ndim == 5:  # weights_type='individual'
+        x1 = hartley_operator_with_transform_individual(x, sd[prefix + 'op.weight'], modes)
     else:
         x1 = hartley_operator_with_transform(x, sd[prefix + 'op.weight'], modes)
     x2 = pointwise(x, sd[prefix + 'conv_branch.weight'], sd.get(prefix + 'conv_branch.bias'))

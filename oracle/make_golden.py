@@ -102,6 +102,26 @@ def case_operator():
     save('operator', **out)
 
 
+def case_operator_transform_individual():
+    """HartleyOperator(use_transform=True, weights_type='individual') (hartley_operator.py:196-241): forward + gradients,
+    incl. an axis that the two corners fill exactly (n == 2m)."""
+    out = {}
+    for tag, shape, modes in (('a', (9, 8, 7), (2, 3, 3)), ('b', (9, 8, 7), (2, 4, 3)), ('c', (6, 11, 8), (3, 2, 4))):
+        torch.manual_seed(14)
+        op = HartleyOperator(8, 8, modes, weights_type='individual', use_transform=True)
+        torch.nn.init.normal_(op.weight, std=0.3)
+        x = torch.randn(2, 8, *shape, requires_grad=True)
+        y = op(x)
+        g = torch.randn(y.shape)
+        (y * g).sum().backward()
+        check(f'HartleyOperator with transform, individual {tag}',
+              orc.hartley_operator_with_transform_individual(x.detach(), op.weight.detach(), modes), y.detach())
+        out.update({f'{tag}/x': x.detach().numpy(), f'{tag}/w': op.weight.detach().numpy(), f'{tag}/y': y.detach().numpy(),
+                    f'{tag}/g': g.numpy(), f'{tag}/dx': x.grad.numpy(), f'{tag}/dw': op.weight.grad.numpy(),
+                    f'{tag}/modes': np.array(modes)})
+    save('operator_transform_individual', **out)
+
+
 def case_block():
     torch.manual_seed(13)
     out = {}
@@ -315,6 +335,7 @@ if __name__ == '__main__':
     torch.set_num_threads(8)
     case_dht()
     case_operator()
+    case_operator_transform_individual()
     case_block()
     case_losses()
     case_input_side()
@@ -322,6 +343,7 @@ if __name__ == '__main__':
     case_hnoseg()
     case_fourier_operator()
     case_hnoseg('Fourier', 'fnoseg_small')
+    case_hnoseg('Hartley', 'hnoseg_individual_small', weights_type='individual')
     # config_fno.ini: the original FNO (per-mode complex weights, biased conv branch, no block skip)
     case_hnoseg('Fourier', 'fno_small', weights_type='individual', use_bias_conv_branch=True, use_block_skip=False)
     if args.full:

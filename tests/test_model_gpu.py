@@ -168,14 +168,15 @@ def test_trainer_cuda_graph_matches_eager(cuda, lname):
     assert n0 > 100 and n1 >= n0  # the graph path adds one eager pass before its capture
 
 
-def test_hnoseg_against_reference_fixture(cuda, golden_dir):
+@pytest.mark.parametrize('wt', ['shared', 'individual'])
+def test_hnoseg_against_reference_fixture(cuda, golden_dir, wt):
     """NeuralOperatorSeg(transform_type='Hartley') (HNOSeg) on the CUDA kernels against outputs and
     Dice gradients recorded from the real reference; state_dict keys are the reference's."""
     from multimodal_3d_image_segmentation_b200 import nets
-    g = dict(np.load(os.path.join(golden_dir, 'hnoseg_small.npz')))
-    model = nets.NeuralOperatorSeg(2, 3, 8, 3, (2, 3, 3), 'Hartley', device=cuda)
+    g = dict(np.load(os.path.join(golden_dir, 'hnoseg_small.npz' if wt == 'shared' else 'hnoseg_individual_small.npz')))
+    model = nets.NeuralOperatorSeg(2, 3, 8, 3, (2, 3, 3), 'Hartley', weights_type=wt, device=cuda)
     sd = _sd(g, 'sd/')
-    assert set(sd) == set(model.state_dict())
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v.shape) for k, v in model.state_dict().items()}
     model.load_state_dict(sd)
     x = torch.from_numpy(g['x']).to(cuda)
     labels = torch.from_numpy(g['labels'].astype(np.int64))
@@ -256,6 +257,23 @@ def test_fnoseg_against_reference_fixture(cuda, golden_dir):
     for k, p in model.named_parameters():
         ref = g[f'DiceLoss/grad/{k}']
         assert rel(p.grad, ref) < 2e-4, (k, rel(p.grad, ref))
+
+
+def test_hartley_operator_with_transform_individual(cuda, golden_dir):
+    """HartleyOperator(use_transform=True, weights_type='individual') (hartley_operator.py:196-241: reversal partner in the
+    FULL spectrum) against outputs and gradients recorded from the real reference, incl. axes with n == 2m."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'operator_transform_individual.npz')))
+    for tag in ('a', 'b', 'c'):
+        modes = tuple(int(v) for v in g[f'{tag}/modes'])
+        op = nets.HartleyOperator(8, 8, modes, weights_type='individual', use_transform=True, device=cuda)
+        with torch.no_grad():
+            op.weight.copy_(torch.from_numpy(g[f'{tag}/w']))
+        x = torch.from_numpy(g[f'{tag}/x']).to(cuda).requires_grad_(True)
+        y = op(x)
+        assert rel(y, g[f'{tag}/y']) < 1e-5, (tag, rel(y, g[f'{tag}/y']))
+        (y * torch.from_numpy(g[f'{tag}/g']).to(cuda)).sum().backward()
+        assert rel(x.grad, g[f'{tag}/dx']) < 1e-5 and rel(op.weight.grad, g[f'{tag}/dw']) < 1e-5, tag
 
 
 def test_fno_individual_weights_against_reference_fixture(cuda, golden_dir):

@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import hno_oracle as orc
@@ -93,9 +94,11 @@ def test_param_count_known_answer():
     assert sum(v.numel() for v in sd.values()) == 28248
 
 
-def test_hnoseg_fixture(golden_dir):
-    """NeuralOperatorSeg(transform_type='Hartley') = HNOSeg, recorded from the real reference."""
-    g = _load(golden_dir, 'hnoseg_small')
+@pytest.mark.parametrize('name', ['hnoseg_small', 'hnoseg_individual_small'])
+def test_hnoseg_fixture(golden_dir, name):
+    """NeuralOperatorSeg(transform_type='Hartley') = HNOSeg, shared and per-mode weights, recorded from
+    the real reference."""
+    g = _load(golden_dir, name)
     sd = _sd(g, 'sd/')
     x = torch.from_numpy(g['x'])
     probs, logits = orc.hnoseg_forward(sd, x, 3, (2, 3, 3), return_logits=True)
@@ -145,3 +148,16 @@ def test_input_side_fixtures(golden_dir):
     for tag, kw in cases.items():
         y = orc.normalize_modalities(g['vol'], **kw)
         assert y.dtype == np.float32 and np.abs(y - g[f'norm/{tag}']).max() < 1e-5, tag
+
+
+def test_hartley_operator_with_transform_individual_fixtures(golden_dir):
+    """HartleyOperator(use_transform=True, weights_type='individual'), recorded from the real reference."""
+    g = _load(golden_dir, 'operator_transform_individual')
+    for tag in ('a', 'b', 'c'):
+        x = torch.from_numpy(g[f'{tag}/x']).requires_grad_(True)
+        w = torch.from_numpy(g[f'{tag}/w']).requires_grad_(True)
+        y = orc.hartley_operator_with_transform_individual(x, w, tuple(int(v) for v in g[f'{tag}/modes']))
+        _close(y.detach(), g[f'{tag}/y'])
+        dx, dw = torch.autograd.grad((y * torch.from_numpy(g[f'{tag}/g'])).sum(), [x, w])
+        _close(dx, g[f'{tag}/dx'], 1e-5)
+        _close(dw, g[f'{tag}/dw'], 1e-5)
