@@ -327,6 +327,32 @@ def test_cross_entropy_labels_soft_targets_and_torch(cuda, shape):
     assert abs(float(lc) - float(lt)) < 2e-6 * max(1.0, float(lt)) and rel(gc, gt) < 1e-5
 
 
+def test_losses_full_size_known_answers(cuda):
+    """BASELINE volume size (2 x 4 x 240 x 240 x 155): closed-form values that do not depend on the size.
+    Perfect predictions p = one-hot(t): Dice = 1 (loss 0), Pearson r = 1 (PCC loss 0), ExpDice clamps at 1 - 1e-7,
+    cross entropy = log(e + C - 1) - 1; uniform predictions p = 1/C: cross entropy = log C, and its gradient sums to 0
+    over the classes of every voxel."""
+    import math
+    from multimodal_3d_image_segmentation_b200 import nets, ops
+    from multimodal_3d_image_segmentation_b200.experiments import to_categorical
+    B, C, shape = 2, 4, (240, 240, 155)
+    lab = torch.randint(0, C, (B, 1) + shape, device=cuda, dtype=torch.uint8,
+                        generator=torch.Generator(device=cuda).manual_seed(20))
+    t = to_categorical(lab, C)
+    assert float(t.sum(dtype=torch.float64)) == B * shape[0] * shape[1] * shape[2]
+    assert abs(float(nets.custom_losses.DiceLoss()(t, t))) < 1e-6
+    assert abs(float(nets.custom_losses.PCCLoss()(t, t))) < 1e-6
+    assert abs(float(nets.custom_losses.ExpDiceLoss()(t, t)) - (-math.log(1 - 1e-7)) ** 0.3) < 1e-3
+    ce = nets.custom_losses.CrossEntropyLoss()
+    assert abs(float(ce(t, t)) - (math.log(math.e + C - 1) - 1.0)) < 1e-6
+    u = torch.full_like(t, 1.0 / C).requires_grad_(True)
+    loss = ce(u, t)
+    assert abs(float(loss) - math.log(C)) < 1e-6
+    (g,) = torch.autograd.grad(loss, u)
+    assert float(g.sum(1).abs().max()) < 1e-12 and abs(float(g.abs().sum()) - 2.0 * (C - 1) / C) < 1e-4
+    assert float(ops.ce_loss_forward(u.detach(), labels=lab[:, 0].contiguous())) == float(loss)
+
+
 @pytest.mark.parametrize('kind', ['DiceLoss', 'PCCLoss', 'ExpDiceLoss'])
 def test_fused_head_loss(cuda, kind):
     from multimodal_3d_image_segmentation_b200 import ops
