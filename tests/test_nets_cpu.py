@@ -59,3 +59,41 @@ def test_padcrop_semantics():
     assert torch.equal(y[:, :, :, 1:5, :], x[:, :, 0:4])  # crop: odd voxel removed at the top; pad: 1 low, 2 high
     assert float(y[:, :, :, 0].abs().sum()) == 0 and float(y[:, :, :, 5:].abs().sum()) == 0
     assert nets.spatial_padcrop(x, (5, 4, 3)) is x
+
+
+@pytest.mark.parametrize('name, kw', [
+    ('hnoseg_small', dict(transform_type='Hartley')),                                   # config_hnoseg.ini
+    ('hnoseg_individual_small', dict(transform_type='Hartley', weights_type='individual')),
+    ('fnoseg_small', dict(transform_type='Fourier')),                                   # config_fnoseg.ini
+    ('fno_small', dict(transform_type='Fourier', weights_type='individual', use_bias_conv_branch=True,
+                       use_block_skip=False)),                                          # config_fno.ini
+])
+def test_neural_operator_seg_layouts_and_meta_forward(golden_dir, name, kw):
+    """state_dict keys / shapes of the NeuralOperatorSeg family equal those recorded from the reference; meta forward."""
+    g = dict(np.load(os.path.join(golden_dir, name + '.npz')))
+    ref = {k[3:]: tuple(v.shape) for k, v in g.items() if k.startswith('sd/')}
+    model = nets.NeuralOperatorSeg(2, 3, 8, 3, (2, 3, 3), **kw)
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == ref
+    model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd/')})
+    meta = nets.NeuralOperatorSeg(2, 3, 8, 3, (2, 3, 3), device='meta', **kw)
+    assert tuple(meta(torch.empty(1, 2, 18, 16, 13, device='meta')).shape) == (1, 3, 18, 16, 13)
+
+
+def test_losses_and_input_side_host_contract():
+    """Constructor arguments of the loss classes (run.py:105-110 passes the ini's [loss] section as kwargs) and the
+    no-CPU-path rule of the experiments.utils mirror."""
+    from multimodal_3d_image_segmentation_b200.experiments import normalize_modalities, to_categorical
+    assert nets.custom_losses.ExpDiceLoss().exp == 0.3 and nets.custom_losses.ExpDiceLoss(exp=0.5).param == 0.5
+    with pytest.raises(ValueError):
+        nets.custom_losses.ExpDiceLoss(exp=-1.0)
+    nets.custom_losses.CrossEntropyLoss()
+    with pytest.raises(NotImplementedError):
+        nets.custom_losses.CrossEntropyLoss(weight=torch.ones(4))
+    for name in ('DiceLoss', 'PCCLoss', 'ExpDiceLoss', 'CrossEntropyLoss'):
+        assert hasattr(nets.custom_losses, name)  # hasattr(custom_losses, loss_name) decides the route in run.py:107
+    with pytest.raises(RuntimeError):
+        to_categorical(torch.zeros(1, 1, 2, 2, 2, dtype=torch.uint8), 2)
+    with pytest.raises(RuntimeError):
+        normalize_modalities(torch.zeros(4, 2, 2, 2), mask_val=0)
+    with pytest.raises(RuntimeError):
+        nets.custom_losses.CrossEntropyLoss()(torch.zeros(1, 2, 2, 2, 2), torch.zeros(1, 2, 2, 2, 2))
