@@ -179,6 +179,57 @@ def hartley_operator_with_transform_individual(x, weight, modes):
 
 
 # ------------------------------------------------------------------------------------------------
+# Hartley multi-head attention (oracle only so far)   nets/hartley_mha.py:136-222
+# ------------------------------------------------------------------------------------------------
+def group_patches(t, patch):
+    """grouping3d (hartley_mha.py:473-498): (B, Z, C, D, H, W) -> (B, Z, C*pd*ph*pw, D/pd, H/ph, W/pw); the new channel
+    index is ((c*pd + i)*ph + j)*pw + k for the voxel (i, j, k) inside its patch."""
+    pd, ph, pw = patch
+    b, z, c, d, h, w = t.shape
+    assert d % pd == 0 and h % ph == 0 and w % pw == 0
+    u = t.unfold(3, pd, pd).unfold(4, ph, ph).unfold(5, pw, pw)        # (b, z, c, nd, nh, nw, pd, ph, pw)
+    u = u.permute(0, 1, 2, 6, 7, 8, 3, 4, 5)                           # (b, z, c, pd, ph, pw, nd, nh, nw)
+    return u.reshape(b, z, c * pd * ph * pw, d // pd, h // ph, w // pw)
+
+
+def ungroup_patches(t, channels, patch):
+    """ungrouping3d (hartley_mha.py:501-524): the inverse of group_patches."""
+    pd, ph, pw = patch
+    b, z, _, nd, nh, nw = t.shape
+    u = t.reshape(b, z, channels, pd, ph, pw, nd, nh, nw).permute(0, 1, 2, 6, 3, 7, 4, 8, 5)
+    return u.reshape(b, z, channels, nd * pd, nh * ph, nw * pw)
+
+
+def hartley_mha(query, w_query, w_key, w_value, w_out, modes, patch=None, key=None, value=None, activation=selu):
+    """HartleyMultiHeadAttention._call, 3-D, no bias (hartley_mha.py:136-222): DHT of every input, per-head channel mixing
+    of the 8 retained corners (freq_conv3d :312-334 = TransformCrop followed by 'zoi,bidhw->bzodhw'), optional patch
+    grouping, attention act(Q^T K / sqrt(features)) V over the retained (grouped) modes -- no softmax --, ungrouping, heads
+    merged head-major, output projection, zero-padding and inverse DHT (inverse3d :365-400 = PadInverse).
+    key defaults to query and value to key (:137-150).  Weights: (Z, Ck, Cin), (Z, Ck, Cin_k), (Z, Cv, Cin_v),
+    (Cv, Z*Cv)."""
+    spatial = tuple(query.shape[2:])
+    assert all(n >= 2 * m for n, m in zip(spatial, modes))
+    key = query if key is None else key
+    value = key if value is None else value
+    q = torch.einsum('zoi,bidhw->bzodhw', w_query, transform_crop(query, modes))
+    k = torch.einsum('zoi,bidhw->bzodhw', w_key, transform_crop(key, modes))
+    v = torch.einsum('zoi,bidhw->bzodhw', w_value, transform_crop(value, modes))
+    if patch is not None:
+        q, k, v = (group_patches(t, patch) for t in (q, k, v))
+    grid = q.shape[3:]
+    q, k, v = (t.flatten(3) for t in (q, k, v))                        # (B, Z, features, tokens)
+    att = torch.einsum('bzcq,bzck->bzqk', q, k) / math.sqrt(k.shape[2])
+    if activation is not None:
+        att = activation(att)
+    out = torch.einsum('bzqk,bzck->bzcq', att, v).reshape(v.shape[:3] + tuple(grid))
+    if patch is not None:
+        out = ungroup_patches(out, w_value.shape[1], patch)
+    out = out.flatten(1, 2)                                            # heads x channels, head-major
+    out = torch.einsum('oi,bidhw->bodhw', w_out, out)
+    return pad_inverse(out, spatial)
+
+
+# ------------------------------------------------------------------------------------------------
 # HNOSeg-XS                                                       nets/hnosegxs.py
 # ------------------------------------------------------------------------------------------------
 def xs_block(x, sd, prefix, num_convs, modes):

@@ -122,6 +122,42 @@ def case_operator_transform_individual():
     save('operator_transform_individual', **out)
 
 
+def case_hartley_mha():
+    """HartleyMultiHeadAttention (BASELINE config 5's layer): self-attention with and without patch
+    grouping, value_dim != key_dim, and cross-attention with separate key / value inputs; forward + gradients."""
+    from nets.hartley_mha import HartleyMultiHeadAttention
+    out = {}
+    cases = (('self_grouped', dict(in_channels=8, key_dim=6, num_heads=2, num_modes=(2, 4, 2), patch_size=(2, 2, 2)), 1),
+             ('self_plain', dict(in_channels=8, key_dim=5, num_heads=3, num_modes=(2, 3, 3), value_dim=4), 1),
+             ('cross', dict(in_channels=8, key_dim=4, num_heads=2, num_modes=(2, 2, 3), patch_size=(1, 2, 3),
+                            key_in_channels=6, value_in_channels=5), 3))
+    for tag, kw, nin in cases:
+        torch.manual_seed(51)
+        op = HartleyMultiHeadAttention(**kw)
+        for w in (op.weight_query, op.weight_key, op.weight_value, op.weight_out):
+            torch.nn.init.normal_(w, std=0.4)
+        chans = [kw['in_channels'], kw.get('key_in_channels', kw['in_channels']),
+                 kw.get('value_in_channels', kw.get('key_in_channels', kw['in_channels']))][:nin]
+        xs = [torch.randn(2, c, 9, 8, 7, requires_grad=True) for c in chans]
+        y = op(xs[0] if nin == 1 else xs)
+        g = torch.randn(y.shape)
+        (y * g).sum().backward()
+        yo = orc.hartley_mha(xs[0].detach(), op.weight_query.detach(), op.weight_key.detach(), op.weight_value.detach(),
+                             op.weight_out.detach(), kw['num_modes'], kw.get('patch_size'),
+                             key=xs[1].detach() if nin > 1 else None, value=xs[2].detach() if nin > 2 else None)
+        check(f'HartleyMultiHeadAttention {tag}', yo, y.detach())
+        out.update({f'{tag}/y': y.detach().numpy(), f'{tag}/g': g.numpy(), f'{tag}/modes': np.array(kw['num_modes']),
+                    f'{tag}/patch': np.array(kw.get('patch_size') or (0, 0, 0)),
+                    f'{tag}/wq': op.weight_query.detach().numpy(), f'{tag}/wk': op.weight_key.detach().numpy(),
+                    f'{tag}/wv': op.weight_value.detach().numpy(), f'{tag}/wo': op.weight_out.detach().numpy(),
+                    f'{tag}/dwq': op.weight_query.grad.numpy(), f'{tag}/dwk': op.weight_key.grad.numpy(),
+                    f'{tag}/dwv': op.weight_value.grad.numpy(), f'{tag}/dwo': op.weight_out.grad.numpy()})
+        for i, x in enumerate(xs):
+            out[f'{tag}/x{i}'] = x.detach().numpy()
+            out[f'{tag}/dx{i}'] = x.grad.numpy()
+    save('hartley_mha', **out)
+
+
 def case_block():
     torch.manual_seed(13)
     out = {}
@@ -336,6 +372,7 @@ if __name__ == '__main__':
     case_dht()
     case_operator()
     case_operator_transform_individual()
+    case_hartley_mha()
     case_block()
     case_losses()
     case_input_side()

@@ -161,3 +161,25 @@ def test_hartley_operator_with_transform_individual_fixtures(golden_dir):
         dx, dw = torch.autograd.grad((y * torch.from_numpy(g[f'{tag}/g'])).sum(), [x, w])
         _close(dx, g[f'{tag}/dx'], 1e-5)
         _close(dw, g[f'{tag}/dw'], 1e-5)
+
+
+def test_hartley_mha_fixtures(golden_dir):
+    """HartleyMultiHeadAttention (BASELINE config 5's layer): the oracle restatement against outputs and
+    gradients of the real reference -- grouped / plain self-attention, value_dim != key_dim, cross-attention.  The CUDA
+    path for this layer is not built yet; the oracle is pinned first."""
+    g = _load(golden_dir, 'hartley_mha')
+    for tag, nin in (('self_grouped', 1), ('self_plain', 1), ('cross', 3)):
+        xs = [torch.from_numpy(g[f'{tag}/x{i}']).requires_grad_(True) for i in range(nin)]
+        ws = [torch.from_numpy(g[f'{tag}/{k}']).requires_grad_(True) for k in ('wq', 'wk', 'wv', 'wo')]
+        patch = tuple(int(v) for v in g[f'{tag}/patch'])
+        y = orc.hartley_mha(xs[0], *ws, tuple(int(v) for v in g[f'{tag}/modes']), patch if patch[0] else None,
+                            key=xs[1] if nin > 1 else None, value=xs[2] if nin > 2 else None)
+        _close(y.detach(), g[f'{tag}/y'])
+        grads = torch.autograd.grad((y * torch.from_numpy(g[f'{tag}/g'])).sum(), xs + ws)
+        for i in range(nin):
+            _close(grads[i], g[f'{tag}/dx{i}'], 1e-5)
+        for k, gw in zip(('dwq', 'dwk', 'dwv', 'dwo'), grads[nin:]):
+            _close(gw, g[f'{tag}/{k}'], 1e-5)
+    # grouping is a pure permutation and ungrouping its inverse
+    t = torch.randn(2, 3, 4, 4, 6, 2)
+    assert torch.equal(orc.ungroup_patches(orc.group_patches(t, (2, 3, 1)), 4, (2, 3, 1)), t)
