@@ -315,10 +315,13 @@ def fourier_operator_with_transform(x, weight_real, weight_imag, modes):
     return torch.fft.irfftn(full, s=(s0, s1, s2), dim=(-3, -2, -1), norm='forward')
 
 
-def hno_block(x, sd, prefix, modes, use_block_skip=True):
+def hno_block(x, sd, prefix, modes, use_block_skip=True, patch=None):
     """NeuralOperatorBlock via _TransBlock.forward (architectures.py:521-548, 551-608), shared weights, SELU:
     spectral layer with its own transform pair + 1x1x1 conv branch -> SELU -> concat skip conv (or additive skip)."""
-    if prefix + 'op.weight_real' in sd:  # transform_type='Fourier' (FNOSeg): no activation in the frequency domain
+    if prefix + 'op.weight_query' in sd:  # HartleyMHABlock (architectures.py:611-635)
+        x1 = hartley_mha(x, sd[prefix + 'op.weight_query'], sd[prefix + 'op.weight_key'], sd[prefix + 'op.weight_value'],
+                         sd[prefix + 'op.weight_out'], modes, patch)
+    elif prefix + 'op.weight_real' in sd:  # transform_type='Fourier' (FNOSeg): no activation in the frequency domain
         x1 = fourier_operator_with_transform(x, sd[prefix + 'op.weight_real'], sd[prefix + 'op.weight_imag'], modes)
     elif sd[prefix + 'op.weight'].ndim == 5:  # weights_type='individual'
         x1 = hartley_operator_with_transform_individual(x, sd[prefix + 'op.weight'], modes)
@@ -334,23 +337,29 @@ def hno_block(x, sd, prefix, modes, use_block_skip=True):
     return y + x
 
 
-def hnoseg_forward(sd, x, num_transform_blocks, num_modes, softmax=True, return_logits=False, use_block_skip=True):
+def hnoseg_forward(sd, x, num_transform_blocks, num_modes, softmax=True, return_logits=False, use_block_skip=True,
+                   patch=None):
     """_TransSeg.forward (architectures.py:321-353) for NeuralOperatorSeg(..., 'Hartley'), use_resize=True, no deep
     supervision."""
     image_size = x.shape[2:]
     x = selu(F.conv3d(x, sd['conv_in.op.weight'], sd['conv_in.op.bias'], stride=2, padding=1))
     x = selu(pointwise(x, sd['conv1.op.weight'], sd['conv1.op.bias']))
+    deep = 'conv_ds.op.weight' in sd  # use_deep_supervision (architectures.py:306-311, 330-343): every block output joins
+    tensors = [x]
     for i in range(num_transform_blocks):
-        x = hno_block(x, sd, f'layers.{i}.', num_modes, use_block_skip)
+        x = hno_block(x, sd, f'layers.{i}.', num_modes, use_block_skip, patch)
+        tensors.append(x)
+    if deep:
+        x = selu(pointwise(torch.cat(tensors, dim=1), sd['conv_ds.op.weight'], sd['conv_ds.op.bias']))
     x = F.interpolate(x, size=tuple(image_size), mode='trilinear')
     logits = center_padcrop(pointwise(x, sd['conv_out.weight']), image_size)
     out = torch.softmax(logits, dim=1) if softmax else logits
     return (out, logits) if return_logits else out
 
 
-def hnoseg_train_step(sd, x, labels, num_transform_blocks, num_modes, loss='DiceLoss', use_block_skip=True):
+def hnoseg_train_step(sd, x, labels, num_transform_blocks, num_modes, loss='DiceLoss', use_block_skip=True, patch=None):
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    probs = hnoseg_forward(params, x, num_transform_blocks, num_modes, use_block_skip=use_block_skip)
+    probs = hnoseg_forward(params, x, num_transform_blocks, num_modes, use_block_skip=use_block_skip, patch=patch)
     value = LOSSES[loss](probs, to_categorical(labels, probs.shape[1]).to(probs.dtype))
     grads = torch.autograd.grad(value, list(params.values()))
     return value.detach(), dict(zip(params.keys(), grads))

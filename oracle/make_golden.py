@@ -216,6 +216,35 @@ def case_model():
     save('model_small', **out)
 
 
+def case_hartley_mha_seg():
+    """HartleyMHASeg (BASELINE config 5's architecture, architectures.py:432-508) in small, deep supervision on (its
+    default): forward + Dice gradients."""
+    torch.manual_seed(61)
+    cfg = dict(in_channels=2, out_channels=3, filters=8, num_transform_blocks=2, num_heads=2, num_modes=(2, 4, 2),
+               patch_size=(2, 2, 2))
+    model = ref.HartleyMHASeg(**cfg)
+    torch.manual_seed(62)
+    x = torch.randn(2, 2, 18, 16, 13)
+    labels = torch.randint(0, 3, (2, 1, 18, 16, 13))
+    probs = model(x)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    o_probs = orc.hnoseg_forward(sd, x, 2, cfg['num_modes'], patch=cfg['patch_size'])
+    check('HartleyMHASeg probs', o_probs, probs.detach())
+    onehot = torch.zeros(2, 3, 18, 16, 13).scatter_(1, labels, 1.0)
+    model.zero_grad()
+    loss = ref_losses.DiceLoss()(model(x), onehot)
+    loss.backward()
+    o_loss, o_grads = orc.hnoseg_train_step(sd, x, labels, 2, cfg['num_modes'], 'DiceLoss', patch=cfg['patch_size'])
+    check('HartleyMHASeg DiceLoss value', o_loss, loss.detach(), 1e-6)
+    out = {'x': x.numpy(), 'labels': labels.numpy().astype(np.uint8), 'probs': probs.detach().numpy(),
+           'DiceLoss/loss': loss.detach().numpy()}
+    for k, p in model.named_parameters():
+        check(f'HartleyMHASeg DiceLoss grad {k}', o_grads[k], p.grad, 2e-4)
+        out[f'DiceLoss/grad/{k}'] = p.grad.numpy().copy()
+    out.update({f'sd/{k}': v.numpy() for k, v in sd.items()})
+    save('hartley_mha_seg_small', **out)
+
+
 def case_fourier_operator():
     """FourierOperator with transform, shared weights (BASELINE config 3's layer): forward + gradients, incl. the
     clamp path (modes larger than half the grid) and an even grid."""
@@ -373,6 +402,7 @@ if __name__ == '__main__':
     case_operator()
     case_operator_transform_individual()
     case_hartley_mha()
+    case_hartley_mha_seg()
     case_block()
     case_losses()
     case_input_side()

@@ -183,3 +183,17 @@ def test_hartley_mha_fixtures(golden_dir):
     # grouping is a pure permutation and ungrouping its inverse
     t = torch.randn(2, 3, 4, 4, 6, 2)
     assert torch.equal(orc.ungroup_patches(orc.group_patches(t, (2, 3, 1)), 4, (2, 3, 1)), t)
+
+
+def test_hartley_mha_seg_fixture(golden_dir):
+    """HartleyMHASeg (BASELINE config 5's architecture, deep supervision on) in small: oracle vs the real reference."""
+    g = _load(golden_dir, 'hartley_mha_seg_small')
+    sd = _sd(g, 'sd/')
+    assert 'conv_ds.op.weight' in sd and tuple(sd['conv_ds.op.weight'].shape) == (3, 24, 1, 1, 1)
+    x = torch.from_numpy(g['x'])
+    _close(orc.hnoseg_forward(sd, x, 2, (2, 4, 2), patch=(2, 2, 2)), g['probs'])
+    loss, grads = orc.hnoseg_train_step(sd, x, torch.from_numpy(g['labels'].astype(np.int64)), 2, (2, 4, 2), 'DiceLoss',
+                                        patch=(2, 2, 2))
+    _close(loss, g['DiceLoss/loss'], 1e-6)
+    for k, v in grads.items():
+        _close(v, g[f'DiceLoss/grad/{k}'], 2e-4)
