@@ -125,17 +125,41 @@ def oracle_step_factory(torch, batch):
     return step
 
 
-def run_reference(args, rank):
+def workload_config(args, world):
+    """The `config` object of the JSON line: ONE definition for both arms, so the driver sees identical strings."""
+    return {'workload': f'HNOSegXS(4,4,24,[3]*8,(10,14,14)) train step fp32 (fwd + {args.loss} + bwd + Adamax), '
+                        f'batch {args.batch}/GPU, 4x240x240x155 volumes, random-init weights',
+            'global_batch': world * args.batch, 'parallelism': f'dp{world}',
+            'l2_policy': 'working set (~10 GB of activations per step) >> 126 MB L2; no explicit flush'}
+
+
+def host_threads():
+    """Threads this process may use: the CPUs of its affinity mask (not OMP_NUM_THREADS, which torchrun exports as 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path (oracle port) on ALL host threads.  It is a baseline, not a scaling
+    arm: there is one host however many GPUs the job has, so rank 0 alone runs it and prints the SAME single-host
+    figure for every N (the other ranks exit without work).  Each step is a bounded sample of the workload: ONE
+    4x240x240x155 volume of the batch-2 step, full training step; volumes/s normalises the batch size."""
     if rank != 0:
         return
+    n_thr = host_threads()
+    for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS'):  # torchrun exports OMP_NUM_THREADS=1 for N > 1
+        os.environ[k] = str(n_thr)
     import torch
+    torch.set_num_threads(n_thr)
     step = oracle_step_factory(torch, 1)
-    budget = float(os.environ.get('HNO_REFERENCE_BUDGET_S', '150'))
+    budget = float(os.environ.get('HNO_REFERENCE_BUDGET_S', '240'))
     t0 = time.perf_counter()
-    step()  # warm-up (also sizes the run)
+    step()  # first warm-up step (also sizes the run)
     t_first = time.perf_counter() - t0
     warm = 1
-    while warm < min(args.warmup, 2) and (warm + 1) * t_first < 0.25 * budget:
+    while warm < args.warmup and (warm + 1 + args.steps) * t_first < budget:
         step()
         warm += 1
     k = max(1, min(args.steps, int((budget - warm * t_first) / max(t_first, 1e-3))))
@@ -145,19 +169,52 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     value = k / dt
     cores = torch.get_num_threads()
-    sample = (f'{k} timed step(s) (asked {args.steps}) + {warm} warm-up of ONE 4x240x240x155 volume each (batch 1 of the '
-              f'batch-{args.batch} workload), full training step incl. Adamax, oracle port, {cores} threads')
+    sample = (f'{k} timed step(s) (asked {args.steps}) + {warm} warm-up (asked {args.warmup}) of ONE 4x240x240x155 volume '
+              f'each (batch 1 of the batch-{args.batch} workload), full training step incl. Adamax, oracle port on {cores} '
+              f'threads of ONE host; the same single-host figure is reported for every --gpus N')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': k,
         'warmup': warm, 'ms_per_step': 1e3 * dt / k, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'HNOSegXS(4,4,24,[3]*8,(10,14,14)) train step fp32, Dice loss, Adamax, batch {args.batch}/GPU, '
-                               '4x240x240x155 volumes', 'sampled_batch': 1},
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
         'cpu_baseline': {'value': value, 'unit': 'volumes/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'volumes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'host_cpus': os.cpu_count(),
     }
     print(json.dumps(line), flush=True)
+
+
+def pin_to_gpu_numa(torch, index):
+    """Binds this process (and, by first touch, the pinned host buffers it allocates afterwards) to the CPUs of the NUMA
+    node the GPU hangs off: with 8 ranks streaming batches, remote-node host memory halves the PCIe copy rate.
+    Best effort: returns a description or None."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id  # not available on every torch build
+    except Exception:
+        bus = None
+    try:
+        if bus is None:
+            out = subprocess.run(['nvidia-smi', f'--id={index}', '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = out.split('\n')[0].strip()
+        dom_bus = bus.lower()
+        if len(dom_bus.split(':')[0]) == 8:  # nvidia-smi prints an 8-digit domain, sysfs uses 4
+            dom_bus = dom_bus[4:]
+        base = f'/sys/bus/pci/devices/{dom_bus}'
+        node = int(open(f'{base}/numa_node').read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {'numa_node': node, 'cpus': len(cpus)}
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------ kernel table
@@ -233,8 +290,8 @@ def kernel_table(torch, dev, batch, peak_gbs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=200)  # >= 2 s timed window per loop at ~10 ms per step
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=2, help='volumes per GPU per step (BASELINE config 2: 2)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--loss', default='DiceLoss', choices=['DiceLoss', 'PCCLoss'])
@@ -245,7 +302,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -270,6 +327,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # nvidia-smi needs ~1 s to come up: start early, keep only the samples taken under load
+    numa = pin_to_gpu_numa(torch, local_rank) if world > 1 else None  # before the pinned buffers are allocated
     torch.manual_seed(0)
     model = nets.HNOSegXS(**CFG, device=dev)  # random init = the reference's SNN initialiser (nets_utils.py:102-117)
     trainer = parallel.Trainer(model, args.loss, lr=5e-3)
@@ -277,9 +335,15 @@ def main():
     gx = torch.Generator().manual_seed(1234 + 2 * rank)
     gl = torch.Generator().manual_seed(1235 + 2 * rank)
     n_host = 2  # distinct host batches, cycled
-    xs_host = [torch.randn(B, 4, *VOLUME, generator=gx).pin_memory() for _ in range(n_host)]
+    # Host batches are RAW modalities in their storage type (int16, as the NIfTI volumes the reference reads): unit-variance
+    # noise on an offset, x_raw = round(1000 + 200 * randn), so that the per-sample per-modality z-scoring the reference
+    # applies in its loader (normalize_modalities, experiments/run.py:52-55) -- here the first kernels of Trainer.step_raw --
+    # hands the network the randn volumes SURVEY.md 8d asks for (quantised to 1/200).
+    xs_host = [(torch.randn(B, 4, *VOLUME, generator=gx) * 200.0 + 1000.0).round_().to(torch.int16).pin_memory()
+               for _ in range(n_host)]
     ls_host = [torch.randint(0, 4, (B, 1, *VOLUME), generator=gl).to(torch.uint8).pin_memory() for _ in range(n_host)]
-    x_dev = xs_host[0].to(dev)
+    from multimodal_3d_image_segmentation_b200.experiments.utils import normalize_rows
+    x_dev = normalize_rows(xs_host[0].to(dev), 4 * B, mask_val=0)  # the same batch, already normalised, resident in HBM
     l_dev = ls_host[0].to(dev)
 
     # ---------------- device-resident throughput
@@ -306,7 +370,7 @@ def main():
 
     # ---------------- end to end: host buffers, copies inside the timed region, loss.item() every step
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty_like(x_dev), torch.empty_like(l_dev)) for _ in range(2)]
+    bufs = [(torch.empty(x_dev.shape, dtype=torch.int16, device=dev), torch.empty_like(l_dev)) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -328,12 +392,13 @@ def main():
                 issue_copy(i + 1)
             slot = i % 2
             cur.wait_event(ready[slot])
-            lv = trainer.step(bufs[slot][0], bufs[slot][1])
+            lv = trainer.step_raw(bufs[slot][0], bufs[slot][1], mask_val=0)
             freed[slot].record(cur)
             lv.item()  # device -> host read of the step's loss, as experiments/train_test.py:162
 
-    e2e_loop(2)
+    e2e_loop(3)
     barrier()
+    parallel.launches(reset=True)
     t0 = time.perf_counter()
     e0.record()
     e2e_loop(args.steps)
@@ -353,7 +418,8 @@ def main():
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(ms2.item()) * 1e-3)
-    h2d = xs_host[0].numel() * 4 + ls_host[0].numel()
+    e2e_launches = parallel.launches()
+    h2d = xs_host[0].numel() * xs_host[0].element_size() + ls_host[0].numel()
 
     if rank != 0:
         if world > 1:
@@ -364,14 +430,14 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': 'volumes/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'HNOSegXS(4,4,24,[3]*8,(10,14,14)) train step fp32 (fwd + {args.loss} + bwd + Adamax), '
-                               f'batch {B}/GPU, 4x240x240x155 volumes, random-init weights',
-                   'global_batch': world * B, 'parallelism': f'dp{world}',
-                   'l2_policy': 'working set (~10 GB of activations per step) >> 126 MB L2; no explicit flush'},
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'volumes/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
-                'wall_s': round(wall, 4)},
+                'wall_s': round(wall, 4), 'ms_per_step': round(float(ms2.item()) / args.steps, 4),
+                'gpu_launches': e2e_launches, 'numa': numa,
+                'what': 'Trainer.step_raw: pinned int16 raw modalities + uint8 labels copied H2D every step (double-buffered '
+                        'copy stream), z-scored per sample and modality on the device (normalize_modalities, run.py:52-55), '
+                        'train step, loss.item()'},
         'gpu_launches': launches, 'loss': final_loss,
     }
     if not args.no_kernel_table:

@@ -218,6 +218,11 @@ int hno_to_categorical(const void* labels, int label_bytes, float* onehot, int* 
 size_t hno_normalize_workspace_bytes(int rows);
 int hno_normalize_modalities(const float* data, float* out, void* workspace, int rows, long n, int has_mask,
                              float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream);
+/* the same on raw int16 intensities (the NIfTI storage type of the BraTS volumes the reference reads,
+ * experiments/utils.py:260-270 -> np.asarray(data, dtype=np.float32) at :47): the batch crosses PCIe at half the bytes and
+ * the exact int16 -> fp32 conversion happens in the load */
+int hno_normalize_modalities_i16(const short* data, float* out, void* workspace, int rows, long n, int has_mask,
+                                 float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adamax step on a flat parameter vector (torch.optim.Adamax semantics, the optimizer of

@@ -65,6 +65,7 @@ SIGNATURES = {
     'hno_to_categorical': (_I, [_P, _I, _P, _P, _I, _I, _L, _P]),
     'hno_normalize_workspace_bytes': (_Z, [_I]),
     'hno_normalize_modalities': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
+    'hno_normalize_modalities_i16': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
     'hno_adamax_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 
@@ -76,9 +77,12 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise HnoError(f'{LIB_PATH} is missing; run python multimodal-3d-image-segmentation_b200/build.py')
+    if not os.path.exists(LIB_PATH) and not build_if_missing:
+        raise HnoError(f'{LIB_PATH} is missing; run python multimodal-3d-image-segmentation_b200/build.py')
+    if build_if_missing:
+        # always through build(): it is a digest comparison when the library is current, and it rebuilds a stale one
+        # (sources newer than the .so) instead of loading it silently.  One process builds at a time (file lock, the
+        # .so is renamed into place), so the ranks of a torchrun job cannot dlopen a half-written library.
         import importlib.util
         spec = importlib.util.spec_from_file_location('_hno_b200_build', os.path.join(HERE, 'build.py'))
         mod = importlib.util.module_from_spec(spec)

@@ -60,8 +60,21 @@ def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     stamp = os.path.join(BUILD, 'digest.txt')
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+
+    def current():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest
+
+    if not force and current():
         return LIB
+    import fcntl
+    with open(os.path.join(BUILD, '.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)  # one builder at a time (ranks of a torchrun job race here otherwise)
+        if not force and current():       # another process built it while this one waited
+            return LIB
+        return _build_locked(digest, stamp, verbose)
+
+
+def _build_locked(digest, stamp, verbose):
     nvcc = _nvcc()
     jobs = [(nvcc, s, os.path.join(BUILD, s.replace('.cu', '.o')), verbose) for s in SOURCES]
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
@@ -73,11 +86,13 @@ def build(force=False, verbose=False):
         failed |= rc != 0
     if failed:
         raise RuntimeError('nvcc failed, see log above')
+    tmp = LIB + f'.tmp{os.getpid()}'
     cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC',
-           '-o', LIB] + [j[2] for j in jobs]
+           '-o', tmp] + [j[2] for j in jobs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
+    os.replace(tmp, LIB)  # atomic: a concurrent dlopen sees the old or the new library, never a partial file
     with open(stamp, 'w') as f:
         f.write(digest)
     return LIB

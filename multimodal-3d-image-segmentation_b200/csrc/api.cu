@@ -82,7 +82,7 @@ int complex_modemix_backward(const float*, const float*, const float*, const flo
                              float*, float*, float*, int, int, int, long, int, cudaStream_t);
 int to_categorical(const void*, int, float*, int*, int, int, long, cudaStream_t);
 size_t normalize_workspace_bytes(int);
-int normalize_modalities(const float*, float*, void*, int, long, int, float, int, float, float, cudaStream_t);
+int normalize_modalities(const void*, int, float*, void*, int, long, int, float, int, float, float, cudaStream_t);
 int adamax_step(float*, const float*, float*, float*, long, float, float, float, float, float, int, float,
                 cudaStream_t);
 
@@ -281,7 +281,13 @@ size_t hno_normalize_workspace_bytes(int rows) { return normalize_workspace_byte
 
 int hno_normalize_modalities(const float* data, float* out, void* workspace, int rows, long n, int has_mask,
                              float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream) {
-  return normalize_modalities(data, out, workspace, rows, n, has_mask, mask_val, has_clip, clip_lo, clip_hi,
+  return normalize_modalities(data, 4, out, workspace, rows, n, has_mask, mask_val, has_clip, clip_lo, clip_hi,
+                              ST(stream));
+}
+
+int hno_normalize_modalities_i16(const short* data, float* out, void* workspace, int rows, long n, int has_mask,
+                                 float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream) {
+  return normalize_modalities(data, 2, out, workspace, rows, n, has_mask, mask_val, has_clip, clip_lo, clip_hi,
                               ST(stream));
 }
 

@@ -88,12 +88,22 @@ __device__ __forceinline__ float norm_clip(float v, const NormArgs& a) {
   return a.has_clip ? fminf(fmaxf(v, a.clip_lo), a.clip_hi) : v;  // np.clip
 }
 
+// Storage types of the raw modalities: fp32 (what the reference's loader hands over) or int16 (the NIfTI storage type of
+// BraTS volumes: shipping it halves the host -> device bytes of a batch; the conversion is exact)
+__device__ __forceinline__ float4 norm_ld4(const float* p, long i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
+__device__ __forceinline__ float4 norm_ld4(const int16_t* p, long i) {
+  const short4 q = __ldg(reinterpret_cast<const short4*>(p) + i);
+  return make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
+}
+__device__ __forceinline__ float norm_ld1(const float* p, long i) { return __ldg(p + i); }
+__device__ __forceinline__ float norm_ld1(const int16_t* p, long i) { return (float)__ldg(p + i); }
+
 // grid (chunks, rows): partials [rows][chunks][3] = (count, sum, sum of squares) of the unmasked, clipped voxels
-template <int V>
-__global__ void __launch_bounds__(256) k_norm_moments(const float* __restrict__ x, double* __restrict__ partials, long n,
+template <int V, typename T>
+__global__ void __launch_bounds__(256) k_norm_moments(const T* __restrict__ x, double* __restrict__ partials, long n,
                                                       NormArgs a) {
   __shared__ double sred[8][3];
-  const float* p = x + (long)blockIdx.y * n;
+  const T* p = x + (long)blockIdx.y * n;
   float s = 0.f, ss = 0.f;
   double cnt = 0.0, sd = 0.0, ssd = 0.0;
   int c32 = 0, run = 0;
@@ -107,10 +117,10 @@ __global__ void __launch_bounds__(256) k_norm_moments(const float* __restrict__ 
   };
   for (long i = blockIdx.x * 256L + threadIdx.x; i < n / V; i += (long)gridDim.x * 256L) {
     if (V == 4) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+      const float4 q = norm_ld4(p, i);
       add(q.x), add(q.y), add(q.z), add(q.w);
     } else {
-      add(__ldg(p + i));
+      add(norm_ld1(p, i));
     }
     if (++run == 32 / V) {  // bounded fp32 run length (raw intensities reach 1e3 - 1e4), then into fp64
       sd += (double)s, ssd += (double)ss, cnt += (double)c32;
@@ -149,10 +159,10 @@ __global__ void __launch_bounds__(32) k_norm_finalize(const double* __restrict__
   }
 }
 
-template <int V>
-__global__ void __launch_bounds__(256) k_norm_apply(const float* __restrict__ x, float* __restrict__ out,
+template <int V, typename T>
+__global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ x, float* __restrict__ out,
                                                     const float* __restrict__ stats, long n, NormArgs a) {
-  const float* p = x + (long)blockIdx.y * n;
+  const T* p = x + (long)blockIdx.y * n;
   float* o = out + (long)blockIdx.y * n;
   const float mean = stats[blockIdx.y * 2 + 0], sd = stats[blockIdx.y * 2 + 1];
   auto f = [&](float v) {
@@ -161,10 +171,10 @@ __global__ void __launch_bounds__(256) k_norm_apply(const float* __restrict__ x,
   };
   for (long i = blockIdx.x * 256L + threadIdx.x; i < n / V; i += (long)gridDim.x * 256L) {
     if (V == 4) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+      const float4 q = norm_ld4(p, i);
       reinterpret_cast<float4*>(o)[i] = make_float4(f(q.x), f(q.y), f(q.z), f(q.w));
     } else {
-      o[i] = f(__ldg(p + i));
+      o[i] = f(norm_ld1(p, i));
     }
   }
 }
@@ -173,28 +183,40 @@ size_t normalize_workspace_bytes(int rows) {
   return (size_t)rows * kNormChunks * 3 * sizeof(double) + (size_t)rows * 2 * sizeof(float) + 256;
 }
 
-int normalize_modalities(const float* data, float* out, void* ws, int rows, long n, int has_mask, float mask_val,
-                         int has_clip, float clip_lo, float clip_hi, cudaStream_t st) {
+template <typename T>
+static int normalize_modalities_t(const T* data, float* out, void* ws, int rows, long n, int has_mask, float mask_val,
+                                  int has_clip, float clip_lo, float clip_hi, cudaStream_t st) {
   HNO_CHECK(data && out && ws, "normalize_modalities: null pointer");
   HNO_CHECK(rows >= 1 && rows <= 65535 && n >= 1, "normalize_modalities: bad sizes");
   HNO_CHECK(!has_clip || clip_lo <= clip_hi, "normalize_modalities: clip_val must be (min, max)");
   double* partials = reinterpret_cast<double*>(ws);
   float* stats = reinterpret_cast<float*>(partials + (size_t)rows * kNormChunks * 3);
   const NormArgs a{has_mask, has_clip, mask_val, clip_lo, clip_hi};
-  const bool v4 = n % 4 == 0 && ((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const bool v4 = n % 4 == 0 && (reinterpret_cast<uintptr_t>(data) % (4 * sizeof(T))) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const long items = v4 ? n / 4 : n;
   const int chunks = (int)((items + 255) / 256 < kNormChunks ? (items + 255) / 256 : kNormChunks);
   dim3 g1(chunks, rows);
-  if (v4) k_norm_moments<4><<<g1, 256, 0, st>>>(data, partials, n, a);
-  else k_norm_moments<1><<<g1, 256, 0, st>>>(data, partials, n, a);
+  if (v4) k_norm_moments<4, T><<<g1, 256, 0, st>>>(data, partials, n, a);
+  else k_norm_moments<1, T><<<g1, 256, 0, st>>>(data, partials, n, a);
   HNO_LAUNCH_CHECK();
   k_norm_finalize<<<rows, 32, 0, st>>>(partials, chunks, stats);
   HNO_LAUNCH_CHECK();
   dim3 g2((unsigned)((items + 255) / 256 < 1184 ? (items + 255) / 256 : 1184), rows);
-  if (v4) k_norm_apply<4><<<g2, 256, 0, st>>>(data, out, stats, n, a);
-  else k_norm_apply<1><<<g2, 256, 0, st>>>(data, out, stats, n, a);
+  if (v4) k_norm_apply<4, T><<<g2, 256, 0, st>>>(data, out, stats, n, a);
+  else k_norm_apply<1, T><<<g2, 256, 0, st>>>(data, out, stats, n, a);
   HNO_LAUNCH_CHECK();
   return 0;
+}
+
+int normalize_modalities(const void* data, int elem_bytes, float* out, void* ws, int rows, long n, int has_mask,
+                         float mask_val, int has_clip, float clip_lo, float clip_hi, cudaStream_t st) {
+  if (elem_bytes == 4)
+    return normalize_modalities_t(static_cast<const float*>(data), out, ws, rows, n, has_mask, mask_val, has_clip,
+                                  clip_lo, clip_hi, st);
+  HNO_CHECK(elem_bytes == 2, "normalize_modalities: element size must be 4 (float32) or 2 (int16), got %d", elem_bytes);
+  return normalize_modalities_t(static_cast<const int16_t*>(data), out, ws, rows, n, has_mask, mask_val, has_clip,
+                                clip_lo, clip_hi, st);
 }
 
 }  // namespace hno

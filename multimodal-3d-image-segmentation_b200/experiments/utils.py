@@ -51,14 +51,28 @@ def to_categorical(y, num_classes=None, validate=True):
 def normalize_modalities(data, mask_val=None, clip_val=None):
     """Normalises every slice along the first axis (one modality each) separately  (experiments/utils.py:25-71):
     optional clip to `clip_val = (min, max)`, mean / std over the voxels that differ from `mask_val` (after clipping; all
-    voxels when mask_val is None), (x - mean) / std, masked voxels set to 0.  Returns float32."""
+    voxels when mask_val is None), (x - mean) / std, masked voxels set to 0.  Returns float32.
+
+    int16 input (the storage type of the NIfTI volumes) is read as it is -- the conversion to float32 is exact and
+    happens inside the kernels, so a raw batch can cross PCIe at half the bytes; `out` lets the caller pass the
+    destination (e.g. a buffer whose address a captured CUDA graph already holds)."""
+    return normalize_rows(data, data.shape[0], mask_val, clip_val)
+
+
+def normalize_rows(data, rows, mask_val=None, clip_val=None, out=None):
+    """normalize_modalities with the number of independently normalised rows given explicitly: a batch (B, C, *spatial)
+    is B * C rows (each sample and modality separately, which is what the reference's per-sample x_processing does)."""
     _cuda(data, 'data')
-    x = data.to(torch.float32).contiguous()
-    rows = x.shape[0]
+    x = data.contiguous() if data.dtype in (torch.float32, torch.int16) else data.to(torch.float32).contiguous()
+    rows = int(rows)
     n = x.numel() // rows
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    elif out.dtype != torch.float32 or out.numel() != x.numel() or not out.is_contiguous() or out.device != x.device:
+        raise ValueError('normalize_rows: out must be a contiguous float32 CUDA tensor of the size of data')
     ws = workspace(_lib.load().hno_normalize_workspace_bytes(rows), x.device, 'normalize')
     lo, hi = (float(clip_val[0]), float(clip_val[1])) if clip_val is not None else (0.0, 0.0)
-    call('hno_normalize_modalities', ptr(x), ptr(out), ptr(ws), rows, n, int(mask_val is not None),
+    fn = 'hno_normalize_modalities_i16' if x.dtype == torch.int16 else 'hno_normalize_modalities'
+    call(fn, ptr(x), ptr(out), ptr(ws), rows, n, int(mask_val is not None),
          float(mask_val) if mask_val is not None else 0.0, int(clip_val is not None), lo, hi, stream_ptr())
     return out

@@ -10,6 +10,7 @@ from ._lib import call, ptr, stream_ptr
 from .plan import get_crop_plan, get_interp_tables
 
 _ws_cache = {}
+_ws_retired = []  # outgrown scratch buffers stay alive: captured CUDA graphs have their addresses baked in
 
 
 def _require_cuda(t, name):
@@ -17,14 +18,24 @@ def _require_cuda(t, name):
         raise RuntimeError(f'hno_b200: {name} must be a CUDA tensor (got {t.device}); this package has no CPU path')
     if t.dtype != torch.float32:
         raise RuntimeError(f'hno_b200: {name} must be float32 (got {t.dtype})')
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's stream (the reference sets it once, experiments/run.py:38-40)
+        raise RuntimeError(f'hno_b200: {name} lives on {t.device} but the current CUDA device is '
+                           f'cuda:{torch.cuda.current_device()}; call torch.cuda.set_device({t.device.index}) first')
 
 
 def workspace(nbytes, device, tag):
-    """Grow-only scratch buffer per (device, tag); kernels on one stream are serialised so reuse is safe."""
-    key = (str(device), tag)
+    """Grow-only scratch buffer per (device, stream, tag).  Kernels on one stream are serialised, so reuse within a
+    stream is safe; different streams get different buffers.  A buffer that is outgrown is retired, not freed:
+    parallel.Trainer replays CUDA graphs that captured its address (a later, larger request -- validation at another
+    batch size, a super-resolution grid -- must not hand that memory back to the caching allocator)."""
+    dev = torch.device(device)
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream if dev.type == 'cuda' else 0, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = _ws_cache[key] = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        if buf is not None:
+            _ws_retired.append(buf)
+        buf = _ws_cache[key] = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
     return buf
 
 

@@ -46,6 +46,22 @@ class FlatParameters:
                 return g
         raise KeyError('parameter is not part of this flat buffer')
 
+    def repack_grads_(self):
+        """Makes `self.grad` hold every parameter's current gradient again and re-points p.grad at its view.
+
+        `optimizer.zero_grad()` (set_to_none=True is the default, and it is what the reference loop calls at
+        experiments/train_test.py:164) drops p.grad, so the next backward allocates fresh gradient tensors
+        OUTSIDE the flat buffer.  A parameter whose .grad is None contributes zeros."""
+        with torch.no_grad():
+            for p, gv in zip(self.params, self.grad_views):
+                g = p.grad
+                if g is None:
+                    gv.zero_()
+                elif g.data_ptr() != gv.data_ptr() or g.shape != gv.shape:
+                    gv.copy_(g.reshape(gv.shape))
+                p.grad = gv
+        return self.grad
+
 
 def allreduce_mean_(flat_grad, group=None):
     """SUM all-reduce + 1/world scaling of the flat gradient: the only collective of a training step."""
@@ -59,6 +75,7 @@ def attach_gradient_allreduce(optimizer, flat, group=None):
     """Drop-in hook for ANY torch.optim optimizer used by experiments/train_test.py:164-171: averages the flat
     gradient across ranks right before optimizer.step(), leaving the reference's training loop untouched."""
     def hook(opt, args, kwargs):
+        flat.repack_grads_()  # survive optimizer.zero_grad(set_to_none=True): gradients may live outside the buffer
         allreduce_mean_(flat.grad, group)
     return optimizer.register_step_pre_hook(hook)
 
@@ -81,13 +98,57 @@ class FusedAdamax:
              float(self.eps), float(self.weight_decay), self.step_count, 1.0, stream_ptr())
 
     def state_dict(self):
-        return {'exp_avg': self.exp_avg, 'exp_inf': self.exp_inf, 'step': self.step_count, 'lr': self.lr}
+        """Snapshot (cloned tensors) of the flat optimizer state."""
+        return {'exp_avg': self.exp_avg.clone(), 'exp_inf': self.exp_inf.clone(), 'step': self.step_count,
+                'lr': self.lr}
 
     def load_state_dict(self, sd):
+        if 'state' in sd and 'param_groups' in sd:  # a torch.optim.Adamax checkpoint of the reference's loop
+            return self.load_torch_state_dict(sd)
         self.exp_avg.copy_(sd['exp_avg'])
         self.exp_inf.copy_(sd['exp_inf'])
         self.step_count = int(sd['step'])
         self.lr = sd.get('lr', self.lr)
+
+    # -- interchange with torch.optim.Adamax (the 'optimizer_state_dict' of experiments/train_test.py:262-286) --
+    def torch_state_dict(self):
+        """The same state in torch.optim.Adamax.state_dict() layout; parameter i = i-th of model.parameters()."""
+        state = {}
+        off = 0
+        for i, p in enumerate(self.flat.params):
+            k = p.numel()
+            state[i] = {'step': torch.tensor(float(self.step_count)),
+                        'exp_avg': self.exp_avg[off:off + k].view(p.shape).clone(),
+                        'exp_inf': self.exp_inf[off:off + k].view(p.shape).clone()}
+            off += k
+        group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': self.weight_decay,
+                 'foreach': None, 'maximize': False, 'differentiable': False, 'capturable': False,
+                 'params': list(range(len(self.flat.params)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_torch_state_dict(self, sd):
+        group = sd['param_groups'][0]
+        ids = list(group['params'])
+        if len(ids) != len(self.flat.params):
+            raise ValueError('optimizer checkpoint has a different number of parameters')
+        off = 0
+        step = 0
+        for pid, p in zip(ids, self.flat.params):
+            k = p.numel()
+            st = sd['state'].get(pid)
+            if st is None:
+                self.exp_avg[off:off + k].zero_()
+                self.exp_inf[off:off + k].zero_()
+            else:
+                self.exp_avg[off:off + k].copy_(st['exp_avg'].reshape(-1))
+                self.exp_inf[off:off + k].copy_(st['exp_inf'].reshape(-1))
+                step = max(step, int(float(st['step'])))
+            off += k
+        self.step_count = step
+        self.lr = group.get('lr', self.lr)
+        self.betas = tuple(group.get('betas', self.betas))
+        self.eps = group.get('eps', self.eps)
+        self.weight_decay = group.get('weight_decay', self.weight_decay)
 
 
 class Trainer:
@@ -107,6 +168,7 @@ class Trainer:
         self.use_graph = (os.environ.get('HNO_GRAPH', '1') != '0') if use_graph is None else bool(use_graph)
         self._graphs = {}
         self._pool = None
+        self._xnorm = {}
         self.model = model
         self.engine = model.engine()
         # CrossEntropyLoss (kind None) is not of the five-moment form: head kernel + one-pass CE kernels + head backward
@@ -166,6 +228,20 @@ class Trainer:
         allreduce_mean_(self.flat.grad, self.group)
         self.optimizer.step(lr)
         return loss
+
+    def step_raw(self, x_raw, labels, lr=None, mask_val=0, clip_val=None):
+        """step() on RAW modalities in their storage type: `x_raw` (B, C, D, H, W) int16 (or float32) un-normalised
+        intensities as the reader returns them (experiments/utils.py:260-270).  The per-sample, per-modality z-scoring the
+        reference runs in its loader workers (`x_processing = normalize_modalities(mask_val=0)`, experiments/run.py:52-55,
+        data_io/dataset.py:49-50) happens here on the device, so a batch crosses PCIe at 2 bytes per voxel instead of 4.
+        The normalised batch lives in one buffer owned by the trainer (its address is what the CUDA graph captured)."""
+        from .experiments.utils import normalize_rows
+        key = (tuple(x_raw.shape), x_raw.device)
+        buf = self._xnorm.get(key)
+        if buf is None:
+            buf = self._xnorm[key] = torch.empty(x_raw.shape, dtype=torch.float32, device=x_raw.device)
+        normalize_rows(x_raw, x_raw.shape[0] * x_raw.shape[1], mask_val=mask_val, clip_val=clip_val, out=buf)
+        return self.step(buf, labels, lr)
 
 
 _graph_launches = 0  # kernels of libhno_b200.so launched through CUDA-graph replays (the library only counts direct ones)

@@ -470,3 +470,18 @@ def test_normalize_modalities(cuda, golden_dir):
     odd[1] = 0
     y = normalize_modalities(torch.from_numpy(odd).to(cuda), mask_val=0).cpu().numpy()
     assert np.abs(y - orc.normalize_modalities(odd, mask_val=0)).max() < 1e-5 and np.all(y[1] == 0)
+    # the int16 kernels (raw NIfTI storage type on the wire) are bit-identical to the fp32 ones, also at ragged lengths and
+    # for a batch normalised row by row into a caller-provided buffer
+    from multimodal_3d_image_segmentation_b200.experiments.utils import normalize_rows
+    yf = normalize_modalities(torch.from_numpy(big.astype(np.float32)).to(cuda), mask_val=0).cpu().numpy()
+    assert np.array_equal(y16 := normalize_modalities(torch.from_numpy(big).to(cuda), mask_val=0).cpu().numpy(), yf)
+    odd16 = np.round(odd * 3).astype(np.int16)
+    a = normalize_modalities(torch.from_numpy(odd16).to(cuda), mask_val=0).cpu().numpy()
+    b = normalize_modalities(torch.from_numpy(odd16.astype(np.float32)).to(cuda), mask_val=0).cpu().numpy()
+    assert np.array_equal(a, b)
+    batch = torch.from_numpy(np.stack([big[:, :20], big[:, 20:40]])).to(cuda)  # (2, 4, 20, 240, 240) int16
+    out = torch.empty(batch.shape, dtype=torch.float32, device=cuda)
+    normalize_rows(batch, 8, mask_val=0, out=out)
+    for i in range(2):
+        assert np.abs(out[i].cpu().numpy() - orc.normalize_modalities(batch[i].cpu().numpy(), mask_val=0)).max() < 2e-5
+    del y16

@@ -32,10 +32,14 @@ def _worker(rank, world, port, out_dir):
     parallel.attach_gradient_allreduce(opt, flat)
     g = torch.Generator().manual_seed(100 + rank)  # this rank's shard of the global batch
     x = torch.randn(4, 5, generator=g)
-    loss = model(x).pow(2).mean()
-    flat.grad.zero_()
-    loss.backward()  # accumulates into the flat gradient views
-    opt.step()       # pre-hook: ONE all-reduce + 1/world
+    # two steps exactly as the reference loop writes them (experiments/train_test.py:164-171): zero_grad() defaults to
+    # set_to_none=True, which detaches p.grad from the flat buffer; the hook has to re-pack before it reduces
+    for it in range(2):
+        loss = model(x + it).pow(2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()       # pre-hook: re-pack + ONE all-reduce + 1/world
+        assert all(p.grad.data_ptr() == gv.data_ptr() for p, gv in zip(flat.params, flat.grad_views))
     torch.save({'params': flat.data.clone(), 'grad': flat.grad.clone()}, os.path.join(out_dir, f'r{rank}.pt'))
     dist.barrier()
     dist.destroy_process_group()
@@ -52,9 +56,11 @@ def test_two_rank_step_equals_single_rank_on_the_concatenated_batch(tmp_path):
     model = _make_module()
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     xs = [torch.randn(4, 5, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
-    loss = sum(model(x).pow(2).mean() for x in xs) / world
-    loss.backward()
-    opt.step()
+    for it in range(2):
+        loss = sum(model(x + it).pow(2).mean() for x in xs) / world
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
     ref = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     assert torch.allclose(res[0]['params'], ref, rtol=1e-6, atol=1e-7)
 
@@ -63,3 +69,47 @@ def test_allreduce_is_identity_without_process_group():
     from multimodal_3d_image_segmentation_b200 import parallel
     g = torch.arange(6, dtype=torch.float32)
     assert torch.equal(parallel.allreduce_mean_(g.clone()), g)
+
+
+def test_repack_after_zero_grad_set_to_none():
+    """optimizer.zero_grad() drops p.grad; backward then allocates gradients outside the flat buffer."""
+    from multimodal_3d_image_segmentation_b200 import parallel
+    model = _make_module()
+    flat = parallel.FlatParameters(model)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    opt.zero_grad()
+    assert all(p.grad is None for p in model.parameters())
+    model(torch.ones(2, 5)).sum().backward()
+    assert flat.grad.abs().sum() == 0  # the situation the hook has to repair
+    want = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    flat.repack_grads_()
+    assert torch.equal(flat.grad, want)
+    assert all(p.grad.data_ptr() == gv.data_ptr() for p, gv in zip(flat.params, flat.grad_views))
+    # a parameter without gradient contributes zeros
+    opt.zero_grad()
+    model[0](torch.ones(2, 5)).sum().backward()
+    flat.repack_grads_()
+    assert flat.grad_views[2].abs().sum() == 0 and flat.grad_views[0].abs().sum() > 0
+
+
+def test_fused_adamax_state_dict_is_a_snapshot_and_converts_to_torch_layout():
+    from multimodal_3d_image_segmentation_b200 import parallel
+    model = _make_module()
+    flat = parallel.FlatParameters(model)
+    opt = parallel.FusedAdamax(flat, lr=1e-2)
+    opt.exp_avg.fill_(0.5)
+    opt.exp_inf.fill_(0.25)
+    opt.step_count = 7
+    sd = opt.state_dict()
+    opt.exp_avg.add_(1.0)
+    assert torch.all(sd['exp_avg'] == 0.5)  # cloned, not the live tensor
+    tsd = opt.torch_state_dict()
+    ref = torch.optim.Adamax(_make_module().parameters(), lr=5e-3)
+    ref.load_state_dict(tsd)  # the reference's optimizer accepts it (train_test.py:276-286)
+    assert ref.state_dict()['param_groups'][0]['lr'] == 1e-2
+    st = ref.state_dict()['state']
+    assert sorted(st) == [0, 1, 2, 3] and float(st[1]['step']) == 7 and st[1]['exp_avg'].shape == (3,)
+    opt2 = parallel.FusedAdamax(parallel.FlatParameters(_make_module()), lr=5e-3)
+    opt2.load_state_dict(ref.state_dict())  # and back
+    assert opt2.step_count == 7 and opt2.lr == 1e-2
+    assert torch.all(opt2.exp_avg == 1.5) and torch.all(opt2.exp_inf == 0.25)
