@@ -157,6 +157,11 @@ int hno_interp_tables_fill(void* host_buf, size_t bytes, int D, int H, int W, in
 /* logits_low [B][C][D][P] -> probs [B][C][Dx][Hx][Wx] (dense).  C <= 8.  activation: 0 none, 1 softmax. */
 int hno_head_forward(const void* tables_host, const void* tables_dev, const float* logits_low, float* probs, int B,
                      int C, long P, int activation, void* stream);
+/* Inference head: logits_low [B][C][D][P] -> labels [B][Dx][Hx][Wx] uint8 = argmax over the classes of the up-sampled
+ * logits, i.e. the label map experiments/train_test.py:402-408 computes with np.argmax(probs, 1) on the host after copying
+ * the probabilities back; here one byte per voxel leaves the device. */
+int hno_head_argmax(const void* tables_host, const void* tables_dev, const float* logits_low, unsigned char* labels,
+                    int B, int C, long P, void* stream);
 size_t hno_head_backward_workspace_bytes(const void* tables_host, int B, int C);
 /* dprobs, probs [B][C][Dx][Hx][Wx] -> dlogits_low [B][C][D][P] (padding columns = 0). */
 int hno_head_backward(const void* tables_host, const void* tables_dev, const float* dprobs, const float* probs,

@@ -63,6 +63,7 @@ int stem_backward(const float*, const float*, float*, float*, void*, int, int, i
 size_t interp_tables_bytes(int, int, int, int, int, int);
 int interp_tables_fill(void*, size_t, int, int, int, int, int, int);
 int head_forward(const void*, const void*, const float*, float*, int, int, long, int, cudaStream_t);
+int head_argmax(const void*, const void*, const float*, uint8_t*, int, int, long, cudaStream_t);
 size_t head_backward_workspace_bytes(const void*, int, int);
 int head_backward(const void*, const void*, const float*, const float*, float*, void*, int, int, long, int,
                   cudaStream_t);
@@ -205,6 +206,11 @@ size_t hno_interp_tables_bytes(int D, int H, int W, int Dx, int Hx, int Wx) {
 
 int hno_interp_tables_fill(void* host_buf, size_t bytes, int D, int H, int W, int Dx, int Hx, int Wx) {
   return interp_tables_fill(host_buf, bytes, D, H, W, Dx, Hx, Wx);
+}
+
+int hno_head_argmax(const void* tables_host, const void* tables_dev, const float* logits_low, unsigned char* labels,
+                    int B, int C, long P, void* stream) {
+  return head_argmax(tables_host, tables_dev, logits_low, labels, B, C, P, ST(stream));
 }
 
 int hno_head_forward(const void* tables_host, const void* tables_dev, const float* logits_low, float* probs, int B,

@@ -206,6 +206,34 @@ __global__ void __launch_bounds__(256) k_head_fwd(const float* __restrict__ ll, 
   for (int c = 0; c < C; ++c) po[(long)c * Nx] = lg[c];
 }
 
+// Inference head: the label map itself.  argmax over the classes of the interpolated logits (softmax is monotone, so
+// this is the label the reference gets from np.argmax(probs, 1) on the host, experiments/train_test.py:402-408; ties
+// go to the lowest class index like numpy).  One byte per voxel leaves the device instead of 4 * C.
+template <int C>
+__global__ void __launch_bounds__(256) k_head_argmax(const float* __restrict__ ll, uint8_t* __restrict__ labels,
+                                                     InterpDev t, long P) {
+  const long Nx = (long)t.hi[0] * t.hi[1] * t.hi[2];
+  const long v = blockIdx.x * 256L + threadIdx.x;
+  if (v >= Nx) return;
+  const int b = blockIdx.y;
+  const int zw = (int)(v % t.hi[2]);
+  const long r = v / t.hi[2];
+  const int zh = (int)(r % t.hi[1]);
+  const int zd = (int)(r / t.hi[1]);
+  const long S = (long)t.lo[0] * P;
+  float lg[C];
+  interp_logits<C>(ll + (long)b * C * S, S, P, t.lo[2], t, zd, zh, zw, lg);
+  int best = 0;
+  float m = lg[0];
+#pragma unroll
+  for (int c = 1; c < C; ++c)
+    if (lg[c] > m) {
+      m = lg[c];
+      best = c;
+    }
+  labels[(long)b * Nx + v] = (uint8_t)best;
+}
+
 // ------------------------------------------------------------------------------------------ head backward
 // MODE 0: dprobs / probs tensors are given (drop-in autograd path).
 // MODE 1: probabilities are recomputed from the low-resolution logits and dL/dprobs comes from the
@@ -947,6 +975,19 @@ int head_forward(const void* th, const void* td, const float* ll, float* probs, 
     if (activation == 1) k_head_fwd<kC, 1><<<grid, 256, 0, st>>>(ll, probs, t, P);
     else k_head_fwd<kC, 0><<<grid, 256, 0, st>>>(ll, probs, t, P);
   })
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+int head_argmax(const void* th, const void* td, const float* ll, uint8_t* labels, int B, int C, long P,
+                cudaStream_t st) {
+  InterpDev t;
+  if (make_dev(th, td, &t)) return -1;
+  HNO_CHECK(ll && labels, "head_argmax: null pointer");
+  HNO_CHECK(P >= (long)t.lo[1] * t.lo[2], "head_argmax: plane pitch too small");
+  const long Nx = (long)t.hi[0] * t.hi[1] * t.hi[2];
+  dim3 grid(ceil_div(Nx, 256), B);
+  HNO_CLASS_SWITCH(C, { k_head_argmax<kC><<<grid, 256, 0, st>>>(ll, labels, t, P); })
   HNO_LAUNCH_CHECK();
   return 0;
 }

@@ -226,6 +226,14 @@ class HNOSegXS(nn.Module):
             _, S = self.engine().run_forward(x, save=False, head=False)
             return ops.head_forward(S.ll, S.tables, S.geom[3], 0)
 
+    def predict_labels(self, x):
+        """Inference as experiments/train_test.py:398-408 uses the model (forward under no_grad, argmax over the classes),
+        with the argmax on the device: returns the uint8 label map (B, D, H, W).  The probabilities are never
+        materialised (4 bytes x classes per voxel neither written nor copied back)."""
+        with torch.no_grad():
+            _, S = self.engine().run_forward(x, save=False, head=False)
+            return ops.head_argmax(S.ll, S.tables, S.geom[3])
+
     def loss(self, x, labels, loss_name='DiceLoss', param=None):
         """Fused head + loss on integer labels; equals loss_fn(self(x), to_categorical(labels)) for loss_name in
         DiceLoss / PCCLoss / ExpDiceLoss(exp=param) / CrossEntropyLoss."""

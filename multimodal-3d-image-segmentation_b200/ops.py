@@ -407,6 +407,16 @@ def head_forward(logits_low, tables, pitch, activation=1):
     return probs
 
 
+def head_argmax(logits_low, tables, pitch):
+    """uint8 label map (B, Dx, Hx, Wx): argmax over the classes of the up-sampled logits (reference: np.argmax of the
+    probabilities on the host, experiments/train_test.py:402-408)."""
+    B, C = logits_low.shape[:2]
+    labels = torch.empty((B,) + tuple(tables.hi), dtype=torch.uint8, device=logits_low.device)
+    call('hno_head_argmax', tables.host.data_ptr(), tables.dev.data_ptr(), ptr(logits_low), ptr(labels), B, C, pitch,
+         stream_ptr())
+    return labels
+
+
 def head_backward(dprobs, probs, tables, pitch, activation=1):
     B, C = dprobs.shape[:2]
     D, H, W = tables.lo

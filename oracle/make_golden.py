@@ -392,12 +392,51 @@ def case_full():
     save('model_full_probe', **out)
 
 
+def case_superres():
+    """BASELINE config 4: zero-shot super-resolution = the SAME weights on a 2x grid (README.md:83-87), run through the
+    reference's testing path (experiments/train_test.py:373-414: model.eval(), no_grad, forward, host argmax).  Stores the
+    reference's logits / probabilities / label map at 8192 sampled voxels of the 1x4x480x480x310 volume."""
+    torch.manual_seed(0)
+    model = ref.HNOSegXS(4, 4, 24, [3] * 8, (10, 14, 14))
+    model.eval()
+    x = torch.randn(1, 4, 480, 480, 310, generator=torch.Generator().manual_seed(9))
+    logits = {}
+    model.conv_out.register_forward_hook(lambda m, i, o: logits.__setitem__('v', o.detach()))
+    with torch.no_grad():
+        probs = model(x)
+    lg = logits['v']
+    labels = np.argmax(probs.numpy(), axis=1).astype(np.uint8)  # train_test.py:402-408
+    idx = torch.randint(0, 480 * 480 * 310, (8192,), generator=torch.Generator().manual_seed(78))
+    out = {'idx': idx.numpy(), 'logits_at_idx': lg.reshape(4, -1)[:, idx].numpy(),
+           'probs_at_idx': probs.reshape(4, -1)[:, idx].numpy(), 'labels_at_idx': labels.reshape(-1)[idx.numpy()],
+           'logits_norm': np.float32(lg.norm().item()), 'label_hist': np.bincount(labels.reshape(-1), minlength=4)}
+    # top-2 logit margin of every sampled voxel (the GPU test may only disagree where the margin is within round-off)
+    top2 = lg.reshape(4, -1)[:, idx].topk(2, dim=0).values
+    out['margin_at_idx'] = (top2[0] - top2[1]).numpy()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    full = dict(np.load(os.path.join(GOLDEN, 'model_full_probe.npz')))
+    for k, v in sd.items():  # same weights as the 1x probe: the fixture does not repeat them
+        assert np.array_equal(full[f'sd/{k}'], v.numpy()), k
+    del probs, lg
+    with torch.no_grad():
+        _, o_logits = orc.hnosegxs_forward(sd, x, [3] * 8, (10, 14, 14), return_logits=True)
+    o_at = o_logits.reshape(4, -1)[:, idx]
+    rel = ((o_at - torch.from_numpy(out['logits_at_idx'])).norm() / torch.from_numpy(out['logits_at_idx']).norm()).item()
+    print(f'  2x grid: oracle vs reference logits rel-L2 at the probe {rel:.2e}')
+    assert rel < 1e-5
+    save('model_superres_probe', **out)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--full', action='store_true')
+    ap.add_argument('--only', default=None, help='run a single case function by name, e.g. case_superres')
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
+    if args.only:
+        globals()[args.only]()
+        sys.exit(0)
     case_dht()
     case_operator()
     case_operator_transform_individual()
@@ -415,4 +454,5 @@ if __name__ == '__main__':
     case_hnoseg('Fourier', 'fno_small', weights_type='individual', use_bias_conv_branch=True, use_block_skip=False)
     if args.full:
         case_full()
+        case_superres()
     print('all oracle-vs-reference checks passed')

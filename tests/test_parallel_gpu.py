@@ -1,0 +1,81 @@
+"""Numerical parity of the data-parallel step over NCCL: N ranks on shards == one rank on the whole batch.
+
+Needs >= 2 GPUs (skipped otherwise): `gpurun --gpus 2 -- python -m pytest tests/test_parallel_gpu.py -m gpu`.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(in_channels=4, out_channels=4, filters=24, num_transform_blocks=[3] * 8, num_modes=(10, 14, 14))
+SHAPE = (64, 56, 48)
+PER_RANK = 2
+STEPS = 3
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _batch(rank, step):
+    g = torch.Generator().manual_seed(1000 + 17 * rank + step)
+    x = torch.randn(PER_RANK, 4, *SHAPE, generator=g)
+    lab = torch.randint(0, 4, (PER_RANK, 1, *SHAPE), generator=g).to(torch.uint8)
+    return x, lab
+
+
+def _worker(rank, world, port, out_dir, loss_name):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    from multimodal_3d_image_segmentation_b200 import nets, parallel
+    from oracle import hno_oracle as orc
+    model = nets.HNOSegXS(**CFG, device=dev)
+    model.load_state_dict(orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14), seed=0))
+    tr = parallel.Trainer(model, loss_name, lr=5e-3)
+    losses = []
+    for step in range(STEPS):
+        x, lab = _batch(rank, step)
+        losses.append(float(tr.step(x.to(dev), lab.to(dev))))
+    torch.save({'params': tr.flat.data.cpu(), 'grad': tr.flat.grad.cpu(), 'losses': losses},
+               os.path.join(out_dir, f'r{rank}.pt'))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('loss_name', ['DiceLoss', 'PCCLoss'])
+def test_nccl_two_rank_step_equals_single_rank_on_the_concatenated_batch(cuda, tmp_path, loss_name):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), loss_name), nprocs=world, join=True)
+    res = [torch.load(os.path.join(tmp_path, f'r{r}.pt')) for r in range(world)]
+    assert torch.equal(res[0]['params'], res[1]['params'])  # replicas stay bit-identical
+    assert torch.equal(res[0]['grad'], res[1]['grad'])
+    from multimodal_3d_image_segmentation_b200 import nets, parallel
+    from oracle import hno_oracle as orc
+    model = nets.HNOSegXS(**CFG, device=cuda)
+    model.load_state_dict(orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14), seed=0))
+    tr = parallel.Trainer(model, loss_name, lr=5e-3)
+    losses = []
+    for step in range(STEPS):
+        xs, labs = zip(*[_batch(r, step) for r in range(world)])
+        losses.append(float(tr.step(torch.cat(xs).to(cuda), torch.cat(labs).to(cuda))))
+    # the global loss is the mean of the rank losses (means over (sample, label), nets/custom_losses.py:70,111)
+    for step in range(STEPS):
+        assert abs(losses[step] - (res[0]['losses'][step] + res[1]['losses'][step]) / 2) < 2e-6
+    single = tr.flat.data.cpu()
+    err = ((single - res[0]['params']).norm() / single.norm()).item()
+    print(f'{loss_name}: 2-rank vs single-rank parameters after {STEPS} steps rel-L2 {err:.2e}')
+    assert err < 1e-6, err
+    g = tr.flat.grad.cpu()
+    assert ((g - res[0]['grad']).norm() / g.norm()).item() < 1e-4
