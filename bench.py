@@ -29,6 +29,33 @@ sys.path.insert(0, ROOT)
 CFG = dict(in_channels=4, out_channels=4, filters=24, num_transform_blocks=[3] * 8, num_modes=(10, 14, 14))
 VOLUME = (240, 240, 155)
 METRIC = 'HNOSeg-XS train volumes/s @4x240x240x155'
+
+# --config: the driver runs the default (BASELINE.json config 2, the one `metric` is quoted on); the others give the
+# remaining BASELINE configs the same kind of line (committed under profiles/).
+SPECS = {
+    'xs_train': dict(
+        kind='train', model='HNOSegXS', kwargs=CFG, metric=METRIC, volume=VOLUME,
+        what='HNOSegXS(4,4,24,[3]*8,(10,14,14))', act_gb='~10 GB'),
+    'hnoseg_train': dict(  # experiments/config_files/config_hnoseg.ini
+        kind='train', model='NeuralOperatorSeg', volume=VOLUME,
+        kwargs=dict(in_channels=4, out_channels=4, filters=24, num_transform_blocks=24, num_modes=(10, 14, 14),
+                    transform_type='Hartley'),
+        metric='HNOSeg train volumes/s @4x240x240x155', what="NeuralOperatorSeg(4,4,24,24,(10,14,14),'Hartley')",
+        act_gb='~30 GB'),
+    'mha_train': dict(  # BASELINE config 5; hyper-parameters of tensorflow/experiments/config_files/config_hartleymha.ini:58-69
+        kind='train', model='HartleyMHASeg', volume=VOLUME,
+        kwargs=dict(in_channels=4, out_channels=4, filters=12, num_transform_blocks=16, num_heads=4,
+                    num_modes=(10, 14, 14), patch_size=(2, 2, 2)),
+        metric='HartleyMHASeg train volumes/s @4x240x240x155', what='HartleyMHASeg(4,4,12,16,4,(10,14,14),(2,2,2))',
+        act_gb='~15 GB'),
+    'superres_infer': dict(  # BASELINE config 4
+        kind='infer', model='HNOSegXS', kwargs=CFG, volume=(480, 480, 310),
+        metric='HNOSeg-XS 2x super-resolution inference volumes/s @4x480x480x310', what='HNOSegXS(4,4,24,[3]*8,(10,14,14))'),
+    'fnoseg_layer': dict(  # BASELINE config 3
+        kind='layer', metric='FNOSeg3D spectral layer fwd+bwd volumes/s @24x121x121x78',
+        what='FourierOperator(24,24,(10,14,14))'),
+}
+SPEC = SPECS['xs_train']
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
 
@@ -105,8 +132,14 @@ def oracle_step_factory(torch, batch):
     """The reference's training step (experiments/train_test.py:146-171) restated on the oracle: forward,
     to_categorical, DiceLoss, backward, Adamax -- on the host cores with all the threads torch can use."""
     from oracle import hno_oracle as orc
-    sd = orc.init_state_dict(CFG['in_channels'], CFG['out_channels'], CFG['filters'], CFG['num_transform_blocks'],
-                             CFG['num_modes'], seed=0)
+    kw = SPEC['kwargs']
+    if SPEC['model'] == 'HNOSegXS':
+        sd = orc.init_state_dict(CFG['in_channels'], CFG['out_channels'], CFG['filters'], CFG['num_transform_blocks'],
+                                 CFG['num_modes'], seed=0)
+    else:  # CPU-constructed twin of the CUDA module: same parameter names / shapes (the modules hold plain nn.Parameters)
+        from multimodal_3d_image_segmentation_b200 import nets
+        torch.manual_seed(0)
+        sd = {k: v.detach().clone() for k, v in getattr(nets, SPEC['model'])(**kw).state_dict().items()}
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     opt = torch.optim.Adamax(list(params.values()), lr=5e-3)
     g = torch.Generator().manual_seed(1234)
@@ -115,7 +148,10 @@ def oracle_step_factory(torch, batch):
 
     def step():
         y = orc.to_categorical(labels, 4)
-        probs = orc.hnosegxs_forward(params, x, CFG['num_transform_blocks'], CFG['num_modes'])
+        if SPEC['model'] == 'HNOSegXS':
+            probs = orc.hnosegxs_forward(params, x, CFG['num_transform_blocks'], CFG['num_modes'])
+        else:
+            probs = orc.hnoseg_forward(params, x, kw['num_transform_blocks'], kw['num_modes'], patch=kw.get('patch_size'))
         loss = orc.dice_loss(probs, y)
         value = loss.item()
         opt.zero_grad()
@@ -127,10 +163,10 @@ def oracle_step_factory(torch, batch):
 
 def workload_config(args, world):
     """The `config` object of the JSON line: ONE definition for both arms, so the driver sees identical strings."""
-    return {'workload': f'HNOSegXS(4,4,24,[3]*8,(10,14,14)) train step fp32 (fwd + {args.loss} + bwd + Adamax), '
+    return {'workload': f'{SPEC["what"]} train step fp32 (fwd + {args.loss} + bwd + Adamax), '
                         f'batch {args.batch}/GPU, 4x240x240x155 volumes, random-init weights',
             'global_batch': world * args.batch, 'parallelism': f'dp{world}',
-            'l2_policy': 'working set (~10 GB of activations per step) >> 126 MB L2; no explicit flush'}
+            'l2_policy': f'working set ({SPEC["act_gb"]} of activations per step) >> 126 MB L2; no explicit flush'}
 
 
 def host_threads():
@@ -173,7 +209,7 @@ def run_reference(args, rank, world):
               f'each (batch 1 of the batch-{args.batch} workload), full training step incl. Adamax, oracle port on {cores} '
               f'threads of ONE host; the same single-host figure is reported for every --gpus N')
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': k,
+        'impl': 'reference', 'metric': SPEC['metric'], 'value': value, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': k,
         'warmup': warm, 'ms_per_step': 1e3 * dt / k, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
         'cpu_baseline': {'value': value, 'unit': 'volumes/s', 'cores': cores, 'kind': 'port', 'sample': sample},
@@ -218,7 +254,7 @@ def pin_to_gpu_numa(torch, index):
 
 
 # ------------------------------------------------------------------------------------------------ kernel table
-def kernel_table(torch, dev, batch, peak_gbs):
+def kernel_table(torch, dev, batch, peak_gbs, VOLUME=VOLUME, forward_only=False):
     """Times each hot-path entry point alone (CUDA events on the launch stream, buffers >> L2 so every launch is
     HBM-cold) and relates it to its ALGORITHMIC bytes."""
     from multimodal_3d_image_segmentation_b200 import ops
@@ -267,6 +303,10 @@ def kernel_table(torch, dev, batch, peak_gbs):
         ('head_loss_backward', 1, 2 * LL + L,
          lambda: ops.head_loss_backward(ll, lab, loss_coef[1], None, tables, P)),
     ]
+    if forward_only:
+        keep = {'dht3_forward': 8, 'dht3_adjoint_selu': 8, 'pwconv48_forward': 11, 'pwconv24_forward': 1, 'modechain_forward': 8,
+                'stem_forward': 1, 'head_conv_forward': 1}
+        cases = [(n, keep[n], b, f) for n, _, b, f in cases if n in keep]
     rows = []
     for name, per_step, nbytes, fn in cases:
         for _ in range(2):
@@ -286,6 +326,254 @@ def kernel_table(torch, dev, batch, peak_gbs):
     return rows
 
 
+def _timed(torch, fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def tf32_peak():
+    """Dense TF32 tensor-core peak derived from the measured bf16 figure (tf32 runs at half the bf16 rate)."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['bf16_tflops']) / 2, 'measured bf16_tflops / 2 (MEASURED_PEAKS.json)'
+    except Exception:
+        return 2250.0 / 2 / 2, 'nominal 2.25 PFLOP/s bf16 / 2, derated 0.5 (no MEASURED_PEAKS.json)'
+
+
+def mha_attention_roofline(torch, dev, batch):
+    """The attention contractions of ONE HartleyMHA block at BASELINE config 5 (1,960 tokens x 96 features x 4 heads per
+    sample), timed alone.  FLOP-bound: graded against the TF32 tensor-core peak with the ALGORITHMIC flops (2 GEMMs forward,
+    4 backward, un-padded sizes); the kernels issue 3 MMAs per product (3xTF32) on 2,048-token padded tiles."""
+    from multimodal_3d_image_segmentation_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(5)
+    z = torch.randn(batch, 12, 20, 28, 28, device=dev, generator=g)
+    ws = [torch.randn(4, 12, 12, device=dev, generator=g) * 0.1 for _ in range(3)] + \
+        [torch.randn(12, 48, device=dev, generator=g) * 0.1]
+    y, S = ops.hartley_attention_forward(z, None, None, *ws, patch=(2, 2, 2), activation=1)
+    dy = torch.randn_like(y)
+    ms_f = _timed(torch, lambda: ops.hartley_attention_forward(z, None, None, *ws, patch=(2, 2, 2), activation=1), 5)
+    ms_b = _timed(torch, lambda: ops.hartley_attention_backward(dy, S), 5)
+    T, F, H = 1960, 96, 4
+    flop_f = 2 * (2.0 * T * T * F) * H * batch
+    peak, src = tf32_peak()
+    tf_f, tf_b = flop_f / (ms_f * 1e-3) / 1e12, 2 * flop_f / (ms_b * 1e-3) / 1e12
+    return {'roofline': {'bound': 'tensor', 'kernel': 'hartley_attention_forward (k_gemm_tn_tc: QK^T + SELU, PV; includes the '
+                         'Q/K/V projections and the output projection, CUDA cores)', 'achieved': round(tf_f, 2), 'peak': peak,
+                         'unit': 'TFLOP/s', 'frac': round(tf_f / peak, 4), 'traffic': None, 'peak_source': src,
+                         'alg_flops_per_launch': flop_f, 'ms_per_launch': round(ms_f, 4),
+                         'issued_frac_3xtf32': round(3 * tf_f / peak, 4)},
+            'kernels': [{'kernel': 'hartley_attention_forward', 'ms': round(ms_f, 4), 'per_step': 16, 'tflops': round(tf_f, 2),
+                         'frac': round(tf_f / peak, 4), 'step_ms': round(16 * ms_f, 3)},
+                        {'kernel': 'hartley_attention_backward', 'ms': round(ms_b, 4), 'per_step': 16, 'tflops': round(tf_b, 2),
+                         'frac': round(tf_b / peak, 4), 'step_ms': round(16 * ms_b, 3)}]}
+
+
+def run_superres(args):
+    """BASELINE config 4: zero-shot 2x super-resolution inference of HNOSeg-XS, one 4 x 480 x 480 x 310 volume per step,
+    following the reference's testing loop (experiments/train_test.py:373-414): copy the volume to the device, forward under
+    no_grad, argmax over the classes, label map back to the host.  Here the argmax runs on the device (uint8 labels)."""
+    import torch
+    from multimodal_3d_image_segmentation_b200 import _lib, nets, parallel
+    from multimodal_3d_image_segmentation_b200.experiments.utils import normalize_rows
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        raise SystemExit('superres_infer is a single-GPU configuration (BASELINE config 4)')
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    _lib.call('hno_device_check')
+    vol = SPEC['volume']
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.manual_seed(0)
+    model = nets.HNOSegXS(**CFG, device=dev).eval()
+    gx = torch.Generator().manual_seed(1234)
+    hosts = [(torch.randn(1, 4, *vol, generator=gx) * 200.0 + 1000.0).round_().to(torch.int16).pin_memory() for _ in range(2)]
+    x_dev = normalize_rows(hosts[0].to(dev), 4, mask_val=0)
+    for _ in range(args.warmup):
+        lab = model.predict_labels(x_dev)
+    torch.cuda.synchronize()
+    parallel.launches(reset=True)
+    t0 = time.perf_counter()
+    ms = _timed(torch, lambda: model.predict_labels(x_dev), args.steps, warm=0)
+    sampler.mark(t0, time.perf_counter())
+    launches = parallel.launches()
+    # end to end: H2D of the raw int16 volume, z-scoring, forward, argmax, D2H of the uint8 label map
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty(hosts[0].shape, dtype=torch.int16, device=dev) for _ in range(2)]
+    xn = torch.empty(hosts[0].shape, dtype=torch.float32, device=dev)
+    out_host = [torch.empty((1,) + tuple(vol), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    ready, freed = [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[i % 2])
+            bufs[i % 2].copy_(hosts[i % 2], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def loop(k):
+        cur = torch.cuda.current_stream()
+        for e in freed:
+            e.record(cur)
+        issue(0)
+        for i in range(k):
+            if i + 1 < k:
+                issue(i + 1)
+            cur.wait_event(ready[i % 2])
+            normalize_rows(bufs[i % 2], 4, mask_val=0, out=xn)
+            lab = model.predict_labels(xn)
+            freed[i % 2].record(cur)
+            out_host[i % 2].copy_(lab, non_blocking=True)
+        torch.cuda.synchronize()
+
+    loop(2)
+    t0 = time.perf_counter()
+    loop(args.steps)
+    wall = time.perf_counter() - t0
+    sampler.mark(t0, t0 + wall)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    line = {
+        'metric': SPEC['metric'], 'value': 1e3 / ms, 'unit': 'volumes/s', 'n_gpus': 1, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{SPEC["what"]} inference (forward + on-device argmax -> uint8 label map), batch 1, one '
+                               '4x480x480x310 volume (2x grid of the training resolution, same weights, modes (10,14,14)), '
+                               'random-init weights', 'global_batch': 1, 'parallelism': 'single GPU',
+                   'l2_policy': 'working set (870 MB per 24-channel activation) >> 126 MB L2; no explicit flush'},
+        'clocks': clocks,
+        'e2e': {'value': args.steps / wall, 'unit': 'volumes/s', 'h2d_bytes_per_step': hosts[0].numel() * 2,
+                'd2h_bytes_per_step': out_host[0].numel(), 'wall_s': round(wall, 4),
+                'what': 'pinned int16 volume H2D (double-buffered), on-device z-scoring, forward, argmax, uint8 label map D2H'},
+        'gpu_launches': launches,
+    }
+    if not args.no_kernel_table:
+        rows = kernel_table(torch, dev, 1, peak, VOLUME=vol, forward_only=True)
+        top = max(rows, key=lambda r: r['step_ms'])
+        line['roofline'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['gbs'], 'peak': peak, 'unit': 'GB/s',
+                            'frac': top['frac'], 'traffic': None, 'peak_source': peak_src,
+                            'alg_bytes_per_launch': top['alg_bytes'], 'ms_per_launch': top['ms']}
+        line['kernels'] = rows
+    if not args.no_cpu_baseline:
+        from oracle import hno_oracle as orc
+        sd = orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14), seed=0)
+        xh = torch.randn(1, 4, *vol, generator=torch.Generator().manual_seed(1))
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.hnosegxs_forward(sd, xh, [3] * 8, (10, 14, 14)).argmax(1)
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': 1.0 / dt, 'unit': 'volumes/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'sample': 'ONE forward + argmax of one 4x480x480x310 volume, no warm-up, oracle port of the '
+                                          'reference', 'host_cpus': os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+def run_fnoseg_layer(args):
+    """BASELINE config 3: the FNOSeg3D spectral layer (FourierOperator: rfftn -> complex truncated-mode mixing -> irfftn in
+    the reference, nets/fourier_operator.py:148-211) forward + backward on BraTS-shaped activations, batch 2."""
+    import torch
+    from multimodal_3d_image_segmentation_b200 import _lib, nets, parallel
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    _lib.call('hno_device_check')
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.manual_seed(0)
+    B, shape = args.batch, (24, 121, 121, 78)
+    op = nets.FourierOperator(24, 24, (10, 14, 14), device=dev)
+    host = [torch.randn(B, *shape).pin_memory() for _ in range(2)]
+    x = host[0].to(dev).requires_grad_(True)
+    w = torch.randn(B, *shape, device=dev)
+
+    def step(xx):
+        xx.grad = None
+        op.zero_grad(set_to_none=True)
+        y = op(xx)
+        y.backward(w)
+        return y
+
+    for _ in range(args.warmup):
+        step(x)
+    torch.cuda.synchronize()
+    parallel.launches(reset=True)
+    t0 = time.perf_counter()
+    ms = _timed(torch, lambda: step(x), args.steps, warm=0)
+    sampler.mark(t0, time.perf_counter())
+    launches = parallel.launches()
+    xb = [torch.empty(B, *shape, device=dev).requires_grad_(True) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready, freed = [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue(i):
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            copy_stream.wait_event(freed[i % 2])
+            xb[i % 2].copy_(host[i % 2], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def loop(k):
+        cur = torch.cuda.current_stream()
+        for e in freed:
+            e.record(cur)
+        issue(0)
+        for i in range(k):
+            if i + 1 < k:
+                issue(i + 1)
+            cur.wait_event(ready[i % 2])
+            step(xb[i % 2])
+            v = op.weight_real.grad.sum()
+            freed[i % 2].record(cur)
+            v.item()
+
+    loop(2)
+    t0 = time.perf_counter()
+    loop(args.steps)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    sampler.mark(t0, t0 + wall)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    A = B * 24 * 121 * 121 * 78 * 4.0
+    alg = 4 * A  # x and dy read, y and dx written (the mode tensors are ~1 % of that)
+    gbs = alg / (ms * 1e-3) / 1e9
+    line = {
+        'metric': SPEC['metric'], 'value': B * 1e3 / ms, 'unit': 'volumes/s', 'n_gpus': 1, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{SPEC["what"]} forward + backward (input and weight gradients) on a {B} x 24 x 121 x 121 x 78 '
+                               'activation (the internal grid of a 4x240x240x155 volume), random-init weights',
+                   'global_batch': B, 'parallelism': 'single GPU',
+                   'l2_policy': 'working set (4 x 219 MB) >> 126 MB L2; no explicit flush'},
+        'clocks': clocks,
+        'e2e': {'value': B * args.steps / wall, 'unit': 'volumes/s', 'h2d_bytes_per_step': int(A), 'd2h_bytes_per_step': 4,
+                'wall_s': round(wall, 4), 'what': 'pinned fp32 activation H2D (double-buffered), layer forward + backward, one '
+                                                  'scalar of the weight gradient read back'},
+        'gpu_launches': launches,
+        'roofline': {'bound': 'hbm', 'kernel': 'FourierOperator forward + backward (2 truncated transforms each way + mode mix)',
+                     'achieved': round(gbs, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(gbs / peak, 4), 'traffic': None,
+                     'peak_source': peak_src, 'alg_bytes_per_launch': int(alg), 'ms_per_launch': round(ms, 4)},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import hno_oracle as orc
+        xr = host[0][:1].clone().requires_grad_(True)
+        wr = op.weight_real.detach().cpu().requires_grad_(True)
+        wi = op.weight_imag.detach().cpu().requires_grad_(True)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            y = orc.fourier_operator_with_transform(xr, wr, wi, (10, 14, 14))
+            y.backward(torch.ones_like(y))
+        dt = (time.perf_counter() - t0) / 3
+        line['cpu_baseline'] = {'value': 1.0 / dt, 'unit': 'volumes/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'sample': '3 forward + backward passes of ONE 24x121x121x78 activation (batch 1), oracle port '
+                                          '(torch.fft rfftn / irfftn) of the reference', 'host_cpus': os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -297,14 +585,26 @@ def main():
     ap.add_argument('--loss', default='DiceLoss', choices=['DiceLoss', 'PCCLoss'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-table', action='store_true')
+    ap.add_argument('--config', default='xs_train', choices=sorted(SPECS),
+                    help='workload: xs_train = BASELINE config 2 (default, what the driver measures); the others time '
+                         'BASELINE configs 3 / 4 / 5 and the HNOSeg config')
     args = ap.parse_args()
+    global SPEC
+    SPEC = SPECS[args.config]
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
+        if SPEC['kind'] != 'train':
+            raise SystemExit('--impl reference is the CPU arm of the training configs; the inference / layer configs carry '
+                             'their CPU figure in cpu_baseline')
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    if SPEC['kind'] == 'infer':
+        return run_superres(args)
+    if SPEC['kind'] == 'layer':
+        return run_fnoseg_layer(args)
 
     import torch
     import torch.distributed as dist
@@ -329,7 +629,8 @@ def main():
         sampler.start()  # nvidia-smi needs ~1 s to come up: start early, keep only the samples taken under load
     numa = pin_to_gpu_numa(torch, local_rank) if world > 1 else None  # before the pinned buffers are allocated
     torch.manual_seed(0)
-    model = nets.HNOSegXS(**CFG, device=dev)  # random init = the reference's SNN initialiser (nets_utils.py:102-117)
+    # random init = the reference's SNN initialiser (nets_utils.py:102-117)
+    model = getattr(nets, SPEC['model'])(**SPEC['kwargs'], device=dev)
     trainer = parallel.Trainer(model, args.loss, lr=5e-3)
     B = args.batch
     gx = torch.Generator().manual_seed(1234 + 2 * rank)
@@ -428,7 +729,7 @@ def main():
 
     peak, peak_src = measured_peak()
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'volumes/s', 'n_gpus': world, 'steps': args.steps,
+        'metric': SPEC['metric'], 'value': value, 'unit': 'volumes/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
         'clocks': clocks,
@@ -440,7 +741,9 @@ def main():
                         'train step, loss.item()'},
         'gpu_launches': launches, 'loss': final_loss,
     }
-    if not args.no_kernel_table:
+    if args.config == 'mha_train' and not args.no_kernel_table:
+        line.update(mha_attention_roofline(torch, dev, B))
+    if args.config == 'xs_train' and not args.no_kernel_table:
         rows = kernel_table(torch, dev, B, peak)
         top = max(rows, key=lambda r: r['step_ms'])
         traffic, traffic_src = None, None

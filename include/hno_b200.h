@@ -99,6 +99,17 @@ int hno_hartley_conv_forward(const float* x, const float* w, float* out, int B, 
 int hno_hartley_conv_backward(const float* dout, const float* y, const float* x, const float* w, float* dx,
                               float* dw, int B, int ci, int co, int n0, int n1, int n2, int accumulate_dw,
                               void* stream);
+/* HartleyOperator(use_transform=True, weights_type='individual')  replaces nets/hartley_operator.py:196-241: the reversal
+ * partner of X lives in the FULL spectrum (x_reverse = get_reverse(dht3(x)), :199), the weight is reversed inside its 2m block
+ * (:200).  x_ext [B][ci][e0][e1][e2]: the retained modes plus, last on every axis with n > 2m, the frequency +m (the partner of
+ * n - m); out / weight over the retained block [n0][n1][n2]; partner_table = [r0 (n0 ints) | r1 (n1) | r2 (n2)], device memory:
+ * position in x_ext of the partner of retained position j.  act: 0 none, 1 SELU (the reference activates the padded spectrum,
+ * :267).  backward: dout = gradient of out, y = out when act == 1 (else null); dx_ext is zero-filled and written. */
+int hno_hartley_conv_full_forward(const float* x_ext, const float* weight, const int* partner_table, float* out, int B,
+                                  int ci, int co, int n0, int n1, int n2, int e0, int e1, int e2, int act, void* stream);
+int hno_hartley_conv_full_backward(const float* dout, const float* y, const float* x_ext, const float* weight,
+                                   const int* partner_table, float* dx_ext, float* dweight, int B, int ci, int co, int n0,
+                                   int n1, int n2, int e0, int e1, int e2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Complex per-mode ("individual" weights) mixing of the retained Fourier half-spectrum
@@ -228,6 +239,57 @@ int hno_normalize_modalities(const float* data, float* out, void* workspace, int
  * the exact int16 -> fp32 conversion happens in the load */
 int hno_normalize_modalities_i16(const short* data, float* out, void* workspace, int rows, long n, int has_mask,
                                  float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Deep-supervision convolution                 replaces nets/architectures.py:295-311, 330-343 and
+ * nets/hnosegxs.py:110-125, 154-172:  x = conv_ds(torch.cat(tensors, 1))  -- a 1x1x1 ConvNormAct over the
+ * concatenation of EVERY block output -- evaluated over the list of sources without forming the concatenation:
+ *   out[b][o][s] = act( bias[o] + sum_i sum_c weight[o][off_i + c] * in_i[b][c][s] ),   act: 0 none, 1 SELU.
+ * in[i]: [B][ch[i]][S] fp32, 16-byte aligned, S % 4 == 0 (the planar layout guarantees it); n <= 40 sources; CO <= 8.
+ * weight2 [CO][CO] (optional, with out2): the bias-free conv_out that follows the head (architectures.py:311-313; it commutes
+ * with the trilinear up-sampling and is applied here, at low resolution): out2 = weight2 * out in the same pass.
+ * backward: dy = gradient of out2 when weight2 is given (else of out); din[i] (may be null per source) = W_i^T d(pre),
+ * dweight [CO][sum ch], dbias [CO] (may be null), dweight2 [CO][CO]; P / HW: plane pitch and valid columns per plane (gradients
+ * of the padding columns are zero); y = the forward's `out`.
+ * ------------------------------------------------------------------------------------------ */
+int hno_dsconv_forward(const float* const* in, const int* ch, int n, const float* weight, const float* bias, float* out,
+                       const float* weight2, float* out2, int B, int CO, long S, int act, void* stream);
+size_t hno_dsconv_backward_workspace_bytes(int ctot, int CO, int B, long S);
+int hno_dsconv_backward(const float* const* in, float* const* din, const int* ch, int n, const float* weight,
+                        const float* dy, const float* y, const float* weight2, float* dweight, float* dbias,
+                        float* dweight2, void* workspace, int B, int CO, long S, long P, long HW, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hartley multi-head attention on the retained modes       replaces nets/hartley_mha.py:136-222
+ * (HartleyMultiHeadAttention._call / _call_notransform between the forward and the inverse transform).
+ * Geometry: mode block (Ld, Lh, Lw) = 2 * num_modes, patch (pd, ph, pw) (1, 1, 1 without grouping), tokens
+ * T = (Ld/pd)(Lh/ph)(Lw/pw) padded to Tp (multiple of 128), features per head F = channels * pd*ph*pw padded to Fp (multiple
+ * of 32; a value accepted by the GEMM tiles: <= 256 or a multiple of 128).  Attention operands live in two layouts,
+ *   x_tok [B*H][Tp][Fp] (token major)   and   x_chan [B*H][Fp][Tp] (feature major),   zero in the padding.
+ *   hno_mha_project_*    freq_conv3d (:310-334, per-head 1x1x1 conv over the cropped block, weight [H][cd][cin], optional
+ *                        bias [H][cd]) + grouping3d (:473-498) into both layouts; backward gives dz (optionally accumulated:
+ *                        self-attention feeds one mode tensor to Q, K and V), dw, dbias.
+ *   hno_mha_attention_*  att = act(Q^T K * scale) (:198-201, scale = 1/sqrt(F), act SELU or none), out = att V (:203);
+ *                        forward keeps att and its transpose for the backward (P, PT [B*H][Tp][Tp]); tcgen05 3xTF32 GEMMs.
+ *   hno_mha_output_*     ungrouping3d (:501-524) + 'oi,bidhw->bodhw' with weight_out [co][H*cd] (+ bias [co]) (:207-216).
+ * ------------------------------------------------------------------------------------------ */
+int hno_mha_project_forward(const float* z, const float* weight, const float* bias, float* x_tok, float* x_chan, int B,
+                            int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp, int Fp,
+                            void* stream);
+int hno_mha_project_backward(const float* dx_tok, const float* z, const float* weight, float* dz, float* dweight,
+                             float* dbias, int B, int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw,
+                             int Tp, int Fp, int accumulate_dz, void* stream);
+int hno_mha_attention_forward(const float* q_tok, const float* k_tok, const float* v_chan, float* P, float* PT,
+                              float* o_tok, int BH, int Tp, int Fqp, int Fvp, float scale, int activation, void* stream);
+int hno_mha_attention_backward(const float* do_tok, const float* do_chan, const float* q_chan, const float* k_chan,
+                               const float* v_tok, const float* P, const float* PT, float* dS, float* dST, float* dq_tok,
+                               float* dk_tok, float* dv_tok, int BH, int Tp, int Fqp, int Fvp, float scale, int activation,
+                               void* stream);
+int hno_mha_output_forward(const float* o_tok, const float* weight_out, const float* bias, float* y, int B, int H, int co,
+                           int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp, int Fp, void* stream);
+int hno_mha_output_backward(const float* dy, const float* o_tok, const float* weight_out, float* do_tok, float* do_chan,
+                            float* dweight_out, float* dbias, int B, int H, int co, int cd, int Ld, int Lh, int Lw, int pd,
+                            int ph, int pw, int Tp, int Fp, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adamax step on a flat parameter vector (torch.optim.Adamax semantics, the optimizer of

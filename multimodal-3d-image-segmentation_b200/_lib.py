@@ -43,6 +43,8 @@ SIGNATURES = {
     'hno_modechain_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _I, _P]),
     'hno_hartley_conv_forward': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'hno_hartley_conv_backward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'hno_hartley_conv_full_forward': (_I, [_P, _P, _P, _P] + [_I] * 10 + [_P]),
+    'hno_hartley_conv_full_backward': (_I, [_P] * 7 + [_I] * 9 + [_P]),
     'hno_complex_modemix_forward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _P]),
     'hno_complex_modemix_backward': (_I, [_P] * 10 + [_I, _I, _I, _L, _I, _P]),
     'hno_stem_supported': (_I, [_I, _I]),
@@ -67,6 +69,15 @@ SIGNATURES = {
     'hno_normalize_workspace_bytes': (_Z, [_I]),
     'hno_normalize_modalities': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
     'hno_normalize_modalities_i16': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
+    'hno_dsconv_forward': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
+    'hno_dsconv_backward_workspace_bytes': (_Z, [_I, _I, _I, _L]),
+    'hno_dsconv_backward': (_I, [_P, _P, _P, _I] + [_P] * 8 + [_I, _I, _L, _L, _L, _I, _P]),
+    'hno_mha_project_forward': (_I, [_P] * 5 + [_I] * 12 + [_P]),
+    'hno_mha_project_backward': (_I, [_P] * 6 + [_I] * 13 + [_P]),
+    'hno_mha_attention_forward': (_I, [_P] * 6 + [_I, _I, _I, _I, _F, _I, _P]),
+    'hno_mha_attention_backward': (_I, [_P] * 12 + [_I, _I, _I, _I, _F, _I, _P]),
+    'hno_mha_output_forward': (_I, [_P] * 4 + [_I] * 12 + [_P]),
+    'hno_mha_output_backward': (_I, [_P] * 7 + [_I] * 12 + [_P]),
     'hno_adamax_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 

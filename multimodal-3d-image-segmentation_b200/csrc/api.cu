@@ -55,6 +55,10 @@ int modechain_backward(const float* dzL, const float* z0, const float* zs, const
 int hartley_conv_forward(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int hartley_conv_backward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int,
                           int, int, int, cudaStream_t);
+int hartley_conv_full_forward(const float*, const float*, const int*, float*, int, int, int, int, int, int, int, int, int,
+                              int, cudaStream_t);
+int hartley_conv_full_backward(const float*, const float*, const float*, const float*, const int*, float*, float*, int, int,
+                               int, int, int, int, int, int, int, cudaStream_t);
 int stem_supported(int, int);
 int stem_forward(const float*, const float*, const float*, float*, int, int, int, int, int, int, long, cudaStream_t);
 size_t stem_backward_workspace_bytes(int, int);
@@ -64,6 +68,24 @@ size_t interp_tables_bytes(int, int, int, int, int, int);
 int interp_tables_fill(void*, size_t, int, int, int, int, int, int);
 int head_forward(const void*, const void*, const float*, float*, int, int, long, int, cudaStream_t);
 int head_argmax(const void*, const void*, const float*, uint8_t*, int, int, long, cudaStream_t);
+int dsconv_forward(const float* const*, const int*, int, const float*, const float*, float*, const float*, float*, int, int,
+                   long, int, cudaStream_t);
+size_t dsconv_backward_workspace_bytes(int, int, int, long);
+int dsconv_backward(const float* const*, float* const*, const int*, int, const float*, const float*, const float*,
+                    const float*, float*, float*, float*, void*, int, int, long, long, long, int, cudaStream_t);
+int mha_project_forward(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int, int, int,
+                        int, int, int, int, cudaStream_t);
+int mha_project_backward(const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int, int,
+                         int, int, int, int, int, int, int, cudaStream_t);
+int mha_attention_forward(const float*, const float*, const float*, float*, float*, float*, int, int, int, int, float, int,
+                          cudaStream_t);
+int mha_attention_backward(const float*, const float*, const float*, const float*, const float*, const float*,
+                           const float*, float*, float*, float*, float*, float*, int, int, int, int, float, int,
+                           cudaStream_t);
+int mha_output_forward(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int,
+                       int, int, cudaStream_t);
+int mha_output_backward(const float*, const float*, const float*, float*, float*, float*, float*, int, int, int, int, int,
+                        int, int, int, int, int, int, int, cudaStream_t);
 size_t head_backward_workspace_bytes(const void*, int, int);
 int head_backward(const void*, const void*, const float*, const float*, float*, void*, int, int, long, int,
                   cudaStream_t);
@@ -295,6 +317,64 @@ int hno_normalize_modalities_i16(const short* data, float* out, void* workspace,
                                  float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream) {
   return normalize_modalities(data, 2, out, workspace, rows, n, has_mask, mask_val, has_clip, clip_lo, clip_hi,
                               ST(stream));
+}
+
+int hno_hartley_conv_full_forward(const float* x_ext, const float* weight, const int* partner_table, float* out, int B,
+                                  int ci, int co, int n0, int n1, int n2, int e0, int e1, int e2, int act, void* stream) {
+  return hartley_conv_full_forward(x_ext, weight, partner_table, out, B, ci, co, n0, n1, n2, e0, e1, e2, act, ST(stream));
+}
+int hno_hartley_conv_full_backward(const float* dout, const float* y, const float* x_ext, const float* weight,
+                                   const int* partner_table, float* dx_ext, float* dweight, int B, int ci, int co, int n0,
+                                   int n1, int n2, int e0, int e1, int e2, void* stream) {
+  return hartley_conv_full_backward(dout, y, x_ext, weight, partner_table, dx_ext, dweight, B, ci, co, n0, n1, n2, e0, e1,
+                                    e2, ST(stream));
+}
+
+int hno_dsconv_forward(const float* const* in, const int* ch, int n, const float* weight, const float* bias, float* out,
+                       const float* weight2, float* out2, int B, int CO, long S, int act, void* stream) {
+  return dsconv_forward(in, ch, n, weight, bias, out, weight2, out2, B, CO, S, act, ST(stream));
+}
+size_t hno_dsconv_backward_workspace_bytes(int ctot, int CO, int B, long S) {
+  return dsconv_backward_workspace_bytes(ctot, CO, B, S);
+}
+int hno_dsconv_backward(const float* const* in, float* const* din, const int* ch, int n, const float* weight,
+                        const float* dy, const float* y, const float* weight2, float* dweight, float* dbias,
+                        float* dweight2, void* workspace, int B, int CO, long S, long P, long HW, int act, void* stream) {
+  return dsconv_backward(in, din, ch, n, weight, dy, y, weight2, dweight, dbias, dweight2, workspace, B, CO, S, P, HW,
+                         act, ST(stream));
+}
+
+int hno_mha_project_forward(const float* z, const float* weight, const float* bias, float* x_tok, float* x_chan, int B,
+                            int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp, int Fp,
+                            void* stream) {
+  return mha_project_forward(z, weight, bias, x_tok, x_chan, B, H, cin, cd, Ld, Lh, Lw, pd, ph, pw, Tp, Fp, ST(stream));
+}
+int hno_mha_project_backward(const float* dx_tok, const float* z, const float* weight, float* dz, float* dweight,
+                             float* dbias, int B, int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw,
+                             int Tp, int Fp, int accumulate_dz, void* stream) {
+  return mha_project_backward(dx_tok, z, weight, dz, dweight, dbias, B, H, cin, cd, Ld, Lh, Lw, pd, ph, pw, Tp, Fp,
+                              accumulate_dz, ST(stream));
+}
+int hno_mha_attention_forward(const float* q_tok, const float* k_tok, const float* v_chan, float* P, float* PT,
+                              float* o_tok, int BH, int Tp, int Fqp, int Fvp, float scale, int activation, void* stream) {
+  return mha_attention_forward(q_tok, k_tok, v_chan, P, PT, o_tok, BH, Tp, Fqp, Fvp, scale, activation, ST(stream));
+}
+int hno_mha_attention_backward(const float* do_tok, const float* do_chan, const float* q_chan, const float* k_chan,
+                               const float* v_tok, const float* P, const float* PT, float* dS, float* dST, float* dq_tok,
+                               float* dk_tok, float* dv_tok, int BH, int Tp, int Fqp, int Fvp, float scale, int activation,
+                               void* stream) {
+  return mha_attention_backward(do_tok, do_chan, q_chan, k_chan, v_tok, P, PT, dS, dST, dq_tok, dk_tok, dv_tok, BH, Tp,
+                                Fqp, Fvp, scale, activation, ST(stream));
+}
+int hno_mha_output_forward(const float* o_tok, const float* weight_out, const float* bias, float* y, int B, int H, int co,
+                           int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp, int Fp, void* stream) {
+  return mha_output_forward(o_tok, weight_out, bias, y, B, H, co, cd, Ld, Lh, Lw, pd, ph, pw, Tp, Fp, ST(stream));
+}
+int hno_mha_output_backward(const float* dy, const float* o_tok, const float* weight_out, float* do_tok, float* do_chan,
+                            float* dweight_out, float* dbias, int B, int H, int co, int cd, int Ld, int Lh, int Lw, int pd,
+                            int ph, int pw, int Tp, int Fp, void* stream) {
+  return mha_output_backward(dy, o_tok, weight_out, do_tok, do_chan, dweight_out, dbias, B, H, co, cd, Ld, Lh, Lw, pd, ph,
+                             pw, Tp, Fp, ST(stream));
 }
 
 int hno_adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, long n, float lr, float beta1,

@@ -188,6 +188,174 @@ int hartley_conv_backward(const float* dout, const float* y, const float* x, con
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ full-spectrum reversal
+// HartleyOperator(use_transform=True, weights_type='individual') (nets/hartley_operator.py:196-241): the reversal partner
+// of X is taken in the FULL N-point spectrum, x_reverse = get_reverse(dht3(x)) (:199), and only afterwards cropped, while
+// the weight is reversed inside its own 2m-sized block (:200).  The partner of the retained frequency n - m + t is m - t;
+// for t = 0 that is +m, which lies OUTSIDE the retained corner set -- so the truncated transform here also produces
+// frequency +m per axis ("extended" mode tensor x_ext [B][CI][E0][E1][E2], E = 2m + 1, or 2m when n == 2m) and
+//     out(j) = act( 1/2 [ W(j) (X(j) + X(r(j))) + W(~j) (X(j) - X(r(j))) ] ),
+// j over the retained block [n0][n1][n2] (position j of the block = position j of x_ext), r(j) = position of the partner in
+// x_ext, per axis from `rtab` = [r0 (n0 ints) | r1 (n1) | r2 (n2)], ~j = (2m - j) mod 2m.  Same thread layout as above.
+struct HcFull {
+  int n0, n1, n2, e0, e1, e2;
+  const int* r0;
+  const int* r1;
+  const int* r2;
+};
+
+__device__ __forceinline__ void hc_full_locate(const HcFull& t, long k, long& kx, long& kxr, long& kwr) {
+  const int k2 = (int)(k % t.n2);
+  const long r = k / t.n2;
+  const int k1 = (int)(r % t.n1);
+  const int k0 = (int)(r / t.n1);
+  kx = ((long)k0 * t.e1 + k1) * t.e2 + k2;
+  kxr = ((long)__ldg(t.r0 + k0) * t.e1 + __ldg(t.r1 + k1)) * t.e2 + __ldg(t.r2 + k2);
+  const int w0 = k0 == 0 ? 0 : t.n0 - k0, w1 = k1 == 0 ? 0 : t.n1 - k1, w2 = k2 == 0 ? 0 : t.n2 - k2;
+  kwr = ((long)w0 * t.n1 + w1) * t.n2 + w2;
+}
+
+template <int CO>
+__global__ void __launch_bounds__(128) k_hconv_full_fwd(const float* __restrict__ x, const float* __restrict__ w,
+                                                        float* __restrict__ out, int B, int CI, HcFull t, int act) {
+  const long M = (long)t.n0 * t.n1 * t.n2, E = (long)t.e0 * t.e1 * t.e2;
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  if (k >= M) return;
+  long kx, kxr, kwr;
+  hc_full_locate(t, k, kx, kxr, kwr);
+  for (int b = 0; b < B; ++b) {
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+    for (int i = 0; i < CI; ++i) {
+      const float a = __ldg(x + ((long)b * CI + i) * E + kx), c = __ldg(x + ((long)b * CI + i) * E + kxr);
+      const float e = a + c, od = a - c;
+#pragma unroll
+      for (int o = 0; o < CO; ++o)
+        acc[o] = fmaf(__ldg(w + ((long)o * CI + i) * M + k), e, fmaf(__ldg(w + ((long)o * CI + i) * M + kwr), od, acc[o]));
+    }
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+      const float v = 0.5f * acc[o];
+      out[((long)b * CO + o) * M + k] = act ? selu_f(v) : v;
+    }
+  }
+}
+
+// dX scatter: thread j adds 1/2 (W(j) + W(~j))^T d(j) at position j and 1/2 (W(j) - W(~j))^T d(j) at position r(j) of the
+// zero-initialised dx_ext.  Every element receives at most two contributions (its own and its partner's), so the
+// floating-point sum does not depend on the order of the atomics.
+template <int CI>
+__global__ void __launch_bounds__(128) k_hconv_full_bwd_x(const float* __restrict__ g, const float* __restrict__ y,
+                                                          const float* __restrict__ w, float* __restrict__ dx, int B,
+                                                          int CO, HcFull t) {
+  const long M = (long)t.n0 * t.n1 * t.n2, E = (long)t.e0 * t.e1 * t.e2;
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  if (k >= M) return;
+  long kx, kxr, kwr;
+  hc_full_locate(t, k, kx, kxr, kwr);
+  for (int b = 0; b < B; ++b) {
+    float own[CI], par[CI];
+#pragma unroll
+    for (int i = 0; i < CI; ++i) own[i] = par[i] = 0.f;
+    for (int o = 0; o < CO; ++o) {
+      float d = __ldg(g + ((long)b * CO + o) * M + k);
+      if (y != nullptr) d *= selu_grad_from_out(__ldg(y + ((long)b * CO + o) * M + k));
+#pragma unroll
+      for (int i = 0; i < CI; ++i) {
+        const float wk = __ldg(w + ((long)o * CI + i) * M + k), wr = __ldg(w + ((long)o * CI + i) * M + kwr);
+        own[i] = fmaf(wk + wr, d, own[i]);
+        par[i] = fmaf(wk - wr, d, par[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CI; ++i) {
+      atomicAdd(dx + ((long)b * CI + i) * E + kx, 0.5f * own[i]);
+      atomicAdd(dx + ((long)b * CI + i) * E + kxr, 0.5f * par[i]);
+    }
+  }
+}
+
+// dW(u)[o][i] = 1/2 sum_b [ d_o(u) (X_i(u) + X_i(r(u))) + d_o(~u) (X_i(~u) - X_i(r(~u))) ]
+__global__ void __launch_bounds__(128) k_hconv_full_bwd_w(const float* __restrict__ g, const float* __restrict__ y,
+                                                          const float* __restrict__ x, float* __restrict__ dw, int B,
+                                                          int CI, int CO, HcFull t) {
+  const long M = (long)t.n0 * t.n1 * t.n2, E = (long)t.e0 * t.e1 * t.e2;
+  const long k = blockIdx.x * 128L + threadIdx.x;
+  if (k >= M) return;
+  const int o = blockIdx.y;
+  long kx, kxr, kwr, vx, vxr, vwr;
+  hc_full_locate(t, k, kx, kxr, kwr);
+  hc_full_locate(t, kwr, vx, vxr, vwr);  // the mode whose ~ is k
+  for (int i = 0; i < CI; ++i) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float dk = __ldg(g + ((long)b * CO + o) * M + k), dv = __ldg(g + ((long)b * CO + o) * M + kwr);
+      if (y != nullptr) {
+        dk *= selu_grad_from_out(__ldg(y + ((long)b * CO + o) * M + k));
+        dv *= selu_grad_from_out(__ldg(y + ((long)b * CO + o) * M + kwr));
+      }
+      const float* xb = x + ((long)b * CI + i) * E;
+      acc = fmaf(dk, __ldg(xb + kx) + __ldg(xb + kxr), fmaf(dv, __ldg(xb + vx) - __ldg(xb + vxr), acc));
+    }
+    dw[((long)o * CI + i) * M + k] = 0.5f * acc;
+  }
+}
+
+static int hc_full_make(HcFull* t, const int* rtab, int n0, int n1, int n2, int e0, int e1, int e2) {
+  HNO_CHECK(rtab, "hartley_conv_full: null partner table");
+  HNO_CHECK(n0 >= 1 && n1 >= 1 && n2 >= 1 && e0 >= n0 && e1 >= n1 && e2 >= n2, "hartley_conv_full: bad sizes");
+  t->n0 = n0, t->n1 = n1, t->n2 = n2, t->e0 = e0, t->e1 = e1, t->e2 = e2;
+  t->r0 = rtab, t->r1 = rtab + n0, t->r2 = rtab + n0 + n1;
+  return 0;
+}
+
+int hartley_conv_full_forward(const float* x_ext, const float* w, const int* rtab, float* out, int B, int ci, int co, int n0,
+                              int n1, int n2, int e0, int e1, int e2, int act, cudaStream_t st) {
+  HcFull t;
+  if (hc_full_make(&t, rtab, n0, n1, n2, e0, e1, e2)) return -1;
+  HNO_CHECK(x_ext && w && out, "hartley_conv_full_forward: null pointer");
+  const int grid = ceil_div((long)n0 * n1 * n2, 128);
+#define X(C)                                                                  \
+  if (co == C) {                                                              \
+    k_hconv_full_fwd<C><<<grid, 128, 0, st>>>(x_ext, w, out, B, ci, t, act);  \
+    HNO_LAUNCH_CHECK();                                                       \
+    return 0;                                                                 \
+  }
+  HNO_HC_CHANNELS(X)
+#undef X
+  set_error("hartley_conv_full_forward: out_channels %d not in {8,16,24,32}", co);
+  return -1;
+}
+
+int hartley_conv_full_backward(const float* dout, const float* y, const float* x_ext, const float* w, const int* rtab,
+                               float* dx_ext, float* dw, int B, int ci, int co, int n0, int n1, int n2, int e0, int e1, int e2,
+                               cudaStream_t st) {
+  HcFull t;
+  if (hc_full_make(&t, rtab, n0, n1, n2, e0, e1, e2)) return -1;
+  HNO_CHECK(dout && x_ext && w, "hartley_conv_full_backward: null pointer");
+  const int grid = ceil_div((long)n0 * n1 * n2, 128);
+  if (dx_ext) {
+    HNO_CUDA(cudaMemsetAsync(dx_ext, 0, (size_t)B * ci * e0 * e1 * e2 * sizeof(float), st));
+    bool done = false;
+#define X(C)                                                                       \
+  if (ci == C) {                                                                   \
+    k_hconv_full_bwd_x<C><<<grid, 128, 0, st>>>(dout, y, w, dx_ext, B, co, t);     \
+    done = true;                                                                   \
+  }
+    HNO_HC_CHANNELS(X)
+#undef X
+    HNO_CHECK(done, "hartley_conv_full_backward: in_channels %d not in {8,16,24,32}", ci);
+    HNO_LAUNCH_CHECK();
+  }
+  if (dw) {
+    dim3 g2(grid, co);
+    k_hconv_full_bwd_w<<<g2, 128, 0, st>>>(dout, y, x_ext, dw, B, ci, co, t);
+    HNO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ complex per-mode mixing
 // Replaces the weights_type == 'individual' branch of FourierOperator._call3d (nets/fourier_operator.py:165-187, four
 // corner einsums 'oidhw,bidhw->bodhw' with weight = complex(weight_real, weight_imag)) on the retained half-spectrum

@@ -51,14 +51,15 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_fwd(const float* __res
                                                               long S, int tiles_per_sample, long total_tiles) {
   static_assert(!RES || (CI1 == CO && CI2 == 0), "residual needs CI1 == CO and a single input");
   constexpr int CI = CI1 + CI2;
-  static_assert(CI % kFwdRows == 0, "input channels must be a multiple of 8");
-  constexpr int NCH = CI / kFwdRows;
+  constexpr int FR = (CI1 % kFwdRows == 0 && CI2 % kFwdRows == 0) ? kFwdRows : 4;  // rows per stage (12-channel tensors: 4)
+  static_assert(CI1 % FR == 0 && CI2 % FR == 0, "input channels must be a multiple of 4");
+  constexpr int NCH = CI / FR;
   constexpr int COp = (CO + 3) & ~3;
   constexpr int TV = kPwThreads * V;
   extern __shared__ float4 smem4[];
   float* wt = reinterpret_cast<float*>(smem4);      // [CI][COp] transposed weights
   float* sbias = wt + CI * COp;                      // [COp]
-  float* ring = sbias + COp;                         // [kFwdStages][kFwdRows][TV]
+  float* ring = sbias + COp;                         // [kFwdStages][FR][TV]
   for (int idx = threadIdx.x; idx < CI * COp; idx += kPwThreads) {
     int i = idx / COp, o = idx - i * COp;
     wt[idx] = o < CO ? weight[o * CI + i] : 0.f;
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_fwd(const float* __res
       const int b = (int)(tile / tiles_per_sample);
       const long s0 = (tile - (long)b * tiles_per_sample) * TV + lv;
       if (s0 < S) {
-        float* dst = ring + ((int)(g % kFwdStages) * kFwdRows) * TV + lv;
+        float* dst = ring + ((int)(g % kFwdStages) * FR) * TV + lv;
 #pragma unroll
-        for (int r = 0; r < kFwdRows; ++r) {
-          const int c = ch * kFwdRows + r;
+        for (int r = 0; r < FR; ++r) {
+          const int c = ch * FR + r;
           const float* src = (CI2 == 0 || c < CI1) ? in1 + ((long)b * CI1 + c) * S + s0
                                                    : in2 + ((long)b * CI2 + (c - CI1)) * S + s0;
           cp_async_vec<V>(dst + r * TV, src);
@@ -108,9 +109,9 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_fwd(const float* __res
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[op][v] = make_float2(sbias[2 * op], sbias[2 * op + 1]);
     }
-    const float* src = ring + ((int)(g % kFwdStages) * kFwdRows) * TV + lv;
+    const float* src = ring + ((int)(g % kFwdStages) * FR) * TV + lv;
 #pragma unroll
-    for (int r = 0; r < kFwdRows; ++r) {
+    for (int r = 0; r < FR; ++r) {
       float2 xd[V];
       if (V == 4) {
         const float4 t = *reinterpret_cast<const float4*>(src + r * TV);
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kPwThreads, 2) k_pwconv_fwd(const float* __res
       } else {
         xd[0] = dup2(src[r * TV]);
       }
-      const float4* w4 = reinterpret_cast<const float4*>(wt + (ch * kFwdRows + r) * COp);
+      const float4* w4 = reinterpret_cast<const float4*>(wt + (ch * FR + r) * COp);
 #pragma unroll
       for (int q = 0; q < COp / 4; ++q) {
         const float4 w = w4[q];
@@ -474,7 +475,7 @@ static int bwd_t(const float* dy, const float* y, const float* in1, const float*
   return reduce_partials(partials, grid, CO * CI, CO, dweight, dbias, (flags & 8) ? 1 : 0, st);
 }
 
-// (CI1, CI2, CO, ACT, RES) combinations the model needs, for filters F in {8, 24} and heads of 2..4 classes.
+// (CI1, CI2, CO, ACT, RES) combinations the model needs, for filters F in {8, 12, 24} and heads of 2..4 classes.
 #define HNO_PW_CONFIGS(X) \
   X(8, 0, 8, 1, true)     \
   X(8, 0, 8, 1, false)    \
@@ -484,6 +485,14 @@ static int bwd_t(const float* dy, const float* y, const float* in1, const float*
   X(8, 0, 2, 0, false)    \
   X(8, 0, 3, 0, false)    \
   X(8, 0, 4, 0, false)    \
+  X(12, 0, 12, 1, true)   \
+  X(12, 0, 12, 1, false)  \
+  X(12, 12, 12, 1, false) \
+  X(12, 12, 12, 0, false) \
+  X(12, 0, 12, 0, false)  \
+  X(12, 0, 2, 0, false)   \
+  X(12, 0, 3, 0, false)   \
+  X(12, 0, 4, 0, false)   \
   X(24, 0, 24, 1, true)   \
   X(24, 0, 24, 1, false)  \
   X(24, 24, 24, 1, false) \
@@ -518,8 +527,10 @@ int pwconv_forward(const float* in1, const float* in2, const float* w, const flo
     a.nsrc = ci2 > 0 ? 2 : 1;
     a.mext = S;
     a.G = B;
-    a.kc = ci1 % 32 == 0 ? 32 : (ci1 % 24 == 0 ? 24 : (ci1 % 8 == 0 ? 8 : 0));
-    a.chunks_per_src = a.kc ? ci1 / a.kc : 0;
+    // channel counts that are no multiple of 8 (12-channel HartleyMHASeg tensors) ride in 16-row chunks whose missing rows
+    // the TMA zero-fills (the B image skips the gap, tc_stream.cu)
+    a.kc = ci1 % 32 == 0 ? 32 : (ci1 % 24 == 0 ? 24 : (ci1 % 16 == 0 ? 16 : (ci1 % 8 == 0 ? 8 : (ci1 < 16 ? 16 : 0))));
+    a.chunks_per_src = a.kc ? (ci1 + a.kc - 1) / a.kc : 0;
     a.b = w;
     a.ldbn = ci1 + ci2;
     a.ldbk = 1;

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kPwThreads, 3) k_stem_wgrad(const float* __res
   }
 }
 
-#define HNO_STEM_CONFIGS(X) X(1, 8) X(2, 8) X(4, 8) X(1, 24) X(2, 24) X(3, 24) X(4, 24)
+#define HNO_STEM_CONFIGS(X) X(1, 8) X(2, 8) X(4, 8) X(1, 12) X(2, 12) X(4, 12) X(1, 24) X(2, 24) X(3, 24) X(4, 24)
 
 int stem_supported(int cin, int f) {
 #define X(A, B_) \

@@ -175,8 +175,13 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
     for (int o = tid >> 5; o < n_outer; o += kNW)
       for (int i = tid & 31; i < n_inner; i += 32) {
         const int n = k_contig ? o : i, k = k_contig ? i : o;
+        // K axis of the image = chunks_per_src * KC rows per source; a source with fewer rows (12-channel tensors in
+        // 16-row chunks) leaves a gap the TMA zero-fills, so image column k maps to column src * rows[0] + r of B
+        const int kps = p.chunks_per_src * KC;
+        const int src = k >= kps ? 1 : 0, r = k - src * kps;
+        const int col = src * p.rows[0] + r;
         float v = 0.f;
-        if (n < p.nvalid && k < p.kvalid) v = p.scale * __ldg(p.b + (long)n * p.ldbn + (long)k * p.ldbk);
+        if (n < p.nvalid && r < p.rows[src] && col < p.kvalid) v = p.scale * __ldg(p.b + (long)n * p.ldbn + (long)col * p.ldbk);
         const float hi = rn_tf32_bits(v);
         if (kFuseN) {  // one image: rows [0, NPAD) = hi, rows [NPAD, 2 NPAD) = lo
           bhi[kmajor_plain_index<NB>(n, k)] = hi;

@@ -8,15 +8,15 @@ constexpr int kPwThreads = 256;
 
 template <int CO, int CI>
 struct WgTile {
-  static constexpr int TO = (CO % 8 == 0) ? CO / 8 : 1;
+  static constexpr int TO = (CO % 8 == 0) ? CO / 8 : ((CO > 8 && CO % 4 == 0) ? CO / 4 : 1);
   static constexpr int NOT_RAW = CO / TO;
   static constexpr int N_OT = NOT_RAW <= 1 ? 1 : (NOT_RAW <= 2 ? 2 : (NOT_RAW <= 4 ? 4 : 8));
-  static constexpr int TI = CI / 8;
-  static constexpr int N_IT = 8;
+  static constexpr int N_IT = CI % 8 == 0 ? 8 : 4;   // column threads per group (12-channel tensors: 4 x 3 rows)
+  static constexpr int TI = CI / N_IT;
   static constexpr int G = N_OT * N_IT;         // threads per group
   static constexpr int NG = kPwThreads / G;     // groups per CTA
-  static_assert(CI % 8 == 0, "input channels must be a multiple of 8");
-  static_assert(CO <= 8 || CO % 8 == 0, "output channels must be <= 8 or a multiple of 8");
+  static_assert(CI % 4 == 0, "input channels must be a multiple of 4");
+  static_assert(CO <= 8 || CO % 4 == 0, "output channels must be <= 8 or a multiple of 4");
 };
 
 // Accumulate dW[o][i] += sum_v dpre[o][v] * x[i][v] over this group's share of a TV-voxel tile.

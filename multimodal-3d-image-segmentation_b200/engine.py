@@ -81,6 +81,7 @@ class XSEngine:
         cur = a1
         stash = {}
         S.blocks = []
+        S.ds = [a1] if m.use_deep_supervision else None
         for i, layer in enumerate(m.layers):
             rec = _Saved()
             rec.map_in = None
@@ -114,8 +115,15 @@ class XSEngine:
             cur = y
             if m.use_unet_skip and i < nb // 2:
                 stash[i] = y
+            if m.use_deep_supervision:
+                S.ds.append(y)
         S.last = cur
-        S.ll = ops.pwconv_forward(cur, None, _w2(m.conv_out), None, 0, False)
+        if m.use_deep_supervision:
+            # conv_out over the concatenation of conv1's and every block's output (reference nets/hnosegxs.py:154-172):
+            # one pass over the list, the 216-channel concatenation is never formed
+            S.ll = ops.dsconv_forward(S.ds, _w2(m.conv_out), None, act=0)[0]
+        else:
+            S.ll = ops.pwconv_forward(cur, None, _w2(m.conv_out), None, 0, False)
         S.tables = get_interp_tables((D, H, W), image, dev)
         S.act = 1 if m.output_activation == 'softmax' else 0
         probs = None
@@ -156,10 +164,17 @@ class XSEngine:
         else:
             dll = ops.head_backward(dprobs, S.probs, S.tables, pitch, S.act)
         dw_, _ = out_w(m.conv_out)
-        dcur, _, g_out, _ = ops.pwconv_backward(dll, None, S.last, None, _w2(m.conv_out), 0, False, hw=hw,
-                                                has_bias=False, dweight=dw_)
-        block_grads = [None] * nb
         dstash = {}
+        if m.use_deep_supervision:
+            dins, g_out, _, _ = ops.dsconv_backward(dll, None, S.ds, _w2(m.conv_out), hw, act=0, has_bias=False,
+                                                    dweight=dw_)
+            dcur = dins[-1]
+            for j in range(nb):  # gradient of source j (= input of block j) waits as an accumulation target
+                dstash[j - 1] = dins[j]
+        else:
+            dcur, _, g_out, _ = ops.pwconv_backward(dll, None, S.last, None, _w2(m.conv_out), 0, False, hw=hw,
+                                                    has_bias=False, dweight=dw_)
+        block_grads = [None] * nb
         for i in reversed(range(nb)):
             layer = m.layers[i]
             rec = S.blocks[i]
@@ -202,13 +217,10 @@ class XSEngine:
                 op = layer.mapping_conv.op
                 tgt = dstash.pop(i - 1) if (i - 1) in dstash else None
                 dw_, db_ = out_w(op)
-                dprev, denc, g_wm, g_bm = ops.pwconv_backward(dxin, rec.xin, prev, enc, _w2(op), 1, False, hw=hw,
-                                                              din1=tgt, dweight=dw_, dbias=db_)
                 k = nb - 1 - i
-                if k in dstash:
-                    dstash[k] += denc
-                else:
-                    dstash[k] = denc
+                dprev, denc, g_wm, g_bm = ops.pwconv_backward(dxin, rec.xin, prev, enc, _w2(op), 1, False, hw=hw,
+                                                              din1=tgt, din2=dstash.get(k), dweight=dw_, dbias=db_)
+                dstash[k] = denc  # accumulated in place when an entry (deep-supervision gradient) was waiting
                 g += [g_wm.reshape(op.weight.shape), g_bm]
                 dcur = dprev
             else:
@@ -217,6 +229,7 @@ class XSEngine:
             if layer.conv_concat is not None:
                 g += [g_wc.reshape(layer.conv_concat.op.weight.shape), g_bc]
             block_grads[i] = g
+        assert not dstash, 'unconsumed skip / deep-supervision gradients'
         dw_, db_ = out_w(m.conv1.op)
         dpre0, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, _w2(m.conv1.op), 1, False, hw=hw,
                                                    in1_is_selu=True, dweight=dw_, dbias=db_)
@@ -292,3 +305,215 @@ class _XSCrossEntropyFunction(torch.autograd.Function):
         grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs)
         ctx.S = ctx.probs = None
         return (None, None, None) + tuple(grads)
+
+
+# =====================================================================================================================
+# FNO-family engine: NeuralOperatorSeg(transform_type='Hartley', shared weights) = HNOSeg, and HartleyMHASeg
+# =====================================================================================================================
+class TransSegEngine:
+    """Whole-network execution of the reference's `_TransSeg` models (nets/architectures.py:255-353) whose blocks are
+    `_TransBlock`s (:511-548): spectral op with its own transform pair + 1x1x1 conv branch -> SELU -> concat-skip conv,
+    optionally with deep supervision (conv_ds over all block outputs, :295-311, 330-343).  One autograd node; planar
+    activations; per block
+
+        t  = W_b x (+ b_b)                                     hno_pwconv_forward (no activation)
+        z  = (1/N) C x                                         hno_dht3_forward
+        z' = mix(z)                                            'hartley': selu(W z)   |   'mha': Hartley multi-head attention
+        y  = selu(t + C^T z')                                  hno_dht3_adjoint, epilogue 3, in place in t
+        out = selu(W_c [y; x] + b_c)                           hno_pwconv_forward over the virtual concat
+
+    The backward runs the same kernels transposed; skip / deep-supervision gradients accumulate in place."""
+
+    def __init__(self, model):
+        self.model = model
+
+    # ------------------------------------------------------------------------------------------ capability
+    @staticmethod
+    def block_kind(block):
+        from .nets.hartley_mha import HartleyMultiHeadAttention
+        from .nets.hartley_operator import HartleyOperator
+        op = block.op
+        if isinstance(op, HartleyOperator) and op.weights_type == 'shared' and op.use_transform and op.bias is None:
+            return 'hartley'
+        if isinstance(op, HartleyMultiHeadAttention) and op.use_transform:
+            return 'mha'
+        return None
+
+    @classmethod
+    def supports(cls, model):
+        if not getattr(model, 'use_resize', True):
+            return False
+        for blk in model.layers:
+            if cls.block_kind(blk) is None or blk.conv_branch is None or blk.conv_concat is None:
+                return False
+        return True
+
+    # ------------------------------------------------------------------------------------------ parameters
+    @staticmethod
+    def _op_params(blk, kind):
+        op = blk.op
+        if kind == 'hartley':
+            return [op.weight]
+        ps = [op.weight_query, op.weight_key, op.weight_value, op.weight_out]
+        if op.use_bias:
+            ps += [op.bias_query, op.bias_key, op.bias_value, op.bias_out]
+        return ps
+
+    def named_slots(self):
+        m = self.model
+        slots = [m.conv_in.op.weight, m.conv_in.op.bias, m.conv1.op.weight, m.conv1.op.bias]
+        for blk in m.layers:
+            slots.append(blk.conv_branch.weight)
+            if blk.conv_branch.bias is not None:
+                slots.append(blk.conv_branch.bias)
+            slots += self._op_params(blk, self.block_kind(blk))
+            slots += [blk.conv_concat.op.weight, blk.conv_concat.op.bias]
+        if m.conv_ds is not None:
+            slots += [m.conv_ds.op.weight, m.conv_ds.op.bias]
+        slots.append(m.conv_out.weight)
+        return slots
+
+    def forward(self, x):
+        params = self.named_slots()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _TransSegFunction.apply(self, x, *params)
+        return self.run_forward(x, save=False)[0]
+
+    # ------------------------------------------------------------------------------------------ forward
+    def run_forward(self, x, save=True, head=True):
+        m = self.model
+        if x.ndim != 5 or x.shape[1] != m.in_channels:
+            raise ValueError(f'{type(m).__name__} expects (B, {m.in_channels}, D, H, W) input, got {tuple(x.shape)}')
+        x = x.contiguous()
+        dev = x.device
+        image = tuple(x.shape[2:])
+        D, H, W = ops.stem_out_shape(image)
+        pitch = plane_pitch(H, W)
+        S = _Saved()
+        S.x, S.geom = x, (D, H, W, pitch)
+        a0 = ops.stem_forward(x, m.conv_in.op.weight, m.conv_in.op.bias, pitch)
+        a1 = ops.pwconv_forward(a0, None, _w2(m.conv1.op), m.conv1.op.bias, 1, False)
+        S.a0, S.a1 = a0, a1
+        ds = [a1] if m.conv_ds is not None else None
+        cur = a1
+        S.blocks = []
+        for blk in m.layers:
+            kind = self.block_kind(blk)
+            rec = _Saved()
+            rec.kind = kind
+            op = blk.op
+            if kind == 'mha':
+                assert all(s >= 2 * mm for s, mm in zip((D, H, W), op.num_modes))  # reference hartley_mha.py:165-172
+            plan = get_crop_plan((D, H, W), op.num_modes, dev)
+            rec.plan = plan
+            t = ops.pwconv_forward(cur, None, _w2(blk.conv_branch), blk.conv_branch.bias, 0, False)
+            z = ops.dht3_forward(cur, plan, 1.0 / plan.n_voxels)
+            if kind == 'hartley':
+                zmix = ops.pwconv_forward(z, None, op.weight, None, 1, False)  # mix + SELU on the retained modes
+                rec.z, rec.zmix = z, zmix
+            else:
+                def flat(b):
+                    return None if b is None else b.reshape(b.shape[1], b.shape[2]).contiguous()
+                bo = None if op.bias_out is None else op.bias_out.reshape(-1).contiguous()
+                zmix, rec.att = ops.hartley_attention_forward(z, None, None, op.weight_query, op.weight_key,
+                                                              op.weight_value, op.weight_out, flat(op.bias_query),
+                                                              flat(op.bias_key), flat(op.bias_value), bo, op.patch_size,
+                                                              op._act, save=save)
+            y = ops.dht3_adjoint(zmix, plan, 1.0, epilogue=3, out=t)  # y = selu(t + C^T z'), in place
+            out = ops.pwconv_forward(y, cur, _w2(blk.conv_concat.op), blk.conv_concat.op.bias, 1, False)
+            rec.x, rec.y, rec.out = cur, y, out
+            if save:
+                S.blocks.append(rec)
+            cur = out
+            if ds is not None:
+                ds.append(out)
+        S.last, S.ds = cur, ds
+        if ds is not None:
+            S.d, S.ll = ops.dsconv_forward(ds, _w2(m.conv_ds.op), m.conv_ds.op.bias, act=1, weight2=_w2(m.conv_out))
+        else:
+            S.ll = ops.pwconv_forward(cur, None, _w2(m.conv_out), None, 0, False)
+        S.tables = get_interp_tables((D, H, W), image, dev)
+        S.act = 1 if m.output_activation_name == 'softmax' else 0
+        probs = None
+        if head:
+            probs = ops.head_forward(S.ll, S.tables, pitch, S.act)
+            S.probs = probs
+        return probs, S
+
+    # ------------------------------------------------------------------------------------------ backward
+    def run_backward(self, S, dprobs=None, fused=None):
+        """Gradients in named_slots() order.  `dprobs` (drop-in autograd) or fused=(labels_u8, coef, grad_loss)."""
+        m = self.model
+        D, H, W, pitch = S.geom
+        hw = (pitch, H * W)
+        F = m.filters
+        if fused is not None:
+            labels, coef, grad_loss = fused
+            dll = ops.head_loss_backward(S.ll, labels, coef, grad_loss, S.tables, pitch)
+        else:
+            dll = ops.head_backward(dprobs, S.probs, S.tables, pitch, S.act)
+        nb = len(m.layers)
+        tail = []
+        if S.ds is not None:
+            dins, g_wds, g_bds, g_out = ops.dsconv_backward(dll, S.d, S.ds, _w2(m.conv_ds.op), hw, act=1,
+                                                            weight2=_w2(m.conv_out))
+            dcur = dins[-1]
+            tail = [g_wds.reshape(m.conv_ds.op.weight.shape), g_bds]
+        else:
+            dins = None
+            dcur, _, g_out, _ = ops.pwconv_backward(dll, None, S.last, None, _w2(m.conv_out), 0, False, hw=hw,
+                                                    has_bias=False)
+        block_grads = [None] * nb
+        for i in reversed(range(nb)):
+            blk, rec = m.layers[i], S.blocks[i]
+            opc = blk.conv_concat.op
+            target = dins[i] if dins is not None else None  # deep-supervision gradient of this block's input
+            dpre, dx, g_wc, g_bc = ops.pwconv_backward(dcur, rec.out, rec.y, rec.x, _w2(opc), 1, False, hw=hw,
+                                                       in1_is_selu=True, din2=target)
+            dzmix = ops.dht3_forward(dpre, rec.plan, 1.0)
+            if rec.kind == 'hartley':
+                dz, _, g_w, _ = ops.pwconv_backward(dzmix, rec.zmix, rec.z, None, blk.op.weight, 1, False, has_bias=False)
+                g_op = [g_w]
+            else:
+                g = ops.hartley_attention_backward(dzmix, rec.att)
+                dz = g[0]
+                g_op = [g[3], g[4], g[5], g[6]]
+                if blk.op.use_bias:
+                    op = blk.op
+                    g_op += [g[7].reshape(op.bias_query.shape), g[8].reshape(op.bias_key.shape),
+                             g[9].reshape(op.bias_value.shape), g[10].reshape(op.bias_out.shape)]
+            ops.dht3_adjoint(dz, rec.plan, 1.0 / rec.plan.n_voxels, epilogue=1, out=dx)  # dx += (1/N) C^T dz
+            cb = blk.conv_branch
+            _, _, g_wb, g_bb = ops.pwconv_backward(dpre, None, rec.x, None, _w2(cb), 0, False, hw=hw, din1=dx,
+                                                   has_bias=cb.bias is not None)
+            g = [g_wb.reshape(cb.weight.shape)]
+            if cb.bias is not None:
+                g.append(g_bb)
+            g += g_op + [g_wc.reshape(opc.weight.shape), g_bc]
+            block_grads[i] = g
+            dcur = dx
+        dpre0, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, _w2(m.conv1.op), 1, False, hw=hw,
+                                                   in1_is_selu=True)
+        g_win, g_bin = ops.stem_backward(dpre0, S.x, F, pitch)
+        grads = [g_win, g_bin, g_w1.reshape(m.conv1.op.weight.shape), g_b1]
+        for g in block_grads:
+            grads += g
+        grads += tail
+        grads.append(g_out.reshape(m.conv_out.weight.shape))
+        return grads
+
+
+class _TransSegFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        probs, S = engine.run_forward(x, save=True)
+        ctx.engine, ctx.S = engine, S
+        return probs
+
+    @staticmethod
+    def backward(ctx, dprobs):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError('hno_b200: the segmentation networks do not provide a gradient w.r.t. the input volume')
+        grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs.contiguous())
+        ctx.S = None
+        return (None, None) + tuple(grads)

@@ -89,28 +89,27 @@ class HartleyOperator(Module):
         kl = [list(range(mm)) + list(range(n - mm, n)) for n, mm in zip(spatial, m)]
         ext = [k + ([mm] if mm not in k else []) for k, mm in zip(kl, m)]
         z_ext = ops.TruncatedDHT.apply(inputs, get_dht_plan(spatial, ext, inputs.device))
-        z = hartley_conv_full_reverse(z_ext, self.weight, spatial, m)
-        z = torch.nn.functional.selu(z)
-        return z.contiguous(), get_dht_plan(spatial, kl, inputs.device)
+        z = ops.HartleyConvFull.apply(z_ext, self.weight, _partner_table(spatial, tuple(m), inputs.device), 1)
+        return z, get_dht_plan(spatial, kl, inputs.device)
 
 
-def hartley_conv_full_reverse(z_ext, weight, spatial, m):
-    """Mix of the with-transform / individual variant (HNOSeg 'FNO'-style config, not on the XS hot path).
-    z_ext holds the retained modes plus, last on each axis, the frequency +m.  Index algebra only; the
-    contraction itself is a torch einsum on a few MB."""
-    idx, ridx, widx = [], [], []
-    for n, mm, ax_len in zip(spatial, m, z_ext.shape[2:]):
-        ks = list(range(mm)) + list(range(n - mm, n))
-        pos = {k: i for i, k in enumerate(ks)}
-        if ax_len > len(ks):
+_partner_tables = {}
+
+
+def _partner_table(spatial, m, device):
+    """int32 device tensor [r0 | r1 | r2]: position, in the extended mode list (retained + [+m]), of the full-spectrum
+    reversal partner (n - k) mod n of every retained frequency k (reference get_reverse on the N-point spectrum, :199)."""
+    key = (tuple(spatial), tuple(m), str(device))
+    t = _partner_tables.get(key)
+    if t is None:
+        tab = []
+        for n, mm in zip(spatial, m):
+            ks = list(range(mm)) + list(range(n - mm, n))
+            pos = {k: i for i, k in enumerate(ks)}
             pos.setdefault(mm, len(ks))
-        idx.append(torch.arange(len(ks), device=z_ext.device))
-        ridx.append(torch.tensor([pos[(n - k) % n] for k in ks], device=z_ext.device))
-        widx.append(torch.tensor([(2 * mm - j) % (2 * mm) for j in range(2 * mm)], device=z_ext.device))
-    x = z_ext[:, :, idx[0]][:, :, :, idx[1]][:, :, :, :, idx[2]]
-    xr = z_ext[:, :, ridx[0]][:, :, :, ridx[1]][:, :, :, :, ridx[2]]
-    wr = weight[:, :, widx[0]][:, :, :, widx[1]][:, :, :, :, widx[2]]
-    return hartley_conv('oidhw,bidhw->bodhw', weight, wr, x, xr)
+            tab += [pos[(n - k) % n] for k in ks]
+        t = _partner_tables[key] = torch.tensor(tab, dtype=torch.int32, device=device)
+    return t
 
 
 def hartley_conv(equation, weight, weight_reverse, x, x_reverse):

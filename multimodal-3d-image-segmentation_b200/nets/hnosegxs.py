@@ -170,8 +170,6 @@ class HNOSegXS(nn.Module):
             raise NotImplementedError('hno_b200 HNOSegXS implements the SELU (self-normalising) variant only')
         if not use_resize:
             raise NotImplementedError('hno_b200 HNOSegXS requires use_resize=True (the stride-2 stem)')
-        if use_deep_supervision:
-            raise NotImplementedError('hno_b200 HNOSegXS does not support use_deep_supervision yet')
         if output_activation not in ('softmax', None, 'identity'):
             raise NotImplementedError("hno_b200 HNOSegXS supports output_activation in {'softmax', None}")
         if np.isscalar(self.num_transform_blocks):
@@ -192,7 +190,9 @@ class HNOSegXS(nn.Module):
         for i, n_convs in enumerate(self.num_transform_blocks):
             cin = f + (f if (self.use_unet_skip and i > nb // 2) else 0)
             self.layers.append(block(n_convs, cin, f))
-        self.conv_out = nn.Conv3d(f, self.out_channels, kernel_size=1, bias=False, device=self.device)
+        # deep supervision (reference :110-125, 134): conv_out reads the concatenation of conv1's and every block's output
+        cout_in = f * (nb + 1) if self.use_deep_supervision else f
+        self.conv_out = nn.Conv3d(cout_in, self.out_channels, kernel_size=1, bias=False, device=self.device)
         self.apply(init_weights_for_snn)
 
     # -- the network as one engine call ---------------------------------------------------------------------
@@ -242,6 +242,8 @@ class HNOSegXS(nn.Module):
     def forward_modular(self, x):
         """Same network composed from the stand-alone sub-modules (dense tensors, one autograd node per op).
         Slower than forward(); kept as an independent cross-check of the engine."""
+        if self.use_deep_supervision:
+            raise NotImplementedError('hno_b200: forward_modular does not implement deep supervision; use forward()')
         image_size = tuple(x.shape[2:])
         x = self.conv1(self.conv_in(x))
         nb = len(self.layers)

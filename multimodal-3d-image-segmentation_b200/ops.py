@@ -302,6 +302,38 @@ def hartley_conv_backward(dout, y, x, weight, need_dx=True, need_dw=True, dw=Non
     return dx, dw
 
 
+class HartleyConvFull(torch.autograd.Function):
+    """selu(1/2 [W(j)(X(j) + X(r j)) + W(~j)(X(j) - X(r j))]) with the partner r(j) taken in the FULL spectrum: the mixing of
+    HartleyOperator(use_transform=True, weights_type='individual') (reference nets/hartley_operator.py:196-241, 267).
+    x_ext (B, CI, E0, E1, E2): retained modes plus frequency +m per axis; rtab: int32 device tensor of partner positions."""
+
+    @staticmethod
+    def forward(ctx, x_ext, weight, rtab, act):
+        _require_cuda(x_ext, 'x_ext')
+        x_ext, weight = x_ext.contiguous(), weight.contiguous()
+        B, ci = x_ext.shape[:2]
+        co = weight.shape[0]
+        n = tuple(weight.shape[2:])
+        e = tuple(x_ext.shape[2:])
+        out = torch.empty((B, co) + n, dtype=torch.float32, device=x_ext.device)
+        call('hno_hartley_conv_full_forward', ptr(x_ext), ptr(weight), ptr(rtab), ptr(out), B, ci, co, *n, *e, int(act),
+             stream_ptr())
+        ctx.save_for_backward(x_ext, weight, rtab, out)
+        ctx.act = int(act)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_ext, weight, rtab, out = ctx.saved_tensors
+        B, ci = x_ext.shape[:2]
+        co = weight.shape[0]
+        dx = torch.empty_like(x_ext) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(weight) if ctx.needs_input_grad[1] else None
+        call('hno_hartley_conv_full_backward', ptr(dout.contiguous()), ptr(out) if ctx.act else None, ptr(x_ext), ptr(weight),
+             ptr(rtab), ptr(dx), ptr(dw), B, ci, co, *weight.shape[2:], *x_ext.shape[2:], stream_ptr())
+        return dx, dw, None, None
+
+
 class ComplexModeMix(torch.autograd.Function):
     """(a + i b)(k) = sum_i (wr + i wi)(o, i, k) (re + i im)(i, k): per-mode complex weights of FourierOperator
     (reference nets/fourier_operator.py:165-187, weights_type='individual') on real / imaginary mode tensors."""
@@ -566,8 +598,220 @@ def head_loss_backward(logits_low, labels, coef, grad_loss, tables, pitch):
     return dll
 
 
+# ------------------------------------------------------------------------------------------ deep-supervision conv
+def _int_array(vals):
+    import ctypes
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def dsconv_forward(sources, weight, bias, act=1, weight2=None):
+    """out = act(bias + sum_i W_i in_i) over a LIST of (B, C_i, D, P) planar tensors (conv_ds over the virtual
+    concatenation of all block outputs, reference nets/architectures.py:306-311, 339-343).  weight (CO, sum C_i).
+    weight2 (CO, CO): the bias-free conv_out that follows; returns (out, weight2 * out) then, else (out, None)."""
+    _require_cuda(sources[0], 'sources[0]')
+    srcs = [t.contiguous() for t in sources]
+    B = srcs[0].shape[0]
+    S = _flat_s(srcs[0])
+    co = weight.shape[0]
+    out = torch.empty((B, co) + tuple(srcs[0].shape[2:]), dtype=torch.float32, device=srcs[0].device)
+    out2 = torch.empty_like(out) if weight2 is not None else None
+    call('hno_dsconv_forward', _ptr_array(srcs), _int_array([t.shape[1] for t in srcs]), len(srcs),
+         ptr(weight.contiguous()), ptr(bias), ptr(out), ptr(weight2.contiguous()) if weight2 is not None else None,
+         ptr(out2), B, co, S, int(act), stream_ptr())
+    return out, out2
+
+
+def dsconv_backward(dy, y, sources, weight, hw, act=1, need_din=True, has_bias=True, dweight=None, dbias=None,
+                    weight2=None, dweight2=None):
+    """Returns ([din_i], dweight, dbias, dweight2).  hw = (P, HW): plane pitch and valid columns of the planar layout;
+    with weight2, dy is the gradient of the second output."""
+    import ctypes
+    srcs = [t.contiguous() for t in sources]
+    B = srcs[0].shape[0]
+    S = _flat_s(srcs[0])
+    co = weight.shape[0]
+    ctot = sum(t.shape[1] for t in srcs)
+    dev = srcs[0].device
+    dins = [torch.empty_like(t) for t in srcs] if need_din else None
+    if dweight is None:
+        dweight = torch.empty((co, ctot), dtype=torch.float32, device=dev)
+    if dbias is None and has_bias:
+        dbias = torch.empty((co,), dtype=torch.float32, device=dev)
+    ws = workspace(_lib.load().hno_dsconv_backward_workspace_bytes(ctot, co, B, S), dev, 'ds')
+    din_arr = _ptr_array(dins) if dins is not None else (ctypes.c_void_p * len(srcs))()
+    P, HW = hw if hw is not None else (S, S)
+    if weight2 is not None and dweight2 is None:
+        dweight2 = torch.empty((co, co), dtype=torch.float32, device=dev)
+    call('hno_dsconv_backward', _ptr_array(srcs), din_arr, _int_array([t.shape[1] for t in srcs]), len(srcs),
+         ptr(weight.contiguous()), ptr(dy.contiguous()), ptr(y),
+         ptr(weight2.contiguous()) if weight2 is not None else None, ptr(dweight), ptr(dbias), ptr(dweight2), ptr(ws), B,
+         co, S, int(P), int(HW), int(act), stream_ptr())
+    return dins, dweight, dbias, dweight2
+
+
+# ------------------------------------------------------------------------------------------ Hartley multi-head attention
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def mha_feature_pitch(features):
+    """Features per head padded for the GEMM tiles: a multiple of 32, and of 128 beyond 256."""
+    fp = _round_up(features, 32)
+    return fp if fp <= 256 else _round_up(features, 128)
+
+
+class MhaGeometry:
+    """Token / feature geometry of HartleyMultiHeadAttention on a cropped mode block (reference nets/hartley_mha.py:
+    179-196: grouping3d turns every patch of pd*ph*pw modes into one token with channels*pd*ph*pw features)."""
+
+    def __init__(self, modes_shape, patch):
+        self.L = tuple(int(v) for v in modes_shape)
+        self.patch = tuple(int(v) for v in patch) if patch is not None else (1, 1, 1)
+        if any(l % p for l, p in zip(self.L, self.patch)):
+            raise AssertionError(f'retained modes {self.L} must be divisible by the patch size {self.patch}')
+        self.P = self.patch[0] * self.patch[1] * self.patch[2]
+        self.T = (self.L[0] // self.patch[0]) * (self.L[1] // self.patch[1]) * (self.L[2] // self.patch[2])
+        self.Tp = _round_up(self.T, 128)
+
+    def args(self):
+        return self.L + self.patch + (self.Tp,)
+
+
+def mha_project_forward(z, w, bias, geom):
+    """z (B, cin, Ld, Lh, Lw), w (H, cd, cin) -> x_tok (B*H, Tp, Fp), x_chan (B*H, Fp, Tp)."""
+    _require_cuda(z, 'z')
+    z = z.contiguous()
+    B, cin = z.shape[:2]
+    H, cd = w.shape[:2]
+    fp = mha_feature_pitch(cd * geom.P)
+    x_tok = torch.empty((B * H, geom.Tp, fp), dtype=torch.float32, device=z.device)
+    x_chan = torch.empty((B * H, fp, geom.Tp), dtype=torch.float32, device=z.device)
+    call('hno_mha_project_forward', ptr(z), ptr(w.contiguous()), ptr(bias), ptr(x_tok), ptr(x_chan), B, H, cin, cd,
+         *geom.args(), fp, stream_ptr())
+    return x_tok, x_chan
+
+
+def mha_project_backward(dx_tok, z, w, geom, dz=None, has_bias=False):
+    """Returns (dz, dw, dbias); `dz` given -> accumulated into."""
+    B, cin = z.shape[:2]
+    H, cd = w.shape[:2]
+    acc = dz is not None
+    if dz is None:
+        dz = torch.empty_like(z)
+    dw = torch.empty_like(w)
+    db = torch.empty((H, cd), dtype=torch.float32, device=z.device) if has_bias else None
+    call('hno_mha_project_backward', ptr(dx_tok), ptr(z), ptr(w.contiguous()), ptr(dz), ptr(dw), ptr(db), B, H, cin, cd,
+         *geom.args(), dx_tok.shape[2], int(acc), stream_ptr())
+    return dz, dw, db
+
+
+class _MhaSaved:
+    pass
+
+
+def hartley_attention_forward(zq, zk, zv, wq, wk, wv, wo, bq=None, bk=None, bv=None, bo=None, patch=None, activation=1,
+                              save=True):
+    """The frequency-domain part of HartleyMultiHeadAttention (reference nets/hartley_mha.py:165-216 between the transforms):
+    per-head Q / K / V projections + grouping, att = act(Q^T K / sqrt(F)), att V, ungrouping, output projection.
+    zk / zv None: shared with the previous input (self-attention computes ONE transform).  Returns (y, saved)."""
+    geom = MhaGeometry(zq.shape[2:], patch)
+    zk_ = zq if zk is None else zk
+    zv_ = zk_ if zv is None else zv
+    B = zq.shape[0]
+    H, kd = wq.shape[:2]
+    vd = wv.shape[1]
+    q_tok, q_chan = mha_project_forward(zq, wq, bq, geom)
+    k_tok, k_chan = mha_project_forward(zk_, wk, bk, geom)
+    v_tok, v_chan = mha_project_forward(zv_, wv, bv, geom)
+    fq, fv = q_tok.shape[2], v_tok.shape[2]
+    scale = 1.0 / float(kd * geom.P) ** 0.5  # att / sqrt(key.shape[2]) with the grouped channel count (:199)
+    dev = zq.device
+    P = torch.empty((B * H, geom.Tp, geom.Tp), dtype=torch.float32, device=dev)
+    PT = torch.empty_like(P) if save else None
+    o_tok = torch.empty((B * H, geom.Tp, fv), dtype=torch.float32, device=dev)
+    call('hno_mha_attention_forward', ptr(q_tok), ptr(k_tok), ptr(v_chan), ptr(P), ptr(PT), ptr(o_tok), B * H, geom.Tp, fq,
+         fv, scale, int(activation), stream_ptr())
+    co = wo.shape[0]
+    y = torch.empty((B, co) + geom.L, dtype=torch.float32, device=dev)
+    call('hno_mha_output_forward', ptr(o_tok), ptr(wo.contiguous()), ptr(bo), ptr(y), B, H, co, vd, *geom.args(), fv,
+         stream_ptr())
+    if not save:
+        return y, None
+    S = _MhaSaved()
+    S.geom, S.scale, S.activation = geom, scale, int(activation)
+    S.z = (zq, zk, zv)
+    S.w = (wq, wk, wv, wo)
+    S.has_bias = (bq is not None, bk is not None, bv is not None, bo is not None)
+    S.q_chan, S.k_chan, S.v_tok, S.P, S.PT, S.o_tok = q_chan, k_chan, v_tok, P, PT, o_tok
+    return y, S
+
+
+def hartley_attention_backward(dy, S):
+    """Returns (dzq, dzk, dzv, dwq, dwk, dwv, dwo, dbq, dbk, dbv, dbo); dzk / dzv are None where the input was shared
+    (their contribution is accumulated into the gradient of the tensor they share)."""
+    geom = S.geom
+    zq, zk, zv = S.z
+    wq, wk, wv, wo = S.w
+    B = zq.shape[0]
+    H, kd = wq.shape[:2]
+    vd = wv.shape[1]
+    co = wo.shape[0]
+    dev = zq.device
+    fq, fv = S.q_chan.shape[1], S.v_tok.shape[2]
+    dy = dy.contiguous()
+    do_tok = torch.empty((B * H, geom.Tp, fv), dtype=torch.float32, device=dev)
+    do_chan = torch.empty((B * H, fv, geom.Tp), dtype=torch.float32, device=dev)
+    dwo = torch.empty_like(wo)
+    dbo = torch.empty((co,), dtype=torch.float32, device=dev) if S.has_bias[3] else None
+    call('hno_mha_output_backward', ptr(dy), ptr(S.o_tok), ptr(wo.contiguous()), ptr(do_tok), ptr(do_chan), ptr(dwo),
+         ptr(dbo), B, H, co, vd, *geom.args(), fv, stream_ptr())
+    tt = B * H * geom.Tp * geom.Tp * 4
+    scratch = workspace(2 * tt, dev, 'mha')
+    dS = scratch[:tt].view(torch.float32)
+    dST = scratch[tt:2 * tt].view(torch.float32)
+    dq_tok = torch.empty((B * H, geom.Tp, fq), dtype=torch.float32, device=dev)
+    dk_tok = torch.empty_like(dq_tok)
+    dv_tok = torch.empty((B * H, geom.Tp, fv), dtype=torch.float32, device=dev)
+    call('hno_mha_attention_backward', ptr(do_tok), ptr(do_chan), ptr(S.q_chan), ptr(S.k_chan), ptr(S.v_tok), ptr(S.P),
+         ptr(S.PT), ptr(dS), ptr(dST), ptr(dq_tok), ptr(dk_tok), ptr(dv_tok), B * H, geom.Tp, fq, fv, S.scale,
+         S.activation, stream_ptr())
+    dzq, dwq, dbq = mha_project_backward(dq_tok, zq, wq, geom, None, S.has_bias[0])
+    if zk is None:
+        _, dwk, dbk = mha_project_backward(dk_tok, zq, wk, geom, dzq, S.has_bias[1])
+        dzk, zk_ = None, zq
+        dzk_acc = dzq
+    else:
+        dzk, dwk, dbk = mha_project_backward(dk_tok, zk, wk, geom, None, S.has_bias[1])
+        zk_, dzk_acc = zk, dzk
+    if zv is None:
+        _, dwv, dbv = mha_project_backward(dv_tok, zk_, wv, geom, dzk_acc, S.has_bias[2])
+        dzv = None
+    else:
+        dzv, dwv, dbv = mha_project_backward(dv_tok, zv, wv, geom, None, S.has_bias[2])
+    return dzq, dzk, dzv, dwq, dwk, dwv, dwo, dbq, dbk, dbv, dbo
+
+
+class HartleyAttention(torch.autograd.Function):
+    """Autograd wrapper of hartley_attention_forward / _backward for the stand-alone module."""
+
+    @staticmethod
+    def forward(ctx, zq, zk, zv, wq, wk, wv, wo, bq, bk, bv, bo, patch, activation):
+        y, S = hartley_attention_forward(zq.detach(), None if zk is None else zk.detach(),
+                                         None if zv is None else zv.detach(), wq.detach(), wk.detach(), wv.detach(),
+                                         wo.detach(), bq, bk, bv, bo, patch, activation, save=True)
+        ctx.S = S
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = hartley_attention_backward(dy, ctx.S)
+        ctx.S = None
+        return g + (None, None)
+
+
 __all__ = ['dht3_forward', 'dht3_adjoint', 'TruncatedDHT', 'TruncatedIDHT', 'AddIDHTSelu', 'pwconv_forward', 'pwconv_backward',
            'PointwiseConv', 'HartleyConv', 'ComplexModeMix', 'stem_forward', 'stem_backward', 'StemConv', 'head_forward',
            'head_backward', 'HeadUpsample', 'ProbabilityLoss', 'CrossEntropyOnProbabilities', 'ce_loss_forward',
            'ce_loss_backward', 'LOSS_DEFAULT_PARAM', 'head_loss_forward', 'head_loss_backward',
-           'get_crop_plan', 'get_interp_tables', 'workspace', 'LOSS_KINDS']
+           'get_crop_plan', 'get_interp_tables', 'workspace', 'LOSS_KINDS', 'HartleyAttention', 'hartley_attention_forward',
+           'hartley_attention_backward', 'dsconv_forward', 'dsconv_backward', 'head_argmax']

@@ -152,7 +152,7 @@ class FusedAdamax:
 
 
 class Trainer:
-    """The library's own training step for HNOSegXS: forward, fused head+loss on integer labels, backward straight
+    """The library's own training step for HNOSegXS (and the engine-backed NeuralOperatorSeg / HartleyMHASeg): forward, fused head+loss on integer labels, backward straight
     into the flat gradient buffer (no autograd graph), one gradient all-reduce, fused Adamax.
 
     Equivalent to the step body of experiments/train_test.py:146-171 with `to_categorical`, `loss_fn(model(x), y)`,
@@ -177,6 +177,9 @@ class Trainer:
         self.flat = FlatParameters(model)
         self.slots = self.engine.named_slots()
         self.dst = [self.flat.grad_view_of(p) for p in self.slots]
+        import inspect
+        # XSEngine writes its gradients straight into the flat buffer; other engines return them and they are copied
+        self._direct = 'dst' in inspect.signature(self.engine.run_backward).parameters
         self.optimizer = FusedAdamax(self.flat, lr=lr)
         self.group = group
 
@@ -188,12 +191,19 @@ class Trainer:
             if self.kind is None:
                 probs, S = self.engine.run_forward(x, save=True)
                 loss = ops.ce_loss_forward(probs, labels=lab)
-                self.engine.run_backward(S, dprobs=ops.ce_loss_backward(probs, labels=lab), dst=self.dst)
+                self._backward(S, dprobs=ops.ce_loss_backward(probs, labels=lab))
                 return loss
             _, S = self.engine.run_forward(x, save=True, head=False)
             loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], self.kind, self.loss_param)
-            self.engine.run_backward(S, fused=(lab, coef, None), dst=self.dst)
+            self._backward(S, fused=(lab, coef, None))
         return loss
+
+    def _backward(self, S, **kw):
+        if self._direct:
+            self.engine.run_backward(S, dst=self.dst, **kw)
+        else:
+            for d, g in zip(self.dst, self.engine.run_backward(S, **kw)):
+                d.copy_(g.reshape(d.shape))
 
     def loss_and_grad_graphed(self, x, labels):
         """loss_and_grad replayed from a CUDA graph captured for exactly these two buffers (contents may change)."""

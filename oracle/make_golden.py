@@ -392,6 +392,36 @@ def case_full():
     save('model_full_probe', **out)
 
 
+def case_deep_supervision():
+    """use_deep_supervision=True (nets/hnosegxs.py:110-125, 154-172; nets/architectures.py:295-311, 330-343) for HNOSeg-XS
+    and HNOSeg in small: probabilities, Dice loss and every parameter gradient recorded from the real reference (the
+    HartleyMHASeg fixture covers the third user of the same head)."""
+    out = {}
+    torch.manual_seed(31)
+    xs = ref.HNOSegXS(2, 3, 8, [1, 2, 1, 2, 1, 2], (2, 3, 3), use_deep_supervision=True)
+    torch.manual_seed(32)
+    hn = ref.NeuralOperatorSeg(2, 3, 8, 3, (2, 3, 3), 'Hartley', use_deep_supervision=True)
+    torch.manual_seed(33)
+    x = torch.randn(2, 2, 18, 16, 13)
+    labels = torch.randint(0, 3, (2, 1, 18, 16, 13))
+    onehot = torch.zeros(2, 3, 18, 16, 13).scatter_(1, labels, 1.0)
+    out.update({'x': x.numpy(), 'labels': labels.numpy().astype(np.uint8)})
+    for tag, model in (('xs', xs), ('hnoseg', hn)):
+        model.zero_grad()
+        probs = model(x)
+        loss = ref_losses.DiceLoss()(probs, onehot)
+        loss.backward()
+        out[f'{tag}/probs'] = probs.detach().numpy()
+        out[f'{tag}/DiceLoss/loss'] = loss.detach().numpy()
+        out.update({f'{tag}/sd/{k}': v.detach().numpy().copy() for k, v in model.state_dict().items()})
+        out.update({f'{tag}/DiceLoss/grad/{k}': p.grad.numpy().copy() for k, p in model.named_parameters()})
+        print(f'  deep supervision {tag}: loss {float(loss):.6f}, conv_out {tuple(model.conv_out.weight.shape)}')
+    # the oracle restates the _TransSeg head (used for HartleyMHASeg): pin it on the HNOSeg variant too
+    sd = {k: v.detach() for k, v in hn.state_dict().items()}
+    check('HNOSeg deep supervision probs', orc.hnoseg_forward(sd, x, 3, (2, 3, 3)), torch.from_numpy(out['hnoseg/probs']))
+    save('deep_supervision_small', **out)
+
+
 def case_superres():
     """BASELINE config 4: zero-shot super-resolution = the SAME weights on a 2x grid (README.md:83-87), run through the
     reference's testing path (experiments/train_test.py:373-414: model.eval(), no_grad, forward, host argmax).  Stores the
@@ -452,6 +482,7 @@ if __name__ == '__main__':
     case_hnoseg('Hartley', 'hnoseg_individual_small', weights_type='individual')
     # config_fno.ini: the original FNO (per-mode complex weights, biased conv branch, no block skip)
     case_hnoseg('Fourier', 'fno_small', weights_type='individual', use_bias_conv_branch=True, use_block_skip=False)
+    case_deep_supervision()
     if args.full:
         case_full()
         case_superres()
