@@ -698,6 +698,212 @@ __global__ void __launch_bounds__(32 * kRowWarps, 4) k_head_bwd_w_rows(const flo
   }
 }
 
+// ---- whole-row kernels (round 2) ---------------------------------------------------------------------------------
+// The segment kernels above spend most of their issue slots outside the arithmetic: a warp blends ~17 taps on 17 of its
+// 32 lanes for every 32-voxel segment (segments overlap by a tap), reloads the W-axis tables for every voxel, and with
+// five segments per 155-voxel row the sixth warp of the CTA idles (ncu, round 1: 196 M warp instructions for 17.9 M
+// voxels, issue-bound at 2 % of HBM).  Here ONE WARP OWNS A WHOLE ROW: it blends the four low-resolution rows of every
+// class over the full low-resolution width into its own shared-memory row (coalesced, all lanes busy, done once per row
+// instead of once per segment), and every lane then walks its voxels lane, lane + 32, ... with the W-axis taps and weights
+// of those voxels held in registers for the whole kernel (they are the same for every row).
+constexpr int kWRowWarps = 8;
+
+template <int C, int ACT, int KMAX>
+__global__ void __launch_bounds__(32 * kWRowWarps, 2) k_head_loss_wrow(const float* __restrict__ ll,
+                                                                       const uint8_t* __restrict__ labels,
+                                                                       double* __restrict__ partials, InterpDev t, long P,
+                                                                       int WP) {
+  extern __shared__ float sRow[];                      // [kWRowWarps][C][WP]
+  __shared__ double sacc[kWRowWarps][C][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int Wx = t.hi[2], Hx = t.hi[1], W = t.lo[2];
+  const int rows = t.hi[0] * Hx;
+  const int S = t.lo[0] * (int)P;
+  const float* llb = ll + (long)b * C * S;
+  const uint8_t* lb = labels + (long)b * rows * Wx;
+  float* sR = sRow + warp * C * WP;
+  int w0[KMAX], w1[KMAX];
+  float lw1[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int zw = lane + 32 * k;
+    const bool ok = zw < Wx;
+    w0[k] = ok ? t.i0[2][zw] : 0;
+    w1[k] = ok ? t.i1[2][zw] : 0;
+    lw1[k] = ok ? t.l1[2][zw] : 0.f;
+  }
+  float m[C][4];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[c][k] = 0.f;
+  if (lane < C * 4) sacc[warp][lane >> 2][lane & 3] = 0.0;
+  __syncwarp();
+  auto fold = [&]() {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = warp_sum(m[c][k]);
+        if (lane == 0) sacc[warp][c][k] += (double)v;
+        m[c][k] = 0.f;
+      }
+  };
+  int cnt = 0;
+  for (int row = blockIdx.x * kWRowWarps + warp; row < rows; row += gridDim.x * kWRowWarps) {
+    const int zd = row / Hx, zh = row - zd * Hx;
+    const RowBlend rb = make_row_blend(t, P, W, zd, zh);
+    const uint8_t* lrow = lb + (long)row * Wx;
+    int lab[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) lab[k] = lane + 32 * k < Wx ? (int)__ldg(lrow + lane + 32 * k) : -1;
+    for (int w = lane; w < W; w += 32) {
+      float r[C];
+      blend_rows<C>(llb, S, rb, w, r);
+#pragma unroll
+      for (int c = 0; c < C; ++c) sR[c * WP + w] = r[c];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (lane + 32 * k < Wx) {
+        const float l1 = lw1[k], l0 = 1.f - l1;
+        float p[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) p[c] = l0 * sR[c * WP + w0[k]] + l1 * sR[c * WP + w1[k]];
+        if (ACT == 1) softmax_fast<C>(p);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float tt = lab[k] == c ? 1.f : 0.f;
+          m[c][0] += p[c];
+          m[c][1] += tt;
+          m[c][2] = fmaf(p[c], tt, m[c][2]);
+          m[c][3] = fmaf(p[c], p[c], m[c][3]);
+        }
+      }
+    }
+    __syncwarp();
+    if (++cnt == 16) {  // bounded fp32 run length (16 rows x KMAX voxels per lane), then into fp64
+      fold();
+      cnt = 0;
+    }
+  }
+  fold();
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * kMoments; i += blockDim.x) {
+    const int c = i / kMoments, k = i - c * kMoments;
+    const int kk = k == 4 ? 1 : k;  // t*t == t for one-hot labels
+    double sum = 0.0;
+    for (int w = 0; w < kWRowWarps; ++w) sum += sacc[w][c][kk];
+    partials[(((long)b * C + c) * gridDim.x + blockIdx.x) * kMoments + k] = sum;
+  }
+}
+
+// backward, W pass with one warp per row: the d(logit) of the whole row goes to the warp's shared-memory row, then lane
+// w_lo gathers the (two to five) voxels that touch low-resolution tap w_lo.  g1 as k_head_bwd_w_rows.
+template <int C, int ACT, int KMAX>
+__global__ void __launch_bounds__(32 * kWRowWarps, 2) k_head_bwd_wrow(const float* __restrict__ ll,
+                                                                      const uint8_t* __restrict__ labels,
+                                                                      const float* __restrict__ coef,
+                                                                      const float* __restrict__ grad_loss,
+                                                                      float* __restrict__ g1, InterpDev t, long P, int WP,
+                                                                      int WXP) {
+  extern __shared__ float sRow[];                      // [kWRowWarps][C][WP] blended rows, then [kWRowWarps][C][WXP] d(logit)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int Wx = t.hi[2], Hx = t.hi[1], W = t.lo[2];
+  const int rows = t.hi[0] * Hx;
+  const int S = t.lo[0] * (int)P;
+  const float* llb = ll + (long)b * C * S;
+  const uint8_t* lb = labels + (long)b * rows * Wx;
+  float* sR = sRow + warp * C * WP;
+  float* sD = sRow + kWRowWarps * C * WP + warp * C * WXP;
+  int w0[KMAX], w1[KMAX];
+  float lw1[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int zw = lane + 32 * k;
+    const bool ok = zw < Wx;
+    w0[k] = ok ? t.i0[2][zw] : 0;
+    w1[k] = ok ? t.i1[2][zw] : 0;
+    lw1[k] = ok ? t.l1[2][zw] : 0.f;
+  }
+  float ca[C], cb[C], cg[C];
+  {
+    const float gl = grad_loss ? __ldg(grad_loss) : 1.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      ca[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 0);
+      cb[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 1);
+      cg[c] = gl * __ldg(coef + ((long)b * C + c) * 3 + 2);
+    }
+  }
+  for (int row = blockIdx.x * kWRowWarps + warp; row < rows; row += gridDim.x * kWRowWarps) {
+    const int zd = row / Hx, zh = row - zd * Hx;
+    const RowBlend rb = make_row_blend(t, P, W, zd, zh);
+    const uint8_t* lrow = lb + (long)row * Wx;
+    int lab[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) lab[k] = lane + 32 * k < Wx ? (int)__ldg(lrow + lane + 32 * k) : -1;
+    for (int w = lane; w < W; w += 32) {
+      float r[C];
+      blend_rows<C>(llb, S, rb, w, r);
+#pragma unroll
+      for (int c = 0; c < C; ++c) sR[c * WP + w] = r[c];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int zw = lane + 32 * k;
+      if (zw < Wx) {
+        const float l1 = lw1[k], l0 = 1.f - l1;
+        float p[C], g[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) p[c] = l0 * sR[c * WP + w0[k]] + l1 * sR[c * WP + w1[k]];
+        if (ACT == 1) softmax_fast<C>(p);
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c] = ca[c] + (lab[k] == c ? cb[c] : 0.f) + cg[c] * p[c];
+        if (ACT == 1) {
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) dot = fmaf(g[c], p[c], dot);
+#pragma unroll
+          for (int c = 0; c < C; ++c) sD[c * WXP + zw] = p[c] * (g[c] - dot);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) sD[c * WXP + zw] = g[c];
+        }
+      }
+    }
+    __syncwarp();
+    for (int wl = lane; wl < W; wl += 32) {
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = 0.f;
+      const int z1 = t.e[2][wl];
+      for (int z2 = t.s[2][wl]; z2 < z1; ++z2) {
+        const float l1 = t.l1[2][z2];
+        const float wgt = (t.i0[2][z2] == wl ? 1.f - l1 : 0.f) + (t.i1[2][z2] == wl ? l1 : 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, sD[c * WXP + z2], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) g1[(((long)b * C + c) * (long)rows + row) * W + wl] = acc[c];
+    }
+    __syncwarp();
+  }
+}
+
+// 0: the whole-row kernels do not apply (too wide a row for the register-resident tables / shared-memory rows)
+static int wrow_kmax(const InterpDev& t) {
+  static const bool on = !(getenv("HNO_HEAD_WROW") && atoi(getenv("HNO_HEAD_WROW")) == 0);
+  if (!on || t.hi[2] < t.lo[2] || t.lo[2] > 256) return 0;
+  if (t.hi[2] <= 32 * 5) return 5;
+  if (t.hi[2] <= 32 * 10) return 10;
+  return 0;
+}
+
 // Largest tap-group size (<= 16) for which every group's voxels and taps fit one warp; 0 = use the per-voxel kernels.
 static int row_kernels_tap_group(const void* th) {
   const auto* h = reinterpret_cast<const InterpHeader*>(th);
@@ -1135,7 +1341,17 @@ int head_loss_forward(const void* th, const void* td, const float* ll, const uin
   double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + ((g12 * sizeof(float) + 255) & ~(size_t)255));
   int chunks = (int)((Nx + 255) / 256 < kLossChunks ? (Nx + 255) / 256 : kLossChunks);
   dim3 grid(chunks, B);
-  if (row_kernels_enabled() && row_kernels_tap_group(th) > 0) {
+  if (const int kmax = wrow_kmax(t)) {
+    const long rows = (long)t.hi[0] * t.hi[1];
+    chunks = (int)((rows + kWRowWarps - 1) / kWRowWarps < kLossChunks ? (rows + kWRowWarps - 1) / kWRowWarps : kLossChunks);
+    grid = dim3(chunks, B);
+    const int WP = (t.lo[2] + 3) & ~3;
+    const size_t smem = (size_t)kWRowWarps * C * WP * sizeof(float);
+    HNO_CLASS_SWITCH(C, {
+      if (kmax == 5) k_head_loss_wrow<kC, 1, 5><<<grid, 32 * kWRowWarps, smem, st>>>(ll, labels, partials, t, P, WP);
+      else k_head_loss_wrow<kC, 1, 10><<<grid, 32 * kWRowWarps, smem, st>>>(ll, labels, partials, t, P, WP);
+    })
+  } else if (row_kernels_enabled() && row_kernels_tap_group(th) > 0) {
     const long rows = (long)t.hi[0] * t.hi[1];
     chunks = (int)(rows < kLossChunks ? rows : kLossChunks);
     grid = dim3(chunks, B);
@@ -1157,7 +1373,24 @@ int head_loss_backward(const void* th, const void* td, const float* ll, const ui
   float* g1 = reinterpret_cast<float*>(ws);
   float* g2 = g1 + (size_t)B * C * t.hi[0] * t.hi[1] * t.lo[2];
   const int tg = row_kernels_enabled() ? row_kernels_tap_group(th) : 0;
-  if (tg > 0) {
+  if (const int kmax = wrow_kmax(t)) {
+    const long rows = (long)t.hi[0] * t.hi[1];
+    const long want = (rows + kWRowWarps - 1) / kWRowWarps;
+    dim3 grid((int)(want < 4 * 296 ? want : 4 * 296), B);
+    const int WP = (t.lo[2] + 3) & ~3, WXP = (t.hi[2] + 3) & ~3;
+    const size_t smem = (size_t)kWRowWarps * C * (WP + WXP) * sizeof(float);
+    HNO_CLASS_SWITCH(C, {
+      if (kmax == 5) {
+        auto kern = k_head_bwd_wrow<kC, 1, 5>;
+        HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 32 * kWRowWarps, smem, st>>>(ll, labels, coef, grad_loss, g1, t, P, WP, WXP);
+      } else {
+        auto kern = k_head_bwd_wrow<kC, 1, 10>;
+        HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 32 * kWRowWarps, smem, st>>>(ll, labels, coef, grad_loss, g1, t, P, WP, WXP);
+      }
+    })
+  } else if (tg > 0) {
     const long rows = (long)t.hi[0] * t.hi[1];
     dim3 grid((int)(rows < 4 * 296 ? rows : 4 * 296), B);
     HNO_CLASS_SWITCH(C, {

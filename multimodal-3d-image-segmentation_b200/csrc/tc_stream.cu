@@ -953,6 +953,7 @@ int tc_stream_launch(const TcStreamArgs& a_in, cudaStream_t st) {
     if (loader >= 0) a.loader = loader;
     if (a.in_rw > 0) a.loader = 0;  // only the cp.async loader can gather
   }
+  if (tc_analysis_eligible(a)) return tc_analysis_launch(a, st);
   {  // HNO_TC_KERNEL=regs selects the experimental ring -> registers -> tensor-memory data path (tc_regs.cu); measured
      // on B200 it ties with the shared-memory-operand ring below (pw48f 0.171-0.182 ms vs 0.169 ms), see DESIGN.md
     static const bool regs = getenv("HNO_TC_KERNEL") && !strcmp(getenv("HNO_TC_KERNEL"), "regs");

@@ -43,6 +43,10 @@ struct TcStreamArgs {
 
 bool tc_stream_eligible(const TcStreamArgs& a);
 int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st);
+// analysis stages of the transform (kc = 16, <= 32 output rows, one source) with the streamed operand fed through tensor
+// memory (tc_analysis.cu); tc_stream_launch routes to it when eligible (HNO_TC_ANALYSIS=0 keeps the shared-memory-operand ring)
+bool tc_analysis_eligible(const TcStreamArgs& a);
+int tc_analysis_launch(const TcStreamArgs& a, cudaStream_t st);
 // register-fed variant (tc_regs.cu): A operand loaded global -> registers -> tensor memory; the default
 bool tc_regs_eligible(const TcStreamArgs& a);
 int tc_regs_launch(const TcStreamArgs& a, cudaStream_t st);
