@@ -12,7 +12,7 @@
 //   * every worker thread owns one voxel (= one TMEM lane): it forms d(pre) in registers, writes the two TF32 terms to
 //     tensor memory and the fp32 value to a shared tile;
 //   * the input gradient runs on the tensor cores: A = d(pre) from TMEM (M = 128 voxels, K = 24), B = [W^T_hi | W^T_lo]
-//     resident in shared memory, 3xTF32 as two instructions per k-step (tc_regs.cu explains the fusion);
+//     resident in shared memory, 3xTF32 as two instructions per k-step (one instruction A [B_hi | B_lo] of N = 2 NP whose halves are added in the epilogue, plus A_lo B_hi into the first half);
 //   * while those MMAs execute, the workers accumulate the weight gradient with packed FFMA2 out of shared memory
 //     (exact fp32 products, fp32 partial sums per CTA, fp64 final reduction: k_reduce_partials);
 //   * the epilogue reads the accumulator (one lane per voxel), applies selu'(in1) / the += of U-Net skips and writes

@@ -47,7 +47,14 @@ struct TcShape {
   // issued by a seventh warp: one STS per element instead of one STG with 64-bit address arithmetic, and the
   // accumulate form becomes a bulk reduce-add (the old values are never loaded by the SM).
   static constexpr bool kTmaOut = NPAD >= 128;
-  static constexpr int kStageBufs = kTmaOut ? 2 : 0;        // staging buffers of 32 rows x 128 voxels
+#ifndef HNO_TC_STAGE_BUFS
+#define HNO_TC_STAGE_BUFS 3
+#endif
+  // staging buffers of 32 rows x 128 voxels.  Three, with up to two bulk stores in flight behind the one being filled: the
+  // issuer used to wait for every store to finish READING its buffer before it even looked at the next one, so stores
+  // were serialised with a bubble and the workers waited ~930 cycles per block for a free buffer (cycle counters,
+  // profiles/r2g_prof2.log).  128-row instances afford it (one lo buffer less), 256-row ones keep two.
+  static constexpr int kStageBufs = kTmaOut ? (NPAD <= 128 ? HNO_TC_STAGE_BUFS : 2) : 0;
   static constexpr int kStageBytes = 32 * 128 * 4;
   // Narrow outputs (pointwise convolutions, analysis stages): the operand split of tile t+1 and the epilogue of tile t
   // run on DIFFERENT warps (4 split warps + 4 epilogue warps) instead of one after the other on the same four -- the
@@ -154,8 +161,9 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
   // 128-byte aligned
   float* stage = sbias + NPAD;
   __shared__ __align__(8) uint64_t bar_read[NST];   // loader 2: ring stage read by the split warps (128 arrivals)
-  __shared__ __align__(8) uint64_t bar_stfull[2];   // staging buffer written by the workers   (128 arrivals)
-  __shared__ __align__(8) uint64_t bar_stfree[2];   // bulk store has read the staging buffer (1 arrival)
+  constexpr int kSB = TcShape<NPAD>::kStageBufs > 0 ? TcShape<NPAD>::kStageBufs : 1;
+  __shared__ __align__(8) uint64_t bar_stfull[kSB];   // staging buffer written by the workers   (128 arrivals)
+  __shared__ __align__(8) uint64_t bar_stfree[kSB];   // bulk store has read the staging buffer (1 arrival)
   __shared__ __align__(8) uint64_t bar_full[NST];   // TMA bytes landed                     (1 arrival + tx)
   __shared__ __align__(8) uint64_t bar_split[NST];  // hi / lo operands ready                (128 arrivals)
   __shared__ __align__(8) uint64_t bar_done[NST];   // MMAs of the item retired              (tcgen05.commit)
@@ -206,10 +214,11 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
     mbar_init(&bar_accfree[1], kTcWorkers);
     mbar_init(&bar_accfull[0], 1);
     mbar_init(&bar_accfull[1], 1);
-    mbar_init(&bar_stfull[0], kTcWorkers);
-    mbar_init(&bar_stfull[1], kTcWorkers);
-    mbar_init(&bar_stfree[0], 1);
-    mbar_init(&bar_stfree[1], 1);
+#pragma unroll
+    for (int sb = 0; sb < kSB; ++sb) {
+      mbar_init(&bar_stfull[sb], kTcWorkers);
+      mbar_init(&bar_stfree[sb], 1);
+    }
     mbar_fence_init();
   }
   if (warp == kWW) tmem_alloc(&tmem_slot, kTmemCols);
@@ -402,8 +411,8 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
         const int g = tile / (uint32_t)p.tiles_per_slab;
         const int m0 = (tile - (uint32_t)g * p.tiles_per_slab) * 128;
         for (int n0 = 0; n0 < p.nout; n0 += 32, ++sblk) {
-          const int sb = sblk & 1;
-          mbar_wait(&bar_stfull[sb], (uint32_t)((sblk >> 1) & 1));
+          const int sb = sblk % kSB;
+          mbar_wait(&bar_stfull[sb], (uint32_t)((sblk / kSB) & 1));
           const uint32_t src = smem_u32(stage + sb * (32 * 128));
           if (p.epi == 1)
             asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmo),
@@ -414,10 +423,12 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
                          "r"(src), "r"(m0), "r"(n0), "r"(g)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer may be rewritten
-          mbar_arrive(&bar_stfree[sb]);
+          // all but the newest kSB - 1 stores have finished reading shared memory: the oldest of them frees its buffer
+          asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kSB - 1) : "memory");
+          if (sblk >= kSB - 1) mbar_arrive(&bar_stfree[(sblk - (kSB - 1)) % kSB]);
         }
       }
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncwarp();
@@ -511,8 +522,8 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
             mbar_arrive(&bar_accfree[ti & 1]);
           }
           if (p.prof_mode == 2) { q1 = clock64(); w_lo += q1 - q0; q0 = q1; }
-          const int sb = st_blk & 1;
-          if (st_blk >= 2) mbar_wait(&bar_stfree[sb], (uint32_t)(((st_blk >> 1) - 1) & 1));
+          const int sb = st_blk % kSB;
+          if (st_blk >= kSB) mbar_wait(&bar_stfree[sb], (uint32_t)(((st_blk / kSB) - 1) & 1));
           if (p.prof_mode == 2) { q1 = clock64(); w_full += q1 - q0; q0 = q1; }
           float* so = stage + sb * (32 * 128) + (quarter * 32 + lane);
           if (tile_live && !has_bias) {  // the common block: no predicates at all (rows >= nout are zeros of the
@@ -954,34 +965,18 @@ int tc_stream_launch(const TcStreamArgs& a_in, cudaStream_t st) {
     if (a.in_rw > 0) a.loader = 0;  // only the cp.async loader can gather
   }
   if (tc_analysis_eligible(a)) return tc_analysis_launch(a, st);
-  {  // HNO_TC_KERNEL=regs selects the experimental ring -> registers -> tensor-memory data path (tc_regs.cu); measured
-     // on B200 it ties with the shared-memory-operand ring below (pw48f 0.171-0.182 ms vs 0.169 ms), see DESIGN.md
-    static const bool regs = getenv("HNO_TC_KERNEL") && !strcmp(getenv("HNO_TC_KERNEL"), "regs");
-    if (regs && tc_regs_eligible(a)) return tc_regs_launch(a, st);
-  }
   const int npad = a.nout <= 32 ? 32 : (a.nout <= 128 ? 128 : 256);
-  static const int variant = getenv("HNO_TC_VARIANT") ? atoi(getenv("HNO_TC_VARIANT")) : 0;
-#define HNO_TC_CASE(KC_, NP_, NST_, NLO_, VAR_)                                  \
-  if (a.kc == KC_ && npad == NP_ && variant == VAR_) return launch_t<KC_, NP_, NST_, NLO_>(a, st);
-  HNO_TC_CASE(24, 32, 4, 3, 1)
-  HNO_TC_CASE(24, 32, 4, 4, 2)
-  HNO_TC_CASE(24, 32, 3, 2, 3)
-  HNO_TC_CASE(16, 32, 5, 4, 1)
-  HNO_TC_CASE(16, 32, 6, 4, 2)
-  HNO_TC_CASE(16, 32, 3, 2, 3)
-  HNO_TC_CASE(16, 32, 5, 2, 4)
-#undef HNO_TC_CASE
   // loader 2 keeps a third set of chunk buffers (the hi image): its own stage counts so that 2 CTAs still fit an SM
-  if (a.loader == 2 && a.kc == 24 && npad == 32 && variant == 0) return launch_t<24, 32, 4, 2>(a, st);
-  if (a.loader == 2 && a.kc == 16 && npad == 32 && variant == 0) return launch_t<16, 32, 3, 2>(a, st);
+  if (a.loader == 2 && a.kc == 24 && npad == 32) return launch_t<24, 32, 4, 2>(a, st);
+  if (a.loader == 2 && a.kc == 16 && npad == 32) return launch_t<16, 32, 3, 2>(a, st);
 #define HNO_TC_CASE(KC_, NP_, NST_, NLO_)                                  \
   if (a.kc == KC_ && npad == NP_) return launch_t<KC_, NP_, NST_, NLO_>(a, st);
   HNO_TC_CASE(24, 32, 5, 3)   // pointwise conv 24(+24) -> <= 32: 2 CTAs / SM of 4 split + 4 epilogue warps
   HNO_TC_CASE(32, 32, 3, 2)
   HNO_TC_CASE(16, 32, 6, 3)   // D / H-axis analysis: 8 KB chunks (TMA loader + L2 prefetch cursor)
   HNO_TC_CASE(8, 32, 4, 2)
-  HNO_TC_CASE(24, 128, 2, 2)  // D-axis synthesis (one chunk per tile)
-  HNO_TC_CASE(16, 128, 3, 2)  // H-axis synthesis (29 rows = two chunks)
+  HNO_TC_CASE(24, 128, 2, 1)  // D-axis synthesis (one chunk per tile); smem: 3 staging buffers instead of a second lo buffer
+  HNO_TC_CASE(16, 128, 2, 1)  // H-axis synthesis (29 rows = two chunks)
   HNO_TC_CASE(32, 128, 2, 1)
   HNO_TC_CASE(8, 128, 3, 2)
   HNO_TC_CASE(24, 256, 3, 2)  // synthesis onto axes of 129..256 samples (2x super-resolution grids)

@@ -47,9 +47,6 @@ int tc_stream_launch(const TcStreamArgs& a, cudaStream_t st);
 // memory (tc_analysis.cu); tc_stream_launch routes to it when eligible (HNO_TC_ANALYSIS=0 keeps the shared-memory-operand ring)
 bool tc_analysis_eligible(const TcStreamArgs& a);
 int tc_analysis_launch(const TcStreamArgs& a, cudaStream_t st);
-// register-fed variant (tc_regs.cu): A operand loaded global -> registers -> tensor memory; the default
-bool tc_regs_eligible(const TcStreamArgs& a);
-int tc_regs_launch(const TcStreamArgs& a, cudaStream_t st);
 // Global switch (tests / A-B measurements): returns the previous value.
 int tc_set_enabled(int on);
 bool tc_enabled();

@@ -151,6 +151,23 @@ class FusedAdamax:
         self.weight_decay = group.get('weight_decay', self.weight_decay)
 
 
+def cosine_warm_restarts_lr(step, base_lr, T_0, T_mult=1, eta_min=0.0):
+    """Learning rate of torch.optim.lr_scheduler.CosineAnnealingWarmRestarts after `step` calls of scheduler.step() -- the
+    reference's schedule (experiments/run.py:96-103: T_0 = batches x epochs, stepped once per batch, train_test.py:173-174) --
+    as a host scalar for FusedAdamax.step(lr=...) / Trainer.step(lr=...): step 0 is the lr of the first update."""
+    import math
+    step, T_0, T_mult = int(step), int(T_0), int(T_mult)
+    if T_0 <= 0 or T_mult < 1:
+        raise ValueError('T_0 must be positive and T_mult >= 1')
+    if T_mult == 1:
+        t_cur, t_i = step % T_0, T_0
+    else:
+        n = int(math.log(step / T_0 * (T_mult - 1) + 1, T_mult)) if step >= T_0 else 0
+        t_cur = step - T_0 * (T_mult ** n - 1) // (T_mult - 1)
+        t_i = T_0 * T_mult ** n
+    return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * t_cur / t_i)) / 2
+
+
 class Trainer:
     """The library's own training step for HNOSegXS (and the engine-backed NeuralOperatorSeg / HartleyMHASeg): forward, fused head+loss on integer labels, backward straight
     into the flat gradient buffer (no autograd graph), one gradient all-reduce, fused Adamax.

@@ -113,3 +113,18 @@ def test_fused_adamax_state_dict_is_a_snapshot_and_converts_to_torch_layout():
     opt2.load_state_dict(ref.state_dict())  # and back
     assert opt2.step_count == 7 and opt2.lr == 1e-2
     assert torch.all(opt2.exp_avg == 1.5) and torch.all(opt2.exp_inf == 0.25)
+
+
+def test_cosine_warm_restarts_matches_torch_scheduler():
+    """Host-side schedule for FusedAdamax == torch's CosineAnnealingWarmRestarts stepped per batch (run.py:96-103)."""
+    from multimodal_3d_image_segmentation_b200 import parallel
+    for T_0, T_mult, eta_min in ((7, 1, 0.0), (5, 2, 1e-4), (3, 3, 0.0)):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adamax([p], lr=5e-3)
+        sch = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=T_0, T_mult=T_mult, eta_min=eta_min)
+        for step in range(60):
+            want = opt.param_groups[0]['lr']
+            got = parallel.cosine_warm_restarts_lr(step, 5e-3, T_0, T_mult, eta_min)
+            assert abs(got - want) < 1e-12, (T_0, T_mult, step, got, want)
+            opt.step()
+            sch.step()

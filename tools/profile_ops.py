@@ -1,5 +1,5 @@
 """Runs selected hot-path entry points at the BASELINE shapes (batch 2) a few times, for ncu captures:
-    python tools/profile_ops.py pw48f dhtf dhts dhta pw48b [reps]"""
+    python tools/profile_ops.py pw48f dhtf dhts dhta pw48b mhaf mhab [reps]"""
 import os
 import sys
 
@@ -24,6 +24,20 @@ z = rnd(batch, F, *plan.modes_shape)
 w48, w24, b24 = rnd(F, 2 * F) * 0.1, rnd(F, F) * 0.1, rnd(F) * 0.01
 hw = (P, H * W)
 xin = rnd(batch, 4, *VOLUME)
+zm = rnd(batch, 12, 20, 28, 28)
+wm = [rnd(4, 12, 12) * 0.1 for _ in range(3)] + [rnd(12, 48) * 0.1]
+_mha = {}
+
+
+def mha_fwd():
+    _mha['y'], _mha['S'] = ops.hartley_attention_forward(zm, None, None, *wm, patch=(2, 2, 2), activation=1)
+
+
+def mha_bwd():
+    if 'S' not in _mha:
+        mha_fwd()
+    ops.hartley_attention_backward(_mha['y'], _mha['S'])
+
 win = rnd(F, 4, 2, 2, 2) * 0.1
 table = {
     'stemf': lambda: ops.stem_forward(xin, win, b24, P),
@@ -35,6 +49,8 @@ table = {
     'dhta': lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=1, out=a[1]),
     'pw48b': lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, in1_is_selu=True),
     'pw48ba': lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, din1=acc[0], din2=acc[1]),
+    'mhaf': mha_fwd,
+    'mhab': mha_bwd,
     'pw24b': lambda: ops.pwconv_backward(a[0], a[1], a[2], None, w24, 1, False, hw=hw, in1_is_selu=True),
 }
 for n in names:
