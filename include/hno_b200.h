@@ -64,6 +64,27 @@ int hno_dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z
                      long slab_stride, void* workspace, int nslab, float scale, int epilogue, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * One HNO-XS block's spectral part in one call       replaces nets/hnosegxs.py:260-263 (+ the SELU of :267-268):
+ *   transform_crop -> n_XS x NeuralOperatorBlock (shared weights) -> pad_inverse
+ * forward :  out = EPI( C^T chain( scale_in * C x ) ),  z_all [L+1][B][C][Ld][Lh][Lw] receives z_0 .. z_L (may be null)
+ * backward:  out (op)= scale_out * C^T chain_bwd( C dt ),  dweights[l] [C][C] written (or accumulated)
+ * Five launches (D analysis, H analysis, spectral core, H synthesis, D synthesis): the W stages, the cas recombination and
+ * the mixes run in ONE kernel whose CTAs own the modes of one (sample, |u_d|, |u_h|) for all channels (csrc/spectral_core.cu).
+ * x, out: planar [B][C][D][pitch]; weights / dweights: L device pointers to [C][C] matrices; epilogue as hno_dht3_adjoint;
+ * workspace: hno_dht3_workspace_bytes; partials (backward only): hno_dht3_chain_partials_bytes.
+ * hno_dht3_chain_eligible == 0: use hno_dht3_forward / hno_modechain_* / hno_dht3_adjoint instead.
+ * ------------------------------------------------------------------------------------------ */
+int hno_dht3_chain_eligible(const void* plan_host, const float* x, long plane_pitch, long slab_stride, int B, int C, int L);
+size_t hno_dht3_chain_partials_bytes(const void* plan_host, int C, int L, int B);
+int hno_dht3_chain_forward(const void* plan_host, const void* plan_dev, const float* x, float* out, long plane_pitch,
+                           long slab_stride, const float* const* weights, float* z_all, void* workspace, int B, int C, int L,
+                           float scale_in, int epilogue, void* stream);
+int hno_dht3_chain_backward(const void* plan_host, const void* plan_dev, const float* dt, float* out, long plane_pitch,
+                            long slab_stride, const float* const* weights, float* const* dweights, const float* z_all,
+                            void* workspace, void* partials, int B, int C, int L, float scale_out, int epilogue,
+                            int accumulate_dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Pointwise (1x1x1) channel mixing  y = act( W * [in1 ; in2] + bias (+ in1 if residual) )
  *   replaces nets/nets_utils.py:120-174 (ConvNormAct, kernel_size 1, SELU, no norm),
  *            nets/hartley_operator.py:287-292 + nets/hnosegxs.py:307-329 (shared-weight mode mix

@@ -33,6 +33,10 @@ SIGNATURES = {
     'hno_dht3_workspace_bytes': (_Z, [_P, _L, _I]),
     'hno_dht3_forward': (_I, [_P, _P, _P, _L, _L, _P, _P, _I, _F, _P]),
     'hno_dht3_adjoint': (_I, [_P, _P, _P, _P, _L, _L, _P, _I, _F, _I, _P]),
+    'hno_dht3_chain_eligible': (_I, [_P, _P, _L, _L, _I, _I, _I]),
+    'hno_dht3_chain_partials_bytes': (_Z, [_P, _I, _I, _I]),
+    'hno_dht3_chain_forward': (_I, [_P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _I, _F, _I, _P]),
+    'hno_dht3_chain_backward': (_I, [_P, _P, _P, _P, _L, _L, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _I, _P]),
     'hno_pwconv_supported': (_I, [_I, _I, _I]),
     'hno_pwconv_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _I, _I, _P]),
     'hno_pwconv_backward_workspace_bytes': (_Z, [_I, _I, _I]),

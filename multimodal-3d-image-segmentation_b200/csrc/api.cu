@@ -39,6 +39,10 @@ int sm_count() {
 int dht3_forward(const void*, const void*, const float*, long, long, float*, void*, int, float, cudaStream_t);
 int dht3_adjoint(const void*, const void*, const float*, float*, long, long, void*, int, float, int, cudaStream_t);
 size_t dht3_workspace_floats(const void*, long, int);
+bool dht3_chain_eligible(const void*, const float*, long, long, int, int, int);
+size_t dht3_chain_partials_bytes(const void*, int, int, int);
+int dht3_chain(const void*, const void*, const float*, float*, long, long, const float* const*, float* const*, float*, void*,
+               void*, int, int, int, float, float, int, int, int, cudaStream_t);
 int pwconv_supported(int, int, int, int, int);
 int pwconv_forward(const float*, const float*, const float*, const float*, float*, int, int, int, int, long, int, int,
                    cudaStream_t);
@@ -328,6 +332,26 @@ int hno_hartley_conv_full_backward(const float* dout, const float* y, const floa
                                    int n1, int n2, int e0, int e1, int e2, void* stream) {
   return hartley_conv_full_backward(dout, y, x_ext, weight, partner_table, dx_ext, dweight, B, ci, co, n0, n1, n2, e0, e1,
                                     e2, ST(stream));
+}
+
+int hno_dht3_chain_eligible(const void* plan_host, const float* x, long plane_pitch, long slab_stride, int B, int C, int L) {
+  return dht3_chain_eligible(plan_host, x, plane_pitch, slab_stride, B, C, L) ? 1 : 0;
+}
+size_t hno_dht3_chain_partials_bytes(const void* plan_host, int C, int L, int B) {
+  return dht3_chain_partials_bytes(plan_host, C, L, B);
+}
+int hno_dht3_chain_forward(const void* plan_host, const void* plan_dev, const float* x, float* out, long plane_pitch,
+                           long slab_stride, const float* const* weights, float* z_all, void* workspace, int B, int C, int L,
+                           float scale_in, int epilogue, void* stream) {
+  return dht3_chain(plan_host, plan_dev, x, out, plane_pitch, slab_stride, weights, nullptr, z_all, workspace, nullptr, B, C,
+                    L, scale_in, 1.f, epilogue, 0, 0, ST(stream));
+}
+int hno_dht3_chain_backward(const void* plan_host, const void* plan_dev, const float* dt, float* out, long plane_pitch,
+                            long slab_stride, const float* const* weights, float* const* dweights, const float* z_all,
+                            void* workspace, void* partials, int B, int C, int L, float scale_out, int epilogue,
+                            int accumulate_dw, void* stream) {
+  return dht3_chain(plan_host, plan_dev, dt, out, plane_pitch, slab_stride, weights, dweights, const_cast<float*>(z_all),
+                    workspace, partials, B, C, L, 1.f, scale_out, epilogue, 1, accumulate_dw, ST(stream));
 }
 
 int hno_dsconv_forward(const float* const* in, const int* ch, int n, const float* weight, const float* bias, float* out,

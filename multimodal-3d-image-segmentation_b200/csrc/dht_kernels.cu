@@ -867,6 +867,71 @@ int dht3_adjoint(const void* plan_host, const void* plan_dev, const float* z, fl
   return 0;
 }
 
+// ---- DHT -> n_XS shared-weight mixes -> inverse DHT of one HNO-XS block as five launches (D analysis, H analysis, spectral
+//      core, H synthesis, D synthesis) instead of eight: the W stages, the cas recombination and the mode chain run inside
+//      ONE kernel (spectral_core.cu).  forward:  out = EPI(C^T chain(scale_in C x));  zall receives z_0..z_L.
+//      backward: out (+)= scale_out C^T chain_bwd(C dt);  dweights written (fp64-reduced per-CTA partials).
+bool spectral_core_eligible(const void* plan_host, int C, int L, int B);
+size_t spectral_core_partials_floats(const void* plan_host, int C, int L, int B);
+int spectral_core(const void* plan_host, const void* plan_dev, float* T2, float* zall, const float* const* weights,
+                  float* const* dweights, float* partials, int B, int C, int L, float scale_in, float scale_out,
+                  bool backward, int accumulate_dw, cudaStream_t st);
+
+bool dht3_chain_eligible(const void* plan_host, const float* x, long plane_pitch, long slab_stride, int B, int C, int L) {
+  static const bool on = !(getenv("HNO_SPECTRAL_CORE") && atoi(getenv("HNO_SPECTRAL_CORE")) == 0);
+  const DhtPlanHeader* h;
+  if (!on || check_plan(plan_host, &h)) return false;
+  HsplitGeom hg;
+  if (!hsplit_geom(h, plane_pitch, slab_stride, x, B * C, &hg)) return false;
+  return spectral_core_eligible(plan_host, C, L, B);
+}
+
+size_t dht3_chain_partials_bytes(const void* plan_host, int C, int L, int B) {
+  return spectral_core_partials_floats(plan_host, C, L, B) * sizeof(float) + 256;
+}
+
+int dht3_chain(const void* plan_host, const void* plan_dev, const float* x, float* out, long plane_pitch, long slab_stride,
+               const float* const* weights, float* const* dweights, float* zall, void* ws, void* partials, int B, int C,
+               int L, float scale_in, float scale_out, int epilogue, int backward, int accumulate_dw, cudaStream_t st) {
+  const DhtPlanHeader* h;
+  if (check_plan(plan_host, &h)) return -1;
+  HNO_CHECK(plan_dev && x && out && ws && weights, "dht3_chain: null pointer");
+  HNO_CHECK(dht3_chain_eligible(plan_host, x, plane_pitch, slab_stride, B, C, L) &&
+                reinterpret_cast<uintptr_t>(out) % 16 == 0,
+            "dht3_chain: configuration not eligible (use hno_dht3_forward / hno_modechain_* / hno_dht3_adjoint)");
+  HNO_CHECK(epilogue >= 0 && epilogue <= 3, "dht3_chain: bad epilogue");
+  const int nslab = B * C;
+  const float* pf = reinterpret_cast<const float*>(plan_dev);
+  HsplitGeom hg;
+  hsplit_geom(h, plane_pitch, slab_stride, x, nslab, &hg);
+  float* G1 = reinterpret_cast<float*>(ws);
+  const long g1h = (long)hg.H * hg.rowlen;
+  float* T2 = G1 + (long)nslab * g1h;
+  TcStreamArgs a1 = hsplit_stage(x, plane_pitch, slab_stride, hg.D, plane_pitch, nslab, pf + h->ax[0].off_full, false,
+                                 hg.D, hg.Jd, G1, hg.Wp, g1h, (long)hg.H * hg.W);
+  a1.out_rw = hg.W;
+  a1.out_rp = hg.rowlen;
+  TcStreamArgs a2 = hsplit_stage(G1, hg.rowlen, g1h, hg.H, hg.rowlen, nslab, pf + h->ax[1].off_full, false, hg.H, hg.Jh,
+                                 T2, hg.rowlen, (long)hg.Jh * hg.rowlen, hg.rowlen);
+  TcStreamArgs s2 = hsplit_stage(T2, hg.rowlen, (long)hg.Jh * hg.rowlen, hg.Jh, hg.rowlen, nslab, pf + h->ax[1].off_full,
+                                 true, hg.H, hg.Jh, G1, hg.rowlen, g1h, hg.rowlen);
+  TcStreamArgs s1 = hsplit_stage(G1, hg.Wp, g1h, hg.Jd, plane_pitch, nslab, pf + h->ax[0].off_full, true, hg.D, hg.Jd, out,
+                                 plane_pitch, slab_stride, (long)hg.H * hg.W);
+  s1.in_rw = hg.W;
+  s1.in_rp = hg.rowlen;
+  s1.act = epilogue >= 2 ? 1 : 0;
+  s1.epi = (epilogue == 1 || epilogue == 3) ? 1 : 0;
+  HNO_CHECK(tc_stream_eligible(a1) && tc_stream_eligible(a2) && tc_stream_eligible(s1) && tc_stream_eligible(s2),
+            "dht3_chain: streamed stages not eligible");
+  if (int rc = tc_stream_launch(a1, st)) return rc;
+  if (int rc = tc_stream_launch(a2, st)) return rc;
+  if (int rc = spectral_core(plan_host, plan_dev, T2, zall, weights, dweights, reinterpret_cast<float*>(partials), B, C, L,
+                             scale_in, scale_out, backward != 0, accumulate_dw, st))
+    return rc;
+  if (int rc = tc_stream_launch(s2, st)) return rc;
+  return tc_stream_launch(s1, st);
+}
+
 size_t dht3_workspace_floats(const void* plan_host, long plane_pitch, int nslab) {
   const auto* h = reinterpret_cast<const DhtPlanHeader*>(plan_host);
   const DhtGeom g = geom(h, plane_pitch);

@@ -34,26 +34,105 @@ __device__ __forceinline__ void mha_locate(const MhaGeom& g, int m, int& t, int&
   po = ((d % g.pd) * g.ph + h % g.ph) * g.pw + w % g.pw;
 }
 
-// z [B][cin][M], w [H][cd][cin], bias [H][cd] or null -> x_tok [B*H][Tp][Fp], x_chan [B*H][Fp][Tp]  (pre-zeroed buffers)
-__global__ void __launch_bounds__(256) k_mha_project_fwd(const float* __restrict__ z, const float* __restrict__ w,
+// Token decomposition without per-element divisions: token t -> (td, th, tw); mode index of patch offset (id, ih, iw).
+struct MhaTok {
+  int td, th, tw;
+};
+__device__ __forceinline__ MhaTok mha_token(const MhaGeom& g, int t) {
+  const int nh = g.Lh / g.ph, nw = g.Lw / g.pw;
+  MhaTok k;
+  k.tw = t % nw;
+  const int r = t / nw;
+  k.th = r % nh;
+  k.td = r / nh;
+  return k;
+}
+
+constexpr int kMhaPMax = 8;  // patch sizes up to 8 modes (2 x 2 x 2) take the register-resident fast paths
+// mode offsets of the (up to kMhaPMax) patch positions of token k, in grouping3d's (id, ih, iw) order
+__device__ __forceinline__ void mha_patch_offsets(const MhaGeom& g, const MhaTok& k, int (&moff)[kMhaPMax]) {
+  const int base = ((k.td * g.pd) * g.Lh + k.th * g.ph) * g.Lw + k.tw * g.pw;
+#pragma unroll
+  for (int po = 0; po < kMhaPMax; ++po) {
+    const int iw = po % g.pw, r = po / g.pw;
+    const int ih = r % g.ph, id = r / g.ph;
+    moff[po] = base + (id * g.Lh + ih) * g.Lw + iw;
+  }
+}
+
+// Weight element (h, c, i) lives at w[h * sh + c * sc + i * si]: the projections read weight_{query,key,value} [H][cd][cin]
+// (sh = cd cin, sc = cin, si = 1), the backward of the output projection reads weight_out [co][H cd] transposed
+// (sh = cd, sc = 1, si = H cd).
+struct MhaW {
+  long sh, sc, si;
+};
+
+// src [B][cin][M] (mode tensor), w, bias [H][cd] or null -> x_tok [B*H][Tp][Fp], x_chan [B*H][Fp][Tp], padding included.
+// grid (Tp / 256, cd, B*H): a thread owns token t of channel c of head h and produces its P patch features: the
+// feature-major copy is written coalesced (consecutive threads = consecutive tokens), the token-major one in runs of P
+// floats; tokens >= T and (last channel block) features >= cd * P are written as zeros -- no memset passes.
+__global__ void __launch_bounds__(256) k_mha_project_fwd(const float* __restrict__ src, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ x_tok,
-                                                         float* __restrict__ x_chan, MhaGeom g, int cin, int cd, int Fp) {
-  const long idx = blockIdx.x * 256L + threadIdx.x;
-  if (idx >= g.M) return;
-  const int m = (int)idx;
-  const int bh = blockIdx.y, b = bh / g.H, h = bh % g.H;
-  int t, po;
-  mha_locate(g, m, t, po);
+                                                         float* __restrict__ x_chan, MhaGeom g, MhaW ws, int cin, int cd,
+                                                         int Fp) {
+  extern __shared__ float swt[];  // the cin weights of this (h, c)
+  const int c = blockIdx.y, bh = blockIdx.z, b = bh / g.H, h = bh % g.H;
+  for (int i = threadIdx.x; i < cin; i += 256) swt[i] = __ldg(w + h * ws.sh + c * ws.sc + i * ws.si);
+  __syncthreads();
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= g.Tp) return;
   const int P = g.pd * g.ph * g.pw;
-  const float* zp = z + (long)b * cin * g.M + m;
-  const float* wp = w + (long)h * cd * cin;
-  float* xt = x_tok + ((long)bh * g.Tp + t) * Fp + po;
-  float* xc = x_chan + ((long)bh * Fp + po) * g.Tp + t;
-  for (int c = 0; c < cd; ++c) {
-    float acc = bias ? __ldg(bias + h * cd + c) : 0.f;
-    for (int i = 0; i < cin; ++i) acc = fmaf(__ldg(wp + c * cin + i), __ldg(zp + (long)i * g.M), acc);
-    xt[c * P] = acc;
-    xc[(long)c * P * g.Tp] = acc;
+  float* xt = x_tok + ((long)bh * g.Tp + t) * Fp + c * P;
+  float* xc = x_chan + ((long)bh * Fp + c * P) * g.Tp + t;
+  const bool live = t < g.T;
+  const float b0 = bias ? __ldg(bias + h * cd + c) : 0.f;
+  const MhaTok k = live ? mha_token(g, t) : MhaTok{0, 0, 0};
+  const float* sp = src + (long)b * cin * g.M;
+  if (P <= kMhaPMax) {
+    // the P mode offsets of this token's patch, then cin x P independent loads (the naive nest -- one load, one FMA, next --
+    // ran at one L2 round trip per element: 27 us for 3 MB)
+    int moff[kMhaPMax];
+    mha_patch_offsets(g, k, moff);
+    float acc[kMhaPMax];
+#pragma unroll
+    for (int po = 0; po < kMhaPMax; ++po) acc[po] = live ? b0 : 0.f;
+    if (live) {
+#pragma unroll 2
+      for (int i = 0; i < cin; ++i) {
+        const float wv = swt[i];
+        const float* zi = sp + (long)i * g.M;
+#pragma unroll
+        for (int po = 0; po < kMhaPMax; ++po)
+          if (po < P) acc[po] = fmaf(wv, __ldg(zi + moff[po]), acc[po]);
+      }
+    }
+#pragma unroll
+    for (int po = 0; po < kMhaPMax; ++po)
+      if (po < P) {
+        xt[po] = acc[po];
+        xc[(long)po * g.Tp] = acc[po];
+      }
+  } else {
+    int po = 0;
+    for (int id = 0; id < g.pd; ++id)
+      for (int ih = 0; ih < g.ph; ++ih)
+        for (int iw = 0; iw < g.pw; ++iw, ++po) {
+          float acc = 0.f;
+          if (live) {
+            const long m = ((long)(k.td * g.pd + id) * g.Lh + k.th * g.ph + ih) * g.Lw + k.tw * g.pw + iw;
+            acc = b0;
+#pragma unroll 4
+            for (int i = 0; i < cin; ++i) acc = fmaf(swt[i], __ldg(sp + (long)i * g.M + m), acc);
+          }
+          xt[po] = acc;
+          xc[(long)po * g.Tp] = acc;
+        }
+  }
+  if (c == cd - 1) {  // feature padding
+    for (int f = cd * P; f < Fp; ++f) {
+      x_tok[((long)bh * g.Tp + t) * Fp + f] = 0.f;
+      x_chan[((long)bh * Fp + f) * g.Tp + t] = 0.f;
+    }
   }
 }
 
@@ -72,38 +151,78 @@ __global__ void __launch_bounds__(256) k_mha_project_bwd_z(const float* __restri
   for (int h = 0; h < g.H; ++h) {
     const float* dx = dx_tok + ((long)(b * g.H + h) * g.Tp + t) * Fp + po;
     const float* wp = w + (long)h * cd * cin + i;
+#pragma unroll 6
     for (int c = 0; c < cd; ++c) acc = fmaf(__ldg(wp + c * cin), __ldg(dx + c * P), acc);
   }
   float* o = dz + ((long)b * cin + i) * g.M + m;
   *o = accumulate ? *o + acc : acc;
 }
 
-// dw [H][cd][cin] = sum_{b, m} dx_tok[b, h][t][c P + po] * z[b][i][m];  one CTA per (h, c, i); i == cin -> the bias gradient
-__global__ void __launch_bounds__(256) k_mha_project_bwd_w(const float* __restrict__ dx_tok, const float* __restrict__ z,
-                                                           float* __restrict__ dw, float* __restrict__ dbias, MhaGeom g,
-                                                           int cin, int cd, int Fp) {
+// dw(h, c, i) = sum_{b, t, po} dx_tok[b, h][t][c P + po] * src[b][i][m(t, po)]          (dw indexed through MhaW like w)
+// grid (cin + extra, cd, H) + bias blocks; one CTA per output, threads over (b, t) pairs (token decode once per pair, patch
+// offsets in the inner loops: no per-element index divisions), bounded fp32 runs folded into fp64.
+//   bias_mode 1 (projections): block i == cin sums dx_tok over everything            -> dbias[h][c]
+//   bias_mode 2 (output projection, src = dy): blocks (c == 0, h == 0, i) of an extra grid row sum src[b][i][:] -> dbias[i]
+__global__ void __launch_bounds__(256) k_mha_wgrad(const float* __restrict__ dx_tok, const float* __restrict__ src,
+                                                   float* __restrict__ dw, float* __restrict__ dbias, MhaGeom g, MhaW ws,
+                                                   int cin, int cd, int Fp, int bias_mode) {
   __shared__ double sred[8];
   const int i = blockIdx.x, c = blockIdx.y, h = blockIdx.z;
-  const bool is_bias = i == cin;
   const int P = g.pd * g.ph * g.pw;
+  const bool proj_bias = bias_mode == 1 && i == cin;
+  const bool out_bias = bias_mode == 2 && h == g.H;  // extra z-slice: only c == 0 does work
+  if (out_bias && c != 0) return;
   double acc = 0.0;
-  for (int b = 0; b < g.B; ++b) {
-    const float* dx = dx_tok + (long)(b * g.H + h) * g.Tp * Fp + c * P;
-    const float* zp = z + ((long)b * cin + (is_bias ? 0 : i)) * g.M;
-    float run = 0.f;
-    int n = 0;
-    for (int m = threadIdx.x; m < g.M; m += 256) {
-      int t, po;
-      mha_locate(g, m, t, po);
-      const float d = __ldg(dx + (long)t * Fp + po);
-      run = is_bias ? run + d : fmaf(d, __ldg(zp + m), run);
-      if (++n == 32) {  // bounded fp32 runs, fp64 across them
-        acc += (double)run;
-        run = 0.f;
-        n = 0;
+  if (out_bias) {
+    for (int b = 0; b < g.B; ++b) {
+      const float* sp = src + ((long)b * cin + i) * g.M;
+      float run = 0.f;
+      int n = 0;
+      for (long m = threadIdx.x; m < g.M; m += 256) {
+        run += __ldg(sp + m);
+        if (++n == 32) {
+          acc += (double)run;
+          run = 0.f;
+          n = 0;
+        }
       }
+      acc += (double)run;
     }
-    acc += (double)run;
+  } else {
+    const int pairs = g.B * g.T;
+    for (int q = threadIdx.x; q < pairs; q += 256) {
+      const int b = q / g.T, t = q - b * g.T;
+      const MhaTok k = mha_token(g, t);
+      const float* dx = dx_tok + ((long)(b * g.H + h) * g.Tp + t) * Fp + c * P;
+      const float* sp = src + ((long)b * cin + (proj_bias ? 0 : i)) * g.M;
+      float run = 0.f;
+      if (P <= kMhaPMax) {
+        int moff[kMhaPMax];
+        mha_patch_offsets(g, k, moff);
+        float d[kMhaPMax], x[kMhaPMax];
+#pragma unroll
+        for (int po = 0; po < kMhaPMax; ++po) {  // all loads first: 2 P independent requests per pair
+          d[po] = po < P ? __ldg(dx + po) : 0.f;
+          x[po] = (po < P && !proj_bias) ? __ldg(sp + moff[po]) : 1.f;
+        }
+#pragma unroll
+        for (int po = 0; po < kMhaPMax; ++po) run = fmaf(d[po], x[po], run);
+      } else {
+        int po = 0;
+        for (int id = 0; id < g.pd; ++id)
+          for (int ih = 0; ih < g.ph; ++ih)
+            for (int iw = 0; iw < g.pw; ++iw, ++po) {
+              const float d = __ldg(dx + po);
+              if (proj_bias) {
+                run += d;
+              } else {
+                const long m = ((long)(k.td * g.pd + id) * g.Lh + k.th * g.ph + ih) * g.Lw + k.tw * g.pw + iw;
+                run = fmaf(d, __ldg(sp + m), run);
+              }
+            }
+      }
+      acc += (double)run;
+    }
   }
   acc = warp_sum_d(acc);
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
@@ -111,8 +230,9 @@ __global__ void __launch_bounds__(256) k_mha_project_bwd_w(const float* __restri
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int k = 0; k < 8; ++k) tot += sred[k];
-    if (is_bias) dbias[h * cd + c] = (float)tot;
-    else dw[((long)h * cd + c) * cin + i] = (float)tot;
+    if (out_bias) dbias[i] = (float)tot;
+    else if (proj_bias) dbias[h * cd + c] = (float)tot;
+    else dw[h * ws.sh + c * ws.sc + i * ws.si] = (float)tot;
   }
 }
 
@@ -131,74 +251,10 @@ __global__ void __launch_bounds__(256) k_mha_output_fwd(const float* __restrict_
   for (int h = 0; h < g.H; ++h) {
     const float* op = o_tok + ((long)(b * g.H + h) * g.Tp + t) * Fp + po;
     const float* wp = wout + (long)o * g.H * cd + h * cd;
+#pragma unroll 6
     for (int c = 0; c < cd; ++c) acc = fmaf(__ldg(wp + c), __ldg(op + c * P), acc);
   }
   y[((long)b * co + o) * g.M + m] = acc;
-}
-
-// dy [B][co][M] -> do_tok [B*H][Tp][Fp], do_chan [B*H][Fp][Tp] = sum_o wout[o][h cd + c] * dy[b][o][m]   (pre-zeroed)
-__global__ void __launch_bounds__(256) k_mha_output_bwd_o(const float* __restrict__ dy, const float* __restrict__ wout,
-                                                          float* __restrict__ do_tok, float* __restrict__ do_chan,
-                                                          MhaGeom g, int co, int cd, int Fp) {
-  const long idx = blockIdx.x * 256L + threadIdx.x;
-  if (idx >= g.M) return;
-  const int m = (int)idx;
-  const int bh = blockIdx.y, b = bh / g.H, h = bh % g.H;
-  int t, po;
-  mha_locate(g, m, t, po);
-  const int P = g.pd * g.ph * g.pw;
-  const float* dp = dy + (long)b * co * g.M + m;
-  float* xt = do_tok + ((long)bh * g.Tp + t) * Fp + po;
-  float* xc = do_chan + ((long)bh * Fp + po) * g.Tp + t;
-  for (int c = 0; c < cd; ++c) {
-    float acc = 0.f;
-    for (int o = 0; o < co; ++o) acc = fmaf(__ldg(wout + (long)o * g.H * cd + h * cd + c), __ldg(dp + (long)o * g.M), acc);
-    xt[c * P] = acc;
-    xc[(long)c * P * g.Tp] = acc;
-  }
-}
-
-// dwout [co][H cd] = sum_{b, m} dy[b][o][m] * o_tok[b, h][t][c P + po];  one CTA per (j = h cd + c, o);  j == H cd -> bias
-__global__ void __launch_bounds__(256) k_mha_output_bwd_w(const float* __restrict__ dy, const float* __restrict__ o_tok,
-                                                          float* __restrict__ dwout, float* __restrict__ dbias, MhaGeom g,
-                                                          int co, int cd, int Fp) {
-  __shared__ double sred[8];
-  const int j = blockIdx.x, o = blockIdx.y;
-  const bool is_bias = j == g.H * cd;
-  const int h = is_bias ? 0 : j / cd, c = is_bias ? 0 : j % cd;
-  const int P = g.pd * g.ph * g.pw;
-  double acc = 0.0;
-  for (int b = 0; b < g.B; ++b) {
-    const float* op = o_tok + (long)(b * g.H + h) * g.Tp * Fp + c * P;
-    const float* dp = dy + ((long)b * co + o) * g.M;
-    float run = 0.f;
-    int n = 0;
-    for (int m = threadIdx.x; m < g.M; m += 256) {
-      const float d = __ldg(dp + m);
-      if (is_bias) {
-        run += d;
-      } else {
-        int t, po;
-        mha_locate(g, m, t, po);
-        run = fmaf(d, __ldg(op + (long)t * Fp + po), run);
-      }
-      if (++n == 32) {
-        acc += (double)run;
-        run = 0.f;
-        n = 0;
-      }
-    }
-    acc += (double)run;
-  }
-  acc = warp_sum_d(acc);
-  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int k = 0; k < 8; ++k) tot += sred[k];
-    if (is_bias) dbias[o] = (float)tot;
-    else dwout[(long)o * g.H * cd + j] = (float)tot;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -221,11 +277,10 @@ int mha_project_forward(const float* z, const float* w, const float* bias, float
   if (make_geom(&g, B, H, Ld, Lh, Lw, pd, ph, pw, Tp)) return -1;
   HNO_CHECK(z && w && x_tok && x_chan, "mha_project_forward: null pointer");
   HNO_CHECK(Fp >= cd * pd * ph * pw && Fp % 32 == 0, "mha_project_forward: feature pitch %d too small / not a multiple of 32", Fp);
-  const size_t bytes = (size_t)B * H * Tp * Fp * sizeof(float);
-  HNO_CUDA(cudaMemsetAsync(x_tok, 0, bytes, st));
-  HNO_CUDA(cudaMemsetAsync(x_chan, 0, bytes, st));
-  dim3 grid(ceil_div(g.M, 256), B * H);
-  k_mha_project_fwd<<<grid, 256, 0, st>>>(z, w, bias, x_tok, x_chan, g, cin, cd, Fp);
+  HNO_CHECK(cd <= 65535 && cin * sizeof(float) <= 48 * 1024, "mha_project_forward: too many channels");
+  const MhaW ws{(long)cd * cin, (long)cin, 1};
+  dim3 grid(ceil_div(Tp, 256), cd, B * H);
+  k_mha_project_fwd<<<grid, 256, cin * sizeof(float), st>>>(z, w, bias, x_tok, x_chan, g, ws, cin, cd, Fp);
   HNO_LAUNCH_CHECK();
   return 0;
 }
@@ -243,8 +298,9 @@ int mha_project_backward(const float* dx_tok, const float* z, const float* w, fl
     HNO_LAUNCH_CHECK();
   }
   if (dw) {
+    const MhaW ws{(long)cd * cin, (long)cin, 1};
     dim3 grid(cin + (dbias ? 1 : 0), cd, H);
-    k_mha_project_bwd_w<<<grid, 256, 0, st>>>(dx_tok, z, dw, dbias, g, cin, cd, Fp);
+    k_mha_wgrad<<<grid, 256, 0, st>>>(dx_tok, z, dw, dbias, g, ws, cin, cd, Fp, dbias ? 1 : 0);
     HNO_LAUNCH_CHECK();
   }
   return 0;
@@ -330,14 +386,15 @@ int mha_output_backward(const float* dy, const float* o_tok, const float* wout, 
   if (make_geom(&g, B, H, Ld, Lh, Lw, pd, ph, pw, Tp)) return -1;
   HNO_CHECK(dy && o_tok && wout && do_tok && do_chan && dwout, "mha_output_backward: null pointer");
   HNO_CHECK(Fp >= cd * pd * ph * pw && Fp % 32 == 0, "mha_output_backward: bad feature pitch %d", Fp);
-  const size_t bytes = (size_t)B * H * Tp * Fp * sizeof(float);
-  HNO_CUDA(cudaMemsetAsync(do_tok, 0, bytes, st));
-  HNO_CUDA(cudaMemsetAsync(do_chan, 0, bytes, st));
-  dim3 grid(ceil_div(g.M, 256), B * H);
-  k_mha_output_bwd_o<<<grid, 256, 0, st>>>(dy, wout, do_tok, do_chan, g, co, cd, Fp);
+  HNO_CHECK(cd <= 65535 && co * sizeof(float) <= 48 * 1024, "mha_output_backward: too many channels");
+  // dO = W_out^T dy in both attention layouts: the projection kernel with the weight read transposed
+  const MhaW ws{(long)cd, 1, (long)H * cd};
+  dim3 grid(ceil_div(Tp, 256), cd, B * H);
+  k_mha_project_fwd<<<grid, 256, co * sizeof(float), st>>>(dy, wout, nullptr, do_tok, do_chan, g, ws, co, cd, Fp);
   HNO_LAUNCH_CHECK();
-  dim3 gw(H * cd + (dbias ? 1 : 0), co);
-  k_mha_output_bwd_w<<<gw, 256, 0, st>>>(dy, o_tok, dwout, dbias, g, co, cd, Fp);
+  // dW_out[o][h cd + c] = sum dy[b][o][m] O[b, h][t][f]; bias: sum of dy over the modes
+  dim3 gw(co, cd, H + (dbias ? 1 : 0));
+  k_mha_wgrad<<<gw, 256, 0, st>>>(o_tok, dy, dwout, dbias, g, ws, co, cd, Fp, dbias ? 2 : 0);
   HNO_LAUNCH_CHECK();
   return 0;
 }

@@ -181,6 +181,19 @@ __global__ void __launch_bounds__(256) k_modechain_reduce(const float* __restric
   }
 }
 
+// partials [nrows][L][n] -> dweights[l][n] (fp64 sums; used by the fused spectral core, spectral_core.cu)
+int reduce_chain_partials(const float* partials, int nrows, int L, int n, float* const* dweights, int accumulate,
+                          cudaStream_t st) {
+  McPtrs P{};
+  for (int l = 0; l < L; ++l) {
+    HNO_CHECK(dweights[l] != nullptr, "reduce_chain_partials: null weight-gradient pointer");
+    P.dw[l] = dweights[l];
+  }
+  k_modechain_reduce<<<ceil_div((long)L * n * 32, 256), 256, 0, st>>>(partials, nrows, L, n, P, accumulate);
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int modechain_supported(int C) { return C == 24 || C == 8; }
 

@@ -91,20 +91,27 @@ class XSEngine:
                 rec.map_in = (cur, enc)
             else:
                 xin = cur
-            zs = [ops.dht3_forward(xin, plan, inv_n)]
-            rec.chain = None
             nmix = len(layer.conv_blocks)
-            if shared and nmix and ops.modechain_supported(zs[0].shape[1], nmix):
-                # all n_XS mixes of the block in one launch (reference nets/hnosegxs.py:261-262)
-                rec.chain = ops.modechain_forward(zs[0], [blk.op.weight for blk in layer.conv_blocks])
-                zs += [rec.chain[j] for j in range(nmix)]
+            rec.chain = rec.zall = None
+            if shared and nmix and ops.dht3_chain_eligible(xin, plan, xin.shape[1], nmix):
+                # transform -> n_XS mixes -> inverse transform + SELU as five launches (the W stages, the recombination and
+                # the mixes in ONE kernel, csrc/spectral_core.cu)
+                u, rec.zall = ops.dht3_chain_forward(xin, plan, [blk.op.weight for blk in layer.conv_blocks], inv_n,
+                                                     epilogue=2, save=save)
+                zs = None
             else:
-                for blk in layer.conv_blocks:
-                    if shared:
-                        zs.append(ops.pwconv_forward(zs[-1], None, blk.op.weight, None, 1, True))
-                    else:
-                        zs.append(ops.hartley_conv_forward(zs[-1], blk.op.weight, True))
-            u = ops.dht3_adjoint(zs[-1], plan, 1.0, epilogue=2, pitch=pitch)  # selu(PadInverse(z))
+                zs = [ops.dht3_forward(xin, plan, inv_n)]
+                if shared and nmix and ops.modechain_supported(zs[0].shape[1], nmix):
+                    # all n_XS mixes of the block in one launch (reference nets/hnosegxs.py:261-262)
+                    rec.chain = ops.modechain_forward(zs[0], [blk.op.weight for blk in layer.conv_blocks])
+                    zs += [rec.chain[j] for j in range(nmix)]
+                else:
+                    for blk in layer.conv_blocks:
+                        if shared:
+                            zs.append(ops.pwconv_forward(zs[-1], None, blk.op.weight, None, 1, True))
+                        else:
+                            zs.append(ops.hartley_conv_forward(zs[-1], blk.op.weight, True))
+                u = ops.dht3_adjoint(zs[-1], plan, 1.0, epilogue=2, pitch=pitch)  # selu(PadInverse(z))
             if layer.conv_concat is not None:
                 y = ops.pwconv_forward(u, xin, _w2(layer.conv_concat.op), layer.conv_concat.op.bias, 1, False)
             else:
@@ -193,25 +200,31 @@ class XSEngine:
                     dxin = target
                 else:
                     dxin = dcur.clone()
-            dz = ops.dht3_forward(dt, plan, 1.0)
             g_mix = []
-            if rec.chain is not None:
+            if rec.zall is not None:
                 ws = [blk.op.weight for blk in layer.conv_blocks]
                 dws = [out_w(w)[0] for w in ws] if dst is not None else None
-                dz, g_mix = ops.modechain_backward(dz, rec.zs[0], rec.chain, ws, dweights=dws)
-                g_mix = list(g_mix)
+                # dxin += (1/N) C^T chain_bwd(C dt): the same five launches as the forward
+                g_mix = list(ops.dht3_chain_backward(dt, plan, rec.zall, ws, inv_n, dxin, epilogue=1, dweights=dws))
             else:
-                for j in reversed(range(len(layer.conv_blocks))):
-                    w = layer.conv_blocks[j].op.weight
-                    dw_, _ = out_w(w)
-                    if shared:
-                        dz, _, gw, _ = ops.pwconv_backward(dz, rec.zs[j + 1], rec.zs[j], None, w, 1, True,
-                                                           has_bias=False, dweight=dw_)
-                    else:
-                        dz, gw = ops.hartley_conv_backward(dz, rec.zs[j + 1], rec.zs[j], w, dw=dw_)
-                    g_mix.append(gw)
-                g_mix.reverse()
-            ops.dht3_adjoint(dz, plan, inv_n, epilogue=1, out=dxin)  # dxin += (1/N) C^T dz
+                dz = ops.dht3_forward(dt, plan, 1.0)
+                if rec.chain is not None:
+                    ws = [blk.op.weight for blk in layer.conv_blocks]
+                    dws = [out_w(w)[0] for w in ws] if dst is not None else None
+                    dz, g_mix = ops.modechain_backward(dz, rec.zs[0], rec.chain, ws, dweights=dws)
+                    g_mix = list(g_mix)
+                else:
+                    for j in reversed(range(len(layer.conv_blocks))):
+                        w = layer.conv_blocks[j].op.weight
+                        dw_, _ = out_w(w)
+                        if shared:
+                            dz, _, gw, _ = ops.pwconv_backward(dz, rec.zs[j + 1], rec.zs[j], None, w, 1, True,
+                                                               has_bias=False, dweight=dw_)
+                        else:
+                            dz, gw = ops.hartley_conv_backward(dz, rec.zs[j + 1], rec.zs[j], w, dw=dw_)
+                        g_mix.append(gw)
+                    g_mix.reverse()
+                ops.dht3_adjoint(dz, plan, inv_n, epilogue=1, out=dxin)  # dxin += (1/N) C^T dz
             if has_map:
                 prev, enc = rec.map_in
                 op = layer.mapping_conv.op

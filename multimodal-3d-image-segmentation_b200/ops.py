@@ -80,6 +80,49 @@ def dht3_adjoint(z, plan, scale, epilogue=0, out=None, pitch=None):
     return out
 
 
+def dht3_chain_eligible(x, plan, C, L):
+    """The fused 'DHT -> shared-weight mixes -> inverse DHT' call applies (planar 16-byte aligned activations, 8 / 24 channels,
+    grids the tensor-core H stage handles)."""
+    nslab, D, pitch = _geom(x)
+    return bool(_lib.load().hno_dht3_chain_eligible(plan.host.data_ptr(), ptr(x), pitch, D * pitch, x.shape[0], int(C),
+                                                    int(L)))
+
+
+def dht3_chain_forward(x, plan, weights, scale_in, epilogue=2, save=True, out=None):
+    """out = EPI(C^T chain(scale_in C x)) for one HNO-XS block (reference nets/hnosegxs.py:260-268).  Returns (out, z_all):
+    z_all (L + 1, B, C, Ld, Lh, Lw) holds z_0 .. z_L for the backward (None when save is False)."""
+    _require_cuda(x, 'x')
+    assert x.is_contiguous() and x.ndim == 4
+    B, C = x.shape[:2]
+    nslab, D, pitch = _geom(x)
+    ws_ = [w.contiguous() for w in weights]
+    L = len(ws_)
+    z_all = torch.empty((L + 1, B, C) + plan.modes_shape, dtype=torch.float32, device=x.device) if save else None
+    if out is None:
+        assert epilogue in (0, 2)
+        out = torch.empty_like(x)
+    ws = workspace(plan.workspace_bytes(pitch, nslab), x.device, 'dht')
+    call('hno_dht3_chain_forward', plan.host.data_ptr(), plan.dev.data_ptr(), ptr(x), ptr(out), pitch, D * pitch,
+         _ptr_array(ws_), ptr(z_all), ptr(ws), B, C, L, float(scale_in), int(epilogue), stream_ptr())
+    return out, z_all
+
+
+def dht3_chain_backward(dt, plan, z_all, weights, scale_out, out, epilogue=1, dweights=None, accumulate=False):
+    """out (+)= scale_out C^T chain_bwd(C dt); returns [dW_1 .. dW_L] (written into `dweights` when given)."""
+    B, C = dt.shape[:2]
+    nslab, D, pitch = _geom(dt)
+    ws_ = [w.contiguous() for w in weights]
+    L = len(ws_)
+    if dweights is None:
+        dweights = [torch.empty_like(w) for w in ws_]
+    ws = workspace(plan.workspace_bytes(pitch, nslab), dt.device, 'dht')
+    part = workspace(_lib.load().hno_dht3_chain_partials_bytes(plan.host.data_ptr(), C, L, B), dt.device, 'mc')
+    call('hno_dht3_chain_backward', plan.host.data_ptr(), plan.dev.data_ptr(), ptr(dt.contiguous()), ptr(out), pitch,
+         D * pitch, _ptr_array(ws_), _ptr_array(dweights), ptr(z_all), ptr(ws), ptr(part), B, C, L, float(scale_out),
+         int(epilogue), int(bool(accumulate)), stream_ptr())
+    return dweights
+
+
 class TruncatedDHT(torch.autograd.Function):
     """TransformCrop: z = (1/N) C x; backward dx = (1/N) C^T dz."""
 

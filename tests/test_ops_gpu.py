@@ -485,3 +485,47 @@ def test_normalize_modalities(cuda, golden_dir):
     for i in range(2):
         assert np.abs(out[i].cpu().numpy() - orc.normalize_modalities(batch[i].cpu().numpy(), mask_val=0)).max() < 2e-5
     del y16
+
+
+@pytest.mark.parametrize('grid,modes', [((25, 33, 32), (10, 14, 14)), ((24, 40, 28), (12, 14, 14)), ((121, 121, 78), (10, 14, 14))])
+def test_fused_spectral_chain_matches_separate_kernels(cuda, grid, modes):
+    """hno_dht3_chain_forward / _backward (transform -> n_XS shared-weight mixes -> inverse transform with the W stages, the cas
+    recombination and the mixes in ONE kernel, csrc/spectral_core.cu) against the separate launches it replaces
+    (hno_dht3_forward -> hno_modechain_* -> hno_dht3_adjoint), incl. a grid whose retained sets contain the Nyquist frequency
+    (n == 2m: sine rows vanish) and the BASELINE grid."""
+    from multimodal_3d_image_segmentation_b200 import ops
+    from multimodal_3d_image_segmentation_b200.plan import get_crop_plan, plane_pitch
+    D, H, W = grid
+    P = plane_pitch(H, W)
+    B, C, L = 2, 24, 3
+    plan = get_crop_plan(grid, modes, cuda)
+    g = torch.Generator(device=cuda).manual_seed(12)
+    x = torch.randn(B, C, D, P, device=cuda, generator=g)
+    x.view(B, C, D, P)[..., H * W:] = 0
+    ws = [torch.randn(C, C, device=cuda, generator=g) * 0.2 for _ in range(L)]
+    inv_n = 1.0 / plan.n_voxels
+    assert ops.dht3_chain_eligible(x, plan, C, L)
+    # forward
+    z0 = ops.dht3_forward(x, plan, inv_n)
+    zs = ops.modechain_forward(z0, ws)
+    u_ref = ops.dht3_adjoint(zs[-1], plan, 1.0, epilogue=2, pitch=P)
+    u, zall = ops.dht3_chain_forward(x, plan, ws, inv_n, epilogue=2, save=True)
+    valid = torch.zeros(P, dtype=torch.bool, device=cuda)
+    valid[:H * W] = True
+    assert rel(zall[0], z0) < 2e-6, rel(zall[0], z0)
+    for l in range(L):
+        assert rel(zall[l + 1], zs[l]) < 5e-6, (l, rel(zall[l + 1], zs[l]))
+    assert rel(u[..., valid], u_ref[..., valid]) < 5e-6, rel(u[..., valid], u_ref[..., valid])
+    # backward: dxin += (1/N) C^T chain_bwd(C dt)
+    dt = torch.randn(B, C, D, P, device=cuda, generator=g)
+    dt[..., H * W:] = 0
+    base = torch.randn(B, C, D, P, device=cuda, generator=g)
+    dz = ops.dht3_forward(dt, plan, 1.0)
+    dz0, dws_ref = ops.modechain_backward(dz, z0, zs, ws)
+    ref = base.clone()
+    ops.dht3_adjoint(dz0, plan, inv_n, epilogue=1, out=ref)
+    out = base.clone()
+    dws = ops.dht3_chain_backward(dt, plan, zall, ws, inv_n, out, epilogue=1)
+    assert rel(out[..., valid], ref[..., valid]) < 5e-6, rel(out[..., valid], ref[..., valid])
+    for l in range(L):
+        assert rel(dws[l], dws_ref[l]) < 2e-5, (l, rel(dws[l], dws_ref[l]))

@@ -39,6 +39,19 @@ def mha_bwd():
     ops.hartley_attention_backward(_mha['y'], _mha['S'])
 
 win = rnd(F, 4, 2, 2, 2) * 0.1
+wch = [w24, w24 * 0.5, w24 * 0.25]
+_ch = {}
+
+
+def chain_fwd():
+    _ch['u'], _ch['z'] = ops.dht3_chain_forward(a[0], plan, wch, 1.0 / plan.n_voxels, epilogue=2, save=True)
+
+
+def chain_bwd():
+    if 'z' not in _ch:
+        chain_fwd()
+    ops.dht3_chain_backward(a[2], plan, _ch['z'], wch, 1.0 / plan.n_voxels, a[3], epilogue=1)
+
 table = {
     'stemf': lambda: ops.stem_forward(xin, win, b24, P),
     'stemb': lambda: ops.stem_backward(a[0], xin, F, P),
@@ -49,6 +62,8 @@ table = {
     'dhta': lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=1, out=a[1]),
     'pw48b': lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, in1_is_selu=True),
     'pw48ba': lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, din1=acc[0], din2=acc[1]),
+    'chainf': chain_fwd,
+    'chainb': chain_bwd,
     'mhaf': mha_fwd,
     'mhab': mha_bwd,
     'pw24b': lambda: ops.pwconv_backward(a[0], a[1], a[2], None, w24, 1, False, hw=hw, in1_is_selu=True),
