@@ -398,6 +398,335 @@ __global__ void __launch_bounds__(kBtThreads, 2) k_pwconv_bwd_tc(const BtDev p, 
   if (warp == 4) tmem_dealloc(tmem, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------ role-split variant
+// Same tile, ring and arithmetic as k_pwconv_bwd_tc, but the per-voxel work (d(pre), TMEM staging, input-gradient epilogue)
+// and the weight gradient run on DIFFERENT warps: in the kernel above 128 threads do both one after the other, so an SM holds
+// 8 compute warps that are each inside one latency-bound phase (ncu: 18 % warps active, issue 44 %, DRAM 64 %).  Here a CTA
+// has 4 voxel warps + 4 weight-gradient warps; d(pre) is double buffered in shared memory and in tensor memory, so the voxel
+// warps form d(pre) of tile t+1 while the tensor core works on tile t and the weight-gradient warps are anywhere inside tile
+// t or t-1.  Every ring stage is released by both groups (256 arrivals).
+constexpr int kB2Threads = 320;  // warps 0-3 voxel, 4 MMA issuer, 5 loader, 6-9 weight gradient
+
+struct B2Cursor {
+  int s;
+  uint32_t ph;
+  __device__ __forceinline__ void advance(int n, int nst) {
+    s += n;
+    if (s >= nst) {
+      s -= nst;
+      ph ^= 1;
+    }
+  }
+  __device__ __forceinline__ B2Cursor plus(int n, int nst) const {
+    B2Cursor c = *this;
+    c.advance(n, nst);
+    return c;
+  }
+};
+
+template <int CI2, bool ACC>
+__global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev p, const __grid_constant__ BtMaps maps) {
+  constexpr int C = kBtC;
+  constexpr int CI = C + CI2;
+  constexpr int NP = CI == 48 ? 48 : 32;
+  constexpr int NB = 2 * NP;
+  constexpr int NSRC = CI2 > 0 ? 4 : 3;
+  constexpr uint32_t kIdesc1 = make_idesc_tf32(128, NB, 0, 0);
+  constexpr uint32_t kIdesc2 = make_idesc_tf32(128, NP, 0, 0);
+  constexpr uint32_t kACol = 0, kDCol = 4 * C;  // TMEM: two A buffers of [hi 24 | lo 24], accumulator [96, 96 + NB)
+  constexpr uint32_t kTmemCols = 256;
+  constexpr int PSTRIDE = C * CI + C;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int NST = p.nst;
+  float* ring = reinterpret_cast<float*>(smem);            // [NST][24][132]
+  float* sdp = ring + NST * kBtStageFloats;                 // [2][24][132]   d(pre) of tiles t, t+1 (end: reduction scratch)
+  float* bimg = sdp + 2 * kBtStageFloats;                   // [NB rows][24 k]
+  float* sbias = bimg + NB * C;                             // [4][24]
+  __shared__ __align__(8) uint64_t bar_full[kBtMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kBtMaxStages];  // 256 arrivals: voxel + weight-gradient warps
+  __shared__ __align__(8) uint64_t bar_ready;                // d(pre) of the tile is in tensor memory (128)
+  __shared__ __align__(8) uint64_t bar_dfree;                // the accumulator has been read back        (128)
+  __shared__ __align__(8) uint64_t bar_accfull;              // tcgen05.commit
+  __shared__ __align__(8) uint64_t bar_sdpfull[2];           // d(pre) tile written to shared memory      (128, voxel warps)
+  __shared__ __align__(8) uint64_t bar_sdpempty[2];          // ... and consumed                          (128, wgrad warps)
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int idx = tid; idx < NP * C; idx += kB2Threads) {
+    const int n = idx / C, k = idx - n * C;
+    const float v = n < CI ? __ldg(p.w + k * CI + n) : 0.f;
+    const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    bimg[kmajor_plain_index<NB>(n, k)] = hi;
+    bimg[kmajor_plain_index<NB>(NP + n, k)] = v - hi;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kBtMaxStages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 256);
+    }
+    mbar_init(&bar_ready, 128);
+    mbar_init(&bar_dfree, 128);
+    mbar_init(&bar_accfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_sdpfull[i], 128);
+      mbar_init(&bar_sdpempty[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(&tmem_slot, kTmemCols);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 4) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t b0 = smem_u32(bimg);
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        mbar_wait(&bar_ready, (uint32_t)(ti & 1));
+        if (ti > 0) mbar_wait(&bar_dfree, (uint32_t)((ti - 1) & 1));
+        tc_fence_after_sync();
+        const uint32_t acol = tmem + kACol + (uint32_t)(ti & 1) * 2 * C;
+#pragma unroll
+        for (int g = 0; g < C / 8; ++g) {
+          const uint64_t db = make_smem_desc(b0 + g * (NB / 8) * 256, kPlainLbo, kPlainSbo, kLayoutNone);
+          bt_mma(tmem + kDCol, acol + 8 * g, db, kIdesc1, g != 0);
+          bt_mma(tmem + kDCol, acol + C + 8 * g, db, kIdesc2, true);
+        }
+        mma_commit(&bar_accfull);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // =============================================================== loader: one bulk tensor copy per stage
+    if (lane == 0) {
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int q = 0; q < NSRC; ++q) tma_prefetch_desc(&maps.m[q]);
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const long tile = blockIdx.x + (long)ti * gridDim.x;
+        const int b = (int)(tile / p.tiles_per_sample);
+        const int s0 = (int)((tile - (long)b * p.tiles_per_sample) * 128);
+#pragma unroll 1
+        for (int q = 0; q < NSRC; ++q) {
+          if (it >= NST) mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_expect_tx(&bar_full[s], kBtStageFloats * 4);
+          tma_load_3d(ring + s * kBtStageFloats, &maps.m[q], s0, 0, b, &bar_full[s]);
+          ++it;
+          if (++s == NST) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // =============================================================== voxel warps: one thread = one voxel = one TMEM lane
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    float2 accB2[C / 2];
+#pragma unroll
+    for (int o = 0; o < C / 2; ++o) accB2[o] = make_float2(0.f, 0.f);
+
+    auto voxel_of = [&](int ti, int& b, long& sv) {
+      const long tile = blockIdx.x + (long)ti * gridDim.x;
+      b = (int)(tile / p.tiles_per_sample);
+      sv = (tile - (long)b * p.tiles_per_sample) * 128 + tid;
+    };
+    // d(pre) of tile ti: registers -> tensor memory (two TF32 terms) and shared memory (fp32)
+    auto dpre = [&](int ti, B2Cursor cur) {
+      int b;
+      long sv;
+      voxel_of(ti, b, sv);
+      const bool live = sv < p.S && (sv % p.P) < p.HW;
+      const int buf = ti & 1;
+      if (ti >= 2) mbar_wait(&bar_sdpempty[buf], (uint32_t)(((ti >> 1) - 1) & 1));
+      const B2Cursor cy = cur.plus(1, NST);
+      mbar_wait(&bar_full[cur.s], cur.ph);
+      mbar_wait(&bar_full[cy.s], cy.ph);
+      const float* pdy = ring + cur.s * kBtStageFloats + tid;
+      const float* py = ring + cy.s * kBtStageFloats + tid;
+      float* ps = sdp + buf * kBtStageFloats + tid;
+      const uint32_t acol = lane_base + kACol + (uint32_t)buf * 2 * C;
+#pragma unroll
+      for (int o0 = 0; o0 < C; o0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const int o = o0 + j;
+          const float d0 = live ? pdy[o * kBtPitch] * selu_grad_from_out(py[o * kBtPitch]) : 0.f;
+          const float d1 = live ? pdy[(o + 1) * kBtPitch] * selu_grad_from_out(py[(o + 1) * kBtPitch]) : 0.f;
+          hi[j] = __float_as_uint(d0);
+          lo[j] = __float_as_uint(tf32_lo(d0));
+          hi[j + 1] = __float_as_uint(d1);
+          lo[j + 1] = __float_as_uint(tf32_lo(d1));
+          ps[o * kBtPitch] = d0;
+          ps[(o + 1) * kBtPitch] = d1;
+          accB2[o / 2] = __fadd2_rn(accB2[o / 2], make_float2(d0, d1));
+        }
+        bt_st8(acol + o0, hi);
+        bt_st8(acol + C + o0, lo);
+      }
+      bt_arrive(&bar_empty[cur.s]);
+      bt_arrive(&bar_empty[cy.s]);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before_sync();
+      bt_arrive(&bar_ready);
+      bt_arrive(&bar_sdpfull[buf]);
+    };
+
+    B2Cursor cur{0, 0};  // first stage (dy) of the tile whose epilogue runs next
+    if (my_tiles > 0) dpre(0, cur);
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      if (ti + 1 < my_tiles) dpre(ti + 1, cur.plus(NSRC, NST));
+      // ---- epilogue of tile ti
+      int b;
+      long sv;
+      voxel_of(ti, b, sv);
+      const bool valid = sv < p.S;
+      const B2Cursor c1 = cur.plus(2, NST);
+      const long off = (long)b * C * p.S + sv;
+      float oldv[3][8];
+      auto fetch_old = [&](int i0, float (&o)[8]) {
+        float* dst = (i0 < C ? p.din1 : p.din2);
+        const bool accumulate = i0 < C ? (p.flags & 1) : (p.flags & 2);
+        if (dst != nullptr && valid && accumulate) {
+          const float* q = dst + off + (long)(i0 < C ? i0 : i0 - C) * p.S;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = __ldcs(q + (long)j * p.S);
+        }
+      };
+      if (ACC) {
+        fetch_old(0, oldv[0]);
+        if (CI > 8) fetch_old(8, oldv[1]);
+      }
+      if (p.flags & 4) mbar_wait(&bar_full[c1.s], c1.ph);
+      mbar_wait(&bar_accfull, (uint32_t)(ti & 1));
+      tc_fence_after_sync();
+      {
+        const uint32_t acc = lane_base + kDCol;
+        const float* pin1 = ring + c1.s * kBtStageFloats + tid;
+#pragma unroll
+        for (int i0 = 0; i0 < CI; i0 += 8) {
+          if (ACC && i0 + 16 < CI) fetch_old(i0 + 16, oldv[(i0 / 8 + 2) % 3]);
+          float a[8], c[8];
+          bt_ld8(acc + i0, a);
+          bt_ld8(acc + NP + i0, c);
+          if (i0 + 8 >= CI) {  // the accumulator is in registers: the next tile's MMAs may overwrite it
+            tc_fence_before_sync();
+            bt_arrive(&bar_dfree);
+          }
+          float* dst = (i0 < C ? p.din1 : p.din2);
+          const bool accumulate = i0 < C ? (p.flags & 1) : (p.flags & 2);
+          if (dst != nullptr && valid) {
+            float* q = dst + off + (long)(i0 < C ? i0 : i0 - C) * p.S;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = a[j] + c[j];
+              if (i0 < C && (p.flags & 4)) v *= selu_grad_from_out(pin1[(i0 + j) * kBtPitch]);
+              if (ACC && accumulate) v += oldv[(i0 / 8) % 3][j];
+              q[(long)j * p.S] = v;
+            }
+          }
+        }
+      }
+      bt_arrive(&bar_empty[c1.s]);
+      if (CI2 > 0) bt_arrive(&bar_empty[c1.plus(1, NST).s]);
+      cur.advance(NSRC, NST);
+    }
+    // ---- bias partials: warp sums, one row of C per voxel warp
+#pragma unroll
+    for (int o = 0; o < C / 2; ++o) {
+      const float bx = warp_sum(accB2[o].x), by = warp_sum(accB2[o].y);
+      if (lane == 0) {
+        sbias[warp * C + 2 * o] = bx;
+        sbias[warp * C + 2 * o + 1] = by;
+      }
+    }
+    bt_worker_sync();
+    float* prow = p.partials + (long)blockIdx.x * PSTRIDE;
+    for (int o = tid; o < C; o += 128)
+      prow[C * CI + o] = (sbias[o] + sbias[C + o]) + (sbias[2 * C + o] + sbias[3 * C + o]);
+  } else {
+    // =============================================================== weight-gradient warps
+    const int gt = tid - 192;
+    const int wg = gt >> 6, wl = gt & 63;
+    const int ot = wl >> 3, it8 = wl & 7;
+    float2 accW[2][3][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) accW[h][q][r] = make_float2(0.f, 0.f);
+
+    auto wgrad = [&](const float* sd, const float* sx, float2 (&acc)[3][3]) {
+      const float* dp0 = sd + (ot * 3) * kBtPitch + wg * 64;
+      const float* x0 = sx + (it8 * 3) * kBtPitch + wg * 64;
+#pragma unroll 2
+      for (int v = 0; v < 64; v += 4) {
+        float4 d[3], x[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) d[q] = *reinterpret_cast<const float4*>(dp0 + q * kBtPitch + v);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) x[r] = *reinterpret_cast<const float4*>(x0 + r * kBtPitch + v);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            float2 a = acc[q][r];
+            a = ffma2(make_float2(d[q].x, d[q].y), make_float2(x[r].x, x[r].y), a);
+            a = ffma2(make_float2(d[q].z, d[q].w), make_float2(x[r].z, x[r].w), a);
+            acc[q][r] = a;
+          }
+      }
+    };
+
+    B2Cursor cur{0, 0};
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int buf = ti & 1;
+      const float* sd = sdp + buf * kBtStageFloats;
+      mbar_wait(&bar_sdpfull[buf], (uint32_t)((ti >> 1) & 1));
+      // dy and y were consumed by the voxel warps before they signalled: release this group's share
+      bt_arrive(&bar_empty[cur.s]);
+      bt_arrive(&bar_empty[cur.plus(1, NST).s]);
+      const B2Cursor c1 = cur.plus(2, NST);
+      mbar_wait(&bar_full[c1.s], c1.ph);
+      wgrad(sd, ring + c1.s * kBtStageFloats, accW[0]);
+      bt_arrive(&bar_empty[c1.s]);
+      if (CI2 > 0) {
+        const B2Cursor c2 = c1.plus(1, NST);
+        mbar_wait(&bar_full[c2.s], c2.ph);
+        wgrad(sd, ring + c2.s * kBtStageFloats, accW[1]);
+        bt_arrive(&bar_empty[c2.s]);
+      }
+      bt_arrive(&bar_sdpempty[buf]);
+      cur.advance(NSRC, NST);
+    }
+    // ---- per-CTA partial sums; the d(pre) buffers are free (their last reader is this group)
+    float* scratch = sdp;
+    float* prow = p.partials + (long)blockIdx.x * PSTRIDE;
+    asm volatile("bar.sync 2, 128;" ::: "memory");  // every warp of the group has read its last d(pre) tile
+#pragma unroll
+    for (int h = 0; h < (CI2 > 0 ? 2 : 1); ++h)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          scratch[wg * (C * CI) + (ot * 3 + q) * CI + h * C + it8 * 3 + r] = accW[h][q][r].x + accW[h][q][r].y;
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    for (int idx = gt; idx < C * CI; idx += 128) prow[idx] = scratch[idx] + scratch[C * CI + idx];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 bool pwconv_bwd_tc_eligible(const float* dy, const float* y, const float* in1, const float* in2, const float* din1,
                             const float* din2, int ci1, int ci2, int co, long S, int act, int residual) {
@@ -416,7 +745,10 @@ template <int CI2, bool ACC>
 static int launch_bt(BtDev p, cudaStream_t st, int* grid_out) {
   constexpr int CI = kBtC + CI2;
   constexpr int NB = 2 * (CI == 48 ? 48 : 32);
-  const size_t fixed = 1024 + (size_t)(kBtStageFloats + NB * kBtC + 2 * kBtC * CI + 2 * kBtC + 64) * sizeof(float);
+  // HNO_PWBWD_SPLIT=0: the single-role kernel (128 workers do the per-voxel work and the weight gradient in turn)
+  static const bool split = !(getenv("HNO_PWBWD_SPLIT") && atoi(getenv("HNO_PWBWD_SPLIT")) == 0);
+  const size_t fixed = split ? 1024 + (size_t)(2 * kBtStageFloats + NB * kBtC + 4 * kBtC + 64) * sizeof(float)
+                             : 1024 + (size_t)(kBtStageFloats + NB * kBtC + 2 * kBtC * CI + 2 * kBtC + 64) * sizeof(float);
   int nst = (int)((233472 / 2 - 2 * 1024 - fixed) / (kBtStageFloats * sizeof(float)));
   static const int nst_env = getenv("HNO_PWBWD_NST") ? atoi(getenv("HNO_PWBWD_NST")) : 0;
   if (nst_env > 0) nst = nst_env;
@@ -424,8 +756,6 @@ static int launch_bt(BtDev p, cudaStream_t st, int* grid_out) {
   HNO_CHECK(nst >= 5, "pwconv_bwd_tc: not enough shared memory for the ring");
   p.nst = nst;
   const size_t smem = fixed + (size_t)nst * kBtStageFloats * sizeof(float);
-  auto kern = k_pwconv_bwd_tc<CI2, ACC>;
-  HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long grid = (long)sm_count() * 2;  // two CTAs per SM (256 TMEM columns and ~100 KB of shared memory each)
   if (grid > p.total_tiles) grid = p.total_tiles;
   *grid_out = (int)grid;
@@ -443,7 +773,16 @@ static int launch_bt(BtDev p, cudaStream_t st, int* grid_out) {
         if (int rc = encode_tensor_map(&maps.m[q], src[q], 3, dims, strides, box, 0)) return rc;
     }
   }
-  kern<<<(int)grid, kBtThreads, smem, st>>>(p, maps);
+  if (split && p.tma) {
+    auto kern = k_pwconv_bwd_split<CI2, ACC>;
+    HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(int)grid, kB2Threads, smem, st>>>(p, maps);
+  } else {
+    HNO_CHECK(!split, "pwconv_bwd_tc: the role-split kernel needs the TMA ring (HNO_PWBWD_TMA=0 requires HNO_PWBWD_SPLIT=0)");
+    auto kern = k_pwconv_bwd_tc<CI2, ACC>;
+    HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(int)grid, kBtThreads, smem, st>>>(p, maps);
+  }
   HNO_LAUNCH_CHECK();
   return 0;
 }
