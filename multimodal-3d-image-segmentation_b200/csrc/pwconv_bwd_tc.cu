@@ -440,16 +440,15 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int NST = p.nst;
   float* ring = reinterpret_cast<float*>(smem);            // [NST][24][132]
-  float* sdp = ring + NST * kBtStageFloats;                 // [2][24][132]   d(pre) of tiles t, t+1 (end: reduction scratch)
-  float* bimg = sdp + 2 * kBtStageFloats;                   // [NB rows][24 k]
+  float* bimg = ring + NST * kBtStageFloats;                // [NB rows][24 k]
   float* sbias = bimg + NB * C;                             // [4][24]
   __shared__ __align__(8) uint64_t bar_full[kBtMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kBtMaxStages];  // 256 arrivals: voxel + weight-gradient warps
   __shared__ __align__(8) uint64_t bar_ready;                // d(pre) of the tile is in tensor memory (128)
   __shared__ __align__(8) uint64_t bar_dfree;                // the accumulator has been read back        (128)
   __shared__ __align__(8) uint64_t bar_accfull;              // tcgen05.commit
-  __shared__ __align__(8) uint64_t bar_sdpfull[2];           // d(pre) tile written to shared memory      (128, voxel warps)
-  __shared__ __align__(8) uint64_t bar_sdpempty[2];          // ... and consumed                          (128, wgrad warps)
+  __shared__ __align__(8) uint64_t bar_sdpfull[4];           // d(pre) written over the dy stage of tile t (128, voxel warps);
+                                                             // the ring bounds the voxel warps' lead to < 3 tiles
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -469,10 +468,7 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
     mbar_init(&bar_ready, 128);
     mbar_init(&bar_dfree, 128);
     mbar_init(&bar_accfull, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_sdpfull[i], 128);
-      mbar_init(&bar_sdpempty[i], 128);
-    }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_sdpfull[i], 128);
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(&tmem_slot, kTmemCols);
@@ -514,7 +510,10 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
         const int s0 = (int)((tile - (long)b * p.tiles_per_sample) * 128);
 #pragma unroll 1
         for (int q = 0; q < NSRC; ++q) {
-          if (it >= NST) mbar_wait(&bar_empty[s], ph ^ 1);
+          if (it >= NST) {
+            mbar_wait(&bar_empty[s], ph ^ 1);
+            fence_proxy_async_smem();  // dy stages are rewritten in place (generic proxy) before the next bulk copy lands
+          }
           mbar_expect_tx(&bar_full[s], kBtStageFloats * 4);
           tma_load_3d(ring + s * kBtStageFloats, &maps.m[q], s0, 0, b, &bar_full[s]);
           ++it;
@@ -538,20 +537,21 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
       b = (int)(tile / p.tiles_per_sample);
       sv = (tile - (long)b * p.tiles_per_sample) * 128 + tid;
     };
-    // d(pre) of tile ti: registers -> tensor memory (two TF32 terms) and shared memory (fp32)
+    // d(pre) of tile ti: registers -> tensor memory (two TF32 terms) and, in fp32, over the dy stage it came from (a thread
+    // owns its voxel's column, so the overwrite is race free; a separate d(pre) buffer cost two ring stages and the kernel
+    // is sensitive to the ring depth: 0.266 ms with 6 stages, 0.301 ms with 5)
     auto dpre = [&](int ti, B2Cursor cur) {
       int b;
       long sv;
       voxel_of(ti, b, sv);
       const bool live = sv < p.S && (sv % p.P) < p.HW;
       const int buf = ti & 1;
-      if (ti >= 2) mbar_wait(&bar_sdpempty[buf], (uint32_t)(((ti >> 1) - 1) & 1));
       const B2Cursor cy = cur.plus(1, NST);
       mbar_wait(&bar_full[cur.s], cur.ph);
       mbar_wait(&bar_full[cy.s], cy.ph);
       const float* pdy = ring + cur.s * kBtStageFloats + tid;
       const float* py = ring + cy.s * kBtStageFloats + tid;
-      float* ps = sdp + buf * kBtStageFloats + tid;
+      float* ps = ring + cur.s * kBtStageFloats + tid;
       const uint32_t acol = lane_base + kACol + (uint32_t)buf * 2 * C;
 #pragma unroll
       for (int o0 = 0; o0 < C; o0 += 8) {
@@ -572,12 +572,13 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
         bt_st8(acol + o0, hi);
         bt_st8(acol + C + o0, lo);
       }
+      fence_proxy_async_smem();
       bt_arrive(&bar_empty[cur.s]);
       bt_arrive(&bar_empty[cy.s]);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before_sync();
       bt_arrive(&bar_ready);
-      bt_arrive(&bar_sdpfull[buf]);
+      bt_arrive(&bar_sdpfull[ti & 3]);
     };
 
     B2Cursor cur{0, 0};  // first stage (dy) of the tile whose epilogue runs next
@@ -687,29 +688,58 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
       }
     };
 
+    // two sources: one pass over the voxels feeds both weight-gradient halves, so the d(pre) rows are read once (the loop is
+    // bound by shared-memory wavefronts -- ncu: LSU data pipe 84 % with separate passes -- and this removes a quarter of them)
+    auto wgrad2 = [&](const float* sd, const float* sx1, const float* sx2) {
+      const float* dp0 = sd + (ot * 3) * kBtPitch + wg * 64;
+      const float* x1 = sx1 + (it8 * 3) * kBtPitch + wg * 64;
+      const float* x2 = sx2 + (it8 * 3) * kBtPitch + wg * 64;
+#pragma unroll 2
+      for (int v = 0; v < 64; v += 4) {
+        float4 d[3], x[6];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) d[q] = *reinterpret_cast<const float4*>(dp0 + q * kBtPitch + v);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          x[r] = *reinterpret_cast<const float4*>(x1 + r * kBtPitch + v);
+          x[3 + r] = *reinterpret_cast<const float4*>(x2 + r * kBtPitch + v);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            float2 a = accW[r / 3][q][r % 3];
+            a = ffma2(make_float2(d[q].x, d[q].y), make_float2(x[r].x, x[r].y), a);
+            a = ffma2(make_float2(d[q].z, d[q].w), make_float2(x[r].z, x[r].w), a);
+            accW[r / 3][q][r % 3] = a;
+          }
+      }
+    };
+
     B2Cursor cur{0, 0};
+    int last_dy = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int buf = ti & 1;
-      const float* sd = sdp + buf * kBtStageFloats;
-      mbar_wait(&bar_sdpfull[buf], (uint32_t)((ti >> 1) & 1));
-      // dy and y were consumed by the voxel warps before they signalled: release this group's share
-      bt_arrive(&bar_empty[cur.s]);
-      bt_arrive(&bar_empty[cur.plus(1, NST).s]);
+      const float* sd = ring + cur.s * kBtStageFloats;  // d(pre), written over dy by the voxel warps
+      mbar_wait(&bar_sdpfull[ti & 3], (uint32_t)((ti >> 2) & 1));
+      bt_arrive(&bar_empty[cur.plus(1, NST).s]);  // y was consumed by the voxel warps before they signalled
       const B2Cursor c1 = cur.plus(2, NST);
       mbar_wait(&bar_full[c1.s], c1.ph);
-      wgrad(sd, ring + c1.s * kBtStageFloats, accW[0]);
-      bt_arrive(&bar_empty[c1.s]);
       if (CI2 > 0) {
         const B2Cursor c2 = c1.plus(1, NST);
         mbar_wait(&bar_full[c2.s], c2.ph);
-        wgrad(sd, ring + c2.s * kBtStageFloats, accW[1]);
+        wgrad2(sd, ring + c1.s * kBtStageFloats, ring + c2.s * kBtStageFloats);
+        bt_arrive(&bar_empty[c1.s]);
         bt_arrive(&bar_empty[c2.s]);
+      } else {
+        wgrad(sd, ring + c1.s * kBtStageFloats, accW[0]);
+        bt_arrive(&bar_empty[c1.s]);
       }
-      bt_arrive(&bar_sdpempty[buf]);
+      if (ti + 1 < my_tiles) bt_arrive(&bar_empty[cur.s]);  // the last tile's stage becomes the reduction scratch
+      last_dy = cur.s;
       cur.advance(NSRC, NST);
     }
-    // ---- per-CTA partial sums; the d(pre) buffers are free (their last reader is this group)
-    float* scratch = sdp;
+    // ---- per-CTA partial sums; the last d(pre) stage is free once every warp of this group has read it
+    float* scratch = ring + last_dy * kBtStageFloats;
     float* prow = p.partials + (long)blockIdx.x * PSTRIDE;
     asm volatile("bar.sync 2, 128;" ::: "memory");  // every warp of the group has read its last d(pre) tile
 #pragma unroll
@@ -747,7 +777,7 @@ static int launch_bt(BtDev p, cudaStream_t st, int* grid_out) {
   constexpr int NB = 2 * (CI == 48 ? 48 : 32);
   // HNO_PWBWD_SPLIT=0: the single-role kernel (128 workers do the per-voxel work and the weight gradient in turn)
   static const bool split = !(getenv("HNO_PWBWD_SPLIT") && atoi(getenv("HNO_PWBWD_SPLIT")) == 0);
-  const size_t fixed = split ? 1024 + (size_t)(2 * kBtStageFloats + NB * kBtC + 4 * kBtC + 64) * sizeof(float)
+  const size_t fixed = split ? 1024 + (size_t)(NB * kBtC + 4 * kBtC + 64) * sizeof(float)
                              : 1024 + (size_t)(kBtStageFloats + NB * kBtC + 2 * kBtC * CI + 2 * kBtC + 64) * sizeof(float);
   int nst = (int)((233472 / 2 - 2 * 1024 - fixed) / (kBtStageFloats * sizeof(float)));
   static const int nst_env = getenv("HNO_PWBWD_NST") ? atoi(getenv("HNO_PWBWD_NST")) : 0;
