@@ -528,12 +528,18 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
           float* so = stage + sb * (32 * 128) + (quarter * 32 + lane);
           if (tile_live && !has_bias) {  // the common block: no predicates at all (rows >= nout are zeros of the
                                          // padded B image and are clipped by the bulk store)
+            // the activation test stays OUTSIDE the unrolled loop: with a (uniform) branch per pair the 16 SELU chains of a
+            // block ran one after the other (cycle counters: 51 cycles per pair, 6,600 of the tile's 11,400 cycles)
+            if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float2 r = make_float2(v[j], v[j + 1]);
-              if (p.act == 1) r = selu2(r);
-              so[j * 128] = r.x;
-              so[(j + 1) * 128] = r.y;
+              for (int j = 0; j < 32; j += 2) {
+                const float2 r = selu2(make_float2(v[j], v[j + 1]));
+                so[j * 128] = r.x;
+                so[(j + 1) * 128] = r.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) so[j * 128] = v[j];
             }
           } else {
 #pragma unroll
