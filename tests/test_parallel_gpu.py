@@ -42,13 +42,14 @@ def _worker(rank, world, port, out_dir, loss_name):
     model = nets.HNOSegXS(**CFG, device=dev)
     model.load_state_dict(orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14), seed=0))
     tr = parallel.Trainer(model, loss_name, lr=5e-3)
-    losses, grads = [], []
+    losses, grads, before, after = [], [], [], []
     for step in range(STEPS):
         x, lab = _batch(rank, step)
+        before.append(tr.flat.data.cpu().clone())
         losses.append(float(tr.step(x.to(dev), lab.to(dev))))
         grads.append(tr.flat.grad.cpu().clone())  # after the all-reduce: the averaged gradient the optimizer used
-    torch.save({'params': tr.flat.data.cpu(), 'grad': tr.flat.grad.cpu(), 'losses': losses, 'grads': grads},
-               os.path.join(out_dir, f'r{rank}.pt'))
+        after.append(tr.flat.data.cpu().clone())
+    torch.save({'losses': losses, 'grads': grads, 'before': before, 'after': after}, os.path.join(out_dir, f'r{rank}.pt'))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,37 +61,36 @@ def test_nccl_two_rank_step_equals_single_rank_on_the_concatenated_batch(cuda, t
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), loss_name), nprocs=world, join=True)
     res = [torch.load(os.path.join(tmp_path, f'r{r}.pt')) for r in range(world)]
-    assert torch.equal(res[0]['params'], res[1]['params'])  # replicas stay bit-identical
-    assert torch.equal(res[0]['grad'], res[1]['grad'])
+    for step in range(STEPS):  # replicas stay bit-identical: same averaged gradient, same parameters, every step
+        assert torch.equal(res[0]['grads'][step], res[1]['grads'][step])
+        assert torch.equal(res[0]['after'][step], res[1]['after'][step])
     from multimodal_3d_image_segmentation_b200 import nets, parallel
     from oracle import hno_oracle as orc
     model = nets.HNOSegXS(**CFG, device=cuda)
     model.load_state_dict(orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14), seed=0))
     tr = parallel.Trainer(model, loss_name, lr=5e-3)
-    losses, grads = [], []
+    # (a) At the parameters the two ranks held before each step, ONE rank on the concatenated batch computes the same loss and
+    # the same gradient as the all-reduced mean of the two shards, up to fp32 summation order (the rank partial sums are combined
+    # by NCCL instead of inside one kernel).  The global loss is the mean of the rank losses (means over (sample, label),
+    # nets/custom_losses.py:70,111).  Comparing free-running trajectories instead is ill-posed: Adamax's first update is
+    # lr * sign(g) for every element, so an element whose gradient is at round-off level moves 2 lr apart (measured 1.2e-3
+    # relative after three steps, later gradients 0.14 apart).
     for step in range(STEPS):
         xs, labs = zip(*[_batch(r, step) for r in range(world)])
-        losses.append(float(tr.step(torch.cat(xs).to(cuda), torch.cat(labs).to(cuda))))
-        grads.append(tr.flat.grad.cpu().clone())
-    # the global loss is the mean of the rank losses (means over (sample, label), nets/custom_losses.py:70,111)
+        tr.flat.data.copy_(res[0]['before'][step])
+        loss = float(tr.loss_and_grad(torch.cat(xs).to(cuda), torch.cat(labs).to(cuda)))
+        dl = abs(loss - (res[0]['losses'][step] + res[1]['losses'][step]) / 2)
+        g = tr.flat.grad.cpu()
+        dg = ((g - res[0]['grads'][step]).norm() / g.norm()).item()
+        print(f'{loss_name}: step {step + 1}: loss {loss:.7f} (2-rank mean differs by {dl:.1e}), gradient rel-L2 {dg:.2e}')
+        assert dl < 2e-6, (step, dl)
+        assert dg < 1e-5, (step, dg)
+    # (b) Given the all-reduced gradients, the fused Adamax reproduces the ranks' parameters bit for bit.
+    model2 = nets.HNOSegXS(**CFG, device=cuda)
+    model2.load_state_dict(orc.init_state_dict(4, 4, 24, [3] * 8, (10, 14, 14), seed=0))
+    tr2 = parallel.Trainer(model2, loss_name, lr=5e-3)
+    assert torch.equal(tr2.flat.data.cpu(), res[0]['before'][0])
     for step in range(STEPS):
-        assert abs(losses[step] - (res[0]['losses'][step] + res[1]['losses'][step]) / 2) < 2e-6
-    # Step 1 starts from identical parameters: the all-reduced mean of the rank gradients IS the large-batch gradient, up
-    # to fp32 summation order (rank partial sums are combined by NCCL instead of inside one kernel).
-    g1 = ((grads[0] - res[0]['grads'][0]).norm() / grads[0].norm()).item()
-    print(f'{loss_name}: 2-rank vs single-rank gradient of step 1 rel-L2 {g1:.2e}')
-    assert g1 < 1e-5, g1
-    # Parameters: Adamax's first update is lr * sign(g) for EVERY element (exp_avg / exp_inf = +-1), so an element whose
-    # gradient is at round-off level may move by 2 lr in the other direction, and from step 2 on the two runs follow slightly
-    # different trajectories (measured: 1.2e-3 relative after three steps, 98 % of the elements further apart than 1e-6 but none
-    # further than the steps' trust region).  The exact statements are the ones above (gradient of step 1, losses, replicas);
-    # here: same trajectory within the trust region.
-    single = tr.flat.data.cpu()
-    diff = (single - res[0]['params']).abs()
-    rel_p = (diff.norm() / single.norm()).item()
-    print(f'{loss_name}: parameters after {STEPS} steps: rel-L2 {rel_p:.2e}, max |diff| {diff.max():.2e}')
-    assert rel_p < 1e-2, rel_p
-    assert diff.max().item() <= 2 * 5e-3 * STEPS + 1e-6
-    for step in range(1, STEPS):  # later steps start from (almost) the same parameters
-        gs = ((grads[step] - res[0]['grads'][step]).norm() / grads[step].norm()).item()
-        assert gs < 5e-2, (step, gs)
+        tr2.flat.grad.copy_(res[0]['grads'][step])
+        tr2.optimizer.step()
+        assert torch.equal(tr2.flat.data.cpu(), res[0]['after'][step]), step
