@@ -41,7 +41,10 @@ template <int NPAD>
 struct TcShape {
   // measured on B200: 8 warps do not speed up the store/SELU epilogue (instruction bound, dhts 0.138 ms either way) and
   // cost the accumulate epilogue its second prefetch block (dhta 0.196 -> 0.292 ms), so every shape runs with 4
-  static constexpr int kWorkerWarps = 4;
+#ifndef HNO_TC_WIDE_WORKER_WARPS
+#define HNO_TC_WIDE_WORKER_WARPS 8
+#endif
+  static constexpr int kWorkerWarps = NPAD == 128 ? HNO_TC_WIDE_WORKER_WARPS : 4;
   static constexpr int kWorkers = 32 * kWorkerWarps;
   // Wide outputs (the synthesis stages: up to 121 rows per voxel) leave through shared memory and bulk tensor stores
   // issued by a seventh warp: one STS per element instead of one STG with 64-bit address arithmetic, and the
@@ -513,10 +516,12 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
         tc_fence_after_sync();
         const bool tile_live = (int)((tile - (uint32_t)g * p.tiles_per_slab) * 128 + 128) <= p.valid_m;  // uniform
         const bool has_bias = p.bias != nullptr;
+        constexpr int RH = 32 / kHalves;  // rows of a 32-row block per warp (two warps per TMEM lane quarter split it)
         for (int n0 = 0; n0 < p.nout; n0 += 32, ++st_blk) {
-          float v[32];
+          float v[RH];
           long long q0 = p.prof_mode == 2 ? clock64() : 0, q1;
-          tmem_ld32(acc + n0, v);
+          if constexpr (RH == 32) tmem_ld32(acc + n0, *reinterpret_cast<float(*)[32]>(v));
+          else tmem_ld16(acc + n0 + half * RH, *reinterpret_cast<float(*)[16]>(v));
           if (n0 + 32 >= p.nout) {  // last read of the accumulator buffer
             tc_fence_before_sync();
             mbar_arrive(&bar_accfree[ti & 1]);
@@ -525,30 +530,31 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
           const int sb = st_blk % kSB;
           if (st_blk >= kSB) mbar_wait(&bar_stfree[sb], (uint32_t)(((st_blk / kSB) - 1) & 1));
           if (p.prof_mode == 2) { q1 = clock64(); w_full += q1 - q0; q0 = q1; }
-          float* so = stage + sb * (32 * 128) + (quarter * 32 + lane);
+          float* so = stage + sb * (32 * 128) + half * RH * 128 + (quarter * 32 + lane);
+          const int nb = n0 + half * RH;  // first output row of this warp's share
           if (tile_live && !has_bias) {  // the common block: no predicates at all (rows >= nout are zeros of the
                                          // padded B image and are clipped by the bulk store)
             // the activation test stays OUTSIDE the unrolled loop: with a (uniform) branch per pair the 16 SELU chains of a
             // block ran one after the other (cycle counters: 51 cycles per pair, 6,600 of the tile's 11,400 cycles)
             if (p.act == 1) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
+              for (int j = 0; j < RH; j += 2) {
                 const float2 r = selu2(make_float2(v[j], v[j + 1]));
                 so[j * 128] = r.x;
                 so[(j + 1) * 128] = r.y;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) so[j * 128] = v[j];
+              for (int j = 0; j < RH; ++j) so[j * 128] = v[j];
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              if (n0 + j >= p.nout) break;  // warp uniform (rows beyond nout are clipped by the store anyway)
+            for (int j = 0; j < RH; j += 2) {
+              if (nb + j >= p.nout) break;  // warp uniform (rows beyond nout are clipped by the store anyway)
               float2 r = make_float2(v[j], v[j + 1]);
               if (has_bias) {
-                r.x += sbias[n0 + j];
-                r.y += sbias[n0 + j + 1];
+                r.x += sbias[nb + j];
+                r.y += sbias[nb + j + 1];
               }
               if (p.act == 1) r = selu2(r);
               if (!live) r = make_float2(0.f, 0.f);
@@ -729,8 +735,8 @@ __global__ void __launch_bounds__(TcShape<NPAD>::kThreads,
 #pragma unroll
           for (int i = 0; i < kChunkBytes / 16 / kTcWorkers; ++i) {
             const float4 x = r4[tid + i * kTcWorkers];
-            *reinterpret_cast<float4*>(hb + i * 512) = x;
-            *reinterpret_cast<float4*>(lb + i * 512) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+            *reinterpret_cast<float4*>(hb + i * (kTcWorkers * 4)) = x;  // kTcWorkers / 32 rows of 128 bytes per pass
+            *reinterpret_cast<float4*>(lb + i * (kTcWorkers * 4)) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
           }
           mbar_arrive(&bar_read[s]);  // the ring stage may be refilled
         } else {

@@ -59,6 +59,7 @@ table = {
     'pw24f': lambda: ops.pwconv_forward(a[0], None, w24, b24, 1, False),
     'dhtf': lambda: ops.dht3_forward(a[0], plan, 1.0),
     'dhts': lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=2, out=a[1]),
+    'dhtp': lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=0, out=a[1]),
     'dhta': lambda: ops.dht3_adjoint(z, plan, 1.0, epilogue=1, out=a[1]),
     'pw48b': lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, in1_is_selu=True),
     'pw48ba': lambda: ops.pwconv_backward(a[0], a[1], a[2], a[3], w48, 1, False, hw=hw, din1=acc[0], din2=acc[1]),
