@@ -11,7 +11,7 @@ Adamax update, for `--batch` (default 2, BASELINE config 2) synthetic 4x240x240x
 random-init weights.  One JSON line is printed by rank 0:
   value      whole-job volumes/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e        the same through the public API with HOST buffers: pinned H2D copy of every batch inside the
-             timed region (double-buffered on a copy stream) and loss.item() every step
+             timed region (double-buffered on a copy stream) and a host read of every step's loss
   roofline   the dominant kernel timed alone with CUDA events against the measured HBM peak
   cpu_baseline  the oracle port of the reference on this box's host cores (bounded sample: 1 volume, 1 step)
 """
@@ -683,11 +683,18 @@ def main():
             bufs[slot][1].copy_(ls_host[i % n_host], non_blocking=True)
             ready[slot].record(copy_stream)
 
+    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e_loop(k):
+        # Every step's loss is copied device -> host and read by the host inside the timed region (the reference prints it,
+        # experiments/train_test.py:162-175; it does not feed back into the step), ONE STEP BEHIND: the host enqueues step
+        # i + 1 before it waits for the loss of step i, so the GPU does not idle for a launch latency after every step.
         cur = torch.cuda.current_stream()
         for s in range(2):
             freed[s].record(cur)
         issue_copy(0)
+        seen = 0.0
         for i in range(k):
             if i + 1 < k:
                 issue_copy(i + 1)
@@ -695,7 +702,13 @@ def main():
             cur.wait_event(ready[slot])
             lv = trainer.step_raw(bufs[slot][0], bufs[slot][1], mask_val=0)
             freed[slot].record(cur)
-            lv.item()  # device -> host read of the step's loss, as experiments/train_test.py:162
+            loss_host[slot].copy_(lv.reshape(1), non_blocking=True)
+            loss_done[slot].record(cur)
+            if i > 0:
+                loss_done[1 - slot].synchronize()
+                seen = float(loss_host[1 - slot])
+        loss_done[(k - 1) % 2].synchronize()
+        return float(loss_host[(k - 1) % 2]) + 0.0 * seen
 
     e2e_loop(3)
     barrier()
@@ -738,7 +751,7 @@ def main():
                 'gpu_launches': e2e_launches, 'numa': numa,
                 'what': 'Trainer.step_raw: pinned int16 raw modalities + uint8 labels copied H2D every step (double-buffered '
                         'copy stream), z-scored per sample and modality on the device (normalize_modalities, run.py:52-55), '
-                        'train step, loss.item()'},
+                        'train step, every loss copied D2H and read by the host one step behind'},
         'gpu_launches': launches, 'loss': final_loss,
     }
     if args.config == 'mha_train' and not args.no_kernel_table:

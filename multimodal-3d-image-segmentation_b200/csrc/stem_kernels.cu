@@ -9,6 +9,8 @@
 #include "hno_b200.h"
 #include "wgrad.cuh"
 
+#include <stdlib.h>
+
 namespace hno {
 
 struct StemGeom {
@@ -152,6 +154,128 @@ __global__ void __launch_bounds__(kPwThreads, 3) k_stem_wgrad(const float* __res
   }
 }
 
+// Pipelined variant (round 2).  The kernel above is phase serialised (gather a tile, barrier, FFMA, barrier: HBM idle while it
+// computes and vice versa) and its 3 x 4 register tile needs 7 LDS.128 per 24 FFMA2, which makes the shared-memory data
+// pipe (4 wavefronts per LDS.128) its real bound: 3,584 wavefronts per 256 voxels against 1,536 FMA-pipe cycles.  Here
+//   * tiles of 128 voxels are DOUBLE BUFFERED and filled with 4-byte cp.async (zero-filled outside the volume / in the plane
+//     padding), issued for tile t+1 before the weight gradient of tile t runs;
+//   * a warp owns 16 voxels of the tile and all F x Q outputs: lane (ot, it) accumulates F/4 x Q/8 outputs (6 x 4 for the
+//     24-filter, 4-modality stem): 10 LDS.128 per 48 FFMA2.
+template <int CIN, int F>
+__global__ void __launch_bounds__(256, 3) k_stem_wgrad_pipe(const float* __restrict__ dpre, const float* __restrict__ x,
+                                                            float* __restrict__ partials, StemGeom g,
+                                                            int tiles_per_sample, long total_tiles) {
+  constexpr int Q = 8 * CIN;
+  constexpr int TV = 128, TVS = TV + 4;
+  constexpr int TO = F / 4, TI = Q / 8;
+  constexpr int STAGE = (F + Q) * TVS;  // floats per buffer: d(pre) rows then patch rows
+  constexpr int PSTRIDE = F * Q + F;
+  static_assert(F % 4 == 0 && 8 * (F * Q) <= 2 * STAGE, "stem weight gradient: unsupported shape");
+  extern __shared__ float4 smem4[];
+  float* buf = reinterpret_cast<float*>(smem4);  // [2][STAGE]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ot = lane >> 3, it = lane & 7;
+  float2 accW[TO][TI];
+  float accB[TO];
+#pragma unroll
+  for (int q = 0; q < TO; ++q) {
+    accB[q] = 0.f;
+#pragma unroll
+    for (int r = 0; r < TI; ++r) accW[q][r] = make_float2(0.f, 0.f);
+  }
+  // loader role of this thread: voxel tid & 127 of the tile, half (tid >> 7) of the rows
+  const int lv = tid & (TV - 1), lh = tid >> 7;
+  auto issue = [&](long tile, float* dst) {
+    const int b = (int)(tile / tiles_per_sample);
+    const long s = (tile - (long)b * tiles_per_sample) * TV + lv;
+    int d = 0, h = 0, w = 0;
+    bool live = false;
+    if (s < g.S) {
+      d = (int)(s / g.P);
+      const int p = (int)(s - (long)d * g.P);
+      if (p < g.H * g.W) {
+        live = true;
+        h = p / g.W;
+        w = p - h * g.W;
+      }
+    }
+    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst) + 4u * lv;
+    const float* dp = dpre + ((long)b * F + lh * (F / 2)) * g.S + (live ? s : 0);
+#pragma unroll
+    for (int o = 0; o < F / 2; ++o)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * ((lh * (F / 2) + o) * TVS)),
+                   "l"(dp + (long)o * g.S), "r"(live ? 4 : 0)
+                   : "memory");
+#pragma unroll
+    for (int qq = 0; qq < Q / 2; ++qq) {
+      const int q = lh * (Q / 2) + qq, i = q >> 3, t = q & 7;
+      const int zd = 2 * d - 1 + (t >> 2), zh = 2 * h - 1 + ((t >> 1) & 1), zw = 2 * w - 1 + (t & 1);
+      const bool inb = live && zd >= 0 && zd < g.Dx && zh >= 0 && zh < g.Hx && zw >= 0 && zw < g.Wx;
+      const float* src = x + ((long)b * CIN + i) * g.Dx * g.HWx + (inb ? (zd * (int)g.HWx + zh * g.Wx + zw) : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * ((F + q) * TVS)), "l"(src),
+                   "r"(inb ? 4 : 0)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  long tile = blockIdx.x;
+  if (tile < total_tiles) issue(tile, buf);
+  int cur = 0;
+  for (; tile < total_tiles; tile += gridDim.x, cur ^= 1) {
+    const long next = tile + gridDim.x;
+    if (next < total_tiles) {
+      issue(next, buf + (cur ^ 1) * STAGE);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* sdp = buf + cur * STAGE + (ot * TO) * TVS + warp * 16;
+    const float* sx = buf + cur * STAGE + (F + it) * TVS + warp * 16;
+#pragma unroll 2
+    for (int v = 0; v < 16; v += 4) {
+      float4 dd[TO], xx[TI];
+#pragma unroll
+      for (int q = 0; q < TO; ++q) dd[q] = *reinterpret_cast<const float4*>(sdp + q * TVS + v);
+#pragma unroll
+      for (int r = 0; r < TI; ++r) xx[r] = *reinterpret_cast<const float4*>(sx + (r * 8) * TVS + v);  // rows r * 8 + it
+#pragma unroll
+      for (int q = 0; q < TO; ++q) {
+#pragma unroll
+        for (int r = 0; r < TI; ++r) {
+          float2 a = accW[q][r];
+          a = ffma2(make_float2(dd[q].x, dd[q].y), make_float2(xx[r].x, xx[r].y), a);
+          a = ffma2(make_float2(dd[q].z, dd[q].w), make_float2(xx[r].z, xx[r].w), a);
+          accW[q][r] = a;
+        }
+        if (it == 0) accB[q] += (dd[q].x + dd[q].y) + (dd[q].z + dd[q].w);
+      }
+    }
+    __syncthreads();  // the buffer is refilled by the next iteration's prefetch
+  }
+  // ---- per-CTA partial row: the 8 warps' tiles through shared memory
+  float* prow = partials + (long)blockIdx.x * PSTRIDE;
+  float* scratch = buf;  // [8][F * Q], then [8][F]
+#pragma unroll
+  for (int q = 0; q < TO; ++q) {
+#pragma unroll
+    for (int r = 0; r < TI; ++r) scratch[warp * (F * Q) + (ot * TO + q) * Q + r * 8 + it] = accW[q][r].x + accW[q][r].y;
+    if (it == 0) scratch[8 * F * Q + warp * F + ot * TO + q] = accB[q];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < F * Q + F; idx += 256) {
+    float sum = 0.f;
+    if (idx < F * Q) {
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) sum += scratch[ww * (F * Q) + idx];
+    } else {
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) sum += scratch[8 * F * Q + ww * F + (idx - F * Q)];
+    }
+    prow[idx] = sum;
+  }
+}
+
 #define HNO_STEM_CONFIGS(X) X(1, 8) X(2, 8) X(4, 8) X(1, 12) X(2, 12) X(4, 12) X(1, 24) X(2, 24) X(3, 24) X(4, 24)
 
 int stem_supported(int cin, int f) {
@@ -200,16 +324,29 @@ template <int CIN, int F>
 static int stem_bwd_t(const float* dpre, const float* x, float* dweight, float* dbias, void* ws, int B,
                       const StemGeom& g, int accumulate, cudaStream_t st) {
   constexpr int Q = 8 * CIN;
-  constexpr int TV = kPwThreads;
-  const int tps = ceil_div(g.S, TV);
-  const long total = (long)tps * B;
-  long gmax = (long)sm_count() * 3;  // 58 KB of shared memory per CTA: three fit, and the phases of one hide behind the others
-  const int grid = (int)(total < gmax ? total : gmax);
-  const size_t smem = (size_t)(F + Q) * (TV + 4) * sizeof(float);
-  auto kern = k_stem_wgrad<CIN, F>;
-  HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* partials = reinterpret_cast<float*>(ws);
-  kern<<<grid, kPwThreads, smem, st>>>(dpre, x, partials, g, tps, total);
+  const long gmax = (long)sm_count() * 3;  // <= 60 KB of shared memory per CTA: three fit, and the phases of one hide behind the others
+  static const bool pipe = !(getenv("HNO_STEM_PIPE") && atoi(getenv("HNO_STEM_PIPE")) == 0);  // 0: the phase-serialised kernel
+  int grid;
+  if (pipe) {
+    constexpr int TV = 128;
+    const int tps = ceil_div(g.S, TV);
+    const long total = (long)tps * B;
+    grid = (int)(total < gmax ? total : gmax);
+    const size_t smem = (size_t)2 * (F + Q) * (TV + 4) * sizeof(float) + (8 * F + 8) * sizeof(float);
+    auto kern = k_stem_wgrad_pipe<CIN, F>;
+    HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(dpre, x, partials, g, tps, total);
+  } else {
+    constexpr int TV = kPwThreads;
+    const int tps = ceil_div(g.S, TV);
+    const long total = (long)tps * B;
+    grid = (int)(total < gmax ? total : gmax);
+    const size_t smem = (size_t)(F + Q) * (TV + 4) * sizeof(float);
+    auto kern = k_stem_wgrad<CIN, F>;
+    HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kPwThreads, smem, st>>>(dpre, x, partials, g, tps, total);
+  }
   HNO_LAUNCH_CHECK();
   return reduce_partials(partials, grid, F * Q, F, dweight, dbias, accumulate, st);
 }
