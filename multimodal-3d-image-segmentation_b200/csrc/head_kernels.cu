@@ -347,6 +347,106 @@ __global__ void __launch_bounds__(256) k_head_bwd_d(const float* __restrict__ g2
   *dst = acc;
 }
 
+// Gather-table variants of the two passes above (round 2).  The per-thread loops over [s, e) with three table loads and two
+// compares per tap made both passes instruction bound (190 us for 324 MB).  Here the (at most kGatherK) taps of every
+// low-resolution index are turned into a fixed-length weight row ONCE per CTA (shared memory: first tap + kGatherK weights,
+// zero beyond the range), a thread reuses its weights for several slices, and the inner loop is K loads + K FMAs with no
+// branches.  Same taps, same order, same products as the loops above (zero-weight terms add exactly 0).
+constexpr int kGatherMax = 6;  // instantiated for 4 taps (2x up-sampling) and 6
+
+template <int AX, int kGatherK>
+__device__ __forceinline__ void head_build_gather(const InterpDev& t, int* ss, float* sw) {
+  for (int i = threadIdx.x; i < t.lo[AX]; i += blockDim.x) {
+    const int s = t.s[AX][i], e = t.e[AX][i];
+    ss[i] = s;
+#pragma unroll
+    for (int k = 0; k < kGatherK; ++k) {
+      const int z = s + k;
+      float w = 0.f;
+      if (z < e) {
+        const float l1 = t.l1[AX][z];
+        w = (t.i0[AX][z] == i ? 1.f - l1 : 0.f) + (t.i1[AX][z] == i ? l1 : 0.f);
+      }
+      sw[i * kGatherK + k] = w;
+    }
+  }
+}
+
+// g1[r][zh][w] -> g2[r][h][w], r = bc * Dx + zd; grid (ceil(H*W / 256), ceil(R / 4))
+template <int kGatherK>
+__global__ void __launch_bounds__(256) k_head_bwd_h_gather(const float* __restrict__ g1, float* __restrict__ g2, InterpDev t,
+                                                           long R) {
+  extern __shared__ float sgw[];
+  const int W = t.lo[2], H = t.lo[1], Hx = t.hi[1];
+  int* ss = reinterpret_cast<int*>(sgw);
+  float* sw = sgw + H;
+  head_build_gather<1, kGatherK>(t, ss, sw);
+  __syncthreads();
+  const int hw = blockIdx.x * 256 + threadIdx.x;
+  if (hw >= H * W) return;
+  const int h = hw / W, w = hw - h * W;
+  float wk[kGatherK];
+  int off[kGatherK];
+  const int s0 = ss[h];
+#pragma unroll
+  for (int k = 0; k < kGatherK; ++k) {
+    wk[k] = sw[h * kGatherK + k];
+    off[k] = min(s0 + k, Hx - 1) * W + w;  // taps beyond the range have weight 0: any valid address will do
+  }
+  const long r0 = (long)blockIdx.y * 4;
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb) {
+    const long r = r0 + rb;
+    if (r >= R) break;
+    const float* src = g1 + r * (long)Hx * W;
+    float v[kGatherK];
+#pragma unroll
+    for (int k = 0; k < kGatherK; ++k) v[k] = __ldg(src + off[k]);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < kGatherK; ++k) acc = fmaf(wk[k], v[k], acc);
+    g2[r * (long)H * W + hw] = acc;
+  }
+}
+
+// g2[bc][zd][h*w] -> dll[bc][d][P] (padding columns zeroed); grid (ceil(P / 256), D, nbc)
+template <int kGatherK>
+__global__ void __launch_bounds__(256) k_head_bwd_d_gather(const float* __restrict__ g2, float* __restrict__ dll, InterpDev t,
+                                                           long P) {
+  __shared__ float swk[kGatherK];
+  __shared__ int ss0;
+  const int W = t.lo[2], H = t.lo[1], D = t.lo[0], Dx = t.hi[0];
+  const int d = blockIdx.y;
+  if (threadIdx.x < kGatherK) {
+    const int k = threadIdx.x, s = t.s[0][d], e = t.e[0][d], z = s + k;
+    float w = 0.f;
+    if (z < e) {
+      const float l1 = t.l1[0][z];
+      w = (t.i0[0][z] == d ? 1.f - l1 : 0.f) + (t.i1[0][z] == d ? l1 : 0.f);
+    }
+    swk[k] = w;
+    if (k == 0) ss0 = s;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= P) return;
+  const long bc = blockIdx.z;
+  float* dst = dll + (bc * D + d) * P + p;
+  const int HW = H * W;
+  if (p >= HW) {
+    *dst = 0.f;
+    return;
+  }
+  const float* src = g2 + bc * (long)Dx * HW + p;
+  float v[kGatherK];
+#pragma unroll
+  for (int k = 0; k < kGatherK; ++k) v[k] = __ldg(src + (long)min(ss0 + k, Dx - 1) * HW);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < kGatherK; ++k) acc = fmaf(swk[k], v[k], acc);
+  *dst = acc;
+}
+
 // ------------------------------------------------------------------------------------------ losses
 // Five moments per (b, c): sum p, sum t, sum p*t, sum p*p, sum t*t.  Block partials in fp64.
 constexpr int kMoments = 5;
@@ -1207,16 +1307,47 @@ size_t head_backward_workspace_bytes(const void* th, int B, int C) {
   return (g1 + g2) * sizeof(float) + mom + 512;
 }
 
-static int head_backward_passes(const InterpDev& t, float* g1, float* g2, float* dll, int B, int C, long P,
+// longest tap range of a low-resolution index along `axis` (from the host copy of the tables)
+static int max_tap_range(const void* th, int axis) {
+  const auto* h = reinterpret_cast<const InterpHeader*>(th);
+  const int* iw = reinterpret_cast<const int*>(th);
+  int m = 0;
+  for (int i = 0; i < h->lo[axis]; ++i) {
+    const int n = iw[h->off_e[axis] + i] - iw[h->off_s[axis] + i];
+    if (n > m) m = n;
+  }
+  return m;
+}
+
+static int head_backward_passes(const void* th, const InterpDev& t, float* g1, float* g2, float* dll, int B, int C, long P,
                                 cudaStream_t st) {
   const long nbc = (long)B * C;
   HNO_CHECK(nbc * t.hi[0] <= 65535 && t.lo[0] <= 65535 && nbc <= 65535, "head backward: grid too large");
-  {
+  static const bool gather_on = !(getenv("HNO_HEAD_GATHER") && atoi(getenv("HNO_HEAD_GATHER")) == 0);
+  const int kh = max_tap_range(th, 1), kd = max_tap_range(th, 0);
+  const bool gh = gather_on && kh <= kGatherMax && (size_t)t.lo[1] * (kGatherMax + 1) * 4 <= 40 * 1024;
+  const bool gd = gather_on && kd <= kGatherMax;
+  if (gh) {
+    const long R = nbc * t.hi[0];
+    dim3 grid(ceil_div((long)t.lo[1] * t.lo[2], 256), (unsigned)ceil_div(R, 4));
+    if (kh <= 4)
+      k_head_bwd_h_gather<4><<<grid, 256, (size_t)t.lo[1] * 5 * 4, st>>>(g1, g2, t, R);
+    else
+      k_head_bwd_h_gather<6><<<grid, 256, (size_t)t.lo[1] * 7 * 4, st>>>(g1, g2, t, R);
+    HNO_LAUNCH_CHECK();
+  } else {
     dim3 grid(ceil_div((long)t.lo[1] * t.lo[2], 256), (unsigned)(nbc * t.hi[0]));
     k_head_bwd_h<<<grid, 256, 0, st>>>(g1, g2, t, nbc);
     HNO_LAUNCH_CHECK();
   }
-  {
+  if (gd) {
+    dim3 grid(ceil_div(P, 256), t.lo[0], (unsigned)nbc);
+    if (kd <= 4)
+      k_head_bwd_d_gather<4><<<grid, 256, 0, st>>>(g2, dll, t, P);
+    else
+      k_head_bwd_d_gather<6><<<grid, 256, 0, st>>>(g2, dll, t, P);
+    HNO_LAUNCH_CHECK();
+  } else {
     dim3 grid(ceil_div(P, 256), t.lo[0], (unsigned)nbc);
     k_head_bwd_d<<<grid, 256, 0, st>>>(g2, dll, t, nbc, P);
     HNO_LAUNCH_CHECK();
@@ -1239,7 +1370,7 @@ int head_backward(const void* th, const void* td, const float* dprobs, const flo
       k_head_bwd_w<kC, 0, 0><<<grid, 256, 0, st>>>(dprobs, probs, nullptr, nullptr, nullptr, nullptr, g1, t, P);
   })
   HNO_LAUNCH_CHECK();
-  return head_backward_passes(t, g1, g2, dll, B, C, P, st);
+  return head_backward_passes(th, t, g1, g2, dll, B, C, P, st);
 }
 
 size_t loss_workspace_bytes(int B, int C) { return (size_t)B * C * kLossChunks * kMoments * sizeof(double) + 256; }
@@ -1403,7 +1534,7 @@ int head_loss_backward(const void* th, const void* td, const float* ll, const ui
     })
   }
   HNO_LAUNCH_CHECK();
-  return head_backward_passes(t, g1, g2, dll, B, C, P, st);
+  return head_backward_passes(th, t, g1, g2, dll, B, C, P, st);
 }
 
 }  // namespace hno
