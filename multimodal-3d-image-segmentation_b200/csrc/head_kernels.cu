@@ -902,7 +902,10 @@ __global__ void __launch_bounds__(32 * kWRowWarps, 2) k_head_loss_wrow(const flo
 
 // backward, W pass with one warp per row: the d(logit) of the whole row goes to the warp's shared-memory row, then lane
 // w_lo gathers the (two to five) voxels that touch low-resolution tap w_lo.  g1 as k_head_bwd_w_rows.
-template <int C, int ACT, int KMAX>
+// KG > 0: the gather runs on per-CTA weight rows (first voxel + KG weights per low-resolution tap, built once in shared memory)
+// instead of walking [s, e) with three table loads and two compares per voxel -- that loop was 43 % of the kernel's
+// instructions (ncu source view, 182 M warp instructions for 17.9 M voxels).
+template <int C, int ACT, int KMAX, int KG>
 __global__ void __launch_bounds__(32 * kWRowWarps, 2) k_head_bwd_wrow(const float* __restrict__ ll,
                                                                       const uint8_t* __restrict__ labels,
                                                                       const float* __restrict__ coef,
@@ -919,6 +922,12 @@ __global__ void __launch_bounds__(32 * kWRowWarps, 2) k_head_bwd_wrow(const floa
   const uint8_t* lb = labels + (long)b * rows * Wx;
   float* sR = sRow + warp * C * WP;
   float* sD = sRow + kWRowWarps * C * WP + warp * C * WXP;
+  int* sGs = reinterpret_cast<int*>(sRow + kWRowWarps * C * (WP + WXP));  // [W] first voxel of a tap
+  float* sGw = reinterpret_cast<float*>(sGs + W);                          // [W][KG]
+  if (KG > 0) {
+    head_build_gather<2, (KG > 0 ? KG : 1)>(t, sGs, sGw);
+    __syncthreads();
+  }
   int w0[KMAX], w1[KMAX];
   float lw1[KMAX];
 #pragma unroll
@@ -981,12 +990,23 @@ __global__ void __launch_bounds__(32 * kWRowWarps, 2) k_head_bwd_wrow(const floa
       float acc[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) acc[c] = 0.f;
-      const int z1 = t.e[2][wl];
-      for (int z2 = t.s[2][wl]; z2 < z1; ++z2) {
-        const float l1 = t.l1[2][z2];
-        const float wgt = (t.i0[2][z2] == wl ? 1.f - l1 : 0.f) + (t.i1[2][z2] == wl ? l1 : 0.f);
+      if (KG > 0) {
+        const int z0 = sGs[wl];
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, sD[c * WXP + z2], acc[c]);
+        for (int k = 0; k < KG; ++k) {
+          const float wgt = sGw[wl * KG + k];
+          const int z2 = min(z0 + k, Wx - 1);  // beyond the range the weight is 0
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, sD[c * WXP + z2], acc[c]);
+        }
+      } else {
+        const int z1 = t.e[2][wl];
+        for (int z2 = t.s[2][wl]; z2 < z1; ++z2) {
+          const float l1 = t.l1[2][z2];
+          const float wgt = (t.i0[2][z2] == wl ? 1.f - l1 : 0.f) + (t.i1[2][z2] == wl ? l1 : 0.f);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, sD[c * WXP + z2], acc[c]);
+        }
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) g1[(((long)b * C + c) * (long)rows + row) * W + wl] = acc[c];
@@ -1509,18 +1529,24 @@ int head_loss_backward(const void* th, const void* td, const float* ll, const ui
     const long want = (rows + kWRowWarps - 1) / kWRowWarps;
     dim3 grid((int)(want < 4 * 296 ? want : 4 * 296), B);
     const int WP = (t.lo[2] + 3) & ~3, WXP = (t.hi[2] + 3) & ~3;
-    const size_t smem = (size_t)kWRowWarps * C * (WP + WXP) * sizeof(float);
+    static const bool gather_on = !(getenv("HNO_HEAD_GATHER") && atoi(getenv("HNO_HEAD_GATHER")) == 0);
+    const int kw = max_tap_range(th, 2);
+    const int kg = !gather_on || kw > kGatherMax ? 0 : (kw <= 4 ? 4 : 6);
+    const size_t smem = (size_t)kWRowWarps * C * (WP + WXP) * sizeof(float) + (size_t)t.lo[2] * (kg + 1) * sizeof(float);
+#define HNO_BWD_WROW(KMAX_, KG_)                                                                             \
+  {                                                                                                          \
+    auto kern = k_head_bwd_wrow<kC, 1, KMAX_, KG_>;                                                          \
+    HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    kern<<<grid, 32 * kWRowWarps, smem, st>>>(ll, labels, coef, grad_loss, g1, t, P, WP, WXP);               \
+  }
     HNO_CLASS_SWITCH(C, {
       if (kmax == 5) {
-        auto kern = k_head_bwd_wrow<kC, 1, 5>;
-        HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 32 * kWRowWarps, smem, st>>>(ll, labels, coef, grad_loss, g1, t, P, WP, WXP);
+        if (kg == 4) HNO_BWD_WROW(5, 4) else if (kg == 6) HNO_BWD_WROW(5, 6) else HNO_BWD_WROW(5, 0)
       } else {
-        auto kern = k_head_bwd_wrow<kC, 1, 10>;
-        HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 32 * kWRowWarps, smem, st>>>(ll, labels, coef, grad_loss, g1, t, P, WP, WXP);
+        if (kg == 4) HNO_BWD_WROW(10, 4) else if (kg == 6) HNO_BWD_WROW(10, 6) else HNO_BWD_WROW(10, 0)
       }
     })
+#undef HNO_BWD_WROW
   } else if (tg > 0) {
     const long rows = (long)t.hi[0] * t.hi[1];
     dim3 grid((int)(rows < 4 * 296 ? rows : 4 * 296), B);
