@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "dht_plan.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace hno {
@@ -38,6 +39,8 @@ struct CorePtrs {
 };
 
 // zall: [L + 1][B][C][Ld][Lh][Lw] (z_0 .. z_L): written by the forward when non-null, read by the backward.
+__device__ long long g_core_prof[16];
+#define CORE_STAMP(i) if (blockIdx.x == 3 && blockIdx.y == 3 && blockIdx.z == 0 && threadIdx.x == 0) g_core_prof[i] = clock64();
 template <int C, bool BWD>
 __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __restrict__ T2, float* __restrict__ zall,
                                                                float* __restrict__ partials, const float* __restrict__ pf,
@@ -47,14 +50,15 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
   // programmatic dependent launch: the H-synthesis kernel behind this one may run its prologue (basis image, TMEM, barriers)
   // now; this kernel's own prologue (tables, weights) runs while the H analysis in front of it drains
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  CORE_STAMP(0)
   extern __shared__ float4 smem4[];
   float* s = reinterpret_cast<float*>(smem4);
-  float* fwT = s;                               // [Wp][Jwp]
-  float* fwP = fwT + g.Wp * g.Jwp;              // [Jw][Wp]
-  float* Tw = fwP + g.Jw * g.Wp;                // [C][4][Jwp]   (the <= 4 input rows of a channel are read straight from T2)
+  float* fwP = s;                               // [Jw][Wp]
+  float* fwT = fwP + g.Jw * g.Wp;               // [Wp][Jwp]     fwT | Tw are dead while the mixes run: the backward pass
+  float* Tw = fwT + g.Wp * g.Jwp;               // [C][4][Jwp]   parks a staging tile there (>= C (nqp + 4) floats, checked on the host)
   float* zq = Tw + C * 4 * g.Jwp;               // [C][nqp]
   float* wts = zq + C * g.nqp;                  // [L][C][C]   forward: transposed [i][o]; backward: as stored [o][i]
-  float* sdp = wts + L * C * C;                 // backward only: [C][nqp + 4] x 2 staging tiles
+  float* sdp = wts + L * C * C;                 // backward only: [C][nqp + 4] x 2 staging tiles (d(pre), z_l)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int jch = blockIdx.x, jcd = blockIdx.y, b = blockIdx.z;
   const int* jd_desc = pi + g.off_jdesc[0];
@@ -70,10 +74,44 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
 
   // ---- tables, weights and the <= 4 rows of every channel
   {
-    const float* src = pf + g.off_fullT_w;
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(fwT);
-    for (int c4 = tid; c4 < (g.Wp * g.Jwp + g.Jw * g.Wp) >> 2; c4 += kCoreThreads)  // fullT and fullP are adjacent in the plan
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16 * c4), "l"(src + 4 * c4) : "memory");
+    const float* src = pf + g.off_fullT_w;  // fullT [Wp][Jwp], then fullP [Jw][Wp] (adjacent in the plan)
+    const unsigned dT = (unsigned)__cvta_generic_to_shared(fwT), dP = (unsigned)__cvta_generic_to_shared(fwP);
+    const int nT = (g.Wp * g.Jwp) >> 2, nP = (g.Jw * g.Wp) >> 2;
+    for (int c4 = tid; c4 < nT + nP; c4 += kCoreThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(c4 < nT ? dT + 16 * c4 : dP + 16 * (c4 - nT)), "l"(src + 4 * c4) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // backward: the saved layer outputs z_L (-> sy) and z_{L-1} (-> sx) of this CTA's modes start their way from HBM now
+  // (they were written by the forward pass, not by the kernel in front, so they may be requested before griddepcontrol.wait);
+  // fetched at the top of every layer they cost ~12,000 cycles per layer (cycle counters: 3 x 13 k of the kernel's 107 k)
+  constexpr int CHq = C / 2;
+  const int pq = tid & 127, phalf = tid >> 7;
+  const int TVSq = g.nqp + 4;
+  const long cstr = (long)g.Ld * g.Lh * g.Lw;
+  bool pvalid = false;
+  long pgoff = 0;
+  {
+    const bool act = pq < g.nq;
+    const int ms = act ? pq / g.Lw : 0, kw = act ? pq - ms * g.Lw : 0;
+    const int kd = kd2[ms >> 1], kh = kh2[ms & 1];
+    pvalid = act && kd >= 0 && kh >= 0;
+    pgoff = pvalid ? (((long)b * C * g.Ld + kd) * g.Lh + kh) * g.Lw + kw + (long)(phalf * CHq) * cstr : 0;
+  }
+  auto prefetch_layer = [&](int layer, float* dst) {  // z_layer of this CTA's modes -> dst[c][TVS] (zeros for missing modes)
+    if (pq < g.nqp) {
+      const float* src = zall + (long)layer * BCM + pgoff;
+      const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst + (phalf * CHq) * TVSq + pq);
+#pragma unroll
+      for (int c = 0; c < CHq; ++c)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * (c * TVSq)), "l"(src + c * cstr),
+                     "r"(pvalid ? 4 : 0)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (BWD) {
+    prefetch_layer(L, sdp);                  // z_L lands where d(pre) of the first layer is formed (in place)
+    prefetch_layer(L - 1, sdp + C * TVSq);
   }
   for (int idx = tid; idx < L * C * C; idx += kCoreThreads) {
     const int l = idx / (C * C), r = idx - l * C * C;
@@ -84,8 +122,11 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
       wts[idx] = __ldg(P.w[l] + o * C + i);
     }
   }
-  cp_async_wait_all();
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // T2 (the H analysis / H^T synthesis in front) is read from here on
+  if (BWD) asm volatile("cp.async.wait_group 2;" ::: "memory");  // the tables; the two layer tiles stay in flight
+  else cp_async_wait_all();
+  CORE_STAMP(1)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  CORE_STAMP(2)  // T2 (the H analysis / H^T synthesis in front) is read from here on
   __syncthreads();
   // ---- W analysis: Tw[c][r][jw] = sum_w rows[c][r][w] fwT[w][jw]; a thread owns the 4 rows of a channel x 4 columns jw
   {
@@ -134,12 +175,13 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
     }
   }
   __syncthreads();
+  CORE_STAMP(3)
 
   // ---- cas recombination (dht_plan.h): Z[kd, kh, kw] = scale * sum over the 8 products; missing sin rows are zero rows and
   //      their sigma is 0, so the full expression is evaluated for every mode.  A thread owns one mode: its signs and row
   //      indices are set up once and reused for all C channels.
-  if (tid < g.nq) {
-    const int q = tid;
+  if ((tid & 127) < g.nq) {  // two threads per mode: channels [0, C/2) and [C/2, C)
+    const int q = tid & 127, c0 = (tid >> 7) * (C / 2);
     const int ms = q / g.Lw, kw = q - ms * g.Lw;
     const int kd = kd2[ms >> 1], kh = kh2[ms & 1];
     if (kd >= 0 && kh >= 0) {
@@ -151,7 +193,7 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
       const float k0c = scale_in, k0s = scale_in * gw, k1c = scale_in * gh, k1s = -scale_in * gh * gw;
       const float k2c = scale_in * gd, k2s = -scale_in * gd * gw, k3c = -scale_in * gd * gh, k3s = -scale_in * gd * gh * gw;
 #pragma unroll 4
-      for (int c = 0; c < C; ++c) {
+      for (int c = c0; c < c0 + C / 2; ++c) {
         const float* t = Tw + c * 4 * g.Jwp;
         float v = k0c * t[cw];
         v = fmaf(k0s, t[swi], v);
@@ -164,10 +206,11 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
         zq[c * g.nqp + q] = v;
       }
     } else {
-      for (int c = 0; c < C; ++c) zq[c * g.nqp + q] = 0.f;
+      for (int c = c0; c < c0 + C / 2; ++c) zq[c * g.nqp + q] = 0.f;
     }
   }
   __syncthreads();
+  CORE_STAMP(4)
 
   // ---- the shared-weight mixes on this CTA's modes.  TWO threads per mode (q = tid & 127, half = tid >> 7): each computes
   //      half of the C output channels from all C inputs, exchanging the layer outputs through zq (its own half only is
@@ -227,7 +270,9 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
       // backward of the chain (k_modechain_bwd on this CTA's modes): d(pre) = g * selu'(z_{l+1}), dW_l += d(pre) z_l^T,
       // g <- W_l^T d(pre) + d(pre); g lives in zq, a thread handles the CH channels of its half
       const int TVS = g.nqp + 4;
-      float* sx = sdp + C * TVS;
+      float* sx = sdp + C * TVS;  // z_l (input of layer l): this tile and the one parked on fwT | Tw take turns
+      float* sy = sdp;            // z_{l+1} (its SELU output): first layer in the d(pre) tile itself, then the previous z_l tile
+      float* spare = fwT;         // free from here until the recombination^T below
       constexpr int TI = C % 3 == 0 ? 3 : 2;  // weight-gradient tile: one output row, TI input columns per thread
       constexpr int NI = C / TI;
       static_assert(C % TI == 0 && C * NI <= kCoreThreads, "weight-gradient tiling");
@@ -235,17 +280,20 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
       const bool wactive = tid < C * NI;
       const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
       for (int l = L - 1; l >= 0; --l) {
+        if (l == L - 1) { CORE_STAMP(8) }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's elements of sy / sx have landed
         if (q < g.nqp) {
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             const int cc = half * CH + c;
-            const float y = valid ? __ldg(zall + (long)(l + 1) * BCM + goff + c * cstride) : 0.f;
-            const float xin = valid ? __ldg(zall + (long)l * BCM + goff + c * cstride) : 0.f;
-            sdp[cc * TVS + q] = valid ? zq[cc * g.nqp + q] * selu_grad_from_out(y) : 0.f;
-            sx[cc * TVS + q] = xin;
+            sdp[cc * TVS + q] = valid ? zq[cc * g.nqp + q] * selu_grad_from_out(sy[cc * TVS + q]) : 0.f;
           }
         }
         __syncthreads();
+        // z_{l-1} replaces z_{l+1} (every thread has read its own elements of it) while this layer computes
+        float* nxt = sy == sdp ? spare : sy;
+        if (l > 0) prefetch_layer(l - 1, nxt);
+        if (l == L - 1) { CORE_STAMP(9) }
         if (wactive) {
           float acc[TI];
 #pragma unroll
@@ -262,6 +310,7 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
 #pragma unroll
           for (int r = 0; r < TI; ++r) pr[r] = acc[r];
         }
+        if (l == L - 1) { CORE_STAMP(10) }
         if (valid) {
           float2 a2[CH / 2];
 #pragma unroll
@@ -284,17 +333,23 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
             zq[(half * CH + 2 * h + 1) * g.nqp + q] = a2[h].y;
           }
         }
+        if (l == L - 1) { CORE_STAMP(11) }
         __syncthreads();  // the staging tiles are rewritten by the next layer
+        if (l == L - 1) { CORE_STAMP(12) }
+        sy = sx;  // next layer: y = z_l (this layer's input tile), x = z_{l-1} (landing in the tile freed above)
+        sx = nxt;
       }
     }
   }
   __syncthreads();
+  CORE_STAMP(5)
 
   // ---- recombination^T (k_dht_tail_adj): Tt[c][jw][r] = sign * scale * sum_{+-d, +-h, +-w} (+-) z[c][mode], stored with the
   //      4 rows of a channel adjacent so that the synthesis reads them with one LDS.128.  A thread owns one (r, jw): the
   //      (up to 8) source modes and their signs are set up once and reused for all C channels.
   float* Tt = Tw;  // [C][Jwp][4]
-  for (int item = tid; item < 4 * g.Jwp; item += kCoreThreads) {
+  for (int item = tid & 127; item < 4 * g.Jwp; item += 128) {  // two threads per (r, jw): half of the channels each
+    const int c0 = (tid >> 7) * (C / 2);
     const int r = item & 3, jw = item >> 2;
     const int isd = r >> 1, ish = r & 1;
     int src[8];
@@ -321,7 +376,7 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
       for (int k = 0; k < 8; ++k) src[k] = 0, coef[k] = 0.f;
     }
 #pragma unroll 2
-    for (int c = 0; c < C; ++c) {
+    for (int c = c0; c < c0 + C / 2; ++c) {
       const float* zp = zq + c * g.nqp;
       float acc = 0.f;
 #pragma unroll
@@ -330,6 +385,7 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
     }
   }
   __syncthreads();
+  CORE_STAMP(6)
 
   // ---- W synthesis: T2[c][r][w] = sum_jw Tt[c][jw][r] fwP[jw][w]; a thread owns the 4 rows of a channel x 4 columns w
   {
@@ -364,9 +420,22 @@ __global__ void __launch_bounds__(kCoreThreads, 3) k_spectral_core(float* __rest
       }
     }
   }
+  __syncthreads();
+  CORE_STAMP(7)
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static void core_prof_print(const char* what, cudaStream_t st) {
+  static const bool on = getenv("HNO_CORE_PROF") && atoi(getenv("HNO_CORE_PROF")) != 0;
+  if (!on) return;
+  cudaStreamSynchronize(st);
+  long long h[16];
+  cudaMemcpyFromSymbol(h, g_core_prof, sizeof(h));
+  fprintf(stderr, "[core_prof %s] prologue %lld | pdl wait %lld | analysis %lld | recombine %lld | chain %lld | recombT %lld | synthesis %lld | total %lld\n",
+          what, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
+  fprintf(stderr, "   chain layer L-1: stage+sync %lld | wgrad (thread 0) %lld | W^T product %lld | final sync %lld\n", h[9] - h[8], h[10] - h[9], h[11] - h[10], h[12] - h[11]);
+}
+
 static bool make_core_geom(const DhtPlanHeader* h, CoreGeom* out) {
   CoreGeom g;
   g.W = h->ax[2].n;
@@ -410,7 +479,7 @@ static bool make_core_geom(const DhtPlanHeader* h, CoreGeom* out) {
 
 static size_t core_smem(const CoreGeom& g, int C, int L, bool bwd) {
   size_t f = (size_t)g.Wp * g.Jwp + (size_t)g.Jw * g.Wp + (size_t)C * 4 * g.Jwp + (size_t)C * g.nqp + (size_t)L * C * C;
-  if (bwd) f += (size_t)2 * C * (g.nqp + 4);
+  if (bwd) f += (size_t)2 * C * (g.nqp + 4);  // d(pre) and z_l staging tiles (the third is parked on fwT | Tw)
   return f * sizeof(float);
 }
 
@@ -420,7 +489,8 @@ bool spectral_core_eligible(const void* plan_host, int C, int L, int B) {
   if (!make_core_geom(h, &g)) return false;
   if (C != 24 && C != 8) return false;
   if (L < 1 || L > kCoreMaxLayers || B < 1 || B > 65535) return false;
-  return core_smem(g, C, L, true) <= 100 * 1024;
+  if ((size_t)g.Wp * g.Jwp + (size_t)C * 4 * g.Jwp < (size_t)C * (g.nqp + 4)) return false;  // the parked staging tile
+  return core_smem(g, C, L, true) <= 75 * 1024 && g.nq <= 128;
 }
 
 size_t spectral_core_partials_floats(const void* plan_host, int C, int L, int B) {
@@ -453,6 +523,7 @@ int spectral_core(const void* plan_host, const void* plan_dev, float* T2, float*
   {                                                                                                                 \
     auto kern = k_spectral_core<CC, BW>;                                                                            \
     HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+    HNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
     cudaLaunchConfig_t cfg = {};                                                                                    \
     cfg.gridDim = grid;                                                                                             \
     cfg.blockDim = dim3(kCoreThreads);                                                                              \
@@ -464,6 +535,11 @@ int spectral_core(const void* plan_host, const void* plan_dev, float* T2, float*
     cfg.attrs = attr;                                                                                               \
     cfg.numAttrs = core_pdl ? 1 : 0;                                                                                \
     HNO_CUDA(cudaLaunchKernelEx(&cfg, kern, T2, zall, partials, pf, pi, g, P, L, B, scale_in, scale_out));          \
+    if (getenv("HNO_CORE_PROF")) {                                                                                  \
+      int nb = 0;                                                                                                   \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kCoreThreads, smem);                                 \
+      fprintf(stderr, "[core_prof] smem %zu B, blocks/SM %d, grid %u\n", smem, nb, grid.x * grid.y * grid.z);       \
+    }                                                                                                               \
   }
   if (C == 24) {
     if (backward) HNO_CORE_LAUNCH(24, true) else HNO_CORE_LAUNCH(24, false)
@@ -472,6 +548,7 @@ int spectral_core(const void* plan_host, const void* plan_dev, float* T2, float*
   }
 #undef HNO_CORE_LAUNCH
   HNO_LAUNCH_CHECK();
+  core_prof_print(backward ? "bwd" : "fwd", st);
   if (backward) return reduce_chain_partials(partials, (int)(grid.x * grid.y * grid.z), L, C * C, dweights, accumulate_dw, st);
   return 0;
 }
