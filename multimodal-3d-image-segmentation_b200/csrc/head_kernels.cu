@@ -394,25 +394,28 @@ __global__ void __launch_bounds__(256) k_head_bwd_h_gather(const float* __restri
     off[k] = min(s0 + k, Hx - 1) * W + w;  // taps beyond the range have weight 0: any valid address will do
   }
   const long r0 = (long)blockIdx.y * 4;
+  float v[4][kGatherK];  // all loads of the four slices first (one slice at a time left the kernel latency bound: ncu
+                         // long_scoreboard 12 stalls per issue, 2.5 TB/s)
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb) {
+    const float* src = g1 + min(r0 + rb, R - 1) * (long)Hx * W;
+#pragma unroll
+    for (int k = 0; k < kGatherK; ++k) v[rb][k] = __ldg(src + off[k]);
+  }
 #pragma unroll
   for (int rb = 0; rb < 4; ++rb) {
     const long r = r0 + rb;
-    if (r >= R) break;
-    const float* src = g1 + r * (long)Hx * W;
-    float v[kGatherK];
-#pragma unroll
-    for (int k = 0; k < kGatherK; ++k) v[k] = __ldg(src + off[k]);
     float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < kGatherK; ++k) acc = fmaf(wk[k], v[k], acc);
-    g2[r * (long)H * W + hw] = acc;
+    for (int k = 0; k < kGatherK; ++k) acc = fmaf(wk[k], v[rb][k], acc);
+    if (r < R) g2[r * (long)H * W + hw] = acc;
   }
 }
 
 // g2[bc][zd][h*w] -> dll[bc][d][P] (padding columns zeroed); grid (ceil(P / 256), D, nbc)
 template <int kGatherK>
 __global__ void __launch_bounds__(256) k_head_bwd_d_gather(const float* __restrict__ g2, float* __restrict__ dll, InterpDev t,
-                                                           long P) {
+                                                           long P, long nbc) {
   __shared__ float swk[kGatherK];
   __shared__ int ss0;
   const int W = t.lo[2], H = t.lo[1], D = t.lo[0], Dx = t.hi[0];
@@ -430,21 +433,28 @@ __global__ void __launch_bounds__(256) k_head_bwd_d_gather(const float* __restri
   __syncthreads();
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= P) return;
-  const long bc = blockIdx.z;
-  float* dst = dll + (bc * D + d) * P + p;
+  const long bc0 = (long)blockIdx.z * 4;  // four (b, c) slices per thread: 4 x K loads in flight, one weight prologue
   const int HW = H * W;
   if (p >= HW) {
-    *dst = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (bc0 + j < nbc) dll[((bc0 + j) * D + d) * P + p] = 0.f;
     return;
   }
-  const float* src = g2 + bc * (long)Dx * HW + p;
-  float v[kGatherK];
+  float v[4][kGatherK];
 #pragma unroll
-  for (int k = 0; k < kGatherK; ++k) v[k] = __ldg(src + (long)min(ss0 + k, Dx - 1) * HW);
-  float acc = 0.f;
+  for (int j = 0; j < 4; ++j) {
+    const float* src = g2 + min(bc0 + j, nbc - 1) * (long)Dx * HW + p;
 #pragma unroll
-  for (int k = 0; k < kGatherK; ++k) acc = fmaf(swk[k], v[k], acc);
-  *dst = acc;
+    for (int k = 0; k < kGatherK; ++k) v[j][k] = __ldg(src + (long)min(ss0 + k, Dx - 1) * HW);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < kGatherK; ++k) acc = fmaf(swk[k], v[j][k], acc);
+    if (bc0 + j < nbc) dll[((bc0 + j) * D + d) * P + p] = acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ losses
@@ -1361,11 +1371,11 @@ static int head_backward_passes(const void* th, const InterpDev& t, float* g1, f
     HNO_LAUNCH_CHECK();
   }
   if (gd) {
-    dim3 grid(ceil_div(P, 256), t.lo[0], (unsigned)nbc);
+    dim3 grid(ceil_div(P, 256), t.lo[0], (unsigned)ceil_div(nbc, 4));
     if (kd <= 4)
-      k_head_bwd_d_gather<4><<<grid, 256, 0, st>>>(g2, dll, t, P);
+      k_head_bwd_d_gather<4><<<grid, 256, 0, st>>>(g2, dll, t, P, nbc);
     else
-      k_head_bwd_d_gather<6><<<grid, 256, 0, st>>>(g2, dll, t, P);
+      k_head_bwd_d_gather<6><<<grid, 256, 0, st>>>(g2, dll, t, P, nbc);
     HNO_LAUNCH_CHECK();
   } else {
     dim3 grid(ceil_div(P, 256), t.lo[0], (unsigned)nbc);
