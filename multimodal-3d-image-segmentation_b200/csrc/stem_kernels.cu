@@ -185,14 +185,24 @@ __global__ void __launch_bounds__(256, 3) k_stem_wgrad_pipe(const float* __restr
   }
   // loader role of this thread: voxel tid & 127 of the tile, half (tid >> 7) of the rows
   const int lv = tid & (TV - 1), lh = tid >> 7;
-  auto issue = [&](long tile, float* dst) {
-    const int b = (int)(tile / tiles_per_sample);
-    const long s = (tile - (long)b * tiles_per_sample) * TV + lv;
+  // Address arithmetic of the gather is kept to one integer add, one widening add and one select per tap (the first version
+  // spent 13 integer instructions per cp.async, more than the weight-gradient math of the tile): the 8 tap offsets are
+  // constants of the launch, the in-bounds mask is 2 + 2 + 2 comparisons per voxel.
+  int toff[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) toff[t] = (t >> 2) * (int)g.HWx + ((t >> 1) & 1) * g.Wx + (t & 1);
+  const long xcs = (long)g.Dx * g.HWx;  // channel stride of x
+  const int P32 = (int)g.P, S32 = (int)g.S;  // 32-bit index arithmetic (the launcher checks the ranges): the 64-bit
+                                             // divisions of the first version were two subroutine-sized sequences per tile
+  auto issue = [&](long tile64, float* dst) {
+    const unsigned tile = (unsigned)tile64;
+    const int b = (int)(tile / (unsigned)tiles_per_sample);
+    const int s = (int)(tile - (unsigned)b * (unsigned)tiles_per_sample) * TV + lv;
     int d = 0, h = 0, w = 0;
     bool live = false;
-    if (s < g.S) {
-      d = (int)(s / g.P);
-      const int p = (int)(s - (long)d * g.P);
+    if (s < S32) {
+      d = s / P32;
+      const int p = s - d * P32;
       if (p < g.H * g.W) {
         live = true;
         h = p / g.W;
@@ -201,20 +211,45 @@ __global__ void __launch_bounds__(256, 3) k_stem_wgrad_pipe(const float* __restr
     }
     const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst) + 4u * lv;
     const float* dp = dpre + ((long)b * F + lh * (F / 2)) * g.S + (live ? s : 0);
+    const int dsz = live ? 4 : 0;
 #pragma unroll
     for (int o = 0; o < F / 2; ++o)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * ((lh * (F / 2) + o) * TVS)),
-                   "l"(dp + (long)o * g.S), "r"(live ? 4 : 0)
+                   "l"(dp + (long)o * g.S), "r"(dsz)
                    : "memory");
+    // tap (kd, kh, kw) reads x[2d - 1 + kd][2h - 1 + kh][2w - 1 + kw]
+    const int zd = 2 * d - 1, zh = 2 * h - 1, zw = 2 * w - 1;
+    const bool okd[2] = {live && zd >= 0, live && zd + 1 < g.Dx};
+    const bool okh[2] = {zh >= 0, zh + 1 < g.Hx};
+    const bool okw[2] = {zw >= 0, zw + 1 < g.Wx};
+    const int base = zd * (int)g.HWx + zh * g.Wx + zw;  // may be negative at the border: only used when the tap is inside
+    const float* xb = x + (long)b * CIN * xcs;
+    if constexpr ((Q / 2) % 8 == 0) {
+      // even channel counts: this thread's half of the rows is whole channels, so the tap index is a compile-time constant
+      // and the shared-memory / channel offsets are immediates on two per-tile bases
+      const unsigned dq = d0 + 4u * ((F + lh * (Q / 2)) * TVS);
+      const float* xh = xb + (long)(lh * (CIN / 2)) * xcs;
 #pragma unroll
-    for (int qq = 0; qq < Q / 2; ++qq) {
-      const int q = lh * (Q / 2) + qq, i = q >> 3, t = q & 7;
-      const int zd = 2 * d - 1 + (t >> 2), zh = 2 * h - 1 + ((t >> 1) & 1), zw = 2 * w - 1 + (t & 1);
-      const bool inb = live && zd >= 0 && zd < g.Dx && zh >= 0 && zh < g.Hx && zw >= 0 && zw < g.Wx;
-      const float* src = x + ((long)b * CIN + i) * g.Dx * g.HWx + (inb ? (zd * (int)g.HWx + zh * g.Wx + zw) : 0);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * ((F + q) * TVS)), "l"(src),
-                   "r"(inb ? 4 : 0)
-                   : "memory");
+      for (int ii = 0; ii < CIN / 2; ++ii) {
+        const float* xi = xh + (long)ii * xcs;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const bool inb = okd[t >> 2] && okh[(t >> 1) & 1] && okw[t & 1];
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dq + 4u * ((ii * 8 + t) * TVS)),
+                       "l"(xi + (inb ? base + toff[t] : 0)), "r"(inb ? 4 : 0)
+                       : "memory");
+        }
+      }
+    } else {
+#pragma unroll
+      for (int qq = 0; qq < Q / 2; ++qq) {
+        const int q = lh * (Q / 2) + qq, i = q >> 3, t = q & 7;
+        const bool inb = okd[t >> 2] && okh[(t >> 1) & 1] && okw[t & 1];
+        const float* src = xb + (long)i * xcs + (inb ? base + toff[t] : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * ((F + q) * TVS)), "l"(src),
+                     "r"(inb ? 4 : 0)
+                     : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -332,6 +367,7 @@ static int stem_bwd_t(const float* dpre, const float* x, float* dweight, float* 
     constexpr int TV = 128;
     const int tps = ceil_div(g.S, TV);
     const long total = (long)tps * B;
+    HNO_CHECK(g.S + TV < (1L << 31) && total < (1L << 31), "stem_backward: volume too large for 32-bit tile indices");
     grid = (int)(total < gmax ? total : gmax);
     const size_t smem = (size_t)2 * (F + Q) * (TV + 4) * sizeof(float) + (8 * F + 8) * sizeof(float);
     auto kern = k_stem_wgrad_pipe<CIN, F>;
