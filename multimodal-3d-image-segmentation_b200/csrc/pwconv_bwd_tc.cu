@@ -505,9 +505,9 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
       uint32_t ph = 0;
       for (int q = 0; q < NSRC; ++q) tma_prefetch_desc(&maps.m[q]);
       for (int ti = 0; ti < my_tiles; ++ti) {
-        const long tile = blockIdx.x + (long)ti * gridDim.x;
-        const int b = (int)(tile / p.tiles_per_sample);
-        const int s0 = (int)((tile - (long)b * p.tiles_per_sample) * 128);
+        const unsigned tile = blockIdx.x + (unsigned)ti * gridDim.x;  // 32-bit: total_tiles and S < 2^31 (launcher)
+        const int b = (int)(tile / (unsigned)p.tiles_per_sample);
+        const int s0 = (int)((tile - (unsigned)b * (unsigned)p.tiles_per_sample) * 128u);
 #pragma unroll 1
         for (int q = 0; q < NSRC; ++q) {
           if (it >= NST) {
@@ -532,10 +532,13 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
 #pragma unroll
     for (int o = 0; o < C / 2; ++o) accB2[o] = make_float2(0.f, 0.f);
 
+    // 32-bit index arithmetic (total_tiles, S < 2^31 are checked by the launcher): the 64-bit division / modulo of the
+    // first version were ~150 instructions per tile and thread
+    const unsigned P32 = (unsigned)p.P, HW32 = (unsigned)p.HW;
     auto voxel_of = [&](int ti, int& b, long& sv) {
-      const long tile = blockIdx.x + (long)ti * gridDim.x;
-      b = (int)(tile / p.tiles_per_sample);
-      sv = (tile - (long)b * p.tiles_per_sample) * 128 + tid;
+      const unsigned tile = blockIdx.x + (unsigned)ti * gridDim.x;
+      b = (int)(tile / (unsigned)p.tiles_per_sample);
+      sv = (long)((tile - (unsigned)b * (unsigned)p.tiles_per_sample) * 128u + (unsigned)tid);
     };
     // d(pre) of tile ti: registers -> tensor memory (two TF32 terms) and, in fp32, over the dy stage it came from (a thread
     // owns its voxel's column, so the overwrite is race free; a separate d(pre) buffer cost two ring stages and the kernel
@@ -544,7 +547,7 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
       int b;
       long sv;
       voxel_of(ti, b, sv);
-      const bool live = sv < p.S && (sv % p.P) < p.HW;
+      const bool live = sv < p.S && ((unsigned)sv % P32) < HW32;
       const int buf = ti & 1;
       const B2Cursor cy = cur.plus(1, NST);
       mbar_wait(&bar_full[cur.s], cur.ph);
