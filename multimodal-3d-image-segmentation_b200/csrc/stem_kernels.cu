@@ -43,8 +43,8 @@ __global__ void __launch_bounds__(256) k_stem_fwd(const float* __restrict__ x, c
   if (s >= g.S) return;
   const int b = blockIdx.y;
   float* po = out + (long)b * F * g.S + s;
-  const int d = (int)(s / g.P);
-  const int p = (int)(s - (long)d * g.P);
+  const int d = (int)s / (int)g.P;  // S < 2^31 (make_geom)
+  const int p = (int)s - d * (int)g.P;
   if (p >= g.H * g.W) {
 #pragma unroll
     for (int o = 0; o < F; ++o) po[(long)o * g.S] = 0.f;
@@ -330,6 +330,7 @@ static int make_geom(StemGeom* g, int Dx, int Hx, int Wx, long P) {
   HNO_CHECK(Dx >= 1 && Hx >= 1 && Wx >= 1, "stem: bad input size %dx%dx%d", Dx, Hx, Wx);
   HNO_CHECK((long)Dx * Hx * Wx < (1L << 31), "stem: input volume too large for 32-bit offsets");
   HNO_CHECK(P >= (long)g->H * g->W, "stem: plane pitch %ld < H*W = %ld", P, (long)g->H * g->W);
+  HNO_CHECK(g->S < (1L << 31) - 256, "stem: output volume too large for 32-bit voxel indices");
   return 0;
 }
 
