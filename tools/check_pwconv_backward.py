@@ -1,6 +1,6 @@
 import sys, os
 import numpy as np, torch, torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multimodal_3d_image_segmentation_b200 import ops
 cuda = torch.device('cuda:0')
 def rel(a, b):
