@@ -609,7 +609,13 @@ __global__ void __launch_bounds__(kB2Threads, 2) k_pwconv_bwd_split(const BtDev 
         fetch_old(0, oldv[0]);
         if (CI > 8) fetch_old(8, oldv[1]);
       }
-      if (p.flags & 4) mbar_wait(&bar_full[c1.s], c1.ph);
+      // the voxel warps read in1 only for the selu'(in1) factor and in2 never, but they release every stage like the other
+      // group: arrive strictly after the stage has landed, so that an arrival can never be counted in the slot's previous phase
+      mbar_wait(&bar_full[c1.s], c1.ph);
+      if (CI2 > 0) {
+        const B2Cursor c2w = c1.plus(1, NST);
+        mbar_wait(&bar_full[c2w.s], c2w.ph);
+      }
       mbar_wait(&bar_accfull, (uint32_t)(ti & 1));
       tc_fence_after_sync();
       {
