@@ -149,6 +149,23 @@ int hno_complex_modemix_backward(const float* da, const float* db, const float* 
                                  int accumulate_dw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fourier spectral layer, shared complex weights (FNOSeg, BASELINE config 3): the mode-domain step between the two transforms
+ *   replaces nets/fourier_operator.py:155, 165-209 (corner slicing of the rfftn output, 'oi,bi...->bo...' with
+ *            w_real + i w_imag, zero-padded re-assembly before irfftn), evaluated on Hartley coefficients:
+ *   z [B][ci][MS] = (1/N) DHT of the input on the symmetric mode set S (hno_dht3_forward);  lin_k / lin_n [MK]: positions in S
+ *   of every rfft half-grid mode k and of its mirror image N - k;  ck [MK]: 1 on the k_w = 0 plane, else 2.
+ *   re = (z[k] + z[N-k]) / 2, im = (z[N-k] - z[k]) / 2;  a + i b = (w_real + i w_imag)(re + i im);
+ *   hp[k] += ck (a - b) / 2,  hp[N-k] += ck (a + b) / 2  ->  hp [B][co][MS], whose hno_dht3_adjoint is the layer output.
+ *   ci, co multiples of 4.  backward: dz and the (dw_real, dw_imag) pair are optional; workspace: hno_fourier_mix_workspace_bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t hno_fourier_mix_workspace_bytes(int ci, int co, long MK, int B);
+int hno_fourier_mix_forward(const float* z, const float* w_real, const float* w_imag, const int* lin_k, const int* lin_n,
+                            const float* ck, float* hp, int B, int ci, int co, long MK, long MS, void* stream);
+int hno_fourier_mix_backward(const float* dhp, const float* z, const float* w_real, const float* w_imag, const int* lin_k,
+                             const int* lin_n, const float* ck, float* dz, float* dw_real, float* dw_imag, void* workspace,
+                             int B, int ci, int co, long MK, long MS, int accumulate_dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The n_XS shared-weight mixes of one HNO-XS block as one launch
  *   replaces nets/hnosegxs.py:261-262 (loop over NeuralOperatorBlock.forward :307-329) with
  *            nets/hartley_operator.py:287-292 (weights_type 'shared'):  z_l = selu(W_l z_{l-1} + z_{l-1}), l = 1..L

@@ -23,7 +23,7 @@ LIB = os.path.join(HERE, 'libhno_b200.so')
 
 SOURCES = ['api.cu', 'dht_plan.cu', 'dht_kernels.cu', 'dht_mid.cu', 'pwconv_kernels.cu', 'pwconv_bwd_tc.cu', 'stem_kernels.cu', 'head_kernels.cu',
            'modes_kernels.cu', 'modechain_kernels.cu', 'input_kernels.cu', 'tc_stream.cu', 'gemm_tc.cu', 'tc_analysis.cu',
-           'mha_kernels.cu', 'dsconv_kernels.cu', 'spectral_core.cu']
+           'mha_kernels.cu', 'dsconv_kernels.cu', 'spectral_core.cu', 'fourier_kernels.cu']
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',

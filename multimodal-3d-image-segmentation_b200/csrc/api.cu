@@ -103,6 +103,11 @@ int ce_loss_forward(const float*, const float*, const uint8_t*, float*, void*, i
 int ce_loss_backward(const float*, const float*, const uint8_t*, const float*, float*, int, int, long, cudaStream_t);
 int head_loss_backward(const void*, const void*, const float*, const uint8_t*, const float*, const float*, float*,
                        void*, int, int, long, cudaStream_t);
+size_t fourier_mix_workspace_bytes(int, int, long, int);
+int fourier_mix_forward(const float*, const float*, const float*, const int*, const int*, const float*, float*, int, int, int, long,
+                        long, cudaStream_t);
+int fourier_mix_backward(const float*, const float*, const float*, const float*, const int*, const int*, const float*, float*,
+                         float*, float*, void*, int, int, int, long, long, int, cudaStream_t);
 int complex_modemix_forward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, long,
                             cudaStream_t);
 int complex_modemix_backward(const float*, const float*, const float*, const float*, const float*, const float*, float*,
@@ -290,6 +295,20 @@ int hno_complex_modemix_backward(const float* da, const float* db, const float* 
                                  float* dw_imag, int B, int ci, int co, long M, int accumulate_dw, void* stream) {
   return complex_modemix_backward(da, db, re, im, w_real, w_imag, dre, dim, dw_real, dw_imag, B, ci, co, M,
                                   accumulate_dw, ST(stream));
+}
+
+size_t hno_fourier_mix_workspace_bytes(int ci, int co, long MK, int B) { return fourier_mix_workspace_bytes(ci, co, MK, B); }
+
+int hno_fourier_mix_forward(const float* z, const float* w_real, const float* w_imag, const int* lin_k, const int* lin_n,
+                            const float* ck, float* hp, int B, int ci, int co, long MK, long MS, void* stream) {
+  return fourier_mix_forward(z, w_real, w_imag, lin_k, lin_n, ck, hp, B, ci, co, MK, MS, ST(stream));
+}
+
+int hno_fourier_mix_backward(const float* dhp, const float* z, const float* w_real, const float* w_imag, const int* lin_k,
+                             const int* lin_n, const float* ck, float* dz, float* dw_real, float* dw_imag, void* workspace,
+                             int B, int ci, int co, long MK, long MS, int accumulate_dw, void* stream) {
+  return fourier_mix_backward(dhp, z, w_real, w_imag, lin_k, lin_n, ck, dz, dw_real, dw_imag, workspace, B, ci, co, MK, MS,
+                              accumulate_dw, ST(stream));
 }
 
 size_t hno_ce_loss_workspace_bytes(int B) { return ce_loss_workspace_bytes(B); }

@@ -100,15 +100,24 @@ class FourierOperator(Module):
             kshape = tuple(len(ax[0]) for ax in axes)
             ck = torch.full((kshape[2],), 2.0)
             ck[[i for i, k in enumerate(axes[2][0]) if k == 0]] = 1.0  # the k_w = 0 plane counts once in the c2r inverse
-            g = self._geom_cache[key] = (plan, lin(2), lin(3), kshape, tuple(ls), ck.view(1, 1, 1, 1, -1).to(device))
+            lk, ln = lin(2), lin(3)
+            ck5 = ck.view(1, 1, 1, 1, -1)
+            # flat tables of the fused mode-domain kernel (hno_fourier_mix_*): int32 positions of k / N - k in S, c_k per K entry
+            fused = (lk.to(torch.int32), ln.to(torch.int32),
+                     ck5.expand((1, 1) + kshape).reshape(-1).contiguous().to(device=device, dtype=torch.float32))
+            g = self._geom_cache[key] = (plan, lk, ln, kshape, tuple(ls), ck5.to(device), fused)
         return g
 
     def spectral(self, x):
         """x -> (H', plan): the Hartley coefficients on S whose unnormalised inverse DHT is the layer's output."""
         x = x.contiguous()
         B = x.shape[0]
-        plan, lin_k, lin_n, kshape, ls, ck = self._geometry(tuple(x.shape[2:]), x.device)
+        plan, lin_k, lin_n, kshape, ls, ck, fused = self._geometry(tuple(x.shape[2:]), x.device)
         z = ops.TruncatedDHT.apply(x, plan).reshape(B, self.in_channels, -1)  # (1/N) DHT on S
+        if self.weights_type != 'individual' and self.in_channels % 4 == 0 and self.out_channels % 4 == 0:
+            # one kernel per direction instead of index_select x 2 + elementwise + two channel mixes + index_add x 2
+            hp = ops.FourierMixShared.apply(z, self.weight_real, self.weight_imag, *fused)
+            return hp.reshape((B, self.out_channels) + ls), plan
         hk = z.index_select(2, lin_k).reshape((B, self.in_channels) + kshape)
         hn = z.index_select(2, lin_n).reshape((B, self.in_channels) + kshape)
         re = ((hk + hn) * 0.5).contiguous()
