@@ -350,6 +350,10 @@ class TransSegEngine:
             return 'hartley'
         if isinstance(op, HartleyMultiHeadAttention) and op.use_transform:
             return 'mha'
+        from .nets.fourier_operator import FourierOperator
+        if (isinstance(op, FourierOperator) and op.weights_type == 'shared' and op.bias is None
+                and op.in_channels % 4 == 0 and op.out_channels % 4 == 0):
+            return 'fourier'  # FNOSeg: hno_fourier_mix_* between the two transforms on the symmetric mode set
         return None
 
     @classmethod
@@ -367,6 +371,8 @@ class TransSegEngine:
         op = blk.op
         if kind == 'hartley':
             return [op.weight]
+        if kind == 'fourier':
+            return [op.weight_real, op.weight_imag]
         ps = [op.weight_query, op.weight_key, op.weight_value, op.weight_out]
         if op.use_bias:
             ps += [op.bias_query, op.bias_key, op.bias_value, op.bias_out]
@@ -417,13 +423,20 @@ class TransSegEngine:
             op = blk.op
             if kind == 'mha':
                 assert all(s >= 2 * mm for s, mm in zip((D, H, W), op.num_modes))  # reference hartley_mha.py:165-172
-            plan = get_crop_plan((D, H, W), op.num_modes, dev)
+            if kind == 'fourier':
+                plan, _, _, _, ls, _, rec.tables = op._geometry((D, H, W), dev)
+            else:
+                plan = get_crop_plan((D, H, W), op.num_modes, dev)
             rec.plan = plan
             t = ops.pwconv_forward(cur, None, _w2(blk.conv_branch), blk.conv_branch.bias, 0, False)
             z = ops.dht3_forward(cur, plan, 1.0 / plan.n_voxels)
             if kind == 'hartley':
                 zmix = ops.pwconv_forward(z, None, op.weight, None, 1, False)  # mix + SELU on the retained modes
                 rec.z, rec.zmix = z, zmix
+            elif kind == 'fourier':
+                rec.z = z.reshape(z.shape[0], z.shape[1], -1)
+                zmix = ops.fourier_mix_forward(rec.z, op.weight_real, op.weight_imag, *rec.tables)
+                zmix = zmix.reshape((z.shape[0], op.out_channels) + tuple(ls))
             else:
                 def flat(b):
                     return None if b is None else b.reshape(b.shape[1], b.shape[2]).contiguous()
@@ -487,6 +500,12 @@ class TransSegEngine:
             if rec.kind == 'hartley':
                 dz, _, g_w, _ = ops.pwconv_backward(dzmix, rec.zmix, rec.z, None, blk.op.weight, 1, False, has_bias=False)
                 g_op = [g_w]
+            elif rec.kind == 'fourier':
+                op = blk.op
+                dz, g_wr, g_wi = ops.fourier_mix_backward(dzmix.reshape(dzmix.shape[0], dzmix.shape[1], -1), rec.z,
+                                                          op.weight_real, op.weight_imag, *rec.tables)
+                dz = dz.reshape((dz.shape[0], dz.shape[1]) + tuple(dzmix.shape[2:]))
+                g_op = [g_wr, g_wi]
             else:
                 g = ops.hartley_attention_backward(dzmix, rec.att)
                 dz = g[0]

@@ -414,6 +414,38 @@ class ComplexModeMix(torch.autograd.Function):
         return dre, dim, dwr, dwi
 
 
+def fourier_mix_forward(z, wr, wi, lin_k, lin_n, ck):
+    """hno_fourier_mix_forward: z [B, ci, MS] -> hp [B, co, MS] (see FourierMixShared)."""
+    _require_cuda(z, 'z')
+    z, wr, wi = z.contiguous(), wr.contiguous(), wi.contiguous()
+    B, ci, MS = z.shape
+    co = wr.shape[0]
+    MK = lin_k.numel()
+    if tuple(wr.shape) != (co, ci) or wi.shape != wr.shape or lin_n.numel() != MK or ck.numel() != MK:
+        raise ValueError(f'fourier_mix: weights {tuple(wr.shape)} / index tables do not match z {tuple(z.shape)}')
+    if lin_k.dtype != torch.int32 or lin_n.dtype != torch.int32 or ck.dtype != torch.float32:
+        raise TypeError('fourier_mix: lin_k / lin_n must be int32 and ck float32')
+    hp = torch.empty((B, co, MS), dtype=torch.float32, device=z.device)
+    call('hno_fourier_mix_forward', ptr(z), ptr(wr), ptr(wi), ptr(lin_k), ptr(lin_n), ptr(ck), ptr(hp), B, ci, co, MK, MS,
+         stream_ptr())
+    return hp
+
+
+def fourier_mix_backward(dhp, z, wr, wi, lin_k, lin_n, ck, need_x=True, need_w=True):
+    """hno_fourier_mix_backward -> (dz, dw_real, dw_imag); entries not asked for are None."""
+    z, wr, wi = z.contiguous(), wr.contiguous(), wi.contiguous()
+    B, ci, MS = z.shape
+    co = wr.shape[0]
+    MK = lin_k.numel()
+    dz = torch.empty_like(z) if need_x else None
+    dwr = torch.empty_like(wr) if need_w else None
+    dwi = torch.empty_like(wi) if need_w else None
+    ws = workspace(_lib.load().hno_fourier_mix_workspace_bytes(ci, co, MK, B), z.device, 'fmix') if need_w else None
+    call('hno_fourier_mix_backward', ptr(dhp.contiguous()), ptr(z), ptr(wr), ptr(wi), ptr(lin_k), ptr(lin_n), ptr(ck),
+         ptr(dz), ptr(dwr), ptr(dwi), ptr(ws), B, ci, co, MK, MS, 0, stream_ptr())
+    return dz, dwr, dwi
+
+
 class FourierMixShared(torch.autograd.Function):
     """Mode-domain step of FourierOperator with shared complex weights (reference nets/fourier_operator.py:155, 165-209) on
     the Hartley coefficients z [B, ci, MS] of the symmetric mode set: Re / Im split over the (k, N - k) pairs, complex
@@ -421,34 +453,15 @@ class FourierMixShared(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, wr, wi, lin_k, lin_n, ck):
-        _require_cuda(z, 'z')
-        z, wr, wi = z.contiguous(), wr.contiguous(), wi.contiguous()
-        B, ci, MS = z.shape
-        co = wr.shape[0]
-        MK = lin_k.numel()
-        if tuple(wr.shape) != (co, ci) or wi.shape != wr.shape or lin_n.numel() != MK or ck.numel() != MK:
-            raise ValueError(f'FourierMixShared: weights {tuple(wr.shape)} / index tables do not match z {tuple(z.shape)}')
-        if lin_k.dtype != torch.int32 or lin_n.dtype != torch.int32 or ck.dtype != torch.float32:
-            raise TypeError('FourierMixShared: lin_k / lin_n must be int32 and ck float32')
-        hp = torch.empty((B, co, MS), dtype=torch.float32, device=z.device)
-        call('hno_fourier_mix_forward', ptr(z), ptr(wr), ptr(wi), ptr(lin_k), ptr(lin_n), ptr(ck), ptr(hp), B, ci, co, MK, MS,
-             stream_ptr())
+        hp = fourier_mix_forward(z, wr, wi, lin_k, lin_n, ck)
         ctx.save_for_backward(z, wr, wi, lin_k, lin_n, ck)
         return hp
 
     @staticmethod
     def backward(ctx, dhp):
         z, wr, wi, lin_k, lin_n, ck = ctx.saved_tensors
-        B, ci, MS = z.shape
-        co = wr.shape[0]
-        MK = lin_k.numel()
-        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
-        dwr = torch.empty_like(wr) if need_w else None
-        dwi = torch.empty_like(wi) if need_w else None
-        ws = workspace(_lib.load().hno_fourier_mix_workspace_bytes(ci, co, MK, B), z.device, 'fmix') if need_w else None
-        call('hno_fourier_mix_backward', ptr(dhp.contiguous()), ptr(z), ptr(wr), ptr(wi), ptr(lin_k), ptr(lin_n), ptr(ck),
-             ptr(dz), ptr(dwr), ptr(dwi), ptr(ws), B, ci, co, MK, MS, 0, stream_ptr())
+        dz, dwr, dwi = fourier_mix_backward(dhp, z, wr, wi, lin_k, lin_n, ck, ctx.needs_input_grad[0],
+                                            ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         return dz, dwr, dwi, None, None, None
 
 
@@ -891,7 +904,7 @@ class HartleyAttention(torch.autograd.Function):
 
 
 __all__ = ['dht3_forward', 'dht3_adjoint', 'TruncatedDHT', 'TruncatedIDHT', 'AddIDHTSelu', 'pwconv_forward', 'pwconv_backward',
-           'PointwiseConv', 'HartleyConv', 'ComplexModeMix', 'FourierMixShared', 'stem_forward', 'stem_backward', 'StemConv', 'head_forward',
+           'PointwiseConv', 'HartleyConv', 'ComplexModeMix', 'FourierMixShared', 'fourier_mix_forward', 'fourier_mix_backward', 'stem_forward', 'stem_backward', 'StemConv', 'head_forward',
            'head_backward', 'HeadUpsample', 'ProbabilityLoss', 'CrossEntropyOnProbabilities', 'ce_loss_forward',
            'ce_loss_backward', 'LOSS_DEFAULT_PARAM', 'head_loss_forward', 'head_loss_backward',
            'get_crop_plan', 'get_interp_tables', 'workspace', 'LOSS_KINDS', 'HartleyAttention', 'hartley_attention_forward',
