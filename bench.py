@@ -48,6 +48,12 @@ SPECS = {
                     transform_type='Fourier'),
         metric='FNOSeg train volumes/s @4x240x240x155', what="NeuralOperatorSeg(4,4,24,24,(10,14,14),'Fourier')",
         act_gb='~30 GB'),
+    'fno_train': dict(  # experiments/config_files/config_fno.ini (per-mode complex weights, 15.9 M parameters)
+        kind='train', model='NeuralOperatorSeg', volume=VOLUME,
+        kwargs=dict(in_channels=4, out_channels=4, filters=24, num_transform_blocks=24, num_modes=(10, 14, 14),
+                    transform_type='Fourier', weights_type='individual'),
+        metric='FNO train volumes/s @4x240x240x155', what="NeuralOperatorSeg(4,4,24,24,(10,14,14),'Fourier','individual')",
+        act_gb='~30 GB'),
     'mha_train': dict(  # BASELINE config 5; hyper-parameters of tensorflow/experiments/config_files/config_hartleymha.ini:58-69
         kind='train', model='HartleyMHASeg', volume=VOLUME,
         kwargs=dict(in_channels=4, out_channels=4, filters=12, num_transform_blocks=16, num_heads=4,

@@ -156,14 +156,16 @@ int hno_complex_modemix_backward(const float* da, const float* db, const float* 
  *   of every rfft half-grid mode k and of its mirror image N - k;  ck [MK]: 1 on the k_w = 0 plane, else 2.
  *   re = (z[k] + z[N-k]) / 2, im = (z[N-k] - z[k]) / 2;  a + i b = (w_real + i w_imag)(re + i im);
  *   hp[k] += ck (a - b) / 2,  hp[N-k] += ck (a + b) / 2  ->  hp [B][co][MS], whose hno_dht3_adjoint is the layer output.
- *   ci, co multiples of 4.  backward: dz and the (dw_real, dw_imag) pair are optional; workspace: hno_fourier_mix_workspace_bytes.
+ *   individual == 0: shared weights w_* [co][ci];  individual != 0: per-mode weights w_* [co][ci][MK] (config_fno.ini, :165-187).
+ *   ci, co multiples of 4.  backward: dz and the (dw_real, dw_imag) pair are optional; workspace (shared weights only):
+ *   hno_fourier_mix_workspace_bytes.
  * ------------------------------------------------------------------------------------------ */
 size_t hno_fourier_mix_workspace_bytes(int ci, int co, long MK, int B);
 int hno_fourier_mix_forward(const float* z, const float* w_real, const float* w_imag, const int* lin_k, const int* lin_n,
-                            const float* ck, float* hp, int B, int ci, int co, long MK, long MS, void* stream);
+                            const float* ck, float* hp, int B, int ci, int co, long MK, long MS, int individual, void* stream);
 int hno_fourier_mix_backward(const float* dhp, const float* z, const float* w_real, const float* w_imag, const int* lin_k,
                              const int* lin_n, const float* ck, float* dz, float* dw_real, float* dw_imag, void* workspace,
-                             int B, int ci, int co, long MK, long MS, int accumulate_dw, void* stream);
+                             int B, int ci, int co, long MK, long MS, int individual, int accumulate_dw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * The n_XS shared-weight mixes of one HNO-XS block as one launch

@@ -52,8 +52,8 @@ SIGNATURES = {
     'hno_complex_modemix_forward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _P]),
     'hno_complex_modemix_backward': (_I, [_P] * 10 + [_I, _I, _I, _L, _I, _P]),
     'hno_fourier_mix_workspace_bytes': (_Z, [_I, _I, _L, _I]),
-    'hno_fourier_mix_forward': (_I, [_P] * 7 + [_I, _I, _I, _L, _L, _P]),
-    'hno_fourier_mix_backward': (_I, [_P] * 11 + [_I, _I, _I, _L, _L, _I, _P]),
+    'hno_fourier_mix_forward': (_I, [_P] * 7 + [_I, _I, _I, _L, _L, _I, _P]),
+    'hno_fourier_mix_backward': (_I, [_P] * 11 + [_I, _I, _I, _L, _L, _I, _I, _P]),
     'hno_stem_supported': (_I, [_I, _I]),
     'hno_stem_forward': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _P]),
     'hno_stem_backward_workspace_bytes': (_Z, [_I, _I]),

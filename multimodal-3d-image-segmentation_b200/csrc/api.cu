@@ -105,9 +105,9 @@ int head_loss_backward(const void*, const void*, const float*, const uint8_t*, c
                        void*, int, int, long, cudaStream_t);
 size_t fourier_mix_workspace_bytes(int, int, long, int);
 int fourier_mix_forward(const float*, const float*, const float*, const int*, const int*, const float*, float*, int, int, int, long,
-                        long, cudaStream_t);
+                        long, int, cudaStream_t);
 int fourier_mix_backward(const float*, const float*, const float*, const float*, const int*, const int*, const float*, float*,
-                         float*, float*, void*, int, int, int, long, long, int, cudaStream_t);
+                         float*, float*, void*, int, int, int, long, long, int, int, cudaStream_t);
 int complex_modemix_forward(const float*, const float*, const float*, const float*, float*, float*, int, int, int, long,
                             cudaStream_t);
 int complex_modemix_backward(const float*, const float*, const float*, const float*, const float*, const float*, float*,
@@ -300,15 +300,15 @@ int hno_complex_modemix_backward(const float* da, const float* db, const float* 
 size_t hno_fourier_mix_workspace_bytes(int ci, int co, long MK, int B) { return fourier_mix_workspace_bytes(ci, co, MK, B); }
 
 int hno_fourier_mix_forward(const float* z, const float* w_real, const float* w_imag, const int* lin_k, const int* lin_n,
-                            const float* ck, float* hp, int B, int ci, int co, long MK, long MS, void* stream) {
-  return fourier_mix_forward(z, w_real, w_imag, lin_k, lin_n, ck, hp, B, ci, co, MK, MS, ST(stream));
+                            const float* ck, float* hp, int B, int ci, int co, long MK, long MS, int individual, void* stream) {
+  return fourier_mix_forward(z, w_real, w_imag, lin_k, lin_n, ck, hp, B, ci, co, MK, MS, individual, ST(stream));
 }
 
 int hno_fourier_mix_backward(const float* dhp, const float* z, const float* w_real, const float* w_imag, const int* lin_k,
                              const int* lin_n, const float* ck, float* dz, float* dw_real, float* dw_imag, void* workspace,
-                             int B, int ci, int co, long MK, long MS, int accumulate_dw, void* stream) {
+                             int B, int ci, int co, long MK, long MS, int individual, int accumulate_dw, void* stream) {
   return fourier_mix_backward(dhp, z, w_real, w_imag, lin_k, lin_n, ck, dz, dw_real, dw_imag, workspace, B, ci, co, MK, MS,
-                              accumulate_dw, ST(stream));
+                              individual, accumulate_dw, ST(stream));
 }
 
 size_t hno_ce_loss_workspace_bytes(int B) { return ce_loss_workspace_bytes(B); }

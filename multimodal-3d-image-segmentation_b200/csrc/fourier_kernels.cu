@@ -168,6 +168,123 @@ __global__ void __launch_bounds__(256) k_fmix_bwd_w(const float* __restrict__ dh
   }
 }
 
+// ---- per-mode ('individual') complex weights w[o][i][j], j = position in the half-grid K (config_fno.ini, reference
+//      fourier_operator.py:165-187): same three steps, the weights are read from global memory (coalesced along j) and the
+//      weight gradient has no reduction over the modes.
+__global__ void __launch_bounds__(kFmThreads) k_fmix_fwd_ind(const float* __restrict__ z, const float* __restrict__ wr,
+                                                             const float* __restrict__ wi, const int* __restrict__ lin_k,
+                                                             const int* __restrict__ lin_n, const float* __restrict__ ck,
+                                                             float* __restrict__ hp, int ci, int co, int MK, long MS) {
+  const int og = blockIdx.y, b = blockIdx.z;
+  const int j = blockIdx.x * kFmThreads + threadIdx.x;
+  if (j >= MK) return;
+  const int ik = __ldg(lin_k + j), in = __ldg(lin_n + j);
+  const float* zb = z + (long)b * ci * MS;
+  const float* wrj = wr + (long)og * kFmOG * ci * MK + j;
+  const float* wij = wi + (long)og * kFmOG * ci * MK + j;
+  float a[kFmOG], bb[kFmOG];
+#pragma unroll
+  for (int o = 0; o < kFmOG; ++o) a[o] = bb[o] = 0.f;
+#pragma unroll 2
+  for (int i = 0; i < ci; ++i) {
+    const float hk = __ldg(zb + (long)i * MS + ik), hn = __ldg(zb + (long)i * MS + in);
+    const float re = 0.5f * (hk + hn), im = 0.5f * (hn - hk);
+#pragma unroll
+    for (int o = 0; o < kFmOG; ++o) {
+      const float r = __ldg(wrj + ((long)o * ci + i) * MK), q = __ldg(wij + ((long)o * ci + i) * MK);
+      a[o] = fmaf(r, re, fmaf(-q, im, a[o]));
+      bb[o] = fmaf(q, re, fmaf(r, im, bb[o]));
+    }
+  }
+  const float c = 0.5f * __ldg(ck + j);
+  float* hb = hp + ((long)b * co + og * kFmOG) * MS;
+#pragma unroll
+  for (int o = 0; o < kFmOG; ++o) {
+    atomicAdd(hb + (long)o * MS + ik, c * (a[o] - bb[o]));
+    atomicAdd(hb + (long)o * MS + in, c * (a[o] + bb[o]));
+  }
+}
+
+__global__ void __launch_bounds__(kFmThreads) k_fmix_bwd_x_ind(const float* __restrict__ dhp, const float* __restrict__ wr,
+                                                               const float* __restrict__ wi, const int* __restrict__ lin_k,
+                                                               const int* __restrict__ lin_n, const float* __restrict__ ck,
+                                                               float* __restrict__ dz, int ci, int co, int MK, long MS) {
+  const int ig = blockIdx.y, b = blockIdx.z;
+  const int j = blockIdx.x * kFmThreads + threadIdx.x;
+  if (j >= MK) return;
+  const int ik = __ldg(lin_k + j), in = __ldg(lin_n + j);
+  const float c = 0.5f * __ldg(ck + j);
+  const float* dhb = dhp + (long)b * co * MS;
+  const float* wrj = wr + (long)ig * kFmOG * MK + j;
+  const float* wij = wi + (long)ig * kFmOG * MK + j;
+  float dre[kFmOG], dim[kFmOG];
+#pragma unroll
+  for (int i = 0; i < kFmOG; ++i) dre[i] = dim[i] = 0.f;
+#pragma unroll 2
+  for (int o = 0; o < co; ++o) {
+    float da, db;
+    fmix_dab(dhb, MS, o, ik, in, c, da, db);
+#pragma unroll
+    for (int i = 0; i < kFmOG; ++i) {
+      const float r = __ldg(wrj + ((long)o * ci + i) * MK), q = __ldg(wij + ((long)o * ci + i) * MK);
+      dre[i] = fmaf(r, da, fmaf(q, db, dre[i]));
+      dim[i] = fmaf(-q, da, fmaf(r, db, dim[i]));
+    }
+  }
+  float* zb = dz + ((long)b * ci + ig * kFmOG) * MS;
+#pragma unroll
+  for (int i = 0; i < kFmOG; ++i) {
+    atomicAdd(zb + (long)i * MS + ik, 0.5f * (dre[i] - dim[i]));
+    atomicAdd(zb + (long)i * MS + in, 0.5f * (dre[i] + dim[i]));
+  }
+}
+
+// grid (ceil(MK / 128), co / 4, ci / 4): a thread owns 4 x 4 (o, i) pairs of its mode and sums over the batch
+__global__ void __launch_bounds__(kFmThreads) k_fmix_bwd_w_ind(const float* __restrict__ dhp, const float* __restrict__ z,
+                                                               const int* __restrict__ lin_k, const int* __restrict__ lin_n,
+                                                               const float* __restrict__ ck, float* __restrict__ dwr,
+                                                               float* __restrict__ dwi, int B, int ci, int co, int MK, long MS,
+                                                               int accumulate) {
+  const int og = blockIdx.y, ig = blockIdx.z;
+  const int j = blockIdx.x * kFmThreads + threadIdx.x;
+  if (j >= MK) return;
+  const int ik = __ldg(lin_k + j), in = __ldg(lin_n + j);
+  const float c = 0.5f * __ldg(ck + j);
+  float gr[kFmOG][kFmOG], gi[kFmOG][kFmOG];
+#pragma unroll
+  for (int o = 0; o < kFmOG; ++o)
+#pragma unroll
+    for (int i = 0; i < kFmOG; ++i) gr[o][i] = gi[o][i] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* dhb = dhp + (long)b * co * MS;
+    const float* zb = z + ((long)b * ci + ig * kFmOG) * MS;
+    float da[kFmOG], db[kFmOG], re[kFmOG], im[kFmOG];
+#pragma unroll
+    for (int o = 0; o < kFmOG; ++o) fmix_dab(dhb, MS, og * kFmOG + o, ik, in, c, da[o], db[o]);
+#pragma unroll
+    for (int i = 0; i < kFmOG; ++i) {
+      const float hk = __ldg(zb + (long)i * MS + ik), hn = __ldg(zb + (long)i * MS + in);
+      re[i] = 0.5f * (hk + hn);
+      im[i] = 0.5f * (hn - hk);
+    }
+#pragma unroll
+    for (int o = 0; o < kFmOG; ++o)
+#pragma unroll
+      for (int i = 0; i < kFmOG; ++i) {
+        gr[o][i] = fmaf(da[o], re[i], fmaf(db[o], im[i], gr[o][i]));
+        gi[o][i] = fmaf(db[o], re[i], fmaf(-da[o], im[i], gi[o][i]));
+      }
+  }
+#pragma unroll
+  for (int o = 0; o < kFmOG; ++o)
+#pragma unroll
+    for (int i = 0; i < kFmOG; ++i) {
+      const long off = ((long)(og * kFmOG + o) * ci + ig * kFmOG + i) * MK + j;
+      dwr[off] = accumulate ? dwr[off] + gr[o][i] : gr[o][i];
+      dwi[off] = accumulate ? dwi[off] + gi[o][i] : gi[o][i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int fmix_check(int B, int ci, int co, long MK, long MS) {
   HNO_CHECK(B >= 1 && B <= 65535 && ci >= kFmOG && co >= kFmOG && ci % kFmOG == 0 && co % kFmOG == 0,
@@ -183,27 +300,40 @@ size_t fourier_mix_workspace_bytes(int ci, int co, long MK, int B) {
 }
 
 int fourier_mix_forward(const float* z, const float* wr, const float* wi, const int* lin_k, const int* lin_n, const float* ck,
-                        float* hp, int B, int ci, int co, long MK, long MS, cudaStream_t st) {
+                        float* hp, int B, int ci, int co, long MK, long MS, int individual, cudaStream_t st) {
   HNO_CHECK(z && wr && wi && lin_k && lin_n && ck && hp, "fourier_mix_forward: null pointer");
   if (fmix_check(B, ci, co, MK, MS)) return -1;
   HNO_CUDA(cudaMemsetAsync(hp, 0, (size_t)B * co * MS * sizeof(float), st));
   dim3 grid(ceil_div(MK, kFmThreads), co / kFmOG, B);
-  k_fmix_fwd<<<grid, kFmThreads, (size_t)2 * kFmOG * ci * sizeof(float), st>>>(z, wr, wi, lin_k, lin_n, ck, hp, ci, co, (int)MK, MS);
+  if (individual)
+    k_fmix_fwd_ind<<<grid, kFmThreads, 0, st>>>(z, wr, wi, lin_k, lin_n, ck, hp, ci, co, (int)MK, MS);
+  else
+    k_fmix_fwd<<<grid, kFmThreads, (size_t)2 * kFmOG * ci * sizeof(float), st>>>(z, wr, wi, lin_k, lin_n, ck, hp, ci, co, (int)MK, MS);
   HNO_LAUNCH_CHECK();
   return 0;
 }
 
 int fourier_mix_backward(const float* dhp, const float* z, const float* wr, const float* wi, const int* lin_k, const int* lin_n,
                          const float* ck, float* dz, float* dwr, float* dwi, void* ws, int B, int ci, int co, long MK, long MS,
-                         int accumulate_dw, cudaStream_t st) {
+                         int individual, int accumulate_dw, cudaStream_t st) {
   HNO_CHECK(dhp && z && wr && wi && lin_k && lin_n && ck, "fourier_mix_backward: null pointer");
   HNO_CHECK((dwr == nullptr) == (dwi == nullptr), "fourier_mix_backward: dw_real and dw_imag come as a pair");
   if (fmix_check(B, ci, co, MK, MS)) return -1;
   if (dz) {
     HNO_CUDA(cudaMemsetAsync(dz, 0, (size_t)B * ci * MS * sizeof(float), st));
     dim3 grid(ceil_div(MK, kFmThreads), ci / kFmOG, B);
-    k_fmix_bwd_x<<<grid, kFmThreads, (size_t)2 * kFmOG * co * sizeof(float), st>>>(dhp, wr, wi, lin_k, lin_n, ck, dz, ci, co, (int)MK, MS);
+    if (individual)
+      k_fmix_bwd_x_ind<<<grid, kFmThreads, 0, st>>>(dhp, wr, wi, lin_k, lin_n, ck, dz, ci, co, (int)MK, MS);
+    else
+      k_fmix_bwd_x<<<grid, kFmThreads, (size_t)2 * kFmOG * co * sizeof(float), st>>>(dhp, wr, wi, lin_k, lin_n, ck, dz, ci, co, (int)MK, MS);
     HNO_LAUNCH_CHECK();
+  }
+  if (dwr && individual) {
+    HNO_CHECK(ci / kFmOG <= 65535 && co / kFmOG <= 65535, "fourier_mix_backward: too many channels");
+    dim3 grid(ceil_div(MK, kFmThreads), co / kFmOG, ci / kFmOG);
+    k_fmix_bwd_w_ind<<<grid, kFmThreads, 0, st>>>(dhp, z, lin_k, lin_n, ck, dwr, dwi, B, ci, co, (int)MK, MS, accumulate_dw);
+    HNO_LAUNCH_CHECK();
+    return 0;
   }
   if (dwr) {
     HNO_CHECK(ws, "fourier_mix_backward: the weight gradient needs the workspace");

@@ -351,9 +351,9 @@ class TransSegEngine:
         if isinstance(op, HartleyMultiHeadAttention) and op.use_transform:
             return 'mha'
         from .nets.fourier_operator import FourierOperator
-        if (isinstance(op, FourierOperator) and op.weights_type == 'shared' and op.bias is None
+        if (isinstance(op, FourierOperator) and op.bias is None
                 and op.in_channels % 4 == 0 and op.out_channels % 4 == 0):
-            return 'fourier'  # FNOSeg: hno_fourier_mix_* between the two transforms on the symmetric mode set
+            return 'fourier'  # FNOSeg / FNO: hno_fourier_mix_* between the two transforms on the symmetric mode set
         return None
 
     @classmethod

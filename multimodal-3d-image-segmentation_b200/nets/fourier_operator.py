@@ -114,7 +114,7 @@ class FourierOperator(Module):
         B = x.shape[0]
         plan, lin_k, lin_n, kshape, ls, ck, fused = self._geometry(tuple(x.shape[2:]), x.device)
         z = ops.TruncatedDHT.apply(x, plan).reshape(B, self.in_channels, -1)  # (1/N) DHT on S
-        if self.weights_type != 'individual' and self.in_channels % 4 == 0 and self.out_channels % 4 == 0:
+        if self.in_channels % 4 == 0 and self.out_channels % 4 == 0:
             # one kernel per direction instead of index_select x 2 + elementwise + two channel mixes + index_add x 2
             hp = ops.FourierMixShared.apply(z, self.weight_real, self.weight_imag, *fused)
             return hp.reshape((B, self.out_channels) + ls), plan

@@ -421,13 +421,15 @@ def fourier_mix_forward(z, wr, wi, lin_k, lin_n, ck):
     B, ci, MS = z.shape
     co = wr.shape[0]
     MK = lin_k.numel()
-    if tuple(wr.shape) != (co, ci) or wi.shape != wr.shape or lin_n.numel() != MK or ck.numel() != MK:
+    individual = wr.ndim > 2  # per-mode weights [co, ci, *K grid] (config_fno.ini) instead of one [co, ci] matrix
+    if (tuple(wr.shape[:2]) != (co, ci) or wi.shape != wr.shape or lin_n.numel() != MK or ck.numel() != MK
+            or (individual and wr[0, 0].numel() != MK)):
         raise ValueError(f'fourier_mix: weights {tuple(wr.shape)} / index tables do not match z {tuple(z.shape)}')
     if lin_k.dtype != torch.int32 or lin_n.dtype != torch.int32 or ck.dtype != torch.float32:
         raise TypeError('fourier_mix: lin_k / lin_n must be int32 and ck float32')
     hp = torch.empty((B, co, MS), dtype=torch.float32, device=z.device)
     call('hno_fourier_mix_forward', ptr(z), ptr(wr), ptr(wi), ptr(lin_k), ptr(lin_n), ptr(ck), ptr(hp), B, ci, co, MK, MS,
-         stream_ptr())
+         int(individual), stream_ptr())
     return hp
 
 
@@ -440,9 +442,11 @@ def fourier_mix_backward(dhp, z, wr, wi, lin_k, lin_n, ck, need_x=True, need_w=T
     dz = torch.empty_like(z) if need_x else None
     dwr = torch.empty_like(wr) if need_w else None
     dwi = torch.empty_like(wi) if need_w else None
-    ws = workspace(_lib.load().hno_fourier_mix_workspace_bytes(ci, co, MK, B), z.device, 'fmix') if need_w else None
+    individual = wr.ndim > 2
+    ws = (workspace(_lib.load().hno_fourier_mix_workspace_bytes(ci, co, MK, B), z.device, 'fmix')
+          if need_w and not individual else None)
     call('hno_fourier_mix_backward', ptr(dhp.contiguous()), ptr(z), ptr(wr), ptr(wi), ptr(lin_k), ptr(lin_n), ptr(ck),
-         ptr(dz), ptr(dwr), ptr(dwi), ptr(ws), B, ci, co, MK, MS, 0, stream_ptr())
+         ptr(dz), ptr(dwr), ptr(dwi), ptr(ws), B, ci, co, MK, MS, int(individual), 0, stream_ptr())
     return dz, dwr, dwi
 
 

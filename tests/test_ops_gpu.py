@@ -531,28 +531,33 @@ def test_fused_spectral_chain_matches_separate_kernels(cuda, grid, modes):
         assert rel(dws[l], dws_ref[l]) < 2e-5, (l, rel(dws[l], dws_ref[l]))
 
 
+@pytest.mark.parametrize('wt', ['shared', 'individual'])
 @pytest.mark.parametrize('ci,co,shape,modes', [(4, 8, (12, 10, 9), (3, 2, 4)), (8, 4, (8, 8, 8), (4, 4, 4)),
                                                (24, 24, (20, 18, 14), (6, 5, 7))])
-def test_fourier_mix_shared_matches_eager_formula(cuda, ci, co, shape, modes):
-    """hno_fourier_mix_* (Re / Im split over the (k, N - k) pairs, complex channel mix, c_k re-assembly; the mode-domain
-    step of nets/fourier_operator.py:155, 165-209) against the same formula in fp64 torch, forward and all gradients,
-    incl. grids whose retained sets contain self-conjugate modes (n == 2 m)."""
+def test_fourier_mix_matches_eager_formula(cuda, ci, co, shape, modes, wt):
+    """hno_fourier_mix_* (Re / Im split over the (k, N - k) pairs, complex channel mix with shared or per-mode weights, c_k
+    re-assembly; the mode-domain step of nets/fourier_operator.py:155, 165-209) against the same formula in fp64 torch,
+    forward and all gradients, incl. grids whose retained sets contain self-conjugate modes (n == 2 m)."""
     from multimodal_3d_image_segmentation_b200 import nets, ops
-    op = nets.FourierOperator(ci, co, modes, device=cuda)
+    op = nets.FourierOperator(ci, co, modes, weights_type=wt, device=cuda)
     plan, lin_k, lin_n, kshape, ls, ck, fused = op._geometry(shape, cuda)
     MS = ls[0] * ls[1] * ls[2]
+    MK = lin_k.numel()
     g = torch.Generator().manual_seed(11)
     z = torch.randn(2, ci, MS, generator=g)
-    wr = torch.randn(co, ci, generator=g) * 0.3
-    wi = torch.randn(co, ci, generator=g) * 0.3
+    wshape = (co, ci) if wt == 'shared' else (co, ci) + tuple(kshape)
+    wr = torch.randn(wshape, generator=g) * 0.3
+    wi = torch.randn(wshape, generator=g) * 0.3
     gy = torch.randn(2, co, MS, generator=g)
     # fp64 reference
     zr, wrr, wir = (t.double().requires_grad_(True) for t in (z, wr, wi))
     lk, ln = lin_k.cpu(), lin_n.cpu()
     hk, hn = zr.index_select(2, lk), zr.index_select(2, ln)
     re, im = (hk + hn) * 0.5, (hn - hk) * 0.5
-    a = torch.einsum('oi,bim->bom', wrr, re) - torch.einsum('oi,bim->bom', wir, im)
-    b = torch.einsum('oi,bim->bom', wir, re) + torch.einsum('oi,bim->bom', wrr, im)
+    eq = 'oi,bim->bom' if wt == 'shared' else 'oim,bim->bom'
+    w2r, w2i = (wrr, wir) if wt == 'shared' else (wrr.reshape(co, ci, MK), wir.reshape(co, ci, MK))
+    a = torch.einsum(eq, w2r, re) - torch.einsum(eq, w2i, im)
+    b = torch.einsum(eq, w2i, re) + torch.einsum(eq, w2r, im)
     ckf = fused[2].cpu().double().view(1, 1, -1)
     hp = torch.zeros(2, co, MS, dtype=torch.float64)
     hp = hp.index_add(2, lk, ckf * (a - b) * 0.5).index_add(2, ln, ckf * (a + b) * 0.5)
