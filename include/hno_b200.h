@@ -316,9 +316,12 @@ int hno_dsconv_backward(const float* const* in, float* const* din, const int* ch
 int hno_mha_project_forward(const float* z, const float* weight, const float* bias, float* x_tok, float* x_chan, int B,
                             int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp, int Fp,
                             void* stream);
+/* workspace of the two backward entry points below (per-tile partial sums of the weight gradients; cin = co for the output
+ * projection, T = number of tokens).  A NULL workspace selects the slower one-CTA-per-output weight-gradient kernel. */
+size_t hno_mha_wgrad_workspace_bytes(int B, int H, int cin, int cd, int T);
 int hno_mha_project_backward(const float* dx_tok, const float* z, const float* weight, float* dz, float* dweight,
-                             float* dbias, int B, int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw,
-                             int Tp, int Fp, int accumulate_dz, void* stream);
+                             float* dbias, void* workspace, int B, int H, int cin, int cd, int Ld, int Lh, int Lw, int pd,
+                             int ph, int pw, int Tp, int Fp, int accumulate_dz, void* stream);
 int hno_mha_attention_forward(const float* q_tok, const float* k_tok, const float* v_chan, float* P, float* PT,
                               float* o_tok, int BH, int Tp, int Fqp, int Fvp, float scale, int activation, void* stream);
 int hno_mha_attention_backward(const float* do_tok, const float* do_chan, const float* q_chan, const float* k_chan,
@@ -328,8 +331,8 @@ int hno_mha_attention_backward(const float* do_tok, const float* do_chan, const 
 int hno_mha_output_forward(const float* o_tok, const float* weight_out, const float* bias, float* y, int B, int H, int co,
                            int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp, int Fp, void* stream);
 int hno_mha_output_backward(const float* dy, const float* o_tok, const float* weight_out, float* do_tok, float* do_chan,
-                            float* dweight_out, float* dbias, int B, int H, int co, int cd, int Ld, int Lh, int Lw, int pd,
-                            int ph, int pw, int Tp, int Fp, void* stream);
+                            float* dweight_out, float* dbias, void* workspace, int B, int H, int co, int cd, int Ld, int Lh,
+                            int Lw, int pd, int ph, int pw, int Tp, int Fp, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adamax step on a flat parameter vector (torch.optim.Adamax semantics, the optimizer of

@@ -80,11 +80,12 @@ SIGNATURES = {
     'hno_dsconv_backward_workspace_bytes': (_Z, [_I, _I, _I, _L]),
     'hno_dsconv_backward': (_I, [_P, _P, _P, _I] + [_P] * 8 + [_I, _I, _L, _L, _L, _I, _P]),
     'hno_mha_project_forward': (_I, [_P] * 5 + [_I] * 12 + [_P]),
-    'hno_mha_project_backward': (_I, [_P] * 6 + [_I] * 13 + [_P]),
+    'hno_mha_wgrad_workspace_bytes': (_Z, [_I] * 5),
+    'hno_mha_project_backward': (_I, [_P] * 7 + [_I] * 13 + [_P]),
     'hno_mha_attention_forward': (_I, [_P] * 6 + [_I, _I, _I, _I, _F, _I, _P]),
     'hno_mha_attention_backward': (_I, [_P] * 12 + [_I, _I, _I, _I, _F, _I, _P]),
     'hno_mha_output_forward': (_I, [_P] * 4 + [_I] * 12 + [_P]),
-    'hno_mha_output_backward': (_I, [_P] * 7 + [_I] * 12 + [_P]),
+    'hno_mha_output_backward': (_I, [_P] * 8 + [_I] * 12 + [_P]),
     'hno_adamax_step': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 

@@ -79,8 +79,9 @@ int dsconv_backward(const float* const*, float* const*, const int*, int, const f
                     const float*, float*, float*, float*, void*, int, int, long, long, long, int, cudaStream_t);
 int mha_project_forward(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int, int, int,
                         int, int, int, int, cudaStream_t);
-int mha_project_backward(const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int, int,
-                         int, int, int, int, int, int, int, cudaStream_t);
+int mha_project_backward(const float*, const float*, const float*, float*, float*, float*, void*, int, int, int, int, int,
+                         int, int, int, int, int, int, int, int, cudaStream_t);
+size_t mha_wgrad_workspace_bytes(int, int, int, int, int);
 int mha_attention_forward(const float*, const float*, const float*, float*, float*, float*, int, int, int, int, float, int,
                           cudaStream_t);
 int mha_attention_backward(const float*, const float*, const float*, const float*, const float*, const float*,
@@ -88,8 +89,8 @@ int mha_attention_backward(const float*, const float*, const float*, const float
                            cudaStream_t);
 int mha_output_forward(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int,
                        int, int, cudaStream_t);
-int mha_output_backward(const float*, const float*, const float*, float*, float*, float*, float*, int, int, int, int, int,
-                        int, int, int, int, int, int, int, cudaStream_t);
+int mha_output_backward(const float*, const float*, const float*, float*, float*, float*, float*, void*, int, int, int, int,
+                        int, int, int, int, int, int, int, int, cudaStream_t);
 size_t head_backward_workspace_bytes(const void*, int, int);
 int head_backward(const void*, const void*, const float*, const float*, float*, void*, int, int, long, int,
                   cudaStream_t);
@@ -392,11 +393,12 @@ int hno_mha_project_forward(const float* z, const float* weight, const float* bi
                             void* stream) {
   return mha_project_forward(z, weight, bias, x_tok, x_chan, B, H, cin, cd, Ld, Lh, Lw, pd, ph, pw, Tp, Fp, ST(stream));
 }
+size_t hno_mha_wgrad_workspace_bytes(int B, int H, int cin, int cd, int T) { return mha_wgrad_workspace_bytes(B, H, cin, cd, T); }
 int hno_mha_project_backward(const float* dx_tok, const float* z, const float* weight, float* dz, float* dweight,
-                             float* dbias, int B, int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw,
-                             int Tp, int Fp, int accumulate_dz, void* stream) {
-  return mha_project_backward(dx_tok, z, weight, dz, dweight, dbias, B, H, cin, cd, Ld, Lh, Lw, pd, ph, pw, Tp, Fp,
-                              accumulate_dz, ST(stream));
+                             float* dbias, void* workspace, int B, int H, int cin, int cd, int Ld, int Lh, int Lw, int pd,
+                             int ph, int pw, int Tp, int Fp, int accumulate_dz, void* stream) {
+  return mha_project_backward(dx_tok, z, weight, dz, dweight, dbias, workspace, B, H, cin, cd, Ld, Lh, Lw, pd, ph, pw, Tp,
+                              Fp, accumulate_dz, ST(stream));
 }
 int hno_mha_attention_forward(const float* q_tok, const float* k_tok, const float* v_chan, float* P, float* PT,
                               float* o_tok, int BH, int Tp, int Fqp, int Fvp, float scale, int activation, void* stream) {
@@ -414,10 +416,10 @@ int hno_mha_output_forward(const float* o_tok, const float* weight_out, const fl
   return mha_output_forward(o_tok, weight_out, bias, y, B, H, co, cd, Ld, Lh, Lw, pd, ph, pw, Tp, Fp, ST(stream));
 }
 int hno_mha_output_backward(const float* dy, const float* o_tok, const float* weight_out, float* do_tok, float* do_chan,
-                            float* dweight_out, float* dbias, int B, int H, int co, int cd, int Ld, int Lh, int Lw, int pd,
-                            int ph, int pw, int Tp, int Fp, void* stream) {
-  return mha_output_backward(dy, o_tok, weight_out, do_tok, do_chan, dweight_out, dbias, B, H, co, cd, Ld, Lh, Lw, pd, ph,
-                             pw, Tp, Fp, ST(stream));
+                            float* dweight_out, float* dbias, void* workspace, int B, int H, int co, int cd, int Ld, int Lh,
+                            int Lw, int pd, int ph, int pw, int Tp, int Fp, void* stream) {
+  return mha_output_backward(dy, o_tok, weight_out, do_tok, do_chan, dweight_out, dbias, workspace, B, H, co, cd, Ld, Lh, Lw,
+                             pd, ph, pw, Tp, Fp, ST(stream));
 }
 
 int hno_adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, long n, float lr, float beta1,

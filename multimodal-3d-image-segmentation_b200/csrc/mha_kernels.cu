@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "gemm_tc.h"
 
+#include <stdlib.h>
+
 namespace hno {
 
 struct MhaGeom {
@@ -236,6 +238,117 @@ __global__ void __launch_bounds__(256) k_mha_wgrad(const float* __restrict__ dx_
   }
 }
 
+// Tiled weight gradient (round 2).  The kernel above runs one CTA per output and re-reads (and re-gathers) both operands for
+// every one of the H cd cin outputs: 82 us per call, four calls per attention block.  Here a CTA stages the 32-token tile of
+// dx_tok (all heads) and the grouped patches of src ONCE in shared memory and every thread owns a few outputs; one partial
+// row per tile, fp64 reduction by k_reduce_partials.  grid (ceil(T / 32), B).
+constexpr int kWgTT = 32;
+__global__ void __launch_bounds__(256) k_mha_wgrad_tile(const float* __restrict__ dx_tok, const float* __restrict__ src,
+                                                        float* __restrict__ partials, MhaGeom g, MhaW ws, int cin, int cd,
+                                                        int Fp, int bias_mode) {
+  extern __shared__ float smw[];
+  const int P = g.pd * g.ph * g.pw;
+  const int HF = g.H * cd * P, HFp = HF + 4;  // dx tile pitch
+  const int CF = cin * P, CFp = CF + 4;       // patch tile pitch
+  float* dxs = smw;                // [32][HFp]
+  float* zs = dxs + kWgTT * HFp;   // [32][CFp]
+  const int b = blockIdx.y, t0 = blockIdx.x * kWgTT;
+  const int F4 = (cd * P) >> 2;  // float4 pieces of a (token, head) row; (cd P) % 4 == 0 is checked by the launcher
+  for (int idx = threadIdx.x; idx < kWgTT * g.H * F4; idx += 256) {
+    const int f4 = idx % F4, r = idx / F4, h = r % g.H, t = r / g.H;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t0 + t < g.T) v = *reinterpret_cast<const float4*>(dx_tok + ((long)(b * g.H + h) * g.Tp + t0 + t) * Fp + 4 * f4);
+    *reinterpret_cast<float4*>(dxs + t * HFp + h * cd * P + 4 * f4) = v;
+  }
+  for (int idx = threadIdx.x; idx < kWgTT * cin; idx += 256) {
+    const int t = idx % kWgTT, i = idx / kWgTT;  // consecutive threads = consecutive tokens = neighbouring patches
+    const bool live = t0 + t < g.T;
+    const MhaTok k = live ? mha_token(g, t0 + t) : MhaTok{0, 0, 0};
+    const float* sp = src + ((long)b * cin + i) * g.M;
+    int po = 0;
+    for (int id = 0; id < g.pd; ++id)
+      for (int ih = 0; ih < g.ph; ++ih)
+        for (int iw = 0; iw < g.pw; ++iw, ++po) {
+          const long m = ((long)(k.td * g.pd + id) * g.Lh + k.th * g.ph + ih) * g.Lw + k.tw * g.pw + iw;
+          zs[t * CFp + i * P + po] = live ? __ldg(sp + m) : 0.f;
+        }
+  }
+  __syncthreads();
+  const int NO = g.H * cd * cin;
+  const int nbias = bias_mode == 1 ? g.H * cd : (bias_mode == 2 ? cin : 0);
+  float* prow = partials + ((long)blockIdx.y * gridDim.x + blockIdx.x) * (NO + nbias);
+  for (int idx = threadIdx.x; idx < NO + nbias; idx += 256) {
+    float acc = 0.f;
+    if (idx < NO) {
+      const int i = idx % cin, r = idx / cin, c = r % cd, h = r / cd;
+      const float* dp = dxs + (h * cd + c) * P;
+      const float* zp = zs + i * P;
+      if ((P & 3) == 0) {
+        for (int t = 0; t < kWgTT; ++t)
+          for (int q = 0; q < P; q += 4) {
+            const float4 d = *reinterpret_cast<const float4*>(dp + t * HFp + q);
+            const float4 x = *reinterpret_cast<const float4*>(zp + t * CFp + q);
+            acc = fmaf(d.x, x.x, fmaf(d.y, x.y, fmaf(d.z, x.z, fmaf(d.w, x.w, acc))));
+          }
+      } else {
+        for (int t = 0; t < kWgTT; ++t)
+          for (int q = 0; q < P; ++q) acc = fmaf(dp[t * HFp + q], zp[t * CFp + q], acc);
+      }
+      prow[h * ws.sh + c * ws.sc + i * ws.si] = acc;
+    } else if (bias_mode == 1) {  // projections: dbias[h][c] = sum of dx_tok
+      const float* dp = dxs + (idx - NO) * P;
+      for (int t = 0; t < kWgTT; ++t)
+        for (int q = 0; q < P; ++q) acc += dp[t * HFp + q];
+      prow[idx] = acc;
+    } else {                      // output projection (src = dy): dbias[i] = sum of src over the modes
+      const float* zp = zs + (idx - NO) * P;
+      for (int t = 0; t < kWgTT; ++t)
+        for (int q = 0; q < P; ++q) acc += zp[t * CFp + q];
+      prow[idx] = acc;
+    }
+  }
+}
+
+int reduce_partials(const float* partials, int nrows, int nw, int nb, float* dweight, float* dbias, int accumulate,
+                    cudaStream_t st);
+
+// Shared-memory footprint of the tiled weight gradient; 0 = shape not served by it (the per-output kernel takes over).
+static size_t wgrad_tile_smem(const MhaGeom& g, int cin, int cd) {
+  const int P = g.pd * g.ph * g.pw;
+  if ((cd * P) % 4 != 0) return 0;
+  const size_t bytes = (size_t)kWgTT * ((size_t)g.H * cd * P + 4 + (size_t)cin * P + 4) * sizeof(float);
+  return bytes <= 200 * 1024 ? bytes : 0;
+}
+
+size_t mha_wgrad_workspace_bytes(int B, int H, int cin, int cd, int T) {
+  return (size_t)ceil_div(T, kWgTT) * B * ((size_t)H * cd * cin + (H * cd > cin ? H * cd : cin)) * sizeof(float) + 256;
+}
+
+// dw (indexed through ws like the weight) and the optional bias gradient; `wsp` may be null (per-output kernel)
+static int mha_wgrad(const float* dx_tok, const float* src, float* dw, float* dbias, void* wsp, const MhaGeom& g, MhaW ws,
+                     int cin, int cd, int Fp, int bias_mode, cudaStream_t st) {
+  const size_t smem = wgrad_tile_smem(g, cin, cd);
+  static const bool tile_on = !(getenv("HNO_MHA_WGRAD_TILE") && atoi(getenv("HNO_MHA_WGRAD_TILE")) == 0);
+  if (wsp != nullptr && smem > 0 && tile_on && g.B <= 65535) {
+    const int NO = g.H * cd * cin;
+    const int nbias = bias_mode == 1 ? g.H * cd : (bias_mode == 2 ? cin : 0);
+    dim3 grid(ceil_div(g.T, kWgTT), g.B);
+    HNO_CUDA(cudaFuncSetAttribute(k_mha_wgrad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mha_wgrad_tile<<<grid, 256, smem, st>>>(dx_tok, src, reinterpret_cast<float*>(wsp), g, ws, cin, cd, Fp, bias_mode);
+    HNO_LAUNCH_CHECK();
+    return reduce_partials(reinterpret_cast<const float*>(wsp), (int)(grid.x * grid.y), NO, nbias, dw, nbias ? dbias : nullptr, 0, st);
+  }
+  if (bias_mode == 2) {
+    dim3 gw(cin, cd, g.H + 1);
+    k_mha_wgrad<<<gw, 256, 0, st>>>(dx_tok, src, dw, dbias, g, ws, cin, cd, Fp, 2);
+  } else {
+    dim3 gw(cin + (bias_mode == 1 ? 1 : 0), cd, g.H);
+    k_mha_wgrad<<<gw, 256, 0, st>>>(dx_tok, src, dw, dbias, g, ws, cin, cd, Fp, bias_mode);
+  }
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
 // o_tok [B*H][Tp][Fp] -> y [B][co][M] = sum_{h, c} wout[o][h cd + c] * o_tok[b, h][t][c P + po] + bias[o]
 __global__ void __launch_bounds__(256) k_mha_output_fwd(const float* __restrict__ o_tok, const float* __restrict__ wout,
                                                         const float* __restrict__ bias, float* __restrict__ y, MhaGeom g,
@@ -285,8 +398,8 @@ int mha_project_forward(const float* z, const float* w, const float* bias, float
   return 0;
 }
 
-int mha_project_backward(const float* dx_tok, const float* z, const float* w, float* dz, float* dw, float* dbias, int B,
-                         int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp, int Fp,
+int mha_project_backward(const float* dx_tok, const float* z, const float* w, float* dz, float* dw, float* dbias, void* wsp,
+                         int B, int H, int cin, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp, int Fp,
                          int accumulate_dz, cudaStream_t st) {
   MhaGeom g;
   if (make_geom(&g, B, H, Ld, Lh, Lw, pd, ph, pw, Tp)) return -1;
@@ -299,9 +412,7 @@ int mha_project_backward(const float* dx_tok, const float* z, const float* w, fl
   }
   if (dw) {
     const MhaW ws{(long)cd * cin, (long)cin, 1};
-    dim3 grid(cin + (dbias ? 1 : 0), cd, H);
-    k_mha_wgrad<<<grid, 256, 0, st>>>(dx_tok, z, dw, dbias, g, ws, cin, cd, Fp, dbias ? 1 : 0);
-    HNO_LAUNCH_CHECK();
+    return mha_wgrad(dx_tok, z, dw, dbias, wsp, g, ws, cin, cd, Fp, dbias ? 1 : 0, st);
   }
   return 0;
 }
@@ -380,8 +491,8 @@ int mha_output_forward(const float* o_tok, const float* wout, const float* bias,
 }
 
 int mha_output_backward(const float* dy, const float* o_tok, const float* wout, float* do_tok, float* do_chan, float* dwout,
-                        float* dbias, int B, int H, int co, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp,
-                        int Fp, cudaStream_t st) {
+                        float* dbias, void* wsp, int B, int H, int co, int cd, int Ld, int Lh, int Lw, int pd, int ph, int pw,
+                        int Tp, int Fp, cudaStream_t st) {
   MhaGeom g;
   if (make_geom(&g, B, H, Ld, Lh, Lw, pd, ph, pw, Tp)) return -1;
   HNO_CHECK(dy && o_tok && wout && do_tok && do_chan && dwout, "mha_output_backward: null pointer");
@@ -393,10 +504,7 @@ int mha_output_backward(const float* dy, const float* o_tok, const float* wout, 
   k_mha_project_fwd<<<grid, 256, co * sizeof(float), st>>>(dy, wout, nullptr, do_tok, do_chan, g, ws, co, cd, Fp);
   HNO_LAUNCH_CHECK();
   // dW_out[o][h cd + c] = sum dy[b][o][m] O[b, h][t][f]; bias: sum of dy over the modes
-  dim3 gw(co, cd, H + (dbias ? 1 : 0));
-  k_mha_wgrad<<<gw, 256, 0, st>>>(o_tok, dy, dwout, dbias, g, ws, co, cd, Fp, dbias ? 2 : 0);
-  HNO_LAUNCH_CHECK();
-  return 0;
+  return mha_wgrad(o_tok, dy, dwout, dbias, wsp, g, ws, co, cd, Fp, dbias ? 2 : 0, st);
 }
 
 }  // namespace hno

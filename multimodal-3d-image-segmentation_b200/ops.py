@@ -798,8 +798,9 @@ def mha_project_backward(dx_tok, z, w, geom, dz=None, has_bias=False):
         dz = torch.empty_like(z)
     dw = torch.empty_like(w)
     db = torch.empty((H, cd), dtype=torch.float32, device=z.device) if has_bias else None
-    call('hno_mha_project_backward', ptr(dx_tok), ptr(z), ptr(w.contiguous()), ptr(dz), ptr(dw), ptr(db), B, H, cin, cd,
-         *geom.args(), dx_tok.shape[2], int(acc), stream_ptr())
+    ws = workspace(_lib.load().hno_mha_wgrad_workspace_bytes(B, H, cin, cd, geom.T), z.device, 'mhaw')
+    call('hno_mha_project_backward', ptr(dx_tok), ptr(z), ptr(w.contiguous()), ptr(dz), ptr(dw), ptr(db), ptr(ws), B, H, cin,
+         cd, *geom.args(), dx_tok.shape[2], int(acc), stream_ptr())
     return dz, dw, db
 
 
@@ -861,8 +862,9 @@ def hartley_attention_backward(dy, S):
     do_chan = torch.empty((B * H, fv, geom.Tp), dtype=torch.float32, device=dev)
     dwo = torch.empty_like(wo)
     dbo = torch.empty((co,), dtype=torch.float32, device=dev) if S.has_bias[3] else None
+    ws = workspace(_lib.load().hno_mha_wgrad_workspace_bytes(B, H, co, vd, geom.T), dev, 'mhaw')
     call('hno_mha_output_backward', ptr(dy), ptr(S.o_tok), ptr(wo.contiguous()), ptr(do_tok), ptr(do_chan), ptr(dwo),
-         ptr(dbo), B, H, co, vd, *geom.args(), fv, stream_ptr())
+         ptr(dbo), ptr(ws), B, H, co, vd, *geom.args(), fv, stream_ptr())
     tt = B * H * geom.Tp * geom.Tp * 4
     scratch = workspace(2 * tt, dev, 'mha')
     dS = scratch[:tt].view(torch.float32)
