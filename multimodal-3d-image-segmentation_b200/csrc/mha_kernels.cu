@@ -370,6 +370,126 @@ __global__ void __launch_bounds__(256) k_mha_output_fwd(const float* __restrict_
   y[((long)b * co + o) * g.M + m] = acc;
 }
 
+// ---- token-major glue kernels (round 2).  The kernels above re-read the mode tensor once per (head, channel) CTA (48 x for the
+// BASELINE attention) or the token rows once per output channel: 27 - 40 us per launch for 3 - 6 MB.  Here a thread owns ONE
+// TOKEN (8-mode patches, channel counts that are multiples of 4): it gathers / scatters its patch once and keeps 4 channels x 8
+// patch positions of accumulators in registers per pass.
+// modes -> tokens: x_tok [B*H][Tp][Fp], x_chan [B*H][Fp][Tp] = per-head 1x1x1 convolution of src [B][cin][M] + grouping.
+// grid (Tp / 128, B*H), 128 threads; weights of the head in shared memory as [c][i].
+__global__ void __launch_bounds__(128) k_mha_project_tok(const float* __restrict__ src, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ x_tok,
+                                                         float* __restrict__ x_chan, MhaGeom g, MhaW ws, int cin, int cd,
+                                                         int Fp) {
+  constexpr int P = 8;
+  extern __shared__ float swt[];  // [cd][cin]
+  const int bh = blockIdx.y, b = bh / g.H, h = bh % g.H;
+  for (int idx = threadIdx.x; idx < cd * cin; idx += 128) {
+    const int c = idx / cin, i = idx - c * cin;
+    swt[idx] = __ldg(w + h * ws.sh + c * ws.sc + i * ws.si);
+  }
+  __syncthreads();
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= g.Tp) return;
+  const bool live = t < g.T;
+  float* xt = x_tok + ((long)bh * g.Tp + t) * Fp;
+  float* xc = x_chan + (long)bh * Fp * g.Tp + t;
+  int moff[kMhaPMax];
+  mha_patch_offsets(g, live ? mha_token(g, t) : MhaTok{0, 0, 0}, moff);
+  const float* sp = src + (long)b * cin * g.M;
+  for (int c0 = 0; c0 < cd; c0 += 4) {
+    float acc[4][P];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float b0 = (live && bias) ? __ldg(bias + h * cd + c0 + c) : 0.f;
+#pragma unroll
+      for (int po = 0; po < P; ++po) acc[c][po] = b0;
+    }
+    if (live) {
+#pragma unroll 2
+      for (int i = 0; i < cin; ++i) {
+        float zv[P];
+#pragma unroll
+        for (int po = 0; po < P; ++po) zv[po] = __ldg(sp + (long)i * g.M + moff[po]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float wv = swt[(c0 + c) * cin + i];
+#pragma unroll
+          for (int po = 0; po < P; ++po) acc[c][po] = fmaf(wv, zv[po], acc[c][po]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float* o = xt + (c0 + c) * P;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+#pragma unroll
+      for (int po = 0; po < P; ++po) xc[(long)((c0 + c) * P + po) * g.Tp] = acc[c][po];
+    }
+  }
+  for (int f = cd * P; f < Fp; ++f) {  // feature padding
+    xt[f] = 0.f;
+    xc[(long)f * g.Tp] = 0.f;
+  }
+}
+
+// tokens -> modes: out [B][nout][M] (+)= sum_{h, c} W(h, c, o) x_tok[b, h][t][c P + po] (+ bias[o]); W(h, c, o) = w[h sh + c sc + o si].
+// grid (ceil(T / 128), nout / 4, B), 128 threads: a thread owns one token and FOUR outputs (one thread for all outputs left 32
+// CTAs on the machine: 35 us, 70 us when accumulating); the weights of the four outputs in shared memory as [h][c][4].
+__global__ void __launch_bounds__(128) k_mha_tok_to_modes(const float* __restrict__ x_tok, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, MhaGeom g,
+                                                          MhaW ws, int nout, int cd, int Fp, int accumulate) {
+  constexpr int P = 8;
+  extern __shared__ float swt[];  // [H][cd][4]
+  const int b = blockIdx.z, o0 = blockIdx.y * 4;
+  for (int idx = threadIdx.x; idx < g.H * cd * 4; idx += 128) {
+    const int o = idx & 3, r = idx >> 2, c = r % cd, h = r / cd;
+    swt[idx] = __ldg(w + h * ws.sh + c * ws.sc + (o0 + o) * ws.si);
+  }
+  __syncthreads();
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= g.T) return;
+  int moff[kMhaPMax];
+  mha_patch_offsets(g, mha_token(g, t), moff);
+  float* ob = out + (long)b * nout * g.M;
+  {
+    float acc[4][P];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float b0 = bias ? __ldg(bias + o0 + o) : 0.f;
+#pragma unroll
+      for (int po = 0; po < P; ++po) acc[o][po] = b0;
+    }
+    for (int h = 0; h < g.H; ++h) {
+      const float* xr = x_tok + ((long)(b * g.H + h) * g.Tp + t) * Fp;
+#pragma unroll 2
+      for (int c = 0; c < cd; ++c) {
+        const float4 v0 = *reinterpret_cast<const float4*>(xr + c * P), v1 = *reinterpret_cast<const float4*>(xr + c * P + 4);
+        const float xv[P] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const float* wp = swt + (h * cd + c) * 4;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float wv = wp[o];
+#pragma unroll
+          for (int po = 0; po < P; ++po) acc[o][po] = fmaf(wv, xv[po], acc[o][po]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float* dst = ob + (long)(o0 + o) * g.M;
+#pragma unroll
+      for (int po = 0; po < P; ++po) dst[moff[po]] = accumulate ? dst[moff[po]] + acc[o][po] : acc[o][po];
+    }
+  }
+}
+
+// the token-major kernels serve 8-mode patches and channel counts that are multiples of 4 (HNO_MHA_TOK=0: never)
+static bool mha_tok_path(const MhaGeom& g, int cin, int cd) {
+  static const bool on = !(getenv("HNO_MHA_TOK") && atoi(getenv("HNO_MHA_TOK")) == 0);
+  return on && g.pd * g.ph * g.pw == 8 && cin % 4 == 0 && cd % 4 == 0 && (size_t)g.H * cd * cin * sizeof(float) <= 48 * 1024;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int make_geom(MhaGeom* g, int B, int H, int Ld, int Lh, int Lw, int pd, int ph, int pw, int Tp) {
   HNO_CHECK(B >= 1 && H >= 1 && Ld >= 1 && Lh >= 1 && Lw >= 1, "mha: bad sizes");
@@ -392,8 +512,13 @@ int mha_project_forward(const float* z, const float* w, const float* bias, float
   HNO_CHECK(Fp >= cd * pd * ph * pw && Fp % 32 == 0, "mha_project_forward: feature pitch %d too small / not a multiple of 32", Fp);
   HNO_CHECK(cd <= 65535 && cin * sizeof(float) <= 48 * 1024, "mha_project_forward: too many channels");
   const MhaW ws{(long)cd * cin, (long)cin, 1};
-  dim3 grid(ceil_div(Tp, 256), cd, B * H);
-  k_mha_project_fwd<<<grid, 256, cin * sizeof(float), st>>>(z, w, bias, x_tok, x_chan, g, ws, cin, cd, Fp);
+  if (mha_tok_path(g, cin, cd)) {
+    dim3 grid(Tp / 128, B * H);
+    k_mha_project_tok<<<grid, 128, (size_t)cd * cin * sizeof(float), st>>>(z, w, bias, x_tok, x_chan, g, ws, cin, cd, Fp);
+  } else {
+    dim3 grid(ceil_div(Tp, 256), cd, B * H);
+    k_mha_project_fwd<<<grid, 256, cin * sizeof(float), st>>>(z, w, bias, x_tok, x_chan, g, ws, cin, cd, Fp);
+  }
   HNO_LAUNCH_CHECK();
   return 0;
 }
@@ -406,8 +531,15 @@ int mha_project_backward(const float* dx_tok, const float* z, const float* w, fl
   HNO_CHECK(dx_tok && z && w, "mha_project_backward: null pointer");
   HNO_CHECK(cin <= 65535 && B <= 65535, "mha_project_backward: too many channels");
   if (dz) {
-    dim3 grid(ceil_div(g.M, 256), cin, B);
-    k_mha_project_bwd_z<<<grid, 256, 0, st>>>(dx_tok, w, dz, g, cin, cd, Fp, accumulate_dz);
+    if (mha_tok_path(g, cin, cd)) {
+      const MhaW wsz{(long)cd * cin, (long)cin, 1};  // W(h, c, i) = w[h][c][i]
+      dim3 grid(ceil_div(g.T, 128), cin / 4, B);
+      k_mha_tok_to_modes<<<grid, 128, (size_t)H * cd * 4 * sizeof(float), st>>>(dx_tok, w, nullptr, dz, g, wsz, cin, cd, Fp,
+                                                                              accumulate_dz);
+    } else {
+      dim3 grid(ceil_div(g.M, 256), cin, B);
+      k_mha_project_bwd_z<<<grid, 256, 0, st>>>(dx_tok, w, dz, g, cin, cd, Fp, accumulate_dz);
+    }
     HNO_LAUNCH_CHECK();
   }
   if (dw) {
@@ -484,8 +616,14 @@ int mha_output_forward(const float* o_tok, const float* wout, const float* bias,
   if (make_geom(&g, B, H, Ld, Lh, Lw, pd, ph, pw, Tp)) return -1;
   HNO_CHECK(o_tok && wout && y, "mha_output_forward: null pointer");
   HNO_CHECK(co <= 65535 && B <= 65535, "mha_output_forward: too many channels");
-  dim3 grid(ceil_div(g.M, 256), co, B);
-  k_mha_output_fwd<<<grid, 256, 0, st>>>(o_tok, wout, bias, y, g, co, cd, Fp);
+  if (mha_tok_path(g, co, cd)) {
+    const MhaW wso{(long)cd, 1, (long)H * cd};  // W(h, c, o) = weight_out[o][h cd + c]
+    dim3 grid(ceil_div(g.T, 128), co / 4, B);
+    k_mha_tok_to_modes<<<grid, 128, (size_t)H * cd * 4 * sizeof(float), st>>>(o_tok, wout, bias, y, g, wso, co, cd, Fp, 0);
+  } else {
+    dim3 grid(ceil_div(g.M, 256), co, B);
+    k_mha_output_fwd<<<grid, 256, 0, st>>>(o_tok, wout, bias, y, g, co, cd, Fp);
+  }
   HNO_LAUNCH_CHECK();
   return 0;
 }
@@ -500,8 +638,13 @@ int mha_output_backward(const float* dy, const float* o_tok, const float* wout, 
   HNO_CHECK(cd <= 65535 && co * sizeof(float) <= 48 * 1024, "mha_output_backward: too many channels");
   // dO = W_out^T dy in both attention layouts: the projection kernel with the weight read transposed
   const MhaW ws{(long)cd, 1, (long)H * cd};
-  dim3 grid(ceil_div(Tp, 256), cd, B * H);
-  k_mha_project_fwd<<<grid, 256, co * sizeof(float), st>>>(dy, wout, nullptr, do_tok, do_chan, g, ws, co, cd, Fp);
+  if (mha_tok_path(g, co, cd)) {
+    dim3 grid(Tp / 128, B * H);
+    k_mha_project_tok<<<grid, 128, (size_t)cd * co * sizeof(float), st>>>(dy, wout, nullptr, do_tok, do_chan, g, ws, co, cd, Fp);
+  } else {
+    dim3 grid(ceil_div(Tp, 256), cd, B * H);
+    k_mha_project_fwd<<<grid, 256, co * sizeof(float), st>>>(dy, wout, nullptr, do_tok, do_chan, g, ws, co, cd, Fp);
+  }
   HNO_LAUNCH_CHECK();
   // dW_out[o][h cd + c] = sum dy[b][o][m] O[b, h][t][f]; bias: sum of dy over the modes
   return mha_wgrad(o_tok, dy, dwout, dbias, wsp, g, ws, co, cd, Fp, dbias ? 2 : 0, st);
