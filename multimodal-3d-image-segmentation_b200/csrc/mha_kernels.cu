@@ -239,10 +239,10 @@ __global__ void __launch_bounds__(256) k_mha_wgrad(const float* __restrict__ dx_
 }
 
 // Tiled weight gradient (round 2).  The kernel above runs one CTA per output and re-reads (and re-gathers) both operands for
-// every one of the H cd cin outputs: 82 us per call, four calls per attention block.  Here a CTA stages the 32-token tile of
+// every one of the H cd cin outputs: 82 us per call, four calls per attention block.  Here a CTA stages a 16-token tile of
 // dx_tok (all heads) and the grouped patches of src ONCE in shared memory and every thread owns a few outputs; one partial
-// row per tile, fp64 reduction by k_reduce_partials.  grid (ceil(T / 32), B).
-constexpr int kWgTT = 32;
+// row per tile, fp64 reduction by k_reduce_partials.  grid (ceil(T / 16), B).
+constexpr int kWgTT = 16;
 __global__ void __launch_bounds__(256) k_mha_wgrad_tile(const float* __restrict__ dx_tok, const float* __restrict__ src,
                                                         float* __restrict__ partials, MhaGeom g, MhaW ws, int cin, int cd,
                                                         int Fp, int bias_mode) {
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(256) k_mha_wgrad_tile(const float* __restrict_
   const int P = g.pd * g.ph * g.pw;
   const int HF = g.H * cd * P, HFp = HF + 4;  // dx tile pitch
   const int CF = cin * P, CFp = CF + 4;       // patch tile pitch
-  float* dxs = smw;                // [32][HFp]
-  float* zs = dxs + kWgTT * HFp;   // [32][CFp]
+  float* dxs = smw;                // [kWgTT][HFp]
+  float* zs = dxs + kWgTT * HFp;   // [kWgTT][CFp]
   const int b = blockIdx.y, t0 = blockIdx.x * kWgTT;
   const int F4 = (cd * P) >> 2;  // float4 pieces of a (token, head) row; (cd P) % 4 == 0 is checked by the launcher
   for (int idx = threadIdx.x; idx < kWgTT * g.H * F4; idx += 256) {
