@@ -279,6 +279,19 @@ int hno_normalize_modalities(const float* data, float* out, void* workspace, int
  * the exact int16 -> fp32 conversion happens in the load */
 int hno_normalize_modalities_i16(const short* data, float* out, void* workspace, int rows, long n, int has_mask,
                                  float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream);
+/* hno_affine_resample_nn  replaces experiments/data_io/dataset.py:205-237 (apply_transform: one SimpleITK
+ * ResampleImageFilter.Execute per channel with an AffineTransform, sitkNearestNeighbor, default pixel value cval, unit
+ * spacing / zero origin) and :240-245 (flip_axis) for a whole batch:
+ *   in / out [B][C][D][H][W], elem_bytes 1 (uint8 labels), 2 (int16 raw intensities) or 4 (float32); out != in.
+ *   xform  DEVICE [B][12] fp64: per sample the 3 x 4 matrix (row-major, SimpleITK's (x, y, z) = (W, H, D) order) that
+ *          maps an output index to the continuous input index -- the affine part and offset the reference passes to
+ *          sitk.AffineTransform (:220-224) after transform_matrix_offset_center (:195-202).
+ *   flags  DEVICE [B] (may be NULL = 0): bit 0 / 1 / 2 flip the D / H / W axis of the RESAMPLED image (the reference
+ *          flips after the resampling, :172-178), bit 3 = no geometric transform for this sample (flips only).
+ *   out[d][h][w] = in[nearest(M (x, y, z, 1))] with round-half-up per axis, cval (cast to the element type) outside.
+ * A 2-D image (C, H, W) is the D == 1 case with an identity z row. */
+int hno_affine_resample_nn(const void* in, void* out, int elem_bytes, const double* xform, const int* flags, int B,
+                           int C, int D, int H, int W, double cval, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Deep-supervision convolution                 replaces nets/architectures.py:295-311, 330-343 and

@@ -5,7 +5,7 @@ fails (or a call returns an error) an exception is raised.  Nothing in this pack
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_long, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libhno_b200.so')
@@ -20,6 +20,7 @@ _I = c_int
 _L = c_long
 _F = c_float
 _Z = c_size_t
+_D = c_double
 
 # name: (restype, argtypes)  -- mirrors include/hno_b200.h one to one
 SIGNATURES = {
@@ -76,6 +77,7 @@ SIGNATURES = {
     'hno_normalize_workspace_bytes': (_Z, [_I]),
     'hno_normalize_modalities': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
     'hno_normalize_modalities_i16': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
+    'hno_affine_resample_nn': (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _D, _P]),
     'hno_dsconv_forward': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
     'hno_dsconv_backward_workspace_bytes': (_Z, [_I, _I, _I, _L]),
     'hno_dsconv_backward': (_I, [_P, _P, _P, _I] + [_P] * 8 + [_I, _I, _L, _L, _L, _I, _P]),

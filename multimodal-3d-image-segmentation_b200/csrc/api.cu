@@ -116,6 +116,7 @@ int complex_modemix_backward(const float*, const float*, const float*, const flo
 int to_categorical(const void*, int, float*, int*, int, int, long, cudaStream_t);
 size_t normalize_workspace_bytes(int);
 int normalize_modalities(const void*, int, float*, void*, int, long, int, float, int, float, float, cudaStream_t);
+int affine_resample_nn(const void*, void*, int, const double*, const int*, int, int, int, int, int, double, cudaStream_t);
 int adamax_step(float*, const float*, float*, float*, long, float, float, float, float, float, int, float,
                 cudaStream_t);
 
@@ -341,6 +342,11 @@ int hno_normalize_modalities_i16(const short* data, float* out, void* workspace,
                                  float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream) {
   return normalize_modalities(data, 2, out, workspace, rows, n, has_mask, mask_val, has_clip, clip_lo, clip_hi,
                               ST(stream));
+}
+
+int hno_affine_resample_nn(const void* in, void* out, int elem_bytes, const double* xform, const int* flags, int B,
+                           int C, int D, int H, int W, double cval, void* stream) {
+  return affine_resample_nn(in, out, elem_bytes, xform, flags, B, C, D, H, W, cval, ST(stream));
 }
 
 int hno_hartley_conv_full_forward(const float* x_ext, const float* weight, const int* partner_table, float* out, int B,

@@ -475,3 +475,125 @@ def train_step(sd, x, labels, num_transform_blocks, num_modes, loss='DiceLoss'):
     value = LOSSES[loss](probs, to_categorical(labels, probs.shape[1]).to(probs.dtype))
     grads = torch.autograd.grad(value, list(params.values()))
     return value.detach(), dict(zip(params.keys(), grads))
+
+
+# ------------------------------------------------------------------------------------------------
+# Affine augmentation                                 experiments/data_io/dataset.py:63-245
+# ------------------------------------------------------------------------------------------------
+# PARITY UNPINNED for the resampler itself: the reference delegates it to SimpleITK (pyproject.toml:21, version not
+# pinned; not installable here).  affine_resample_nn restates the PUBLISHED semantics of what the reference configures --
+# itk::ResampleImageFilter with an itk::AffineTransform (y = A x + t about a zero centre), unit spacing, zero origin,
+# identity direction, itk::NearestNeighborInterpolateImageFunction (ConvertContinuousIndexToNearestIndex = round half
+# up, IsInsideBuffer = continuous index in [-0.5, size - 0.5)) and SetDefaultPixelValue(cval).  ITK walks a scan line by
+# interpolating between its transformed end points, this evaluates A x + t per voxel: the two can differ in the last
+# bit, i.e. only on exact rounding ties.  Everything the reference itself computes (which parameters are drawn from the
+# generator and in which order, the matrix, the flips) IS pinned: oracle/make_golden.py runs the reference's
+# ImageTransform with this resampler behind a stand-in `SimpleITK` module and records matrices and outputs
+# (tests/golden/augment.npz).
+def affine_resample_nn(x, matrix, offset, cval=0.0):
+    """x (C, D, H, W) or (C, H, W) numpy; matrix (n, n), offset (n,) in SimpleITK's (x, y[, z]) order, mapping an OUTPUT
+    index to the continuous INPUT index (dataset.py:220-224).  Returns the resampled array (same shape and dtype)."""
+    x = np.asarray(x)
+    nd = x.ndim - 1
+    size_xyz = x.shape[1:][::-1]
+    A = np.eye(3)
+    t = np.zeros(3)
+    A[:nd, :nd] = np.asarray(matrix, dtype=np.float64).reshape(nd, nd)
+    t[:nd] = np.asarray(offset, dtype=np.float64)
+    W, H = size_xyz[0], size_xyz[1]
+    D = size_xyz[2] if nd == 3 else 1
+    vol = x.reshape(x.shape[0], D, H, W)
+    pz, py, px = np.meshgrid(np.arange(D, dtype=np.float64), np.arange(H, dtype=np.float64),
+                             np.arange(W, dtype=np.float64), indexing='ij')
+    idx = []
+    for r in range(3):  # same operation order as the CUDA kernel, no fused multiply-add
+        s = (A[r, 0] * px + A[r, 1] * py) + A[r, 2] * pz
+        idx.append(np.floor((s + t[r]) + 0.5))
+    inside = ((idx[0] >= 0) & (idx[0] < W) & (idx[1] >= 0) & (idx[1] < H) & (idx[2] >= 0) & (idx[2] < D))
+    ix = np.where(inside, idx[0], 0).astype(np.int64)
+    iy = np.where(inside, idx[1], 0).astype(np.int64)
+    iz = np.where(inside, idx[2], 0).astype(np.int64)
+    out = np.where(inside[None], vol[:, iz, iy, ix], np.asarray(cval).astype(x.dtype))
+    return out.astype(x.dtype).reshape(x.shape)
+
+
+def centred_affine(matrix, size_xyz):
+    """dataset.py:195-202: the homogeneous matrix conjugated with the translation to size / 2 + 0.5."""
+    n = matrix.shape[0]
+    centre = np.asarray(size_xyz, dtype=np.float64) / 2.0 + 0.5
+    to_c, from_c = np.eye(n), np.eye(n)
+    to_c[:-1, -1] = centre
+    from_c[:-1, -1] = -centre
+    return to_c @ matrix @ from_c
+
+
+def image_transform(x, y, rng, rotation_range=None, shift_range=None, zoom_range=None, flip=None, cval=0.0,
+                    augmentation_probability=1.0):
+    """ImageTransform.__call__ (dataset.py:94-181) on numpy arrays with `rng` = np.random.default_rng(seed): the same
+    draws in the same order (binomial gate; one uniform per non-zero rotation / shift entry; zoom; one random() per
+    enabled flip axis AFTER the resampling).  Returns (x', y', record) with record = dict(matrix, offset, flips)."""
+    x = np.asarray(x)
+    nd = x.ndim - 1
+    rec = dict(matrix=None, offset=None, flips=[False] * nd)
+    if not rng.binomial(1, augmentation_probability):
+        return x, y, rec
+    theta = None
+    if rotation_range is not None:
+        if np.isscalar(rotation_range):
+            theta = np.pi / 180 * rng.uniform(-rotation_range, rotation_range) if rotation_range else 0
+        else:
+            theta = [np.pi / 180 * rng.uniform(-r, r) if r else 0 for r in rotation_range]
+    shift = None
+    if shift_range is not None:
+        shift = [rng.uniform(-s, s) * x.shape[1 + i] if s else 0 for i, s in enumerate(shift_range)]
+    zoom = rng.uniform(zoom_range[0], zoom_range[1]) if zoom_range is not None else None
+    M = None
+    if theta is not None:
+        if np.isscalar(theta):
+            if theta != 0:
+                c, s = np.cos(theta), np.sin(theta)
+                M = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+        elif any(t != 0 for t in theta):
+            a, b, g = theta[::-1]  # rotations about x, y, z
+            ca, sa, cb, sb, cg, sg = np.cos(a), np.sin(a), np.cos(b), np.sin(b), np.cos(g), np.sin(g)
+            M = np.array([[cb * cg, -ca * sg + sa * sb * cg, sa * sg + ca * sb * cg, 0],
+                          [cb * sg, ca * cg + sa * sb * sg, -sa * cg + ca * sb * sg, 0],
+                          [-sb, sa * cb, ca * cb, 0],
+                          [0, 0, 0, 1]])
+    if shift is not None and any(s != 0 for s in shift):
+        S = np.eye(nd + 1)
+        S[:-1, -1] = np.asarray(shift[::-1])
+        M = S if M is None else S @ M
+    if zoom is not None and zoom != 1:
+        Z = np.eye(nd + 1)
+        Z[:-1, :-1] *= zoom
+        M = Z if M is None else Z @ M
+    if M is not None:
+        Mc = centred_affine(M, x.shape[1:][::-1])
+        rec['matrix'], rec['offset'] = Mc[:-1, :-1].copy(), Mc[:-1, -1].copy()
+        x = affine_resample_nn(x, rec['matrix'], rec['offset'], cval)
+        if y is not None:
+            y = affine_resample_nn(y, rec['matrix'], rec['offset'], cval)
+    if flip is not None:
+        for i, f in enumerate(flip):
+            if f and rng.random() < 0.5:
+                rec['flips'][i] = True
+                x = np.flip(x, 1 + i)
+                if y is not None:
+                    y = np.flip(y, 1 + i)
+    return x, y, rec
+
+
+# the cases oracle/make_golden.py::case_augment records from the reference and tests/test_augment.py replays
+AUGMENT_CASES = [
+    # name, spatial, kwargs of ImageTransform, number of consecutive calls on one generator
+    ('brats_ini', (9, 12, 10), dict(rotation_range=[30, 30, 30], shift_range=[0.2, 0.2, 0.2], zoom_range=[0.8, 1.2],
+                                    augmentation_probability=0.8, seed=7), 6),  # [augmentation] of config_hnoseg_xs.ini shape
+    ('flips', (7, 8, 9), dict(flip=[True, False, True], seed=3), 5),
+    ('all', (8, 9, 11), dict(rotation_range=[20, 0, 45], shift_range=[0.1, 0, 0.3], zoom_range=[0.7, 1.3],
+                             flip=[False, True, True], cval=-3.0, augmentation_probability=0.7, seed=11), 6),
+    ('shift_only', (6, 7, 8), dict(shift_range=[0.25, 0.25, 0], seed=5), 3),
+    ('zoom_only', (6, 7, 8), dict(zoom_range=[0.6, 1.5], seed=9), 3),
+    ('planar', (10, 13), dict(rotation_range=25, shift_range=[0.2, 0.1], zoom_range=[0.8, 1.25], flip=[True, True],
+                              seed=13), 5),
+]

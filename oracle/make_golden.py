@@ -362,6 +362,113 @@ def case_input_side():
     save('input_side', **out)
 
 
+def _reference_image_transform():
+    """experiments/data_io/dataset.py imports SimpleITK (absent here).  The module is loaded by path with a stand-in
+    `SimpleITK` whose AffineTransform records (matrix, offset) and whose ResampleImageFilter.Execute runs the oracle's
+    nearest-neighbour resampler: everything the REFERENCE computes (parameter draws, matrix composition, centring, channel
+    loop, flips) runs unmodified; only the third-party resampler is the restatement (oracle header: parity unpinned there)."""
+    import importlib.util
+    import types
+    captured = []
+
+    class AffineTransform:
+        def __init__(self, matrix, offset):
+            self.matrix = np.asarray(matrix, dtype=np.float64)
+            self.offset = np.asarray(offset, dtype=np.float64)
+            captured.append((self.matrix.copy(), self.offset.copy()))
+
+    class _Image:
+        def __init__(self, arr):
+            self.arr = np.asarray(arr)
+
+        def GetSize(self):
+            return self.arr.shape[::-1]
+
+        def GetSpacing(self):
+            return (1.0,) * self.arr.ndim
+
+        def GetOrigin(self):
+            return (0.0,) * self.arr.ndim
+
+    class ResampleImageFilter:
+        def SetInterpolator(self, interp):
+            assert interp == 'nn'
+
+        def SetDefaultPixelValue(self, v):
+            self.cval = v
+
+        def SetTransform(self, t):
+            self.t = t
+
+        def SetSize(self, s):
+            self.size = s
+
+        def SetOutputSpacing(self, s):
+            assert all(v == 1.0 for v in s)
+
+        def SetOutputOrigin(self, o):
+            assert all(v == 0.0 for v in o)
+
+        def Execute(self, image):
+            assert tuple(self.size) == tuple(image.GetSize())
+            n = image.arr.ndim
+            out = orc.affine_resample_nn(image.arr[None], self.t.matrix.reshape(n, n), self.t.offset, self.cval)[0]
+            return _Image(out)
+
+    stub = types.ModuleType('SimpleITK')
+    stub.AffineTransform = AffineTransform
+    stub.ResampleImageFilter = ResampleImageFilter
+    stub.sitkNearestNeighbor = 'nn'
+    stub.GetImageFromArray = lambda a: _Image(a)
+    stub.GetArrayFromImage = lambda im: im.arr
+    saved = sys.modules.get('SimpleITK')
+    sys.modules['SimpleITK'] = stub
+    try:
+        spec = importlib.util.spec_from_file_location('_ref_dataset', os.path.join('/root/reference', 'experiments', 'data_io', 'dataset.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules['SimpleITK'] = saved
+    return mod, captured
+
+
+AUGMENT_CASES = orc.AUGMENT_CASES
+
+
+def case_augment():
+    """ImageTransform (experiments/data_io/dataset.py:63-192) recorded from the reference: for every case the inputs, the
+    (matrix, offset) it hands to sitk.AffineTransform per call and the augmented image / label arrays."""
+    ref_ds, captured = _reference_image_transform()
+    out = {}
+    for name, spatial, kw, calls in AUGMENT_CASES:
+        data_rng = np.random.default_rng(100 + len(name))
+        x = data_rng.normal(size=(3,) + spatial).astype(np.float32)
+        y = data_rng.integers(0, 4, (1,) + spatial).astype(np.uint8)
+        tr = ref_ds.ImageTransform(**kw)
+        okw = {k: v for k, v in kw.items() if k != 'seed'}
+        orng = np.random.default_rng(kw.get('seed'))
+        out[f'{name}/x'], out[f'{name}/y'] = x, y
+        for c in range(calls):
+            del captured[:]
+            xr, yr = tr(x, y)
+            xo, yo, rec = orc.image_transform(x, y, orng, **okw)
+            assert np.array_equal(np.asarray(xr), np.asarray(xo)) and np.array_equal(np.asarray(yr), np.asarray(yo)), (name, c)
+            if captured:
+                # one AffineTransform per apply_transform call (x and y): identical
+                m, o = captured[0]
+                nd = len(spatial)
+                assert np.allclose(m.reshape(nd, nd), rec['matrix'], rtol=0, atol=1e-12) and np.allclose(o, rec['offset'], rtol=0, atol=1e-9)
+                out[f'{name}/{c}/matrix'], out[f'{name}/{c}/offset'] = m.reshape(nd, nd), o
+            else:
+                assert rec['matrix'] is None
+            out[f'{name}/{c}/flips'] = np.asarray(rec['flips'])
+            out[f'{name}/{c}/xo'] = np.ascontiguousarray(xr)
+            out[f'{name}/{c}/yo'] = np.ascontiguousarray(yr)
+        print(f'  augment {name}: {calls} calls identical (reference ImageTransform vs oracle)')
+    save('augment', **out)
+
+
 def case_full():
     """BASELINE config 1: HNOSegXS(4,4,24,[3]*8,(10,14,14)) on one 1x4x240x240x155 volume."""
     torch.manual_seed(0)
@@ -475,6 +582,7 @@ if __name__ == '__main__':
     case_block()
     case_losses()
     case_input_side()
+    case_augment()
     case_model()
     case_hnoseg()
     case_fourier_operator()
