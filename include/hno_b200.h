@@ -213,6 +213,17 @@ int hno_head_forward(const void* tables_host, const void* tables_dev, const floa
  * the probabilities back; here one byte per voxel leaves the device. */
 int hno_head_argmax(const void* tables_host, const void* tables_dev, const float* logits_low, unsigned char* labels,
                     int B, int C, long P, void* stream);
+/* Full-resolution head of the use_resize=False models (nets/hnosegxs.py:102-109, 150, 174-180; nets/architectures.py:286-289,
+ * 345-351): no interpolation; conv_out runs through hno_pwconv_forward and these apply the output activation between the
+ * planar logits [B][C][D][P] and the dense probabilities [B][C][D][H][W] (activation 0 none, 1 softmax; C <= 8), produce
+ * the uint8 argmax label map (first maximum, as np.argmax at experiments/train_test.py:402-408), and run the backward
+ * (padding columns of dlogits = 0; probs may be NULL for activation 0). */
+int hno_head_direct_forward(const float* logits, float* probs, int B, int C, int D, int H, int W, long P, int activation,
+                            void* stream);
+int hno_head_direct_argmax(const float* logits, unsigned char* labels, int B, int C, int D, int H, int W, long P,
+                           void* stream);
+int hno_head_direct_backward(const float* dprobs, const float* probs, float* dlogits, int B, int C, int D, int H, int W,
+                             long P, int activation, void* stream);
 size_t hno_head_backward_workspace_bytes(const void* tables_host, int B, int C);
 /* dprobs, probs [B][C][Dx][Hx][Wx] -> dlogits_low [B][C][D][P] (padding columns = 0). */
 int hno_head_backward(const void* tables_host, const void* tables_dev, const float* dprobs, const float* probs,

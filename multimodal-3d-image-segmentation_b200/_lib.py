@@ -63,6 +63,9 @@ SIGNATURES = {
     'hno_interp_tables_fill': (_I, [_P, _Z] + [_I] * 6),
     'hno_head_forward': (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _P]),
     'hno_head_argmax': (_I, [_P, _P, _P, _P, _I, _I, _L, _P]),
+    'hno_head_direct_forward': (_I, [_P, _P, _I, _I, _I, _I, _I, _L, _I, _P]),
+    'hno_head_direct_argmax': (_I, [_P, _P, _I, _I, _I, _I, _I, _L, _P]),
+    'hno_head_direct_backward': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _I, _P]),
     'hno_head_backward_workspace_bytes': (_Z, [_P, _I, _I]),
     'hno_head_backward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
     'hno_loss_workspace_bytes': (_Z, [_I, _I]),

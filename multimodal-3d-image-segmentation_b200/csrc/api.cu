@@ -72,6 +72,8 @@ size_t interp_tables_bytes(int, int, int, int, int, int);
 int interp_tables_fill(void*, size_t, int, int, int, int, int, int);
 int head_forward(const void*, const void*, const float*, float*, int, int, long, int, cudaStream_t);
 int head_argmax(const void*, const void*, const float*, uint8_t*, int, int, long, cudaStream_t);
+int head_direct_forward(const float*, float*, uint8_t*, int, int, int, int, int, long, int, cudaStream_t);
+int head_direct_backward(const float*, const float*, float*, int, int, int, int, int, long, int, cudaStream_t);
 int dsconv_forward(const float* const*, const int*, int, const float*, const float*, float*, const float*, float*, int, int,
                    long, int, cudaStream_t);
 size_t dsconv_backward_workspace_bytes(int, int, int, long);
@@ -239,6 +241,21 @@ size_t hno_interp_tables_bytes(int D, int H, int W, int Dx, int Hx, int Wx) {
 
 int hno_interp_tables_fill(void* host_buf, size_t bytes, int D, int H, int W, int Dx, int Hx, int Wx) {
   return interp_tables_fill(host_buf, bytes, D, H, W, Dx, Hx, Wx);
+}
+
+int hno_head_direct_forward(const float* logits, float* probs, int B, int C, int D, int H, int W, long P, int activation,
+                            void* stream) {
+  return head_direct_forward(logits, probs, nullptr, B, C, D, H, W, P, activation, ST(stream));
+}
+
+int hno_head_direct_argmax(const float* logits, unsigned char* labels, int B, int C, int D, int H, int W, long P,
+                           void* stream) {
+  return head_direct_forward(logits, nullptr, labels, B, C, D, H, W, P, 0, ST(stream));
+}
+
+int hno_head_direct_backward(const float* dprobs, const float* probs, float* dlogits, int B, int C, int D, int H, int W,
+                             long P, int activation, void* stream) {
+  return head_direct_backward(dprobs, probs, dlogits, B, C, D, H, W, P, activation, ST(stream));
 }
 
 int hno_head_argmax(const void* tables_host, const void* tables_dev, const float* logits_low, unsigned char* labels,

@@ -1573,4 +1573,103 @@ int head_loss_backward(const void* th, const void* td, const float* ll, const ui
   return head_backward_passes(th, t, g1, g2, dll, B, C, P, st);
 }
 
+// ------------------------------------------------------------------------------------------ full-resolution head
+// use_resize=False (nets/hnosegxs.py:102-109, 150, 174-180; nets/architectures.py:286-289, 345-351): the network runs at
+// the image resolution, there is no interpolation, and the head is conv_out (hno_pwconv_forward) followed by the output
+// activation.  These kernels are that activation between the planar logits [B][C][D][P] and the dense probabilities
+// [B][C][D][H][W]: one thread per planar position, all classes in registers, coalesced along the plane.
+template <int C, int ACT>
+__global__ void __launch_bounds__(256) k_head_direct_fwd(const float* __restrict__ ll, float* __restrict__ probs,
+                                                         uint8_t* __restrict__ labels, long DP, long P, long HW) {
+  const long j = blockIdx.x * 256L + threadIdx.x;
+  if (j >= DP) return;
+  const long d = j / P, col = j - d * P;
+  if (col >= HW) return;
+  const int b = blockIdx.y;
+  const long v = d * HW + col, N = (DP / P) * HW;
+  float lg[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) lg[c] = __ldg(ll + ((long)b * C + c) * DP + j);
+  if (labels != nullptr) {  // np.argmax: the first maximum
+    int best = 0;
+#pragma unroll
+    for (int c = 1; c < C; ++c)
+      if (lg[c] > lg[best]) best = c;
+    labels[(long)b * N + v] = (uint8_t)best;
+    return;
+  }
+  if (ACT == 1) softmax_inplace<C>(lg);
+#pragma unroll
+  for (int c = 0; c < C; ++c) probs[((long)b * C + c) * N + v] = lg[c];
+}
+
+// d logits_c = p_c (dp_c - sum_k dp_k p_k) for the softmax, dp_c without activation; padding columns of the planes get 0
+template <int C, int ACT>
+__global__ void __launch_bounds__(256) k_head_direct_bwd(const float* __restrict__ dprobs,
+                                                         const float* __restrict__ probs, float* __restrict__ dll,
+                                                         long DP, long P, long HW) {
+  const long j = blockIdx.x * 256L + threadIdx.x;
+  if (j >= DP) return;
+  const long d = j / P, col = j - d * P;
+  const int b = blockIdx.y;
+  float g[C];
+  if (col < HW) {
+    const long v = d * HW + col, N = (DP / P) * HW;
+    float dot = 0.f, p[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      g[c] = __ldg(dprobs + ((long)b * C + c) * N + v);
+      if (ACT == 1) {
+        p[c] = __ldg(probs + ((long)b * C + c) * N + v);
+        dot = fmaf(g[c], p[c], dot);
+      }
+    }
+    if (ACT == 1) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) g[c] = p[c] * (g[c] - dot);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) g[c] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) dll[((long)b * C + c) * DP + j] = g[c];
+}
+
+static int head_direct_check(const char* who, int B, int D, int H, int W, long P) {
+  HNO_CHECK(B >= 1 && B <= 65535 && D >= 1 && H >= 1 && W >= 1, "%s: bad sizes", who);
+  HNO_CHECK(P >= (long)H * W, "%s: plane pitch too small", who);
+  return 0;
+}
+
+int head_direct_forward(const float* ll, float* probs, uint8_t* labels, int B, int C, int D, int H, int W, long P,
+                        int activation, cudaStream_t st) {
+  HNO_CHECK(ll && (probs != nullptr) != (labels != nullptr), "head_direct_forward: pass logits and exactly one output");
+  HNO_CHECK(activation == 0 || activation == 1, "head_direct_forward: activation must be 0 (none) or 1 (softmax)");
+  if (head_direct_check("head_direct_forward", B, D, H, W, P)) return -1;
+  const long DP = (long)D * P, HW = (long)H * W;
+  dim3 grid(ceil_div(DP, 256), B);
+  HNO_CLASS_SWITCH(C, {
+    if (activation == 1) k_head_direct_fwd<kC, 1><<<grid, 256, 0, st>>>(ll, probs, labels, DP, P, HW);
+    else k_head_direct_fwd<kC, 0><<<grid, 256, 0, st>>>(ll, probs, labels, DP, P, HW);
+  })
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
+int head_direct_backward(const float* dprobs, const float* probs, float* dll, int B, int C, int D, int H, int W,
+                         long P, int activation, cudaStream_t st) {
+  HNO_CHECK(dprobs && dll && (activation == 0 || probs), "head_direct_backward: null pointer");
+  HNO_CHECK(activation == 0 || activation == 1, "head_direct_backward: activation must be 0 (none) or 1 (softmax)");
+  if (head_direct_check("head_direct_backward", B, D, H, W, P)) return -1;
+  const long DP = (long)D * P, HW = (long)H * W;
+  dim3 grid(ceil_div(DP, 256), B);
+  HNO_CLASS_SWITCH(C, {
+    if (activation == 1) k_head_direct_bwd<kC, 1><<<grid, 256, 0, st>>>(dprobs, probs, dll, DP, P, HW);
+    else k_head_direct_bwd<kC, 0><<<grid, 256, 0, st>>>(dprobs, probs, dll, DP, P, HW);
+  })
+  HNO_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace hno

@@ -475,8 +475,12 @@ static int bwd_t(const float* dy, const float* y, const float* in1, const float*
   return reduce_partials(partials, grid, CO * CI, CO, dweight, dbias, (flags & 8) ? 1 : 0, st);
 }
 
-// (CI1, CI2, CO, ACT, RES) combinations the model needs, for filters F in {8, 12, 24} and heads of 2..4 classes.
+// (CI1, CI2, CO, ACT, RES) combinations the model needs, for filters F in {8, 12, 24} and heads of 2..4 classes; the 4 -> F
+// rows are conv1 of the use_resize=False models reading the (4-channel, or zero-padded to 4) image directly.
 #define HNO_PW_CONFIGS(X) \
+  X(4, 0, 8, 1, false)    \
+  X(4, 0, 12, 1, false)   \
+  X(4, 0, 24, 1, false)   \
   X(8, 0, 8, 1, true)     \
   X(8, 0, 8, 1, false)    \
   X(8, 8, 8, 1, false)    \
@@ -514,7 +518,7 @@ int pwconv_forward(const float* in1, const float* in2, const float* w, const flo
                    int ci2, int co, long S, int act, int residual, cudaStream_t st) {
   HNO_CHECK(in1 && w && out && (ci2 == 0 || in2), "pwconv_forward: null pointer");
   HNO_CHECK(B >= 1 && B <= 65535 && S >= 1, "pwconv_forward: bad sizes B=%d S=%ld", B, S);
-  if (!residual && (ci2 == 0 || ci2 == ci1) && S >= 4096) {
+  if (!residual && (ci2 == 0 || ci2 == ci1) && S >= 4096 && ci1 >= 8) {
     // tensor-core path (tcgen05, 3xTF32): the activation streams through TMA exactly once
     TcStreamArgs a{};
     a.a[0] = in1;

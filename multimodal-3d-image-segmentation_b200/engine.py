@@ -20,6 +20,68 @@ class _Saved:
     pass
 
 
+def _entry_forward(m, x, S):
+    """First activation of the network and the grid the blocks run on.  use_resize=True: the stride-2 stem (reference
+    nets/hnosegxs.py:102-105, 150-151).  use_resize=False (:102-109 skipped): the image itself as a planar tensor -- a view
+    when the channel count is a multiple of 4 and the plane needs no padding (4 x 240 x 240 x 155: both hold), else a
+    zero-padded copy; conv1's weight gets zero columns for the padding channels (S.w1)."""
+    image = tuple(x.shape[2:])
+    B, C = x.shape[:2]
+    w1 = _w2(m.conv1.op)
+    if m.use_resize:
+        D, H, W = ops.stem_out_shape(image)
+        pitch = plane_pitch(H, W)
+        a0 = ops.stem_forward(x, m.conv_in.op.weight, m.conv_in.op.bias, pitch)
+    else:
+        D, H, W = image
+        pitch = plane_pitch(H, W)
+        cp = (C + 3) // 4 * 4
+        if cp == C and pitch == H * W:
+            a0 = x.view(B, C, D, pitch)
+        else:
+            a0 = x.new_zeros((B, cp, D, pitch))
+            a0[:, :C, :, :H * W] = x.view(B, C, D, H * W)
+            if cp != C:
+                w1 = torch.nn.functional.pad(w1, (0, cp - C))
+    S.x, S.geom, S.a0, S.w1 = x, (D, H, W, pitch), a0, w1
+    S.a1 = ops.pwconv_forward(a0, None, w1, m.conv1.op.bias, 1, False)
+    return S.a1
+
+
+def _entry_backward(m, S, dcur, hw, dst_w1=None, dst_b1=None, dst_win=None, dst_bin=None):
+    """Gradients of conv1 and (use_resize=True) the stem: [g_win, g_bin,] g_w1, g_b1 in named_slots() order."""
+    op = m.conv1.op
+    if m.use_resize:
+        dpre0, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, S.w1, 1, False, hw=hw, in1_is_selu=True,
+                                                   dweight=dst_w1, dbias=dst_b1)
+        g_win, g_bin = ops.stem_backward(dpre0, S.x, m.filters, S.geom[3], dweight=dst_win, dbias=dst_bin)
+        return [g_win, g_bin, g_w1.reshape(op.weight.shape), g_b1]
+    cin = m.in_channels
+    padded = S.w1.shape[1] != cin
+    _, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, S.w1, 1, False, hw=hw, need_in1=False,
+                                           dweight=None if padded else dst_w1, dbias=dst_b1)
+    if padded:
+        g_w1 = g_w1[:, :cin]
+        if dst_w1 is not None:
+            dst_w1.copy_(g_w1)
+            g_w1 = dst_w1
+    return [g_w1.reshape(op.weight.shape), g_b1]
+
+
+def _head_forward(m, S, image, act):
+    """Probabilities (or logits, act 0) at the image resolution from the low-resolution logits S.ll."""
+    D, H, W, pitch = S.geom
+    if m.use_resize:
+        return ops.head_forward(S.ll, S.tables, pitch, act)
+    return ops.head_direct_forward(S.ll, (D, H, W), act)
+
+
+def _head_backward(m, S, dprobs):
+    if m.use_resize:
+        return ops.head_backward(dprobs, S.probs, S.tables, S.geom[3], S.act)
+    return ops.head_direct_backward(dprobs, S.probs, S.geom[3], S.act)
+
+
 class XSEngine:
     def __init__(self, model):
         self.model = model
@@ -28,7 +90,8 @@ class XSEngine:
     def named_slots(self):
         """[(parameter, kind)] in a fixed order; the backward returns gradients in the same order."""
         m = self.model
-        slots = [m.conv_in.op.weight, m.conv_in.op.bias, m.conv1.op.weight, m.conv1.op.bias]
+        slots = [m.conv_in.op.weight, m.conv_in.op.bias] if m.use_resize else []
+        slots += [m.conv1.op.weight, m.conv1.op.bias]
         for layer in m.layers:
             if layer.mapping_conv is not None:
                 slots += [layer.mapping_conv.op.weight, layer.mapping_conv.op.bias]
@@ -64,20 +127,15 @@ class XSEngine:
             raise ValueError(f'HNOSegXS expects (B, {m.in_channels}, D, H, W) input, got {tuple(x.shape)}')
         x = x.contiguous()
         dev = x.device
-        B = x.shape[0]
         image = tuple(x.shape[2:])
-        D, H, W = ops.stem_out_shape(image)
-        pitch = plane_pitch(H, W)
+        S = _Saved()
+        a1 = _entry_forward(m, x, S)
+        D, H, W, pitch = S.geom
         plan = get_crop_plan((D, H, W), m.num_modes, dev)
         inv_n = 1.0 / plan.n_voxels
         shared = m.weights_type == 'shared'
         nb = len(m.layers)
-        S = _Saved()
-        S.x, S.geom, S.plan = x, (D, H, W, pitch), plan
-
-        a0 = ops.stem_forward(x, m.conv_in.op.weight, m.conv_in.op.bias, pitch)
-        a1 = ops.pwconv_forward(a0, None, _w2(m.conv1.op), m.conv1.op.bias, 1, False)
-        S.a0, S.a1 = a0, a1
+        S.plan = plan
         cur = a1
         stash = {}
         S.blocks = []
@@ -131,11 +189,11 @@ class XSEngine:
             S.ll = ops.dsconv_forward(S.ds, _w2(m.conv_out), None, act=0)[0]
         else:
             S.ll = ops.pwconv_forward(cur, None, _w2(m.conv_out), None, 0, False)
-        S.tables = get_interp_tables((D, H, W), image, dev)
+        S.tables = get_interp_tables((D, H, W), image, dev) if m.use_resize else None
         S.act = 1 if m.output_activation == 'softmax' else 0
         probs = None
         if head:
-            probs = ops.head_forward(S.ll, S.tables, pitch, S.act)
+            probs = _head_forward(m, S, image, S.act)
             S.probs = probs
         return probs, S
 
@@ -169,7 +227,7 @@ class XSEngine:
             labels, coef, grad_loss = fused
             dll = ops.head_loss_backward(S.ll, labels, coef, grad_loss, S.tables, pitch)
         else:
-            dll = ops.head_backward(dprobs, S.probs, S.tables, pitch, S.act)
+            dll = _head_backward(m, S, dprobs)
         dw_, _ = out_w(m.conv_out)
         dstash = {}
         if m.use_deep_supervision:
@@ -244,13 +302,10 @@ class XSEngine:
             block_grads[i] = g
         assert not dstash, 'unconsumed skip / deep-supervision gradients'
         dw_, db_ = out_w(m.conv1.op)
-        dpre0, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, _w2(m.conv1.op), 1, False, hw=hw,
-                                                   in1_is_selu=True, dweight=dw_, dbias=db_)
-        dw_, db_ = out_w(m.conv_in.op)
-        g_win, g_bin = ops.stem_backward(dpre0, S.x, F, pitch, dweight=dw_, dbias=db_)
+        dwin_, dbin_ = out_w(m.conv_in.op) if m.use_resize else (None, None)
+        grads = _entry_backward(m, S, dcur, hw, dw_, db_, dwin_, dbin_)
         if dst is not None:
             return dst
-        grads = [g_win, g_bin, g_w1.reshape(m.conv1.op.weight.shape), g_b1]
         for g in block_grads:
             grads += g
         grads.append(g_out.reshape(m.conv_out.weight.shape))
@@ -290,14 +345,28 @@ class _XSLossFunction(torch.autograd.Function):
         if S.act != 1:
             raise NotImplementedError('the fused loss needs output_activation="softmax"')
         lab = _labels_u8(labels, x)
+        ctx.engine, ctx.S, ctx.lab = engine, S, lab
+        if S.tables is None:
+            # use_resize=False: no interpolation to fuse with; the probabilities are formed once at the image resolution and
+            # the moment-based loss kernels run on them and the one-hot labels (hno_to_categorical + hno_loss_*)
+            from .experiments.utils import to_categorical
+            S.probs = _head_forward(engine.model, S, tuple(x.shape[2:]), 1)
+            ctx.onehot = to_categorical(lab[:, None], S.probs.shape[1], validate=False)
+            loss, ctx.coef = ops.prob_loss_forward(S.probs, ctx.onehot, kind, param)
+            return loss[0]
         loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], kind, param)
-        ctx.engine, ctx.S, ctx.lab, ctx.coef = engine, S, lab, coef
+        ctx.coef = coef
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         g = g.reshape(1).to(torch.float32).contiguous()
-        grads = ctx.engine.run_backward(ctx.S, fused=(ctx.lab, ctx.coef, g))
+        if ctx.S.tables is None:
+            dprobs = ops.prob_loss_backward(ctx.S.probs, ctx.onehot, ctx.coef, g)
+            grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs)
+            ctx.onehot = None
+        else:
+            grads = ctx.engine.run_backward(ctx.S, fused=(ctx.lab, ctx.coef, g))
         ctx.S = None
         return (None, None, None, None, None) + tuple(grads)
 
@@ -358,8 +427,6 @@ class TransSegEngine:
 
     @classmethod
     def supports(cls, model):
-        if not getattr(model, 'use_resize', True):
-            return False
         for blk in model.layers:
             if cls.block_kind(blk) is None or blk.conv_branch is None or blk.conv_concat is None:
                 return False
@@ -380,7 +447,8 @@ class TransSegEngine:
 
     def named_slots(self):
         m = self.model
-        slots = [m.conv_in.op.weight, m.conv_in.op.bias, m.conv1.op.weight, m.conv1.op.bias]
+        slots = [m.conv_in.op.weight, m.conv_in.op.bias] if m.use_resize else []
+        slots += [m.conv1.op.weight, m.conv1.op.bias]
         for blk in m.layers:
             slots.append(blk.conv_branch.weight)
             if blk.conv_branch.bias is not None:
@@ -406,13 +474,9 @@ class TransSegEngine:
         x = x.contiguous()
         dev = x.device
         image = tuple(x.shape[2:])
-        D, H, W = ops.stem_out_shape(image)
-        pitch = plane_pitch(H, W)
         S = _Saved()
-        S.x, S.geom = x, (D, H, W, pitch)
-        a0 = ops.stem_forward(x, m.conv_in.op.weight, m.conv_in.op.bias, pitch)
-        a1 = ops.pwconv_forward(a0, None, _w2(m.conv1.op), m.conv1.op.bias, 1, False)
-        S.a0, S.a1 = a0, a1
+        a1 = _entry_forward(m, x, S)
+        D, H, W, pitch = S.geom
         ds = [a1] if m.conv_ds is not None else None
         cur = a1
         S.blocks = []
@@ -458,11 +522,11 @@ class TransSegEngine:
             S.d, S.ll = ops.dsconv_forward(ds, _w2(m.conv_ds.op), m.conv_ds.op.bias, act=1, weight2=_w2(m.conv_out))
         else:
             S.ll = ops.pwconv_forward(cur, None, _w2(m.conv_out), None, 0, False)
-        S.tables = get_interp_tables((D, H, W), image, dev)
+        S.tables = get_interp_tables((D, H, W), image, dev) if m.use_resize else None
         S.act = 1 if m.output_activation_name == 'softmax' else 0
         probs = None
         if head:
-            probs = ops.head_forward(S.ll, S.tables, pitch, S.act)
+            probs = _head_forward(m, S, image, S.act)
             S.probs = probs
         return probs, S
 
@@ -477,7 +541,7 @@ class TransSegEngine:
             labels, coef, grad_loss = fused
             dll = ops.head_loss_backward(S.ll, labels, coef, grad_loss, S.tables, pitch)
         else:
-            dll = ops.head_backward(dprobs, S.probs, S.tables, pitch, S.act)
+            dll = _head_backward(m, S, dprobs)
         nb = len(m.layers)
         tail = []
         if S.ds is not None:
@@ -524,10 +588,7 @@ class TransSegEngine:
             g += g_op + [g_wc.reshape(opc.weight.shape), g_bc]
             block_grads[i] = g
             dcur = dx
-        dpre0, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, _w2(m.conv1.op), 1, False, hw=hw,
-                                                   in1_is_selu=True)
-        g_win, g_bin = ops.stem_backward(dpre0, S.x, F, pitch)
-        grads = [g_win, g_bin, g_w1.reshape(m.conv1.op.weight.shape), g_b1]
+        grads = _entry_backward(m, S, dcur, hw)
         for g in block_grads:
             grads += g
         grads += tail

@@ -134,8 +134,6 @@ class _TransSeg(nn.Module):
             raise NotImplementedError(f'hno_b200 {type(self).__name__} supports 3-D (ndim=5) only')
         if not _is_selu(activation):
             raise NotImplementedError('hno_b200 implements the SELU (self-normalising) variant only')
-        if not use_resize:
-            raise NotImplementedError('hno_b200: use_resize=False is not supported')
         if output_activation not in ('softmax', None):
             raise NotImplementedError("hno_b200: output_activation must be 'softmax' or None")
         self.in_channels = in_channels
@@ -153,9 +151,13 @@ class _TransSeg(nn.Module):
 
     def create_layers(self):
         f = self.filters
-        self.conv_in = ConvNormAct(self.in_channels, f, kernel_size=2, stride=2, use_bias=True,
-                                   activation=self.activation, ndim=self.ndim, device=self.device)
-        self.conv1 = ConvNormAct(f, f, use_bias=True, activation=self.activation, ndim=self.ndim, device=self.device)
+        self.conv_in = None
+        cur = self.in_channels
+        if self.use_resize:  # reference :286-289; without it the blocks run at the image resolution
+            self.conv_in = ConvNormAct(cur, f, kernel_size=2, stride=2, use_bias=True, activation=self.activation,
+                                       ndim=self.ndim, device=self.device)
+            cur = f
+        self.conv1 = ConvNormAct(cur, f, use_bias=True, activation=self.activation, ndim=self.ndim, device=self.device)
         self.layers = nn.ModuleList([self.block(f, f) for _ in range(self.num_transform_blocks)])
         self.conv_ds = None
         cur = f
@@ -190,14 +192,16 @@ class _TransSeg(nn.Module):
     def forward(self, x):
         image_size = tuple(x.shape[2:])
         if x.is_meta:
-            y = self.conv1(self.conv_in(x))
+            y = self.conv1(self.conv_in(x) if self.use_resize else x)
             tensors = [y]
             for layer in self.layers:
                 y = layer(y)
                 tensors.append(y)
             if self.conv_ds is not None:
                 y = self.conv_ds(torch.cat(tensors, 1))
-            y = self.conv_out(nn.functional.interpolate(y, size=image_size, mode='trilinear'))
+            if self.use_resize:
+                y = nn.functional.interpolate(y, size=image_size, mode='trilinear')
+            y = self.conv_out(y)
             return torch.softmax(y, 1) if self.output_activation_name == 'softmax' else y
         from ..engine import TransSegEngine
         if TransSegEngine.supports(self):
@@ -210,6 +214,8 @@ class _TransSeg(nn.Module):
         if self.conv_ds is not None:
             raise NotImplementedError('hno_b200: deep supervision needs blocks the fused engine supports (Hartley operator with '
                                       'shared weights or Hartley multi-head attention, concat skip)')
+        if not self.use_resize:
+            raise NotImplementedError('hno_b200: use_resize=False needs blocks the fused engine supports')
         x = self.conv1(self.conv_in(x))
         for layer in self.layers:
             x = layer(x)

@@ -168,8 +168,6 @@ class HNOSegXS(nn.Module):
             raise NotImplementedError('hno_b200 HNOSegXS supports 3-D volumes (ndim=5) only')
         if not _is_selu(activation):
             raise NotImplementedError('hno_b200 HNOSegXS implements the SELU (self-normalising) variant only')
-        if not use_resize:
-            raise NotImplementedError('hno_b200 HNOSegXS requires use_resize=True (the stride-2 stem)')
         if output_activation not in ('softmax', None, 'identity'):
             raise NotImplementedError("hno_b200 HNOSegXS supports output_activation in {'softmax', None}")
         if np.isscalar(self.num_transform_blocks):
@@ -182,9 +180,13 @@ class HNOSegXS(nn.Module):
         block = partial(HNOXSBlock, num_modes=self.num_modes, weights_type=self.weights_type, ndim=self.ndim,
                         activation=self.activation, device=self.device, use_block_concat=self.use_block_concat)
         f = self.filters
-        self.conv_in = ConvNormAct(self.in_channels, f, kernel_size=2, stride=2, use_bias=True,
-                                   activation=self.activation, ndim=self.ndim, device=self.device)
-        self.conv1 = ConvNormAct(f, f, use_bias=True, activation=self.activation, ndim=self.ndim, device=self.device)
+        self.conv_in = None
+        cur = self.in_channels
+        if self.use_resize:  # reference :102-105; without it the blocks run at the image resolution
+            self.conv_in = ConvNormAct(cur, f, kernel_size=2, stride=2, use_bias=True, activation=self.activation,
+                                       ndim=self.ndim, device=self.device)
+            cur = f
+        self.conv1 = ConvNormAct(cur, f, use_bias=True, activation=self.activation, ndim=self.ndim, device=self.device)
         self.layers = nn.ModuleList()
         nb = len(self.num_transform_blocks)
         for i, n_convs in enumerate(self.num_transform_blocks):
@@ -224,6 +226,8 @@ class HNOSegXS(nn.Module):
         """Full-resolution logits, i.e. the output of conv_out (reference :178) before the softmax."""
         with torch.no_grad():
             _, S = self.engine().run_forward(x, save=False, head=False)
+            if S.tables is None:  # use_resize=False
+                return ops.head_direct_forward(S.ll, S.geom[:3], 0)
             return ops.head_forward(S.ll, S.tables, S.geom[3], 0)
 
     def predict_labels(self, x):
@@ -232,6 +236,8 @@ class HNOSegXS(nn.Module):
         materialised (4 bytes x classes per voxel neither written nor copied back)."""
         with torch.no_grad():
             _, S = self.engine().run_forward(x, save=False, head=False)
+            if S.tables is None:  # use_resize=False
+                return ops.head_direct_argmax(S.ll, S.geom[:3])
             return ops.head_argmax(S.ll, S.tables, S.geom[3])
 
     def loss(self, x, labels, loss_name='DiceLoss', param=None):
@@ -245,6 +251,8 @@ class HNOSegXS(nn.Module):
         if self.use_deep_supervision:
             raise NotImplementedError('hno_b200: forward_modular does not implement deep supervision; use forward()')
         image_size = tuple(x.shape[2:])
+        if not self.use_resize:
+            raise NotImplementedError('hno_b200: forward_modular covers the use_resize=True network; use forward()')
         x = self.conv1(self.conv_in(x))
         nb = len(self.layers)
         stash = {}

@@ -558,6 +558,58 @@ def head_backward(dprobs, probs, tables, pitch, activation=1):
     return dll
 
 
+def head_direct_forward(logits, spatial, activation=1):
+    """Full-resolution head of the use_resize=False models: planar logits (B, C, D, P) -> dense output (B, C, D, H, W) with
+    the softmax over the classes (activation=1) or as they are (0).  No interpolation (reference nets/hnosegxs.py:174-180
+    with use_resize False)."""
+    _require_cuda(logits, 'logits')
+    logits = logits.contiguous()
+    B, C = logits.shape[:2]
+    D, H, W = spatial
+    P = _geom(logits)[2]
+    probs = torch.empty((B, C, D, H, W), dtype=torch.float32, device=logits.device)
+    call('hno_head_direct_forward', ptr(logits), ptr(probs), B, C, D, H, W, P, int(activation), stream_ptr())
+    return probs
+
+
+def head_direct_argmax(logits, spatial):
+    """uint8 label map (B, D, H, W) of planar full-resolution logits (first maximum, like np.argmax)."""
+    _require_cuda(logits, 'logits')
+    logits = logits.contiguous()
+    B, C = logits.shape[:2]
+    D, H, W = spatial
+    labels = torch.empty((B, D, H, W), dtype=torch.uint8, device=logits.device)
+    call('hno_head_direct_argmax', ptr(logits), ptr(labels), B, C, D, H, W, _geom(logits)[2], stream_ptr())
+    return labels
+
+
+def head_direct_backward(dprobs, probs, pitch, activation=1):
+    """Gradient of the planar logits (B, C, D, pitch); padding columns are zero."""
+    B, C, D, H, W = dprobs.shape
+    dll = torch.empty((B, C, D, pitch), dtype=torch.float32, device=dprobs.device)
+    call('hno_head_direct_backward', ptr(dprobs.contiguous()), ptr(probs), ptr(dll), B, C, D, H, W, pitch,
+         int(activation), stream_ptr())
+    return dll
+
+
+class HeadDirect(torch.autograd.Function):
+    """Output activation of a use_resize=False network on planar or dense logits (softmax over dim 1, or identity)."""
+
+    @staticmethod
+    def forward(ctx, logits, spatial, activation):
+        logits = logits.contiguous()
+        probs = head_direct_forward(logits, spatial, activation)
+        ctx.save_for_backward(probs)
+        ctx.cfg = (_geom(logits)[2], activation, tuple(logits.shape))
+        return probs
+
+    @staticmethod
+    def backward(ctx, dprobs):
+        (probs,) = ctx.saved_tensors
+        pitch, activation, shape = ctx.cfg
+        return head_direct_backward(dprobs, probs, pitch, activation).view(shape), None, None
+
+
 class HeadUpsample(torch.autograd.Function):
     """probs = softmax(trilinear(logits_low)) (activation=1) or just the interpolation (activation=0)."""
 
@@ -587,16 +639,9 @@ class ProbabilityLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y_pred, y_true, kind, param=0.0):
-        _require_cuda(y_pred, 'y_pred')
         y_pred = y_pred.contiguous()
         y_true = y_true.contiguous().to(torch.float32)
-        B, C = y_pred.shape[:2]
-        N = _flat_s(y_pred)
-        loss = torch.empty((1,), dtype=torch.float32, device=y_pred.device)
-        coef = torch.empty((B * C * 3,), dtype=torch.float32, device=y_pred.device)
-        ws = workspace(_lib.load().hno_loss_workspace_bytes(B, C), y_pred.device, 'loss')
-        call('hno_loss_forward', ptr(y_pred), ptr(y_true), ptr(loss), ptr(coef), ptr(ws), B, C, N, int(kind),
-             float(param), stream_ptr())
+        loss, coef = prob_loss_forward(y_pred, y_true, kind, param)
         ctx.save_for_backward(y_pred, y_true, coef)
         return loss[0]
 
@@ -605,12 +650,30 @@ class ProbabilityLoss(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             raise RuntimeError('hno_b200: losses do not provide a gradient w.r.t. y_true')
         y_pred, y_true, coef = ctx.saved_tensors
-        B, C = y_pred.shape[:2]
-        N = _flat_s(y_pred)
-        dyp = torch.empty_like(y_pred)
+        return prob_loss_backward(y_pred, y_true, coef, g), None, None, None
+
+
+def prob_loss_forward(y_pred, y_true, kind, param=0.0):
+    """(loss[1], coef[B*C*3]) of DiceLoss / PCCLoss / ExpDiceLoss on contiguous fp32 probabilities and one-hot targets."""
+    _require_cuda(y_pred, 'y_pred')
+    B, C = y_pred.shape[:2]
+    N = _flat_s(y_pred)
+    loss = torch.empty((1,), dtype=torch.float32, device=y_pred.device)
+    coef = torch.empty((B * C * 3,), dtype=torch.float32, device=y_pred.device)
+    ws = workspace(_lib.load().hno_loss_workspace_bytes(B, C), y_pred.device, 'loss')
+    call('hno_loss_forward', ptr(y_pred), ptr(y_true), ptr(loss), ptr(coef), ptr(ws), B, C, N, int(kind),
+         float(param), stream_ptr())
+    return loss, coef
+
+
+def prob_loss_backward(y_pred, y_true, coef, g):
+    B, C = y_pred.shape[:2]
+    N = _flat_s(y_pred)
+    dyp = torch.empty_like(y_pred)
+    if g is not None:  # None: d loss / d loss = 1
         g = g.reshape(1).to(torch.float32).contiguous()
-        call('hno_loss_backward', ptr(y_pred), ptr(y_true), ptr(coef), ptr(g), ptr(dyp), B, C, N, stream_ptr())
-        return dyp, None, None, None
+    call('hno_loss_backward', ptr(y_pred), ptr(y_true), ptr(coef), ptr(g), ptr(dyp), B, C, N, stream_ptr())
+    return dyp
 
 
 def _ce_check(y_pred, y_true, labels):

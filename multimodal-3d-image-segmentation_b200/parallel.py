@@ -210,6 +210,15 @@ class Trainer:
                 loss = ops.ce_loss_forward(probs, labels=lab)
                 self._backward(S, dprobs=ops.ce_loss_backward(probs, labels=lab))
                 return loss
+            if not getattr(self.model, 'use_resize', True):
+                # full-resolution network: no interpolation to fuse the loss with; probabilities once, then the moment-based
+                # loss kernels on them and the one-hot labels
+                from .experiments.utils import to_categorical
+                probs, S = self.engine.run_forward(x, save=True)
+                onehot = to_categorical(lab[:, None], probs.shape[1], validate=False)
+                loss, coef = ops.prob_loss_forward(probs, onehot, self.kind, self.loss_param)
+                self._backward(S, dprobs=ops.prob_loss_backward(probs, onehot, coef, None))
+                return loss
             _, S = self.engine.run_forward(x, save=True, head=False)
             loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], self.kind, self.loss_param)
             self._backward(S, fused=(lab, coef, None))

@@ -339,10 +339,12 @@ def hno_block(x, sd, prefix, modes, use_block_skip=True, patch=None):
 
 def hnoseg_forward(sd, x, num_transform_blocks, num_modes, softmax=True, return_logits=False, use_block_skip=True,
                    patch=None):
-    """_TransSeg.forward (architectures.py:321-353) for NeuralOperatorSeg(..., 'Hartley'), use_resize=True, no deep
-    supervision."""
+    """_TransSeg.forward (architectures.py:321-353) for NeuralOperatorSeg(..., 'Hartley'); use_resize and deep supervision
+    are read off the state_dict (conv_in / conv_ds present or not, :286-289, :306-311)."""
     image_size = x.shape[2:]
-    x = selu(F.conv3d(x, sd['conv_in.op.weight'], sd['conv_in.op.bias'], stride=2, padding=1))
+    use_resize = 'conv_in.op.weight' in sd
+    if use_resize:
+        x = selu(F.conv3d(x, sd['conv_in.op.weight'], sd['conv_in.op.bias'], stride=2, padding=1))
     x = selu(pointwise(x, sd['conv1.op.weight'], sd['conv1.op.bias']))
     deep = 'conv_ds.op.weight' in sd  # use_deep_supervision (architectures.py:306-311, 330-343): every block output joins
     tensors = [x]
@@ -351,7 +353,8 @@ def hnoseg_forward(sd, x, num_transform_blocks, num_modes, softmax=True, return_
         tensors.append(x)
     if deep:
         x = selu(pointwise(torch.cat(tensors, dim=1), sd['conv_ds.op.weight'], sd['conv_ds.op.bias']))
-    x = F.interpolate(x, size=tuple(image_size), mode='trilinear')
+    if use_resize:
+        x = F.interpolate(x, size=tuple(image_size), mode='trilinear')
     logits = center_padcrop(pointwise(x, sd['conv_out.weight']), image_size)
     out = torch.softmax(logits, dim=1) if softmax else logits
     return (out, logits) if return_logits else out
@@ -471,7 +474,7 @@ def init_state_dict(in_channels, out_channels, filters, num_transform_blocks, nu
 def train_step(sd, x, labels, num_transform_blocks, num_modes, loss='DiceLoss'):
     """One step of experiments/train_test.py:146-171 without the optimizer: returns (loss, grads by key)."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    probs = hnosegxs_forward(params, x, num_transform_blocks, num_modes)
+    probs = hnosegxs_forward(params, x, num_transform_blocks, num_modes, use_resize='conv_in.op.weight' in sd)
     value = LOSSES[loss](probs, to_categorical(labels, probs.shape[1]).to(probs.dtype))
     grads = torch.autograd.grad(value, list(params.values()))
     return value.detach(), dict(zip(params.keys(), grads))

@@ -469,6 +469,61 @@ def case_augment():
     save('augment', **out)
 
 
+def case_noresize():
+    """use_resize=False (nets/hnosegxs.py:102-109, 150, 174; nets/architectures.py:286-289, 345-347): the blocks run at the
+    image resolution, no stem and no interpolation.  HNOSegXS with 2 input channels on a grid whose planes need padding and
+    with 4 channels on one that does not, and NeuralOperatorSeg('Hartley') with deep supervision: forward + Dice gradients."""
+    out = {}
+    xs_cases = (('xs2', 2, (11, 10, 9), 31), ('xs4', 4, (10, 8, 8), 32))
+    for tag, cin, spatial, seed in xs_cases:
+        torch.manual_seed(seed)
+        cfg = dict(in_channels=cin, out_channels=3, filters=8, num_transform_blocks=[1, 2, 1, 2], num_modes=(2, 3, 3),
+                   use_resize=False)
+        model = ref.HNOSegXS(**cfg)
+        x = torch.randn(2, cin, *spatial)
+        labels = torch.randint(0, 3, (2, 1) + spatial)
+        onehot = torch.zeros(2, 3, *spatial).scatter_(1, labels, 1.0)
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        assert 'conv_in.op.weight' not in sd
+        probs = model(x)
+        loss = ref_losses.DiceLoss()(probs, onehot)
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        check(f'{tag} probs', orc.hnosegxs_forward(sd, x, cfg['num_transform_blocks'], cfg['num_modes'], use_resize=False),
+              probs.detach())
+        o_loss, o_grads = orc.train_step(sd, x, labels, cfg['num_transform_blocks'], cfg['num_modes'], 'DiceLoss')
+        check(f'{tag} DiceLoss value', o_loss, loss.detach(), 1e-6)
+        for k in grads:
+            check(f'{tag} grad {k}', o_grads[k], grads[k], 2e-4)
+        out.update({f'{tag}/x': x.numpy(), f'{tag}/labels': labels.numpy().astype(np.uint8), f'{tag}/probs': probs.detach().numpy(),
+                    f'{tag}/loss': loss.detach().numpy()})
+        out.update({f'{tag}/sd/{k}': v.numpy() for k, v in sd.items()})
+        out.update({f'{tag}/grad/{k}': v.numpy() for k, v in grads.items()})
+    torch.manual_seed(33)
+    cfg = dict(in_channels=3, out_channels=3, filters=8, num_transform_blocks=2, num_modes=(2, 3, 3), transform_type='Hartley',
+               use_resize=False, use_deep_supervision=True)
+    model = ref.NeuralOperatorSeg(**cfg)
+    spatial = (10, 9, 12)
+    x = torch.randn(2, 3, *spatial)
+    labels = torch.randint(0, 3, (2, 1) + spatial)
+    onehot = torch.zeros(2, 3, *spatial).scatter_(1, labels, 1.0)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    probs = model(x)
+    loss = ref_losses.DiceLoss()(probs, onehot)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    check('hnoseg probs', orc.hnoseg_forward(sd, x, 2, cfg['num_modes']), probs.detach())
+    o_loss, o_grads = orc.hnoseg_train_step(sd, x, labels, 2, cfg['num_modes'], 'DiceLoss')
+    check('hnoseg DiceLoss value', o_loss, loss.detach(), 1e-6)
+    for k in grads:
+        check(f'hnoseg grad {k}', o_grads[k], grads[k], 2e-4)
+    out.update({'hnoseg/x': x.numpy(), 'hnoseg/labels': labels.numpy().astype(np.uint8), 'hnoseg/probs': probs.detach().numpy(),
+                'hnoseg/loss': loss.detach().numpy()})
+    out.update({f'hnoseg/sd/{k}': v.numpy() for k, v in sd.items()})
+    out.update({f'hnoseg/grad/{k}': v.numpy() for k, v in grads.items()})
+    save('noresize_small', **out)
+
+
 def case_full():
     """BASELINE config 1: HNOSegXS(4,4,24,[3]*8,(10,14,14)) on one 1x4x240x240x155 volume."""
     torch.manual_seed(0)
@@ -583,6 +638,7 @@ if __name__ == '__main__':
     case_losses()
     case_input_side()
     case_augment()
+    case_noresize()
     case_model()
     case_hnoseg()
     case_fourier_operator()
