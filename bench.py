@@ -36,6 +36,10 @@ SPECS = {
     'xs_train': dict(
         kind='train', model='HNOSegXS', kwargs=CFG, metric=METRIC, volume=VOLUME,
         what='HNOSegXS(4,4,24,[3]*8,(10,14,14))', act_gb='~10 GB'),
+    'xs_noresize_train': dict(  # the same network with use_resize=False: blocks at the image resolution (no stem, no interpolation)
+        kind='train', model='HNOSegXS', kwargs=dict(CFG, use_resize=False), volume=VOLUME,
+        metric='HNOSeg-XS (use_resize=False) train volumes/s @4x240x240x155',
+        what='HNOSegXS(4,4,24,[3]*8,(10,14,14),use_resize=False)', act_gb='~45 GB'),
     'hnoseg_train': dict(  # experiments/config_files/config_hnoseg.ini
         kind='train', model='NeuralOperatorSeg', volume=VOLUME,
         kwargs=dict(in_channels=4, out_channels=4, filters=24, num_transform_blocks=24, num_modes=(10, 14, 14),
@@ -597,6 +601,9 @@ def main():
     ap.add_argument('--loss', default='DiceLoss', choices=['DiceLoss', 'PCCLoss'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-table', action='store_true')
+    ap.add_argument('--augment', action='store_true',
+                    help="end-to-end loop only: the loader's random affine augmentation (experiments/config_files/"
+                         "config_hnoseg_xs.ini [augmentation]) on the device, every step, on the raw batch and its labels")
     ap.add_argument('--config', default='xs_train', choices=sorted(SPECS),
                     help='workload: xs_train = BASELINE config 2 (default, what the driver measures); the others time '
                          'BASELINE configs 3 / 4 / 5 and the HNOSeg config')
@@ -697,6 +704,11 @@ def main():
 
     loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+    augment = None
+    if args.augment:
+        from multimodal_3d_image_segmentation_b200.experiments.data_io import ImageTransform
+        augment = ImageTransform(rotation_range=[30, 30, 30], shift_range=[0.2, 0.2, 0.2], zoom_range=[0.8, 1.2],
+                                 augmentation_probability=0.8, seed=1 + rank)
 
     def e2e_loop(k):
         # Every step's loss is copied device -> host and read by the host inside the timed region (the reference prints it,
@@ -712,7 +724,7 @@ def main():
                 issue_copy(i + 1)
             slot = i % 2
             cur.wait_event(ready[slot])
-            lv = trainer.step_raw(bufs[slot][0], bufs[slot][1], mask_val=0)
+            lv = trainer.step_raw(bufs[slot][0], bufs[slot][1], mask_val=0, augment=augment)
             freed[slot].record(cur)
             loss_host[slot].copy_(lv.reshape(1), non_blocking=True)
             loss_done[slot].record(cur)
@@ -763,7 +775,9 @@ def main():
                 'gpu_launches': e2e_launches, 'numa': numa,
                 'what': 'Trainer.step_raw: pinned int16 raw modalities + uint8 labels copied H2D every step (double-buffered '
                         'copy stream), z-scored per sample and modality on the device (normalize_modalities, run.py:52-55), '
-                        'train step, every loss copied D2H and read by the host one step behind'},
+                        'train step, every loss copied D2H and read by the host one step behind'
+                        + ('; random affine augmentation of the normalised batch and its labels on the device every step '
+                           '(hno_affine_resample_nn, parameters drawn on the host like dataset.py:106-178)' if args.augment else '')},
         'gpu_launches': launches, 'loss': final_loss,
     }
     if args.config == 'mha_train' and not args.no_kernel_table:

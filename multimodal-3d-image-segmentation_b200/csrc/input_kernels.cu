@@ -228,7 +228,14 @@ int normalize_modalities(const void* data, int elem_bytes, float* out, void* ws,
 // channels of that input voxel -- or cval when the index leaves the buffer (ITK: continuous index in [-0.5, size - 0.5)).
 // The coordinates are fp64 with an explicit operation order (no FMA contraction), so the CPU oracle reproduces every
 // rounding decision.  A gather of 1 / 2 / 4-byte elements: HBM bound, one read + one write of the batch.
-template <typename T>
+template <typename T, int V>
+struct alignas(sizeof(T) * V) AugPack {
+  T v[V];
+};
+
+// V consecutive output voxels (linear index) per thread: the gathers stay scalar, the store is one sizeof(T) * V word
+// (4 B for uint8, 8 B for int16, 16 B for fp32 at V = 4), which is what keeps the write side coalesced for the narrow types.
+template <typename T, int V>
 __global__ void __launch_bounds__(256) k_affine_resample_nn(const T* __restrict__ in, T* __restrict__ out,
                                                             const double* __restrict__ xform,
                                                             const int* __restrict__ flags, int C, int D, int H, int W,
@@ -241,32 +248,60 @@ __global__ void __launch_bounds__(256) k_affine_resample_nn(const T* __restrict_
   double m[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) m[k] = xform[b * 12 + k];
-  for (long i = blockIdx.x * 256L + threadIdx.x; i < N; i += (long)gridDim.x * 256L) {
-    const int w = (int)(i % W);
+  for (long g = blockIdx.x * 256L + threadIdx.x; g < N / V; g += (long)gridDim.x * 256L) {
+    const long i = g * V;
+    int w = (int)(i % W);
     const long t = i / W;
-    const int h = (int)(t % H);
-    const int d = (int)(t / H);
-    const int px = (fl & 4) ? W - 1 - w : w;
-    const int py = (fl & 2) ? H - 1 - h : h;
-    const int pz = (fl & 1) ? D - 1 - d : d;
-    long src;
-    if (fl & 8) {  // no geometric transform was drawn for this sample: flips only
-      src = ((long)pz * H + py) * W + px;
-    } else {
-      const double x = (double)px, y = (double)py, z = (double)pz;
-      double c[3];
+    int h = (int)(t % H);
+    int d = (int)(t / H);
+    long src[V];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        double s = __dadd_rn(__dmul_rn(m[4 * r + 0], x), __dmul_rn(m[4 * r + 1], y));
-        s = __dadd_rn(s, __dmul_rn(m[4 * r + 2], z));
-        c[r] = floor(__dadd_rn(__dadd_rn(s, m[4 * r + 3]), 0.5));
+    for (int e = 0; e < V; ++e) {
+      const int px = (fl & 4) ? W - 1 - w : w;
+      const int py = (fl & 2) ? H - 1 - h : h;
+      const int pz = (fl & 1) ? D - 1 - d : d;
+      if (fl & 8) {  // no geometric transform was drawn for this sample: flips only
+        src[e] = ((long)pz * H + py) * W + px;
+      } else {
+        const double x = (double)px, y = (double)py, z = (double)pz;
+        double c[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          double s = __dadd_rn(__dmul_rn(m[4 * r + 0], x), __dmul_rn(m[4 * r + 1], y));
+          s = __dadd_rn(s, __dmul_rn(m[4 * r + 2], z));
+          c[r] = floor(__dadd_rn(__dadd_rn(s, m[4 * r + 3]), 0.5));
+        }
+        const bool inside = c[0] >= 0.0 && c[0] < (double)W && c[1] >= 0.0 && c[1] < (double)H && c[2] >= 0.0 &&
+                            c[2] < (double)D;
+        src[e] = inside ? ((long)c[2] * H + (long)c[1]) * W + (long)c[0] : -1;
       }
-      const bool inside = c[0] >= 0.0 && c[0] < (double)W && c[1] >= 0.0 && c[1] < (double)H && c[2] >= 0.0 &&
-                          c[2] < (double)D;
-      src = inside ? ((long)c[2] * H + (long)c[1]) * W + (long)c[0] : -1;
+      if (++w == W) {
+        w = 0;
+        if (++h == H) h = 0, ++d;
+      }
     }
-    for (int ch = 0; ch < C; ++ch) ob[ch * N + i] = src >= 0 ? __ldg(ib + ch * N + src) : cval;
+    for (int ch = 0; ch < C; ++ch) {
+      AugPack<T, V> pk;
+#pragma unroll
+      for (int e = 0; e < V; ++e) pk.v[e] = src[e] >= 0 ? __ldg(ib + ch * N + src[e]) : cval;
+      *reinterpret_cast<AugPack<T, V>*>(ob + ch * N + i) = pk;
+    }
   }
+}
+
+template <typename T>
+static void affine_resample_launch(const void* in, void* out, const double* xform, const int* flags, int B, int C, int D,
+                                   int H, int W, T cval, cudaStream_t st) {
+  const long N = (long)D * H * W;
+  const bool v4 = N % 4 == 0 && reinterpret_cast<uintptr_t>(out) % (4 * sizeof(T)) == 0;
+  const long items = v4 ? N / 4 : N;
+  dim3 grid((unsigned)((items + 255) / 256 < 8L * sm_count() ? (items + 255) / 256 : 8L * sm_count()), B);
+  if (v4)
+    k_affine_resample_nn<T, 4><<<grid, 256, 0, st>>>(static_cast<const T*>(in), static_cast<T*>(out), xform, flags, C, D,
+                                                     H, W, cval);
+  else
+    k_affine_resample_nn<T, 1><<<grid, 256, 0, st>>>(static_cast<const T*>(in), static_cast<T*>(out), xform, flags, C, D,
+                                                     H, W, cval);
 }
 
 int affine_resample_nn(const void* in, void* out, int elem_bytes, const double* xform, const int* flags, int B, int C,
@@ -276,18 +311,9 @@ int affine_resample_nn(const void* in, void* out, int elem_bytes, const double* 
   HNO_CHECK(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4,
             "affine_resample_nn: elements must be uint8 (1), int16 (2) or float32 (4)");
   HNO_CHECK(B >= 1 && B <= 65535 && C >= 1 && D >= 1 && H >= 1 && W >= 1, "affine_resample_nn: bad sizes");
-  const long N = (long)D * H * W;
-  dim3 grid((unsigned)((N + 255) / 256 < 8L * sm_count() ? (N + 255) / 256 : 8L * sm_count()), B);
-  if (elem_bytes == 1) {
-    k_affine_resample_nn<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out),
-                                                        xform, flags, C, D, H, W, (uint8_t)cval);
-  } else if (elem_bytes == 2) {
-    k_affine_resample_nn<int16_t><<<grid, 256, 0, st>>>(static_cast<const int16_t*>(in), static_cast<int16_t*>(out),
-                                                        xform, flags, C, D, H, W, (int16_t)cval);
-  } else {
-    k_affine_resample_nn<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), xform,
-                                                      flags, C, D, H, W, (float)cval);
-  }
+  if (elem_bytes == 1) affine_resample_launch<uint8_t>(in, out, xform, flags, B, C, D, H, W, (uint8_t)cval, st);
+  else if (elem_bytes == 2) affine_resample_launch<int16_t>(in, out, xform, flags, B, C, D, H, W, (int16_t)cval, st);
+  else affine_resample_launch<float>(in, out, xform, flags, B, C, D, H, W, (float)cval, st);
   HNO_LAUNCH_CHECK();
   return 0;
 }

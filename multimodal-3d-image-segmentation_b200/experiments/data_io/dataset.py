@@ -126,15 +126,17 @@ class ImageTransform:
 
     transform = __call__
 
-    def batch(self, x, y=None, params=None):
-        """`params`: optional list of (xform, flags) per sample (from `draw`), e.g. to replay an augmentation."""
+    def batch(self, x, y=None, params=None, out_x=None, out_y=None):
+        """`params`: optional list of (xform, flags) per sample (from `draw`), e.g. to replay an augmentation.
+        `out_x` / `out_y`: optional destination tensors (same shape and dtype as x / y; must not alias them), e.g. buffers whose
+        addresses a captured CUDA graph holds; when given they are always written (a plain copy if nothing was drawn)."""
         spatial = tuple(x.shape[2:])
         if len(spatial) not in (2, 3):
             raise ValueError(f'ImageTransform.batch expects (B, C, H, W) or (B, C, D, H, W), got {tuple(x.shape)}')
         B = x.shape[0]
         if params is None:
             params = [self.draw(spatial) for _ in range(B)]
-        if all(p[0] is None and p[1] == 0 for p in params):
+        if all(p[0] is None and p[1] == 0 for p in params) and out_x is None and out_y is None:
             return x if y is None else (x, y)  # the reference returns its inputs untouched, too
         host = np.zeros((B, 12))
         flags = np.zeros((B,), dtype=np.int32)
@@ -147,18 +149,18 @@ class ImageTransform:
         dev = x.device
         xf_dev = torch.from_numpy(host).to(dev)
         fl_dev = torch.from_numpy(flags).to(dev)
-        xo = _resample(x, xf_dev, fl_dev, self.cval)
+        xo = _resample(x, xf_dev, fl_dev, self.cval, out_x)
         if y is None:
             return xo
         if tuple(y.shape[2:]) != spatial or y.shape[0] != B:
             raise ValueError('ImageTransform.batch: x and y must share the batch size and the spatial shape')
-        return xo, _resample(y, xf_dev, fl_dev, self.cval)
+        return xo, _resample(y, xf_dev, fl_dev, self.cval, out_y)
 
 
 _BYTES = {torch.uint8: 1, torch.int16: 2, torch.float32: 4}
 
 
-def _resample(t, xf_dev, fl_dev, cval):
+def _resample(t, xf_dev, fl_dev, cval, out=None):
     if not isinstance(t, torch.Tensor) or t.device.type != 'cuda':
         raise RuntimeError('hno_b200: ImageTransform works on CUDA tensors; this package has no CPU path')
     if t.device.index is not None and t.device.index != torch.cuda.current_device():
@@ -175,7 +177,13 @@ def _resample(t, xf_dev, fl_dev, cval):
     B, C = t.shape[:2]
     sp = tuple(t.shape[2:])
     D, H, W = (1,) + sp if len(sp) == 2 else sp
-    out = torch.empty_like(t)
+    if out is not None:
+        if (out.dtype != t.dtype or orig != t.dtype or out.shape != t.shape or not out.is_contiguous() or out.device != t.device
+                or out.data_ptr() == t.data_ptr()):
+            raise ValueError('ImageTransform: out must be a distinct contiguous tensor of the shape and dtype of its input '
+                             '(uint8, int16 or float32)')
+    else:
+        out = torch.empty_like(t)
     call('hno_affine_resample_nn', ptr(t), ptr(out), _BYTES[t.dtype], ptr(xf_dev), ptr(fl_dev), B, C, D, H, W,
          float(cval), stream_ptr())
     return out if out.dtype == orig else out.to(orig)

@@ -199,13 +199,15 @@ class Trainer:
         self._direct = 'dst' in inspect.signature(self.engine.run_backward).parameters
         self.optimizer = FusedAdamax(self.flat, lr=lr)
         self.group = group
-        # SAMPLE STREAMS (HNO_SAMPLE_STREAMS, default on): the samples of a batch are independent until the loss is averaged
-        # (every loss term is a mean over (sample, label) pairs), so each sample's forward + loss + backward runs as its own
-        # chain of launches on one of two streams.  Roughly a quarter of a step is L2-resident, latency-bound work (H stages,
-        # spectral core: ~85 us forward / ~110 us backward per block) during which HBM idles; with two independent chains in
-        # flight the other sample's HBM-bound kernels fill those gaps.  Sample b > 0 writes its gradient into a second flat
-        # buffer that is added once at the end; the per-sample losses are averaged.
-        self.sample_streams = (os.environ.get('HNO_SAMPLE_STREAMS', '1') != '0' and self._direct and self.kind is not None
+        # SAMPLE STREAMS (HNO_SAMPLE_STREAMS=1, default off): the samples of a batch are independent until the loss is averaged
+        # (every loss term is a mean over (sample, label) pairs), so each sample's forward + loss + backward can run as its own
+        # chain of launches on one of two streams; sample b > 0 writes its gradient into a second flat buffer that is added
+        # once at the end, the per-sample losses are averaged.  The idea: a quarter of a step is L2-resident, latency-bound work
+        # (H stages, spectral core) during which HBM idles, and the other sample's HBM-bound kernels could fill those gaps.
+        # MEASURED (profiles/r4b_bench_split.json vs r4b_bench_nosplit.json): 9.56 ms against 9.26 ms for the batched chain --
+        # the persistent HBM-bound kernels occupy every SM's shared memory, so kernels of the other stream only start in their
+        # tails, and twice the launches (27,100 per 100 steps against 13,600) each pay their prologue.  Kept as an A/B switch.
+        self.sample_streams = (os.environ.get('HNO_SAMPLE_STREAMS', '0') == '1' and self._direct and self.kind is not None
                                and getattr(model, 'use_resize', True))
         self._streams = None
         self._flat2 = None
@@ -337,18 +339,27 @@ class Trainer:
         self.optimizer.step(lr)
         return loss
 
-    def step_raw(self, x_raw, labels, lr=None, mask_val=0, clip_val=None):
+    def step_raw(self, x_raw, labels, lr=None, mask_val=0, clip_val=None, augment=None):
         """step() on RAW modalities in their storage type: `x_raw` (B, C, D, H, W) int16 (or float32) un-normalised
         intensities as the reader returns them (experiments/utils.py:260-270).  The per-sample, per-modality z-scoring the
         reference runs in its loader workers (`x_processing = normalize_modalities(mask_val=0)`, experiments/run.py:52-55,
         data_io/dataset.py:49-50) happens here on the device, so a batch crosses PCIe at 2 bytes per voxel instead of 4.
-        The normalised batch lives in one buffer owned by the trainer (its address is what the CUDA graph captured)."""
+        The normalised batch lives in one buffer owned by the trainer (its address is what the CUDA graph captured).
+        `augment`: an experiments.data_io.ImageTransform; like the reference's loader (data_io/dataset.py:49-56: x_processing
+        first, then the transform on image and labels) the NORMALISED batch and its label maps are augmented, one gather
+        launch each, into two more trainer-owned buffers."""
         from .experiments.utils import normalize_rows
         key = (tuple(x_raw.shape), x_raw.device)
         buf = self._xnorm.get(key)
         if buf is None:
             buf = self._xnorm[key] = torch.empty(x_raw.shape, dtype=torch.float32, device=x_raw.device)
         normalize_rows(x_raw, x_raw.shape[0] * x_raw.shape[1], mask_val=mask_val, clip_val=clip_val, out=buf)
+        if augment is not None:
+            akey = key + (tuple(labels.shape), labels.dtype)
+            abuf = self._xnorm.get(akey)
+            if abuf is None:
+                abuf = self._xnorm[akey] = (torch.empty_like(buf), torch.empty_like(labels))
+            buf, labels = augment.batch(buf, labels, out_x=abuf[0], out_y=abuf[1])
         return self.step(buf, labels, lr)
 
 
