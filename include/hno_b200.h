@@ -196,6 +196,10 @@ size_t hno_stem_backward_workspace_bytes(int cin, int f);
 /* dpre: gradient w.r.t. the PRE-activation of the stem output, [B][F][D][P]. */
 int hno_stem_backward(const float* dpre, const float* x, float* dweight, float* dbias, void* workspace, int B,
                       int cin, int f, int Dx, int Hx, int Wx, long P, int accumulate, void* stream);
+/* gradient w.r.t. the image (the transposed convolution; autograd of nets/hnosegxs.py:150-151 w.r.t. x):
+ * dx [B][cin][Dx][Hx][Wx] = sum_o weight[o][.][k] dpre[o][(z + 1) / 2], k = (z + 1) % 2 per axis.  Overwrites dx. */
+int hno_stem_backward_input(const float* dpre, const float* weight, float* dx, int B, int cin, int f, int Dx, int Hx,
+                            int Wx, long P, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Head: trilinear up-sampling (F.interpolate, align_corners=False) of the low-resolution logits

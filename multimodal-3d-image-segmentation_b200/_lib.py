@@ -59,6 +59,7 @@ SIGNATURES = {
     'hno_stem_forward': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _P]),
     'hno_stem_backward_workspace_bytes': (_Z, [_I, _I]),
     'hno_stem_backward': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _I, _P]),
+    'hno_stem_backward_input': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _P]),
     'hno_interp_tables_bytes': (_Z, [_I] * 6),
     'hno_interp_tables_fill': (_I, [_P, _Z] + [_I] * 6),
     'hno_head_forward': (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _P]),

@@ -68,6 +68,7 @@ int stem_forward(const float*, const float*, const float*, float*, int, int, int
 size_t stem_backward_workspace_bytes(int, int);
 int stem_backward(const float*, const float*, float*, float*, void*, int, int, int, int, int, int, long, int,
                   cudaStream_t);
+int stem_backward_input(const float*, const float*, float*, int, int, int, int, int, int, long, cudaStream_t);
 size_t interp_tables_bytes(int, int, int, int, int, int);
 int interp_tables_fill(void*, size_t, int, int, int, int, int, int);
 int head_forward(const void*, const void*, const float*, float*, int, int, long, int, cudaStream_t);
@@ -233,6 +234,11 @@ size_t hno_stem_backward_workspace_bytes(int cin, int f) { return stem_backward_
 int hno_stem_backward(const float* dpre, const float* x, float* dweight, float* dbias, void* workspace, int B, int cin,
                       int f, int Dx, int Hx, int Wx, long P, int accumulate, void* stream) {
   return stem_backward(dpre, x, dweight, dbias, workspace, B, cin, f, Dx, Hx, Wx, P, accumulate, ST(stream));
+}
+
+int hno_stem_backward_input(const float* dpre, const float* weight, float* dx, int B, int cin, int f, int Dx, int Hx,
+                            int Wx, long P, void* stream) {
+  return stem_backward_input(dpre, weight, dx, B, cin, f, Dx, Hx, Wx, P, ST(stream));
 }
 
 size_t hno_interp_tables_bytes(int D, int H, int W, int Dx, int Hx, int Wx) {

@@ -401,4 +401,61 @@ int stem_backward(const float* dpre, const float* x, float* dweight, float* dbia
   return -1;
 }
 
+// Input gradient (the transposed convolution).  Stride == kernel, so every input voxel z feeds exactly one output voxel
+// d = (z + 1) >> 1 through tap k = (z + 1) & 1 per axis:  dx[i][z] = sum_o W[o][i][k] dpre[o][d].  One thread per input voxel;
+// the eight voxels of a patch read the same F values of dpre (cache hits).  Only needed when the caller asks for the
+// gradient w.r.t. the image (autograd-differentiable w.r.t. the input); training never does.
+template <int CIN, int F>
+__global__ void __launch_bounds__(256) k_stem_dx(const float* __restrict__ dpre, const float* __restrict__ weight,
+                                                 float* __restrict__ dx, StemGeom g) {
+  constexpr int Q = 8 * CIN;
+  __shared__ float wt[Q * F];  // wt[q][o]
+  for (int idx = threadIdx.x; idx < Q * F; idx += 256) {
+    const int q = idx / F, o = idx - q * F;
+    wt[idx] = weight[o * Q + q];
+  }
+  __syncthreads();
+  const long Nx = (long)g.Dx * g.HWx;
+  const long v = blockIdx.x * 256L + threadIdx.x;
+  if (v >= Nx) return;
+  const int b = blockIdx.y;
+  const int zw = (int)(v % g.Wx);
+  const long r = v / g.Wx;
+  const int zh = (int)(r % g.Hx);
+  const int zd = (int)(r / g.Hx);
+  const int d = (zd + 1) >> 1, h = (zh + 1) >> 1, w = (zw + 1) >> 1;
+  const int t = (((zd + 1) & 1) << 2) | (((zh + 1) & 1) << 1) | ((zw + 1) & 1);
+  const float* dp = dpre + (long)b * F * g.S + (long)d * g.P + (long)h * g.W + w;
+  float acc[CIN];
+#pragma unroll
+  for (int i = 0; i < CIN; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int o = 0; o < F; ++o) {
+    const float gv = __ldg(dp + (long)o * g.S);
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) acc[i] = fmaf(wt[(i * 8 + t) * F + o], gv, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < CIN; ++i) dx[((long)b * CIN + i) * Nx + v] = acc[i];
+}
+
+int stem_backward_input(const float* dpre, const float* weight, float* dx, int B, int cin, int f, int Dx, int Hx, int Wx,
+                        long P, cudaStream_t st) {
+  HNO_CHECK(dpre && weight && dx, "stem_backward_input: null pointer");
+  HNO_CHECK(B >= 1 && B <= 65535, "stem_backward_input: bad batch size");
+  StemGeom g;
+  if (make_geom(&g, Dx, Hx, Wx, P)) return -1;
+  dim3 grid(ceil_div((long)Dx * g.HWx, 256), B);
+#define X(A, B_)                                                      \
+  if (cin == A && f == B_) {                                          \
+    k_stem_dx<A, B_><<<grid, 256, 0, st>>>(dpre, weight, dx, g);      \
+    HNO_LAUNCH_CHECK();                                               \
+    return 0;                                                         \
+  }
+  HNO_STEM_CONFIGS(X)
+#undef X
+  set_error("stem_backward_input: unsupported configuration in_channels=%d filters=%d", cin, f);
+  return -1;
+}
+
 }  // namespace hno

@@ -48,18 +48,25 @@ def _entry_forward(m, x, S):
     return S.a1
 
 
-def _entry_backward(m, S, dcur, hw, dst_w1=None, dst_b1=None, dst_win=None, dst_bin=None):
-    """Gradients of conv1 and (use_resize=True) the stem: [g_win, g_bin,] g_w1, g_b1 in named_slots() order."""
+def _entry_backward(m, S, dcur, hw, dst_w1=None, dst_b1=None, dst_win=None, dst_bin=None, need_dx=False):
+    """Gradients of conv1 and (use_resize=True) the stem: [g_win, g_bin,] g_w1, g_b1 in named_slots() order.  `need_dx`: also
+    the gradient w.r.t. the image, left in S.dx (training never asks for it: the image is data)."""
     op = m.conv1.op
+    S.dx = None
     if m.use_resize:
         dpre0, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, S.w1, 1, False, hw=hw, in1_is_selu=True,
                                                    dweight=dst_w1, dbias=dst_b1)
         g_win, g_bin = ops.stem_backward(dpre0, S.x, m.filters, S.geom[3], dweight=dst_win, dbias=dst_bin)
+        if need_dx:
+            S.dx = ops.stem_backward_input(dpre0, m.conv_in.op.weight, tuple(S.x.shape[2:]), S.geom[3])
         return [g_win, g_bin, g_w1.reshape(op.weight.shape), g_b1]
     cin = m.in_channels
     padded = S.w1.shape[1] != cin
-    _, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, S.w1, 1, False, hw=hw, need_in1=False,
-                                           dweight=None if padded else dst_w1, dbias=dst_b1)
+    din, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, S.w1, 1, False, hw=hw, need_in1=need_dx,
+                                             dweight=None if padded else dst_w1, dbias=dst_b1)
+    if need_dx:  # planar (B, cp, D, pitch) -> the image's dense layout
+        B, _, D, H, W = S.x.shape
+        S.dx = din[:, :cin, :, :H * W].reshape(B, cin, D, H, W)
     if padded:
         g_w1 = g_w1[:, :cin]
         if dst_w1 is not None:
@@ -104,7 +111,7 @@ class XSEngine:
     # ------------------------------------------------------------------------------------------ public entry points
     def forward(self, x):
         params = self.named_slots()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
             return _XSFunction.apply(self, x, *params)
         return self.run_forward(x, save=False)[0]
 
@@ -198,8 +205,8 @@ class XSEngine:
         return probs, S
 
     # ------------------------------------------------------------------------------------------ backward
-    def run_backward(self, S, dprobs=None, fused=None, dst=None):
-        """Returns the gradients in named_slots() order.  Either `dprobs` (drop-in autograd) or
+    def run_backward(self, S, dprobs=None, fused=None, dst=None, need_dx=False):
+        """Returns the gradients in named_slots() order (need_dx: the image gradient is left in S.dx).  Either `dprobs` (drop-in autograd) or
         fused=(labels_u8, coef, grad_loss) (fused head + loss) drives the head.  `dst`: optional list of
         destination tensors in named_slots() order (views of a flat gradient buffer); they are overwritten."""
         m = self.model
@@ -303,7 +310,7 @@ class XSEngine:
         assert not dstash, 'unconsumed skip / deep-supervision gradients'
         dw_, db_ = out_w(m.conv1.op)
         dwin_, dbin_ = out_w(m.conv_in.op) if m.use_resize else (None, None)
-        grads = _entry_backward(m, S, dcur, hw, dw_, db_, dwin_, dbin_)
+        grads = _entry_backward(m, S, dcur, hw, dw_, db_, dwin_, dbin_, need_dx=need_dx)
         if dst is not None:
             return dst
         for g in block_grads:
@@ -331,11 +338,11 @@ class _XSFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dprobs):
-        if ctx.needs_input_grad[1]:
-            raise RuntimeError('hno_b200: HNOSegXS does not provide a gradient w.r.t. its input volume')
-        grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs.contiguous())
+        need_dx = ctx.needs_input_grad[1]
+        grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs.contiguous(), need_dx=need_dx)
+        dx = ctx.S.dx if need_dx else None
         ctx.S = None
-        return (None, None) + tuple(grads)
+        return (None, dx) + tuple(grads)
 
 
 class _XSLossFunction(torch.autograd.Function):
@@ -361,14 +368,16 @@ class _XSLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         g = g.reshape(1).to(torch.float32).contiguous()
+        need_dx = ctx.needs_input_grad[1]
         if ctx.S.tables is None:
             dprobs = ops.prob_loss_backward(ctx.S.probs, ctx.onehot, ctx.coef, g)
-            grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs)
+            grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs, need_dx=need_dx)
             ctx.onehot = None
         else:
-            grads = ctx.engine.run_backward(ctx.S, fused=(ctx.lab, ctx.coef, g))
+            grads = ctx.engine.run_backward(ctx.S, fused=(ctx.lab, ctx.coef, g), need_dx=need_dx)
+        dx = ctx.S.dx if need_dx else None
         ctx.S = None
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, dx, None, None, None) + tuple(grads)
 
 
 class _XSCrossEntropyFunction(torch.autograd.Function):
@@ -384,9 +393,11 @@ class _XSCrossEntropyFunction(torch.autograd.Function):
     def backward(ctx, g):
         g = g.reshape(1).to(torch.float32).contiguous()
         dprobs = ops.ce_loss_backward(ctx.probs, labels=ctx.lab, grad_loss=g)
-        grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs)
+        need_dx = ctx.needs_input_grad[1]
+        grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs, need_dx=need_dx)
+        dx = ctx.S.dx if need_dx else None
         ctx.S = ctx.probs = None
-        return (None, None, None) + tuple(grads)
+        return (None, dx, None) + tuple(grads)
 
 
 # =====================================================================================================================
@@ -462,7 +473,7 @@ class TransSegEngine:
 
     def forward(self, x):
         params = self.named_slots()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
             return _TransSegFunction.apply(self, x, *params)
         return self.run_forward(x, save=False)[0]
 
@@ -531,8 +542,9 @@ class TransSegEngine:
         return probs, S
 
     # ------------------------------------------------------------------------------------------ backward
-    def run_backward(self, S, dprobs=None, fused=None):
-        """Gradients in named_slots() order.  `dprobs` (drop-in autograd) or fused=(labels_u8, coef, grad_loss)."""
+    def run_backward(self, S, dprobs=None, fused=None, need_dx=False):
+        """Gradients in named_slots() order.  `dprobs` (drop-in autograd) or fused=(labels_u8, coef, grad_loss); need_dx: the
+        image gradient is left in S.dx."""
         m = self.model
         D, H, W, pitch = S.geom
         hw = (pitch, H * W)
@@ -588,7 +600,7 @@ class TransSegEngine:
             g += g_op + [g_wc.reshape(opc.weight.shape), g_bc]
             block_grads[i] = g
             dcur = dx
-        grads = _entry_backward(m, S, dcur, hw)
+        grads = _entry_backward(m, S, dcur, hw, need_dx=need_dx)
         for g in block_grads:
             grads += g
         grads += tail
@@ -605,8 +617,8 @@ class _TransSegFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dprobs):
-        if ctx.needs_input_grad[1]:
-            raise RuntimeError('hno_b200: the segmentation networks do not provide a gradient w.r.t. the input volume')
-        grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs.contiguous())
+        need_dx = ctx.needs_input_grad[1]
+        grads = ctx.engine.run_backward(ctx.S, dprobs=dprobs.contiguous(), need_dx=need_dx)
+        dx = ctx.S.dx if need_dx else None
         ctx.S = None
-        return (None, None) + tuple(grads)
+        return (None, dx) + tuple(grads)

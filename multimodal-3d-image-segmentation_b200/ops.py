@@ -502,24 +502,36 @@ def stem_backward(dpre, x, f, pitch=None, dweight=None, dbias=None, accumulate=F
     return dweight, dbias
 
 
+def stem_backward_input(dpre, weight, image, pitch=None):
+    """dx (B, cin, Dx, Hx, Wx): gradient of the stem w.r.t. the image from the gradient of its pre-activation."""
+    B, f = dpre.shape[:2]
+    cin = weight.shape[1]
+    Dx, Hx, Wx = image
+    D, H, W = stem_out_shape(image)
+    P = H * W if pitch is None else pitch
+    dx = torch.empty((B, cin, Dx, Hx, Wx), dtype=torch.float32, device=dpre.device)
+    call('hno_stem_backward_input', ptr(dpre.contiguous()), ptr(weight.contiguous()), ptr(dx), B, cin, f, Dx, Hx, Wx, P,
+         stream_ptr())
+    return dx
+
+
 class StemConv(torch.autograd.Function):
-    """selu(Conv3d(k=2, s=2, p=1)(x)); the gradient w.r.t. x is not provided (x is the network input)."""
+    """selu(Conv3d(k=2, s=2, p=1)(x)); the image gradient (transposed convolution) is computed only when asked for."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         y = stem_forward(x, weight, bias)
-        ctx.save_for_backward(x, y)
+        ctx.save_for_backward(x, y, weight)
         ctx.f = weight.shape[0]
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        if ctx.needs_input_grad[0]:
-            raise RuntimeError('hno_b200: the stem does not provide a gradient w.r.t. the network input')
-        x, y = ctx.saved_tensors
+        x, y, weight = ctx.saved_tensors
         dpre = selu_backward(dy, y)
         dw, db = stem_backward(dpre, x, ctx.f)
-        return None, dw, db
+        dx = stem_backward_input(dpre, weight, tuple(x.shape[2:])) if ctx.needs_input_grad[0] else None
+        return dx, dw, db
 
 
 def selu_backward(dy, y):
