@@ -36,6 +36,9 @@ SPECS = {
     'xs_train': dict(
         kind='train', model='HNOSegXS', kwargs=CFG, metric=METRIC, volume=VOLUME,
         what='HNOSegXS(4,4,24,[3]*8,(10,14,14))', act_gb='~10 GB'),
+    'xs_train_zyx': dict(  # SURVEY 8d's second row: the data-faithful axis order (SimpleITK arrays are (z, y, x): 155 x 240 x 240)
+        kind='train', model='HNOSegXS', kwargs=CFG, volume=(155, 240, 240),
+        metric='HNOSeg-XS train volumes/s @4x155x240x240', what='HNOSegXS(4,4,24,[3]*8,(10,14,14))', act_gb='~10 GB'),
     'xs_noresize_train': dict(  # the same network with use_resize=False: blocks at the image resolution (no stem, no interpolation)
         kind='train', model='HNOSegXS', kwargs=dict(CFG, use_resize=False), volume=VOLUME,
         metric='HNOSeg-XS (use_resize=False) train volumes/s @4x240x240x155',
@@ -149,7 +152,7 @@ def oracle_step_factory(torch, batch):
     to_categorical, DiceLoss, backward, Adamax -- on the host cores with all the threads torch can use."""
     from oracle import hno_oracle as orc
     kw = SPEC['kwargs']
-    if SPEC['model'] == 'HNOSegXS':
+    if SPEC['model'] == 'HNOSegXS' and kw.get('use_resize', True):
         sd = orc.init_state_dict(CFG['in_channels'], CFG['out_channels'], CFG['filters'], CFG['num_transform_blocks'],
                                  CFG['num_modes'], seed=0)
     else:  # CPU-constructed twin of the CUDA module: same parameter names / shapes (the modules hold plain nn.Parameters)
@@ -159,13 +162,14 @@ def oracle_step_factory(torch, batch):
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     opt = torch.optim.Adamax(list(params.values()), lr=5e-3)
     g = torch.Generator().manual_seed(1234)
-    x = torch.randn(batch, 4, *VOLUME, generator=g)
-    labels = torch.randint(0, 4, (batch, 1, *VOLUME), generator=g)
+    x = torch.randn(batch, 4, *SPEC['volume'], generator=g)
+    labels = torch.randint(0, 4, (batch, 1, *SPEC['volume']), generator=g)
 
     def step():
         y = orc.to_categorical(labels, 4)
         if SPEC['model'] == 'HNOSegXS':
-            probs = orc.hnosegxs_forward(params, x, CFG['num_transform_blocks'], CFG['num_modes'])
+            probs = orc.hnosegxs_forward(params, x, CFG['num_transform_blocks'], CFG['num_modes'],
+                                         use_resize=kw.get('use_resize', True))
         else:
             probs = orc.hnoseg_forward(params, x, kw['num_transform_blocks'], kw['num_modes'], patch=kw.get('patch_size'))
         loss = orc.dice_loss(probs, y)
@@ -180,7 +184,7 @@ def oracle_step_factory(torch, batch):
 def workload_config(args, world):
     """The `config` object of the JSON line: ONE definition for both arms, so the driver sees identical strings."""
     return {'workload': f'{SPEC["what"]} train step fp32 (fwd + {args.loss} + bwd + Adamax), '
-                        f'batch {args.batch}/GPU, 4x240x240x155 volumes, random-init weights',
+                        f'batch {args.batch}/GPU, 4x{"x".join(str(v) for v in SPEC["volume"])} volumes, random-init weights',
             'global_batch': world * args.batch, 'parallelism': f'dp{world}',
             'l2_policy': f'working set ({SPEC["act_gb"]} of activations per step) >> 126 MB L2; no explicit flush'}
 
@@ -659,9 +663,10 @@ def main():
     # noise on an offset, x_raw = round(1000 + 200 * randn), so that the per-sample per-modality z-scoring the reference
     # applies in its loader (normalize_modalities, experiments/run.py:52-55) -- here the first kernels of Trainer.step_raw --
     # hands the network the randn volumes SURVEY.md 8d asks for (quantised to 1/200).
-    xs_host = [(torch.randn(B, 4, *VOLUME, generator=gx) * 200.0 + 1000.0).round_().to(torch.int16).pin_memory()
+    VOL = SPEC['volume']
+    xs_host = [(torch.randn(B, 4, *VOL, generator=gx) * 200.0 + 1000.0).round_().to(torch.int16).pin_memory()
                for _ in range(n_host)]
-    ls_host = [torch.randint(0, 4, (B, 1, *VOLUME), generator=gl).to(torch.uint8).pin_memory() for _ in range(n_host)]
+    ls_host = [torch.randint(0, 4, (B, 1, *VOL), generator=gl).to(torch.uint8).pin_memory() for _ in range(n_host)]
     from multimodal_3d_image_segmentation_b200.experiments.utils import normalize_rows
     x_dev = normalize_rows(xs_host[0].to(dev), 4 * B, mask_val=0)  # the same batch, already normalised, resident in HBM
     l_dev = ls_host[0].to(dev)
