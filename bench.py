@@ -787,8 +787,8 @@ def main():
     }
     if args.config == 'mha_train' and not args.no_kernel_table:
         line.update(mha_attention_roofline(torch, dev, B))
-    if args.config == 'xs_train' and not args.no_kernel_table:
-        rows = kernel_table(torch, dev, B, peak)
+    if args.config in ('xs_train', 'xs_train_zyx') and not args.no_kernel_table:
+        rows = kernel_table(torch, dev, B, peak, VOLUME=SPEC['volume'])
         top = max(rows, key=lambda r: r['step_ms'])
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (never measured here)

@@ -1581,12 +1581,13 @@ int head_loss_backward(const void* th, const void* td, const float* ll, const ui
 template <int C, int ACT>
 __global__ void __launch_bounds__(256) k_head_direct_fwd(const float* __restrict__ ll, float* __restrict__ probs,
                                                          uint8_t* __restrict__ labels, long DP, long P, long HW) {
-  const long j = blockIdx.x * 256L + threadIdx.x;
-  if (j >= DP) return;
-  const long d = j / P, col = j - d * P;
+  // grid (plane chunks, D, B): no integer division in the index arithmetic (218 -> ~60 warp instructions per voxel)
+  const long col = blockIdx.x * 256L + threadIdx.x;
   if (col >= HW) return;
-  const int b = blockIdx.y;
-  const long v = d * HW + col, N = (DP / P) * HW;
+  const long d = blockIdx.y;
+  const int b = blockIdx.z;
+  const long j = d * P + col;
+  const long v = d * HW + col, N = (long)gridDim.y * HW;
   float lg[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) lg[c] = __ldg(ll + ((long)b * C + c) * DP + j);
@@ -1608,13 +1609,14 @@ template <int C, int ACT>
 __global__ void __launch_bounds__(256) k_head_direct_bwd(const float* __restrict__ dprobs,
                                                          const float* __restrict__ probs, float* __restrict__ dll,
                                                          long DP, long P, long HW) {
-  const long j = blockIdx.x * 256L + threadIdx.x;
-  if (j >= DP) return;
-  const long d = j / P, col = j - d * P;
-  const int b = blockIdx.y;
+  const long col = blockIdx.x * 256L + threadIdx.x;
+  if (col >= P) return;
+  const long d = blockIdx.y;
+  const int b = blockIdx.z;
+  const long j = d * P + col;
   float g[C];
   if (col < HW) {
-    const long v = d * HW + col, N = (DP / P) * HW;
+    const long v = d * HW + col, N = (long)gridDim.y * HW;
     float dot = 0.f, p[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -1637,7 +1639,7 @@ __global__ void __launch_bounds__(256) k_head_direct_bwd(const float* __restrict
 }
 
 static int head_direct_check(const char* who, int B, int D, int H, int W, long P) {
-  HNO_CHECK(B >= 1 && B <= 65535 && D >= 1 && H >= 1 && W >= 1, "%s: bad sizes", who);
+  HNO_CHECK(B >= 1 && B <= 65535 && D >= 1 && D <= 65535 && H >= 1 && W >= 1, "%s: bad sizes", who);
   HNO_CHECK(P >= (long)H * W, "%s: plane pitch too small", who);
   return 0;
 }
@@ -1648,7 +1650,7 @@ int head_direct_forward(const float* ll, float* probs, uint8_t* labels, int B, i
   HNO_CHECK(activation == 0 || activation == 1, "head_direct_forward: activation must be 0 (none) or 1 (softmax)");
   if (head_direct_check("head_direct_forward", B, D, H, W, P)) return -1;
   const long DP = (long)D * P, HW = (long)H * W;
-  dim3 grid(ceil_div(DP, 256), B);
+  dim3 grid(ceil_div(HW, 256), D, B);
   HNO_CLASS_SWITCH(C, {
     if (activation == 1) k_head_direct_fwd<kC, 1><<<grid, 256, 0, st>>>(ll, probs, labels, DP, P, HW);
     else k_head_direct_fwd<kC, 0><<<grid, 256, 0, st>>>(ll, probs, labels, DP, P, HW);
@@ -1663,7 +1665,7 @@ int head_direct_backward(const float* dprobs, const float* probs, float* dll, in
   HNO_CHECK(activation == 0 || activation == 1, "head_direct_backward: activation must be 0 (none) or 1 (softmax)");
   if (head_direct_check("head_direct_backward", B, D, H, W, P)) return -1;
   const long DP = (long)D * P, HW = (long)H * W;
-  dim3 grid(ceil_div(DP, 256), B);
+  dim3 grid(ceil_div(P, 256), D, B);
   HNO_CLASS_SWITCH(C, {
     if (activation == 1) k_head_direct_bwd<kC, 1><<<grid, 256, 0, st>>>(dprobs, probs, dll, DP, P, HW);
     else k_head_direct_bwd<kC, 0><<<grid, 256, 0, st>>>(dprobs, probs, dll, DP, P, HW);

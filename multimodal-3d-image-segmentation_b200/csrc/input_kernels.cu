@@ -250,10 +250,11 @@ __global__ void __launch_bounds__(256) k_affine_resample_nn(const T* __restrict_
   for (int k = 0; k < 12; ++k) m[k] = xform[b * 12 + k];
   for (long g = blockIdx.x * 256L + threadIdx.x; g < N / V; g += (long)gridDim.x * 256L) {
     const long i = g * V;
-    int w = (int)(i % W);
-    const long t = i / W;
-    int h = (int)(t % H);
-    int d = (int)(t / H);
+    const unsigned iu = (unsigned)i;  // N < 2^31 (checked by the launcher): 32-bit divisions
+    const unsigned t = iu / (unsigned)W;
+    int w = (int)(iu - t * (unsigned)W);
+    int d = (int)(t / (unsigned)H);
+    int h = (int)(t - (unsigned)d * (unsigned)H);
     long src[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
@@ -311,6 +312,7 @@ int affine_resample_nn(const void* in, void* out, int elem_bytes, const double* 
   HNO_CHECK(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4,
             "affine_resample_nn: elements must be uint8 (1), int16 (2) or float32 (4)");
   HNO_CHECK(B >= 1 && B <= 65535 && C >= 1 && D >= 1 && H >= 1 && W >= 1, "affine_resample_nn: bad sizes");
+  HNO_CHECK((long)D * H * W < (1L << 31), "affine_resample_nn: volume too large for 32-bit voxel indices");
   if (elem_bytes == 1) affine_resample_launch<uint8_t>(in, out, xform, flags, B, C, D, H, W, (uint8_t)cval, st);
   else if (elem_bytes == 2) affine_resample_launch<int16_t>(in, out, xform, flags, B, C, D, H, W, (int16_t)cval, st);
   else affine_resample_launch<float>(in, out, xform, flags, B, C, D, H, W, (float)cval, st);

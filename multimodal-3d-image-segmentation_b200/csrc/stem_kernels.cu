@@ -419,10 +419,11 @@ __global__ void __launch_bounds__(256) k_stem_dx(const float* __restrict__ dpre,
   const long v = blockIdx.x * 256L + threadIdx.x;
   if (v >= Nx) return;
   const int b = blockIdx.y;
-  const int zw = (int)(v % g.Wx);
-  const long r = v / g.Wx;
-  const int zh = (int)(r % g.Hx);
-  const int zd = (int)(r / g.Hx);
+  const unsigned vu = (unsigned)v;  // Nx < 2^31 (make_geom)
+  const unsigned r = vu / (unsigned)g.Wx;
+  const int zw = (int)(vu - r * (unsigned)g.Wx);
+  const int zd = (int)(r / (unsigned)g.Hx);
+  const int zh = (int)(r - (unsigned)zd * (unsigned)g.Hx);
   const int d = (zd + 1) >> 1, h = (zh + 1) >> 1, w = (zw + 1) >> 1;
   const int t = (((zd + 1) & 1) << 2) | (((zh + 1) & 1) << 1) | ((zw + 1) & 1);
   const float* dp = dpre + (long)b * F * g.S + (long)d * g.P + (long)h * g.W + w;
