@@ -20,7 +20,7 @@ class _Saved:
     pass
 
 
-def _entry_forward(m, x, S):
+def _entry_forward(m, x, S, w_in=None):
     """First activation of the network and the grid the blocks run on.  use_resize=True: the stride-2 stem (reference
     nets/hnosegxs.py:102-105, 150-151).  use_resize=False (:102-109 skipped): the image itself as a planar tensor -- a view
     when the channel count is a multiple of 4 and the plane needs no padding (4 x 240 x 240 x 155: both hold), else a
@@ -31,7 +31,7 @@ def _entry_forward(m, x, S):
     if m.use_resize:
         D, H, W = ops.stem_out_shape(image)
         pitch = plane_pitch(H, W)
-        a0 = ops.stem_forward(x, m.conv_in.op.weight, m.conv_in.op.bias, pitch)
+        a0 = ops.stem_forward(x, m.conv_in.op.weight if w_in is None else w_in, m.conv_in.op.bias, pitch)
     else:
         D, H, W = image
         pitch = plane_pitch(H, W)
@@ -56,6 +56,16 @@ def _entry_backward(m, S, dcur, hw, dst_w1=None, dst_b1=None, dst_win=None, dst_
     if m.use_resize:
         dpre0, _, g_w1, g_b1 = ops.pwconv_backward(dcur, S.a1, S.a0, None, S.w1, 1, False, hw=hw, in1_is_selu=True,
                                                    dweight=dst_w1, dbias=dst_b1)
+        perm = getattr(S, 'perm', None)
+        if perm is not None:  # the network ran on permuted axes: the stem's tap axes go back to the parameter's order
+            assert not need_dx
+            inv = [perm.index(i) for i in range(3)]
+            g_win, g_bin = ops.stem_backward(dpre0, S.x, m.filters, S.geom[3], dbias=dst_bin)
+            g_win = g_win.permute(0, 1, *[2 + i for i in inv])
+            if dst_win is not None:
+                dst_win.copy_(g_win.reshape(dst_win.shape))
+                g_win = dst_win
+            return [g_win, g_bin, g_w1.reshape(op.weight.shape), g_b1]
         g_win, g_bin = ops.stem_backward(dpre0, S.x, m.filters, S.geom[3], dweight=dst_win, dbias=dst_bin)
         if need_dx:
             S.dx = ops.stem_backward_input(dpre0, m.conv_in.op.weight, tuple(S.x.shape[2:]), S.geom[3])
@@ -128,17 +138,31 @@ class XSEngine:
         return _XSLossFunction.apply(self, x, labels, ops.LOSS_KINDS[loss_name], float(param), *self.named_slots())
 
     # ------------------------------------------------------------------------------------------ forward
-    def run_forward(self, x, save=True, head=True):
+    def run_forward(self, x, save=True, head=True, perm=None):
+        """`perm` (fused-loss training path only, head=False): run the network on the volume with its spatial axes permuted,
+        x' = x.permute(0, 1, 2 + perm[0], 2 + perm[1], 2 + perm[2]).  Every operator of HNOSeg-XS with shared weights is
+        equivariant under such a permutation once the mode counts and the 2x2x2 stem taps are permuted with it (pointwise
+        convolutions, separable transform and interpolation, voxel-wise loss sums), so loss and gradients are those of the
+        un-permuted volume; the point is speed: the transform contracts D -> H -> W and its L2-resident stages are cheapest
+        with the SHORTEST axis last (155 x 240 x 240 as 240 x 240 x 155: DESIGN 8.3)."""
         m = self.model
         if x.ndim != 5 or x.shape[1] != m.in_channels:
             raise ValueError(f'HNOSegXS expects (B, {m.in_channels}, D, H, W) input, got {tuple(x.shape)}')
+        modes, w_in = m.num_modes, None
+        if perm is not None:
+            assert not head and m.use_resize and m.weights_type == 'shared' and sorted(perm) == [0, 1, 2]
+            dims = [2 + p for p in perm]
+            x = x.permute(0, 1, *dims)
+            modes = tuple(m.num_modes[p] for p in perm)
+            w_in = m.conv_in.op.weight.permute(0, 1, *dims).contiguous()
         x = x.contiguous()
         dev = x.device
         image = tuple(x.shape[2:])
         S = _Saved()
-        a1 = _entry_forward(m, x, S)
+        S.perm = perm
+        a1 = _entry_forward(m, x, S, w_in)
         D, H, W, pitch = S.geom
-        plan = get_crop_plan((D, H, W), m.num_modes, dev)
+        plan = get_crop_plan((D, H, W), modes, dev)
         inv_n = 1.0 / plan.n_voxels
         shared = m.weights_type == 'shared'
         nb = len(m.layers)

@@ -428,3 +428,33 @@ def test_training_step_gradients_at_the_timed_shape(cuda, golden_dir):
     print(f'timed shape: loss {loss:.7f} (oracle {o_loss:.7f}), flat gradient rel-L2 {r:.2e}, worst tensor {worst}')
     assert r < 2e-3, r  # gradients vs the fp64 oracle (the fp32 reference itself is at 1.7e-4)
     assert worst[0] < 5e-3, worst
+
+
+@pytest.mark.parametrize('spatial,expect', [((13, 16, 18), (1, 2, 0)), ((16, 11, 18), (0, 2, 1)), ((16, 18, 12), None)])
+def test_trainer_axis_permutation_is_exact(cuda, golden_dir, monkeypatch, spatial, expect):
+    """The Trainer runs a volume whose last axis is not the shortest on permuted axes (shortest last; real BraTS tensors are
+    155 x 240 x 240).  HNOSeg-XS with shared weights is equivariant under the permutation once modes and stem taps follow it:
+    loss and every gradient must be those of the un-permuted run and of the fp64 oracle."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    from multimodal_3d_image_segmentation_b200.parallel import Trainer
+    g = dict(np.load(os.path.join(golden_dir, 'model_small.npz')))
+    sd = _sd(g, 'shared/sd/')
+    blocks, modes = [1, 2, 1, 2, 1, 2], (2, 3, 4)  # distinct mode counts per axis: a wrong mode permutation would show
+    model = nets.HNOSegXS(2, 3, 8, blocks, modes, device=cuda)
+    model.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 2, *spatial, generator=gen)
+    labels = torch.randint(0, 3, (2, 1) + spatial, generator=gen)
+    o_loss, o_grads = orc.train_step({k: v.double() for k, v in sd.items()}, x.double(), labels, blocks, modes, 'DiceLoss')
+    out = {}
+    for mode in ('0', 'force'):
+        monkeypatch.setenv('HNO_AXIS_PERM', mode)
+        tr = Trainer(model, loss_name='DiceLoss', use_graph=False)
+        assert tr._axis_perm(spatial) == (expect if mode == 'force' else None)
+        loss = tr.loss_and_grad(x.to(cuda), labels.to(cuda))
+        out[mode] = (float(loss), {k: tr.flat.grad_view_of(p).clone() for k, p in model.named_parameters()})
+        assert abs(out[mode][0] - float(o_loss)) < 2e-6, mode
+        for k, v in out[mode][1].items():
+            assert rel(v, o_grads[k]) < 2e-4, (mode, k, rel(v, o_grads[k]))
+    for k in out['0'][1]:
+        assert rel(out['force'][1][k], out['0'][1][k]) < 1e-4, k
