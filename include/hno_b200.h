@@ -307,6 +307,11 @@ int hno_normalize_modalities_i16(const short* data, float* out, void* workspace,
  * A 2-D image (C, H, W) is the D == 1 case with an identity z row. */
 int hno_affine_resample_nn(const void* in, void* out, int elem_bytes, const double* xform, const int* flags, int B,
                            int C, int D, int H, int W, double cval, void* stream);
+/* Batched 2-D transpose out[n][c][r] = in[n][r][c] (1-, 2- or 4-byte elements; out != in): the layout change
+ * behind running a volume with its shortest spatial axis last (the networks are equivariant under axis permutations;
+ * parallel.Trainer._axis_perm).  No counterpart in the reference, which runs whatever order the reader delivers
+ * (experiments/utils.py:260-270: SimpleITK's (z, y, x)). */
+int hno_transpose2d(const void* in, void* out, int elem_bytes, long n, int R, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Deep-supervision convolution                 replaces nets/architectures.py:295-311, 330-343 and

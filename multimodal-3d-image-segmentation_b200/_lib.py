@@ -82,6 +82,7 @@ SIGNATURES = {
     'hno_normalize_modalities': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
     'hno_normalize_modalities_i16': (_I, [_P, _P, _P, _I, _L, _I, _F, _I, _F, _F, _P]),
     'hno_affine_resample_nn': (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _D, _P]),
+    'hno_transpose2d': (_I, [_P, _P, _I, _L, _I, _I, _P]),
     'hno_dsconv_forward': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
     'hno_dsconv_backward_workspace_bytes': (_Z, [_I, _I, _I, _L]),
     'hno_dsconv_backward': (_I, [_P, _P, _P, _I] + [_P] * 8 + [_I, _I, _L, _L, _L, _I, _P]),

@@ -120,6 +120,7 @@ int to_categorical(const void*, int, float*, int*, int, int, long, cudaStream_t)
 size_t normalize_workspace_bytes(int);
 int normalize_modalities(const void*, int, float*, void*, int, long, int, float, int, float, float, cudaStream_t);
 int affine_resample_nn(const void*, void*, int, const double*, const int*, int, int, int, int, int, double, cudaStream_t);
+int transpose2d(const void*, void*, int, long, int, int, cudaStream_t);
 int adamax_step(float*, const float*, float*, float*, long, float, float, float, float, float, int, float,
                 cudaStream_t);
 
@@ -365,6 +366,10 @@ int hno_normalize_modalities_i16(const short* data, float* out, void* workspace,
                                  float mask_val, int has_clip, float clip_lo, float clip_hi, void* stream) {
   return normalize_modalities(data, 2, out, workspace, rows, n, has_mask, mask_val, has_clip, clip_lo, clip_hi,
                               ST(stream));
+}
+
+int hno_transpose2d(const void* in, void* out, int elem_bytes, long n, int R, int C, void* stream) {
+  return transpose2d(in, out, elem_bytes, n, R, C, ST(stream));
 }
 
 int hno_affine_resample_nn(const void* in, void* out, int elem_bytes, const double* xform, const int* flags, int B,

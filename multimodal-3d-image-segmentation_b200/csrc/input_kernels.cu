@@ -320,4 +320,46 @@ int affine_resample_nn(const void* in, void* out, int elem_bytes, const double* 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ axis permutation
+// out[n][c][r] = in[n][r][c]: the batched 2-D transpose behind "shortest spatial axis last" (parallel.Trainer._axis_perm):
+// (D, H, W) -> (H, W, D) is R = D, C = H * W per (sample, channel); (D, H, W) -> (D, W, H) is R = H, C = W per (sample, channel,
+// slice).  32 x 32 tiles through padded shared memory, both sides coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256) k_transpose2d(const T* __restrict__ in, T* __restrict__ out, int R, int C) {
+  __shared__ T tile[32][33];
+  const long base = (long)blockIdx.z * R * C;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    if (r < R && c < C) tile[ty + 8 * k][tx] = __ldg(in + base + (long)r * C + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + tx;
+    if (r < R && c < C) out[base + (long)c * R + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+int transpose2d(const void* in, void* out, int elem_bytes, long n, int R, int C, cudaStream_t st) {
+  HNO_CHECK(in && out && in != out, "transpose2d: null or aliased pointers");
+  HNO_CHECK(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4, "transpose2d: elements must be 1, 2 or 4 bytes");
+  HNO_CHECK(n >= 1 && R >= 1 && C >= 1 && (R + 31) / 32 <= 65535, "transpose2d: bad sizes");
+  for (long n0 = 0; n0 < n; n0 += 65535) {  // gridDim.z limit
+    const long nn = n - n0 < 65535 ? n - n0 : 65535;
+    const long off = n0 * R * C;
+    dim3 grid((C + 31) / 32, (R + 31) / 32, (unsigned)nn);
+    if (elem_bytes == 1)
+      k_transpose2d<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(in) + off, static_cast<uint8_t*>(out) + off, R, C);
+    else if (elem_bytes == 2)
+      k_transpose2d<int16_t><<<grid, 256, 0, st>>>(static_cast<const int16_t*>(in) + off, static_cast<int16_t*>(out) + off, R, C);
+    else
+      k_transpose2d<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in) + off, static_cast<float*>(out) + off, R, C);
+    HNO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 }  // namespace hno

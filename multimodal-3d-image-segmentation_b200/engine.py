@@ -152,7 +152,7 @@ class XSEngine:
         if perm is not None:
             assert not head and m.use_resize and m.weights_type == 'shared' and sorted(perm) == [0, 1, 2]
             dims = [2 + p for p in perm]
-            x = x.permute(0, 1, *dims)
+            x = ops.permute_spatial(x, perm)
             modes = tuple(m.num_modes[p] for p in perm)
             w_in = m.conv_in.op.weight.permute(0, 1, *dims).contiguous()
         x = x.contiguous()

@@ -540,6 +540,33 @@ def selu_backward(dy, y):
     return dy * torch.where(y > 0, torch.full_like(y, scale), y + scale * alpha)
 
 
+def permute_spatial(t, perm):
+    """t.permute(<leading dims>, spatial axes in order `perm`).contiguous() for the two permutations that move one spatial axis
+    to the end -- (1, 2, 0) and (0, 2, 1) -- as ONE batched 2-D transpose (hno_transpose2d); t: (..., D, H, W) contiguous,
+    uint8 / int16 / float32."""
+    perm = tuple(perm)
+    if t.device.type != 'cuda':
+        raise RuntimeError('hno_b200: permute_spatial needs a CUDA tensor; this package has no CPU path')
+    t = t.contiguous()
+    lead = tuple(t.shape[:-3])
+    D, H, W = t.shape[-3:]
+    n = 1
+    for v in lead:
+        n *= v
+    if perm == (1, 2, 0):
+        out = torch.empty(lead + (H, W, D), dtype=t.dtype, device=t.device)
+        R, C = D, H * W
+    elif perm == (0, 2, 1):
+        out = torch.empty(lead + (D, W, H), dtype=t.dtype, device=t.device)
+        n, R, C = n * D, H, W
+    else:
+        raise ValueError(f'permute_spatial handles (1, 2, 0) and (0, 2, 1), got {perm}')
+    if t.element_size() not in (1, 2, 4):
+        raise TypeError(f'permute_spatial: unsupported element type {t.dtype}')
+    call('hno_transpose2d', ptr(t), ptr(out), t.element_size(), n, R, C, stream_ptr())
+    return out
+
+
 # ------------------------------------------------------------------------------------------ head / losses
 def head_forward(logits_low, tables, pitch, activation=1):
     B, C = logits_low.shape[:2]

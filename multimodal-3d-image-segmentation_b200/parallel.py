@@ -296,7 +296,7 @@ class Trainer:
             perm = self._axis_perm(tuple(x.shape[2:]))
             if perm is not None:
                 _, S = self.engine.run_forward(x, save=True, head=False, perm=perm)
-                lab = lab.permute(0, *[1 + p for p in perm]).contiguous()
+                lab = ops.permute_spatial(lab, perm)
             else:
                 _, S = self.engine.run_forward(x, save=True, head=False)
             loss, coef = ops.head_loss_forward(S.ll, lab, S.tables, S.geom[3], self.kind, self.loss_param)

@@ -571,3 +571,17 @@ def test_fourier_mix_matches_eager_formula(cuda, ci, co, shape, modes, wt):
     assert rel(wrc.grad, wrr.grad) < 2e-6 and rel(wic.grad, wir.grad) < 2e-6
     out2 = ops.FourierMixShared.apply(zc, wrc, wic, *fused)  # two-term atomic sums: bit-identical from run to run
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.int16, torch.uint8])
+def test_permute_spatial_is_a_pure_layout_change(cuda, dtype):
+    """hno_transpose2d behind ops.permute_spatial: both 'one axis to the end' permutations, ragged sizes, every element size."""
+    from multimodal_3d_image_segmentation_b200 import ops as hops
+    gen = torch.Generator().manual_seed(8)
+    for shape in ((2, 3, 5, 33, 70), (1, 1, 37, 31, 1), (3, 40, 64, 9)):
+        t = torch.randint(0, 200, shape, generator=gen).to(dtype).to(cuda)
+        lead = len(shape) - 3
+        for perm in ((1, 2, 0), (0, 2, 1)):
+            want = t.permute(*range(lead), *[lead + p for p in perm]).contiguous()
+            got = hops.permute_spatial(t, perm)
+            assert got.shape == want.shape and torch.equal(got, want), (shape, perm)
