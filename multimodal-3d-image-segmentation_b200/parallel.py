@@ -226,55 +226,35 @@ class Trainer:
         return self._streams
 
     def _loss_and_grad_split(self, x, labels):
-        """loss_and_grad with one launch chain per sample on two streams (see __init__)."""
+        """loss_and_grad of a 2-sample batch with one launch chain per sample on two streams (see __init__)."""
         from . import ops
         from .engine import _labels_u8
-        B = x.shape[0]
+        assert x.shape[0] == 2
         streams = self._split_state(x.device)
         cur = torch.cuda.current_stream()
-        scale = self._grad_scale.get(B)
+        scale = self._grad_scale.get(2)
         if scale is None:
-            scale = self._grad_scale[B] = torch.full((1,), 1.0 / B, dtype=torch.float32, device=x.device)
-        losses = torch.empty((B,), dtype=torch.float32, device=x.device)
+            scale = self._grad_scale[2] = torch.full((1,), 0.5, dtype=torch.float32, device=x.device)
+        losses = torch.empty((2,), dtype=torch.float32, device=x.device)
         lab = _labels_u8(labels, x)
-        for s in streams:
+        for b, s in enumerate(streams):
             s.wait_stream(cur)
-        for b in range(B):
-            with torch.cuda.stream(streams[b % 2]):
+            with torch.cuda.stream(s):
                 xb, lb = x[b:b + 1], lab[b:b + 1]
                 _, S = self.engine.run_forward(xb, save=True, head=False)
                 loss_b, coef = ops.head_loss_forward(S.ll, lb, S.tables, S.geom[3], self.kind, self.loss_param)
                 losses[b:b + 1].copy_(loss_b)
-                if b == 0:
-                    self.engine.run_backward(S, dst=self.dst, fused=(lb, coef, scale))
-                else:
-                    # samples 2, 3, ... of a stream run after its earlier ones, so accumulating into its buffer is ordered
-                    self.engine.run_backward(S, dst=self._dst2 if b == 1 else self._dst_tmp(b), fused=(lb, coef, scale))
-                    if b > 1:
-                        (self.flat.grad if b % 2 == 0 else self._flat2).add_(self._tmp_flat[b % 2])
+                self.engine.run_backward(S, dst=self.dst if b == 0 else self._dst2, fused=(lb, coef, scale))
                 del S
         for s in streams:
             cur.wait_stream(s)
         self.flat.grad.add_(self._flat2)
         return losses.mean().reshape(1)
 
-    def _dst_tmp(self, b):
-        """Scratch gradient views for the third and later samples of a batch (one flat buffer per stream)."""
-        if not hasattr(self, '_tmp_flat'):
-            self._tmp_flat, self._tmp_dst = {}, {}
-        k = b % 2
-        if k not in self._tmp_flat:
-            base = self.flat.grad.data_ptr()
-            esz = self.flat.grad.element_size()
-            self._tmp_flat[k] = torch.zeros_like(self.flat.grad)
-            self._tmp_dst[k] = [self._tmp_flat[k][(d.data_ptr() - base) // esz:(d.data_ptr() - base) // esz + d.numel()].view(d.shape)
-                                for d in self.dst]
-        return self._tmp_dst[k]
-
     def loss_and_grad(self, x, labels):
         from . import ops
         from .engine import _labels_u8
-        if self.sample_streams and x.shape[0] > 1:
+        if self.sample_streams and x.shape[0] == 2:
             with torch.no_grad():
                 return self._loss_and_grad_split(x, labels)
         with torch.no_grad():

@@ -128,3 +128,30 @@ def test_cosine_warm_restarts_matches_torch_scheduler():
             assert abs(got - want) < 1e-12, (T_0, T_mult, step, got, want)
             opt.step()
             sch.step()
+
+
+def test_axis_permutation_policy(monkeypatch):
+    """Trainer._axis_perm (host logic): large volumes whose last axis is not the shortest run with the shortest axis last;
+    the BASELINE-literal order, small volumes, per-mode weights and use_resize=False are left alone."""
+    import types
+    from multimodal_3d_image_segmentation_b200.parallel import Trainer
+    monkeypatch.delenv('HNO_AXIS_PERM', raising=False)
+
+    def policy(spatial, **kw):
+        model = types.SimpleNamespace(use_resize=kw.get('use_resize', True), weights_type=kw.get('weights_type', 'shared'))
+        return Trainer._axis_perm(types.SimpleNamespace(_direct=kw.get('direct', True), model=model), spatial)
+
+    assert policy((240, 240, 155)) is None            # BASELINE-literal order: already shortest last
+    assert policy((155, 240, 240)) == (1, 2, 0)       # SimpleITK (z, y, x) order of a BraTS volume
+    assert policy((240, 155, 240)) == (0, 2, 1)
+    assert policy((13, 16, 18)) is None               # small: the transposes cost more than they save
+    assert policy((155, 240, 240), weights_type='individual') is None
+    assert policy((155, 240, 240), use_resize=False) is None
+    assert policy((155, 240, 240), direct=False) is None
+    monkeypatch.setenv('HNO_AXIS_PERM', '0')
+    assert policy((155, 240, 240)) is None
+    monkeypatch.setenv('HNO_AXIS_PERM', 'force')
+    assert policy((13, 16, 18)) == (1, 2, 0)
+    for spatial in ((155, 240, 240), (240, 155, 240), (13, 16, 18), (16, 11, 18)):
+        perm = policy(spatial)
+        assert sorted(perm) == [0, 1, 2] and spatial[perm[2]] == min(spatial)
