@@ -20,6 +20,25 @@ class _Saved:
     pass
 
 
+def preferred_axis_perm(model, spatial):
+    """Spatial permutation a volume of shape `spatial` should run on, or None.  HNOSeg-XS with shared weights is equivariant
+    under permutations of the volume's axes (XSEngine.run_forward), and the transform's L2-resident stages are cheapest with
+    the shortest axis LAST: real BraTS tensors are (155, 240, 240) (SimpleITK's z, y, x order) and run 13 % slower than the
+    same volume stored (240, 240, 155).  HNO_AXIS_PERM: '0' off, '1' (default) large volumes only -- below ~2 M voxels the
+    transposing copies cost more than they save --, 'force' any size (tests)."""
+    import os
+    mode = os.environ.get('HNO_AXIS_PERM', '1')
+    if mode == '0':
+        return None
+    if not getattr(model, 'use_resize', True) or getattr(model, 'weights_type', 'shared') != 'shared':
+        return None
+    d, h, w = spatial
+    if (d * h * w < (1 << 21) and mode != 'force') or w <= min(d, h):
+        return None
+    k = 0 if d <= h else 1  # the shortest axis goes last, the other two keep their order
+    return tuple(i for i in range(3) if i != k) + (k,)
+
+
 def _entry_forward(m, x, S, w_in=None):
     """First activation of the network and the grid the blocks run on.  use_resize=True: the stride-2 stem (reference
     nets/hnosegxs.py:102-105, 150-151).  use_resize=False (:102-109 skipped): the image itself as a planar tensor -- a view

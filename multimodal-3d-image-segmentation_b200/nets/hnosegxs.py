@@ -234,11 +234,18 @@ class HNOSegXS(nn.Module):
         """Inference as experiments/train_test.py:398-408 uses the model (forward under no_grad, argmax over the classes),
         with the argmax on the device: returns the uint8 label map (B, D, H, W).  The probabilities are never
         materialised (4 bytes x classes per voxel neither written nor copied back)."""
+        from ..engine import preferred_axis_perm
         with torch.no_grad():
-            _, S = self.engine().run_forward(x, save=False, head=False)
+            # a large volume whose last axis is not its shortest (SimpleITK's (z, y, x) order) runs on permuted axes and the
+            # one-byte label map is transposed back (engine.preferred_axis_perm)
+            perm = preferred_axis_perm(self, tuple(x.shape[2:])) if x.ndim == 5 else None
+            _, S = self.engine().run_forward(x, save=False, head=False, perm=perm)
             if S.tables is None:  # use_resize=False
                 return ops.head_direct_argmax(S.ll, S.geom[:3])
-            return ops.head_argmax(S.ll, S.tables, S.geom[3])
+            labels = ops.head_argmax(S.ll, S.tables, S.geom[3])
+            if perm is not None:
+                labels = ops.permute_spatial(labels, tuple(perm.index(i) for i in range(3)))
+            return labels
 
     def loss(self, x, labels, loss_name='DiceLoss', param=None):
         """Fused head + loss on integer labels; equals loss_fn(self(x), to_categorical(labels)) for loss_name in

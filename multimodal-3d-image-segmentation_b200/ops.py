@@ -541,9 +541,9 @@ def selu_backward(dy, y):
 
 
 def permute_spatial(t, perm):
-    """t.permute(<leading dims>, spatial axes in order `perm`).contiguous() for the two permutations that move one spatial axis
-    to the end -- (1, 2, 0) and (0, 2, 1) -- as ONE batched 2-D transpose (hno_transpose2d); t: (..., D, H, W) contiguous,
-    uint8 / int16 / float32."""
+    """t.permute(<leading dims>, spatial axes in order `perm`).contiguous() for the permutations that move one spatial axis to
+    the end -- (1, 2, 0) and (0, 2, 1) -- and the inverse of the first, (2, 0, 1), each as ONE batched 2-D transpose
+    (hno_transpose2d); t: (..., D, H, W) contiguous, uint8 / int16 / float32."""
     perm = tuple(perm)
     if t.device.type != 'cuda':
         raise RuntimeError('hno_b200: permute_spatial needs a CUDA tensor; this package has no CPU path')
@@ -559,8 +559,11 @@ def permute_spatial(t, perm):
     elif perm == (0, 2, 1):
         out = torch.empty(lead + (D, W, H), dtype=t.dtype, device=t.device)
         n, R, C = n * D, H, W
+    elif perm == (2, 0, 1):
+        out = torch.empty(lead + (W, D, H), dtype=t.dtype, device=t.device)
+        R, C = D * H, W
     else:
-        raise ValueError(f'permute_spatial handles (1, 2, 0) and (0, 2, 1), got {perm}')
+        raise ValueError(f'permute_spatial handles (1, 2, 0), (0, 2, 1) and (2, 0, 1), got {perm}')
     if t.element_size() not in (1, 2, 4):
         raise TypeError(f'permute_spatial: unsupported element type {t.dtype}')
     call('hno_transpose2d', ptr(t), ptr(out), t.element_size(), n, R, C, stream_ptr())

@@ -284,22 +284,9 @@ class Trainer:
         return loss
 
     def _axis_perm(self, spatial):
-        """Spatial permutation the step runs on, or None.  HNOSeg-XS with shared weights is equivariant under permutations of
-        the volume's axes (engine.XSEngine.run_forward), and the transform's L2-resident stages are cheapest with the shortest
-        axis LAST: real BraTS tensors are (155, 240, 240) (SimpleITK's z, y, x order) and run 13 % slower than the same volume
-        stored (240, 240, 155).  HNO_AXIS_PERM=0 disables; small volumes are left alone (the two transposing copies cost more
-        than they save)."""
-        mode = os.environ.get('HNO_AXIS_PERM', '1')  # '0' off, '1' large volumes only, 'force' any size (tests)
-        if mode == '0' or not self._direct:
-            return None
-        m = self.model
-        if not getattr(m, 'use_resize', True) or getattr(m, 'weights_type', 'shared') != 'shared':
-            return None
-        d, h, w = spatial
-        if (d * h * w < (1 << 21) and mode != 'force') or w <= min(d, h):
-            return None
-        k = 0 if d <= h else 1  # the shortest axis goes last, the other two keep their order
-        return tuple(i for i in range(3) if i != k) + (k,)
+        """Spatial permutation the step runs on, or None (engine.preferred_axis_perm; XSEngine only)."""
+        from .engine import preferred_axis_perm
+        return preferred_axis_perm(self.model, spatial) if self._direct else None
 
     def _backward(self, S, **kw):
         if self._direct:

@@ -458,3 +458,21 @@ def test_trainer_axis_permutation_is_exact(cuda, golden_dir, monkeypatch, spatia
             assert rel(v, o_grads[k]) < 2e-4, (mode, k, rel(v, o_grads[k]))
     for k in out['0'][1]:
         assert rel(out['force'][1][k], out['0'][1][k]) < 1e-4, k
+
+
+@pytest.mark.parametrize('spatial', [(13, 16, 18), (16, 11, 18)])
+def test_predict_labels_axis_permutation(cuda, golden_dir, monkeypatch, spatial):
+    """Inference on permuted axes (shortest last) + the label map transposed back == inference as stored."""
+    from multimodal_3d_image_segmentation_b200 import nets
+    g = dict(np.load(os.path.join(golden_dir, 'model_small.npz')))
+    model = nets.HNOSegXS(2, 3, 8, [1, 2, 1, 2, 1, 2], (2, 3, 4), device=cuda)
+    model.load_state_dict(_sd(g, 'shared/sd/'))
+    x = torch.randn(2, 2, *spatial, generator=torch.Generator().manual_seed(78)).to(cuda)
+    monkeypatch.setenv('HNO_AXIS_PERM', '0')
+    plain = model.predict_labels(x)
+    assert torch.equal(plain.long(), model.forward_logits(x).argmax(1))
+    monkeypatch.setenv('HNO_AXIS_PERM', 'force')
+    permuted = model.predict_labels(x)
+    assert permuted.shape == plain.shape and permuted.dtype == torch.uint8
+    # identical up to argmax ties at round-off level
+    assert (permuted == plain).float().mean().item() >= 0.999

@@ -578,10 +578,10 @@ def test_permute_spatial_is_a_pure_layout_change(cuda, dtype):
     """hno_transpose2d behind ops.permute_spatial: both 'one axis to the end' permutations, ragged sizes, every element size."""
     from multimodal_3d_image_segmentation_b200 import ops as hops
     gen = torch.Generator().manual_seed(8)
-    for shape in ((2, 3, 5, 33, 70), (1, 1, 37, 31, 1), (3, 40, 64, 9)):
+    for shape in ((2, 3, 5, 33, 70), (1, 1, 37, 31, 1), (3, 40, 64, 9)):  # (..., D, H, W)
         t = torch.randint(0, 200, shape, generator=gen).to(dtype).to(cuda)
         lead = len(shape) - 3
-        for perm in ((1, 2, 0), (0, 2, 1)):
+        for perm in ((1, 2, 0), (0, 2, 1), (2, 0, 1)):
             want = t.permute(*range(lead), *[lead + p for p in perm]).contiguous()
             got = hops.permute_spatial(t, perm)
             assert got.shape == want.shape and torch.equal(got, want), (shape, perm)
