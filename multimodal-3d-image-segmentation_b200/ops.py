@@ -634,24 +634,6 @@ def head_direct_backward(dprobs, probs, pitch, activation=1):
     return dll
 
 
-class HeadDirect(torch.autograd.Function):
-    """Output activation of a use_resize=False network on planar or dense logits (softmax over dim 1, or identity)."""
-
-    @staticmethod
-    def forward(ctx, logits, spatial, activation):
-        logits = logits.contiguous()
-        probs = head_direct_forward(logits, spatial, activation)
-        ctx.save_for_backward(probs)
-        ctx.cfg = (_geom(logits)[2], activation, tuple(logits.shape))
-        return probs
-
-    @staticmethod
-    def backward(ctx, dprobs):
-        (probs,) = ctx.saved_tensors
-        pitch, activation, shape = ctx.cfg
-        return head_direct_backward(dprobs, probs, pitch, activation).view(shape), None, None
-
-
 class HeadUpsample(torch.autograd.Function):
     """probs = softmax(trilinear(logits_low)) (activation=1) or just the interpolation (activation=0)."""
 

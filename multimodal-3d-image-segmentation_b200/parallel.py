@@ -345,6 +345,8 @@ class Trainer:
             buf = self._xnorm[key] = torch.empty(x_raw.shape, dtype=torch.float32, device=x_raw.device)
         normalize_rows(x_raw, x_raw.shape[0] * x_raw.shape[1], mask_val=mask_val, clip_val=clip_val, out=buf)
         if augment is not None:
+            if labels.dtype not in (torch.uint8, torch.int16):
+                labels = labels.to(torch.uint8)  # class indices; the gather kernel moves 1- / 2- / 4-byte elements
             akey = key + (tuple(labels.shape), labels.dtype)
             abuf = self._xnorm.get(akey)
             if abuf is None:
