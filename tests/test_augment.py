@@ -137,3 +137,46 @@ def test_device_transform_brats_grid_properties(cuda):
     moved = tr.batch(x, params=[(shift, 0)] * B)
     assert torch.equal(moved[:, :, :233, 5:, :152], x[:, :, 7:, :235, 3:])
     assert int(moved[:, :, 233:].abs().max()) == 0 and int(moved[:, :, :, :5].abs().max()) == 0
+
+
+def test_draw_transform_geometry_invariants():
+    """Host logic: what the composed matrix must satisfy whatever the draws (reference dataset.py:128-165, 195-202)."""
+    spatial = (30, 40, 50)
+    centre = np.asarray(spatial[::-1], dtype=np.float64) / 2.0 + 0.5
+    for seed in range(20):
+        # rotation + zoom, no shift: a similarity about size / 2 + 0.5 -- the centre is a fixed point, A = zoom * R
+        rng = np.random.default_rng(seed)
+        xf, flags = draw_transform(rng, spatial, rotation_range=[30, 20, 10], zoom_range=[0.7, 1.4])
+        A, t = xf[:, :3], xf[:, 3]
+        assert flags == 0 and np.allclose(A @ centre + t, centre, atol=1e-9)
+        zoom = np.cbrt(np.linalg.det(A))
+        assert 0.7 <= zoom <= 1.4 and np.allclose(A @ A.T, zoom * zoom * np.eye(3), atol=1e-12)
+        # shift only: identity matrix, offset = the drawn fractions of the size in (x, y, z) order
+        rng = np.random.default_rng(seed)
+        xf, _ = draw_transform(rng, spatial, shift_range=[0.1, 0.2, 0.3])
+        assert np.array_equal(xf[:, :3], np.eye(3))
+        frac = xf[:, 3] / np.asarray(spatial[::-1], dtype=np.float64)
+        assert np.all(np.abs(frac) <= np.array([0.3, 0.2, 0.1]) + 1e-12)
+    # the probability gate: nothing else is drawn when it says no
+    rng = np.random.default_rng(0)
+    none = [draw_transform(rng, spatial, rotation_range=[30, 30, 30], flip=[True] * 3, augmentation_probability=0.0)
+            for _ in range(5)]
+    assert all(xf is None and fl == 0 for xf, fl in none)
+    ref = np.random.default_rng(0)
+    for _ in range(5):
+        ref.binomial(1, 0.0)
+    assert rng.random() == ref.random()  # the generator advanced by exactly the five gates
+
+
+def test_resampler_shift_round_trip_and_zoom():
+    rng = np.random.default_rng(4)
+    x = rng.integers(1, 100, (2, 9, 10, 11)).astype(np.int16)
+    eye = np.eye(3)
+    there = orc.affine_resample_nn(x, eye, np.array([2.0, -1.0, 3.0]))
+    back = orc.affine_resample_nn(there, eye, np.array([-2.0, 1.0, -3.0]))
+    # voxels that never left the volume come back unchanged, the rest were filled with cval = 0
+    assert np.array_equal(back[:, 3:, :9, 2:], x[:, 3:, :9, 2:])
+    assert np.all(back[:, :3] == 0) and np.all(back[:, :, 9:] == 0) and np.all(back[:, :, :, :2] == 0)
+    # zoom by exactly 2 about the origin: output p reads input 2 p (nearest neighbour = exact sub-sampling)
+    z = orc.affine_resample_nn(x, 2.0 * eye, np.zeros(3), cval=-1)
+    assert np.array_equal(z[:, :5, :5, :6], x[:, ::2, ::2, ::2]) and np.all(z[:, 5:] == -1)
