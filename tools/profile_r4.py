@@ -24,6 +24,7 @@ D, H, W = ops.stem_out_shape(sp)
 pitch = plane_pitch(H, W)
 dpre = torch.randn(B, 24, D, pitch, device=dev)
 wstem = torch.randn(24, C, 2, 2, 2, device=dev)
+xz = torch.randn(B, C, 155, 240, 240, device=dev)  # SimpleITK (z, y, x) order
 
 
 def timed(fn, n=10):
@@ -48,7 +49,8 @@ for name, fn, nbytes in (
         ('affine_resample_nn fp32 images + u8 labels', lambda: tr.batch(x, y, params=params), 2 * (x.numel() * 4 + y.numel())),
         ('head_direct_forward (softmax)', lambda: ops.head_direct_forward(logits, sp, 1), 2 * B * C * N * 4),
         ('head_direct_backward', lambda: ops.head_direct_backward(dprobs, probs, sp[1] * sp[2], 1), 3 * B * C * N * 4),
-        ('stem_backward_input', lambda: ops.stem_backward_input(dpre, wstem, sp, pitch), dpre.numel() * 4 + B * C * N * 4)):
+        ('stem_backward_input', lambda: ops.stem_backward_input(dpre, wstem, sp, pitch), dpre.numel() * 4 + B * C * N * 4),
+        ('permute_spatial (155,240,240)->(240,240,155) fp32', lambda: ops.permute_spatial(xz, (1, 2, 0)), 2 * xz.numel() * 4)):
     ms = timed(fn)
     rows.append({'kernel': name, 'ms': round(ms, 4), 'alg_bytes': nbytes, 'GB_per_s': round(nbytes / ms / 1e6, 1)})
     print(json.dumps(rows[-1]))
