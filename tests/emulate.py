@@ -110,3 +110,39 @@ def interp_matrix(tables, a):
         M[o, i0[o]] += 1.0 - l1[o]
         M[o, i1[o]] += l1[o]
     return M
+
+
+def stem_input_gradient(dpre, weight, image):
+    """What k_stem_dx computes (csrc/stem_kernels.cu): with stride == kernel == 2 and padding 1 every image voxel z feeds exactly
+    one output voxel (z + 1) >> 1 through tap (z + 1) & 1 per axis.  dpre (B, F, D, H, W), weight (F, C, 2, 2, 2)."""
+    B, F = dpre.shape[:2]
+    C = weight.shape[1]
+    Dx, Hx, Wx = image
+    zd, zh, zw = np.meshgrid(np.arange(Dx), np.arange(Hx), np.arange(Wx), indexing='ij')
+    d, h, w = (zd + 1) >> 1, (zh + 1) >> 1, (zw + 1) >> 1
+    kd, kh, kw = (zd + 1) & 1, (zh + 1) & 1, (zw + 1) & 1
+    g = dpre[:, :, d, h, w].astype(np.float64)                       # (B, F, Dx, Hx, Wx)
+    wt = weight[:, :, kd, kh, kw].astype(np.float64)                 # (F, C, Dx, Hx, Wx)
+    return np.einsum('bfdhw,fcdhw->bcdhw', g, wt)
+
+
+def resample_index_walk(N, W, H, V=4):
+    """The (d, h, w) walk of k_affine_resample_nn<T, V> (csrc/input_kernels.cu): a thread decodes the first of its V consecutive
+    linear indices with two 32-bit divisions and steps the rest with carries.  Returns an (N, 3) int array."""
+    out = np.zeros((N, 3), dtype=np.int64)
+    for g in range(N // V):
+        i = g * V
+        t = i // W
+        w = i - t * W
+        d = t // H
+        h = t - d * H
+        for e in range(V):
+            out[i + e] = (d, h, w)
+            w += 1
+            if w == W:
+                w = 0
+                h += 1
+                if h == H:
+                    h = 0
+                    d += 1
+    return out

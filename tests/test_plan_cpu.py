@@ -112,3 +112,27 @@ def test_interp_tables_match_torch_interpolate(lo, hi):
             touching = [o for o in range(hi[a]) if i0[o] == lo_idx or i1[o] == lo_idx]
             if touching:
                 assert s[lo_idx] == touching[0] and e[lo_idx] == touching[-1] + 1
+
+
+def test_stem_input_gradient_mapping_is_the_transposed_convolution():
+    """The tap / voxel mapping k_stem_dx uses == autograd of Conv3d(kernel 2, stride 2, padding 1) w.r.t. its input."""
+    import torch
+    torch.manual_seed(0)
+    for image in ((5, 6, 7), (4, 4, 4), (7, 3, 2)):
+        x = torch.randn(2, 3, *image, dtype=torch.float64, requires_grad=True)
+        wgt = torch.randn(5, 3, 2, 2, 2, dtype=torch.float64)
+        y = torch.nn.functional.conv3d(x, wgt, stride=2, padding=1)
+        g = torch.randn_like(y)
+        (dx,) = torch.autograd.grad((y * g).sum(), x)
+        got = emulate.stem_input_gradient(g.numpy(), wgt.numpy(), image)
+        assert np.abs(got - dx.numpy()).max() < 1e-12, image
+
+
+def test_resample_index_walk_matches_unravel():
+    for (D, H, W) in ((3, 4, 8), (5, 3, 4), (2, 6, 2), (4, 1, 3)):
+        N = D * H * W
+        if N % 4:
+            continue
+        walk = emulate.resample_index_walk(N, W, H)
+        want = np.stack(np.unravel_index(np.arange(N), (D, H, W)), 1)
+        assert np.array_equal(walk, want), (D, H, W)
